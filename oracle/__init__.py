@@ -1,0 +1,17 @@
+"""CPU oracle for the GW-BSE dense FP64 contraction path of VOTCA-XTP.
+
+TEST INFRASTRUCTURE ONLY.  This package is a plain NumPy/SciPy restatement of
+the reference algorithm (votca/votca, xtp/src/libxtp/gwbse/*, threecenter.cc,
+davidsonsolver.cc ...).  It exists to check the CUDA product path
+(`votca_b200`) and to serve as the timed CPU baseline in `bench.py`.
+Only `tests/`, `__graft_entry__.smoke()` and the `cpu_baseline` /
+`--impl reference` legs of `bench.py` may import it; the product never does.
+
+Parity pinning: every module below is checked against the reference's own
+MatrixMarket fixtures (xtp/src/tests/DataFiles/{threecenter_gwbse,rpa,
+sigma_exact,sigma_cda,sigma_ppm,gw,bse,bse_operator}) in
+`tests/test_oracle_golden.py` at the tolerances of the reference's unit tests.
+AO integrals for shells above p are *parity unpinned* (no reference fixture
+pins a d/f/g three-centre integral in the GW layout);
+they are validated by internal identities only.
+"""

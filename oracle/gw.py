@@ -1,0 +1,318 @@
+"""Oracle for GW (test infrastructure).  Follows xtp/src/libxtp/gwbse/gw.cc:35-78,
+210-776, xtp/include/votca/xtp/gw.h:214-300 (QPFunc) and
+xtp/src/libxtp/anderson_mixing.cc:28-95.  QSGW (gw.cc:778-1184) is outside the
+BASELINE.json configs and is not restated.
+"""
+import math
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import qp_solver as qps
+from . import sigma as osigma
+from .rpa import RPA
+
+
+@dataclass
+class GWOptions:
+    homo: int = 0
+    qpmin: int = 0
+    qpmax: int = 0
+    rpamin: int = 0
+    rpamax: int = 0
+    eta: float = 1e-3
+    g_sc_limit: float = 1e-5
+    g_sc_max_iterations: int = 100
+    gw_sc_limit: float = 1e-5
+    gw_sc_max_iterations: int = 50
+    shift: float = 0.0
+    ScaHFX: float = 0.0
+    sigma_integration: str = "ppm"
+    reset_3c: int = 5
+    qp_solver: str = "grid"
+    qp_solver_alpha: float = 0.75
+    qp_grid_steps: int = 0
+    qp_grid_spacing: float = 0.0
+    qp_full_window_half_width: float = -1.0
+    qp_dense_spacing: float = -1.0
+    qp_adaptive_shell_width: float = -1.0
+    qp_adaptive_shell_count: int = 0
+    gw_mixing_order: int = 20
+    gw_mixing_alpha: float = 0.7
+    quadrature_scheme: str = "legendre"
+    order: int = 12
+    alpha: float = 1e-3
+    qp_restrict_search: bool = True
+    qp_zero_margin: float = 1e-6
+    qp_virtual_min_energy: float = -0.1
+    qp_root_finder: str = "bisection"
+    qp_grid_search_mode: str = "adaptive_with_dense_fallback"
+
+
+class Anderson:
+    def __init__(self, order, alpha):
+        self.order = order + 1
+        self.alpha = alpha
+        self.input, self.output = [], []
+
+    def update_output(self, v):
+        if len(self.output) > self.order - 1:
+            self.output.pop(0)
+        self.output.append(np.array(v))
+
+    def update_input(self, v):
+        if len(self.output) > self.order - 1:
+            self.input.pop(0)
+        self.input.append(np.array(v))
+
+    def mix_history(self):
+        iteration = len(self.output)
+        used = iteration - 1
+        out_mixed = self.output[-1].copy()
+        in_mixed = self.input[-1].copy()
+        if iteration > 1 and self.order > 1:
+            dn = out_mixed - in_mixed
+            A = np.zeros((used, used))
+            c = np.zeros(used)
+            for m in range(1, iteration):
+                dm = dn - self.output[used - m] + self.input[used - m]
+                c[m - 1] = dm @ dn
+                for j in range(1, iteration):
+                    A[m - 1, j - 1] = dm @ (dn - self.output[used - j] + self.input[used - j])
+            # fullPivHouseholderQr().solve: rank-revealing least squares
+            coef = np.linalg.lstsq(A, c, rcond=None)[0]
+            for n in range(1, iteration):
+                out_mixed += coef[n - 1] * (self.output[used - n] - self.output[used])
+                in_mixed += coef[n - 1] * (self.input[used - n] - self.input[used])
+        return self.alpha * out_mixed + (1 - self.alpha) * in_mixed
+
+
+class QPFunc:
+    """f(w) = Sigma_c(w) + offset - w  (gw.h:214-249)."""
+
+    def __init__(self, level, sigma, offset):
+        self.level, self.sigma_c, self.offset = level, sigma, offset
+        self.n_sigma = 0
+        self.n_deriv = 0
+
+    def sigma(self, w):
+        self.n_sigma += 1
+        return self.sigma_c.calc_correlation_diag_element(self.level, w)
+
+    def value(self, w):
+        return self.sigma(w) + self.offset - w
+
+    def deriv(self, w):
+        self.n_deriv += 1
+        return self.sigma_c.calc_correlation_diag_element_derivative(self.level, w) - 1.0
+
+
+class GW:
+    def __init__(self, Mmn, vxc, dft_energies):
+        self.Mmn = Mmn
+        self.vxc = np.asarray(vxc)
+        self.dft_energies = np.asarray(dft_energies, dtype=np.float64)
+        self.rpa = RPA(Mmn)
+
+    # gw.cc:35-58
+    def configure(self, opt):
+        self.opt = opt
+        qps.normalize_grid_search_options(opt)
+        self.qptotal = opt.qpmax - opt.qpmin + 1
+        self.rpa.configure(opt.homo, opt.rpamin, opt.rpamax)
+        self.sigma = osigma.create(opt.sigma_integration, self.Mmn, self.rpa)
+        self.sigma.configure(osigma.SigmaOptions(
+            homo=opt.homo, qpmin=opt.qpmin, qpmax=opt.qpmax, rpamin=opt.rpamin, rpamax=opt.rpamax,
+            eta=opt.eta, quadrature_scheme=opt.quadrature_scheme, order=opt.order, alpha=opt.alpha))
+        self.Sigma_x = np.zeros((self.qptotal, self.qptotal))
+        self.Sigma_c = np.zeros((self.qptotal, self.qptotal))
+        self.gw_sc_iteration = 0
+        self.sigma_evals = 0
+
+    def _solver_opt(self):
+        o = self.opt
+        return qps.SolverOptions(
+            g_sc_limit=o.g_sc_limit, qp_bisection_max_iter=o.g_sc_max_iterations,
+            qp_full_window_half_width=o.qp_full_window_half_width, qp_dense_spacing=o.qp_dense_spacing,
+            qp_adaptive_shell_width=o.qp_adaptive_shell_width,
+            qp_adaptive_shell_count=o.qp_adaptive_shell_count)
+
+    def get_hqp(self):
+        o = self.opt
+        return (self.Sigma_x + self.Sigma_c - self.vxc
+                + np.diag(self.dft_energies[o.qpmin:o.qpmin + self.qptotal]))
+
+    def get_gwa_results(self):
+        o = self.opt
+        return (np.diag(self.Sigma_x) + np.diag(self.Sigma_c) - np.diag(self.vxc)
+                + self.dft_energies[o.qpmin:o.qpmin + self.qptotal])
+
+    def rpa_input_energies(self):
+        return self.rpa.get_rpa_input_energies()
+
+    def calc_homo_lumo_shift(self, freqs):
+        o = self.opt
+        dftgap = self.dft_energies[o.homo + 1] - self.dft_energies[o.homo]
+        qpgap = freqs[o.homo + 1 - o.qpmin] - freqs[o.homo - o.qpmin]
+        return qpgap - dftgap
+
+    # gw.cc:218-310
+    def calculate_gw_perturbation(self):
+        o = self.opt
+        self.Sigma_x = (1 - o.ScaHFX) * self.sigma.calc_exchange_matrix()
+        shifted = self.dft_energies.copy()
+        shifted[o.homo + 1:] += o.shift
+        self.rpa.set_rpa_input_energies(shifted[o.rpamin:o.rpamax + 1])
+        freqs = shifted[o.qpmin:o.qpmin + self.qptotal].copy()
+        mixing = Anderson(o.gw_mixing_order, o.gw_mixing_alpha)
+        self.iterations = 0
+        for i_gw in range(o.gw_sc_max_iterations):
+            self.gw_sc_iteration = i_gw
+            self.iterations = i_gw + 1
+            if i_gw % o.reset_3c == 0 and i_gw != 0:
+                self.Mmn.rebuild()
+            self.sigma.prepare_screening()
+            if o.gw_mixing_order > 0 and i_gw > 0:
+                mixing.update_input(freqs)
+            freqs = self.solve_qp(freqs)
+            if o.gw_sc_max_iterations > 1:
+                old = self.rpa.get_rpa_input_energies().copy()
+                if o.gw_mixing_order > 0 and i_gw > 0:
+                    mixing.update_output(freqs)
+                    mixed = mixing.mix_history()
+                    self.rpa.update_rpa_input_energies(self.dft_energies, mixed, o.qpmin)
+                    freqs = mixed
+                else:
+                    self.rpa.update_rpa_input_energies(self.dft_energies, freqs, o.qpmin)
+                if np.abs(self.rpa.get_rpa_input_energies() - old).max() <= o.gw_sc_limit:
+                    break
+                elif i_gw == o.gw_sc_max_iterations - 1:
+                    break
+        self.Sigma_c[np.diag_indices(self.qptotal)] = self.sigma.calc_correlation_diag(freqs)
+
+    # gw.cc:772-776
+    def calculate_hqp(self):
+        diag = np.diag(self.Sigma_c).copy()
+        self.Sigma_c = self.sigma.calc_correlation_offdiag(self.get_gwa_results())
+        self.Sigma_c[np.diag_indices(self.qptotal)] = diag
+
+    # gw.cc:323-410
+    def solve_qp(self, freqs):
+        o = self.opt
+        intercepts = (self.dft_energies[o.qpmin:o.qpmin + self.qptotal] + np.diag(self.Sigma_x)
+                      - np.diag(self.vxc))
+        new = np.array(freqs, dtype=np.float64)
+        self.converged = np.zeros(self.qptotal, dtype=bool)
+        for lvl in range(self.qptotal):
+            f0, icpt = freqs[lvl], intercepts[lvl]
+            newf = None
+            if o.qp_solver == "fixedpoint":
+                newf = self._solve_fixedpoint(icpt, f0, lvl)
+            if newf is not None:
+                new[lvl] = newf
+                self.converged[lvl] = True
+            else:
+                newf = self._solve_grid(icpt, f0, lvl)
+                if newf is not None:
+                    new[lvl] = newf
+                    self.converged[lvl] = True
+                else:
+                    newf = self._solve_linearisation(icpt, f0, lvl)
+                    if newf is not None:
+                        new[lvl] = newf
+        return new
+
+    def _solve_linearisation(self, icpt, f0, lvl):
+        fqp = QPFunc(lvl, self.sigma, icpt)
+        s = fqp.sigma(f0)
+        ds = fqp.deriv(f0)  # dSigma/dw - 1
+        # gw.cc:420-425: Z = 1 - dsigma_domega where fqp.deriv already subtracts 1
+        Z = 1.0 - ds
+        self.sigma_evals += fqp.n_sigma
+        if abs(Z) > 1e-9:
+            return f0 + (icpt - f0 + s) / Z
+        return None
+
+    def _solve_fixedpoint(self, icpt, f0, lvl):
+        o = self.opt
+        f = QPFunc(lvl, self.sigma, icpt)
+        x, ok = qps.newton_raphson(f, f0, o.g_sc_max_iterations, o.g_sc_limit, o.qp_solver_alpha)
+        self.sigma_evals += f.n_sigma
+        return x if ok else None
+
+    # gw.cc:433-502
+    def _windowed_adaptive(self, icpt, f0, lvl, lo, hi, allow_rejected):
+        fqp = QPFunc(lvl, self.sigma, icpt)
+        res, acc, rej, _ = qps.solve_qp_grid_windowed(
+            fqp, f0, lo, hi, self.gw_sc_iteration, self._solver_opt(),
+            use_brent=(self.opt.qp_root_finder == "brent"))
+        self.sigma_evals += fqp.n_sigma
+        if acc:
+            return res
+        if rej and not allow_rejected:
+            return None
+        return res
+
+    # gw.cc:504-616
+    def _windowed_dense(self, icpt, f0, lvl, lo, hi, allow_rejected):
+        o = self.opt
+        fqp = QPFunc(lvl, self.sigma, icpt)
+        sopt = self._solver_opt()
+        use_brent = o.qp_root_finder == "brent"
+        acc, rej = [], []
+        if lo < hi:
+            fprev = lo
+            tprev = fqp.value(fprev)
+            n_steps = max(2, int(math.ceil((hi - lo) / o.qp_dense_spacing)) + 1)
+            for i in range(1, n_steps):
+                freq = hi if i == n_steps - 1 else min(hi, lo + float(i) * o.qp_dense_spacing)
+                targ = fqp.value(freq)
+                if tprev * targ < 0.0:
+                    cand = qps.refine_qp_interval(fprev, tprev, freq, targ, fqp, f0, sopt, use_brent)
+                    if cand is not None:
+                        (acc if cand.accepted else rej).append(cand)
+                fprev, tprev = freq, targ
+        self.sigma_evals += fqp.n_sigma
+        if acc:
+            return qps._argmax_first(acc).omega
+        if rej:
+            if not allow_rejected:
+                return None
+            return qps._argmax_first(rej).omega
+        return None
+
+    # gw.cc:618-675
+    def _windowed(self, icpt, f0, lvl, lo, hi, allow_rejected):
+        mode = self.opt.qp_grid_search_mode
+        if mode == "adaptive":
+            return self._windowed_adaptive(icpt, f0, lvl, lo, hi, allow_rejected)
+        if mode == "dense":
+            return self._windowed_dense(icpt, f0, lvl, lo, hi, allow_rejected)
+        if mode == "adaptive_with_dense_fallback":
+            r = self._windowed_adaptive(icpt, f0, lvl, lo, hi, allow_rejected)
+            if r is not None:
+                return r
+            return self._windowed_dense(icpt, f0, lvl, lo, hi, allow_rejected)
+        raise RuntimeError("Unknown gw.qp_grid_search_mode '" + mode + "'")
+
+    # gw.cc:677-739
+    def _solve_grid(self, icpt, f0, lvl):
+        o = self.opt
+        rng = o.qp_full_window_half_width
+        full_lo, full_hi = f0 - rng, f0 + rng
+        r_lo, r_hi = full_lo, full_hi
+        use_restricted = False
+        if o.qp_restrict_search:
+            mo_level = lvl + o.qpmin
+            if mo_level <= o.homo:
+                r_hi = min(full_hi, -o.qp_zero_margin)
+            else:
+                r_lo = max(full_lo, o.qp_virtual_min_energy)
+            tol = 1e-12
+            use_restricted = abs(r_lo - full_lo) > tol or abs(r_hi - full_hi) > tol
+        if use_restricted and r_lo < r_hi:
+            r = self._windowed(icpt, f0, lvl, r_lo, r_hi, False)
+            if r is not None:
+                return r
+            return self._windowed_dense(icpt, f0, lvl, full_lo, full_hi, True)
+        return self._windowed(icpt, f0, lvl, full_lo, full_hi, True)

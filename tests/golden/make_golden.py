@@ -1,0 +1,70 @@
+#!/usr/bin/env python
+"""Builds tests/golden/votca_fixtures.npz from the reference's own unit-test data.
+
+Run in the build container only (needs /root/reference):
+    python tests/golden/make_golden.py
+Sources: xtp/src/tests/DataFiles/{threecenter_gwbse,rpa,sigma_exact,sigma_cda,
+sigma_ppm,gw,bse,bse_operator}/*.mm (MatrixMarket, 6 significant digits),
+molecule.xyz and 3-21G.xml (identical in all of these directories), and the
+inline vectors of test_sigma_*.cc, test_gw.cc, test_bse_operator.cc,
+test_rpa_h2p.cc.  The npz is what the GPU box sees; /root/reference does not
+exist there.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+from oracle import basis as obasis  # noqa: E402
+from oracle import mmio  # noqa: E402
+
+REF = "/root/reference/xtp/src/tests/DataFiles"
+DIRS = ["threecenter_gwbse", "rpa", "sigma_exact", "sigma_cda", "sigma_ppm", "gw", "bse", "bse_operator"]
+
+
+def main():
+    out = {}
+    for d in DIRS:
+        for fn in sorted(os.listdir(os.path.join(REF, d))):
+            if fn.endswith(".mm"):
+                out[f"{d}/{fn[:-3]}"] = mmio.read_matrix(os.path.join(REF, d, fn))
+    elems, pos = obasis.read_xyz(os.path.join(REF, "rpa", "molecule.xyz"))
+    out["molecule/elements"] = np.array(elems)
+    out["molecule/positions_bohr"] = pos
+    bs = obasis.load_basisset(os.path.join(REF, "rpa", "3-21G.xml"))
+    out["basis/3-21G.json"] = np.array(json.dumps(bs))
+    # inline vectors of the reference unit tests
+    out["inline/sigma_exact_mo_energy"] = np.array(  # test_sigma_exact.cc:54-57, test_sigma_cda.cc:53-56
+        [0.0468207, 0.0907801, 0.0907801, 0.104563, 0.592491, 0.663355, 0.663355, 0.768373, 1.69292,
+         1.97724, 1.97724, 2.50877, 2.98732, 3.4418, 3.4418, 4.81084, 17.1838])
+    out["inline/sigma_ppm_mo_energy"] = np.array(  # test_sigma_ppm.cc:57-60, test_bse_operator.cc:55-57
+        [-0.612601, -0.341755, -0.341755, -0.341755, 0.137304, 0.16678, 0.16678, 0.16678, 0.671592,
+         0.671592, 0.671592, 0.974255, 1.01205, 1.01205, 1.01205, 1.64823, 19.4429])
+    out["inline/gw_mo_eigenvalues"] = np.array(  # test_gw.cc:46-49
+        [-10.6784, -0.746424, -0.394948, -0.394948, -0.394948, 0.165212, 0.227713, 0.227713, 0.227713,
+         0.763971, 0.763971, 0.763971, 1.05054, 1.13372, 1.13372, 1.13372, 1.72964])
+    out["inline/bse_operator_epsilon_inv"] = np.array(  # test_bse_operator.cc:68-73
+        [0.999807798016267, 0.994206065211371, 0.917916768047073, 0.902913813951883, 0.902913745974602,
+         0.902913584797742, 0.853352878674581, 0.853352727016914, 0.853352541699637, 0.79703468058566,
+         0.797034577207669, 0.797034400395582, 0.787701833916331, 0.518976361745313, 0.518975064844033,
+         0.518973712898761, 0.459286057710524])
+    out["inline/rpa_update_dft"] = np.array([-0.5, -0.4, -0.3, -0.2, -0.2, -0.1, 0, 0.1, 0.2, 0.3])  # test_rpa.cc:47-57
+    out["inline/rpa_update_gw"] = np.array([-0.15, -0.05, 0.05, 0.15, 0.45, 0.55, 0.65])
+    out["inline/rpa_update_ref"] = np.array([-0.85, -0.15, -0.05, 0.05, 0.15, 0.45, 0.55, 0.65, 0.75, 0.85])
+    out["inline/rpa_h2p_erpa"] = np.array(-0.0587973)  # test_rpa_h2p.cc:86
+    out["inline/rpa_h2p_omega"] = np.array(  # test_rpa_h2p.cc:62-71
+        [0.104192, 0.104192, 0.187814, 0.559693, 0.559693, 0.572575, 0.577988, 0.577989, 0.579088, 0.618403,
+         0.618403, 0.67005, 0.678538, 0.678538, 0.722771, 1.10797, 1.41413, 1.41413, 1.58866, 1.60381,
+         1.60381, 1.64709, 1.87331, 1.87331, 1.88646, 1.8926, 1.89268, 1.89268, 1.933, 1.933, 2.01832,
+         2.40974, 2.42192, 2.42192, 2.46371, 2.85829, 2.8853, 2.8853, 2.90367, 2.90367, 2.92541, 2.94702,
+         3.3382, 3.3382, 3.35102, 3.3566, 3.3566, 3.35835, 3.39617, 3.39617, 4.22882, 4.71607, 4.72233,
+         4.72233, 4.76567, 16.5917, 17.0793, 17.093, 17.093, 17.1377])
+    np.savez_compressed(os.path.join(HERE, "votca_fixtures.npz"), **out)
+    print("wrote", len(out), "arrays")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,185 @@
+"""Pins the CPU oracle against the reference's own golden vectors.
+
+Each test mirrors one Boost test of xtp/src/tests and uses the same tolerance
+(Eigen isApprox = relative Frobenius norm).
+"""
+import numpy as np
+import pytest
+
+from oracle import bse as obse
+from oracle import bse_operator as bop
+from oracle import gw as ogw
+from oracle import rpa as orpa
+from oracle import sigma as osig
+from tests.helpers import methane_mmn, rel_frob
+
+
+# test_threecenter_gwbse.cc:36-126
+def test_threecenter_gwbse(golden, methane):
+    tc = methane_mmn(golden["threecenter_gwbse/MOs"], mmax=5, nmax=7)
+    for i, name in [(0, "ref0b"), (2, "ref2b"), (4, "ref4b")]:
+        assert rel_frob(golden["threecenter_gwbse/" + name], tc[i]) < 1e-5
+    tc.multiply_right(np.eye(methane["basis"].size))
+    for i, name in [(0, "ref0b"), (2, "ref2b"), (4, "ref4b")]:
+        assert rel_frob(golden["threecenter_gwbse/" + name], tc[i]) < 1e-5
+
+
+# test_rpa.cc:41-67
+def test_rpa_calcenergies(golden):
+    r = orpa.RPA(None)
+    r.configure(4, 0, 9)
+    r.update_rpa_input_energies(golden["inline/rpa_update_dft"], golden["inline/rpa_update_gw"], 1)
+    assert rel_frob(golden["inline/rpa_update_ref"], r.get_rpa_input_energies()) < 1e-4
+
+
+# test_rpa.cc:69-140
+def test_rpa_full(golden):
+    tc = methane_mmn(golden["rpa/eigenvectors"])
+    r = orpa.RPA(tc)
+    r.configure(4, 0, 16)
+    r.set_rpa_input_energies(golden["rpa/eigenvals"].ravel())
+    assert rel_frob(golden["rpa/i_ref"], r.calculate_epsilon_i(0.5)) < 1e-4
+    assert rel_frob(golden["rpa/r_ref"], r.calculate_epsilon_r(0.0)) < 1e-4
+    assert rel_frob(golden["rpa/r_complex_ref"], r.calculate_epsilon_r(complex(0.5, 0.5))) < 1e-4
+
+
+# test_rpa_h2p.cc:36-112
+def test_rpa_h2p(golden):
+    tc = methane_mmn(golden["rpa/eigenvectors"])
+    r = orpa.RPA(tc)
+    r.configure(4, 0, 16)
+    r.set_rpa_input_energies(golden["rpa/eigenvals"].ravel())
+    omega, XpY, erpa = r.diagonalize_h2p()
+    assert abs(erpa - float(golden["inline/rpa_h2p_erpa"])) < 1e-6 * abs(erpa) * 100
+    assert rel_frob(golden["inline/rpa_h2p_omega"], omega) < 1e-4
+
+
+@pytest.mark.parametrize("kind,tolx,tolc", [("exact", 1e-5, 1e-5), ("ppm", 1e-5, 1e-5), ("cda", 1e-4, 1e-5)])
+def test_sigma(golden, kind, tolx, tolc):
+    # test_sigma_exact.cc:43-120, test_sigma_ppm.cc:44-122, test_sigma_cda.cc:41-111
+    d = "sigma_" + kind
+    e = golden["inline/sigma_ppm_mo_energy"] if kind == "ppm" else golden["inline/sigma_exact_mo_energy"]
+    tc = methane_mmn(golden[d + "/MOs"])
+    r = orpa.RPA(tc)
+    r.configure(4, 0, 16)
+    r.set_rpa_input_energies(e)
+    s = osig.create(kind, tc, r)
+    s.configure(osig.SigmaOptions(homo=4, qpmin=0, qpmax=16, rpamin=0, rpamax=16, eta=1e-3,
+                                  quadrature_scheme="legendre", order=100, alpha=1e-3))
+    assert rel_frob(golden[d + "/x_ref"], s.calc_exchange_matrix()) < tolx
+    s.prepare_screening()
+    c = s.calc_correlation_offdiag(e)
+    c[np.diag_indices(17)] = s.calc_correlation_diag(e)
+    cref = golden[d + "/c_ref"]
+    assert rel_frob(np.diag(cref), np.diag(c)) < tolc
+    if kind != "cda":  # the reference checks only the diagonal for CDA (off-diagonal returns 0)
+        assert rel_frob(cref, c) < tolc
+
+
+def _gw_options(**kw):
+    o = ogw.GWOptions(homo=4, qpmin=0, qpmax=16, rpamin=0, rpamax=16, gw_sc_max_iterations=1, eta=1e-3,
+                      sigma_integration="ppm", reset_3c=5, qp_solver="grid", gw_mixing_order=0,
+                      gw_mixing_alpha=0.7, g_sc_limit=1e-5, g_sc_max_iterations=50, gw_sc_limit=1e-5)
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+# test_gw.cc:111-270
+@pytest.mark.parametrize("suffix", ["", "2"])
+def test_gw_full(golden, suffix):
+    tc = methane_mmn(golden["gw/mo_eigenvectors" + suffix])
+    g = ogw.GW(tc, golden["gw/vxc" + suffix], golden["inline/gw_mo_eigenvalues"])
+    g.configure(_gw_options(qp_grid_steps=601, qp_grid_spacing=0.005))
+    g.calculate_gw_perturbation()
+    ref = golden["gw/ref" + suffix]
+    assert rel_frob(np.diag(ref), g.get_gwa_results()) < 1e-4
+    g.calculate_hqp()
+    assert rel_frob(ref, g.get_hqp()) < 1e-4
+
+
+# test_gw.cc:272-340
+def test_gw_canonical_and_brent(golden):
+    res = {}
+    for finder in ("bisection", "brent"):
+        tc = methane_mmn(golden["gw/mo_eigenvectors2"])
+        g = ogw.GW(tc, golden["gw/vxc2"], golden["inline/gw_mo_eigenvalues"])
+        g.configure(_gw_options(qp_full_window_half_width=1.5, qp_dense_spacing=0.005,
+                                qp_adaptive_shell_width=0.02, qp_root_finder=finder))
+        g.calculate_gw_perturbation()
+        res[finder] = g.get_gwa_results()
+    assert rel_frob(np.diag(golden["gw/ref2"]), res["bisection"]) < 1e-4
+    assert rel_frob(res["bisection"], res["brent"]) < 1e-5
+
+
+# test_bse_operator.cc:37-151
+def test_bse_operator(golden):
+    tc = methane_mmn(golden["bse_operator/MOs"])
+    tc.multiply_right(golden["bse_operator/rpa_op"])
+    eps = golden["inline/bse_operator_epsilon_inv"]
+    opt = bop.BSEOperatorOptions(cmax=8, homo=4, qpmin=0, rpamin=0, vmin=0)
+    for name, mk in [("hqp", bop.hqp_op), ("hx", bop.hx_op), ("hd", bop.hd_op), ("hd2", bop.hd2_op)]:
+        op = mk(eps, tc, golden["bse_operator/Hqp"])
+        op.configure(opt)
+        dense = op.dense()
+        assert rel_frob(golden["bse_operator/%s_ref" % name], dense) < 1e-3
+        assert np.abs(np.diag(dense) - op.diagonal()).max() < 1e-12
+        # the factorised formulation (what the GPU path computes) is the same operator
+        assert np.abs(op.matmul_factorised(np.eye(op.size)) - dense).max() < 1e-12
+
+
+def _bse_options(**kw):
+    o = obse.BSEOptions(cmax=16, rpamax=16, rpamin=0, vmin=0, nmax=3, useTDA=True, homo=4, qpmin=0, qpmax=16,
+                        max_dyn_iter=10, dyn_tolerance=1e-5, davidson_correction="DPR",
+                        davidson_tolerance="lapack", davidson_update="safe", davidson_maxiter=50)
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+def _subspace(ref, vec):
+    return np.linalg.norm(ref.T @ vec, axis=0)
+
+
+# test_bse.cc:37-377
+@pytest.mark.parametrize("factorised", [False, True])
+def test_bse(golden, factorised):
+    Hqp = golden["bse/Hqp"]
+    rpa_e = np.diag(Hqp).copy()
+    tc = methane_mmn(golden["bse/MOs"])
+    b = obse.BSE(tc, factorised=factorised)
+    nrm = lambda a: a / np.linalg.norm(a, axis=0)  # noqa: E731
+
+    b.configure(_bse_options(use_Hqp_offdiag=False), rpa_e, Hqp)
+    es = b.solve_singlets()
+    assert rel_frob(golden["bse/singlets_nooffdiag_tda"].ravel(), es["eigenvalues"]) < 1e-3
+    assert np.allclose(_subspace(golden["bse/singlets_psi_nooffdiag_tda"], es["eigenvectors"]), 1, atol=1e-5)
+
+    b.configure(_bse_options(), rpa_e, Hqp)
+    assert rel_frob(Hqp, b.Hqp) < 1e-3
+    es = b.solve_singlets()
+    assert rel_frob(golden["bse/singlets_tda"].ravel(), es["eigenvalues"]) < 1e-3
+    assert np.allclose(_subspace(golden["bse/singlets_psi_tda"], es["eigenvectors"]), 1, atol=1e-5)
+    dyn = b.perturbative_dynamical_screening(es, rpa_e)
+    assert rel_frob(golden["bse/singlets_dynamic_TDA"].ravel(), dyn) < 5e-3
+
+    b.configure(_bse_options(useTDA=False), rpa_e, Hqp)
+    es = b.solve_singlets()
+    assert rel_frob(golden["bse/singlets_btda"].ravel(), es["eigenvalues"]) < 1e-3
+    assert np.allclose(_subspace(nrm(golden["bse/singlets_psi_btda"]), nrm(es["eigenvectors"])), 1, atol=1e-5)
+    assert np.allclose(_subspace(nrm(golden["bse/singlets_psi_AR_btda"]), nrm(es["eigenvectors2"])), 1,
+                       atol=1e-5)
+    dyn = b.perturbative_dynamical_screening(es, rpa_e)
+    assert rel_frob(golden["bse/singlets_dynamic_full"].ravel(), dyn) < 5e-2
+
+    b.configure(_bse_options(nmax=1), rpa_e, Hqp)
+    es = b.solve_triplets()
+    assert rel_frob(golden["bse/triplets_tda"].ravel(), es["eigenvalues"]) < 1e-3
+    dyn = b.perturbative_dynamical_screening(es, rpa_e)
+    assert rel_frob(golden["bse/triplets_dynamic_TDA"].ravel(), dyn) < 1e-3
+
+    b.configure(_bse_options(nmax=1, cmax=15, vmin=1), rpa_e, Hqp)
+    assert rel_frob(golden["bse/Hqp_cut"], b.Hqp) < 1e-3
+    b2 = obse.BSE(tc)
+    b2.configure(_bse_options(nmax=1, qpmin=1, qpmax=15), rpa_e, golden["bse/Hqp_cut"])
+    assert rel_frob(golden["bse/Hqp_extended"], b2.Hqp) < 1e-3
