@@ -1,0 +1,209 @@
+/* gwbse_b200.h - C ABI of libgwbse_b200.so
+ *
+ * B200-native (sm_100a) implementation of the dense FP64 contraction path
+ * behind VOTCA-XTP's `xtp_tools -e dftgwbse`.  This is the boundary a
+ * maintainer binds to from the reference's C++ classes; every entry point
+ * names the reference interface it replaces (paths relative to the votca
+ * repository root).  INTEGRATION.md shows the reference-side shim.
+ *
+ * Conventions
+ *  - every function returns 0 on success, non-zero on failure;
+ *    gwbse_last_error(ctx) returns the message (the C++ shim rethrows it as
+ *    std::runtime_error, the reference's only error convention,
+ *    xtp/src/libxtp/cudamatrix.cc:25-37).
+ *  - pointers are HOST pointers unless the parameter name ends in `_dev`.
+ *  - host matrices are column-major with explicit leading dimension (Eigen
+ *    MatrixXd layout).
+ *  - one context per process/GPU; calls on one context are serialised by the
+ *    caller (the reference's OpenMP_CUDA has the same rule,
+ *    xtp/include/votca/xtp/openmp_cuda.h:49-65).
+ *  - there is no CPU fallback: without a CUDA device gwbse_ctx_create fails.
+ *
+ * Device layout of Mmn ("aux-major"):  element (m, n, chi) of the reference's
+ * matrix_[m](n, chi) (xtp/include/votca/xtp/threecenter.h:125-134) lives at
+ *     X[chi * ldx + mloc * npad + n],  ldx = mlocal * npad,
+ * i.e. one (mlocal*npad) x naux column-major matrix.  mloc is the index of m
+ * among the levels owned by this rank (m-cyclic sharding: owner = m % world).
+ */
+#ifndef GWBSE_B200_H
+#define GWBSE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+typedef struct gwbse_ctx gwbse_ctx;
+
+/* ---- context ----------------------------------------------------------- */
+/* replaces OpenMP_CUDA::OpenMP_CUDA / CudaPipeline ctor (openmp_cuda.cc:48-71,
+ * cudapipeline.h:89-104): binds one GPU, creates stream + solver handles.   */
+int gwbse_ctx_create(int device, gwbse_ctx** out);
+void gwbse_ctx_destroy(gwbse_ctx* ctx);
+const char* gwbse_last_error(const gwbse_ctx* ctx);
+const char* gwbse_create_error(void); /* message of a failed gwbse_ctx_create */
+int gwbse_sync(gwbse_ctx* ctx);
+/* number of kernels of this library launched so far on ctx (bench.py gpu_launches) */
+long long gwbse_launch_count(const gwbse_ctx* ctx);
+int gwbse_device_count(void); /* OpenMP_CUDA::AvailableGPUs, openmp_cuda.cc:30-46 */
+/* tuning knobs: "bse_chunk_bytes" (size of the Hd/Hd2 intermediate held at once) */
+int gwbse_set_option(gwbse_ctx* ctx, const char* key, double value);
+/* CUDA-event timers on the context's stream (bench.py times kernels with these) */
+int gwbse_timer_start(gwbse_ctx* ctx);
+int gwbse_timer_stop_ms(gwbse_ctx* ctx, float* ms);
+
+/* ---- multi-GPU (one process per GPU, NCCL over NVLink) ------------------ */
+/* m-cyclic sharding of Mmn; replaces the thread-per-GPU loop + host reduction
+ * of OpenMP_CUDA::getReductionVar (openmp_cuda.cc:480-493).                 */
+int gwbse_nccl_unique_id(unsigned char* id128);
+int gwbse_comm_init(gwbse_ctx* ctx, int rank, int world, const unsigned char* id128);
+int gwbse_comm_rank(const gwbse_ctx* ctx);
+int gwbse_comm_world(const gwbse_ctx* ctx);
+int gwbse_comm_allreduce_host(gwbse_ctx* ctx, double* buf, size_t n); /* sum, in place */
+
+/* ---- raw device memory (CudaMatrix, cudamatrix.h:95-190) ---------------- */
+int gwbse_dev_malloc(gwbse_ctx* ctx, size_t bytes, double** out_dev);
+int gwbse_dev_free(gwbse_ctx* ctx, double* p_dev);
+int gwbse_h2d(gwbse_ctx* ctx, double* dst_dev, const double* src, size_t n);
+int gwbse_d2h(gwbse_ctx* ctx, double* dst, const double* src_dev, size_t n);
+int gwbse_d2d(gwbse_ctx* ctx, double* dst_dev, const double* src_dev, size_t n);
+int gwbse_dev_memset_zero(gwbse_ctx* ctx, double* dst_dev, size_t n);
+int gwbse_dev_mem_info(gwbse_ctx* ctx, size_t* free_bytes, size_t* total_bytes);
+
+/* ---- dense primitives on device matrices -------------------------------- */
+/* CudaPipeline::gemm (cudapipeline.h:106-131): C = alpha op(A) op(B) + beta C,
+ * column-major, transa/transb in {'N','T'}; hand-written DMMA kernel.       */
+int gwbse_dgemm_dev(gwbse_ctx* ctx, char transa, char transb, int m, int n, int k, double alpha,
+                    const double* A_dev, int lda, const double* B_dev, int ldb, double beta, double* C_dev,
+                    int ldc);
+/* same with tile-shape / split-K override (tests, tuning): cfg 0=128x128, 1=128x32, 2=64x64, -1 auto */
+int gwbse_dgemm_dev_ex(gwbse_ctx* ctx, char transa, char transb, int m, int n, int k, double alpha,
+                       const double* A_dev, int lda, const double* B_dev, int ldb, double beta, double* C_dev,
+                       int ldc, int cfg, int splitk);
+/* CudaPipeline::diag_gemm (cudapipeline.h:133-162): C = A diag(d) (side 'R') or diag(d) A (side 'L') */
+int gwbse_diag_scale_dev(gwbse_ctx* ctx, char side, int m, int n, const double* A_dev, int lda,
+                         const double* d_dev, double* C_dev, int ldc);
+/* CudaPipeline::axpy (cudapipeline.cc:36-51): Y += alpha X over an m x n block */
+int gwbse_axpy_dev(gwbse_ctx* ctx, int m, int n, double alpha, const double* X_dev, int ldx, double* Y_dev,
+                   int ldy);
+/* column 2-norms of an m x n device matrix -> host (DavidsonSolver residual norms) */
+int gwbse_colnorms_dev(gwbse_ctx* ctx, int m, int n, const double* A_dev, int lda, double* norms);
+/* A(:,j) *= s[j]  (s on host) */
+int gwbse_scale_cols_dev(gwbse_ctx* ctx, int m, int n, double* A_dev, int lda, const double* s);
+/* column-wise dot products d[j] = X(:,j) . Y(:,j) -> host (BSE::ExpectationValue, bse.cc:489-498) */
+int gwbse_coldots_dev(gwbse_ctx* ctx, int m, int n, const double* X_dev, int ldx, const double* Y_dev, int ldy,
+                      double* dots);
+
+/* symmetric eigen-decomposition, A (n x n, device, lower used) -> eigenvectors in place, w on host.
+ * Eigen::SelfAdjointEigenSolver call sites: ppm.cc:37, bse.cc:194, aomatrix.cc:56,73, rpa.cc:328-345.
+ * Non-contraction auxiliary: cuSOLVER Dsyevd.                                */
+int gwbse_sym_eig_dev(gwbse_ctx* ctx, int n, double* A_dev, int lda, double* w);
+/* general inverse (MatrixXd::inverse(): ppm.cc:44, sigma_cda.cc:43, ImaginaryAxisIntegration.cc:97):
+ * LU with partial pivoting, result overwrites A.  cuSOLVER getrf/getrs.     */
+int gwbse_inverse_dev(gwbse_ctx* ctx, int n, double* A_dev, int lda);
+/* solve A x = b for nrhs right-hand sides (partialPivLu().solve, sigma_cda.cc:57-60); A destroyed */
+int gwbse_lu_solve_dev(gwbse_ctx* ctx, int n, int nrhs, double* A_dev, int lda, double* B_dev, int ldb);
+/* real non-symmetric generalized problem T x = lambda B x (Eigen::GeneralizedEigenSolver,
+ * davidsonsolver.cc:252): small, host in/out.  wr/wi eigenvalues, VR right eigenvectors as LAPACK dgeev. */
+int gwbse_gen_eig_host(gwbse_ctx* ctx, int n, const double* T, const double* B, double* wr, double* wi,
+                       double* VR);
+
+/* ---- Mmn: TCMatrix_gwbse (threecenter.h:41-142) ------------------------- */
+/* TCMatrix_gwbse::Initialize (threecenter.cc:29-48) */
+int gwbse_mmn_alloc(gwbse_ctx* ctx, int naux, int mmin, int mmax, int nmin, int nmax);
+int gwbse_mmn_free(gwbse_ctx* ctx);
+/* geometry queries (auxsize/msize/nsize + device layout) */
+int gwbse_mmn_dims(const gwbse_ctx* ctx, int* naux, int* mtotal, int* ntotal, int* mlocal, int* npad);
+/* TCMatrix_gwbse::Fill3cMO for a block of auxiliary functions
+ * (libint2_calls.cc:595-651 + OpenMP_CUDA::MultiplyLeftRight, openmp_cuda.cc:172-192).
+ * ao3c: aux_count symmetric N x N matrices (column-major, contiguous) = the
+ * output of ComputeAO3cBlock (libint2_calls.cc:544-593); mos: N x nmo
+ * coefficient matrix (MOs().eigenvectors()).  Contracts
+ * M[m](n, aux_offset+k) = sum_{mu,nu} C(mu,nmin+n) ao3c[k](mu,nu) C(nu,mmin+m). */
+int gwbse_mmn_set_mos(gwbse_ctx* ctx, const double* mos, int ldmos, int nbasis, int nmo);
+int gwbse_mmn_fill_block(gwbse_ctx* ctx, int aux_offset, int aux_count, const double* ao3c);
+int gwbse_mmn_fill_block_dev(gwbse_ctx* ctx, int aux_offset, int aux_count, const double* ao3c_dev);
+/* TCMatrix_gwbse::MultiplyRightWithAuxMatrix (threecenter.cc:54-65,
+ * OpenMP_CUDA::MultiplyRight openmp_cuda.cc:131-150): M[m] <- M[m] * R      */
+int gwbse_mmn_mul_right(gwbse_ctx* ctx, const double* R, int ldr);
+int gwbse_mmn_mul_right_dev(gwbse_ctx* ctx, const double* R_dev, int ldr);
+/* AOCoulomb::Pseudo_InvSqrt_GWBSE (aomatrix.cc:53-86) on the device; S, V: naux x naux host */
+int gwbse_pseudo_invsqrt(gwbse_ctx* ctx, int naux, const double* S, const double* V, double etol, double* L_out,
+                         int* removed);
+/* operator[] (threecenter.h:125-134): copy slice M[m] (ntotal x naux, col-major, ld) to/from host.
+ * m is the global storage index (m_abs - mmin); must be owned by this rank. */
+int gwbse_mmn_get_slice(gwbse_ctx* ctx, int m, double* out, int ld);
+int gwbse_mmn_set_slice(gwbse_ctx* ctx, int m, const double* in, int ld);
+/* TCMatrix_gwbse::Rebuild support (gw.cc:242-246): keep / restore a pristine copy on the device */
+int gwbse_mmn_snapshot(gwbse_ctx* ctx);
+int gwbse_mmn_restore(gwbse_ctx* ctx);
+
+/* ---- RPA (rpa.h:35-115) -------------------------------------------------- */
+/* RPA::calculate_epsilon_i / _r(double) / _r(complex) (rpa.cc:75-202 +
+ * OpenMP_CUDA::A_TDA openmp_cuda.cc:218-256): kind 0 = imaginary axis,
+ * 1 = real axis, 2 = complex.  energies: RPA input energies (rpatotal).
+ * Result (naux x naux) stays on the device (gwbse_rpa_epsilon_ptr) and is
+ * copied to eps_out if non-NULL.  Multi-GPU: partials are all-reduced.     */
+int gwbse_rpa_epsilon(gwbse_ctx* ctx, int kind, double freq_re, double freq_im, double eta,
+                      const double* energies, int homo, int rpamin, int rpamax, double* eps_out, int ld);
+double* gwbse_rpa_epsilon_ptr(gwbse_ctx* ctx);
+/* RPA::Calculate_H2p_ApB (rpa.cc:281-326): (A+B) two-particle matrix, S x S, lower triangle */
+int gwbse_rpa_h2p_apb(gwbse_ctx* ctx, const double* energies, int homo, int rpamin, int rpamax,
+                      double* apb_out_dev, int ld);
+
+/* ---- Sigma (sigma_base.h:33-106) ---------------------------------------- */
+/* Sigma_base::CalcExchangeMatrix (sigma_base.cc:36-52): q x q, host out */
+int gwbse_sigma_x(gwbse_ctx* ctx, int homo, int rpamin, int qpmin, int qpmax, double* out, int ld);
+/* Sigma_PPM::CalcCorrelationDiagElement / ...Derivative (sigma_ppm.cc:37-91), batched over
+ * nreq (level, frequency) requests.  weights/freqs: PPM parameters (naux), energies: RPA input.
+ * dsigma may be NULL.  lumo_abs = homo + 1 exactly as the reference uses it. */
+int gwbse_sigma_ppm_set(gwbse_ctx* ctx, const double* ppm_weight, const double* ppm_freq, const double* energies,
+                        int homo, int rpamin, int qpmin, double eta);
+int gwbse_sigma_ppm_eval(gwbse_ctx* ctx, int nreq, const int* levels, const double* freqs, double* sigma,
+                         double* dsigma);
+/* Sigma_PPM::CalcCorrelationOffDiagElement for all pairs (sigma_ppm.cc:93-126 via
+ * Sigma_base::CalcCorrelationOffDiag sigma_base.cc:65-78): q x q symmetric, zero diagonal */
+int gwbse_sigma_ppm_offdiag(gwbse_ctx* ctx, int q, const double* freqs, double* out, int ld);
+/* Sigma_Exact (sigma_exact.cc:29-148): residues from XpY (S x S device), then batched evaluation */
+int gwbse_sigma_exact_prepare(gwbse_ctx* ctx, const double* rpa_omegas, const double* XpY_dev, int ldxpy,
+                              const double* energies, int homo, int rpamin, int rpamax, int qpmin, int qpmax,
+                              double eta);
+int gwbse_sigma_exact_eval(gwbse_ctx* ctx, int nreq, const int* levels, const double* freqs, double* sigma,
+                           double* dsigma);
+int gwbse_sigma_exact_offdiag(gwbse_ctx* ctx, int q, const double* freqs, double* out, int ld);
+
+/* ---- BSE operator (bse_operator.h:32-87) --------------------------------- */
+/* BSE_OPERATOR::configure + ctor data (bse_operator.cc:29-38): eps_inv (naux), Hqp ((vt+ct)^2, ld) */
+int gwbse_bse_configure(gwbse_ctx* ctx, int homo, int rpamin, int vmin, int cmax, const double* eps_inv,
+                        const double* Hqp, int ldh);
+/* BSE_OPERATOR<cqp,cx,cd,cd2>::matmul (bse_operator.cc:40-119): Y = H X, X,Y: bse_size x k */
+int gwbse_bse_matmul(gwbse_ctx* ctx, int cqp, int cx, int cd, int cd2, int k, const double* X, int ldx, double* Y,
+                     int ldy);
+int gwbse_bse_matmul_dev(gwbse_ctx* ctx, int cqp, int cx, int cd, int cd2, int k, const double* X_dev, int ldx,
+                         double* Y_dev, int ldy);
+/* BSE_OPERATOR::diagonal (bse_operator.cc:134-175) */
+int gwbse_bse_diagonal(gwbse_ctx* ctx, int cqp, int cx, int cd, int cd2, double* diag);
+
+/* ---- Davidson helpers (davidsonsolver.cc) -------------------------------- */
+/* DavidsonSolver::gramschmidt (davidsonsolver.cc:442-478) on a device matrix Q (rows x ncols):
+ * orthonormalises columns [nstart, ncols) against the earlier ones, twice.  */
+int gwbse_gramschmidt_dev(gwbse_ctx* ctx, int rows, int ncols, int nstart, double* Q_dev, int ldq);
+/* DavidsonSolver::computeCorrectionVector, DPR / Olsen (davidsonsolver.cc:392-440):
+ * W(:,j) = normalised correction for residual R(:,j), Ritz vector Q(:,j), value lambda[j].
+ * olsen = 0 -> DPR.  diag_dev: operator diagonal (rows).                    */
+int gwbse_davidson_correction_dev(gwbse_ctx* ctx, int rows, int ncols, int olsen, const double* diag_dev,
+                                  const double* lambda, const double* R_dev, int ldr, const double* Q_dev,
+                                  int ldq, double* W_dev, int ldw);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* GWBSE_B200_H */

@@ -1,0 +1,342 @@
+"""GPU parity tests of the C ABI kernels against the CPU oracle (run with -m gpu on the B200).
+
+FP64 contractions are compared at 1e-11 relative Frobenius error (BASELINE.json asks 1e-10 for Mmn);
+the only difference to the oracle is summation order.
+"""
+import numpy as np
+import pytest
+
+from oracle import bse_operator as bop
+from oracle import rpa as orpa
+from oracle import sigma as osig
+from oracle import threecenter
+from oracle.davidson import DavidsonSolver
+from tests.helpers import methane_mmn, rel_frob
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-11
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from votca_b200.api import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def random_tc(rng, naux=70, mtotal=30, ntotal=45):
+    tc = threecenter.TCMatrix(naux, 0, mtotal - 1, 0, ntotal - 1)
+    tc.M = rng.standard_normal((mtotal, ntotal, naux)) / np.sqrt(naux)
+    return tc
+
+
+def push(ctx, tc):
+    ctx.mmn_alloc(tc.naux, tc.mmin, tc.mmax, tc.nmin, tc.nmax)
+    ctx.mmn_set_all(tc.M)
+
+
+# ------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("cfg", [-1, 0, 1, 2])
+@pytest.mark.parametrize("ta,tb", [("N", "N"), ("T", "N"), ("N", "T"), ("T", "T")])
+def test_dgemm_transposes(ctx, cfg, ta, tb):
+    rng = np.random.default_rng(1)
+    for (m, n, k) in [(1, 1, 1), (7, 5, 3), (130, 67, 41), (257, 129, 100), (64, 300, 17), (33, 20, 515)]:
+        A = rng.standard_normal((k, m) if ta == "T" else (m, k))
+        B = rng.standard_normal((n, k) if tb == "T" else (k, n))
+        C0 = rng.standard_normal((m, n))
+        ref = 0.7 * (A.T if ta == "T" else A) @ (B.T if tb == "T" else B) - 0.3 * C0
+        out = ctx.gemm_host(ta, tb, 0.7, A, B, -0.3, C0, cfg=cfg)
+        assert rel_frob(ref, out) < TOL, (m, n, k)
+
+
+@pytest.mark.parametrize("splitk", [1, 2, 5])
+def test_dgemm_splitk_and_beta(ctx, splitk):
+    rng = np.random.default_rng(2)
+    A = rng.standard_normal((150, 900))
+    B = rng.standard_normal((900, 140))
+    C0 = rng.standard_normal((150, 140))
+    for cfg in (0, 1, 2):
+        out = ctx.gemm_host("N", "N", 1.0, A, B, 1.0, C0, cfg=cfg, splitk=splitk)
+        assert rel_frob(A @ B + C0, out) < TOL
+
+
+def test_dgemm_empty_k(ctx):
+    C0 = np.arange(12.0).reshape(3, 4)
+    out = ctx.gemm_host("N", "N", 1.0, np.zeros((3, 0)), np.zeros((0, 4)), 0.0, C0)
+    assert np.all(out == 0.0)
+
+
+def test_dgemm_shape_error(ctx):
+    from votca_b200.api import GwbseError
+    d = ctx.malloc(16)
+    with pytest.raises(GwbseError, match="Shape mismatch"):
+        ctx.dgemm("N", "N", 4, 4, 4, 1.0, d, 2, d, 4, 0.0, d, 4)
+    ctx.free(d)
+
+
+# ------------------------------------------------------------------ dense auxiliaries
+def test_dense_aux(ctx):
+    rng = np.random.default_rng(3)
+    A = rng.standard_normal((37, 37))
+    S = A @ A.T + 37 * np.eye(37)
+    w, V = ctx.sym_eig(S)
+    assert np.allclose(w, np.linalg.eigvalsh(S), rtol=1e-12)
+    assert rel_frob(S, (V * w) @ V.T) < 1e-12
+    assert rel_frob(np.linalg.inv(A), ctx.inverse(A)) < 1e-9
+    b = rng.standard_normal((37, 3))
+    assert rel_frob(np.linalg.solve(A, b), ctx.lu_solve(A, b)) < 1e-9
+    T = rng.standard_normal((12, 12))
+    Bm = rng.standard_normal((12, 12)) + 5 * np.eye(12)
+    wr, wi, VR = ctx.gen_eig(T, Bm)
+    import scipy.linalg
+    wref = scipy.linalg.eigvals(T, Bm)
+    assert np.allclose(np.sort_complex(wr + 1j * wi), np.sort_complex(wref), rtol=1e-9, atol=1e-10)
+    for i in range(12):  # real eigenpairs satisfy T x = lambda B x
+        if wi[i] == 0.0:
+            x = VR[:, i]
+            assert np.linalg.norm(T @ x - wr[i] * (Bm @ x)) < 1e-9 * np.linalg.norm(x)
+
+
+# ------------------------------------------------------------------ Mmn
+def test_mmn_fill_and_mulright(ctx):
+    rng = np.random.default_rng(4)
+    N, naux = 41, 53
+    mos = rng.standard_normal((N, N))
+    ao = rng.standard_normal((naux, N, N))
+    ao = ao + ao.transpose(0, 2, 1)
+    tc = threecenter.TCMatrix(naux, 2, 24, 2, N - 1)
+    tc.fill_3c_mo(ao, mos)
+    ctx.mmn_alloc(naux, 2, 24, 2, N - 1)
+    ctx.mmn_set_mos(mos)
+    ctx.mmn_fill_block(0, ao[:20])
+    ctx.mmn_fill_block(20, ao[20:])
+    assert rel_frob(tc.M, ctx.mmn_get_all()) < TOL
+    R = rng.standard_normal((naux, naux))
+    tc.multiply_right(R)
+    ctx.mmn_mul_right(R)
+    assert rel_frob(tc.M, ctx.mmn_get_all()) < TOL
+    # snapshot / restore (Rebuild)
+    ctx.call("gwbse_mmn_snapshot")
+    ctx.mmn_mul_right(R)
+    ctx.call("gwbse_mmn_restore")
+    assert rel_frob(tc.M, ctx.mmn_get_all()) < TOL
+
+
+def test_mmn_golden_threecenter(ctx, golden, methane):
+    """test_threecenter_gwbse.cc:36-126 through the CUDA path (AO integrals from the host)."""
+    mos = golden["threecenter_gwbse/MOs"]
+    ctx.mmn_alloc(17, 0, 5, 0, 7)
+    ctx.mmn_set_mos(mos)
+    ctx.mmn_fill_block(0, methane["ao3c"])
+    L, removed = ctx.pseudo_invsqrt(methane["S"], methane["V"])
+    Lref, rref = threecenter.pseudo_invsqrt_gwbse(methane["S"], methane["V"])
+    assert removed == rref
+    assert rel_frob(Lref, L) < 1e-9
+    ctx.mmn_mul_right(L)
+    for i, name in [(0, "ref0b"), (2, "ref2b"), (4, "ref4b")]:
+        assert rel_frob(golden["threecenter_gwbse/" + name], ctx.mmn_get_slice(i)) < 1e-5
+    ctx.mmn_mul_right(np.eye(17))
+    for i, name in [(0, "ref0b"), (2, "ref2b"), (4, "ref4b")]:
+        assert rel_frob(golden["threecenter_gwbse/" + name], ctx.mmn_get_slice(i)) < 1e-5
+
+
+# ------------------------------------------------------------------ RPA
+def test_rpa_epsilon_golden(ctx, golden):
+    tc = methane_mmn(golden["rpa/eigenvectors"])
+    push(ctx, tc)
+    e = golden["rpa/eigenvals"].ravel()
+    assert rel_frob(golden["rpa/i_ref"], ctx.rpa_epsilon(0, 0.5, 1e-4, e, 4, 0, 16)) < 1e-4
+    assert rel_frob(golden["rpa/r_ref"], ctx.rpa_epsilon(1, 0.0, 1e-4, e, 4, 0, 16)) < 1e-4
+    assert rel_frob(golden["rpa/r_complex_ref"], ctx.rpa_epsilon(2, complex(0.5, 0.5), 1e-4, e, 4, 0, 16)) < 1e-4
+
+
+@pytest.mark.parametrize("shape", [(70, 30, 45, 10), (200, 40, 161, 23)])
+def test_rpa_epsilon_random(ctx, shape):
+    naux, mtotal, ntotal, homo = shape
+    rng = np.random.default_rng(5)
+    tc = random_tc(rng, naux, mtotal, ntotal)
+    push(ctx, tc)
+    e = np.sort(rng.uniform(-1, 2, ntotal))
+    r = orpa.RPA(tc)
+    r.configure(homo, 0, ntotal - 1)
+    r.set_rpa_input_energies(e)
+    assert rel_frob(r.calculate_epsilon_i(0.5), ctx.rpa_epsilon(0, 0.5, r.ETA, e, homo, 0, ntotal - 1)) < TOL
+    assert rel_frob(r.calculate_epsilon_r(0.3), ctx.rpa_epsilon(1, 0.3, r.ETA, e, homo, 0, ntotal - 1)) < TOL
+    w = complex(0.2, 0.4)
+    assert rel_frob(r.calculate_epsilon_r(w), ctx.rpa_epsilon(2, w, r.ETA, e, homo, 0, ntotal - 1)) < TOL
+    assert rel_frob(np.tril(r.h2p_apb()), np.tril(ctx.rpa_h2p_apb(e, homo, 0, ntotal - 1))) < TOL
+
+
+# ------------------------------------------------------------------ Sigma
+def _sigma_setup(ctx, rng, kind, naux=60, mtotal=26, ntotal=37, homo=8, qpmin=2, qpmax=22):
+    tc = random_tc(rng, naux, mtotal, ntotal)
+    e = np.sort(np.concatenate([rng.uniform(-1.2, -0.3, homo + 1), rng.uniform(0.05, 2.5, ntotal - homo - 1)]))
+    r = orpa.RPA(tc)
+    r.configure(homo, 0, ntotal - 1)
+    r.set_rpa_input_energies(e)
+    s = osig.create(kind, tc, r)
+    s.configure(osig.SigmaOptions(homo=homo, qpmin=qpmin, qpmax=qpmax, rpamin=0, rpamax=ntotal - 1, eta=1e-3))
+    return tc, e, r, s
+
+
+def test_sigma_x(ctx):
+    rng = np.random.default_rng(6)
+    tc, e, r, s = _sigma_setup(ctx, rng, "ppm")
+    push(ctx, tc)
+    assert rel_frob(s.calc_exchange_matrix(), ctx.sigma_x(8, 0, 2, 22)) < TOL
+
+
+def test_sigma_ppm(ctx):
+    rng = np.random.default_rng(7)
+    tc, e, r, s = _sigma_setup(ctx, rng, "ppm")
+    s.prepare_screening()  # rotates tc.M in place; push the rotated tensor
+    push(ctx, tc)
+    ctx.sigma_ppm_set(s.ppm_weight, s.ppm_freq, e, 8, 0, 2, 1e-3)
+    q = s.qptotal
+    levels = np.repeat(np.arange(q), 3)
+    freqs = np.tile([-0.45, 0.1, 0.77], q) + 0.01 * levels
+    sig, dsig = ctx.sigma_ppm_eval(levels, freqs, deriv=True)
+    ref = np.array([s.calc_correlation_diag_element(l, w) for l, w in zip(levels, freqs)])
+    dref = np.array([s.calc_correlation_diag_element_derivative(l, w) for l, w in zip(levels, freqs)])
+    assert rel_frob(ref, sig) < 1e-10
+    assert rel_frob(dref, dsig) < 1e-10
+    fq = e[2:2 + q] + 0.05
+    assert rel_frob(s.calc_correlation_offdiag(fq), ctx.sigma_ppm_offdiag(fq)) < 1e-10
+
+
+def test_sigma_exact(ctx):
+    rng = np.random.default_rng(8)
+    tc, e, r, s = _sigma_setup(ctx, rng, "exact", naux=40, mtotal=20, ntotal=20, homo=5, qpmin=1, qpmax=18)
+    tc.M *= 0.2  # keep the RPA matrix positive definite
+    push(ctx, tc)
+    omega, XpY, _ = r.diagonalize_h2p()
+    s.rpa_omegas = omega
+    s.residues = [s._calc_residues(i, XpY) for i in range(s.qptotal)]
+    ctx.sigma_exact_prepare(omega, XpY, e, 5, 0, 19, 1, 18, 1e-3)
+    q = s.qptotal
+    levels = np.repeat(np.arange(q), 2)
+    freqs = np.tile([-0.5, 0.6], q) + 0.013 * levels
+    sig, dsig = ctx.sigma_exact_eval(levels, freqs, deriv=True)
+    ref = np.array([s.calc_correlation_diag_element(l, w) for l, w in zip(levels, freqs)])
+    dref = np.array([s.calc_correlation_diag_element_derivative(l, w) for l, w in zip(levels, freqs)])
+    assert rel_frob(ref, sig) < 1e-10
+    assert rel_frob(dref, dsig) < 1e-10
+    fq = e[1:1 + q] + 0.02
+    assert rel_frob(s.calc_correlation_offdiag(fq), ctx.sigma_exact_offdiag(fq)) < 1e-10
+
+
+def test_sigma_golden(ctx, golden):
+    """test_sigma_ppm.cc / test_sigma_exact.cc reference matrices through the CUDA path."""
+    for kind in ("ppm", "exact"):
+        d = "sigma_" + kind
+        e = golden["inline/sigma_ppm_mo_energy"] if kind == "ppm" else golden["inline/sigma_exact_mo_energy"]
+        tc = methane_mmn(golden[d + "/MOs"])
+        r = orpa.RPA(tc)
+        r.configure(4, 0, 16)
+        r.set_rpa_input_energies(e)
+        push(ctx, tc)
+        assert rel_frob(golden[d + "/x_ref"], ctx.sigma_x(4, 0, 0, 16)) < 1e-5
+        if kind == "ppm":
+            s = osig.create("ppm", tc, r)
+            s.configure(osig.SigmaOptions(homo=4, qpmin=0, qpmax=16, rpamin=0, rpamax=16, eta=1e-3))
+            # PPM parameters from the device epsilon matrices (ppm.cc:30-59 on the GPU path)
+            w, phi = ctx.sym_eig(ctx.rpa_epsilon(1, 0.0, 1e-4, e, 4, 0, 16))
+            weight = 1 - 1 / w
+            eps_i = ctx.rpa_epsilon(0, 0.5, 1e-4, e, 4, 0, 16)
+            inv = ctx.inverse(phi.T @ eps_i @ phi)
+            freq = np.zeros(17)
+            for i in range(17):
+                if weight[i] < 1e-5:
+                    weight[i], freq[i] = 0.0, 0.5
+                else:
+                    nom = inv[i, i] - 1.0
+                    freq[i] = np.sqrt(abs(-nom / (nom + weight[i]) * 0.25))
+            ctx.mmn_mul_right(phi)
+            ctx.sigma_ppm_set(weight, freq, e, 4, 0, 0, 1e-3)
+            c = ctx.sigma_ppm_offdiag(e)
+            c[np.diag_indices(17)] = ctx.sigma_ppm_eval(np.arange(17), e)
+        else:
+            omega, XpY, _ = r.diagonalize_h2p()
+            ctx.sigma_exact_prepare(omega, XpY, e, 4, 0, 16, 0, 16, 1e-3)
+            c = ctx.sigma_exact_offdiag(e)
+            c[np.diag_indices(17)] = ctx.sigma_exact_eval(np.arange(17), e)
+        assert rel_frob(golden[d + "/c_ref"], c) < 1e-5
+
+
+# ------------------------------------------------------------------ BSE operator
+OPS = {"singlet_tda": (1, 2, 1, 0), "triplet_tda": (1, 0, 1, 0), "singlet_btda_b": (0, 2, 0, 1),
+       "hqp": (1, 0, 0, 0), "hx": (0, 1, 0, 0), "hd": (0, 0, 1, 0), "hd2": (0, 0, 0, 1)}
+
+
+def test_bse_operator_golden(ctx, golden):
+    tc = methane_mmn(golden["bse_operator/MOs"])
+    tc.multiply_right(golden["bse_operator/rpa_op"])
+    push(ctx, tc)
+    eps = golden["inline/bse_operator_epsilon_inv"]
+    ctx.bse_configure(4, 0, 0, 8, eps, golden["bse_operator/Hqp"][:9, :9])
+    eye = np.eye(20)
+    for name in ("hqp", "hx", "hd", "hd2"):
+        dense = ctx.bse_matmul(OPS[name], eye)
+        assert rel_frob(golden["bse_operator/%s_ref" % name], dense) < 1e-3
+        assert np.abs(np.diag(dense) - ctx.bse_diagonal(OPS[name])).max() < 1e-12
+
+
+@pytest.mark.parametrize("dims", [(50, 30, 33, 9, 3, 27, 6), (90, 40, 47, 15, 0, 39, 21)])
+@pytest.mark.parametrize("chunk", [1 << 30, 1 << 16])
+def test_bse_operator_random(ctx, dims, chunk):
+    naux, mtotal, ntotal, homo, vmin, cmax, k = dims
+    rng = np.random.default_rng(9)
+    tc = random_tc(rng, naux, mtotal, ntotal)
+    push(ctx, tc)
+    ctx.set_option("bse_chunk_bytes", chunk)
+    vt, ct = homo - vmin + 1, cmax - homo
+    Hqp = rng.standard_normal((vt + ct, vt + ct))
+    Hqp = Hqp + Hqp.T
+    eps = rng.uniform(0.3, 1.0, naux)
+    ctx.bse_configure(homo, 0, vmin, cmax, eps, Hqp)
+    X = rng.standard_normal((vt * ct, k))
+    opt = bop.BSEOperatorOptions(homo=homo, rpamin=0, qpmin=0, vmin=vmin, cmax=cmax)
+    for name, co in OPS.items():
+        op = bop.BSEOperator(*co, eps, tc, Hqp)
+        op.configure(opt)
+        ref = op.matmul(X)  # reference formulation (row-by-row rebuild of H)
+        assert rel_frob(ref, ctx.bse_matmul(co, X)) < TOL, name
+        assert rel_frob(op.diagonal(), ctx.bse_diagonal(co)) < TOL, name
+    ctx.set_option("bse_chunk_bytes", 1 << 30)
+
+
+def test_bse_operator_errors(ctx):
+    from votca_b200.api import GwbseError
+    rng = np.random.default_rng(10)
+    push(ctx, random_tc(rng))
+    ctx.bse_configure(9, 0, 3, 27, np.ones(70), np.eye(25))
+    with pytest.raises(GwbseError, match="Hd and Hd2"):
+        ctx.bse_matmul((1, 0, 1, 1), np.zeros((7 * 18, 1)))
+
+
+# ------------------------------------------------------------------ Davidson helpers
+def test_gramschmidt_and_correction(ctx):
+    rng = np.random.default_rng(11)
+    Q = rng.standard_normal((500, 14))
+    Q[:, :6] = np.linalg.qr(Q[:, :6])[0]
+    ref = Q.copy()
+    DavidsonSolver._gramschmidt(ref, 6)
+    out = ctx.gramschmidt(Q, 6)
+    assert rel_frob(ref, out) < 1e-11
+    assert np.abs(out.T @ out - np.eye(14)).max() < 1e-13
+    Q0 = rng.standard_normal((500, 5))
+    ref0 = Q0.copy()
+    DavidsonSolver._gramschmidt(ref0, 0)
+    assert rel_frob(ref0, ctx.gramschmidt(Q0, 0)) < 1e-11
+    ds = DavidsonSolver()
+    ds.Adiag = rng.uniform(1, 3, 500)
+    lam = np.array([0.9, 1.1, 1.2])
+    R = rng.standard_normal((500, 3))
+    Qv = rng.standard_normal((500, 3))
+    for corr in ("DPR", "OLSEN"):
+        ds.correction = corr
+        refw = np.array([ds._correction(Qv[:, j], lam[j], R[:, j]) for j in range(3)]).T
+        refw /= np.linalg.norm(refw, axis=0)
+        assert rel_frob(refw, ctx.davidson_correction(ds.Adiag, lam, R, Qv, olsen=(corr == "OLSEN"))) < 1e-11

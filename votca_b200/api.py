@@ -1,0 +1,305 @@
+"""Thin NumPy-facing wrapper over the C ABI (tests / bench plumbing only).
+
+Every method maps 1:1 onto an entry point of include/gwbse_b200.h; host arrays are
+converted to column-major float64 and results come back as NumPy arrays.  No math
+happens here.
+"""
+import ctypes
+
+import numpy as np
+
+from ._capi import capi, fmat, ptr
+
+
+class GwbseError(RuntimeError):
+    pass
+
+
+class Context:
+    def __init__(self, device=0):
+        self.api = capi()
+        h = ctypes.c_void_p()
+        if self.api.gwbse_ctx_create(int(device), ctypes.byref(h)) != 0:
+            raise GwbseError(self.api.gwbse_create_error().decode())
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.api.gwbse_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise GwbseError(self.api.gwbse_last_error(self.h).decode())
+
+    def call(self, name, *args):
+        self._ck(getattr(self.api, name)(self.h, *args))
+
+    # ---- misc ----
+    def sync(self):
+        self.call("gwbse_sync")
+
+    def set_option(self, key, value):
+        self.call("gwbse_set_option", key.encode(), float(value))
+
+    def launch_count(self):
+        return int(self.api.gwbse_launch_count(self.h))
+
+    def timer_start(self):
+        self.call("gwbse_timer_start")
+
+    def timer_stop_ms(self):
+        ms = ctypes.c_float()
+        self.call("gwbse_timer_stop_ms", ctypes.byref(ms))
+        return float(ms.value)
+
+    def comm_init(self, rank, world, uid):
+        buf = (ctypes.c_ubyte * 128).from_buffer_copy(bytes(uid))
+        self.call("gwbse_comm_init", int(rank), int(world), buf)
+
+    def nccl_unique_id(self):
+        buf = (ctypes.c_ubyte * 128)()
+        if self.api.gwbse_nccl_unique_id(buf) != 0:
+            raise GwbseError("cannot create NCCL unique id")
+        return bytes(buf)
+
+    # ---- device memory ----
+    def malloc(self, n):
+        p = ctypes.c_void_p()
+        self.call("gwbse_dev_malloc", ctypes.c_size_t(int(n) * 8), ctypes.byref(p))
+        return p
+
+    def free(self, p):
+        self.call("gwbse_dev_free", p)
+
+    def upload(self, a):
+        a = fmat(a)
+        p = self.malloc(max(a.size, 1))
+        self.call("gwbse_h2d", p, ptr(a), ctypes.c_size_t(a.size))
+        return p
+
+    def h2d(self, p, a):
+        a = fmat(a)
+        self.call("gwbse_h2d", p, ptr(a), ctypes.c_size_t(a.size))
+
+    def download(self, p, shape):
+        out = np.empty(shape, dtype=np.float64, order="F")
+        self.call("gwbse_d2h", ptr(out), p, ctypes.c_size_t(out.size))
+        return out
+
+    # ---- dense primitives ----
+    def dgemm(self, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, cfg=-1, splitk=0):
+        self.call("gwbse_dgemm_dev_ex", ta.encode(), tb.encode(), m, n, k, float(alpha), A, lda, B, ldb, float(beta),
+                  C, ldc, cfg, splitk)
+
+    def gemm_host(self, ta, tb, alpha, A, B, beta=0.0, C=None, cfg=-1, splitk=0):
+        """Convenience: op(A) op(B) on host arrays through the device GEMM."""
+        A, B = fmat(A), fmat(B)
+        m = A.shape[1] if ta == "T" else A.shape[0]
+        k = A.shape[0] if ta == "T" else A.shape[1]
+        n = B.shape[0] if tb == "T" else B.shape[1]
+        Cm = np.zeros((m, n), order="F") if C is None else fmat(C).copy(order="F")
+        dA, dB, dC = self.upload(A), self.upload(B), self.upload(Cm)
+        self.dgemm(ta, tb, m, n, k, alpha, dA, max(A.shape[0], 1), dB, max(B.shape[0], 1), beta, dC, max(m, 1),
+                   cfg, splitk)
+        out = self.download(dC, (m, n))
+        for p in (dA, dB, dC):
+            self.free(p)
+        return out
+
+    def sym_eig(self, A):
+        A = fmat(A).copy(order="F")
+        n = A.shape[0]
+        d = self.upload(A)
+        w = np.empty(n)
+        self.call("gwbse_sym_eig_dev", n, d, n, ptr(w))
+        V = self.download(d, (n, n))
+        self.free(d)
+        return w, V
+
+    def inverse(self, A):
+        A = fmat(A).copy(order="F")
+        n = A.shape[0]
+        d = self.upload(A)
+        self.call("gwbse_inverse_dev", n, d, n)
+        out = self.download(d, (n, n))
+        self.free(d)
+        return out
+
+    def lu_solve(self, A, B):
+        A, B = fmat(A).copy(order="F"), fmat(B).copy(order="F")
+        if B.ndim == 1:
+            B = B[:, None].copy(order="F")
+        n, nrhs = A.shape[0], B.shape[1]
+        dA, dB = self.upload(A), self.upload(B)
+        self.call("gwbse_lu_solve_dev", n, nrhs, dA, n, dB, n)
+        out = self.download(dB, (n, nrhs))
+        self.free(dA)
+        self.free(dB)
+        return out
+
+    def gen_eig(self, T, B):
+        T, B = fmat(T), fmat(B)
+        n = T.shape[0]
+        wr, wi, VR = np.empty(n), np.empty(n), np.empty((n, n), order="F")
+        self.call("gwbse_gen_eig_host", n, ptr(T), ptr(B), ptr(wr), ptr(wi), ptr(VR))
+        return wr, wi, VR
+
+    # ---- Mmn ----
+    def mmn_alloc(self, naux, mmin, mmax, nmin, nmax):
+        self.call("gwbse_mmn_alloc", naux, mmin, mmax, nmin, nmax)
+        self.naux, self.mtotal, self.ntotal = naux, mmax - mmin + 1, nmax - nmin + 1
+
+    def mmn_set_mos(self, mos):
+        mos = fmat(mos)
+        self.call("gwbse_mmn_set_mos", ptr(mos), mos.shape[0], mos.shape[0], mos.shape[1])
+
+    def mmn_fill_block(self, aux_offset, ao3c):
+        """ao3c: (count, N, N) symmetric matrices."""
+        a = np.ascontiguousarray(ao3c, dtype=np.float64)
+        self.call("gwbse_mmn_fill_block", aux_offset, a.shape[0], ptr(a))
+
+    def mmn_mul_right(self, R):
+        R = fmat(R)
+        self.call("gwbse_mmn_mul_right", ptr(R), R.shape[0])
+
+    def mmn_get_slice(self, m):
+        out = np.empty((self.ntotal, self.naux), order="F")
+        self.call("gwbse_mmn_get_slice", m, ptr(out), self.ntotal)
+        return out
+
+    def mmn_set_slice(self, m, a):
+        a = fmat(a)
+        self.call("gwbse_mmn_set_slice", m, ptr(a), a.shape[0])
+
+    def mmn_get_all(self):
+        return np.array([self.mmn_get_slice(m) for m in range(self.mtotal)])
+
+    def mmn_set_all(self, M):
+        for m in range(self.mtotal):
+            self.mmn_set_slice(m, M[m])
+
+    def pseudo_invsqrt(self, S, V, etol=5e-7):
+        S, V = fmat(S), fmat(V)
+        n = S.shape[0]
+        L = np.empty((n, n), order="F")
+        removed = ctypes.c_int()
+        self.call("gwbse_pseudo_invsqrt", n, ptr(S), ptr(V), float(etol), ptr(L), ctypes.byref(removed))
+        return L, int(removed.value)
+
+    # ---- RPA ----
+    def rpa_epsilon(self, kind, freq, eta, energies, homo, rpamin, rpamax, fetch=True):
+        e = np.ascontiguousarray(energies, dtype=np.float64)
+        fre, fim = (freq.real, freq.imag) if isinstance(freq, complex) else (float(freq), 0.0)
+        out = np.empty((self.naux, self.naux), order="F") if fetch else None
+        self.call("gwbse_rpa_epsilon", kind, fre, fim, float(eta), ptr(e), homo, rpamin, rpamax, ptr(out),
+                  self.naux)
+        return out
+
+    def rpa_h2p_apb(self, energies, homo, rpamin, rpamax):
+        e = np.ascontiguousarray(energies, dtype=np.float64)
+        S = (homo + 1 - rpamin) * (rpamax - homo)
+        d = self.malloc(S * S)
+        self.call("gwbse_rpa_h2p_apb", ptr(e), homo, rpamin, rpamax, d, S)
+        out = self.download(d, (S, S))
+        self.free(d)
+        return out
+
+    # ---- Sigma ----
+    def sigma_x(self, homo, rpamin, qpmin, qpmax):
+        q = qpmax - qpmin + 1
+        out = np.empty((q, q), order="F")
+        self.call("gwbse_sigma_x", homo, rpamin, qpmin, qpmax, ptr(out), q)
+        return out
+
+    def sigma_ppm_set(self, weight, freq, energies, homo, rpamin, qpmin, eta):
+        w, f, e = (np.ascontiguousarray(x, dtype=np.float64) for x in (weight, freq, energies))
+        self.call("gwbse_sigma_ppm_set", ptr(w), ptr(f), ptr(e), homo, rpamin, qpmin, float(eta))
+
+    def _sigma_eval(self, fn, levels, freqs, deriv):
+        lv = np.ascontiguousarray(levels, dtype=np.int32)
+        fr = np.ascontiguousarray(freqs, dtype=np.float64)
+        s = np.empty(len(lv))
+        ds = np.empty(len(lv)) if deriv else None
+        self.call(fn, len(lv), ptr(lv), ptr(fr), ptr(s), ptr(ds))
+        return (s, ds) if deriv else s
+
+    def sigma_ppm_eval(self, levels, freqs, deriv=False):
+        return self._sigma_eval("gwbse_sigma_ppm_eval", levels, freqs, deriv)
+
+    def sigma_ppm_offdiag(self, freqs):
+        fr = np.ascontiguousarray(freqs, dtype=np.float64)
+        q = len(fr)
+        out = np.empty((q, q), order="F")
+        self.call("gwbse_sigma_ppm_offdiag", q, ptr(fr), ptr(out), q)
+        return out
+
+    def sigma_exact_prepare(self, omegas, XpY, energies, homo, rpamin, rpamax, qpmin, qpmax, eta):
+        om, e = (np.ascontiguousarray(x, dtype=np.float64) for x in (omegas, energies))
+        d = self.upload(XpY)
+        try:
+            self.call("gwbse_sigma_exact_prepare", ptr(om), d, XpY.shape[0], ptr(e), homo, rpamin, rpamax, qpmin,
+                      qpmax, float(eta))
+        finally:
+            self.free(d)
+
+    def sigma_exact_eval(self, levels, freqs, deriv=False):
+        return self._sigma_eval("gwbse_sigma_exact_eval", levels, freqs, deriv)
+
+    def sigma_exact_offdiag(self, freqs):
+        fr = np.ascontiguousarray(freqs, dtype=np.float64)
+        q = len(fr)
+        out = np.empty((q, q), order="F")
+        self.call("gwbse_sigma_exact_offdiag", q, ptr(fr), ptr(out), q)
+        return out
+
+    # ---- BSE ----
+    def bse_configure(self, homo, rpamin, vmin, cmax, eps_inv, Hqp):
+        e = np.ascontiguousarray(eps_inv, dtype=np.float64)
+        H = fmat(Hqp)
+        self.call("gwbse_bse_configure", homo, rpamin, vmin, cmax, ptr(e), ptr(H), H.shape[0])
+        self.bse_size = (homo - vmin + 1) * (cmax - homo)
+
+    def bse_matmul(self, coeffs, X):
+        X = fmat(X)
+        if X.ndim == 1:
+            X = X[:, None].copy(order="F")
+        Y = np.empty_like(X, order="F")
+        cqp, cx, cd, cd2 = coeffs
+        self.call("gwbse_bse_matmul", cqp, cx, cd, cd2, X.shape[1], ptr(X), X.shape[0], ptr(Y), Y.shape[0])
+        return Y
+
+    def bse_diagonal(self, coeffs):
+        out = np.empty(self.bse_size)
+        cqp, cx, cd, cd2 = coeffs
+        self.call("gwbse_bse_diagonal", cqp, cx, cd, cd2, ptr(out))
+        return out
+
+    # ---- Davidson helpers ----
+    def gramschmidt(self, Q, nstart):
+        Q = fmat(Q).copy(order="F")
+        d = self.upload(Q)
+        try:
+            self.call("gwbse_gramschmidt_dev", Q.shape[0], Q.shape[1], nstart, d, Q.shape[0])
+            return self.download(d, Q.shape)
+        finally:
+            self.free(d)
+
+    def davidson_correction(self, diag, lam, R, Q, olsen=False):
+        R, Q = fmat(R), fmat(Q)
+        lam = np.ascontiguousarray(lam, dtype=np.float64)
+        dd, dR, dQ = self.upload(diag), self.upload(R), self.upload(Q)
+        dW = self.malloc(R.size)
+        try:
+            self.call("gwbse_davidson_correction_dev", R.shape[0], R.shape[1], int(olsen), dd, ptr(lam), dR,
+                      R.shape[0], dQ, Q.shape[0], dW, R.shape[0])
+            return self.download(dW, R.shape)
+        finally:
+            for p in (dd, dR, dQ, dW):
+                self.free(p)

@@ -1,0 +1,398 @@
+// C ABI, part 1: context, device memory, dense primitives, dense auxiliaries.
+#include <cstring>
+#include <vector>
+
+#include "../../include/gwbse_b200.h"
+#include "context.cuh"
+
+using namespace gwbse;
+
+static thread_local std::string g_create_error;
+
+void gwbse_ctx::gemm(const GemmParams& p, int cfg, int splitk) {
+  const size_t need = gemm_ws_bytes_needed(p, num_sms, cfg, splitk);
+  double* ws = need ? buf("gemm_ws", need / sizeof(double)) : nullptr;
+  gemm_launch(p, stream, ws, need, num_sms, cfg, splitk);
+  launches += (need ? 2 : 1);
+}
+
+static void check_solver(cusolverStatus_t st, const char* what) {
+  if (st != CUSOLVER_STATUS_SUCCESS)
+    throw std::runtime_error(std::string("cuSOLVER error ") + std::to_string((int)st) + " in " + what);
+}
+
+extern "C" {
+
+int gwbse_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+const char* gwbse_create_error(void) { return g_create_error.c_str(); }
+
+int gwbse_ctx_create(int device, gwbse_ctx** out) {
+  if (!out) return 1;
+  *out = nullptr;
+  gwbse_ctx* ctx = nullptr;
+  try {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+      throw std::runtime_error(std::string("gwbse_b200 needs a CUDA device (sm_100a); none found: ") +
+                               cudaGetErrorString(e));
+    if (device < 0 || device >= n) throw std::runtime_error("gwbse_ctx_create: invalid device index");
+    GW_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    GW_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+      throw std::runtime_error(std::string("gwbse_b200 is built for sm_100a only; device is ") + prop.name);
+    ctx = new gwbse_ctx();
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    GW_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    GW_CUDA(cudaEventCreate(&ctx->ev0));
+    GW_CUDA(cudaEventCreate(&ctx->ev1));
+    check_solver(cusolverDnCreate(&ctx->solver), "cusolverDnCreate");
+    check_solver(cusolverDnSetStream(ctx->solver, ctx->stream), "cusolverDnSetStream");
+    *out = ctx;
+    return 0;
+  } catch (const std::exception& e) {
+    g_create_error = e.what();
+    delete ctx;
+    return 1;
+  }
+}
+
+void gwbse_ctx_destroy(gwbse_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& kv : ctx->bufs)
+    if (kv.second.p) cudaFree(kv.second.p);
+  for (double* p : {ctx->X, ctx->X2, ctx->Xsnap, ctx->mos, ctx->eps, ctx->exact_res, ctx->bse.eps_inv, ctx->bse.hqp})
+    if (p) cudaFree(p);
+  for (auto* st : {&ctx->sig_ppm, &ctx->sig_exact})
+    for (double* p : {st->fac, st->pole, st->energies})
+      if (p) cudaFree(p);
+  if (ctx->solver) cusolverDnDestroy(ctx->solver);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* gwbse_last_error(const gwbse_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int gwbse_sync(gwbse_ctx* ctx) {
+  GW_API_BEGIN(ctx)
+  GW_CUDA(cudaStreamSynchronize(ctx->stream));
+  GW_API_END(ctx)
+}
+
+long long gwbse_launch_count(const gwbse_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int gwbse_set_option(gwbse_ctx* ctx, const char* key, double value) {
+  GW_API_BEGIN(ctx)
+  const std::string k(key ? key : "");
+  if (k == "bse_chunk_bytes") {
+    GW_REQUIRE(value >= 1024, "bse_chunk_bytes too small");
+    ctx->bse_chunk_bytes = (size_t)value;
+  } else {
+    throw std::runtime_error("unknown option '" + k + "'");
+  }
+  GW_API_END(ctx)
+}
+
+int gwbse_timer_start(gwbse_ctx* ctx) {
+  GW_API_BEGIN(ctx)
+  GW_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  GW_API_END(ctx)
+}
+int gwbse_timer_stop_ms(gwbse_ctx* ctx, float* ms) {
+  GW_API_BEGIN(ctx)
+  GW_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  GW_CUDA(cudaEventSynchronize(ctx->ev1));
+  GW_CUDA(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+  GW_API_END(ctx)
+}
+
+// ------------------------------ memory ------------------------------------
+int gwbse_dev_malloc(gwbse_ctx* ctx, size_t bytes, double** out_dev) {
+  GW_API_BEGIN(ctx)
+  // same pre-check and message style as CudaMatrix::alloc (cudamatrix.cc:97-113)
+  size_t fr = 0, tot = 0;
+  GW_CUDA(cudaMemGetInfo(&fr, &tot));
+  if (bytes > fr)
+    throw std::runtime_error("There were requested : " + std::to_string((double)bytes / 1048576.0) +
+                             " MB but the device has " + std::to_string((double)fr / 1048576.0) + " MB free.");
+  GW_CUDA(cudaMalloc(out_dev, bytes ? bytes : 8));
+  GW_API_END(ctx)
+}
+int gwbse_dev_free(gwbse_ctx* ctx, double* p) {
+  GW_API_BEGIN(ctx)
+  GW_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (p) GW_CUDA(cudaFree(p));
+  GW_API_END(ctx)
+}
+int gwbse_h2d(gwbse_ctx* ctx, double* dst, const double* src, size_t n) {
+  GW_API_BEGIN(ctx)
+  GW_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  GW_CUDA(cudaStreamSynchronize(ctx->stream));
+  GW_API_END(ctx)
+}
+int gwbse_d2h(gwbse_ctx* ctx, double* dst, const double* src, size_t n) {
+  GW_API_BEGIN(ctx)
+  GW_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  GW_CUDA(cudaStreamSynchronize(ctx->stream));
+  GW_API_END(ctx)
+}
+int gwbse_d2d(gwbse_ctx* ctx, double* dst, const double* src, size_t n) {
+  GW_API_BEGIN(ctx)
+  GW_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  GW_API_END(ctx)
+}
+int gwbse_dev_memset_zero(gwbse_ctx* ctx, double* dst, size_t n) {
+  GW_API_BEGIN(ctx)
+  GW_CUDA(cudaMemsetAsync(dst, 0, n * sizeof(double), ctx->stream));
+  GW_API_END(ctx)
+}
+int gwbse_dev_mem_info(gwbse_ctx* ctx, size_t* fr, size_t* tot) {
+  GW_API_BEGIN(ctx)
+  GW_CUDA(cudaMemGetInfo(fr, tot));
+  GW_API_END(ctx)
+}
+
+// ------------------------------ GEMM --------------------------------------
+static GemmParams blas_params(char ta, char tb, int m, int n, int k, double alpha, const double* A, int lda,
+                              const double* B, int ldb, double beta, double* C, int ldc) {
+  const bool at = (ta == 'T' || ta == 't'), bt = (tb == 'T' || tb == 't');
+  GW_REQUIRE(at || ta == 'N' || ta == 'n', "transa must be N or T");
+  GW_REQUIRE(bt || tb == 'N' || tb == 'n', "transb must be N or T");
+  // shape checks in the spirit of CudaPipeline::gemm (cudapipeline.h:113-118)
+  GW_REQUIRE(lda >= (at ? k : m) && ldb >= (bt ? n : k) && ldc >= m, "Shape mismatch in cuda gemm");
+  GemmParams p;
+  p.M = m;
+  p.N = n;
+  p.Ko = 1;
+  p.Ki = k;
+  p.A.ptr = A;
+  if (at) {  // op(A)(i,l) = A(l,i): k contiguous
+    p.A.s_ri = lda;
+    p.A.s_ki = 1;
+  } else {
+    p.A.s_ri = 1;
+    p.A.s_ki = lda;
+  }
+  p.B.ptr = B;
+  if (bt) {  // op(B)(l,j) = B(j,l): row index j contiguous
+    p.B.s_ri = 1;
+    p.B.s_ki = ldb;
+  } else {
+    p.B.s_ri = ldb;
+    p.B.s_ki = 1;
+  }
+  p.C = C;
+  p.sC_mi = 1;
+  p.sC_ni = ldc;
+  p.alpha = alpha;
+  p.beta = beta;
+  return p;
+}
+
+int gwbse_dgemm_dev_ex(gwbse_ctx* ctx, char ta, char tb, int m, int n, int k, double alpha, const double* A,
+                       int lda, const double* B, int ldb, double beta, double* C, int ldc, int cfg, int splitk) {
+  GW_API_BEGIN(ctx)
+  if (m > 0 && n > 0) {
+    if (k <= 0) {
+      // C = beta * C
+      if (beta == 0.0) {
+        GW_CUDA(cudaMemset2DAsync(C, sizeof(double) * ldc, 0, sizeof(double) * m, n, ctx->stream));
+      } else if (beta != 1.0) {
+        std::vector<double> s(n, beta);
+        double* sd = ctx->buf("tmp_scale", n);
+        GW_CUDA(cudaMemcpyAsync(sd, s.data(), sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+        GW_CUDA(cudaStreamSynchronize(ctx->stream));
+        launch_scale_cols(m, n, C, ldc, sd, ctx->stream);
+      }
+    } else {
+      ctx->gemm(blas_params(ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc), cfg, splitk);
+    }
+  }
+  GW_API_END(ctx)
+}
+
+int gwbse_dgemm_dev(gwbse_ctx* ctx, char ta, char tb, int m, int n, int k, double alpha, const double* A, int lda,
+                    const double* B, int ldb, double beta, double* C, int ldc) {
+  return gwbse_dgemm_dev_ex(ctx, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, -1, 0);
+}
+
+int gwbse_diag_scale_dev(gwbse_ctx* ctx, char side, int m, int n, const double* A, int lda, const double* d,
+                         double* C, int ldc) {
+  GW_API_BEGIN(ctx)
+  launch_diag_scale(side, m, n, A, lda, d, C, ldc, ctx->stream);
+  ctx->launches++;
+  GW_API_END(ctx)
+}
+
+int gwbse_axpy_dev(gwbse_ctx* ctx, int m, int n, double alpha, const double* X, int ldx, double* Y, int ldy) {
+  GW_API_BEGIN(ctx)
+  launch_axpy(m, n, alpha, X, ldx, Y, ldy, ctx->stream);
+  ctx->launches++;
+  GW_API_END(ctx)
+}
+
+int gwbse_colnorms_dev(gwbse_ctx* ctx, int m, int n, const double* A, int lda, double* norms) {
+  GW_API_BEGIN(ctx)
+  if (n > 0) {
+    double* d = ctx->buf("colred", n);
+    launch_colnorms(m, n, A, lda, d, ctx->stream);
+    ctx->launches++;
+    GW_CUDA(cudaMemcpyAsync(norms, d, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    GW_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  GW_API_END(ctx)
+}
+
+int gwbse_coldots_dev(gwbse_ctx* ctx, int m, int n, const double* X, int ldx, const double* Y, int ldy,
+                      double* dots) {
+  GW_API_BEGIN(ctx)
+  if (n > 0) {
+    double* d = ctx->buf("colred", n);
+    launch_coldots(m, n, X, ldx, Y, ldy, d, ctx->stream);
+    ctx->launches++;
+    GW_CUDA(cudaMemcpyAsync(dots, d, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    GW_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  GW_API_END(ctx)
+}
+
+int gwbse_scale_cols_dev(gwbse_ctx* ctx, int m, int n, double* A, int lda, const double* s) {
+  GW_API_BEGIN(ctx)
+  if (n > 0) {
+    double* d = ctx->buf("colscale", n);
+    GW_CUDA(cudaMemcpyAsync(d, s, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    launch_scale_cols(m, n, A, lda, d, ctx->stream);
+    ctx->launches++;
+    GW_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  GW_API_END(ctx)
+}
+
+// --------------------------- dense auxiliaries -----------------------------
+int gwbse_sym_eig_dev(gwbse_ctx* ctx, int n, double* A, int lda, double* w) {
+  GW_API_BEGIN(ctx)
+  if (n > 0) {
+    int lwork = 0;
+    double* wd = ctx->buf("eig_w", n);
+    check_solver(cusolverDnDsyevd_bufferSize(ctx->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, A,
+                                             lda, wd, &lwork),
+                 "Dsyevd_bufferSize");
+    double* work = ctx->buf("solver_work", (size_t)lwork + 8);
+    int* info = reinterpret_cast<int*>(ctx->buf("solver_info", 8));
+    check_solver(cusolverDnDsyevd(ctx->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, A, lda, wd,
+                                  work, lwork, info),
+                 "Dsyevd");
+    int hinfo = 0;
+    GW_CUDA(cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    GW_CUDA(cudaMemcpyAsync(w, wd, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    GW_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (hinfo != 0) throw std::runtime_error("Small hermitian eigenvalue problem failed.");
+  }
+  GW_API_END(ctx)
+}
+
+static void lu_factor(gwbse_ctx* ctx, int n, double* A, int lda, int** ipiv_out) {
+  int lwork = 0;
+  check_solver(cusolverDnDgetrf_bufferSize(ctx->solver, n, n, A, lda, &lwork), "Dgetrf_bufferSize");
+  double* work = ctx->buf("solver_work", (size_t)lwork + 8);
+  int* info = reinterpret_cast<int*>(ctx->buf("solver_info", 8));
+  int* ipiv = reinterpret_cast<int*>(ctx->buf("solver_ipiv", (size_t)n / 2 + 8));
+  check_solver(cusolverDnDgetrf(ctx->solver, n, n, A, lda, work, ipiv, info), "Dgetrf");
+  int hinfo = 0;
+  GW_CUDA(cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  GW_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (hinfo != 0) throw std::runtime_error("LU factorisation failed (singular matrix), info=" + std::to_string(hinfo));
+  *ipiv_out = ipiv;
+}
+
+int gwbse_lu_solve_dev(gwbse_ctx* ctx, int n, int nrhs, double* A, int lda, double* B, int ldb) {
+  GW_API_BEGIN(ctx)
+  if (n > 0 && nrhs > 0) {
+    int* ipiv = nullptr;
+    lu_factor(ctx, n, A, lda, &ipiv);
+    int* info = reinterpret_cast<int*>(ctx->buf("solver_info", 8));
+    check_solver(cusolverDnDgetrs(ctx->solver, CUBLAS_OP_N, n, nrhs, A, lda, ipiv, B, ldb, info), "Dgetrs");
+  }
+  GW_API_END(ctx)
+}
+
+__global__ void set_identity_kernel(double* A, int n, long long ld) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y;
+  if (i < n && j < n) A[i + j * ld] = (i == j) ? 1.0 : 0.0;
+}
+
+int gwbse_inverse_dev(gwbse_ctx* ctx, int n, double* A, int lda) {
+  GW_API_BEGIN(ctx)
+  if (n > 0) {
+    int* ipiv = nullptr;
+    lu_factor(ctx, n, A, lda, &ipiv);
+    double* I = ctx->buf("inverse_rhs", (size_t)n * n);
+    set_identity_kernel<<<dim3((n + 255) / 256, n), 256, 0, ctx->stream>>>(I, n, n);
+    GW_CUDA(cudaGetLastError());
+    int* info = reinterpret_cast<int*>(ctx->buf("solver_info", 8));
+    check_solver(cusolverDnDgetrs(ctx->solver, CUBLAS_OP_N, n, n, A, lda, ipiv, I, n, info), "Dgetrs");
+    GW_CUDA(cudaMemcpy2DAsync(A, sizeof(double) * lda, I, sizeof(double) * n, sizeof(double) * n, n,
+                              cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  GW_API_END(ctx)
+}
+
+// Generalized non-symmetric eigenproblem T x = lambda B x for the harmonic Ritz step.
+// Solved as (B^-1 T) x = lambda x with cusolverDnXgeev (hybrid host/device LAPACK-class routine).
+int gwbse_gen_eig_host(gwbse_ctx* ctx, int n, const double* T, const double* B, double* wr, double* wi,
+                       double* VR) {
+  GW_API_BEGIN(ctx)
+  if (n > 0) {
+    const size_t nn = (size_t)n * n;
+    double* dT = ctx->buf("geig_T", nn);
+    double* dB = ctx->buf("geig_B", nn);
+    double* dW = ctx->buf("geig_W", 2 * (size_t)n);  // complex eigenvalues
+    double* dVR = ctx->buf("geig_VR", nn);
+    GW_CUDA(cudaMemcpyAsync(dT, T, sizeof(double) * nn, cudaMemcpyHostToDevice, ctx->stream));
+    GW_CUDA(cudaMemcpyAsync(dB, B, sizeof(double) * nn, cudaMemcpyHostToDevice, ctx->stream));
+    // dT <- B^-1 T
+    int* ipiv = nullptr;
+    lu_factor(ctx, n, dB, n, &ipiv);
+    int* info = reinterpret_cast<int*>(ctx->buf("solver_info", 8));
+    check_solver(cusolverDnDgetrs(ctx->solver, CUBLAS_OP_N, n, n, dB, n, ipiv, dT, n, info), "Dgetrs");
+    cusolverDnParams_t params;
+    check_solver(cusolverDnCreateParams(&params), "CreateParams");
+    size_t wdev = 0, whost = 0;
+    check_solver(cusolverDnXgeev_bufferSize(ctx->solver, params, CUSOLVER_EIG_MODE_NOVECTOR, CUSOLVER_EIG_MODE_VECTOR, n, CUDA_R_64F, dT,
+                       n, CUDA_C_64F, dW, CUDA_R_64F, nullptr, n, CUDA_R_64F, dVR, n, CUDA_R_64F, &wdev, &whost),
+                 "Xgeev_bufferSize");
+    double* dwork = ctx->buf("solver_work", wdev / sizeof(double) + 8);
+    std::vector<unsigned char> hwork(whost + 8);
+    check_solver(cusolverDnXgeev(ctx->solver, params, CUSOLVER_EIG_MODE_NOVECTOR, CUSOLVER_EIG_MODE_VECTOR, n, CUDA_R_64F, dT,
+                        n, CUDA_C_64F, dW, CUDA_R_64F, nullptr, n, CUDA_R_64F, dVR, n, CUDA_R_64F, dwork, wdev,
+                        hwork.data(), whost, info),
+                 "Xgeev");
+    cusolverDnDestroyParams(params);
+    int hinfo = 0;
+    std::vector<double> W(2 * (size_t)n);
+    GW_CUDA(cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    GW_CUDA(cudaMemcpyAsync(W.data(), dW, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    GW_CUDA(cudaMemcpyAsync(VR, dVR, sizeof(double) * nn, cudaMemcpyDeviceToHost, ctx->stream));
+    GW_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (hinfo != 0) throw std::runtime_error("Small generalized eigenvalue problem failed.");
+    for (int i = 0; i < n; ++i) {
+      wr[i] = W[2 * i];
+      wi[i] = W[2 * i + 1];
+    }
+  }
+  GW_API_END(ctx)
+}
+
+}  // extern "C"

@@ -1,0 +1,430 @@
+// C ABI, part 2: the Mmn tensor (TCMatrix_gwbse), RPA dielectric matrix, Sigma_x.
+#include <algorithm>
+#include <vector>
+
+#include "../../include/gwbse_b200.h"
+#include "context.cuh"
+
+using namespace gwbse;
+
+namespace {
+
+inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
+
+void require_mmn(const gwbse_ctx* ctx) { GW_REQUIRE(ctx->X != nullptr, "Mmn not allocated (gwbse_mmn_alloc)"); }
+
+// contraction for a block of aux functions whose AO integrals already sit on the device
+void fill_block_dev(gwbse_ctx* ctx, int aux_offset, int aux_count, const double* ao3c_dev) {
+  require_mmn(ctx);
+  GW_REQUIRE(ctx->mos != nullptr, "MO coefficients not set (gwbse_mmn_set_mos)");
+  GW_REQUIRE(aux_offset >= 0 && aux_offset + aux_count <= ctx->naux, "aux block out of range");
+  const int N = ctx->nbasis;
+  GW_REQUIRE(ctx->mmax < ctx->nmo && ctx->nmax < ctx->nmo, "level range exceeds number of MOs");
+  if (ctx->mlocal == 0 || aux_count == 0) return;
+  const int max_batch = 4096;
+  for (int b0 = 0; b0 < aux_count; b0 += max_batch) {
+    const int nb = std::min(max_batch, aux_count - b0);
+    double* H = ctx->buf("fill_H", (size_t)N * ctx->mlocal * nb);
+    // H_k[nu, ml] = sum_mu T_k[mu, nu] C[mu, m(ml)]      (2 N^2 mlocal flops per aux function)
+    GemmParams p;
+    p.M = N;
+    p.N = ctx->mlocal;
+    p.Ki = N;
+    p.Z1 = nb;
+    p.A.ptr = ao3c_dev + (size_t)b0 * N * N;
+    p.A.s_ri = N;
+    p.A.s_ki = 1;
+    p.A.s_z1 = (long long)N * N;
+    p.B.ptr = ctx->mos + (size_t)(ctx->mmin + ctx->rank) * N;
+    p.B.s_ri = (long long)ctx->world * N;
+    p.B.s_ki = 1;
+    p.C = H;
+    p.sC_mi = 1;
+    p.sC_ni = N;
+    p.sC_z1 = (long long)N * ctx->mlocal;
+    ctx->gemm(p);
+    // M[m](n, k) = sum_nu C[nu, nmin+n] H_k[nu, ml]       (2 n N mlocal flops per aux function)
+    GemmParams q;
+    q.M = ctx->ntotal;
+    q.N = ctx->mlocal;
+    q.Ki = N;
+    q.Z1 = nb;
+    q.A.ptr = ctx->mos + (size_t)ctx->nmin * N;
+    q.A.s_ri = N;
+    q.A.s_ki = 1;
+    q.B.ptr = H;
+    q.B.s_ri = N;
+    q.B.s_ki = 1;
+    q.B.s_z1 = (long long)N * ctx->mlocal;
+    q.C = ctx->X + (long long)(aux_offset + b0) * ctx->ldx;
+    q.sC_mi = 1;
+    q.sC_ni = ctx->npad;
+    q.sC_z1 = ctx->ldx;
+    ctx->gemm(q);
+  }
+}
+
+void mul_right_dev(gwbse_ctx* ctx, const double* R_dev, int ldr) {
+  require_mmn(ctx);
+  if (ctx->ldx == 0) return;
+  GW_REQUIRE(ldr >= ctx->naux, "Shape mismatch in MultiplyRight");
+  if (!ctx->X2) {
+    size_t fr = 0, tot = 0;
+    GW_CUDA(cudaMemGetInfo(&fr, &tot));
+    const size_t bytes = sizeof(double) * (size_t)ctx->ldx * ctx->naux;
+    if (bytes > fr)
+      throw std::runtime_error("There were requested : " + std::to_string((double)bytes / 1048576.0) +
+                               " MB but the device has " + std::to_string((double)fr / 1048576.0) + " MB free.");
+    GW_CUDA(cudaMalloc(&ctx->X2, bytes));
+  }
+  // X2 = X * R as one flat GEMM over all (m, n) rows (padding rows are zero and stay zero)
+  GW_REQUIRE(ctx->ldx < (1LL << 31), "Mmn row count exceeds 2^31");
+  GemmParams p;
+  p.M = (int)ctx->ldx;
+  p.N = ctx->naux;
+  p.Ki = ctx->naux;
+  p.A.ptr = ctx->X;
+  p.A.s_ri = 1;
+  p.A.s_ki = ctx->ldx;
+  p.B.ptr = R_dev;
+  p.B.s_ri = ldr;
+  p.B.s_ki = 1;
+  p.C = ctx->X2;
+  p.sC_mi = 1;
+  p.sC_ni = ctx->ldx;
+  ctx->gemm(p);
+  std::swap(ctx->X, ctx->X2);
+  // evaluators hold pointers into X
+  ctx->sig_ppm.ready = false;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gwbse_mmn_alloc(gwbse_ctx* ctx, int naux, int mmin, int mmax, int nmin, int nmax) {
+  GW_API_BEGIN(ctx)
+  GW_REQUIRE(naux > 0 && mmax >= mmin && nmax >= nmin && mmin >= 0 && nmin >= 0, "invalid Mmn ranges");
+  GW_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (double** p : {&ctx->X, &ctx->X2, &ctx->Xsnap}) {
+    if (*p) GW_CUDA(cudaFree(*p));
+    *p = nullptr;
+  }
+  ctx->naux = naux;
+  ctx->mmin = mmin;
+  ctx->mmax = mmax;
+  ctx->nmin = nmin;
+  ctx->nmax = nmax;
+  ctx->mtotal = mmax - mmin + 1;
+  ctx->ntotal = nmax - nmin + 1;
+  ctx->npad = round_up(ctx->ntotal, 16);
+  ctx->mlocal = ctx->local_count(ctx->mtotal);
+  ctx->ldx = (long long)ctx->mlocal * ctx->npad;
+  const size_t bytes = sizeof(double) * (size_t)std::max<long long>(ctx->ldx, 1) * naux;
+  size_t fr = 0, tot = 0;
+  GW_CUDA(cudaMemGetInfo(&fr, &tot));
+  if (bytes > fr)
+    throw std::runtime_error("There were requested : " + std::to_string((double)bytes / 1048576.0) +
+                             " MB but the device has " + std::to_string((double)fr / 1048576.0) + " MB free.");
+  GW_CUDA(cudaMalloc(&ctx->X, bytes));
+  GW_CUDA(cudaMemsetAsync(ctx->X, 0, bytes, ctx->stream));
+  ctx->sig_ppm.ready = ctx->sig_exact.ready = ctx->bse.ready = false;
+  GW_API_END(ctx)
+}
+
+int gwbse_mmn_free(gwbse_ctx* ctx) {
+  GW_API_BEGIN(ctx)
+  GW_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (double** p : {&ctx->X, &ctx->X2, &ctx->Xsnap}) {
+    if (*p) GW_CUDA(cudaFree(*p));
+    *p = nullptr;
+  }
+  ctx->sig_ppm.ready = ctx->sig_exact.ready = ctx->bse.ready = false;
+  GW_API_END(ctx)
+}
+
+int gwbse_mmn_dims(const gwbse_ctx* ctx, int* naux, int* mtotal, int* ntotal, int* mlocal, int* npad) {
+  if (!ctx) return 1;
+  if (naux) *naux = ctx->naux;
+  if (mtotal) *mtotal = ctx->mtotal;
+  if (ntotal) *ntotal = ctx->ntotal;
+  if (mlocal) *mlocal = ctx->mlocal;
+  if (npad) *npad = ctx->npad;
+  return 0;
+}
+
+int gwbse_mmn_set_mos(gwbse_ctx* ctx, const double* mos, int ldmos, int nbasis, int nmo) {
+  GW_API_BEGIN(ctx)
+  GW_REQUIRE(ldmos >= nbasis && nbasis > 0 && nmo > 0, "invalid MO matrix shape");
+  GW_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ctx->mos) GW_CUDA(cudaFree(ctx->mos));
+  ctx->mos = nullptr;
+  GW_CUDA(cudaMalloc(&ctx->mos, sizeof(double) * (size_t)nbasis * nmo));
+  GW_CUDA(cudaMemcpy2DAsync(ctx->mos, sizeof(double) * nbasis, mos, sizeof(double) * ldmos, sizeof(double) * nbasis,
+                            nmo, cudaMemcpyHostToDevice, ctx->stream));
+  GW_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->nbasis = nbasis;
+  ctx->nmo = nmo;
+  GW_API_END(ctx)
+}
+
+int gwbse_mmn_fill_block_dev(gwbse_ctx* ctx, int aux_offset, int aux_count, const double* ao3c_dev) {
+  GW_API_BEGIN(ctx)
+  fill_block_dev(ctx, aux_offset, aux_count, ao3c_dev);
+  GW_API_END(ctx)
+}
+
+int gwbse_mmn_fill_block(gwbse_ctx* ctx, int aux_offset, int aux_count, const double* ao3c) {
+  GW_API_BEGIN(ctx)
+  const size_t per = (size_t)ctx->nbasis * ctx->nbasis;
+  // stream the block through a bounded staging buffer (<= 1 GiB)
+  const int chunk = (int)std::max<size_t>(1, std::min<size_t>(aux_count, ((size_t)1 << 27) / std::max<size_t>(per, 1)));
+  for (int b0 = 0; b0 < aux_count; b0 += chunk) {
+    const int nb = std::min(chunk, aux_count - b0);
+    double* stage = ctx->buf("fill_ao", per * nb);
+    GW_CUDA(cudaMemcpyAsync(stage, ao3c + (size_t)b0 * per, sizeof(double) * per * nb, cudaMemcpyHostToDevice,
+                            ctx->stream));
+    fill_block_dev(ctx, aux_offset + b0, nb, stage);
+    GW_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  GW_API_END(ctx)
+}
+
+int gwbse_mmn_mul_right_dev(gwbse_ctx* ctx, const double* R_dev, int ldr) {
+  GW_API_BEGIN(ctx)
+  mul_right_dev(ctx, R_dev, ldr);
+  GW_API_END(ctx)
+}
+
+int gwbse_mmn_mul_right(gwbse_ctx* ctx, const double* R, int ldr) {
+  GW_API_BEGIN(ctx)
+  require_mmn(ctx);
+  GW_REQUIRE(ldr >= ctx->naux, "Shape mismatch in MultiplyRight");
+  double* Rd = ctx->buf("mulright_R", (size_t)ctx->naux * ctx->naux);
+  GW_CUDA(cudaMemcpy2DAsync(Rd, sizeof(double) * ctx->naux, R, sizeof(double) * ldr, sizeof(double) * ctx->naux,
+                            ctx->naux, cudaMemcpyHostToDevice, ctx->stream));
+  mul_right_dev(ctx, Rd, ctx->naux);
+  GW_CUDA(cudaStreamSynchronize(ctx->stream));
+  GW_API_END(ctx)
+}
+
+int gwbse_mmn_get_slice(gwbse_ctx* ctx, int m, double* out, int ld) {
+  GW_API_BEGIN(ctx)
+  require_mmn(ctx);
+  GW_REQUIRE(m >= 0 && m < ctx->mtotal && ctx->owns(m), "slice index not owned by this rank");
+  GW_REQUIRE(ld >= ctx->ntotal, "leading dimension too small");
+  const double* src = ctx->X + (long long)ctx->local_index(m) * ctx->npad;
+  GW_CUDA(cudaMemcpy2DAsync(out, sizeof(double) * ld, src, sizeof(double) * ctx->ldx, sizeof(double) * ctx->ntotal,
+                            ctx->naux, cudaMemcpyDeviceToHost, ctx->stream));
+  GW_CUDA(cudaStreamSynchronize(ctx->stream));
+  GW_API_END(ctx)
+}
+
+int gwbse_mmn_set_slice(gwbse_ctx* ctx, int m, const double* in, int ld) {
+  GW_API_BEGIN(ctx)
+  require_mmn(ctx);
+  GW_REQUIRE(m >= 0 && m < ctx->mtotal && ctx->owns(m), "slice index not owned by this rank");
+  GW_REQUIRE(ld >= ctx->ntotal, "leading dimension too small");
+  double* dst = ctx->X + (long long)ctx->local_index(m) * ctx->npad;
+  GW_CUDA(cudaMemcpy2DAsync(dst, sizeof(double) * ctx->ldx, in, sizeof(double) * ld, sizeof(double) * ctx->ntotal,
+                            ctx->naux, cudaMemcpyHostToDevice, ctx->stream));
+  GW_CUDA(cudaStreamSynchronize(ctx->stream));
+  GW_API_END(ctx)
+}
+
+int gwbse_mmn_snapshot(gwbse_ctx* ctx) {
+  GW_API_BEGIN(ctx)
+  require_mmn(ctx);
+  const size_t bytes = sizeof(double) * (size_t)std::max<long long>(ctx->ldx, 1) * ctx->naux;
+  if (!ctx->Xsnap) GW_CUDA(cudaMalloc(&ctx->Xsnap, bytes));
+  GW_CUDA(cudaMemcpyAsync(ctx->Xsnap, ctx->X, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  GW_API_END(ctx)
+}
+
+int gwbse_mmn_restore(gwbse_ctx* ctx) {
+  GW_API_BEGIN(ctx)
+  require_mmn(ctx);
+  GW_REQUIRE(ctx->Xsnap != nullptr, "no Mmn snapshot to restore");
+  const size_t bytes = sizeof(double) * (size_t)std::max<long long>(ctx->ldx, 1) * ctx->naux;
+  GW_CUDA(cudaMemcpyAsync(ctx->X, ctx->Xsnap, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  ctx->sig_ppm.ready = false;
+  GW_API_END(ctx)
+}
+
+// AOCoulomb::Pseudo_InvSqrt_GWBSE, aomatrix.cc:53-86: two symmetric eigensolves + GEMMs
+int gwbse_pseudo_invsqrt(gwbse_ctx* ctx, int n, const double* S, const double* V, double etol, double* L_out,
+                         int* removed) {
+  GW_API_BEGIN(ctx)
+  const size_t nn = (size_t)n * n;
+  double* dS = ctx->buf("pis_S", nn);
+  double* dV = ctx->buf("pis_V", nn);
+  double* dT = ctx->buf("pis_T", nn);
+  double* dSs = ctx->buf("pis_Ss", nn);
+  double* dd = ctx->buf("pis_d", n);
+  int* drem = reinterpret_cast<int*>(ctx->buf("pis_rem", 8));
+  std::vector<double> w(n);
+  GW_CUDA(cudaMemcpyAsync(dS, S, sizeof(double) * nn, cudaMemcpyHostToDevice, ctx->stream));
+  GW_CUDA(cudaMemcpyAsync(dV, V, sizeof(double) * nn, cudaMemcpyHostToDevice, ctx->stream));
+  GW_CUDA(cudaMemsetAsync(drem, 0, sizeof(int), ctx->stream));
+  if (gwbse_sym_eig_dev(ctx, n, dS, n, w.data())) throw std::runtime_error(ctx->err);
+  double* wd = ctx->buf("eig_w", n);  // eigenvalues still on the device
+  launch_invsqrt_scale(dd, wd, n, etol, drem, ctx->stream);
+  // Ssqrt = U diag(d) U^T
+  launch_diag_scale('R', n, n, dS, n, dd, dT, n, ctx->stream);
+  if (gwbse_dgemm_dev(ctx, 'N', 'T', n, n, n, 1.0, dT, n, dS, n, 0.0, dSs, n)) throw std::runtime_error(ctx->err);
+  // ortho = Ssqrt V Ssqrt
+  if (gwbse_dgemm_dev(ctx, 'N', 'N', n, n, n, 1.0, dSs, n, dV, n, 0.0, dT, n)) throw std::runtime_error(ctx->err);
+  if (gwbse_dgemm_dev(ctx, 'N', 'N', n, n, n, 1.0, dT, n, dSs, n, 0.0, dV, n)) throw std::runtime_error(ctx->err);
+  if (gwbse_sym_eig_dev(ctx, n, dV, n, w.data())) throw std::runtime_error(ctx->err);
+  launch_invsqrt_scale(dd, wd, n, etol, drem, ctx->stream);
+  // Vm1 = W diag(d2) W^T ; result = (Vm1 Ssqrt)^T = Ssqrt Vm1  (both symmetric)
+  launch_diag_scale('R', n, n, dV, n, dd, dT, n, ctx->stream);
+  if (gwbse_dgemm_dev(ctx, 'N', 'T', n, n, n, 1.0, dT, n, dV, n, 0.0, dS, n)) throw std::runtime_error(ctx->err);
+  if (gwbse_dgemm_dev(ctx, 'N', 'N', n, n, n, 1.0, dSs, n, dS, n, 0.0, dT, n)) throw std::runtime_error(ctx->err);
+  ctx->launches += 4;
+  int hrem = 0;
+  GW_CUDA(cudaMemcpyAsync(L_out, dT, sizeof(double) * nn, cudaMemcpyDeviceToHost, ctx->stream));
+  GW_CUDA(cudaMemcpyAsync(&hrem, drem, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  GW_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (removed) *removed = hrem;
+  GW_API_END(ctx)
+}
+
+// ------------------------------- RPA ---------------------------------------
+int gwbse_rpa_epsilon(gwbse_ctx* ctx, int kind, double fre, double fim, double eta, const double* energies,
+                      int homo, int rpamin, int rpamax, double* eps_out, int ld) {
+  GW_API_BEGIN(ctx)
+  require_mmn(ctx);
+  GW_REQUIRE(kind >= 0 && kind <= 2, "epsilon kind must be 0 (imag), 1 (real) or 2 (complex)");
+  GW_REQUIRE(rpamin == ctx->mmin && rpamin == ctx->nmin && rpamax == ctx->nmax,
+             "RPA range must match the Mmn n-range and start at mmin");
+  const int n_occ = homo + 1 - rpamin;
+  const int n_unocc = rpamax - homo;
+  GW_REQUIRE(n_occ > 0 && n_unocc > 0 && n_occ <= ctx->mtotal, "invalid occupied/virtual split");
+  const int naux = ctx->naux;
+  if (!ctx->eps) GW_CUDA(cudaMalloc(&ctx->eps, sizeof(double) * (size_t)naux * naux));
+  const int rpatotal = n_occ + n_unocc;
+  double* e_dev = ctx->buf("rpa_e", rpatotal);
+  GW_CUDA(cudaMemcpyAsync(e_dev, energies, sizeof(double) * rpatotal, cudaMemcpyHostToDevice, ctx->stream));
+  const int nloc_occ = ctx->local_count(n_occ);
+  double* w = ctx->buf("rpa_w", (size_t)std::max(nloc_occ, 1) * n_unocc);
+  launch_rpa_weights(w, e_dev, kind, fre, fim, eta, n_occ, n_unocc, ctx->rank, ctx->world, nloc_occ, ctx->stream);
+  ctx->launches++;
+  if (nloc_occ > 0) {
+    GemmParams p;
+    p.M = naux;
+    p.N = naux;
+    p.Ko = nloc_occ;
+    p.Ki = n_unocc;
+    p.A.ptr = ctx->X + n_occ;
+    p.A.s_ri = ctx->ldx;
+    p.A.s_ki = 1;
+    p.A.s_ko = ctx->npad;
+    p.B = p.A;
+    p.C = ctx->eps;
+    p.sC_mi = 1;
+    p.sC_ni = naux;
+    p.alpha = (kind == 2) ? -2.0 : 1.0;
+    p.w = w;
+    p.sW_ko = n_unocc;
+    p.lower_only = 1;
+    ctx->gemm(p);
+    launch_symmetrize_lower(ctx->eps, naux, naux, ctx->stream);
+    ctx->launches++;
+  } else {
+    GW_CUDA(cudaMemsetAsync(ctx->eps, 0, sizeof(double) * (size_t)naux * naux, ctx->stream));
+  }
+  if (ctx->world > 1) {
+    allreduce_dev(ctx, ctx->eps, (size_t)naux * naux);
+  }
+  launch_add_diagonal(ctx->eps, naux, naux, 1.0, ctx->stream);
+  ctx->launches++;
+  if (eps_out) {
+    GW_REQUIRE(ld >= naux, "leading dimension too small");
+    GW_CUDA(cudaMemcpy2DAsync(eps_out, sizeof(double) * ld, ctx->eps, sizeof(double) * naux, sizeof(double) * naux,
+                              naux, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  GW_CUDA(cudaStreamSynchronize(ctx->stream));
+  GW_API_END(ctx)
+}
+
+double* gwbse_rpa_epsilon_ptr(gwbse_ctx* ctx) { return ctx ? ctx->eps : nullptr; }
+
+// (A+B)[v1 c1, v2 c2] = 4 sum_chi M[v1][c1,chi] M[v2][c2,chi] + delta (e_c - e_v), rpa.cc:281-326
+int gwbse_rpa_h2p_apb(gwbse_ctx* ctx, const double* energies, int homo, int rpamin, int rpamax, double* apb_dev,
+                      int ld) {
+  GW_API_BEGIN(ctx)
+  require_mmn(ctx);
+  GW_REQUIRE(ctx->world == 1, "H2p is single-GPU (exact sigma does not scale, SURVEY.md 8e)");
+  GW_REQUIRE(rpamin == ctx->mmin && rpamin == ctx->nmin && rpamax == ctx->nmax, "RPA range must match Mmn");
+  const int n_occ = homo + 1 - rpamin, n_unocc = rpamax - homo;
+  const int S = n_occ * n_unocc;
+  GW_REQUIRE(ld >= S, "leading dimension too small");
+  // rows (v, c): compound index with inner length n_unocc
+  GemmParams p;
+  p.M = S;
+  p.N = S;
+  p.Ki = ctx->naux;
+  p.A.ptr = ctx->X + n_occ;
+  p.A.Lr = n_unocc;
+  p.A.s_ri = 1;
+  p.A.s_ro = ctx->npad;
+  p.A.s_ki = ctx->ldx;
+  p.B = p.A;
+  p.C = apb_dev;
+  p.sC_mi = 1;
+  p.sC_ni = ld;
+  p.alpha = 4.0;
+  p.lower_only = 1;
+  ctx->gemm(p);
+  launch_symmetrize_lower(apb_dev, S, ld, ctx->stream);
+  // + diag(AmB)
+  std::vector<double> amb(S);
+  for (int v = 0; v < n_occ; ++v)
+    for (int c = 0; c < n_unocc; ++c) amb[(size_t)v * n_unocc + c] = energies[n_occ + c] - energies[v];
+  double* d = ctx->buf("h2p_amb", S);
+  GW_CUDA(cudaMemcpyAsync(d, amb.data(), sizeof(double) * S, cudaMemcpyHostToDevice, ctx->stream));
+  // axpy on the diagonal viewed as a strided vector: 1 x S block with ld+1 stride
+  launch_axpy(1, S, 1.0, d, 1, apb_dev, (long long)ld + 1, ctx->stream);
+  ctx->launches += 2;
+  GW_CUDA(cudaStreamSynchronize(ctx->stream));
+  GW_API_END(ctx)
+}
+
+// ------------------------------ Sigma_x -------------------------------------
+int gwbse_sigma_x(gwbse_ctx* ctx, int homo, int rpamin, int qpmin, int qpmax, double* out, int ld) {
+  GW_API_BEGIN(ctx)
+  require_mmn(ctx);
+  GW_REQUIRE(ctx->world == 1, "gwbse_sigma_x: multi-GPU path uses gwbse_sigma_x after gathering (not built yet)");
+  GW_REQUIRE(rpamin == ctx->mmin && rpamin == ctx->nmin, "RPA range must match Mmn");
+  const int q = qpmax - qpmin + 1;
+  const int occ = homo - rpamin + 1;
+  const int qpoff = qpmin - rpamin;
+  GW_REQUIRE(q > 0 && qpoff >= 0 && qpoff + q <= ctx->mtotal && occ > 0 && occ <= ctx->ntotal, "invalid qp window");
+  GW_REQUIRE(ld >= q, "leading dimension too small");
+  double* sx = ctx->buf("sigma_x", (size_t)q * q);
+  GemmParams p;
+  p.M = q;
+  p.N = q;
+  p.Ko = ctx->naux;
+  p.Ki = occ;
+  p.A.ptr = ctx->X + (long long)qpoff * ctx->npad;
+  p.A.s_ri = ctx->npad;
+  p.A.s_ki = 1;
+  p.A.s_ko = ctx->ldx;
+  p.B = p.A;
+  p.C = sx;
+  p.sC_mi = 1;
+  p.sC_ni = q;
+  p.alpha = -1.0;
+  p.lower_only = 1;
+  ctx->gemm(p);
+  launch_symmetrize_lower(sx, q, q, ctx->stream);
+  ctx->launches++;
+  GW_CUDA(cudaMemcpy2DAsync(out, sizeof(double) * ld, sx, sizeof(double) * q, sizeof(double) * q, q,
+                            cudaMemcpyDeviceToHost, ctx->stream));
+  GW_CUDA(cudaStreamSynchronize(ctx->stream));
+  GW_API_END(ctx)
+}
+
+}  // extern "C"

@@ -1,0 +1,223 @@
+// C ABI, part 3: Sigma_c evaluators (PPM and exact), batched over (level, frequency).
+#include <algorithm>
+#include <vector>
+
+#include "../../include/gwbse_b200.h"
+#include "context.cuh"
+
+using namespace gwbse;
+
+namespace {
+
+void upload(gwbse_ctx* ctx, double** dst, const double* src, size_t n) {
+  if (*dst) GW_CUDA(cudaFree(*dst));
+  *dst = nullptr;
+  GW_CUDA(cudaMalloc(dst, sizeof(double) * std::max<size_t>(n, 1)));
+  GW_CUDA(cudaMemcpyAsync(*dst, src, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+}
+
+void sigma_eval(gwbse_ctx* ctx, gwbse_ctx::SigmaState& st, int nreq, const int* levels, const double* freqs,
+                double* sigma, double* dsigma) {
+  GW_REQUIRE(st.ready, "sigma evaluator not prepared");
+  if (nreq <= 0) return;
+  for (int i = 0; i < nreq; ++i)
+    GW_REQUIRE(levels[i] >= 0 && levels[i] < st.q, "gw_level out of range");
+  int* lev_d = reinterpret_cast<int*>(ctx->buf("sig_levels", (size_t)nreq / 2 + 8));
+  double* frq_d = ctx->buf("sig_freqs", nreq);
+  GW_CUDA(cudaMemcpyAsync(lev_d, levels, sizeof(int) * nreq, cudaMemcpyHostToDevice, ctx->stream));
+  GW_CUDA(cudaMemcpyAsync(frq_d, freqs, sizeof(double) * nreq, cudaMemcpyHostToDevice, ctx->stream));
+  int nsplit = (4 * ctx->num_sms + nreq - 1) / nreq;
+  nsplit = std::max(1, std::min(nsplit, std::min(64, std::max(1, st.npoles / 8))));
+  double* partial = ctx->buf("sig_partial", (size_t)nreq * nsplit * 2);
+  double* out = ctx->buf("sig_out", (size_t)nreq * 2);
+  launch_sigma_eval(st, ctx->ntotal, nreq, lev_d, frq_d, partial, nsplit, dsigma != nullptr, ctx->stream);
+  launch_sigma_eval_reduce(partial, nreq, nsplit, dsigma != nullptr, out, ctx->stream);
+  ctx->launches += 2;
+  GW_CUDA(cudaMemcpyAsync(sigma, out, sizeof(double) * nreq, cudaMemcpyDeviceToHost, ctx->stream));
+  if (dsigma)
+    GW_CUDA(cudaMemcpyAsync(dsigma, out + nreq, sizeof(double) * nreq, cudaMemcpyDeviceToHost, ctx->stream));
+  GW_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+// Off-diagonal Sigma_c for all level pairs as a weighted GEMM:
+//   S[i,j] = sum_{p,n} (pref fac_p g(w_i - e_n +- pole_p) M_i[n,p]) M_j[n,p],  Sigma_c[i,j] = S[i,j] + S[j,i]
+// sigma_ppm.cc:93-126 / sigma_exact.cc:85-107 evaluate the same sum pair by pair.
+void sigma_offdiag(gwbse_ctx* ctx, gwbse_ctx::SigmaState& st, double pref, int q, const double* freqs, double* out,
+                   int ld) {
+  GW_REQUIRE(st.ready, "sigma evaluator not prepared");
+  GW_REQUIRE(q == st.q && ld >= q, "q does not match the prepared evaluator");
+  double* frq_d = ctx->buf("sig_freqs", q);
+  GW_CUDA(cudaMemcpyAsync(frq_d, freqs, sizeof(double) * q, cudaMemcpyHostToDevice, ctx->stream));
+  const int npad = (int)st.lstride;
+  const long long ldo = (long long)q * npad;
+  const size_t budget = (size_t)1 << 25;  // doubles (256 MiB)
+  const int chunk = (int)std::max<size_t>(1, std::min<size_t>(std::min(st.npoles, 65535), budget / (size_t)ldo));
+  double* A = ctx->buf("sig_offdiag_A", (size_t)ldo * chunk);
+  double* S = ctx->buf("sig_offdiag_S", (size_t)q * q * 2);
+  for (int p0 = 0, it = 0; p0 < st.npoles; p0 += chunk, ++it) {
+    const int np = std::min(chunk, st.npoles - p0);
+    launch_sigma_offdiag_weight(st, ctx->ntotal, npad, q, p0, np, frq_d, pref, A, ldo, ctx->stream);
+    ctx->launches++;
+    GemmParams p;
+    p.M = q;
+    p.N = q;
+    p.Ko = np;
+    p.Ki = ctx->ntotal;
+    p.A.ptr = A;
+    p.A.s_ri = npad;
+    p.A.s_ki = 1;
+    p.A.s_ko = ldo;
+    p.B.ptr = st.mat + (long long)st.qpoff * st.lstride + (long long)p0 * st.ld;
+    p.B.s_ri = st.lstride;
+    p.B.s_ki = 1;
+    p.B.s_ko = st.ld;
+    p.C = S;
+    p.sC_mi = 1;
+    p.sC_ni = q;
+    p.beta = it == 0 ? 0.0 : 1.0;
+    ctx->gemm(p);
+  }
+  launch_offdiag_finish(S, q, S + (size_t)q * q, ctx->stream);
+  ctx->launches++;
+  GW_CUDA(cudaMemcpy2DAsync(out, sizeof(double) * ld, S + (size_t)q * q, sizeof(double) * q, sizeof(double) * q, q,
+                            cudaMemcpyDeviceToHost, ctx->stream));
+  GW_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+}  // namespace
+
+extern "C" {
+
+int gwbse_sigma_ppm_set(gwbse_ctx* ctx, const double* ppm_weight, const double* ppm_freq, const double* energies,
+                        int homo, int rpamin, int qpmin, double eta) {
+  GW_API_BEGIN(ctx)
+  GW_REQUIRE(ctx->X != nullptr, "Mmn not allocated");
+  GW_REQUIRE(ctx->world == 1, "sigma evaluators are single-GPU in this build");
+  auto& st = ctx->sig_ppm;
+  const int naux = ctx->naux;
+  std::vector<double> fac(naux);
+  for (int i = 0; i < naux; ++i)  // sigma_ppm.cc:47-52: weights below 1e-9 are skipped
+    fac[i] = (ppm_weight[i] < 1.e-9) ? 0.0 : ppm_weight[i] * ppm_freq[i];
+  upload(ctx, &st.fac, fac.data(), naux);
+  upload(ctx, &st.pole, ppm_freq, naux);
+  upload(ctx, &st.energies, energies, ctx->ntotal);
+  st.npoles = naux;
+  st.nocc_boundary = homo + 1;  // sigma_ppm.cc:40,56-57 uses lumo = homo + 1 unshifted
+  st.qpoff = qpmin - rpamin;
+  st.q = ctx->mtotal - st.qpoff;
+  st.eta = eta;
+  st.diag_pref = 0.5;
+  st.mat = ctx->X;
+  st.ld = ctx->ldx;
+  st.lstride = ctx->npad;
+  st.ready = true;
+  GW_CUDA(cudaStreamSynchronize(ctx->stream));
+  GW_API_END(ctx)
+}
+
+int gwbse_sigma_ppm_eval(gwbse_ctx* ctx, int nreq, const int* levels, const double* freqs, double* sigma,
+                         double* dsigma) {
+  GW_API_BEGIN(ctx)
+  ctx->sig_ppm.mat = ctx->X;
+  sigma_eval(ctx, ctx->sig_ppm, nreq, levels, freqs, sigma, dsigma);
+  GW_API_END(ctx)
+}
+
+int gwbse_sigma_ppm_offdiag(gwbse_ctx* ctx, int q, const double* freqs, double* out, int ld) {
+  GW_API_BEGIN(ctx)
+  ctx->sig_ppm.mat = ctx->X;
+  const int qsave = ctx->sig_ppm.q;
+  ctx->sig_ppm.q = q;
+  try {
+    sigma_offdiag(ctx, ctx->sig_ppm, 0.25, q, freqs, out, ld);
+  } catch (...) {
+    ctx->sig_ppm.q = qsave;
+    throw;
+  }
+  ctx->sig_ppm.q = qsave;
+  GW_API_END(ctx)
+}
+
+int gwbse_sigma_exact_prepare(gwbse_ctx* ctx, const double* rpa_omegas, const double* XpY_dev, int ldxpy,
+                              const double* energies, int homo, int rpamin, int rpamax, int qpmin, int qpmax,
+                              double eta) {
+  GW_API_BEGIN(ctx)
+  GW_REQUIRE(ctx->X != nullptr, "Mmn not allocated");
+  GW_REQUIRE(ctx->world == 1, "exact sigma is single-GPU (SURVEY.md 8e)");
+  GW_REQUIRE(rpamin == ctx->mmin && rpamin == ctx->nmin && rpamax == ctx->nmax, "RPA range must match Mmn");
+  const int n_occ = homo + 1 - rpamin, n_unocc = rpamax - homo;
+  const int S = n_occ * n_unocc;
+  const int q = qpmax - qpmin + 1, qpoff = qpmin - rpamin;
+  const int naux = ctx->naux, npad = ctx->npad;
+  GW_REQUIRE(ldxpy >= S && q > 0 && qpoff >= 0 && qpoff + q <= ctx->mtotal, "invalid sizes");
+  // Z[chi, s] = sum_{v,c} M[v][c,chi] XpY[(v,c), s]
+  double* Z = ctx->buf("exact_Z", (size_t)naux * S);
+  GemmParams p;
+  p.M = naux;
+  p.N = S;
+  p.Ko = n_occ;
+  p.Ki = n_unocc;
+  p.A.ptr = ctx->X + n_occ;
+  p.A.s_ri = ctx->ldx;
+  p.A.s_ki = 1;
+  p.A.s_ko = npad;
+  p.B.ptr = XpY_dev;
+  p.B.s_ri = ldxpy;
+  p.B.s_ki = 1;
+  p.B.s_ko = n_unocc;
+  p.C = Z;
+  p.sC_mi = 1;
+  p.sC_ni = naux;
+  ctx->gemm(p);
+  // R[(i,n), s] = sum_chi M_i[n,chi] Z[chi,s]
+  const long long ldr = (long long)q * npad;
+  if (ctx->exact_res) GW_CUDA(cudaFree(ctx->exact_res));
+  ctx->exact_res = nullptr;
+  GW_CUDA(cudaMalloc(&ctx->exact_res, sizeof(double) * (size_t)ldr * S));
+  GemmParams r;
+  r.M = (int)ldr;
+  r.N = S;
+  r.Ki = naux;
+  r.A.ptr = ctx->X + (long long)qpoff * npad;
+  r.A.s_ri = 1;
+  r.A.s_ki = ctx->ldx;
+  r.B.ptr = Z;
+  r.B.s_ri = naux;
+  r.B.s_ki = 1;
+  r.C = ctx->exact_res;
+  r.sC_mi = 1;
+  r.sC_ni = ldr;
+  ctx->gemm(r);
+  auto& st = ctx->sig_exact;
+  std::vector<double> fac(S, 1.0);
+  upload(ctx, &st.fac, fac.data(), S);
+  upload(ctx, &st.pole, rpa_omegas, S);
+  upload(ctx, &st.energies, energies, ctx->ntotal);
+  st.npoles = S;
+  st.nocc_boundary = n_occ;
+  st.qpoff = 0;
+  st.q = q;
+  st.eta = eta;
+  st.diag_pref = 2.0;
+  st.mat = ctx->exact_res;
+  st.ld = ldr;
+  st.lstride = npad;
+  st.ready = true;
+  GW_CUDA(cudaStreamSynchronize(ctx->stream));
+  GW_API_END(ctx)
+}
+
+int gwbse_sigma_exact_eval(gwbse_ctx* ctx, int nreq, const int* levels, const double* freqs, double* sigma,
+                           double* dsigma) {
+  GW_API_BEGIN(ctx)
+  sigma_eval(ctx, ctx->sig_exact, nreq, levels, freqs, sigma, dsigma);
+  GW_API_END(ctx)
+}
+
+int gwbse_sigma_exact_offdiag(gwbse_ctx* ctx, int q, const double* freqs, double* out, int ld) {
+  GW_API_BEGIN(ctx)
+  sigma_offdiag(ctx, ctx->sig_exact, 1.0, q, freqs, out, ld);
+  GW_API_END(ctx)
+}
+
+}  // extern "C"

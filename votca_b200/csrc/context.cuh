@@ -1,0 +1,145 @@
+// Internal state of a gwbse_ctx (one per process / GPU).
+#pragma once
+#include <cuda_runtime.h>
+#include <cusolverDn.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "gemm_dmma.cuh"
+
+struct DevBuf {
+  double* p = nullptr;
+  size_t cap = 0;  // doubles
+};
+
+struct gwbse_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int num_sms = 148;
+  std::string err;
+  cusolverDnHandle_t solver = nullptr;
+  long long launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+  // multi-GPU
+  int rank = 0, world = 1;
+  void* nccl_comm = nullptr;
+
+  // named grow-only device scratch buffers
+  std::map<std::string, DevBuf> bufs;
+
+  // ---- Mmn ----
+  int naux = 0, mmin = 0, mmax = -1, nmin = 0, nmax = -1;
+  int mtotal = 0, ntotal = 0, npad = 0, mlocal = 0;
+  long long ldx = 0;
+  double* X = nullptr;      // current Mmn
+  double* X2 = nullptr;     // out-of-place target of MultiplyRight
+  double* Xsnap = nullptr;  // pristine copy for Rebuild
+  double* mos = nullptr;    // MO coefficients on device (nbasis x nmo)
+  int nbasis = 0, nmo = 0;
+
+  // ---- RPA ----
+  double* eps = nullptr;  // naux x naux
+
+  // ---- Sigma_c evaluators (shared kernel: poles x levels) ----
+  struct SigmaState {
+    bool ready = false;
+    int npoles = 0;        // naux (ppm) or rpasize (exact)
+    int nocc_boundary = 0;  // rows [0, boundary) take +pole, the rest -pole
+    int qpoff = 0;          // first qp level in Mmn storage index
+    int q = 0;
+    double eta = 0.0;
+    double diag_pref = 1.0;  // multiplies fac[] for the diagonal element
+    const double* mat = nullptr;  // matrix holding level blocks: element (level l, n, pole p) at mat[p*ld + l*lstride + n]
+    long long ld = 0, lstride = 0;
+    double* fac = nullptr;     // per pole prefactor (device)
+    double* pole = nullptr;    // per pole frequency (device)
+    double* energies = nullptr;  // ntotal (device)
+  } sig_ppm, sig_exact;
+  double* exact_res = nullptr;  // residues (q*npad) x S
+
+  // ---- BSE ----
+  struct BseState {
+    bool ready = false;
+    int homo = 0, rpamin = 0, vmin = 0, cmax = 0;
+    int vt = 0, ct = 0, size = 0;
+    int voff = 0, coff = 0;  // vmin - rpamin, cmin - rpamin (rows / slices of Mmn)
+    double* eps_inv = nullptr;  // naux (device)
+    double* hqp = nullptr;      // (vt+ct)^2 device, ld = vt+ct
+    std::vector<double> hqp_host;
+    std::vector<double> eps_inv_host;
+  } bse;
+  size_t bse_chunk_bytes = (size_t)1 << 30;  // size of the Hd intermediate per chunk
+
+  double* buf(const std::string& name, size_t n) {
+    DevBuf& b = bufs[name];
+    if (b.cap < n) {
+      if (b.p) GW_CUDA(cudaFree(b.p));
+      b.p = nullptr;
+      b.cap = 0;
+      GW_CUDA(cudaMalloc(&b.p, sizeof(double) * n));
+      b.cap = n;
+    }
+    return b.p;
+  }
+  void gemm(const gwbse::GemmParams& p, int cfg = -1, int splitk = 0);
+  bool owns(int m) const { return (m % world) == rank; }
+  int local_index(int m) const { return m / world; }
+  // number of local levels with global storage index in [0, upto)
+  int local_count(int upto) const { return upto <= rank ? 0 : (upto - rank + world - 1) / world; }
+};
+
+#define GW_API_BEGIN(ctx) \
+  if (!(ctx)) return 1;   \
+  try {                   \
+    GW_CUDA(cudaSetDevice((ctx)->device));
+#define GW_API_END(ctx)               \
+  return 0;                           \
+  }                                   \
+  catch (const std::exception& e) {   \
+    (ctx)->err = e.what();            \
+    return 1;                         \
+  }                                   \
+  catch (...) {                       \
+    (ctx)->err = "unknown exception"; \
+    return 1;                         \
+  }
+
+namespace gwbse {
+// NCCL plumbing (comm.cu)
+void allreduce_dev(gwbse_ctx* ctx, double* buf_dev, size_t n);
+void allgather_dev(gwbse_ctx* ctx, const double* send_dev, double* recv_dev, size_t n_per_rank);
+// streaming kernels (streaming.cu)
+void launch_symmetrize_lower(double* A, int n, long long ld, cudaStream_t s);
+void launch_add_diagonal(double* A, int n, long long ld, double v, cudaStream_t s);
+void launch_rpa_weights(double* w, const double* e, int kind, double fre, double fim, double eta, int n_occ,
+                        int n_unocc, int rank, int world, int nloc_occ, cudaStream_t s);
+void launch_diag_scale(char side, int m, int n, const double* A, long long lda, const double* d, double* C,
+                       long long ldc, cudaStream_t s);
+void launch_axpy(int m, int n, double alpha, const double* X, long long ldx, double* Y, long long ldy,
+                 cudaStream_t s);
+void launch_colnorms(int m, int n, const double* A, long long lda, double* out_dev, cudaStream_t s);
+void launch_coldots(int m, int n, const double* X, long long ldx, const double* Y, long long ldy, double* out_dev,
+                    cudaStream_t s);
+void launch_scale_cols(int m, int n, double* A, long long lda, const double* s_dev, cudaStream_t s);
+void launch_copy_block(int m, int n, const double* A, long long lda, double* B, long long ldb, cudaStream_t s);
+void launch_invsqrt_scale(double* out, const double* w, int n, double etol, int* removed_dev, cudaStream_t s);
+void launch_sigma_eval(const gwbse_ctx::SigmaState& st, int ntotal, int nreq, const int* levels_dev,
+                       const double* freqs_dev, double* partial_dev, int nsplit, bool want_deriv, cudaStream_t s);
+void launch_sigma_eval_reduce(const double* partial_dev, int nreq, int nsplit, bool want_deriv, double* out_dev,
+                              cudaStream_t s);
+void launch_sigma_offdiag_weight(const gwbse_ctx::SigmaState& st, int ntotal, int npad, int q, int p0, int np,
+                                 const double* freqs_dev, double pref, double* out, long long ldo, cudaStream_t s);
+void launch_offdiag_finish(const double* S, int q, double* out, cudaStream_t s);
+void launch_bse_diag(const double* X, long long ldx, int npad, int naux, int vt, int ct, int voff, int coff,
+                     const double* eps_inv, const double* hqp, int ldh, int cqp, int cx, int cd, int cd2,
+                     double* out, cudaStream_t s);
+void launch_dpr(int rows, int ncols, const double* diag, const double* lambda_dev, const double* R, long long ldr,
+                double* W, long long ldw, cudaStream_t s);
+void launch_olsen_finish(int rows, int ncols, const double* diag, const double* lambda_dev, const double* Q,
+                         long long ldq, const double* num_dev, const double* den_dev, double* W, long long ldw,
+                         cudaStream_t s);
+}  // namespace gwbse

@@ -1,0 +1,193 @@
+// Launcher + instantiations of the FP64 DMMA GEMM (see gemm_dmma.cuh).
+#include <algorithm>
+#include <cstdint>
+
+#include "gemm_dmma.cuh"
+
+namespace gwbse {
+
+namespace {
+
+struct Cfg {
+  int BM, BN, occ;
+};
+constexpr Cfg kCfg[3] = {{128, 128, 1}, {128, 32, 2}, {64, 64, 2}};
+
+template <int BM, int BN, int WGM, int WGN, int STAGES, int MINB, bool AK, bool BKM, bool HASW>
+void launch_one(const GemmParams& p, dim3 grid, cudaStream_t stream) {
+  using SM = GemmSmem<BM, BN, STAGES, HASW>;
+  auto kern = gemm_dmma_kernel<BM, BN, WGM, WGN, STAGES, MINB, AK, BKM, HASW>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::bytes));
+    attr_set = true;
+  }
+  kern<<<grid, WGM * WGN * 32, SM::bytes, stream>>>(p);
+  GW_CUDA(cudaGetLastError());
+}
+
+template <int BM, int BN, int WGM, int WGN, int STAGES, int MINB>
+void launch_cfg(const GemmParams& p, dim3 grid, bool ak, bool bk, cudaStream_t stream) {
+  const bool hasw = p.w != nullptr;
+  if (hasw) {
+    GW_REQUIRE(ak, "weighted GEMM needs a K-major A operand");
+    if (bk)
+      launch_one<BM, BN, WGM, WGN, STAGES, MINB, true, true, true>(p, grid, stream);
+    else
+      launch_one<BM, BN, WGM, WGN, STAGES, MINB, true, false, true>(p, grid, stream);
+    return;
+  }
+  if (ak && bk)
+    launch_one<BM, BN, WGM, WGN, STAGES, MINB, true, true, false>(p, grid, stream);
+  else if (ak && !bk)
+    launch_one<BM, BN, WGM, WGN, STAGES, MINB, true, false, false>(p, grid, stream);
+  else if (!ak && bk)
+    launch_one<BM, BN, WGM, WGN, STAGES, MINB, false, true, false>(p, grid, stream);
+  else
+    launch_one<BM, BN, WGM, WGN, STAGES, MINB, false, false, false>(p, grid, stream);
+}
+
+bool is_kmajor(const GemmOperand& op, int Ki) {
+  if (op.s_ki == 1) return true;
+  if (op.s_ri == 1) return false;
+  GW_REQUIRE(Ki == 1, "GEMM operand needs a unit stride along k or along its row index");
+  return true;
+}
+
+int deduce_vec(const GemmOperand& op, bool kmajor, int rows) {
+  auto even = [](long long v) { return (v & 1LL) == 0; };
+  if (reinterpret_cast<uintptr_t>(op.ptr) % 16 != 0) return 1;
+  if (!even(op.s_ko) || !even(op.s_z1) || !even(op.s_z2)) return 1;
+  const bool flat = op.Lr >= rows;
+  if (!flat && !even(op.s_ro)) return 1;
+  if (kmajor) {
+    if (!even(op.s_ri)) return 1;
+  } else {
+    if (!even(op.s_ki)) return 1;
+    if (!flat && (op.Lr & 1)) return 1;
+  }
+  return 2;
+}
+
+struct Plan {
+  int cfg, splitk, tiles_m, tiles_n;
+  bool swap;
+};
+
+Plan make_plan(const GemmParams& p, int num_sms, int force_cfg, int force_splitk) {
+  Plan pl{};
+  pl.swap = false;
+  int M = p.M, N = p.N;
+  if (force_cfg < 0 && !p.w && !p.nscale && !p.lower_only && M <= 32 && N > 32) {
+    pl.swap = true;
+    std::swap(M, N);
+  }
+  int cfg = force_cfg;
+  if (cfg < 0) {
+    if (N <= 32)
+      cfg = 1;
+    else if (M <= 64 || N <= 64 || ((long long)ceil_div(M, 128) * ceil_div(N, 128) * p.Z1 * p.Z2 < num_sms / 2 &&
+                                    (long long)p.Ko * p.Ki < 2048))
+      cfg = 2;
+    else
+      cfg = 0;
+  }
+  pl.cfg = cfg;
+  pl.tiles_m = ceil_div(M, kCfg[cfg].BM);
+  pl.tiles_n = ceil_div(N, kCfg[cfg].BN);
+  long long tiles = (long long)pl.tiles_m * pl.tiles_n;
+  if (p.lower_only) tiles = (tiles + pl.tiles_m) / 2;
+  tiles *= (long long)p.Z1 * p.Z2;
+  const long long T_total = (long long)p.Ko * ceil_div(p.Ki, GEMM_BK);
+  int splitk = force_splitk;
+  if (splitk <= 0) {
+    const long long target = (long long)num_sms * kCfg[cfg].occ;
+    splitk = 1;
+    if (tiles < target) {
+      long long want = ceil_div(2 * target, tiles);
+      long long cap = std::max<long long>(1, T_total / 8);
+      splitk = (int)std::max<long long>(1, std::min<long long>(std::min(want, cap), 64));
+    }
+  }
+  splitk = (int)std::min<long long>(splitk, std::max<long long>(1, T_total));
+  pl.splitk = splitk;
+  return pl;
+}
+
+GemmParams apply_swap(GemmParams p) {
+  std::swap(p.A, p.B);
+  std::swap(p.M, p.N);
+  std::swap(p.sC_mi, p.sC_ni);
+  std::swap(p.sC_mo, p.sC_no);
+  std::swap(p.Lm, p.Ln);
+  return p;
+}
+
+}  // namespace
+
+size_t gemm_ws_bytes_needed(const GemmParams& p, int num_sms, int force_cfg, int force_splitk) {
+  Plan pl = make_plan(p, num_sms, force_cfg, force_splitk);
+  if (pl.splitk <= 1) return 0;
+  return sizeof(double) * (size_t)pl.tiles_m * kCfg[pl.cfg].BM * pl.tiles_n * kCfg[pl.cfg].BN * pl.splitk * p.Z1 *
+         p.Z2;
+}
+
+void gemm_launch(GemmParams p, cudaStream_t stream, double* ws, size_t ws_bytes, int num_sms, int force_cfg,
+                 int force_splitk) {
+  if (p.M <= 0 || p.N <= 0 || p.Z1 <= 0 || p.Z2 <= 0) return;
+  GW_REQUIRE(p.Ko >= 1 && p.Ki >= 0, "bad K extents");
+  Plan pl = make_plan(p, num_sms, force_cfg, force_splitk);
+  if (pl.swap) p = apply_swap(p);
+  const bool ak = is_kmajor(p.A, p.Ki), bk = is_kmajor(p.B, p.Ki);
+  p.A.vec = deduce_vec(p.A, ak, p.M);
+  p.B.vec = deduce_vec(p.B, bk, p.N);
+  p.tiles_m = pl.tiles_m;
+  p.tiles_n = pl.tiles_n;
+  p.splitk = pl.splitk;
+  if (pl.splitk > 1) {
+    const size_t need = sizeof(double) * (size_t)pl.tiles_m * kCfg[pl.cfg].BM * pl.tiles_n * kCfg[pl.cfg].BN *
+                        pl.splitk * p.Z1 * p.Z2;
+    if (ws == nullptr || need > ws_bytes) {
+      // fall back to fewer splits that fit (or none)
+      const size_t per = need / pl.splitk;
+      int fit = per ? (int)(ws_bytes / per) : 0;
+      p.splitk = pl.splitk = std::max(1, std::min(pl.splitk, ws ? fit : 1));
+    }
+    p.ws = ws;
+  }
+  const long long gz = (long long)p.Z1 * p.Z2 * p.splitk;
+  GW_REQUIRE(gz <= 65535 && pl.tiles_n <= 65535, "GEMM grid too large (batch or N tiles)");
+  dim3 grid(pl.tiles_m, pl.tiles_n, (unsigned)gz);
+  switch (pl.cfg) {
+    case 0:
+      launch_cfg<128, 128, 2, 4, 4, 1>(p, grid, ak, bk, stream);
+      break;
+    case 1:
+      launch_cfg<128, 32, 4, 1, 4, 2>(p, grid, ak, bk, stream);
+      break;
+    default:
+      launch_cfg<64, 64, 2, 2, 4, 2>(p, grid, ak, bk, stream);
+      break;
+  }
+  if (p.splitk > 1) {
+    dim3 rb(128);
+    dim3 rg(ceil_div(p.M, 128), p.N, p.Z1 * p.Z2);
+    GW_REQUIRE(p.N <= 65535 && p.Z1 * p.Z2 <= 65535, "split-K reduce grid too large");
+    switch (pl.cfg) {
+      case 0:
+        gemm_splitk_reduce_kernel<128, 128><<<rg, rb, 0, stream>>>(p);
+        break;
+      case 1:
+        gemm_splitk_reduce_kernel<128, 32><<<rg, rb, 0, stream>>>(p);
+        break;
+      default:
+        gemm_splitk_reduce_kernel<64, 64><<<rg, rb, 0, stream>>>(p);
+        break;
+    }
+    GW_CUDA(cudaGetLastError());
+  }
+}
+
+void gemm_init_attributes() {}
+
+}  // namespace gwbse

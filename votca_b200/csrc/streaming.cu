@@ -1,0 +1,377 @@
+// Streaming (HBM-bound) kernels of the GW-BSE path: coalesced, vectorised where
+// alignment allows, warp-shuffle reductions.  SURVEY.md section 8a rows a7 (weights),
+// a12/a14 (Sigma_c evaluation), a18 (BSE diagonal), a20 (Davidson corrections).
+#include <cmath>
+
+#include "context.cuh"
+
+namespace gwbse {
+
+namespace {
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum; result valid in thread 0.  blockDim.x multiple of 32, <= 1024.
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  const int nw = blockDim.x >> 5;
+  v = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.0;
+  if (w == 0) v = warp_sum(v);
+  __syncthreads();
+  return v;
+}
+
+__global__ void symmetrize_lower_kernel(double* A, int n, long long ld) {
+  __shared__ double tile[32][33];
+  const int tr = blockIdx.y, tc = blockIdx.x;  // destination tile (rows tr, cols tc), upper part: tc >= tr
+  if (tc < tr) return;
+  // source: lower tile rows tc*32.., cols tr*32..
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = tc * 32 + threadIdx.x, c = tr * 32 + j;
+    tile[j][threadIdx.x] = (r < n && c < n) ? A[r + (long long)c * ld] : 0.0;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = tr * 32 + threadIdx.x, c = tc * 32 + j;  // dest element (r, c) = source (c, r)
+    if (r < n && c < n && c > r) A[r + (long long)c * ld] = tile[threadIdx.x][j];
+  }
+}
+
+__global__ void add_diagonal_kernel(double* A, int n, long long ld, double v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) A[i + (long long)i * ld] += v;
+}
+
+// RPA transition weights, rpa.cc:115-127 (imag / real) and rpa.cc:178-190 (complex)
+__global__ void rpa_weights_kernel(double* w, const double* e, int kind, double fre, double fim, double eta,
+                                   int n_occ, int n_unocc, int rank, int world) {
+  const int ml = blockIdx.y;
+  const int v = rank + ml * world;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_unocc || v >= n_occ) return;
+  const double dE = e[n_occ + c] - e[v];
+  double d;
+  if (kind == 0) {
+    d = 4.0 * dE / (dE * dE + fre * fre);
+  } else if (kind == 1) {
+    const double eta2 = eta * eta;
+    const double dm = dE - fre, dp = dE + fre;
+    d = 2.0 * (dm / (dm * dm + eta2) + dp / (dp * dp + eta2));
+  } else {
+    const double dm = fre - dE, dp = fre + dE;
+    const double s1 = (fim + eta) * (fim + eta), s2 = (fim - eta) * (fim - eta);
+    d = dm / (dm * dm + s1) - dp / (dp * dp + s2);
+  }
+  w[(long long)ml * n_unocc + c] = d;
+}
+
+__global__ void diag_scale_kernel(int side_right, int m, int n, const double* A, long long lda, const double* d,
+                                  double* C, long long ldc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y;
+  if (i < m && j < n) C[i + j * ldc] = A[i + j * lda] * (side_right ? d[j] : d[i]);
+}
+
+__global__ void axpy_kernel(int m, int n, double alpha, const double* X, long long ldx, double* Y, long long ldy) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y;
+  if (i < m && j < n) Y[i + j * ldy] += alpha * X[i + j * ldx];
+}
+
+__global__ void coldots_kernel(int m, const double* X, long long ldx, const double* Y, long long ldy, double* out,
+                               int take_sqrt) {
+  __shared__ double sh[32];
+  const int j = blockIdx.x;
+  const double* x = X + j * ldx;
+  const double* y = Y + j * ldy;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) s += x[i] * y[i];
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) out[j] = take_sqrt ? sqrt(s) : s;
+}
+
+__global__ void scale_cols_kernel(int m, int n, double* A, long long lda, const double* s) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y;
+  if (i < m && j < n) A[i + j * lda] *= s[j];
+}
+
+__global__ void copy_block_kernel(int m, int n, const double* A, long long lda, double* B, long long ldb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y;
+  if (i < m && j < n) B[i + j * ldb] = A[i + j * lda];
+}
+
+__global__ void invsqrt_scale_kernel(double* out, const double* w, int n, double etol, int* removed) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (w[i] < etol) {
+    out[i] = 0.0;
+    atomicAdd(removed, 1);
+  } else {
+    out[i] = 1.0 / sqrt(w[i]);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Sigma_c diagonal element (and derivative), one (level, frequency) request
+// per blockIdx.y, pole range split over blockIdx.x.
+//   sigma = pref * sum_p fac_p sum_n M[n,p]^2 t/(t^2+eta^2),  t = w - e_n +- pole_p
+// sigma_ppm.cc:37-91 (fac = w*Omega, pref 1/2), sigma_exact.cc:40-83 (fac 1, pref 2).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sigma_eval_kernel(const double* __restrict__ mat, long long ld,
+                                                         long long lstride, int qpoff, int ntotal, int npoles,
+                                                         int boundary, double eta2, double pref,
+                                                         const double* __restrict__ fac,
+                                                         const double* __restrict__ pole,
+                                                         const double* __restrict__ energies,
+                                                         const int* __restrict__ levels,
+                                                         const double* __restrict__ freqs, double* partial,
+                                                         int want_deriv) {
+  extern __shared__ double sh_e[];  // ntotal energies + 32 reduction slots
+  double* sh_red = sh_e + ntotal;
+  const int req = blockIdx.y;
+  const int level = levels[req];
+  const double w = freqs[req];
+  for (int i = threadIdx.x; i < ntotal; i += blockDim.x) sh_e[i] = w - energies[i];
+  __syncthreads();
+  const int nsplit = gridDim.x;
+  const int per = (npoles + nsplit - 1) / nsplit;
+  const int p0 = blockIdx.x * per, p1 = min(npoles, p0 + per);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const double* base = mat + (long long)(qpoff + level) * lstride;
+  double s = 0.0, ds = 0.0;
+  for (int p = p0 + warp; p < p1; p += nwarps) {
+    const double f = fac[p];
+    if (f == 0.0) continue;
+    const double om = pole[p];
+    const double* col = base + (long long)p * ld;
+    double sp = 0.0, dsp = 0.0;
+    for (int n = lane; n < ntotal; n += 32) {
+      const double m = col[n];
+      const double t = sh_e[n] + (n < boundary ? om : -om);
+      const double t2 = t * t;
+      const double inv = 1.0 / (t2 + eta2);
+      const double m2 = m * m;
+      sp += m2 * t * inv;
+      if (want_deriv) dsp += m2 * (eta2 - t2) * inv * inv;
+    }
+    s += f * sp;
+    ds += f * dsp;
+  }
+  s = block_sum(s, sh_red);
+  ds = block_sum(ds, sh_red);
+  if (threadIdx.x == 0) {
+    partial[((long long)req * nsplit + blockIdx.x) * 2 + 0] = pref * s;
+    partial[((long long)req * nsplit + blockIdx.x) * 2 + 1] = pref * ds;
+  }
+}
+
+__global__ void sigma_eval_reduce_kernel(const double* partial, int nreq, int nsplit, double* out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nreq) return;
+  double s = 0.0, ds = 0.0;
+  for (int k = 0; k < nsplit; ++k) {
+    s += partial[((long long)r * nsplit + k) * 2 + 0];
+    ds += partial[((long long)r * nsplit + k) * 2 + 1];
+  }
+  out[r] = s;
+  out[nreq + r] = ds;
+}
+
+// A_i[n, p] = pref * fac_p * M_i[n, p] * t/(t^2+eta^2), t = w_i - e_n +- pole_p  (off-diagonal Sigma_c as a GEMM)
+__global__ void sigma_offdiag_weight_kernel(const double* __restrict__ mat, long long ld, long long lstride,
+                                            int qpoff, int ntotal, int npad, int boundary, double eta2, double pref,
+                                            const double* __restrict__ fac, const double* __restrict__ pole,
+                                            const double* __restrict__ energies, const double* __restrict__ freqs,
+                                            int p0, double* out, long long ldo) {
+  const int level = blockIdx.y;
+  const int p = p0 + blockIdx.z;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= npad) return;
+  double v = 0.0;
+  if (n < ntotal) {
+    const double om = pole[p];
+    const double t = freqs[level] - energies[n] + (n < boundary ? om : -om);
+    const double m = mat[(long long)p * ld + (long long)(qpoff + level) * lstride + n];
+    v = pref * fac[p] * m * t / (t * t + eta2);
+  }
+  out[(long long)blockIdx.z * ldo + (long long)level * npad + n] = v;
+}
+
+__global__ void offdiag_finish_kernel(const double* S, int q, double* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y;
+  if (i >= q || j >= q) return;
+  out[i + (long long)j * q] = (i == j) ? 0.0 : S[i + (long long)j * q] + S[j + (long long)i * q];
+}
+
+// BSE_OPERATOR::diagonal, bse_operator.cc:134-175.  One thread per (v, c), c fastest.
+__global__ void bse_diag_kernel(const double* __restrict__ X, long long ldx, int npad, int naux, int vt, int ct,
+                                int voff, int coff, const double* __restrict__ eps_inv,
+                                const double* __restrict__ hqp, int ldh, int cqp, int cx, int cd, int cd2,
+                                double* out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int v = blockIdx.y;
+  if (c >= ct) return;
+  double entry = 0.0;
+  const double* Mv = X + (long long)(voff + v) * npad;  // slice v
+  const double* Mc = X + (long long)(coff + c) * npad;  // slice c
+  if (cx != 0) {
+    double s = 0.0;
+    for (int p = 0; p < naux; ++p) {
+      const double m = Mv[(long long)p * ldx + coff + c];
+      s += m * m;
+    }
+    entry += cx * s;
+  }
+  if (cqp != 0) entry += cqp * (hqp[(c + vt) + (long long)(c + vt) * ldh] - hqp[v + (long long)v * ldh]);
+  if (cd != 0) {
+    double s = 0.0;
+    for (int p = 0; p < naux; ++p)
+      s += Mc[(long long)p * ldx + coff + c] * eps_inv[p] * Mv[(long long)p * ldx + voff + v];
+    entry -= cd * s;
+  }
+  if (cd2 != 0) {
+    double s = 0.0;
+    for (int p = 0; p < naux; ++p)
+      s += Mc[(long long)p * ldx + voff + v] * eps_inv[p] * Mv[(long long)p * ldx + coff + c];
+    entry -= cd2 * s;
+  }
+  out[(long long)ct * v + c] = entry;
+}
+
+// DavidsonSolver::dpr, davidsonsolver.cc:416-422 (+ the isfinite filter of :411-413)
+__global__ void dpr_kernel(int rows, const double* diag, const double* lambda, const double* R, long long ldr,
+                           double* W, long long ldw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y;
+  if (i >= rows) return;
+  const double v = -R[i + j * ldr] / (diag[i] - lambda[j]);
+  W[i + j * ldw] = isfinite(v) ? v : 0.0;
+}
+
+// DavidsonSolver::olsen, davidsonsolver.cc:424-440: W holds dpr(r); W += (x.dpr(r) / x.dpr(x)) * x
+__global__ void olsen_finish_kernel(int rows, const double* Q, long long ldq, const double* num, const double* den,
+                                    double* W, long long ldw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y;
+  if (i >= rows) return;
+  const double eps = num[j] / den[j];
+  const double v = W[i + j * ldw] + eps * Q[i + j * ldq];
+  W[i + j * ldw] = isfinite(v) ? v : 0.0;
+}
+
+inline dim3 grid2(int m, int n, int bx = 256) { return dim3((m + bx - 1) / bx, n); }
+
+}  // namespace
+
+void launch_symmetrize_lower(double* A, int n, long long ld, cudaStream_t s) {
+  const int t = (n + 31) / 32;
+  symmetrize_lower_kernel<<<dim3(t, t), dim3(32, 8), 0, s>>>(A, n, ld);
+  GW_CUDA(cudaGetLastError());
+}
+void launch_add_diagonal(double* A, int n, long long ld, double v, cudaStream_t s) {
+  add_diagonal_kernel<<<(n + 255) / 256, 256, 0, s>>>(A, n, ld, v);
+  GW_CUDA(cudaGetLastError());
+}
+void launch_rpa_weights(double* w, const double* e, int kind, double fre, double fim, double eta, int n_occ,
+                        int n_unocc, int rank, int world, int nloc_occ, cudaStream_t s) {
+  if (nloc_occ <= 0) return;
+  rpa_weights_kernel<<<dim3((n_unocc + 255) / 256, nloc_occ), 256, 0, s>>>(w, e, kind, fre, fim, eta, n_occ, n_unocc,
+                                                                            rank, world);
+  GW_CUDA(cudaGetLastError());
+}
+void launch_diag_scale(char side, int m, int n, const double* A, long long lda, const double* d, double* C,
+                       long long ldc, cudaStream_t s) {
+  if (m <= 0 || n <= 0) return;
+  diag_scale_kernel<<<grid2(m, n), 256, 0, s>>>(side == 'R' || side == 'r', m, n, A, lda, d, C, ldc);
+  GW_CUDA(cudaGetLastError());
+}
+void launch_axpy(int m, int n, double alpha, const double* X, long long ldx, double* Y, long long ldy,
+                 cudaStream_t s) {
+  if (m <= 0 || n <= 0) return;
+  axpy_kernel<<<grid2(m, n), 256, 0, s>>>(m, n, alpha, X, ldx, Y, ldy);
+  GW_CUDA(cudaGetLastError());
+}
+void launch_colnorms(int m, int n, const double* A, long long lda, double* out_dev, cudaStream_t s) {
+  if (n <= 0) return;
+  coldots_kernel<<<n, 256, 0, s>>>(m, A, lda, A, lda, out_dev, 1);
+  GW_CUDA(cudaGetLastError());
+}
+void launch_coldots(int m, int n, const double* X, long long ldx, const double* Y, long long ldy, double* out_dev,
+                    cudaStream_t s) {
+  if (n <= 0) return;
+  coldots_kernel<<<n, 256, 0, s>>>(m, X, ldx, Y, ldy, out_dev, 0);
+  GW_CUDA(cudaGetLastError());
+}
+void launch_scale_cols(int m, int n, double* A, long long lda, const double* s_dev, cudaStream_t s) {
+  if (m <= 0 || n <= 0) return;
+  scale_cols_kernel<<<grid2(m, n), 256, 0, s>>>(m, n, A, lda, s_dev);
+  GW_CUDA(cudaGetLastError());
+}
+void launch_copy_block(int m, int n, const double* A, long long lda, double* B, long long ldb, cudaStream_t s) {
+  if (m <= 0 || n <= 0) return;
+  copy_block_kernel<<<grid2(m, n), 256, 0, s>>>(m, n, A, lda, B, ldb);
+  GW_CUDA(cudaGetLastError());
+}
+void launch_invsqrt_scale(double* out, const double* w, int n, double etol, int* removed_dev, cudaStream_t s) {
+  invsqrt_scale_kernel<<<(n + 255) / 256, 256, 0, s>>>(out, w, n, etol, removed_dev);
+  GW_CUDA(cudaGetLastError());
+}
+void launch_sigma_eval(const gwbse_ctx::SigmaState& st, int ntotal, int nreq, const int* levels_dev,
+                       const double* freqs_dev, double* partial_dev, int nsplit, bool want_deriv, cudaStream_t s) {
+  if (nreq <= 0) return;
+  const size_t sh = sizeof(double) * (ntotal + 32);
+  sigma_eval_kernel<<<dim3(nsplit, nreq), 256, sh, s>>>(st.mat, st.ld, st.lstride, st.qpoff, ntotal, st.npoles,
+                                                        st.nocc_boundary, st.eta * st.eta, st.diag_pref, st.fac,
+                                                        st.pole, st.energies, levels_dev, freqs_dev, partial_dev,
+                                                        want_deriv ? 1 : 0);
+  GW_CUDA(cudaGetLastError());
+}
+void launch_sigma_eval_reduce(const double* partial_dev, int nreq, int nsplit, bool, double* out_dev,
+                              cudaStream_t s) {
+  if (nreq <= 0) return;
+  sigma_eval_reduce_kernel<<<(nreq + 127) / 128, 128, 0, s>>>(partial_dev, nreq, nsplit, out_dev);
+  GW_CUDA(cudaGetLastError());
+}
+void launch_sigma_offdiag_weight(const gwbse_ctx::SigmaState& st, int ntotal, int npad, int q, int p0, int np,
+                                 const double* freqs_dev, double pref, double* out, long long ldo, cudaStream_t s) {
+  if (np <= 0 || q <= 0) return;
+  sigma_offdiag_weight_kernel<<<dim3((npad + 127) / 128, q, np), 128, 0, s>>>(
+      st.mat, st.ld, st.lstride, st.qpoff, ntotal, npad, st.nocc_boundary, st.eta * st.eta, pref, st.fac, st.pole,
+      st.energies, freqs_dev, p0, out, ldo);
+  GW_CUDA(cudaGetLastError());
+}
+void launch_offdiag_finish(const double* S, int q, double* out, cudaStream_t s) {
+  offdiag_finish_kernel<<<grid2(q, q, 128), 128, 0, s>>>(S, q, out);
+  GW_CUDA(cudaGetLastError());
+}
+void launch_bse_diag(const double* X, long long ldx, int npad, int naux, int vt, int ct, int voff, int coff,
+                     const double* eps_inv, const double* hqp, int ldh, int cqp, int cx, int cd, int cd2,
+                     double* out, cudaStream_t s) {
+  bse_diag_kernel<<<dim3((ct + 127) / 128, vt), 128, 0, s>>>(X, ldx, npad, naux, vt, ct, voff, coff, eps_inv, hqp,
+                                                              ldh, cqp, cx, cd, cd2, out);
+  GW_CUDA(cudaGetLastError());
+}
+void launch_dpr(int rows, int ncols, const double* diag, const double* lambda_dev, const double* R, long long ldr,
+                double* W, long long ldw, cudaStream_t s) {
+  if (ncols <= 0) return;
+  dpr_kernel<<<grid2(rows, ncols), 256, 0, s>>>(rows, diag, lambda_dev, R, ldr, W, ldw);
+  GW_CUDA(cudaGetLastError());
+}
+void launch_olsen_finish(int rows, int ncols, const double*, const double*, const double* Q, long long ldq,
+                         const double* num_dev, const double* den_dev, double* W, long long ldw, cudaStream_t s) {
+  if (ncols <= 0) return;
+  olsen_finish_kernel<<<grid2(rows, ncols), 256, 0, s>>>(rows, Q, ldq, num_dev, den_dev, W, ldw);
+  GW_CUDA(cudaGetLastError());
+}
+
+}  // namespace gwbse
