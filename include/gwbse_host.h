@@ -1,0 +1,58 @@
+/* gwbse_host.h - C entry points of libgwbse_host.so, the C++ host layer above gwbse_b200.h.
+ *
+ * The host layer mirrors the reference's classes (headers under votca_b200/host: TCMatrix_gwbse, RPA, Sigma_*, GW,
+ * BSE_OPERATOR, DavidsonSolver, BSE, GWBSE).  This "job" facade exposes GWBSE::Initialize/Evaluate
+ * (xtp/src/libxtp/gwbse/gwbse.cc:60-578, 822-1250) to non-C++ callers (tests, bench.py):
+ *   - options use the keys of share/xtp/xml/subpackages/gwbse.xml ("gw.mode", "bse.exctotal", ...) and can
+ *     be loaded from the same options XML the reference takes with `xtp_tools -e dftgwbse -o opts.xml`;
+ *   - inputs are what the reference reads from the Orbitals object (orbitals.cc:990-1063);
+ *   - outputs carry the .orb dataset names (QPpert_energies, QPdiag_eigenvalues, BSE_singlet_eigenvalues ...).
+ * All functions return 0 on success; gwbse_job_error() gives the message of the last failure.
+ */
+#ifndef GWBSE_HOST_H
+#define GWBSE_HOST_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+typedef struct gwbse_job gwbse_job;
+
+int gwbse_job_create(int device, gwbse_job** out);
+void gwbse_job_destroy(gwbse_job* job);
+const char* gwbse_job_error(const gwbse_job* job);
+const char* gwbse_job_create_error(void);
+const char* gwbse_job_log(const gwbse_job* job);
+
+/* multi-GPU: call before gwbse_job_run on every rank (id from gwbse_nccl_unique_id on rank 0) */
+int gwbse_job_comm_init(gwbse_job* job, int rank, int world, const unsigned char* id128);
+
+int gwbse_job_set_option(gwbse_job* job, const char* key, const char* value);
+int gwbse_job_load_options_xml(gwbse_job* job, const char* path);
+/* scalars: "homo", "ScaHFX" */
+int gwbse_job_set_scalar(gwbse_job* job, const char* name, double value);
+/* arrays (column-major, copied): "mos" (nbasis x nmo), "mo_energies" (nmo x 1), "vxc" (q x q),
+ * "aux_overlap", "aux_coulomb" (naux x naux), "dipole_x|y|z" (ctotal x vtotal interlevel dipoles),
+ * "Hqp", "RPA_inputenergies" (BSE-only runs).
+ * "ao3c": naux matrices N x N, rows = N*N, cols = naux; NOT copied, must stay alive until run returns. */
+int gwbse_job_set_array(gwbse_job* job, const char* name, const double* data, long rows, long cols);
+/* AO integral producer callback instead of "ao3c": fill(user, aux_offset, aux_count, out[aux_count*N*N]) */
+typedef void (*gwbse_ao3c_fn)(void* user, long aux_offset, long aux_count, double* out);
+int gwbse_job_set_ao3c_callback(gwbse_job* job, long nbasis, long naux, gwbse_ao3c_fn fn, void* user);
+
+int gwbse_job_run(gwbse_job* job);
+
+int gwbse_job_array_dims(const gwbse_job* job, const char* name, long* rows, long* cols);
+int gwbse_job_get_array(const gwbse_job* job, const char* name, double* out);
+int gwbse_job_get_scalar(const gwbse_job* job, const char* name, double* out);
+long long gwbse_job_launch_count(const gwbse_job* job);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* GWBSE_HOST_H */

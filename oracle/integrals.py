@@ -306,3 +306,36 @@ def coulomb3c(auxbasis, dftbasis):
                 out[sc.start:sc.start + sc.nfunc, sb.start:sb.start + sb.nfunc,
                     sa.start:sa.start + sa.nfunc] = blk.transpose(0, 2, 1)
     return out
+
+
+# ----------------------------------------------------------------------------
+# dipole integrals <mu| r |nu> about the origin (AODipole, libint2_calls.cc emultipole1)
+# ----------------------------------------------------------------------------
+def dipole(basis):
+    n = basis.size
+    D = np.zeros((3, n, n))
+    for i, sa in enumerate(basis.shells):
+        for sb in basis.shells[:i + 1]:
+            a = sa.exps[:, None]
+            b = sb.exps[None, :]
+            cc = sa.coefs[:, None] * sb.coefs[None, :]
+            p = a + b
+            AB = sa.center - sb.center
+            P = [(a * sa.center[k] + b * sb.center[k]) / p for k in range(3)]
+            pref = cc * (math.pi / p) ** 1.5
+            E = [hermite_E(sa.l, sb.l, a, b, AB[k]) for k in range(3)]
+            ca, cb = cart_components(sa.l), cart_components(sb.l)
+            blk = np.zeros((3, len(ca), len(cb)))
+            for ia, la in enumerate(ca):
+                for ib, lb in enumerate(cb):
+                    e0 = [E[k][la[k]][lb[k]][0] for k in range(3)]
+                    e1 = [E[k][la[k]][lb[k]][1] for k in range(3)]
+                    for k in range(3):
+                        f = [e0[0], e0[1], e0[2]]
+                        f[k] = e1[k] + P[k] * e0[k]
+                        blk[k, ia, ib] = np.sum(pref * f[0] * f[1] * f[2])
+            for k in range(3):
+                pb = pure_transform(sa.l) @ blk[k] @ pure_transform(sb.l).T
+                D[k, sa.start:sa.start + sa.nfunc, sb.start:sb.start + sb.nfunc] = pb
+                D[k, sb.start:sb.start + sb.nfunc, sa.start:sa.start + sa.nfunc] = pb.T
+    return D

@@ -92,7 +92,9 @@ def test_dense_aux(ctx):
     wr, wi, VR = ctx.gen_eig(T, Bm)
     import scipy.linalg
     wref = scipy.linalg.eigvals(T, Bm)
-    assert np.allclose(np.sort_complex(wr + 1j * wi), np.sort_complex(wref), rtol=1e-9, atol=1e-10)
+    key = lambda z: (np.round(z.real, 8), np.round(z.imag, 8))  # noqa: E731
+    got = np.array(sorted(wr + 1j * wi, key=key))
+    assert np.allclose(got, np.array(sorted(wref, key=key)), rtol=1e-9, atol=1e-10)
     for i in range(12):  # real eigenpairs satisfy T x = lambda B x
         if wi[i] == 0.0:
             x = VR[:, i]

@@ -12,6 +12,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, "include", "gwbse_b200.h")
 LIBPATH = os.path.join(ROOT, "votca_b200", "lib", "libgwbse_b200.so")
+HOST_HEADER = os.path.join(ROOT, "include", "gwbse_host.h")
+HOST_LIBPATH = os.path.join(ROOT, "votca_b200", "lib", "libgwbse_host.so")
 
 _SCALARS = {
     "int": ctypes.c_int,
@@ -29,6 +31,7 @@ def parse_header(path=HEADER):
     txt = open(path).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
     txt = re.sub(r"^\s*#.*$", "", txt, flags=re.M)
+    txt = re.sub(r"typedef[^;]*\(\*[^;]*;", "", txt)
     protos = {}
     for m in re.finditer(r"([A-Za-z_][\w\s\*]*?)\b(gwbse_\w+)\s*\(([^;{]*?)\)\s*;", txt):
         ret, name, args = m.group(1).strip(), m.group(2), m.group(3).strip()
@@ -51,17 +54,21 @@ def _ctype(tstr):
         if base == "char":
             return ctypes.c_char_p
         return ctypes.c_void_p
+    if t == "gwbse_ao3c_fn":
+        return ctypes.c_void_p
+    if t == "long":
+        return ctypes.c_long
     return _SCALARS[t]
 
 
 class CApi:
-    def __init__(self, libpath=LIBPATH):
+    def __init__(self, libpath=LIBPATH, header=HEADER):
         if not os.path.exists(libpath):
             raise RuntimeError(
                 f"{libpath} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(gwbse_b200 has no CPU fallback)")
         self.lib = ctypes.CDLL(libpath, mode=ctypes.RTLD_GLOBAL)
-        self.protos = parse_header()
+        self.protos = parse_header(header)
         for name, (ret, args) in self.protos.items():
             fn = getattr(self.lib, name)
             fn.restype = _ctype(ret) if ret != "void" else None
@@ -72,6 +79,7 @@ class CApi:
 
 
 _api = None
+_host_api = None
 
 
 def capi():
@@ -79,6 +87,15 @@ def capi():
     if _api is None:
         _api = CApi()
     return _api
+
+
+def host_api():
+    """C++ host layer (GWBSE job facade); loads the kernel library first."""
+    global _host_api
+    if _host_api is None:
+        capi()
+        _host_api = CApi(HOST_LIBPATH, HOST_HEADER)
+    return _host_api
 
 
 def ptr(a):

@@ -303,3 +303,88 @@ class Context:
         finally:
             for p in (dd, dR, dQ, dW):
                 self.free(p)
+
+
+class Job:
+    """GWBSE job facade of the C++ host layer (include/gwbse_host.h): options in, .orb-named arrays out."""
+
+    def __init__(self, device=0):
+        from ._capi import host_api
+        self.api = host_api()
+        h = ctypes.c_void_p()
+        if self.api.gwbse_job_create(int(device), ctypes.byref(h)) != 0:
+            raise GwbseError(self.api.gwbse_job_create_error().decode())
+        self.h = h
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.api.gwbse_job_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise GwbseError(self.api.gwbse_job_error(self.h).decode())
+
+    def comm_init(self, rank, world, uid):
+        buf = (ctypes.c_ubyte * 128).from_buffer_copy(bytes(uid))
+        self._ck(self.api.gwbse_job_comm_init(self.h, int(rank), int(world), buf))
+
+    def set_options(self, **kw):
+        """Keys as in gwbse.xml with '.' written as '__', e.g. gw__mode='G0W0'."""
+        for k, v in kw.items():
+            self.set_option(k.replace("__", "."), v)
+
+    def set_option(self, key, value):
+        if isinstance(value, bool):
+            value = "true" if value else "false"
+        self._ck(self.api.gwbse_job_set_option(self.h, key.encode(), str(value).encode()))
+
+    def load_options_xml(self, path):
+        self._ck(self.api.gwbse_job_load_options_xml(self.h, str(path).encode()))
+
+    def set_scalar(self, name, value):
+        self._ck(self.api.gwbse_job_set_scalar(self.h, name.encode(), float(value)))
+
+    def set_array(self, name, a):
+        a = fmat(a)
+        if a.ndim == 1:
+            a = a[:, None]
+        self._ck(self.api.gwbse_job_set_array(self.h, name.encode(), ptr(a), a.shape[0], a.shape[1]))
+
+    def set_ao3c(self, ao3c):
+        """ao3c: (naux, N, N) C-contiguous; referenced, not copied."""
+        a = np.ascontiguousarray(ao3c, dtype=np.float64)
+        self._keep.append(a)
+        naux, N = a.shape[0], a.shape[1]
+        self._ck(self.api.gwbse_job_set_array(self.h, b"ao3c", ptr(a), N * N, naux))
+
+    def run(self):
+        self._ck(self.api.gwbse_job_run(self.h))
+
+    def get(self, name):
+        r, c = ctypes.c_long(), ctypes.c_long()
+        if self.api.gwbse_job_array_dims(self.h, name.encode(), ctypes.byref(r), ctypes.byref(c)) != 0:
+            raise KeyError(name)
+        out = np.empty((r.value, c.value), order="F")
+        if out.size:
+            self.api.gwbse_job_get_array(self.h, name.encode(), ptr(out))
+        return out[:, 0] if c.value == 1 else out
+
+    def scalar(self, name):
+        v = ctypes.c_double()
+        if self.api.gwbse_job_get_scalar(self.h, name.encode(), ctypes.byref(v)) != 0:
+            raise KeyError(name)
+        return float(v.value)
+
+    def log(self):
+        return self.api.gwbse_job_log(self.h).decode()
+
+    def launch_count(self):
+        return int(self.api.gwbse_job_launch_count(self.h))

@@ -70,7 +70,7 @@ void gwbse_ctx_destroy(gwbse_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (auto& kv : ctx->bufs)
     if (kv.second.p) cudaFree(kv.second.p);
-  for (double* p : {ctx->X, ctx->X2, ctx->Xsnap, ctx->mos, ctx->eps, ctx->exact_res, ctx->bse.eps_inv, ctx->bse.hqp})
+  for (double* p : {ctx->X, ctx->X2, ctx->Xsnap, ctx->mos, ctx->exact_res, ctx->bse.eps_inv, ctx->bse.hqp})
     if (p) cudaFree(p);
   for (auto* st : {&ctx->sig_ppm, &ctx->sig_exact})
     for (double* p : {st->fac, st->pole, st->energies})

@@ -302,7 +302,7 @@ int gwbse_rpa_epsilon(gwbse_ctx* ctx, int kind, double fre, double fim, double e
   const int n_unocc = rpamax - homo;
   GW_REQUIRE(n_occ > 0 && n_unocc > 0 && n_occ <= ctx->mtotal, "invalid occupied/virtual split");
   const int naux = ctx->naux;
-  if (!ctx->eps) GW_CUDA(cudaMalloc(&ctx->eps, sizeof(double) * (size_t)naux * naux));
+  ctx->eps = ctx->buf("rpa_eps", (size_t)naux * naux);
   const int rpatotal = n_occ + n_unocc;
   double* e_dev = ctx->buf("rpa_e", rpatotal);
   GW_CUDA(cudaMemcpyAsync(e_dev, energies, sizeof(double) * rpatotal, cudaMemcpyHostToDevice, ctx->stream));

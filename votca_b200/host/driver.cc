@@ -1,0 +1,249 @@
+// C facade of the host layer (include/gwbse_host.h).
+#include "../../include/gwbse_host.h"
+
+#include <cstring>
+#include <map>
+#include <memory>
+
+#include "gwbse.h"
+
+using namespace votca;
+using namespace votca::xtp;
+
+namespace {
+
+struct ArraySource : AOIntegralSource {
+  Index N = 0, naux = 0;
+  const double* ao3c = nullptr;
+  gwbse_ao3c_fn fn = nullptr;
+  void* user = nullptr;
+  MatrixXd S, V;
+  Index AuxSize() const override { return naux; }
+  Index BasisSize() const override { return N; }
+  void ComputeAO3cBlock(Index aux_offset, Index aux_count, double* out) const override {
+    if (fn) {
+      fn(user, aux_offset, aux_count, out);
+    } else {
+      if (!ao3c) throw std::runtime_error("no AO three-centre integrals supplied (ao3c)");
+      std::memcpy(out, ao3c + static_cast<size_t>(aux_offset) * N * N, sizeof(double) * aux_count * N * N);
+    }
+  }
+  MatrixXd AuxOverlap() const override { return S; }
+  MatrixXd AuxCoulomb() const override { return V; }
+};
+
+}  // namespace
+
+struct gwbse_job {
+  std::unique_ptr<Device> dev;
+  Logger log;
+  Options options;
+  std::map<std::string, MatrixXd> in;
+  std::map<std::string, double> scalars;
+  std::map<std::string, MatrixXd> out;
+  std::map<std::string, double> out_scalars;
+  ArraySource ints;
+  std::string err;
+  mutable std::string logcache;
+};
+
+static thread_local std::string g_job_create_error;
+
+#define JOB_BEGIN(job) \
+  if (!(job)) return 1; \
+  try {
+#define JOB_END(job)                   \
+  return 0;                            \
+  }                                    \
+  catch (const std::exception& e) {    \
+    (job)->err = e.what();             \
+    return 1;                          \
+  }
+
+static MatrixXd vec2mat(const VectorXd& v) { return MatrixXd(v.data(), v.size(), 1, std::max<Index>(v.size(), 1)); }
+static VectorXd mat2vec(const MatrixXd& m) { return VectorXd(m.data(), m.size()); }
+
+extern "C" {
+
+int gwbse_job_create(int device, gwbse_job** out) {
+  if (!out) return 1;
+  *out = nullptr;
+  try {
+    auto job = std::make_unique<gwbse_job>();
+    job->dev = std::make_unique<Device>(device);
+    *out = job.release();
+    return 0;
+  } catch (const std::exception& e) {
+    g_job_create_error = e.what();
+    return 1;
+  }
+}
+
+void gwbse_job_destroy(gwbse_job* job) { delete job; }
+const char* gwbse_job_error(const gwbse_job* job) { return job ? job->err.c_str() : "null job"; }
+const char* gwbse_job_create_error(void) { return g_job_create_error.c_str(); }
+const char* gwbse_job_log(const gwbse_job* job) {
+  if (!job) return "";
+  job->logcache = job->log.str();
+  return job->logcache.c_str();
+}
+
+int gwbse_job_comm_init(gwbse_job* job, int rank, int world, const unsigned char* id128) {
+  JOB_BEGIN(job)
+  job->dev->check(gwbse_comm_init(job->dev->ctx(), rank, world, id128));
+  JOB_END(job)
+}
+
+int gwbse_job_set_option(gwbse_job* job, const char* key, const char* value) {
+  JOB_BEGIN(job)
+  job->options.set(key, value);
+  JOB_END(job)
+}
+
+int gwbse_job_load_options_xml(gwbse_job* job, const char* path) {
+  JOB_BEGIN(job)
+  job->options.LoadFromXML(path);
+  JOB_END(job)
+}
+
+int gwbse_job_set_scalar(gwbse_job* job, const char* name, double value) {
+  JOB_BEGIN(job)
+  job->scalars[name] = value;
+  JOB_END(job)
+}
+
+int gwbse_job_set_array(gwbse_job* job, const char* name, const double* data, long rows, long cols) {
+  JOB_BEGIN(job)
+  const std::string n(name);
+  if (n == "ao3c") {
+    job->ints.ao3c = data;
+    job->ints.fn = nullptr;
+    job->ints.naux = cols;
+    job->ints.N = static_cast<Index>(std::llround(std::sqrt(static_cast<double>(rows))));
+    if (job->ints.N * job->ints.N != rows) throw std::runtime_error("ao3c: rows must be N*N");
+  } else {
+    job->in[n] = MatrixXd(data, rows, cols, std::max<long>(rows, 1));
+  }
+  JOB_END(job)
+}
+
+int gwbse_job_set_ao3c_callback(gwbse_job* job, long nbasis, long naux, gwbse_ao3c_fn fn, void* user) {
+  JOB_BEGIN(job)
+  job->ints.fn = fn;
+  job->ints.user = user;
+  job->ints.ao3c = nullptr;
+  job->ints.N = nbasis;
+  job->ints.naux = naux;
+  JOB_END(job)
+}
+
+int gwbse_job_run(gwbse_job* job) {
+  JOB_BEGIN(job)
+  auto need = [&](const char* n) -> const MatrixXd& {
+    auto it = job->in.find(n);
+    if (it == job->in.end()) throw std::runtime_error(std::string("input array '") + n + "' not set");
+    return it->second;
+  };
+  GWBSE::Inputs in;
+  if (!job->scalars.count("homo")) throw std::runtime_error("input scalar 'homo' not set");
+  in.homo = static_cast<Index>(job->scalars["homo"]);
+  in.ScaHFX = job->scalars.count("ScaHFX") ? job->scalars["ScaHFX"] : 0.0;
+  const MatrixXd& mos = need("mos");
+  const VectorXd mo_e = mat2vec(need("mo_energies"));
+  in.mos = &mos;
+  in.mo_energies = &mo_e;
+  if (job->in.count("vxc")) in.vxc = &job->in["vxc"];
+  job->ints.S = need("aux_overlap");
+  job->ints.V = need("aux_coulomb");
+  if (job->ints.naux != job->ints.S.rows()) throw std::runtime_error("aux matrices do not match ao3c");
+  in.integrals = &job->ints;
+  std::vector<MatrixXd> dip;
+  if (job->in.count("dipole_x") && job->in.count("dipole_y") && job->in.count("dipole_z")) {
+    dip = {job->in["dipole_x"], job->in["dipole_y"], job->in["dipole_z"]};
+    in.interlevel_dipoles = &dip;
+  }
+  VectorXd rpa_in;
+  if (job->in.count("Hqp") && job->in.count("RPA_inputenergies")) {
+    in.Hqp = &job->in["Hqp"];
+    rpa_in = mat2vec(job->in["RPA_inputenergies"]);
+    in.rpa_input_energies = &rpa_in;
+  }
+  GWBSE gwbse(*job->dev, job->log);
+  gwbse.Initialize(job->options, in);
+  GWBSE::Results r = gwbse.Evaluate();
+  auto& o = job->out;
+  o.clear();
+  o["RPA_inputenergies"] = vec2mat(r.RPA_inputenergies);
+  o["QPpert_energies"] = vec2mat(r.QPpert_energies);
+  o["QPdiag_eigenvalues"] = vec2mat(r.QPdiag_eigenvalues);
+  o["QPdiag_eigenvectors"] = r.QPdiag_eigenvectors;
+  o["Hqp"] = r.Hqp;
+  o["Sigma_x"] = r.Sigma_x;
+  o["Sigma_c"] = r.Sigma_c;
+  o["BSE_singlet_eigenvalues"] = vec2mat(r.BSE_singlet.eigenvalues);
+  o["BSE_singlet_eigenvectors"] = r.BSE_singlet.eigenvectors;
+  o["BSE_singlet_eigenvectors2"] = r.BSE_singlet.eigenvectors2;
+  o["BSE_triplet_eigenvalues"] = vec2mat(r.BSE_triplet.eigenvalues);
+  o["BSE_triplet_eigenvectors"] = r.BSE_triplet.eigenvectors;
+  o["BSE_triplet_eigenvectors2"] = r.BSE_triplet.eigenvectors2;
+  o["BSE_singlet_dynamic"] = vec2mat(r.BSE_singlet_dynamic);
+  o["BSE_triplet_dynamic"] = vec2mat(r.BSE_triplet_dynamic);
+  o["oscillator_strengths"] = vec2mat(r.oscillator_strengths);
+  MatrixXd td(3, static_cast<Index>(r.transition_dipoles.size()));
+  for (size_t s = 0; s < r.transition_dipoles.size(); ++s)
+    for (Index i = 0; i < 3; ++i) td(i, s) = r.transition_dipoles[s](i);
+  o["transition_dipoles"] = td;
+  o["singlet_qp_contrib"] = vec2mat(r.singlet_analysis.qp_contrib);
+  o["singlet_direct_contrib"] = vec2mat(r.singlet_analysis.direct_contrib);
+  o["singlet_exchange_contrib"] = vec2mat(r.singlet_analysis.exchange_contrib);
+  o["triplet_qp_contrib"] = vec2mat(r.triplet_analysis.qp_contrib);
+  o["triplet_direct_contrib"] = vec2mat(r.triplet_analysis.direct_contrib);
+  auto& s = job->out_scalars;
+  s["rpamin"] = r.rpamin;
+  s["rpamax"] = r.rpamax;
+  s["qpmin"] = r.qpmin;
+  s["qpmax"] = r.qpmax;
+  s["bse_vmin"] = r.bse_vmin;
+  s["bse_cmax"] = r.bse_cmax;
+  s["removed_functions"] = r.removed_functions;
+  s["gw_iterations"] = r.gw_iterations;
+  s["singlet_davidson_iterations"] = r.singlet_davidson_iterations;
+  s["triplet_davidson_iterations"] = r.triplet_davidson_iterations;
+  s["singlet_converged"] = r.BSE_singlet.success;
+  s["triplet_converged"] = r.BSE_triplet.success;
+  s["sigma_batches"] = static_cast<double>(r.sigma_batches);
+  s["sigma_evaluations"] = static_cast<double>(r.sigma_evaluations);
+  s["time_fill"] = r.time_fill;
+  s["time_gw"] = r.time_gw;
+  s["time_bse"] = r.time_bse;
+  JOB_END(job)
+}
+
+int gwbse_job_array_dims(const gwbse_job* job, const char* name, long* rows, long* cols) {
+  if (!job) return 1;
+  auto it = job->out.find(name);
+  if (it == job->out.end()) return 1;
+  *rows = it->second.rows();
+  *cols = it->second.cols();
+  return 0;
+}
+
+int gwbse_job_get_array(const gwbse_job* job, const char* name, double* out) {
+  if (!job) return 1;
+  auto it = job->out.find(name);
+  if (it == job->out.end()) return 1;
+  std::memcpy(out, it->second.data(), sizeof(double) * it->second.size());
+  return 0;
+}
+
+int gwbse_job_get_scalar(const gwbse_job* job, const char* name, double* out) {
+  if (!job) return 1;
+  auto it = job->out_scalars.find(name);
+  if (it == job->out_scalars.end()) return 1;
+  *out = it->second;
+  return 0;
+}
+
+long long gwbse_job_launch_count(const gwbse_job* job) { return job ? gwbse_launch_count(job->dev->ctx()) : 0; }
+
+}  // extern "C"

@@ -1,0 +1,634 @@
+// GW - host mirror of xtp/include/votca/xtp/gw.h:37-300 and xtp/src/libxtp/gwbse/gw.cc:35-78,210-776
+// (G0W0 / evGW; QSGW is outside the BASELINE configs).  Control flow (iteration order, mixing, convergence,
+// root selection) is kept; what changes is how Sigma_c is evaluated: the per-level QP searches run on host
+// threads exactly as in the reference's `omp parallel for` (gw.cc:344), but their Sigma_c requests are
+// collected by a batcher and served by ONE batched kernel pass per round instead of one Eigen loop each.
+#pragma once
+#include <condition_variable>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <unordered_set>
+
+#include "qp_rootsearch.h"
+#include "sigma.h"
+
+namespace votca {
+namespace xtp {
+
+// anderson_mixing.cc:28-95
+class Anderson {
+ public:
+  void Configure(const Index order, const double alpha) {
+    order_ = order + 1;
+    alpha_ = alpha;
+  }
+  void UpdateOutput(const VectorXd& newOutput) {
+    if (Index(output_.size()) > order_ - 1) output_.erase(output_.begin());
+    output_.push_back(newOutput);
+  }
+  void UpdateInput(const VectorXd& newInput) {
+    if (Index(output_.size()) > order_ - 1) input_.erase(input_.begin());
+    input_.push_back(newInput);
+  }
+  const VectorXd MixHistory() {
+    const Index iteration = output_.size();
+    const Index used_history = iteration - 1;
+    VectorXd OutMixed = output_.back();
+    VectorXd InMixed = input_.back();
+    if (iteration > 1 && order_ > 1) {
+      VectorXd DeltaN = OutMixed - InMixed;
+      MatrixXd A(used_history, used_history);
+      VectorXd c(used_history);
+      for (Index m = 1; m < iteration; m++) {
+        const VectorXd dm = DeltaN - output_[used_history - m] + input_[used_history - m];
+        c(m - 1) = dm.dot(DeltaN);
+        for (Index j = 1; j < iteration; j++)
+          A(m - 1, j - 1) = dm.dot(DeltaN - output_[used_history - j] + input_[used_history - j]);
+      }
+      VectorXd coefficients = SolveFullPivQR(A, c);
+      for (Index n = 1; n < iteration; n++) {
+        OutMixed += coefficients(n - 1) * (output_[used_history - n] - output_[used_history]);
+        InMixed += coefficients(n - 1) * (input_[used_history - n] - input_[used_history]);
+      }
+    }
+    return alpha_ * OutMixed + (1 - alpha_) * InMixed;
+  }
+
+  // rank-revealing solve standing in for Eigen's fullPivHouseholderQr().solve (anderson_mixing.cc:72):
+  // Gaussian elimination with complete pivoting, free variables of a rank-deficient system set to zero.
+  static VectorXd SolveFullPivQR(MatrixXd A, VectorXd b) {
+    const Index n = A.rows();
+    std::vector<Index> colperm(n);
+    for (Index i = 0; i < n; ++i) colperm[i] = i;
+    double maxpiv = 0.0;
+    Index rank = 0;
+    for (Index k = 0; k < n; ++k) {
+      Index pi = k, pj = k;
+      double best = 0.0;
+      for (Index j = k; j < n; ++j)
+        for (Index i = k; i < n; ++i)
+          if (std::abs(A(i, j)) > best) {
+            best = std::abs(A(i, j));
+            pi = i;
+            pj = j;
+          }
+      if (k == 0) maxpiv = best;
+      if (best <= maxpiv * 1e-14 * double(n) || best == 0.0) break;
+      for (Index j = 0; j < n; ++j) std::swap(A(k, j), A(pi, j));
+      std::swap(b(k), b(pi));
+      for (Index i = 0; i < n; ++i) std::swap(A(i, k), A(i, pj));
+      std::swap(colperm[k], colperm[pj]);
+      for (Index i = k + 1; i < n; ++i) {
+        const double f = A(i, k) / A(k, k);
+        for (Index j = k; j < n; ++j) A(i, j) -= f * A(k, j);
+        b(i) -= f * b(k);
+      }
+      ++rank;
+    }
+    VectorXd y(n, 0.0);
+    for (Index k = rank - 1; k >= 0; --k) {
+      double s = b(k);
+      for (Index j = k + 1; j < rank; ++j) s -= A(k, j) * y(j);
+      y(k) = s / A(k, k);
+    }
+    VectorXd x(n, 0.0);
+    for (Index k = 0; k < n; ++k) x(colperm[k]) = y(k);
+    return x;
+  }
+
+ private:
+  std::vector<VectorXd> input_, output_;
+  double alpha_ = 0.7;
+  Index order_ = 25;
+};
+
+// Collects Sigma_c requests of the concurrently running per-level searches into batches.
+class SigmaBatcher {
+ public:
+  explicit SigmaBatcher(const Sigma_base& sigma) : sigma_(sigma) {}
+
+  // called by worker threads
+  void Evaluate(Index level, double freq, bool want_deriv, double& s, double& ds) {
+    std::unique_lock<std::mutex> lk(mu_);
+    Request r{(int)level, freq, want_deriv, 0.0, 0.0, false};
+    queue_.push_back(&r);
+    cv_server_.notify_one();
+    cv_workers_.wait(lk, [&] { return r.done; });
+    if (!error_.empty()) throw std::runtime_error(error_);
+    s = r.s;
+    ds = r.ds;
+  }
+  void WorkerStarted() {
+    std::lock_guard<std::mutex> lk(mu_);
+    ++running_;
+  }
+  void WorkerFinished() {
+    std::lock_guard<std::mutex> lk(mu_);
+    --running_;
+    cv_server_.notify_one();
+  }
+  // run on the calling thread until all workers have finished
+  void Serve() {
+    std::unique_lock<std::mutex> lk(mu_);
+    while (true) {
+      cv_server_.wait(lk, [&] { return running_ == 0 || (Index)queue_.size() == running_; });
+      if (running_ == 0 && queue_.empty()) return;
+      std::vector<Request*> batch;
+      batch.swap(queue_);
+      std::vector<int> lv(batch.size());
+      std::vector<double> fr(batch.size()), s, ds;
+      bool any_deriv = false;
+      for (size_t i = 0; i < batch.size(); ++i) {
+        lv[i] = batch[i]->level;
+        fr[i] = batch[i]->freq;
+        any_deriv = any_deriv || batch[i]->want_deriv;
+      }
+      lk.unlock();
+      try {
+        sigma_.EvalBatch(lv, fr, s, any_deriv ? &ds : nullptr);
+      } catch (const std::exception& e) {
+        error_ = e.what();
+        s.assign(batch.size(), 0.0);
+        ds.assign(batch.size(), 0.0);
+      }
+      lk.lock();
+      ++batches_;
+      evaluations_ += batch.size();
+      for (size_t i = 0; i < batch.size(); ++i) {
+        batch[i]->s = s[i];
+        batch[i]->ds = any_deriv ? ds[i] : 0.0;
+        batch[i]->done = true;
+      }
+      cv_workers_.notify_all();
+    }
+  }
+  std::size_t batches() const { return batches_; }
+  std::size_t evaluations() const { return evaluations_; }
+
+ private:
+  struct Request {
+    int level;
+    double freq;
+    bool want_deriv;
+    double s, ds;
+    bool done;
+  };
+  const Sigma_base& sigma_;
+  std::mutex mu_;
+  std::condition_variable cv_server_, cv_workers_;
+  std::vector<Request*> queue_;
+  Index running_ = 0;
+  std::size_t batches_ = 0, evaluations_ = 0;
+  std::string error_;
+};
+
+class GW {
+  using EvalStage = qp_solver::EvalStage;
+  using QPStats = qp_solver::Stats;
+  using QPRootCandidate = qp_solver::RootCandidate;
+  using QPWindowDiagnostics = qp_solver::WindowDiagnostics;
+
+ public:
+  GW(Logger& log, TCMatrix_gwbse& Mmn, const MatrixXd& vxc, const VectorXd& dft_energies)
+      : log_(log), Mmn_(Mmn), vxc_(vxc), dft_energies_(dft_energies), rpa_(log, Mmn) {}
+
+  struct options {
+    Index homo = 0, qpmin = 0, qpmax = 0, rpamin = 0, rpamax = 0;
+    double eta = 1e-3;
+    double g_sc_limit = 1e-5;
+    Index g_sc_max_iterations = 100;
+    double gw_sc_limit = 1e-5;
+    Index gw_sc_max_iterations = 50;
+    double shift = 0;
+    double ScaHFX = 0.0;
+    std::string sigma_integration = "ppm";
+    Index reset_3c = 5;
+    std::string qp_solver = "grid";
+    double qp_solver_alpha = 0.75;
+    Index qp_grid_steps = 0;
+    double qp_grid_spacing = 0.0;
+    double qp_full_window_half_width = -1.0;
+    double qp_dense_spacing = -1.0;
+    double qp_adaptive_shell_width = -1.0;
+    Index qp_adaptive_shell_count = 0;
+    Index gw_mixing_order = 20;
+    double gw_mixing_alpha = 0.7;
+    std::string quadrature_scheme = "legendre";
+    Index order = 12;
+    double alpha = 1e-3;
+    bool qp_restrict_search = true;
+    double qp_zero_margin = 1e-6;
+    double qp_virtual_min_energy = -0.1;
+    std::string qp_root_finder = "bisection";
+    std::string qp_grid_search_mode = "adaptive_with_dense_fallback";
+  };
+
+  // gw.cc:35-58
+  void configure(const options& opt) {
+    opt_ = opt;
+    qp_solver::NormalizeGridSearchOptions(opt_);
+    qptotal_ = opt_.qpmax - opt_.qpmin + 1;
+    rpa_.configure(opt_.homo, opt_.rpamin, opt_.rpamax);
+    sigma_ = SigmaFactory_Create(opt_.sigma_integration, Mmn_, rpa_);
+    Sigma_base::options sigma_opt;
+    sigma_opt.homo = opt_.homo;
+    sigma_opt.qpmax = opt_.qpmax;
+    sigma_opt.qpmin = opt_.qpmin;
+    sigma_opt.rpamin = opt_.rpamin;
+    sigma_opt.rpamax = opt_.rpamax;
+    sigma_opt.eta = opt_.eta;
+    sigma_opt.alpha = opt_.alpha;
+    sigma_opt.quadrature_scheme = opt_.quadrature_scheme;
+    sigma_opt.order = opt_.order;
+    sigma_->configure(sigma_opt);
+    Sigma_x_ = MatrixXd::Zero(qptotal_, qptotal_);
+    Sigma_c_ = MatrixXd::Zero(qptotal_, qptotal_);
+  }
+
+  // gw.cc:67-72
+  MatrixXd getHQP() const {
+    MatrixXd H = Sigma_x_ + Sigma_c_ - vxc_;
+    for (Index i = 0; i < qptotal_; ++i) H(i, i) += dft_energies_(opt_.qpmin + i);
+    return H;
+  }
+  // gw.cc:312-321
+  VectorXd getGWAResults() const {
+    VectorXd r(qptotal_);
+    for (Index i = 0; i < qptotal_; ++i)
+      r(i) = Sigma_x_(i, i) + Sigma_c_(i, i) - vxc_(i, i) + dft_energies_(opt_.qpmin + i);
+    return r;
+  }
+  VectorXd RPAInputEnergies() const { return rpa_.getRPAInputEnergies(); }
+  const MatrixXd& Sigma_x() const { return Sigma_x_; }
+  const MatrixXd& Sigma_c() const { return Sigma_c_; }
+  Index iterations() const { return gw_sc_iteration_ + 1; }
+  std::size_t sigma_batches() const { return sigma_batches_; }
+  std::size_t sigma_evaluations() const { return sigma_evaluations_; }
+
+  // gw.cc:74-78: eigen-decomposition of Hqp (device symmetric eigensolver)
+  std::pair<VectorXd, MatrixXd> DiagonalizeQPHamiltonian() const {
+    MatrixXd H = getHQP();
+    VectorXd w = Mmn_.device().sym_eig(H);
+    return {w, H};
+  }
+
+  // gw.cc:218-310
+  void CalculateGWPerturbation() {
+    Sigma_x_ = (1 - opt_.ScaHFX) * sigma_->CalcExchangeMatrix();
+    log_(" Calculated Hartree exchange contribution");
+    log_(" Scissor shifting DFT energies by: " + std::to_string(opt_.shift) + " Hrt");
+    VectorXd dft_shifted_energies = ScissorShift_DFTlevel(dft_energies_);
+    rpa_.setRPAInputEnergies(dft_shifted_energies.segment(opt_.rpamin, opt_.rpamax - opt_.rpamin + 1));
+    VectorXd frequencies = dft_shifted_energies.segment(opt_.qpmin, qptotal_);
+    Anderson mixing_;
+    mixing_.Configure(opt_.gw_mixing_order, opt_.gw_mixing_alpha);
+    for (Index i_gw = 0; i_gw < opt_.gw_sc_max_iterations; ++i_gw) {
+      gw_sc_iteration_ = i_gw;
+      if (i_gw % opt_.reset_3c == 0 && i_gw != 0) {
+        Mmn_.Rebuild();
+        log_(" Rebuilding 3c integrals");
+      }
+      sigma_->PrepareScreening();
+      log_(" Calculated screening via RPA");
+      log_(" Solving QP equations ");
+      if (opt_.gw_mixing_order > 0 && i_gw > 0) mixing_.UpdateInput(frequencies);
+      frequencies = SolveQP(frequencies);
+      if (opt_.gw_sc_max_iterations > 1) {
+        VectorXd rpa_energies_old = rpa_.getRPAInputEnergies();
+        if (opt_.gw_mixing_order > 0 && i_gw > 0) {
+          mixing_.UpdateOutput(frequencies);
+          VectorXd mixed_frequencies = mixing_.MixHistory();
+          rpa_.UpdateRPAInputEnergies(dft_energies_, mixed_frequencies, opt_.qpmin);
+          frequencies = mixed_frequencies;
+        } else {
+          rpa_.UpdateRPAInputEnergies(dft_energies_, frequencies, opt_.qpmin);
+        }
+        log_(" GW_Iteration:" + std::to_string(i_gw) + " Shift[Hrt]:" + std::to_string(CalcHomoLumoShift(frequencies)));
+        if (Converged(rpa_.getRPAInputEnergies(), rpa_energies_old, opt_.gw_sc_limit)) {
+          log_(" Converged after " + std::to_string(i_gw + 1) + " GW iterations.");
+          break;
+        } else if (i_gw == opt_.gw_sc_max_iterations - 1) {
+          log_(" WARNING! GW-self-consistency cycle not converged after " +
+               std::to_string(opt_.gw_sc_max_iterations) + " iterations.");
+          log_("      Run continues. Inspect results carefully!");
+          break;
+        }
+      }
+    }
+    VectorXd diag = sigma_->CalcCorrelationDiag(frequencies);
+    for (Index i = 0; i < qptotal_; ++i) Sigma_c_(i, i) = diag(i);
+  }
+
+  // gw.cc:772-776
+  void CalculateHQP() {
+    VectorXd diag_backup = Sigma_c_.diagonal();
+    Sigma_c_ = sigma_->CalcCorrelationOffDiag(getGWAResults());
+    for (Index i = 0; i < qptotal_; ++i) Sigma_c_(i, i) = diag_backup(i);
+  }
+
+ private:
+  // f(w) = Sigma_c(w) + offset - w, gw.h:214-300; Sigma_c requests go through the batcher
+  class QPFunc {
+   public:
+    QPFunc(Index gw_level, SigmaBatcher& batcher, double offset)
+        : gw_level_(gw_level), offset_(offset), batcher_(batcher) {}
+    std::pair<double, double> operator()(double frequency) const {
+      double s, ds;
+      batcher_.Evaluate(gw_level_, frequency, true, s, ds);
+      Count(frequency, EvalStage::Other);
+      ++stats_.deriv_calls;
+      return {s + offset_ - frequency, ds - 1.0};
+    }
+    double sigma(double frequency, EvalStage stage = EvalStage::Other) const {
+      Count(frequency, stage);
+      double s, ds;
+      batcher_.Evaluate(gw_level_, frequency, false, s, ds);
+      return s;
+    }
+    double value(double frequency, EvalStage stage = EvalStage::Other) const {
+      return sigma(frequency, stage) + offset_ - frequency;
+    }
+    double deriv(double frequency) const {
+      ++stats_.deriv_calls;
+      double s, ds;
+      batcher_.Evaluate(gw_level_, frequency, true, s, ds);
+      return ds - 1.0;
+    }
+    const QPStats& GetStats() const { return stats_; }
+
+   private:
+    void Count(double x, EvalStage stage) const {
+      std::uint64_t key = 0;
+      std::memcpy(&key, &x, sizeof(double));
+      if (!seen_frequencies_.insert(key).second)
+        ++stats_.sigma_repeat_calls;
+      else
+        ++stats_.sigma_unique_frequencies;
+      switch (stage) {
+        case EvalStage::Scan: ++stats_.sigma_scan_calls; break;
+        case EvalStage::Refine: ++stats_.sigma_refine_calls; break;
+        case EvalStage::Derivative: ++stats_.sigma_derivative_calls; break;
+        default: ++stats_.sigma_other_calls; break;
+      }
+    }
+    Index gw_level_;
+    double offset_;
+    SigmaBatcher& batcher_;
+    mutable std::unordered_set<std::uint64_t> seen_frequencies_;
+    mutable QPStats stats_;
+  };
+
+  double CalcHomoLumoShift(const VectorXd& frequencies) const {
+    double DFTgap = dft_energies_(opt_.homo + 1) - dft_energies_(opt_.homo);
+    double QPgap = frequencies(opt_.homo + 1 - opt_.qpmin) - frequencies(opt_.homo - opt_.qpmin);
+    return QPgap - DFTgap;
+  }
+  VectorXd ScissorShift_DFTlevel(const VectorXd& dft_energies) const {
+    VectorXd shifted = dft_energies;
+    for (Index i = opt_.homo + 1; i < shifted.size(); ++i) shifted(i) += opt_.shift;
+    return shifted;
+  }
+  bool Converged(const VectorXd& e1, const VectorXd& e2, double epsilon) const {
+    Index state = 0;
+    double diff_max = 0.0;
+    for (Index i = 0; i < e1.size(); ++i)
+      if (std::abs(e1(i) - e2(i)) > diff_max) {
+        diff_max = std::abs(e1(i) - e2(i));
+        state = i;
+      }
+    log_(" E_diff max=" + std::to_string(diff_max) + " StateNo:" + std::to_string(state));
+    return !(diff_max > epsilon);
+  }
+
+  // gw.cc:323-410: one host thread per level (the reference's dynamic OpenMP loop), batched Sigma_c
+  VectorXd SolveQP(const VectorXd& frequencies) {
+    sigma_->ResetDiagEvalCounter();
+    VectorXd intercepts(qptotal_);
+    for (Index i = 0; i < qptotal_; ++i)
+      intercepts(i) = dft_energies_(opt_.qpmin + i) + Sigma_x_(i, i) - vxc_(i, i);
+    VectorXd frequencies_new = frequencies;
+    std::vector<char> converged(qptotal_, 0);
+    std::vector<QPStats> stats(qptotal_);
+    std::vector<std::string> errors(qptotal_);
+    SigmaBatcher batcher(*sigma_);
+    std::vector<std::thread> workers;
+    workers.reserve(qptotal_);
+    for (Index gw_level = 0; gw_level < qptotal_; ++gw_level) batcher.WorkerStarted();
+    for (Index gw_level = 0; gw_level < qptotal_; ++gw_level) {
+      workers.emplace_back([&, gw_level] {
+        try {
+          double initial_f = frequencies[gw_level];
+          double intercept = intercepts[gw_level];
+          std::optional<double> newf;
+          if (opt_.qp_solver == "fixedpoint")
+            newf = SolveQP_FixedPoint(batcher, intercept, initial_f, gw_level, &stats[gw_level]);
+          if (newf) {
+            frequencies_new[gw_level] = *newf;
+            converged[gw_level] = 1;
+          } else {
+            newf = SolveQP_Grid(batcher, intercept, initial_f, gw_level, &stats[gw_level]);
+            if (newf) {
+              frequencies_new[gw_level] = *newf;
+              converged[gw_level] = 1;
+            } else {
+              newf = SolveQP_Linearisation(batcher, intercept, initial_f, gw_level, &stats[gw_level]);
+              if (newf) frequencies_new[gw_level] = *newf;
+            }
+          }
+        } catch (const std::exception& e) {
+          errors[gw_level] = e.what();
+        }
+        batcher.WorkerFinished();
+      });
+    }
+    batcher.Serve();
+    for (auto& t : workers) t.join();
+    for (const auto& e : errors)
+      if (!e.empty()) throw std::runtime_error(e);
+    QPStats total_stats;
+    for (const auto& s : stats) total_stats.Add(s);
+    sigma_batches_ += batcher.batches();
+    sigma_evaluations_ += batcher.evaluations();
+    std::string notconv;
+    for (Index s = 0; s < qptotal_; ++s)
+      if (!converged[s]) notconv += " " + std::to_string(s);
+    if (!notconv.empty()) {
+      log_(" Not converged PQP states are:" + notconv);
+      log_(" Increase the grid search interval");
+    }
+    log_(" Sigma diagonal evaluations in SolveQP: " + std::to_string(batcher.evaluations()) + " in " +
+         std::to_string(batcher.batches()) + " batched kernel passes");
+    log_(" QP diagnostics: scan=" + std::to_string(total_stats.sigma_scan_calls) +
+         " refine=" + std::to_string(total_stats.sigma_refine_calls) +
+         " other=" + std::to_string(total_stats.sigma_other_calls) +
+         " total_sigma=" + std::to_string(total_stats.TotalSigmaCalls()) +
+         " unique_omega=" + std::to_string(total_stats.sigma_unique_frequencies) +
+         " repeat_sigma=" + std::to_string(total_stats.sigma_repeat_calls) +
+         " deriv_calls=" + std::to_string(total_stats.deriv_calls));
+    return frequencies_new;
+  }
+
+  qp_solver::SolverOptions MakeSolverOptions() const {
+    qp_solver::SolverOptions s;
+    s.g_sc_limit = opt_.g_sc_limit;
+    s.qp_bisection_max_iter = opt_.g_sc_max_iterations;
+    s.qp_full_window_half_width = opt_.qp_full_window_half_width;
+    s.qp_dense_spacing = opt_.qp_dense_spacing;
+    s.qp_adaptive_shell_width = opt_.qp_adaptive_shell_width;
+    s.qp_adaptive_shell_count = opt_.qp_adaptive_shell_count;
+    return s;
+  }
+
+  // gw.cc:412-431
+  std::optional<double> SolveQP_Linearisation(SigmaBatcher& b, double intercept0, double frequency0, Index gw_level,
+                                              QPStats* stats) const {
+    std::optional<double> newf;
+    QPFunc fqp(gw_level, b, intercept0);
+    double sigma = fqp.sigma(frequency0, EvalStage::Other);
+    double dsigma_domega = fqp.deriv(frequency0);
+    double Z = 1.0 - dsigma_domega;
+    if (std::abs(Z) > 1e-9) newf = frequency0 + (intercept0 - frequency0 + sigma) / Z;
+    if (stats) *stats = fqp.GetStats();
+    return newf;
+  }
+
+  // gw.cc:433-502
+  std::optional<double> SolveQP_Grid_Windowed_Adaptive(SigmaBatcher& b, double intercept0, double frequency0,
+                                                       Index gw_level, double left_limit, double right_limit,
+                                                       bool allow_rejected_return, QPStats* stats) const {
+    QPFunc fqp(gw_level, b, intercept0);
+    qp_solver::SolverOptions solver_opt = MakeSolverOptions();
+    QPWindowDiagnostics wdiag;
+    std::vector<QPRootCandidate> accepted_roots, rejected_roots;
+    const bool use_brent = (opt_.qp_root_finder == "brent");
+    auto result = qp_solver::SolveQP_Grid_Windowed(fqp, frequency0, left_limit, right_limit, gw_sc_iteration_,
+                                                   solver_opt, &wdiag, &accepted_roots, &rejected_roots, use_brent);
+    if (stats) *stats = fqp.GetStats();
+    if (!accepted_roots.empty()) return result;
+    if (!rejected_roots.empty() && !allow_rejected_return) return std::nullopt;
+    return result;
+  }
+
+  // gw.cc:504-616
+  std::optional<double> SolveQP_Grid_Windowed_Dense(SigmaBatcher& b, double intercept0, double frequency0,
+                                                    Index gw_level, double left_limit, double right_limit,
+                                                    bool allow_rejected_return, QPStats* stats) const {
+    QPFunc fqp(gw_level, b, intercept0);
+    qp_solver::SolverOptions solver_opt = MakeSolverOptions();
+    const bool use_brent = (opt_.qp_root_finder == "brent");
+    std::vector<QPRootCandidate> accepted_roots, rejected_roots;
+    if (left_limit < right_limit) {
+      double freq_prev = left_limit;
+      double targ_prev = fqp.value(freq_prev, EvalStage::Scan);
+      const Index n_steps =
+          std::max<Index>(2, static_cast<Index>(std::ceil((right_limit - left_limit) / opt_.qp_dense_spacing)) + 1);
+      for (Index i_node = 1; i_node < n_steps; ++i_node) {
+        const double freq =
+            (i_node == n_steps - 1)
+                ? right_limit
+                : std::min(right_limit, left_limit + static_cast<double>(i_node) * opt_.qp_dense_spacing);
+        const double targ = fqp.value(freq, EvalStage::Scan);
+        if (targ_prev * targ < 0.0) {
+          auto cand =
+              qp_solver::RefineQPInterval(freq_prev, targ_prev, freq, targ, fqp, frequency0, solver_opt, use_brent);
+          if (cand) (cand->accepted ? accepted_roots : rejected_roots).push_back(*cand);
+        }
+        freq_prev = freq;
+        targ_prev = targ;
+      }
+    }
+    if (stats) *stats = fqp.GetStats();
+    if (!accepted_roots.empty()) return qp_solver::BestRoot(accepted_roots).omega;
+    if (!rejected_roots.empty()) {
+      if (!allow_rejected_return) return std::nullopt;
+      return qp_solver::BestRoot(rejected_roots).omega;
+    }
+    return std::nullopt;
+  }
+
+  // gw.cc:618-675
+  std::optional<double> SolveQP_Grid_Windowed(SigmaBatcher& b, double intercept0, double frequency0, Index gw_level,
+                                              double left_limit, double right_limit, bool allow_rejected_return,
+                                              QPStats* stats) const {
+    if (opt_.qp_grid_search_mode == "adaptive")
+      return SolveQP_Grid_Windowed_Adaptive(b, intercept0, frequency0, gw_level, left_limit, right_limit,
+                                            allow_rejected_return, stats);
+    if (opt_.qp_grid_search_mode == "dense")
+      return SolveQP_Grid_Windowed_Dense(b, intercept0, frequency0, gw_level, left_limit, right_limit,
+                                         allow_rejected_return, stats);
+    if (opt_.qp_grid_search_mode == "adaptive_with_dense_fallback") {
+      QPStats total_stats;
+      auto adaptive = SolveQP_Grid_Windowed_Adaptive(b, intercept0, frequency0, gw_level, left_limit, right_limit,
+                                                     allow_rejected_return, &total_stats);
+      if (adaptive) {
+        if (stats) *stats = total_stats;
+        return adaptive;
+      }
+      QPStats dense_stats;
+      auto dense = SolveQP_Grid_Windowed_Dense(b, intercept0, frequency0, gw_level, left_limit, right_limit,
+                                               allow_rejected_return, &dense_stats);
+      total_stats.Add(dense_stats);
+      if (stats) *stats = total_stats;
+      return dense;
+    }
+    throw std::runtime_error("Unknown gw.qp_grid_search_mode '" + opt_.qp_grid_search_mode + "'");
+  }
+
+  // gw.cc:677-739
+  std::optional<double> SolveQP_Grid(SigmaBatcher& b, double intercept0, double frequency0, Index gw_level,
+                                     QPStats* stats) const {
+    const double range = opt_.qp_full_window_half_width;
+    const double full_left_limit = frequency0 - range;
+    const double full_right_limit = frequency0 + range;
+    double restricted_left_limit = full_left_limit;
+    double restricted_right_limit = full_right_limit;
+    bool use_restricted_window = false;
+    if (opt_.qp_restrict_search) {
+      const Index mo_level = gw_level + opt_.qpmin;
+      const bool is_occupied = (mo_level <= opt_.homo);
+      if (is_occupied)
+        restricted_right_limit = std::min(full_right_limit, -opt_.qp_zero_margin);
+      else
+        restricted_left_limit = std::max(full_left_limit, opt_.qp_virtual_min_energy);
+      const double tol = 1e-12;
+      use_restricted_window = (std::abs(restricted_left_limit - full_left_limit) > tol) ||
+                              (std::abs(restricted_right_limit - full_right_limit) > tol);
+    }
+    if (use_restricted_window && restricted_left_limit < restricted_right_limit) {
+      auto restricted = SolveQP_Grid_Windowed(b, intercept0, frequency0, gw_level, restricted_left_limit,
+                                              restricted_right_limit, false, stats);
+      if (restricted) return restricted;
+      return SolveQP_Grid_Windowed_Dense(b, intercept0, frequency0, gw_level, full_left_limit, full_right_limit,
+                                         true, stats);
+    }
+    return SolveQP_Grid_Windowed(b, intercept0, frequency0, gw_level, full_left_limit, full_right_limit, true, stats);
+  }
+
+  // gw.cc:741-757
+  std::optional<double> SolveQP_FixedPoint(SigmaBatcher& b, double intercept0, double frequency0, Index gw_level,
+                                           QPStats* stats) const {
+    std::optional<double> newf;
+    QPFunc f(gw_level, b, intercept0);
+    NewtonRapson<QPFunc> newton(opt_.g_sc_max_iterations, opt_.g_sc_limit, opt_.qp_solver_alpha);
+    double freq_new = newton.FindRoot(f, frequency0);
+    if (newton.getInfo() == NewtonRapson<QPFunc>::success) newf = freq_new;
+    if (stats) *stats = f.GetStats();
+    return newf;
+  }
+
+  Index qptotal_ = 0;
+  MatrixXd Sigma_x_, Sigma_c_;
+  options opt_;
+  std::unique_ptr<Sigma_base> sigma_;
+  Logger& log_;
+  TCMatrix_gwbse& Mmn_;
+  const MatrixXd& vxc_;
+  const VectorXd& dft_energies_;
+  Index gw_sc_iteration_ = 0;
+  std::size_t sigma_batches_ = 0, sigma_evaluations_ = 0;
+  RPA rpa_;
+};
+
+}  // namespace xtp
+}  // namespace votca

@@ -1,0 +1,394 @@
+// GWBSE - host mirror of the orchestrator xtp/src/libxtp/gwbse/gwbse.cc:60-578 (Initialize: options ->
+// level ranges and solver settings, same option keys as share/xtp/xml/subpackages/gwbse.xml) and
+// gwbse.cc:822-1250 (Evaluate: Mmn -> GW -> BSE).  Inputs that the reference takes from the Orbitals
+// object (MO coefficients/energies, homo, Vxc from libxc, AO integrals from libint, AO dipoles) are
+// supplied by the caller; outputs use the dataset names of the .orb file (orbitals.cc:990-1063).
+#pragma once
+#include <chrono>
+#include <cstdio>
+#include <fstream>
+#include <map>
+#include <sstream>
+
+#include "bse.h"
+#include "gw.h"
+
+namespace votca {
+namespace xtp {
+
+// Minimal stand-in for tools::Property restricted to what GWBSE::Initialize reads: a flat map of
+// dotted keys ("gw.mode", "bse.davidson.tolerance", ...) with the defaults of gwbse.xml.
+class Options {
+ public:
+  Options() {
+    // share/xtp/xml/subpackages/gwbse.xml
+    const char* defaults[][2] = {
+        {"tasks", "all"}, {"ranges", "default"}, {"ignore_corelevels", "none"},
+        {"gw.mode", "evGW"}, {"gw.scissor_shift", "0.0"}, {"gw.sigma_integrator", "ppm"}, {"gw.eta", "1e-3"},
+        {"gw.alpha", "1e-3"}, {"gw.quadrature_scheme", "legendre"}, {"gw.quadrature_order", "12"},
+        {"gw.qp_solver", "grid"}, {"gw.qp_grid_search_mode", "adaptive_with_dense_fallback"},
+        {"gw.qp_root_finder", "bisection"}, {"gw.qp_restrict_search", "true"}, {"gw.qp_zero_margin", "1e-6"},
+        {"gw.qp_virtual_min_energy", "-0.1"}, {"gw.qp_sc_max_iter", "100"}, {"gw.qp_sc_limit", "1e-5"},
+        {"gw.sc_max_iter", "50"}, {"gw.mixing_order", "20"}, {"gw.sc_limit", "1e-5"}, {"gw.mixing_alpha", "0.7"},
+        {"gw.rebuild_3c_freq", "5"}, {"bse.exctotal", "10"}, {"bse.useTDA", "false"},
+        {"bse.dyn_screen_max_iter", "0"}, {"bse.dyn_screen_tol", "1e-5"}, {"bse.davidson.correction", "DPR"},
+        {"bse.davidson.tolerance", "normal"}, {"bse.davidson.update", "safe"}, {"bse.davidson.maxiter", "50"},
+        {"bse.use_Hqp_offdiag", "false"}, {"bse.print_weight", "0.5"}};
+    for (auto& d : defaults) kv_[d[0]] = d[1];
+  }
+  void set(const std::string& key, const std::string& value) {
+    std::string k = key;
+    for (const char* pre : {"options.dftgwbse.gwbse.", "dftgwbse.gwbse.", "gwbse.", "."})
+      if (k.rfind(pre, 0) == 0) {
+        k = k.substr(std::string(pre).size());
+        break;
+      }
+    kv_[k] = value;
+  }
+  bool exists(const std::string& key) const {
+    auto it = kv_.find(key);
+    return it != kv_.end() && !it->second.empty();
+  }
+  std::string str(const std::string& key) const {
+    auto it = kv_.find(key);
+    if (it == kv_.end()) throw std::runtime_error("option '" + key + "' not found");
+    return it->second;
+  }
+  double dbl(const std::string& key) const { return std::stod(str(key)); }
+  Index idx(const std::string& key) const { return static_cast<Index>(std::stol(str(key))); }
+  bool flag(const std::string& key) const {
+    const std::string v = str(key);
+    if (v == "true" || v == "1") return true;
+    if (v == "false" || v == "0") return false;
+    throw std::runtime_error("option '" + key + "' is not a bool: " + v);
+  }
+
+  // Reads an options XML as the reference accepts with -o (elements nest, text is the value); every leaf
+  // below <gwbse> becomes a dotted key.  Attributes and comments are ignored.
+  void LoadFromXML(const std::string& path) {
+    std::ifstream f(path);
+    if (!f) throw std::runtime_error("cannot open options file " + path);
+    std::stringstream ss;
+    ss << f.rdbuf();
+    const std::string s = ss.str();
+    std::vector<std::string> stack;
+    size_t i = 0;
+    std::string text;
+    while (i < s.size()) {
+      if (s[i] == '<') {
+        if (s.compare(i, 4, "<!--") == 0) {
+          i = s.find("-->", i);
+          i = (i == std::string::npos) ? s.size() : i + 3;
+          continue;
+        }
+        size_t j = s.find('>', i);
+        if (j == std::string::npos) throw std::runtime_error("malformed XML in " + path);
+        std::string tag = s.substr(i + 1, j - i - 1);
+        i = j + 1;
+        if (tag.empty() || tag[0] == '?' || tag[0] == '!') continue;
+        if (tag[0] == '/') {
+          std::string t;
+          for (char c : text)
+            if (!std::isspace(static_cast<unsigned char>(c)) || !t.empty()) t += c;
+          while (!t.empty() && std::isspace(static_cast<unsigned char>(t.back()))) t.pop_back();
+          if (!t.empty() && !stack.empty()) {
+            std::string key;
+            bool in_gwbse = false;
+            for (const auto& e : stack) {
+              if (in_gwbse) key += (key.empty() ? "" : ".") + e;
+              if (e == "gwbse") in_gwbse = true;
+            }
+            if (in_gwbse && !key.empty()) kv_[key] = t;
+          }
+          text.clear();
+          if (!stack.empty()) stack.pop_back();
+        } else {
+          const bool selfclose = tag.back() == '/';
+          std::string name = tag.substr(0, tag.find_first_of(" \t\r\n/"));
+          text.clear();
+          if (!selfclose) stack.push_back(name);
+        }
+      } else {
+        text += s[i++];
+      }
+    }
+  }
+
+ private:
+  std::map<std::string, std::string> kv_;
+};
+
+class GWBSE {
+ public:
+  struct Inputs {
+    Index homo = -1;                       // Orbitals::getHomo()
+    const MatrixXd* mos = nullptr;         // MOs().eigenvectors()
+    const VectorXd* mo_energies = nullptr;  // MOs().eigenvalues()
+    const MatrixXd* vxc = nullptr;         // qptotal x qptotal, CalculateVXC (gwbse.cc:750-788) is host/libxc work
+    double ScaHFX = 0.0;                   // Orbitals::getScaHFX()
+    const AOIntegralSource* integrals = nullptr;
+    const std::vector<MatrixXd>* interlevel_dipoles = nullptr;  // optional: CalcFreeTransition_Dipoles
+    // BSE-only runs (do_gw == false): orbitals_.QPdiag / RPAInputEnergies from a previous run
+    const MatrixXd* Hqp = nullptr;
+    const VectorXd* rpa_input_energies = nullptr;
+  };
+  struct Results {
+    Index rpamin = 0, rpamax = 0, qpmin = 0, qpmax = 0, bse_vmin = 0, bse_cmax = 0;
+    VectorXd RPA_inputenergies, QPpert_energies;
+    VectorXd QPdiag_eigenvalues;
+    MatrixXd QPdiag_eigenvectors, Hqp, Sigma_x, Sigma_c;
+    EigenSystem BSE_singlet, BSE_triplet;
+    VectorXd BSE_singlet_dynamic, BSE_triplet_dynamic;
+    std::vector<VectorXd> transition_dipoles;
+    VectorXd oscillator_strengths;
+    BSE::Interaction singlet_analysis, triplet_analysis;
+    Index removed_functions = 0, gw_iterations = 0;
+    Index singlet_davidson_iterations = 0, triplet_davidson_iterations = 0;
+    std::size_t sigma_batches = 0, sigma_evaluations = 0;
+    double time_fill = 0, time_gw = 0, time_bse = 0;
+  };
+
+  GWBSE(const Device& dev, Logger& log) : dev_(dev), log_(log) {}
+
+  // gwbse.cc:60-578
+  void Initialize(const Options& options, const Inputs& in) {
+    in_ = in;
+    if (!in.mos || !in.mo_energies || in.homo < 0) throw std::runtime_error("GWBSE: MOs, energies and homo required");
+    Index rpamax = 0, rpamin = 0, qpmin = 0, qpmax = 0, bse_vmin = 0, bse_cmax = 0;
+    const Index homo = in.homo;
+    const Index num_of_levels = in.mos->cols();
+    const Index num_of_occlevels = homo + 1;
+    const std::string ranges = options.str("ranges");
+    if (ranges == "factor") {
+      rpamax = Index(options.dbl("rpamax") * double(num_of_levels)) - 1;
+      qpmin = num_of_occlevels - Index(options.dbl("qpmin") * double(num_of_occlevels)) - 1;
+      qpmax = num_of_occlevels + Index(options.dbl("qpmax") * double(num_of_occlevels)) - 1;
+      bse_vmin = num_of_occlevels - Index(options.dbl("bsemin") * double(num_of_occlevels)) - 1;
+      bse_cmax = num_of_occlevels + Index(options.dbl("bsemax") * double(num_of_occlevels)) - 1;
+    } else if (ranges == "explicit") {
+      rpamax = options.idx("rpamax");
+      qpmin = options.idx("qpmin");
+      qpmax = options.idx("qpmax");
+      bse_vmin = options.idx("bsemin");
+      bse_cmax = options.idx("bsemax");
+    } else if (ranges == "default") {
+      rpamax = num_of_levels - 1;
+      qpmin = 0;
+      qpmax = 3 * homo + 1;
+      bse_vmin = 0;
+      bse_cmax = 3 * homo + 1;
+    } else if (ranges == "full") {
+      rpamax = num_of_levels - 1;
+      qpmin = 0;
+      qpmax = num_of_levels - 1;
+      bse_vmin = 0;
+      bse_cmax = num_of_levels - 1;
+    } else {
+      throw std::runtime_error("unknown ranges option '" + ranges + "'");
+    }
+    if (options.str("ignore_corelevels") != "none")
+      throw std::runtime_error("ignore_corelevels needs the ECP/element tables of the host package (not on this path)");
+    if (rpamax >= num_of_levels) rpamax = num_of_levels - 1;
+    if (qpmax >= num_of_levels) qpmax = num_of_levels - 1;
+    if (bse_cmax >= num_of_levels) bse_cmax = num_of_levels - 1;
+    if (bse_vmin < 0) bse_vmin = 0;
+    if (qpmin < 0) qpmin = 0;
+    const Index bse_vmax = homo, bse_cmin = homo + 1;
+    if (rpamin < 0 || rpamax < 0 || rpamin > rpamax)
+      throw std::runtime_error("Invalid RPA level range after setup/clamping.");
+    if (qpmin < 0 || qpmax < 0 || qpmin > qpmax) throw std::runtime_error("Invalid GW level range after setup/clamping.");
+    if (bse_vmin < 0 || bse_vmax < 0 || bse_vmin > bse_vmax)
+      throw std::runtime_error("Invalid BSE occupied level range after setup/clamping.");
+    if (bse_cmin < 0 || bse_cmax < 0 || bse_cmin > bse_cmax)
+      throw std::runtime_error("Invalid BSE virtual level range after setup/clamping.");
+    if (bse_vmax >= num_of_levels || bse_cmax >= num_of_levels)
+      throw std::runtime_error("BSE level range exceeds available orbital indices.");
+    gwopt_.homo = homo;
+    gwopt_.qpmin = qpmin;
+    gwopt_.qpmax = qpmax;
+    gwopt_.rpamin = rpamin;
+    gwopt_.rpamax = rpamax;
+    bseopt_.vmin = bse_vmin;
+    bseopt_.cmax = bse_cmax;
+    bseopt_.homo = homo;
+    bseopt_.qpmin = qpmin;
+    bseopt_.qpmax = qpmax;
+    bseopt_.rpamin = rpamin;
+    bseopt_.rpamax = rpamax;
+    const Index bse_size = (bse_vmax - bse_vmin + 1) * (bse_cmax - bse_cmin + 1);
+    log_(" RPA level range [" + std::to_string(rpamin) + ":" + std::to_string(rpamax) + "]");
+    log_(" GW  level range [" + std::to_string(qpmin) + ":" + std::to_string(qpmax) + "]");
+    log_(" BSE level range occ[" + std::to_string(bse_vmin) + ":" + std::to_string(bse_vmax) + "]  virt[" +
+         std::to_string(bse_cmin) + ":" + std::to_string(bse_cmax) + "]");
+    gwopt_.reset_3c = options.idx("gw.rebuild_3c_freq");
+    bseopt_.nmax = options.idx("bse.exctotal");
+    if (bseopt_.nmax > bse_size || bseopt_.nmax < 0) bseopt_.nmax = bse_size;
+    bseopt_.davidson_correction = options.str("bse.davidson.correction");
+    bseopt_.davidson_tolerance = options.str("bse.davidson.tolerance");
+    bseopt_.davidson_update = options.str("bse.davidson.update");
+    bseopt_.davidson_maxiter = options.idx("bse.davidson.maxiter");
+    bseopt_.useTDA = options.flag("bse.useTDA");
+    log_(bseopt_.useTDA ? " BSE type: TDA" : " BSE type: full");
+    const Index full_bse_size = bseopt_.useTDA ? bse_size : 2 * bse_size;
+    log_(" BSE Hamiltonian has size " + std::to_string(full_bse_size) + "x" + std::to_string(full_bse_size));
+    bseopt_.use_Hqp_offdiag = options.flag("bse.use_Hqp_offdiag");
+    bseopt_.max_dyn_iter = options.idx("bse.dyn_screen_max_iter");
+    bseopt_.dyn_tolerance = options.dbl("bse.dyn_screen_tol");
+    do_dynamical_screening_bse_ = bseopt_.max_dyn_iter > 0;
+    const std::string mode = options.str("gw.mode");
+    if (mode == "G0W0") {
+      gwopt_.gw_sc_max_iterations = 1;
+    } else if (mode == "evGW") {
+      gwopt_.gw_sc_max_iterations = options.idx("gw.sc_max_iter");
+    } else {
+      throw std::runtime_error("unknown gw.mode '" + mode + "'");
+    }
+    log_(" Running GW as: " + mode);
+    gwopt_.ScaHFX = in.ScaHFX;
+    gwopt_.shift = options.dbl("gw.scissor_shift");
+    gwopt_.g_sc_limit = options.dbl("gw.qp_sc_limit");
+    gwopt_.g_sc_max_iterations = options.idx("gw.qp_sc_max_iter");
+    gwopt_.gw_sc_limit = options.dbl("gw.sc_limit");
+    bseopt_.min_print_weight = options.dbl("bse.print_weight");
+    std::string tasks = options.str("tasks");
+    for (char& c : tasks) c = static_cast<char>(std::tolower(static_cast<unsigned char>(c)));
+    do_gw_ = tasks.find("gw") != std::string::npos;
+    if (tasks.find("all") != std::string::npos) do_gw_ = do_bse_singlets_ = do_bse_triplets_ = true;
+    if (tasks.find("singlets") != std::string::npos) do_bse_singlets_ = true;
+    if (tasks.find("triplets") != std::string::npos) do_bse_triplets_ = true;
+    gwopt_.sigma_integration = options.str("gw.sigma_integrator");
+    log_(" Sigma integration: " + gwopt_.sigma_integration);
+    gwopt_.eta = options.dbl("gw.eta");
+    if (gwopt_.sigma_integration == "exact")
+      log_(" RPA Hamiltonian size: " + std::to_string((homo + 1 - rpamin) * (rpamax - homo)));
+    if (gwopt_.sigma_integration == "cda") {
+      gwopt_.order = options.idx("gw.quadrature_order");
+      gwopt_.quadrature_scheme = options.str("gw.quadrature_scheme");
+      gwopt_.alpha = options.dbl("gw.alpha");
+    }
+    gwopt_.qp_solver = options.str("gw.qp_solver");
+    if (gwopt_.qp_solver == "grid") {
+      if (options.exists("gw.qp_full_window_half_width"))
+        gwopt_.qp_full_window_half_width = options.dbl("gw.qp_full_window_half_width");
+      if (options.exists("gw.qp_dense_spacing")) gwopt_.qp_dense_spacing = options.dbl("gw.qp_dense_spacing");
+      if (options.exists("gw.qp_adaptive_shell_width"))
+        gwopt_.qp_adaptive_shell_width = options.dbl("gw.qp_adaptive_shell_width");
+      if (options.exists("gw.qp_adaptive_shell_count"))
+        gwopt_.qp_adaptive_shell_count = options.idx("gw.qp_adaptive_shell_count");
+      const bool has_steps = options.exists("gw.qp_grid_steps"), has_spacing = options.exists("gw.qp_grid_spacing");
+      if (has_steps != has_spacing)
+        throw std::runtime_error(
+            "Deprecated gw.qp_grid_steps and gw.qp_grid_spacing must be given together if either is used.");
+      if (has_steps) {
+        gwopt_.qp_grid_steps = options.idx("gw.qp_grid_steps");
+        gwopt_.qp_grid_spacing = options.dbl("gw.qp_grid_spacing");
+      }
+      qp_solver::NormalizeGridSearchOptions(gwopt_);
+    }
+    gwopt_.qp_root_finder = options.str("gw.qp_root_finder");
+    gwopt_.gw_mixing_order = options.idx("gw.mixing_order");
+    gwopt_.gw_mixing_alpha = options.dbl("gw.mixing_alpha");
+    gwopt_.qp_grid_search_mode = options.str("gw.qp_grid_search_mode");
+    gwopt_.qp_restrict_search = options.flag("gw.qp_restrict_search");
+    gwopt_.qp_zero_margin = options.dbl("gw.qp_zero_margin");
+    gwopt_.qp_virtual_min_energy = options.dbl("gw.qp_virtual_min_energy");
+  }
+
+  const GW::options& gw_options() const { return gwopt_; }
+  const BSE::options& bse_options() const { return bseopt_; }
+
+  // gwbse.cc:822-1250
+  Results Evaluate() {
+    using clock = std::chrono::system_clock;
+    Results res;
+    res.rpamin = gwopt_.rpamin;
+    res.rpamax = gwopt_.rpamax;
+    res.qpmin = gwopt_.qpmin;
+    res.qpmax = gwopt_.qpmax;
+    res.bse_vmin = bseopt_.vmin;
+    res.bse_cmax = bseopt_.cmax;
+    if (!in_.integrals) throw std::runtime_error("GWBSE: AO integral source required");
+    if (!do_gw_ && !(in_.Hqp && in_.rpa_input_energies))
+      throw std::runtime_error("You want no GW calculation but the orb file has no matching QP coefficients.");
+    auto t0 = clock::now();
+    TCMatrix_gwbse Mmn(dev_);
+    const Index max_3c = std::max(bseopt_.cmax, gwopt_.qpmax);
+    Mmn.Initialize(in_.integrals->AuxSize(), gwopt_.rpamin, max_3c, gwopt_.rpamin, gwopt_.rpamax);
+    log_(" Calculating Mmn_beta (3-center-repulsion x orbitals)  ");
+    Mmn.Fill(*in_.integrals, *in_.mos);
+    res.removed_functions = Mmn.Removedfunctions();
+    log_(" Removed " + std::to_string(Mmn.Removedfunctions()) + " functions from Aux Coulomb matrix to avoid near linear dependencies");
+    res.time_fill = std::chrono::duration<double>(clock::now() - t0).count();
+    MatrixXd Hqp;
+    VectorXd rpa_e;
+    if (do_gw_) {
+      auto start = clock::now();
+      if (!in_.vxc) throw std::runtime_error("GWBSE: Vxc matrix required for GW");
+      GW gw(log_, Mmn, *in_.vxc, *in_.mo_energies);
+      gw.configure(gwopt_);
+      gw.CalculateGWPerturbation();
+      res.QPpert_energies = gw.getGWAResults();
+      res.RPA_inputenergies = gw.RPAInputEnergies();
+      gw.CalculateHQP();
+      Hqp = gw.getHQP();
+      auto es = gw.DiagonalizeQPHamiltonian();
+      res.QPdiag_eigenvalues = es.first;
+      res.QPdiag_eigenvectors = es.second;
+      res.Sigma_x = gw.Sigma_x();
+      res.Sigma_c = gw.Sigma_c();
+      res.gw_iterations = gw.iterations();
+      res.sigma_batches = gw.sigma_batches();
+      res.sigma_evaluations = gw.sigma_evaluations();
+      res.time_gw = std::chrono::duration<double>(clock::now() - start).count();
+      char buf[96];
+      std::snprintf(buf, sizeof(buf), " GW calculation took %f seconds.", res.time_gw);
+      log_(buf);
+      rpa_e = res.RPA_inputenergies;
+    } else {
+      Hqp = *in_.Hqp;
+      rpa_e = *in_.rpa_input_energies;
+      res.RPA_inputenergies = rpa_e;
+    }
+    res.Hqp = Hqp;
+    if (do_bse_singlets_ || do_bse_triplets_) {
+      auto start = clock::now();
+      BSE bse(log_, Mmn);
+      bse.configure(bseopt_, rpa_e, Hqp);
+      if (do_bse_triplets_) {
+        res.BSE_triplet = bse.Solve_triplets();
+        res.triplet_davidson_iterations = bse.last_davidson_iterations();
+        res.triplet_analysis = bse.Analyze_eh_interaction(false, res.BSE_triplet);
+      }
+      if (do_bse_singlets_) {
+        res.BSE_singlet = bse.Solve_singlets();
+        res.singlet_davidson_iterations = bse.last_davidson_iterations();
+        if (in_.interlevel_dipoles) {
+          res.transition_dipoles = bse.CalcCoupledTransition_Dipoles(res.BSE_singlet, *in_.interlevel_dipoles);
+          res.oscillator_strengths = BSE::Oscillatorstrengths(res.transition_dipoles, res.BSE_singlet.eigenvalues);
+        }
+        res.singlet_analysis = bse.Analyze_eh_interaction(true, res.BSE_singlet);
+      }
+      if (do_dynamical_screening_bse_) {
+        if (do_bse_triplets_) res.BSE_triplet_dynamic = bse.Perturbative_DynamicalScreening(res.BSE_triplet, rpa_e);
+        if (do_bse_singlets_) res.BSE_singlet_dynamic = bse.Perturbative_DynamicalScreening(res.BSE_singlet, rpa_e);
+      }
+      res.time_bse = std::chrono::duration<double>(clock::now() - start).count();
+      char buf[96];
+      std::snprintf(buf, sizeof(buf), " BSE calculation took %f seconds.", res.time_bse);
+      log_(buf);
+    }
+    log_(" GWBSE calculation finished ");
+    return res;
+  }
+
+ private:
+  const Device& dev_;
+  Logger& log_;
+  Inputs in_;
+  GW::options gwopt_;
+  BSE::options bseopt_;
+  bool do_gw_ = false, do_bse_singlets_ = false, do_bse_triplets_ = false, do_dynamical_screening_bse_ = false;
+};
+
+}  // namespace xtp
+}  // namespace votca

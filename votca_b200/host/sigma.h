@@ -1,0 +1,433 @@
+// Sigma_base / Sigma_PPM / Sigma_Exact / Sigma_CDA - host mirror of
+// xtp/include/votca/xtp/sigma_base.h:33-106, xtp/src/libxtp/gwbse/sigma_base.cc:36-78,
+// self_energy_evaluators/sigma_{ppm,exact,cda}.{h,cc}, gwbse/ppm.cc:30-59,
+// ImaginaryAxisIntegration.cc:90-176.  Same virtual interface; in addition every evaluator offers a
+// batched EvalBatch() so the QP solver can evaluate many (level, frequency) requests in one kernel pass.
+#pragma once
+#include <atomic>
+#include <cmath>
+#include <complex>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "rpa.h"
+
+namespace votca {
+namespace xtp {
+
+class Sigma_base {
+ public:
+  Sigma_base(TCMatrix_gwbse& Mmn, const RPA& rpa) : Mmn_(Mmn), rpa_(rpa) {}
+  virtual ~Sigma_base() = default;
+
+  struct options {
+    Index homo;
+    Index qpmin;
+    Index qpmax;
+    Index rpamin;
+    Index rpamax;
+    double eta;
+    std::string quadrature_scheme;
+    Index order;
+    double alpha;
+  };
+
+  void configure(options opt) {
+    opt_ = opt;
+    qptotal_ = opt.qpmax - opt.qpmin + 1;
+    rpatotal_ = opt.rpamax - opt.rpamin + 1;
+  }
+
+  // sigma_base.cc:36-52
+  MatrixXd CalcExchangeMatrix() const {
+    MatrixXd result(qptotal_, qptotal_);
+    const Device& dev = Mmn_.device();
+    dev.check(gwbse_sigma_x(dev.ctx(), (int)opt_.homo, (int)opt_.rpamin, (int)opt_.qpmin, (int)opt_.qpmax,
+                            result.data(), (int)qptotal_));
+    return result;
+  }
+  // sigma_base.cc:54-63 (one batched pass instead of an OpenMP loop)
+  VectorXd CalcCorrelationDiag(const VectorXd& frequencies) const {
+    std::vector<int> lv(qptotal_);
+    std::vector<double> fr(qptotal_), s;
+    for (Index i = 0; i < qptotal_; ++i) {
+      lv[i] = (int)i;
+      fr[i] = frequencies[i];
+    }
+    EvalBatch(lv, fr, s, nullptr);
+    return VectorXd(s.data(), qptotal_);
+  }
+  // sigma_base.cc:65-78
+  virtual MatrixXd CalcCorrelationOffDiag(const VectorXd& frequencies) const = 0;
+
+  virtual void PrepareScreening() = 0;
+  virtual void EvalBatch(const std::vector<int>& levels, const std::vector<double>& freqs,
+                         std::vector<double>& sigma, std::vector<double>* dsigma) const = 0;
+
+  double CalcCorrelationDiagElement(Index gw_level, double frequency) const {
+    CountDiagEval();
+    std::vector<double> s;
+    EvalBatch({(int)gw_level}, {frequency}, s, nullptr);
+    return s[0];
+  }
+  double CalcCorrelationDiagElementDerivative(Index gw_level, double frequency) const {
+    std::vector<double> s, ds;
+    EvalBatch({(int)gw_level}, {frequency}, s, &ds);
+    return ds[0];
+  }
+  void ResetDiagEvalCounter() const { diag_eval_counter_.store(0); }
+  std::size_t GetDiagEvalCounter() const { return diag_eval_counter_.load(); }
+  void CountDiagEval(std::size_t n = 1) const { diag_eval_counter_.fetch_add(n); }
+  Index qptotal() const { return qptotal_; }
+
+ protected:
+  options opt_;
+  TCMatrix_gwbse& Mmn_;
+  const RPA& rpa_;
+  Index qptotal_ = 0;
+  Index rpatotal_ = 0;
+
+ private:
+  mutable std::atomic<std::size_t> diag_eval_counter_{0};
+};
+
+// ---------------------------------------------------------------------------------------------
+class PPM {
+ public:
+  PPM() : screening_r(0.0), screening_i(0.5) {}
+  // ppm.cc:30-59; phi stays on the device (phi_dev) and is consumed by MultiplyRight without a PCIe trip
+  void PPM_construct_parameters(const RPA& rpa, const TCMatrix_gwbse& Mmn) {
+    const Device& dev = Mmn.device();
+    const Index n = Mmn.auxsize();
+    double* eps = rpa.calculate_epsilon_r_dev(screening_r);
+    phi_dev_ = dev.alloc(static_cast<size_t>(n * n));
+    dev.check(gwbse_d2d(dev.ctx(), phi_dev_.get(), eps, static_cast<size_t>(n * n)));
+    VectorXd ev(n);
+    dev.check(gwbse_sym_eig_dev(dev.ctx(), (int)n, phi_dev_.get(), (int)n, ev.data()));
+    ppm_weight_ = VectorXd(n);
+    for (Index i = 0; i < n; ++i) ppm_weight_(i) = 1 - 1.0 / ev(i);
+    // ortho = phi^T eps_i phi ; epsilon_1_inv = ortho^-1
+    double* eps_i = rpa.calculate_epsilon_i_dev(screening_i);
+    Device::Buffer tmp = dev.alloc(static_cast<size_t>(n * n));
+    Device::Buffer ortho = dev.alloc(static_cast<size_t>(n * n));
+    dev.gemm('T', 'N', n, n, n, 1.0, phi_dev_.get(), n, eps_i, n, 0.0, tmp.get(), n);
+    dev.gemm('N', 'N', n, n, n, 1.0, tmp.get(), n, phi_dev_.get(), n, 0.0, ortho.get(), n);
+    dev.check(gwbse_inverse_dev(dev.ctx(), (int)n, ortho.get(), (int)n));
+    Device::Buffer dg = dev.alloc(static_cast<size_t>(n));
+    dev.check(gwbse_dev_memset_zero(dev.ctx(), dg.get(), static_cast<size_t>(n)));
+    dev.check(gwbse_axpy_dev(dev.ctx(), 1, (int)n, 1.0, ortho.get(), (int)(n + 1), dg.get(), 1));
+    MatrixXd inv_diag = dev.download(dg.get(), n, 1);
+    ppm_freq_ = VectorXd(n);
+    for (Index i = 0; i < n; i++) {
+      if (ppm_weight_(i) < 1.e-5) {
+        ppm_weight_(i) = 0.0;
+        ppm_freq_(i) = 0.5;
+        continue;
+      } else {
+        double nom = inv_diag(i, 0) - 1.0;
+        double frac = -1.0 * nom / (nom + ppm_weight_(i)) * screening_i * screening_i;
+        ppm_freq_(i) = std::sqrt(std::abs(frac));
+      }
+    }
+  }
+  const VectorXd& getPpm_weight() const { return ppm_weight_; }
+  const VectorXd& getPpm_freq() const { return ppm_freq_; }
+  const double* getPpm_phi_dev() const { return phi_dev_.get(); }
+  void FreeMatrix() { phi_dev_ = Device::Buffer(); }
+
+ private:
+  double screening_r, screening_i;
+  Device::Buffer phi_dev_;
+  VectorXd ppm_freq_, ppm_weight_;
+};
+
+class Sigma_PPM : public Sigma_base {
+ public:
+  Sigma_PPM(TCMatrix_gwbse& Mmn, const RPA& rpa) : Sigma_base(Mmn, rpa) {}
+  // sigma_ppm.cc:32-35
+  void PrepareScreening() final {
+    ppm_.PPM_construct_parameters(rpa_, Mmn_);
+    Mmn_.MultiplyRightWithAuxMatrix_dev(ppm_.getPpm_phi_dev(), Mmn_.auxsize());
+    ppm_.FreeMatrix();
+    const Device& dev = Mmn_.device();
+    dev.check(gwbse_sigma_ppm_set(dev.ctx(), ppm_.getPpm_weight().data(), ppm_.getPpm_freq().data(),
+                                  rpa_.getRPAInputEnergies().data(), (int)opt_.homo, (int)opt_.rpamin,
+                                  (int)opt_.qpmin, opt_.eta));
+  }
+  void EvalBatch(const std::vector<int>& levels, const std::vector<double>& freqs, std::vector<double>& sigma,
+                 std::vector<double>* dsigma) const final {
+    const Device& dev = Mmn_.device();
+    sigma.resize(levels.size());
+    if (dsigma) dsigma->resize(levels.size());
+    dev.check(gwbse_sigma_ppm_eval(dev.ctx(), (int)levels.size(), levels.data(), freqs.data(), sigma.data(),
+                                   dsigma ? dsigma->data() : nullptr));
+  }
+  MatrixXd CalcCorrelationOffDiag(const VectorXd& frequencies) const final {
+    MatrixXd out(qptotal_, qptotal_);
+    const Device& dev = Mmn_.device();
+    dev.check(gwbse_sigma_ppm_offdiag(dev.ctx(), (int)qptotal_, frequencies.data(), out.data(), (int)qptotal_));
+    return out;
+  }
+  const PPM& ppm() const { return ppm_; }
+
+ private:
+  PPM ppm_;
+};
+
+class Sigma_Exact : public Sigma_base {
+ public:
+  Sigma_Exact(TCMatrix_gwbse& Mmn, const RPA& rpa) : Sigma_base(Mmn, rpa) {}
+  // sigma_exact.cc:29-38, 109-148
+  void PrepareScreening() final {
+    Device::Buffer XpY;
+    RPA::rpa_eigensolution sol = rpa_.Diagonalize_H2p(&XpY, false);
+    rpa_omegas_ = sol.omega;
+    ERPA_correlation_ = sol.ERPA_correlation;
+    const Device& dev = Mmn_.device();
+    const Index S = rpa_omegas_.size();
+    dev.check(gwbse_sigma_exact_prepare(dev.ctx(), rpa_omegas_.data(), XpY.get(), (int)S,
+                                        rpa_.getRPAInputEnergies().data(), (int)opt_.homo, (int)opt_.rpamin,
+                                        (int)opt_.rpamax, (int)opt_.qpmin, (int)opt_.qpmax, opt_.eta));
+  }
+  void EvalBatch(const std::vector<int>& levels, const std::vector<double>& freqs, std::vector<double>& sigma,
+                 std::vector<double>* dsigma) const final {
+    const Device& dev = Mmn_.device();
+    sigma.resize(levels.size());
+    if (dsigma) dsigma->resize(levels.size());
+    dev.check(gwbse_sigma_exact_eval(dev.ctx(), (int)levels.size(), levels.data(), freqs.data(), sigma.data(),
+                                     dsigma ? dsigma->data() : nullptr));
+  }
+  MatrixXd CalcCorrelationOffDiag(const VectorXd& frequencies) const final {
+    MatrixXd out(qptotal_, qptotal_);
+    const Device& dev = Mmn_.device();
+    dev.check(gwbse_sigma_exact_offdiag(dev.ctx(), (int)qptotal_, frequencies.data(), out.data(), (int)qptotal_));
+    return out;
+  }
+  const VectorXd& rpa_omegas() const { return rpa_omegas_; }
+  double ERPA_correlation() const { return ERPA_correlation_; }
+
+ private:
+  VectorXd rpa_omegas_;
+  double ERPA_correlation_ = 0.0;
+};
+
+// Gauss-Legendre nodes/weights on [-1,1] by Newton iteration on P_n (the reference ships the same
+// numbers as 50-digit tables, gaussian_quadrature/gauss_legendre_quadrature.cc:28-561).
+inline void gauss_legendre(Index n, std::vector<double>& x, std::vector<double>& w) {
+  x.assign(n, 0.0);
+  w.assign(n, 0.0);
+  const double pi = 3.14159265358979323846;
+  for (Index i = 0; i < (n + 1) / 2; ++i) {
+    double z = std::cos(pi * (double(i) + 0.75) / (double(n) + 0.5));
+    double pp = 0.0;
+    for (int it = 0; it < 100; ++it) {
+      double p1 = 1.0, p2 = 0.0;
+      for (Index j = 0; j < n; ++j) {
+        const double p3 = p2;
+        p2 = p1;
+        p1 = ((2.0 * double(j) + 1.0) * z * p2 - double(j) * p3) / double(j + 1);
+      }
+      pp = double(n) * (z * p1 - p2) / (z * z - 1.0);
+      const double z1 = z;
+      z = z1 - p1 / pp;
+      if (std::abs(z - z1) < 1e-16) break;
+    }
+    x[i] = -z;
+    x[n - 1 - i] = z;
+    w[i] = 2.0 / ((1.0 - z * z) * pp * pp);
+    w[n - 1 - i] = w[i];
+  }
+}
+
+class Sigma_CDA : public Sigma_base {
+ public:
+  Sigma_CDA(TCMatrix_gwbse& Mmn, const RPA& rpa) : Sigma_base(Mmn, rpa) {}
+
+  // sigma_cda.cc:30-45 + ImaginaryAxisIntegration::CalcDielInvVector (ImaginaryAxisIntegration.cc:90-102)
+  void PrepareScreening() final {
+    const Device& dev = Mmn_.device();
+    const Index n = Mmn_.auxsize();
+    const size_t nn = static_cast<size_t>(n * n);
+    std::vector<double> gx, gw;
+    gauss_legendre(opt_.order, gx, gw);
+    const double halfpi = 0.5 * 3.14159265358979323846;
+    pts_.clear();
+    wts_.clear();
+    if (opt_.quadrature_scheme == "legendre") {
+      symmetry_ = false;
+      for (Index j = 0; j < opt_.order; ++j) {
+        pts_.push_back(std::tan(halfpi * gx[j]));
+        const double c = std::cos(halfpi * gx[j]);
+        wts_.push_back(gw[j] * halfpi / (c * c));
+      }
+    } else if (opt_.quadrature_scheme == "modified_legendre") {
+      symmetry_ = true;
+      for (Index j = 0; j < opt_.order; ++j) {
+        pts_.push_back(0.5 * (1.0 + gx[j]) / (1.0 - gx[j]));
+        wts_.push_back(gw[j] / ((1.0 - gx[j]) * (1.0 - gx[j])));
+      }
+    } else {
+      throw std::runtime_error("quadrature scheme '" + opt_.quadrature_scheme + "' is not available in this build");
+    }
+    // kappa_0 = eps(0)^-1 - 1
+    kzero_ = dev.alloc(nn);
+    double* eps = rpa_.calculate_epsilon_r_dev(std::complex<double>(0.0, 0.0));
+    dev.check(gwbse_d2d(dev.ctx(), kzero_.get(), eps, nn));
+    dev.check(gwbse_inverse_dev(dev.ctx(), (int)n, kzero_.get(), (int)n));
+    add_identity(kzero_.get(), n, -1.0);
+    dielinv_.clear();
+    for (Index j = 0; j < opt_.order; ++j) {
+      Device::Buffer k = dev.alloc(nn);
+      double* e = rpa_.calculate_epsilon_i_dev(pts_[j]);
+      dev.check(gwbse_d2d(dev.ctx(), k.get(), e, nn));
+      dev.check(gwbse_inverse_dev(dev.ctx(), (int)n, k.get(), (int)n));
+      add_identity(k.get(), n, -1.0);
+      // k <- -k + kzero * exp(-(alpha w)^2)
+      VectorXd m1(n, -1.0);
+      dev.check(gwbse_scale_cols_dev(dev.ctx(), (int)n, (int)n, k.get(), (int)n, m1.data()));
+      dev.check(gwbse_axpy_dev(dev.ctx(), (int)n, (int)n, std::exp(-std::pow(opt_.alpha * pts_[j], 2)),
+                               kzero_.get(), (int)n, k.get(), (int)n));
+      dielinv_.push_back(std::move(k));
+    }
+  }
+
+  // sigma_cda.cc:118-124 for a batch of requests (each request is evaluated independently)
+  void EvalBatch(const std::vector<int>& levels, const std::vector<double>& freqs, std::vector<double>& sigma,
+                 std::vector<double>* dsigma) const final {
+    sigma.resize(levels.size());
+    if (dsigma) dsigma->resize(levels.size());
+    for (size_t r = 0; r < levels.size(); ++r) {
+      sigma[r] = Element(levels[r], freqs[r]);
+      if (dsigma) {  // sigma_cda.h:57-63: central difference with h = 1e-3
+        const double h = 1e-3;
+        (*dsigma)[r] = (Element(levels[r], freqs[r] + h) - Element(levels[r], freqs[r] - h)) / (2 * h);
+      }
+    }
+  }
+  // sigma_cda.h:64-67
+  MatrixXd CalcCorrelationOffDiag(const VectorXd&) const final { return MatrixXd::Zero(qptotal_, qptotal_); }
+
+ private:
+  void add_identity(double* A, Index n, double v) const {
+    const Device& dev = Mmn_.device();
+    VectorXd ones(n, v);
+    Device::Buffer d = dev.upload(ones);
+    dev.check(gwbse_axpy_dev(dev.ctx(), 1, (int)n, 1.0, d.get(), 1, A, (int)(n + 1)));
+  }
+
+  double Element(Index gw_level, double frequency) const {
+    const Index gw_level_offset = gw_level + opt_.qpmin - opt_.rpamin;
+    const MatrixXd Imx = Mmn_[gw_level_offset];  // ntotal x naux
+    return CalcResidueContribution(frequency, Imx) + SigmaGQDiag(frequency, Imx, rpa_.getEta());
+  }
+
+  // ImaginaryAxisIntegration.cc:104-176
+  double SigmaGQDiag(double frequency, const MatrixXd& Imx, double eta) const {
+    const Device& dev = Mmn_.device();
+    const Index n = Mmn_.auxsize(), nt = Imx.rows();
+    const Index lumo = opt_.homo + 1;
+    const Index occ = lumo - opt_.rpamin;
+    const Index unocc = opt_.rpamax - opt_.homo;
+    const VectorXd& e = rpa_.getRPAInputEnergies();
+    std::vector<std::complex<double>> dE(nt);
+    for (Index i = 0; i < nt; ++i) dE[i] = std::complex<double>(frequency - e(i), 0.0);
+    for (Index i = 0; i < occ; ++i) dE[i] = std::complex<double>(dE[i].real(), eta);
+    for (Index i = nt - unocc; i < nt; ++i) dE[i] = std::complex<double>(dE[i].real(), -eta);
+    Device::Buffer dI = dev.upload(Imx);
+    Device::Buffer dT = dev.alloc(static_cast<size_t>(nt * n));
+    const double pi = 3.14159265358979323846;
+    double result = 0.0;
+    for (size_t j = 0; j < pts_.size(); ++j) {
+      const std::complex<double> cp(0.0, pts_[j]);
+      dev.gemm('N', 'N', nt, n, n, 1.0, dI.get(), nt, dielinv_[j].get(), n, 0.0, dT.get(), nt);
+      const MatrixXd T = dev.download(dT.get(), nt, n);
+      double acc = 0.0;
+      for (Index i = 0; i < nt; ++i) {
+        std::complex<double> den = 1.0 / (dE[i] + cp);
+        if (symmetry_) den += 1.0 / (dE[i] - cp);
+        double rowdot = 0.0;
+        for (Index a = 0; a < n; ++a) rowdot += T(i, a) * Imx(i, a);
+        acc += (den * rowdot).real();
+      }
+      result += wts_[j] * 0.5 / pi * acc;
+    }
+    return result;
+  }
+
+  // sigma_cda.cc:62-77
+  static double CalcResiduePrefactor(double e_f, double e_m, double frequency) {
+    double factor = 0.0;
+    double tolerance = 1e-10;
+    if (e_f < e_m && e_m < frequency) {
+      factor = 1.0;
+    } else if (e_f > e_m && e_m > frequency) {
+      factor = -1.0;
+    } else if (std::abs(e_m - frequency) < tolerance && e_f > e_m) {
+      factor = -0.5;
+    } else if (std::abs(e_m - frequency) < tolerance && e_f < e_m) {
+      factor = 0.5;
+    }
+    return factor;
+  }
+
+  // sigma_cda.cc:81-116 with CalcDiagContribution (:52-60) and the tail (:128-141)
+  double CalcResidueContribution(double frequency, const MatrixXd& Imx) const {
+    const Device& dev = Mmn_.device();
+    const VectorXd& rpa_energies = rpa_.getRPAInputEnergies();
+    const Index rpatotal = rpa_energies.size();
+    const Index n = Mmn_.auxsize();
+    double sigma_c = 0.0, sigma_c_tail = 0.0;
+    const Index homo = opt_.homo - opt_.rpamin;
+    const Index lumo = homo + 1;
+    const double fermi_rpa = (rpa_energies(lumo) + rpa_energies(homo)) / 2.0;
+    // tail: (Imx_row * kappa_0) . Imx_row for all rows at once
+    Device::Buffer dI = dev.upload(Imx);
+    Device::Buffer dT = dev.alloc(static_cast<size_t>(rpatotal * n));
+    dev.gemm('N', 'N', rpatotal, n, n, 1.0, dI.get(), rpatotal, kzero_.get(), n, 0.0, dT.get(), rpatotal);
+    const MatrixXd T = dev.download(dT.get(), rpatotal, n);
+    for (Index i = 0; i < rpatotal; ++i) {
+      const double delta = rpa_energies(i) - frequency;
+      const double abs_delta = std::abs(delta);
+      const double factor = CalcResiduePrefactor(fermi_rpa, rpa_energies(i), frequency);
+      if (std::abs(factor) > 1e-10) {
+        // x = eps(|delta| + i eta)^-1 row - row ; contribution = x . row
+        double* eps = rpa_.calculate_epsilon_r_dev(std::complex<double>(abs_delta, rpa_.getEta()));
+        Device::Buffer A = dev.alloc(static_cast<size_t>(n * n));
+        dev.check(gwbse_d2d(dev.ctx(), A.get(), eps, static_cast<size_t>(n * n)));
+        VectorXd row(n);
+        for (Index a = 0; a < n; ++a) row(a) = Imx(i, a);
+        Device::Buffer b = dev.upload(row);
+        dev.check(gwbse_lu_solve_dev(dev.ctx(), (int)n, 1, A.get(), (int)n, b.get(), (int)n));
+        const MatrixXd x = dev.download(b.get(), n, 1);
+        double dot = 0.0;
+        for (Index a = 0; a < n; ++a) dot += (x(a, 0) - row(a)) * row(a);
+        sigma_c += factor * dot;
+      }
+      if (abs_delta > 1e-10) {
+        const double erfc_factor = 0.5 * std::copysign(1.0, delta) * std::exp(std::pow(opt_.alpha * delta, 2)) *
+                                   std::erfc(std::abs(opt_.alpha * delta));
+        double value = 0.0;
+        for (Index a = 0; a < n; ++a) value += T(i, a) * Imx(i, a);
+        sigma_c_tail += value * erfc_factor;
+      }
+    }
+    return sigma_c + sigma_c_tail;
+  }
+
+  std::vector<double> pts_, wts_;
+  bool symmetry_ = false;
+  Device::Buffer kzero_;
+  std::vector<Device::Buffer> dielinv_;
+};
+
+// SigmaFactory, xtp/src/libxtp/factories/sigmafactory.cc:32-36
+inline std::unique_ptr<Sigma_base> SigmaFactory_Create(const std::string& name, TCMatrix_gwbse& Mmn, const RPA& rpa) {
+  if (name == "ppm") return std::make_unique<Sigma_PPM>(Mmn, rpa);
+  if (name == "exact") return std::make_unique<Sigma_Exact>(Mmn, rpa);
+  if (name == "cda") return std::make_unique<Sigma_CDA>(Mmn, rpa);
+  throw std::runtime_error("SigmaFactory: unknown sigma_integrator '" + name + "'");
+}
+
+}  // namespace xtp
+}  // namespace votca
