@@ -164,6 +164,10 @@ int gwbse_sigma_x(gwbse_ctx* ctx, int homo, int rpamin, int qpmin, int qpmax, do
  * dsigma may be NULL.  lumo_abs = homo + 1 exactly as the reference uses it. */
 int gwbse_sigma_ppm_set(gwbse_ctx* ctx, const double* ppm_weight, const double* ppm_freq, const double* energies,
                         int homo, int rpamin, int qpmin, double eta);
+/* The evaluators read rpa_.getRPAInputEnergies() at evaluation time (sigma_ppm.cc:53, sigma_exact.cc:51);
+ * evGW changes them between PrepareScreening and the final CalcCorrelationDiag (gw.cc:258-308), so the host
+ * refreshes the device copy before evaluating.  which: 0 = ppm, 1 = exact.                                */
+int gwbse_sigma_update_energies(gwbse_ctx* ctx, int which, const double* energies);
 int gwbse_sigma_ppm_eval(gwbse_ctx* ctx, int nreq, const int* levels, const double* freqs, double* sigma,
                          double* dsigma);
 /* Sigma_PPM::CalcCorrelationOffDiagElement for all pairs (sigma_ppm.cc:93-126 via

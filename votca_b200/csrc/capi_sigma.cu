@@ -115,6 +115,15 @@ int gwbse_sigma_ppm_set(gwbse_ctx* ctx, const double* ppm_weight, const double* 
   GW_API_END(ctx)
 }
 
+int gwbse_sigma_update_energies(gwbse_ctx* ctx, int which, const double* energies) {
+  GW_API_BEGIN(ctx)
+  auto& st = which == 0 ? ctx->sig_ppm : ctx->sig_exact;
+  GW_REQUIRE(st.ready && st.energies != nullptr, "sigma evaluator not prepared");
+  GW_CUDA(cudaMemcpyAsync(st.energies, energies, sizeof(double) * ctx->ntotal, cudaMemcpyHostToDevice, ctx->stream));
+  GW_CUDA(cudaStreamSynchronize(ctx->stream));
+  GW_API_END(ctx)
+}
+
 int gwbse_sigma_ppm_eval(gwbse_ctx* ctx, int nreq, const int* levels, const double* freqs, double* sigma,
                          double* dsigma) {
   GW_API_BEGIN(ctx)

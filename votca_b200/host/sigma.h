@@ -160,12 +160,14 @@ class Sigma_PPM : public Sigma_base {
     const Device& dev = Mmn_.device();
     sigma.resize(levels.size());
     if (dsigma) dsigma->resize(levels.size());
+    dev.check(gwbse_sigma_update_energies(dev.ctx(), 0, rpa_.getRPAInputEnergies().data()));
     dev.check(gwbse_sigma_ppm_eval(dev.ctx(), (int)levels.size(), levels.data(), freqs.data(), sigma.data(),
                                    dsigma ? dsigma->data() : nullptr));
   }
   MatrixXd CalcCorrelationOffDiag(const VectorXd& frequencies) const final {
     MatrixXd out(qptotal_, qptotal_);
     const Device& dev = Mmn_.device();
+    dev.check(gwbse_sigma_update_energies(dev.ctx(), 0, rpa_.getRPAInputEnergies().data()));
     dev.check(gwbse_sigma_ppm_offdiag(dev.ctx(), (int)qptotal_, frequencies.data(), out.data(), (int)qptotal_));
     return out;
   }
@@ -195,12 +197,14 @@ class Sigma_Exact : public Sigma_base {
     const Device& dev = Mmn_.device();
     sigma.resize(levels.size());
     if (dsigma) dsigma->resize(levels.size());
+    dev.check(gwbse_sigma_update_energies(dev.ctx(), 1, rpa_.getRPAInputEnergies().data()));
     dev.check(gwbse_sigma_exact_eval(dev.ctx(), (int)levels.size(), levels.data(), freqs.data(), sigma.data(),
                                      dsigma ? dsigma->data() : nullptr));
   }
   MatrixXd CalcCorrelationOffDiag(const VectorXd& frequencies) const final {
     MatrixXd out(qptotal_, qptotal_);
     const Device& dev = Mmn_.device();
+    dev.check(gwbse_sigma_update_energies(dev.ctx(), 1, rpa_.getRPAInputEnergies().data()));
     dev.check(gwbse_sigma_exact_offdiag(dev.ctx(), (int)qptotal_, frequencies.data(), out.data(), (int)qptotal_));
     return out;
   }
