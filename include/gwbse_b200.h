@@ -53,6 +53,13 @@ long long gwbse_launch_count(const gwbse_ctx* ctx);
 int gwbse_device_count(void); /* OpenMP_CUDA::AvailableGPUs, openmp_cuda.cc:30-46 */
 /* tuning knobs: "bse_chunk_bytes" (size of the Hd/Hd2 intermediate held at once) */
 int gwbse_set_option(gwbse_ctx* ctx, const char* key, double value);
+/* Per-kernel accounting of the DMMA GEMM (bench.py roofline): when enabled every GEMM launch is bracketed
+ * by CUDA events on the context's stream; stats = summed kernel milliseconds, algorithmic flops, launches. */
+int gwbse_gemm_profile(gwbse_ctx* ctx, int enable);
+int gwbse_gemm_stats(gwbse_ctx* ctx, double* ms, double* flops, long long* launches);
+/* Live FP64 tensor (DMMA) issue-rate probe: register-resident mma.sync loop on every SM -> TFLOP/s.
+ * This is the roofline denominator for the contraction kernels (MEASURED_PEAKS.json has no FP64 entry). */
+int gwbse_fp64_peak_probe(gwbse_ctx* ctx, double* tflops);
 /* CUDA-event timers on the context's stream (bench.py times kernels with these) */
 int gwbse_timer_start(gwbse_ctx* ctx);
 int gwbse_timer_stop_ms(gwbse_ctx* ctx, float* ms);

@@ -42,6 +42,11 @@ int gwbse_job_set_array(gwbse_job* job, const char* name, const double* data, lo
 typedef void (*gwbse_ao3c_fn)(void* user, long aux_offset, long aux_count, double* out);
 int gwbse_job_set_ao3c_callback(gwbse_job* job, long nbasis, long naux, gwbse_ao3c_fn fn, void* user);
 
+/* AO integrals already resident on the device (naux contiguous N x N matrices) */
+int gwbse_job_set_ao3c_dev(gwbse_job* job, long nbasis, long naux, const double* ao3c_dev);
+/* the kernel-library context of this job (gwbse_b200.h), e.g. for gwbse_gemm_stats / timers */
+void* gwbse_job_ctx(gwbse_job* job);
+
 int gwbse_job_run(gwbse_job* job);
 
 int gwbse_job_array_dims(const gwbse_job* job, const char* name, long* rows, long* cols);

@@ -388,3 +388,46 @@ class Job:
 
     def launch_count(self):
         return int(self.api.gwbse_job_launch_count(self.h))
+
+
+def _job_extras():
+    def set_ao3c_dev(self, nbasis, naux, dev_ptr):
+        """AO tensor already on the device (int address, e.g. torch tensor.data_ptr())."""
+        self._ck(self.api.gwbse_job_set_ao3c_dev(self.h, int(nbasis), int(naux), ctypes.c_void_p(int(dev_ptr))))
+
+    def set_ao3c_host_ptr(self, nbasis, naux, host_ptr):
+        """AO tensor in (pinned) host memory given by raw address; referenced, not copied."""
+        self._ck(self.api.gwbse_job_set_array(self.h, b"ao3c", ctypes.c_void_p(int(host_ptr)), int(nbasis) * int(nbasis),
+                                              int(naux)))
+
+    def kernel_ctx(self):
+        """The underlying gwbse_b200 context as a Context-like wrapper (profiling, timers)."""
+        c = Context.__new__(Context)
+        c.api = capi()
+        c.h = ctypes.c_void_p(self.api.gwbse_job_ctx(self.h))
+        c.close = lambda: None  # owned by the job
+        return c
+
+    Job.set_ao3c_dev = set_ao3c_dev
+    Job.set_ao3c_host_ptr = set_ao3c_host_ptr
+    Job.kernel_ctx = kernel_ctx
+
+    def gemm_profile(self, enable=True):
+        self.call("gwbse_gemm_profile", int(bool(enable)))
+
+    def gemm_stats(self):
+        ms, fl, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
+        self.call("gwbse_gemm_stats", ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(n))
+        return {"ms": ms.value, "flops": fl.value, "launches": int(n.value)}
+
+    def fp64_peak_probe(self):
+        t = ctypes.c_double()
+        self.call("gwbse_fp64_peak_probe", ctypes.byref(t))
+        return t.value
+
+    Context.gemm_profile = gemm_profile
+    Context.gemm_stats = gemm_stats
+    Context.fp64_peak_probe = fp64_peak_probe
+
+
+_job_extras()

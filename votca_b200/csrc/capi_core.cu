@@ -1,4 +1,5 @@
 // C ABI, part 1: context, device memory, dense primitives, dense auxiliaries.
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -9,12 +10,62 @@ using namespace gwbse;
 
 static thread_local std::string g_create_error;
 
-void gwbse_ctx::gemm(const GemmParams& p, int cfg, int splitk) {
+void gwbse_ctx::gemm(const GemmParams& p, int cfg, int splitk, double algo_flops) {
   const size_t need = gemm_ws_bytes_needed(p, num_sms, cfg, splitk);
   double* ws = need ? buf("gemm_ws", need / sizeof(double)) : nullptr;
+  if (gemm_profile) {
+    if (gemm_events_used == gemm_events.size()) {
+      if (gemm_events.size() >= 4096) gemm_collect();
+      if (gemm_events_used == gemm_events.size()) {
+        cudaEvent_t a, b;
+        GW_CUDA(cudaEventCreate(&a));
+        GW_CUDA(cudaEventCreate(&b));
+        gemm_events.emplace_back(a, b);
+      }
+    }
+    GW_CUDA(cudaEventRecord(gemm_events[gemm_events_used].first, stream));
+  }
   gemm_launch(p, stream, ws, need, num_sms, cfg, splitk);
+  if (gemm_profile) {
+    GW_CUDA(cudaEventRecord(gemm_events[gemm_events_used].second, stream));
+    ++gemm_events_used;
+    if (algo_flops < 0.0) {
+      algo_flops = 2.0 * p.M * (double)p.N * (double)p.Ko * (double)p.Ki * p.Z1 * p.Z2;
+      if (p.lower_only) algo_flops *= 0.5 * (1.0 + 1.0 / std::max(p.N, 1));
+    }
+    gemm_flops += algo_flops;
+    ++gemm_launches;
+  }
   launches += (need ? 2 : 1);
 }
+
+void gwbse_ctx::gemm_collect() {
+  if (gemm_events_used == 0) return;
+  GW_CUDA(cudaStreamSynchronize(stream));
+  for (size_t i = 0; i < gemm_events_used; ++i) {
+    float ms = 0.f;
+    GW_CUDA(cudaEventElapsedTime(&ms, gemm_events[i].first, gemm_events[i].second));
+    gemm_ms += ms;
+  }
+  gemm_events_used = 0;
+}
+
+namespace {
+__global__ void __launch_bounds__(256) dmma_probe_kernel(double* out, int iters, double seed) {
+  double a = seed + threadIdx.x * 1e-9, b = seed * 0.5;
+  double c[8][2];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) c[j][0] = c[j][1] = 0.0;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) gwbse::dmma884(c[j], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s += c[j][0] + c[j][1];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+}  // namespace
 
 static void check_solver(cusolverStatus_t st, const char* what) {
   if (st != CUSOLVER_STATUS_SUCCESS)
@@ -76,6 +127,10 @@ void gwbse_ctx_destroy(gwbse_ctx* ctx) {
     for (double* p : {st->fac, st->pole, st->energies})
       if (p) cudaFree(p);
   if (ctx->solver) cusolverDnDestroy(ctx->solver);
+  for (auto& e : ctx->gemm_events) {
+    cudaEventDestroy(e.first);
+    cudaEventDestroy(e.second);
+  }
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -101,6 +156,46 @@ int gwbse_set_option(gwbse_ctx* ctx, const char* key, double value) {
   } else {
     throw std::runtime_error("unknown option '" + k + "'");
   }
+  GW_API_END(ctx)
+}
+
+int gwbse_gemm_profile(gwbse_ctx* ctx, int enable) {
+  GW_API_BEGIN(ctx)
+  ctx->gemm_collect();
+  ctx->gemm_profile = enable != 0;
+  ctx->gemm_ms = 0.0;
+  ctx->gemm_flops = 0.0;
+  ctx->gemm_launches = 0;
+  GW_API_END(ctx)
+}
+
+int gwbse_gemm_stats(gwbse_ctx* ctx, double* ms, double* flops, long long* launches) {
+  GW_API_BEGIN(ctx)
+  ctx->gemm_collect();
+  if (ms) *ms = ctx->gemm_ms;
+  if (flops) *flops = ctx->gemm_flops;
+  if (launches) *launches = ctx->gemm_launches;
+  GW_API_END(ctx)
+}
+
+int gwbse_fp64_peak_probe(gwbse_ctx* ctx, double* tflops) {
+  GW_API_BEGIN(ctx)
+  const int grid = ctx->num_sms * 4, iters = 20000;
+  double* out = ctx->buf("probe_out", (size_t)grid * 256);
+  dmma_probe_kernel<<<grid, 256, 0, ctx->stream>>>(out, 1000, 1.0);  // warm-up
+  float best = 1e30f;
+  for (int r = 0; r < 3; ++r) {
+    GW_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    dmma_probe_kernel<<<grid, 256, 0, ctx->stream>>>(out, iters, 1.0);
+    GW_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    GW_CUDA(cudaEventSynchronize(ctx->ev1));
+    float ms = 0.f;
+    GW_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    best = std::min(best, ms);
+  }
+  GW_CUDA(cudaGetLastError());
+  // warps * iters * 8 mma * (8*8*4*2 flop)
+  *tflops = (double)grid * 8 * (double)iters * 8 * 512.0 / (best * 1e-3) / 1e12;
   GW_API_END(ctx)
 }
 

@@ -23,6 +23,13 @@ struct gwbse_ctx {
   cusolverDnHandle_t solver = nullptr;
   long long launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // GEMM accounting (gwbse_gemm_profile)
+  bool gemm_profile = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm_events;
+  size_t gemm_events_used = 0;
+  double gemm_ms = 0.0, gemm_flops = 0.0;
+  long long gemm_launches = 0;
+  void gemm_collect();
 
   // multi-GPU
   int rank = 0, world = 1;
@@ -85,7 +92,8 @@ struct gwbse_ctx {
     }
     return b.p;
   }
-  void gemm(const gwbse::GemmParams& p, int cfg = -1, int splitk = 0);
+  // algo_flops < 0: 2*M*N*K per batch (half for lower_only)
+  void gemm(const gwbse::GemmParams& p, int cfg = -1, int splitk = 0, double algo_flops = -1.0);
   bool owns(int m) const { return (m % world) == rank; }
   int local_index(int m) const { return m / world; }
   // number of local levels with global storage index in [0, upto)

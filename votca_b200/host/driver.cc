@@ -15,6 +15,7 @@ namespace {
 struct ArraySource : AOIntegralSource {
   Index N = 0, naux = 0;
   const double* ao3c = nullptr;
+  const double* ao3c_dev = nullptr;
   gwbse_ao3c_fn fn = nullptr;
   void* user = nullptr;
   MatrixXd S, V;
@@ -27,6 +28,9 @@ struct ArraySource : AOIntegralSource {
       if (!ao3c) throw std::runtime_error("no AO three-centre integrals supplied (ao3c)");
       std::memcpy(out, ao3c + static_cast<size_t>(aux_offset) * N * N, sizeof(double) * aux_count * N * N);
     }
+  }
+  const double* DeviceBlock(Index aux_offset, Index) const override {
+    return ao3c_dev ? ao3c_dev + static_cast<size_t>(aux_offset) * N * N : nullptr;
   }
   MatrixXd AuxOverlap() const override { return S; }
   MatrixXd AuxCoulomb() const override { return V; }
@@ -117,6 +121,7 @@ int gwbse_job_set_array(gwbse_job* job, const char* name, const double* data, lo
   const std::string n(name);
   if (n == "ao3c") {
     job->ints.ao3c = data;
+    job->ints.ao3c_dev = nullptr;
     job->ints.fn = nullptr;
     job->ints.naux = cols;
     job->ints.N = static_cast<Index>(std::llround(std::sqrt(static_cast<double>(rows))));
@@ -136,6 +141,18 @@ int gwbse_job_set_ao3c_callback(gwbse_job* job, long nbasis, long naux, gwbse_ao
   job->ints.naux = naux;
   JOB_END(job)
 }
+
+int gwbse_job_set_ao3c_dev(gwbse_job* job, long nbasis, long naux, const double* ao3c_dev) {
+  JOB_BEGIN(job)
+  job->ints.ao3c_dev = ao3c_dev;
+  job->ints.ao3c = nullptr;
+  job->ints.fn = nullptr;
+  job->ints.N = nbasis;
+  job->ints.naux = naux;
+  JOB_END(job)
+}
+
+void* gwbse_job_ctx(gwbse_job* job) { return job ? job->dev->ctx() : nullptr; }
 
 int gwbse_job_run(gwbse_job* job) {
   JOB_BEGIN(job)

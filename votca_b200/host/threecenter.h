@@ -18,6 +18,8 @@ struct AOIntegralSource {
   virtual Index BasisSize() const = 0;
   // aux_count symmetric N x N matrices for aux functions [aux_offset, aux_offset+aux_count)
   virtual void ComputeAO3cBlock(Index aux_offset, Index aux_count, double* out) const = 0;
+  // optional: device pointer to the same block if the integrals already live on the GPU (nullptr otherwise)
+  virtual const double* DeviceBlock(Index /*aux_offset*/, Index /*aux_count*/) const { return nullptr; }
   virtual MatrixXd AuxOverlap() const = 0;  // AOOverlap::Fill(auxbasis)
   virtual MatrixXd AuxCoulomb() const = 0;  // AOCoulomb::Fill(auxbasis)
 };
@@ -110,6 +112,10 @@ class TCMatrix_gwbse {
     std::vector<double> block(static_cast<size_t>(aux_block_ * N * N));
     for (Index a0 = 0; a0 < auxbasissize_; a0 += aux_block_) {
       const Index cnt = std::min(aux_block_, auxbasissize_ - a0);
+      if (const double* d = ints.DeviceBlock(a0, cnt)) {
+        dev_.check(gwbse_mmn_fill_block_dev(dev_.ctx(), (int)a0, (int)cnt, d));
+        continue;
+      }
       ints.ComputeAO3cBlock(a0, cnt, block.data());
       dev_.check(gwbse_mmn_fill_block(dev_.ctx(), (int)a0, (int)cnt, block.data()));
     }
