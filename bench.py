@@ -248,6 +248,16 @@ def main():
     results = {"QP_homo": float(job.get("QPpert_energies")[homo]), "QP_lumo": float(job.get("QPpert_energies")[homo + 1]),
                "S1": float(job.get("BSE_singlet_eigenvalues")[0]), "singlet_converged": job.scalar("singlet_converged")}
 
+    if os.environ.get("GWBSE_PROFILE") and rank == 0:
+        # one extra, untimed step with the library's region profiler (per entry point device/host ms)
+        kctx.set_option("profile", 1)
+        job.run()
+        rep = kctx.profile_report()
+        kctx.set_option("profile", 0)
+        sys.stderr.write(rep + "\n" + "\n".join(l for l in job.log().splitlines()[-40:]) + "\n")
+        with open(os.environ["GWBSE_PROFILE"], "w") as fh:
+            fh.write(rep)
+
     # ---------------- e2e: AO integrals from pinned host memory, results back to the host ----------------
     e2e = None
     if not args.no_e2e:

@@ -50,8 +50,10 @@ const char* gwbse_create_error(void); /* message of a failed gwbse_ctx_create */
 int gwbse_sync(gwbse_ctx* ctx);
 /* number of kernels of this library launched so far on ctx (bench.py gpu_launches) */
 long long gwbse_launch_count(const gwbse_ctx* ctx);
+int gwbse_profile_report(gwbse_ctx* ctx, char* buf, size_t buflen); /* also resets the counters */
 int gwbse_device_count(void); /* OpenMP_CUDA::AvailableGPUs, openmp_cuda.cc:30-46 */
-/* tuning knobs: "bse_chunk_bytes" (size of the Hd/Hd2 intermediate held at once) */
+/* tuning knobs: "bse_chunk_bytes" (size of the Hd/Hd2 intermediate held at once), "profile" (0/1: time every
+ * entry point with CUDA events on the context's stream; read the table with gwbse_profile_report) */
 int gwbse_set_option(gwbse_ctx* ctx, const char* key, double value);
 /* Per-kernel accounting of the DMMA GEMM (bench.py roofline): when enabled every GEMM launch is bracketed
  * by CUDA events on the context's stream; stats = summed kernel milliseconds, algorithmic flops, launches. */
@@ -177,6 +179,12 @@ int gwbse_sigma_ppm_set(gwbse_ctx* ctx, const double* ppm_weight, const double* 
 int gwbse_sigma_update_energies(gwbse_ctx* ctx, int which, const double* energies);
 int gwbse_sigma_ppm_eval(gwbse_ctx* ctx, int nreq, const int* levels, const double* freqs, double* sigma,
                          double* dsigma);
+/* Grouped form of the two evaluators above (which: 0 = ppm, 1 = exact): group g evaluates level levels[g]
+ * at the frequencies freqs[group_ptr[g] .. group_ptr[g+1]); the level's data is streamed once per group.
+ * This is what the QP root search uses: its scan / sub-step / bisection frequencies are known ahead
+ * (qp_solver_utils.h:484-628) and are evaluated together.                                              */
+int gwbse_sigma_eval_groups(gwbse_ctx* ctx, int which, int ngroups, const int* levels, const int* group_ptr,
+                            const double* freqs, double* sigma, double* dsigma);
 /* Sigma_PPM::CalcCorrelationOffDiagElement for all pairs (sigma_ppm.cc:93-126 via
  * Sigma_base::CalcCorrelationOffDiag sigma_base.cc:65-78): q x q symmetric, zero diagonal */
 int gwbse_sigma_ppm_offdiag(gwbse_ctx* ctx, int q, const double* freqs, double* out, int ld);

@@ -431,3 +431,12 @@ def _job_extras():
 
 
 _job_extras()
+
+
+def _profile_report(self):
+    buf = ctypes.create_string_buffer(16384)
+    self.call("gwbse_profile_report", buf, ctypes.c_size_t(len(buf)))
+    return buf.value.decode()
+
+
+Context.profile_report = _profile_report

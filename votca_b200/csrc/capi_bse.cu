@@ -197,6 +197,7 @@ extern "C" {
 int gwbse_bse_configure(gwbse_ctx* ctx, int homo, int rpamin, int vmin, int cmax, const double* eps_inv,
                         const double* Hqp, int ldh) {
   GW_API_BEGIN(ctx)
+  GW_PROF(ctx, "bse_configure");
   GW_REQUIRE(ctx->X != nullptr, "Mmn not allocated");
   GW_REQUIRE(rpamin == ctx->mmin && rpamin == ctx->nmin, "RPA range must match Mmn");
   auto& st = ctx->bse;
@@ -231,6 +232,7 @@ int gwbse_bse_configure(gwbse_ctx* ctx, int homo, int rpamin, int vmin, int cmax
 int gwbse_bse_matmul_dev(gwbse_ctx* ctx, int cqp, int cx, int cd, int cd2, int k, const double* X_dev, int ldx,
                          double* Y_dev, int ldy) {
   GW_API_BEGIN(ctx)
+  GW_PROF(ctx, "bse_matmul");
   bse_matmul_dev(ctx, cqp, cx, cd, cd2, k, X_dev, ldx, Y_dev, ldy);
   GW_API_END(ctx)
 }
@@ -238,6 +240,7 @@ int gwbse_bse_matmul_dev(gwbse_ctx* ctx, int cqp, int cx, int cd, int cd2, int k
 int gwbse_bse_matmul(gwbse_ctx* ctx, int cqp, int cx, int cd, int cd2, int k, const double* X, int ldx, double* Y,
                      int ldy) {
   GW_API_BEGIN(ctx)
+  GW_PROF(ctx, "bse_matmul_h2d");
   const int B = ctx->bse.size;
   GW_REQUIRE(ctx->bse.ready, "BSE operator not configured (gwbse_bse_configure)");
   GW_REQUIRE(ldx >= B && ldy >= B, "Shape mismatch in BSE matmul");
@@ -256,6 +259,7 @@ int gwbse_bse_matmul(gwbse_ctx* ctx, int cqp, int cx, int cd, int cd2, int k, co
 
 int gwbse_bse_diagonal(gwbse_ctx* ctx, int cqp, int cx, int cd, int cd2, double* diag) {
   GW_API_BEGIN(ctx)
+  GW_PROF(ctx, "bse_diagonal");
   auto& st = ctx->bse;
   GW_REQUIRE(st.ready, "BSE operator not configured (gwbse_bse_configure)");
   GW_REQUIRE(!(cd != 0 && cd2 != 0), "Hamiltonian cannot contain Hd and Hd2 at the same time");
@@ -273,6 +277,7 @@ int gwbse_bse_diagonal(gwbse_ctx* ctx, int cqp, int cx, int cd, int cd2, double*
 // DavidsonSolver::gramschmidt, davidsonsolver.cc:442-478, same order of operations.
 int gwbse_gramschmidt_dev(gwbse_ctx* ctx, int rows, int ncols, int nstart, double* Q, int ldq) {
   GW_API_BEGIN(ctx)
+  GW_PROF(ctx, "gramschmidt");
   GW_REQUIRE(ldq >= rows && nstart >= 0 && nstart <= ncols, "invalid Gram-Schmidt arguments");
   const int nup = ncols - nstart;
   if (nup > 0) {
@@ -325,6 +330,7 @@ int gwbse_davidson_correction_dev(gwbse_ctx* ctx, int rows, int ncols, int olsen
                                   const double* lambda, const double* R, int ldr, const double* Q, int ldq,
                                   double* W, int ldw) {
   GW_API_BEGIN(ctx)
+  GW_PROF(ctx, "davidson_correction");
   if (ncols > 0) {
     double* lam = ctx->buf("dav_lambda", ncols);
     GW_CUDA(cudaMemcpyAsync(lam, lambda, sizeof(double) * ncols, cudaMemcpyHostToDevice, ctx->stream));

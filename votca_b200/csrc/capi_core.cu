@@ -1,5 +1,6 @@
 // C ABI, part 1: context, device memory, dense primitives, dense auxiliaries.
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
 #include <vector>
 
@@ -150,11 +151,36 @@ long long gwbse_launch_count(const gwbse_ctx* ctx) { return ctx ? ctx->launches 
 int gwbse_set_option(gwbse_ctx* ctx, const char* key, double value) {
   GW_API_BEGIN(ctx)
   const std::string k(key ? key : "");
-  if (k == "bse_chunk_bytes") {
+  if (k == "profile") {
+    ctx->collect_regions();
+    ctx->regions.clear();
+    ctx->profile = value != 0.0;
+  } else if (k == "bse_chunk_bytes") {
     GW_REQUIRE(value >= 1024, "bse_chunk_bytes too small");
     ctx->bse_chunk_bytes = (size_t)value;
   } else {
     throw std::runtime_error("unknown option '" + k + "'");
+  }
+  GW_API_END(ctx)
+}
+
+int gwbse_profile_report(gwbse_ctx* ctx, char* buf, size_t buflen) {
+  GW_API_BEGIN(ctx)
+  ctx->collect_regions();
+  std::string out = "region                          calls   device_ms     host_ms\n";
+  std::vector<std::pair<double, std::string>> rows;
+  for (auto& kv : ctx->regions) {
+    char line[160];
+    std::snprintf(line, sizeof(line), "%-30s %6lld %11.2f %11.2f\n", kv.first.c_str(), kv.second.calls, kv.second.ms,
+                  kv.second.wall_ms);
+    rows.emplace_back(-kv.second.ms, line);
+  }
+  std::sort(rows.begin(), rows.end());
+  for (auto& r : rows) out += r.second;
+  ctx->regions.clear();
+  if (buf && buflen) {
+    std::strncpy(buf, out.c_str(), buflen - 1);
+    buf[buflen - 1] = 0;
   }
   GW_API_END(ctx)
 }
@@ -298,6 +324,7 @@ static GemmParams blas_params(char ta, char tb, int m, int n, int k, double alph
 int gwbse_dgemm_dev_ex(gwbse_ctx* ctx, char ta, char tb, int m, int n, int k, double alpha, const double* A,
                        int lda, const double* B, int ldb, double beta, double* C, int ldc, int cfg, int splitk) {
   GW_API_BEGIN(ctx)
+  GW_PROF(ctx, "dgemm_dev");
   if (m > 0 && n > 0) {
     if (k <= 0) {
       // C = beta * C
@@ -377,6 +404,7 @@ int gwbse_scale_cols_dev(gwbse_ctx* ctx, int m, int n, double* A, int lda, const
 // --------------------------- dense auxiliaries -----------------------------
 int gwbse_sym_eig_dev(gwbse_ctx* ctx, int n, double* A, int lda, double* w) {
   GW_API_BEGIN(ctx)
+  GW_PROF(ctx, "sym_eig");
   if (n > 0) {
     int lwork = 0;
     double* wd = ctx->buf("eig_w", n);
@@ -430,6 +458,7 @@ __global__ void set_identity_kernel(double* A, int n, long long ld) {
 
 int gwbse_inverse_dev(gwbse_ctx* ctx, int n, double* A, int lda) {
   GW_API_BEGIN(ctx)
+  GW_PROF(ctx, "inverse");
   if (n > 0) {
     int* ipiv = nullptr;
     lu_factor(ctx, n, A, lda, &ipiv);
@@ -449,6 +478,7 @@ int gwbse_inverse_dev(gwbse_ctx* ctx, int n, double* A, int lda) {
 int gwbse_gen_eig_host(gwbse_ctx* ctx, int n, const double* T, const double* B, double* wr, double* wi,
                        double* VR) {
   GW_API_BEGIN(ctx)
+  GW_PROF(ctx, "gen_eig_host");
   if (n > 0) {
     const size_t nn = (size_t)n * n;
     double* dT = ctx->buf("geig_T", nn);

@@ -170,12 +170,14 @@ int gwbse_mmn_set_mos(gwbse_ctx* ctx, const double* mos, int ldmos, int nbasis, 
 
 int gwbse_mmn_fill_block_dev(gwbse_ctx* ctx, int aux_offset, int aux_count, const double* ao3c_dev) {
   GW_API_BEGIN(ctx)
+  GW_PROF(ctx, "mmn_fill_block");
   fill_block_dev(ctx, aux_offset, aux_count, ao3c_dev);
   GW_API_END(ctx)
 }
 
 int gwbse_mmn_fill_block(gwbse_ctx* ctx, int aux_offset, int aux_count, const double* ao3c) {
   GW_API_BEGIN(ctx)
+  GW_PROF(ctx, "mmn_fill_block_h2d");
   const size_t per = (size_t)ctx->nbasis * ctx->nbasis;
   // stream the block through a bounded staging buffer (<= 1 GiB)
   const int chunk = (int)std::max<size_t>(1, std::min<size_t>(aux_count, ((size_t)1 << 27) / std::max<size_t>(per, 1)));
@@ -192,12 +194,14 @@ int gwbse_mmn_fill_block(gwbse_ctx* ctx, int aux_offset, int aux_count, const do
 
 int gwbse_mmn_mul_right_dev(gwbse_ctx* ctx, const double* R_dev, int ldr) {
   GW_API_BEGIN(ctx)
+  GW_PROF(ctx, "mmn_mul_right");
   mul_right_dev(ctx, R_dev, ldr);
   GW_API_END(ctx)
 }
 
 int gwbse_mmn_mul_right(gwbse_ctx* ctx, const double* R, int ldr) {
   GW_API_BEGIN(ctx)
+  GW_PROF(ctx, "mmn_mul_right_h2d");
   require_mmn(ctx);
   GW_REQUIRE(ldr >= ctx->naux, "Shape mismatch in MultiplyRight");
   double* Rd = ctx->buf("mulright_R", (size_t)ctx->naux * ctx->naux);
@@ -234,6 +238,7 @@ int gwbse_mmn_set_slice(gwbse_ctx* ctx, int m, const double* in, int ld) {
 
 int gwbse_mmn_snapshot(gwbse_ctx* ctx) {
   GW_API_BEGIN(ctx)
+  GW_PROF(ctx, "mmn_snapshot");
   require_mmn(ctx);
   const size_t bytes = sizeof(double) * (size_t)std::max<long long>(ctx->ldx, 1) * ctx->naux;
   if (!ctx->Xsnap) GW_CUDA(cudaMalloc(&ctx->Xsnap, bytes));
@@ -243,6 +248,7 @@ int gwbse_mmn_snapshot(gwbse_ctx* ctx) {
 
 int gwbse_mmn_restore(gwbse_ctx* ctx) {
   GW_API_BEGIN(ctx)
+  GW_PROF(ctx, "mmn_restore");
   require_mmn(ctx);
   GW_REQUIRE(ctx->Xsnap != nullptr, "no Mmn snapshot to restore");
   const size_t bytes = sizeof(double) * (size_t)std::max<long long>(ctx->ldx, 1) * ctx->naux;
@@ -255,6 +261,7 @@ int gwbse_mmn_restore(gwbse_ctx* ctx) {
 int gwbse_pseudo_invsqrt(gwbse_ctx* ctx, int n, const double* S, const double* V, double etol, double* L_out,
                          int* removed) {
   GW_API_BEGIN(ctx)
+  GW_PROF(ctx, "pseudo_invsqrt");
   const size_t nn = (size_t)n * n;
   double* dS = ctx->buf("pis_S", nn);
   double* dV = ctx->buf("pis_V", nn);
@@ -294,6 +301,7 @@ int gwbse_pseudo_invsqrt(gwbse_ctx* ctx, int n, const double* S, const double* V
 int gwbse_rpa_epsilon(gwbse_ctx* ctx, int kind, double fre, double fim, double eta, const double* energies,
                       int homo, int rpamin, int rpamax, double* eps_out, int ld) {
   GW_API_BEGIN(ctx)
+  GW_PROF(ctx, "rpa_epsilon");
   require_mmn(ctx);
   GW_REQUIRE(kind >= 0 && kind <= 2, "epsilon kind must be 0 (imag), 1 (real) or 2 (complex)");
   GW_REQUIRE(rpamin == ctx->mmin && rpamin == ctx->nmin && rpamax == ctx->nmax,
@@ -354,6 +362,7 @@ double* gwbse_rpa_epsilon_ptr(gwbse_ctx* ctx) { return ctx ? ctx->eps : nullptr;
 int gwbse_rpa_h2p_apb(gwbse_ctx* ctx, const double* energies, int homo, int rpamin, int rpamax, double* apb_dev,
                       int ld) {
   GW_API_BEGIN(ctx)
+  GW_PROF(ctx, "rpa_h2p_apb");
   require_mmn(ctx);
   GW_REQUIRE(ctx->world == 1, "H2p is single-GPU (exact sigma does not scale, SURVEY.md 8e)");
   GW_REQUIRE(rpamin == ctx->mmin && rpamin == ctx->nmin && rpamax == ctx->nmax, "RPA range must match Mmn");
@@ -394,6 +403,7 @@ int gwbse_rpa_h2p_apb(gwbse_ctx* ctx, const double* energies, int homo, int rpam
 // ------------------------------ Sigma_x -------------------------------------
 int gwbse_sigma_x(gwbse_ctx* ctx, int homo, int rpamin, int qpmin, int qpmax, double* out, int ld) {
   GW_API_BEGIN(ctx)
+  GW_PROF(ctx, "sigma_x");
   require_mmn(ctx);
   GW_REQUIRE(ctx->world == 1, "gwbse_sigma_x: multi-GPU path uses gwbse_sigma_x after gathering (not built yet)");
   GW_REQUIRE(rpamin == ctx->mmin && rpamin == ctx->nmin, "RPA range must match Mmn");

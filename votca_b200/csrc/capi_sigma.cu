@@ -16,27 +16,49 @@ void upload(gwbse_ctx* ctx, double** dst, const double* src, size_t n) {
   GW_CUDA(cudaMemcpyAsync(*dst, src, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
 }
 
+// groups: levels[g] with frequencies freqs[gptr[g] .. gptr[g+1])
+void sigma_eval_groups(gwbse_ctx* ctx, gwbse_ctx::SigmaState& st, int ngroups, const int* levels, const int* gptr,
+                       const double* freqs, double* sigma, double* dsigma) {
+  GW_REQUIRE(st.ready, "sigma evaluator not prepared");
+  if (ngroups <= 0) return;
+  const int nfreq = gptr[ngroups];
+  if (nfreq <= 0) return;
+  for (int i = 0; i < ngroups; ++i) {
+    GW_REQUIRE(levels[i] >= 0 && levels[i] < st.q, "gw_level out of range");
+    GW_REQUIRE(gptr[i + 1] >= gptr[i], "group offsets must be non-decreasing");
+  }
+  GW_REQUIRE(ngroups <= 65535, "too many sigma request groups in one batch");
+  int* lev_d = reinterpret_cast<int*>(ctx->buf("sig_levels", (size_t)ngroups / 2 + 8));
+  int* gp_d = reinterpret_cast<int*>(ctx->buf("sig_gptr", (size_t)(ngroups + 1) / 2 + 8));
+  double* frq_d = ctx->buf("sig_freqs", nfreq);
+  GW_CUDA(cudaMemcpyAsync(lev_d, levels, sizeof(int) * ngroups, cudaMemcpyHostToDevice, ctx->stream));
+  GW_CUDA(cudaMemcpyAsync(gp_d, gptr, sizeof(int) * (ngroups + 1), cudaMemcpyHostToDevice, ctx->stream));
+  GW_CUDA(cudaMemcpyAsync(frq_d, freqs, sizeof(double) * nfreq, cudaMemcpyHostToDevice, ctx->stream));
+  const int nchunks = sigma_multi_chunks(st.npoles);
+  double* partial = ctx->buf("sig_partial", (size_t)nfreq * nchunks * 2);
+  double* out = ctx->buf("sig_out", (size_t)nfreq * 2);
+  launch_sigma_multi(st, ctx->ntotal, ngroups, nfreq, lev_d, gp_d, frq_d, partial, out, dsigma != nullptr,
+                     ctx->stream);
+  ctx->launches += 2;
+  GW_CUDA(cudaMemcpyAsync(sigma, out, sizeof(double) * nfreq, cudaMemcpyDeviceToHost, ctx->stream));
+  if (dsigma)
+    GW_CUDA(cudaMemcpyAsync(dsigma, out + nfreq, sizeof(double) * nfreq, cudaMemcpyDeviceToHost, ctx->stream));
+  GW_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
 void sigma_eval(gwbse_ctx* ctx, gwbse_ctx::SigmaState& st, int nreq, const int* levels, const double* freqs,
                 double* sigma, double* dsigma) {
-  GW_REQUIRE(st.ready, "sigma evaluator not prepared");
   if (nreq <= 0) return;
-  for (int i = 0; i < nreq; ++i)
-    GW_REQUIRE(levels[i] >= 0 && levels[i] < st.q, "gw_level out of range");
-  int* lev_d = reinterpret_cast<int*>(ctx->buf("sig_levels", (size_t)nreq / 2 + 8));
-  double* frq_d = ctx->buf("sig_freqs", nreq);
-  GW_CUDA(cudaMemcpyAsync(lev_d, levels, sizeof(int) * nreq, cudaMemcpyHostToDevice, ctx->stream));
-  GW_CUDA(cudaMemcpyAsync(frq_d, freqs, sizeof(double) * nreq, cudaMemcpyHostToDevice, ctx->stream));
-  int nsplit = (4 * ctx->num_sms + nreq - 1) / nreq;
-  nsplit = std::max(1, std::min(nsplit, std::min(64, std::max(1, st.npoles / 8))));
-  double* partial = ctx->buf("sig_partial", (size_t)nreq * nsplit * 2);
-  double* out = ctx->buf("sig_out", (size_t)nreq * 2);
-  launch_sigma_eval(st, ctx->ntotal, nreq, lev_d, frq_d, partial, nsplit, dsigma != nullptr, ctx->stream);
-  launch_sigma_eval_reduce(partial, nreq, nsplit, dsigma != nullptr, out, ctx->stream);
-  ctx->launches += 2;
-  GW_CUDA(cudaMemcpyAsync(sigma, out, sizeof(double) * nreq, cudaMemcpyDeviceToHost, ctx->stream));
-  if (dsigma)
-    GW_CUDA(cudaMemcpyAsync(dsigma, out + nreq, sizeof(double) * nreq, cudaMemcpyDeviceToHost, ctx->stream));
-  GW_CUDA(cudaStreamSynchronize(ctx->stream));
+  // one group per request (consecutive requests of the same level are merged)
+  std::vector<int> lv, gp;
+  for (int i = 0; i < nreq; ++i) {
+    if (i == 0 || levels[i] != levels[i - 1]) {
+      lv.push_back(levels[i]);
+      gp.push_back(i);
+    }
+  }
+  gp.push_back(nreq);
+  sigma_eval_groups(ctx, st, (int)lv.size(), lv.data(), gp.data(), freqs, sigma, dsigma);
 }
 
 // Off-diagonal Sigma_c for all level pairs as a weighted GEMM:
@@ -127,13 +149,25 @@ int gwbse_sigma_update_energies(gwbse_ctx* ctx, int which, const double* energie
 int gwbse_sigma_ppm_eval(gwbse_ctx* ctx, int nreq, const int* levels, const double* freqs, double* sigma,
                          double* dsigma) {
   GW_API_BEGIN(ctx)
+  GW_PROF(ctx, "sigma_ppm_eval");
   ctx->sig_ppm.mat = ctx->X;
   sigma_eval(ctx, ctx->sig_ppm, nreq, levels, freqs, sigma, dsigma);
   GW_API_END(ctx)
 }
 
+int gwbse_sigma_eval_groups(gwbse_ctx* ctx, int which, int ngroups, const int* levels, const int* group_ptr,
+                            const double* freqs, double* sigma, double* dsigma) {
+  GW_API_BEGIN(ctx)
+  GW_PROF(ctx, "sigma_eval_groups");
+  auto& st = which == 0 ? ctx->sig_ppm : ctx->sig_exact;
+  if (which == 0) st.mat = ctx->X;
+  sigma_eval_groups(ctx, st, ngroups, levels, group_ptr, freqs, sigma, dsigma);
+  GW_API_END(ctx)
+}
+
 int gwbse_sigma_ppm_offdiag(gwbse_ctx* ctx, int q, const double* freqs, double* out, int ld) {
   GW_API_BEGIN(ctx)
+  GW_PROF(ctx, "sigma_ppm_offdiag");
   ctx->sig_ppm.mat = ctx->X;
   const int qsave = ctx->sig_ppm.q;
   ctx->sig_ppm.q = q;
@@ -151,6 +185,7 @@ int gwbse_sigma_exact_prepare(gwbse_ctx* ctx, const double* rpa_omegas, const do
                               const double* energies, int homo, int rpamin, int rpamax, int qpmin, int qpmax,
                               double eta) {
   GW_API_BEGIN(ctx)
+  GW_PROF(ctx, "sigma_exact_prepare");
   GW_REQUIRE(ctx->X != nullptr, "Mmn not allocated");
   GW_REQUIRE(ctx->world == 1, "exact sigma is single-GPU (SURVEY.md 8e)");
   GW_REQUIRE(rpamin == ctx->mmin && rpamin == ctx->nmin && rpamax == ctx->nmax, "RPA range must match Mmn");
@@ -219,12 +254,14 @@ int gwbse_sigma_exact_prepare(gwbse_ctx* ctx, const double* rpa_omegas, const do
 int gwbse_sigma_exact_eval(gwbse_ctx* ctx, int nreq, const int* levels, const double* freqs, double* sigma,
                            double* dsigma) {
   GW_API_BEGIN(ctx)
+  GW_PROF(ctx, "sigma_exact_eval");
   sigma_eval(ctx, ctx->sig_exact, nreq, levels, freqs, sigma, dsigma);
   GW_API_END(ctx)
 }
 
 int gwbse_sigma_exact_offdiag(gwbse_ctx* ctx, int q, const double* freqs, double* out, int ld) {
   GW_API_BEGIN(ctx)
+  GW_PROF(ctx, "sigma_exact_offdiag");
   sigma_offdiag(ctx, ctx->sig_exact, 1.0, q, freqs, out, ld);
   GW_API_END(ctx)
 }

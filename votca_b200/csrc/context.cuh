@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cusolverDn.h>
 
+#include <chrono>
 #include <map>
 #include <string>
 #include <vector>
@@ -23,6 +24,38 @@ struct gwbse_ctx {
   cusolverDnHandle_t solver = nullptr;
   long long launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // region profiler (set_option "profile"): CUDA-event pairs per C-ABI entry point + host wall time
+  bool profile = false;
+  struct Region {
+    double ms = 0.0, wall_ms = 0.0;
+    long long calls = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+  };
+  std::map<std::string, Region> regions;
+  std::vector<cudaEvent_t> event_pool;
+  cudaEvent_t get_event() {
+    if (!event_pool.empty()) {
+      cudaEvent_t e = event_pool.back();
+      event_pool.pop_back();
+      return e;
+    }
+    cudaEvent_t e;
+    GW_CUDA(cudaEventCreate(&e));
+    return e;
+  }
+  void collect_regions() {
+    GW_CUDA(cudaStreamSynchronize(stream));
+    for (auto& kv : regions) {
+      for (auto& pr : kv.second.pending) {
+        float ms = 0.f;
+        GW_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+        kv.second.ms += ms;
+        event_pool.push_back(pr.first);
+        event_pool.push_back(pr.second);
+      }
+      kv.second.pending.clear();
+    }
+  }
   // GEMM accounting (gwbse_gemm_profile)
   bool gemm_profile = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm_events;
@@ -100,6 +133,30 @@ struct gwbse_ctx {
   int local_count(int upto) const { return upto <= rank ? 0 : (upto - rank + world - 1) / world; }
 };
 
+struct ProfScope {
+  gwbse_ctx* ctx;
+  const char* name;
+  cudaEvent_t e0 = nullptr;
+  std::chrono::steady_clock::time_point t0;
+  ProfScope(gwbse_ctx* c, const char* n) : ctx(c), name(n) {
+    if (!ctx->profile) return;
+    e0 = ctx->get_event();
+    cudaEventRecord(e0, ctx->stream);
+    t0 = std::chrono::steady_clock::now();
+  }
+  ~ProfScope() {
+    if (!e0) return;
+    cudaEvent_t e1 = ctx->get_event();
+    cudaEventRecord(e1, ctx->stream);
+    auto& r = ctx->regions[name];
+    r.pending.emplace_back(e0, e1);
+    r.calls++;
+    r.wall_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (r.pending.size() > 2048) ctx->collect_regions();
+  }
+};
+#define GW_PROF(ctx, name) ProfScope _prof_scope(ctx, name)
+
 #define GW_API_BEGIN(ctx) \
   if (!(ctx)) return 1;   \
   try {                   \
@@ -135,10 +192,10 @@ void launch_coldots(int m, int n, const double* X, long long ldx, const double* 
 void launch_scale_cols(int m, int n, double* A, long long lda, const double* s_dev, cudaStream_t s);
 void launch_copy_block(int m, int n, const double* A, long long lda, double* B, long long ldb, cudaStream_t s);
 void launch_invsqrt_scale(double* out, const double* w, int n, double etol, int* removed_dev, cudaStream_t s);
-void launch_sigma_eval(const gwbse_ctx::SigmaState& st, int ntotal, int nreq, const int* levels_dev,
-                       const double* freqs_dev, double* partial_dev, int nsplit, bool want_deriv, cudaStream_t s);
-void launch_sigma_eval_reduce(const double* partial_dev, int nreq, int nsplit, bool want_deriv, double* out_dev,
-                              cudaStream_t s);
+int sigma_multi_chunks(int npoles);
+void launch_sigma_multi(const gwbse_ctx::SigmaState& st, int ntotal, int ngroups, int nfreq, const int* levels_dev,
+                        const int* gptr_dev, const double* freqs_dev, double* partial_dev, double* out_dev,
+                        bool want_deriv, cudaStream_t s);
 void launch_sigma_offdiag_weight(const gwbse_ctx::SigmaState& st, int ntotal, int npad, int q, int p0, int np,
                                  const double* freqs_dev, double pref, double* out, long long ldo, cudaStream_t s);
 void launch_offdiag_finish(const double* S, int q, double* out, cudaStream_t s);

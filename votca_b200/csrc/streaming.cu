@@ -121,69 +121,123 @@ __global__ void invsqrt_scale_kernel(double* out, const double* w, int n, double
 }
 
 // ---------------------------------------------------------------------------
-// Sigma_c diagonal element (and derivative), one (level, frequency) request
-// per blockIdx.y, pole range split over blockIdx.x.
-//   sigma = pref * sum_p fac_p sum_n M[n,p]^2 t/(t^2+eta^2),  t = w - e_n +- pole_p
+// Sigma_c diagonal element (and derivative) for GROUPS of frequencies per level.
+//   sigma(w) = pref * sum_p fac_p sum_n M[n,p]^2 t/(t^2+eta^2),  t = w - e_n +- pole_p
+//   dsigma/dw = pref * sum_p fac_p sum_n M[n,p]^2 (eta^2 - t^2)/(t^2+eta^2)^2
 // sigma_ppm.cc:37-91 (fac = w*Omega, pref 1/2), sigma_exact.cc:40-83 (fac 1, pref 2).
+// One CTA = (group, chunk of SIG_PC poles); the level's M columns are read from HBM once and re-used
+// from L1 for every block of 8 frequencies of the group.  The kernel is FP64-arithmetic bound
+// (12 FP64 instructions per element and frequency, one of them a reciprocal), not HBM bound, as soon
+// as a group holds more than ~2 frequencies.  Partial sums are per (frequency, chunk) in a fixed
+// order, so a result does not depend on how requests were batched.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) sigma_eval_kernel(const double* __restrict__ mat, long long ld,
-                                                         long long lstride, int qpoff, int ntotal, int npoles,
-                                                         int boundary, double eta2, double pref,
-                                                         const double* __restrict__ fac,
-                                                         const double* __restrict__ pole,
-                                                         const double* __restrict__ energies,
-                                                         const int* __restrict__ levels,
-                                                         const double* __restrict__ freqs, double* partial,
-                                                         int want_deriv) {
-  extern __shared__ double sh_e[];  // ntotal energies + 32 reduction slots
-  double* sh_red = sh_e + ntotal;
-  const int req = blockIdx.y;
-  const int level = levels[req];
-  const double w = freqs[req];
-  for (int i = threadIdx.x; i < ntotal; i += blockDim.x) sh_e[i] = w - energies[i];
-  __syncthreads();
-  const int nsplit = gridDim.x;
-  const int per = (npoles + nsplit - 1) / nsplit;
-  const int p0 = blockIdx.x * per, p1 = min(npoles, p0 + per);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  const double* base = mat + (long long)(qpoff + level) * lstride;
-  double s = 0.0, ds = 0.0;
-  for (int p = p0 + warp; p < p1; p += nwarps) {
-    const double f = fac[p];
-    if (f == 0.0) continue;
-    const double om = pole[p];
-    const double* col = base + (long long)p * ld;
-    double sp = 0.0, dsp = 0.0;
-    for (int n = lane; n < ntotal; n += 32) {
-      const double m = col[n];
-      const double t = sh_e[n] + (n < boundary ? om : -om);
-      const double t2 = t * t;
-      const double inv = 1.0 / (t2 + eta2);
-      const double m2 = m * m;
-      sp += m2 * t * inv;
-      if (want_deriv) dsp += m2 * (eta2 - t2) * inv * inv;
-    }
-    s += f * sp;
-    ds += f * dsp;
+constexpr int SIG_PC = 8;   // poles per CTA
+constexpr int SIG_FB = 8;   // frequencies per register block
+
+__device__ __forceinline__ double rcp_pos(double x) {
+  // x = t^2 + eta^2 is positive, finite and normal: MUFU seed + 2 Newton steps (no special-case path)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+
+template <bool DERIV>
+__global__ void __launch_bounds__(256) sigma_multi_kernel(const double* __restrict__ mat, long long ld,
+                                                          long long lstride, int qpoff, int ntotal, int npoles,
+                                                          int boundary, double eta2,
+                                                          const double* __restrict__ fac,
+                                                          const double* __restrict__ pole,
+                                                          const double* __restrict__ energies,
+                                                          const int* __restrict__ levels,
+                                                          const int* __restrict__ gptr,
+                                                          const double* __restrict__ freqs, double* partial,
+                                                          int nchunks) {
+  __shared__ double sh[2 * SIG_FB][8];
+  const int g = blockIdx.y, chunk = blockIdx.x;
+  const int level = levels[g];
+  const int f_begin = gptr[g], nf = gptr[g + 1] - f_begin;
+  const int p0 = chunk * SIG_PC;
+  double om[SIG_PC], fc[SIG_PC];
+  const double* cols[SIG_PC];
+  bool any = false;
+#pragma unroll
+  for (int p = 0; p < SIG_PC; ++p) {
+    const int pp = min(p0 + p, npoles - 1);
+    om[p] = pole[pp];
+    fc[p] = (p0 + p < npoles) ? fac[pp] : 0.0;
+    any = any || fc[p] != 0.0;
+    cols[p] = mat + (long long)pp * ld + (long long)(qpoff + level) * lstride;
   }
-  s = block_sum(s, sh_red);
-  ds = block_sum(ds, sh_red);
-  if (threadIdx.x == 0) {
-    partial[((long long)req * nsplit + blockIdx.x) * 2 + 0] = pref * s;
-    partial[((long long)req * nsplit + blockIdx.x) * 2 + 1] = pref * ds;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const double two_eta2 = 2.0 * eta2;
+  for (int fb = 0; fb < nf; fb += SIG_FB) {
+    double wf[SIG_FB], as[SIG_FB], ad[SIG_FB];
+#pragma unroll
+    for (int f = 0; f < SIG_FB; ++f) {
+      wf[f] = freqs[f_begin + min(fb + f, nf - 1)];
+      as[f] = 0.0;
+      ad[f] = 0.0;
+    }
+    if (any) {
+      for (int n = threadIdx.x; n < ntotal; n += 256) {
+        const double e = energies[n];
+        const bool occ = n < boundary;
+#pragma unroll
+        for (int p = 0; p < SIG_PC; ++p) {
+          const double m = cols[p][n];
+          const double m2 = fc[p] * m * m;
+          const double a = occ ? e - om[p] : e + om[p];  // t = w - a
+#pragma unroll
+          for (int f = 0; f < SIG_FB; ++f) {
+            const double t = wf[f] - a;
+            const double r = rcp_pos(fma(t, t, eta2));
+            as[f] = fma(m2, t * r, as[f]);
+            if (DERIV) ad[f] = fma(m2, r * fma(two_eta2, r, -1.0), ad[f]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int f = 0; f < SIG_FB; ++f) {
+      as[f] = warp_sum(as[f]);
+      if (DERIV) ad[f] = warp_sum(ad[f]);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int f = 0; f < SIG_FB; ++f) {
+        sh[f][warp] = as[f];
+        if (DERIV) sh[SIG_FB + f][warp] = ad[f];
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < SIG_FB * (DERIV ? 2 : 1)) {
+      const int f = threadIdx.x % SIG_FB, isd = threadIdx.x / SIG_FB;
+      if (fb + f < nf) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += sh[threadIdx.x][w];
+        partial[((long long)(f_begin + fb + f) * nchunks + chunk) * 2 + isd] = v;
+      }
+    }
+    __syncthreads();
   }
 }
 
-__global__ void sigma_eval_reduce_kernel(const double* partial, int nreq, int nsplit, double* out) {
+__global__ void sigma_multi_reduce_kernel(const double* partial, int nfreq, int nchunks, double pref, int deriv,
+                                          double* out) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= nreq) return;
+  if (r >= nfreq) return;
   double s = 0.0, ds = 0.0;
-  for (int k = 0; k < nsplit; ++k) {
-    s += partial[((long long)r * nsplit + k) * 2 + 0];
-    ds += partial[((long long)r * nsplit + k) * 2 + 1];
+  for (int k = 0; k < nchunks; ++k) {
+    s += partial[((long long)r * nchunks + k) * 2 + 0];
+    if (deriv) ds += partial[((long long)r * nchunks + k) * 2 + 1];
   }
-  out[r] = s;
-  out[nreq + r] = ds;
+  out[r] = pref * s;
+  out[nfreq + r] = pref * ds;
 }
 
 // A_i[n, p] = pref * fac_p * M_i[n, p] * t/(t^2+eta^2), t = w_i - e_n +- pole_p  (off-diagonal Sigma_c as a GEMM)
@@ -326,20 +380,25 @@ void launch_invsqrt_scale(double* out, const double* w, int n, double etol, int*
   invsqrt_scale_kernel<<<(n + 255) / 256, 256, 0, s>>>(out, w, n, etol, removed_dev);
   GW_CUDA(cudaGetLastError());
 }
-void launch_sigma_eval(const gwbse_ctx::SigmaState& st, int ntotal, int nreq, const int* levels_dev,
-                       const double* freqs_dev, double* partial_dev, int nsplit, bool want_deriv, cudaStream_t s) {
-  if (nreq <= 0) return;
-  const size_t sh = sizeof(double) * (ntotal + 32);
-  sigma_eval_kernel<<<dim3(nsplit, nreq), 256, sh, s>>>(st.mat, st.ld, st.lstride, st.qpoff, ntotal, st.npoles,
-                                                        st.nocc_boundary, st.eta * st.eta, st.diag_pref, st.fac,
-                                                        st.pole, st.energies, levels_dev, freqs_dev, partial_dev,
-                                                        want_deriv ? 1 : 0);
+int sigma_multi_chunks(int npoles) { return (npoles + SIG_PC - 1) / SIG_PC; }
+
+void launch_sigma_multi(const gwbse_ctx::SigmaState& st, int ntotal, int ngroups, int nfreq, const int* levels_dev,
+                        const int* gptr_dev, const double* freqs_dev, double* partial_dev, double* out_dev,
+                        bool want_deriv, cudaStream_t s) {
+  if (ngroups <= 0 || nfreq <= 0) return;
+  const int nchunks = sigma_multi_chunks(st.npoles);
+  dim3 grid(nchunks, ngroups);
+  if (want_deriv)
+    sigma_multi_kernel<true><<<grid, 256, 0, s>>>(st.mat, st.ld, st.lstride, st.qpoff, ntotal, st.npoles,
+                                                  st.nocc_boundary, st.eta * st.eta, st.fac, st.pole, st.energies,
+                                                  levels_dev, gptr_dev, freqs_dev, partial_dev, nchunks);
+  else
+    sigma_multi_kernel<false><<<grid, 256, 0, s>>>(st.mat, st.ld, st.lstride, st.qpoff, ntotal, st.npoles,
+                                                   st.nocc_boundary, st.eta * st.eta, st.fac, st.pole, st.energies,
+                                                   levels_dev, gptr_dev, freqs_dev, partial_dev, nchunks);
   GW_CUDA(cudaGetLastError());
-}
-void launch_sigma_eval_reduce(const double* partial_dev, int nreq, int nsplit, bool, double* out_dev,
-                              cudaStream_t s) {
-  if (nreq <= 0) return;
-  sigma_eval_reduce_kernel<<<(nreq + 127) / 128, 128, 0, s>>>(partial_dev, nreq, nsplit, out_dev);
+  sigma_multi_reduce_kernel<<<(nfreq + 127) / 128, 128, 0, s>>>(partial_dev, nfreq, nchunks, st.diag_pref,
+                                                                want_deriv ? 1 : 0, out_dev);
   GW_CUDA(cudaGetLastError());
 }
 void launch_sigma_offdiag_weight(const gwbse_ctx::SigmaState& st, int ntotal, int npad, int q, int p0, int np,

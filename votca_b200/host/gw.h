@@ -8,6 +8,7 @@
 #include <cstring>
 #include <mutex>
 #include <thread>
+#include <unordered_map>
 #include <unordered_set>
 
 #include "qp_rootsearch.h"
@@ -103,21 +104,22 @@ class Anderson {
   Index order_ = 25;
 };
 
-// Collects Sigma_c requests of the concurrently running per-level searches into batches.
+// Collects Sigma_c requests of the concurrently running per-level searches into batches.  A request is one
+// level with a SET of frequencies (the one needed now plus the ones the search is known to need next), so
+// the kernel streams the level's data once for all of them.
 class SigmaBatcher {
  public:
   explicit SigmaBatcher(const Sigma_base& sigma) : sigma_(sigma) {}
 
-  // called by worker threads
-  void Evaluate(Index level, double freq, bool want_deriv, double& s, double& ds) {
+  // called by worker threads: evaluates Sigma_c (and d/dw if want_deriv) at freqs for this level
+  void Evaluate(Index level, const std::vector<double>& freqs, bool want_deriv, std::vector<double>& s,
+                std::vector<double>& ds) {
     std::unique_lock<std::mutex> lk(mu_);
-    Request r{(int)level, freq, want_deriv, 0.0, 0.0, false};
+    Request r{(int)level, &freqs, want_deriv, &s, &ds, false};
     queue_.push_back(&r);
     cv_server_.notify_one();
     cv_workers_.wait(lk, [&] { return r.done; });
     if (!error_.empty()) throw std::runtime_error(error_);
-    s = r.s;
-    ds = r.ds;
   }
   void WorkerStarted() {
     std::lock_guard<std::mutex> lk(mu_);
@@ -136,28 +138,32 @@ class SigmaBatcher {
       if (running_ == 0 && queue_.empty()) return;
       std::vector<Request*> batch;
       batch.swap(queue_);
-      std::vector<int> lv(batch.size());
-      std::vector<double> fr(batch.size()), s, ds;
+      std::vector<int> lv(batch.size()), gp(batch.size() + 1, 0);
+      std::vector<double> fr, s, ds;
       bool any_deriv = false;
       for (size_t i = 0; i < batch.size(); ++i) {
         lv[i] = batch[i]->level;
-        fr[i] = batch[i]->freq;
+        fr.insert(fr.end(), batch[i]->freqs->begin(), batch[i]->freqs->end());
+        gp[i + 1] = (int)fr.size();
         any_deriv = any_deriv || batch[i]->want_deriv;
       }
       lk.unlock();
       try {
-        sigma_.EvalBatch(lv, fr, s, any_deriv ? &ds : nullptr);
+        sigma_.EvalGroups(lv, gp, fr, s, any_deriv ? &ds : nullptr);
       } catch (const std::exception& e) {
         error_ = e.what();
-        s.assign(batch.size(), 0.0);
-        ds.assign(batch.size(), 0.0);
+        s.assign(fr.size(), 0.0);
+        ds.assign(fr.size(), 0.0);
       }
       lk.lock();
       ++batches_;
-      evaluations_ += batch.size();
+      evaluations_ += fr.size();
       for (size_t i = 0; i < batch.size(); ++i) {
-        batch[i]->s = s[i];
-        batch[i]->ds = any_deriv ? ds[i] : 0.0;
+        batch[i]->s->assign(s.begin() + gp[i], s.begin() + gp[i + 1]);
+        if (any_deriv)
+          batch[i]->ds->assign(ds.begin() + gp[i], ds.begin() + gp[i + 1]);
+        else
+          batch[i]->ds->clear();
         batch[i]->done = true;
       }
       cv_workers_.notify_all();
@@ -169,9 +175,10 @@ class SigmaBatcher {
  private:
   struct Request {
     int level;
-    double freq;
+    const std::vector<double>* freqs;
     bool want_deriv;
-    double s, ds;
+    std::vector<double>* s;
+    std::vector<double>* ds;
     bool done;
   };
   const Sigma_base& sigma_;
@@ -328,40 +335,78 @@ class GW {
   }
 
  private:
-  // f(w) = Sigma_c(w) + offset - w, gw.h:214-300; Sigma_c requests go through the batcher
+  // f(w) = Sigma_c(w) + offset - w, gw.h:214-300.  Sigma_c requests go through the batcher.  Every value the
+  // GPU returns is cached under the frequency's bit pattern (the key the reference already uses for its
+  // statistics, gw.h:261-267); prefetch() announces frequencies the search will ask for next so that they
+  // ride along with the current request.  The cache only removes round trips: each Sigma_c(w) is computed
+  // by the same kernel arithmetic whether it was prefetched or not.
   class QPFunc {
    public:
     QPFunc(Index gw_level, SigmaBatcher& batcher, double offset)
         : gw_level_(gw_level), offset_(offset), batcher_(batcher) {}
     std::pair<double, double> operator()(double frequency) const {
-      double s, ds;
-      batcher_.Evaluate(gw_level_, frequency, true, s, ds);
       Count(frequency, EvalStage::Other);
       ++stats_.deriv_calls;
-      return {s + offset_ - frequency, ds - 1.0};
+      const Entry& e = Fetch(frequency, true);
+      return {e.s + offset_ - frequency, e.ds - 1.0};
     }
     double sigma(double frequency, EvalStage stage = EvalStage::Other) const {
       Count(frequency, stage);
-      double s, ds;
-      batcher_.Evaluate(gw_level_, frequency, false, s, ds);
-      return s;
+      return Fetch(frequency, false).s;
     }
     double value(double frequency, EvalStage stage = EvalStage::Other) const {
       return sigma(frequency, stage) + offset_ - frequency;
     }
     double deriv(double frequency) const {
       ++stats_.deriv_calls;
-      double s, ds;
-      batcher_.Evaluate(gw_level_, frequency, true, s, ds);
-      return ds - 1.0;
+      return Fetch(frequency, true).ds - 1.0;
+    }
+    // hint: these frequencies will be requested soon (with_deriv: value and derivative)
+    void prefetch(const double* freqs, std::size_t n, bool with_deriv = false) const {
+      for (std::size_t i = 0; i < n; ++i) {
+        auto it = cache_.find(Key(freqs[i]));
+        if (it != cache_.end() && (!with_deriv || it->second.has_ds)) continue;
+        pending_.push_back(freqs[i]);
+        pending_deriv_ = pending_deriv_ || with_deriv;
+      }
     }
     const QPStats& GetStats() const { return stats_; }
 
    private:
-    void Count(double x, EvalStage stage) const {
+    struct Entry {
+      double s = 0.0, ds = 0.0;
+      bool has_ds = false;
+    };
+    static std::uint64_t Key(double x) {
       std::uint64_t key = 0;
       std::memcpy(&key, &x, sizeof(double));
-      if (!seen_frequencies_.insert(key).second)
+      return key;
+    }
+    const Entry& Fetch(double frequency, bool need_deriv) const {
+      auto it = cache_.find(Key(frequency));
+      if (it != cache_.end() && (!need_deriv || it->second.has_ds)) return it->second;
+      std::vector<double> fr;
+      fr.push_back(frequency);
+      std::unordered_set<std::uint64_t> in_req{Key(frequency)};
+      for (double f : pending_)
+        if (in_req.insert(Key(f)).second && fr.size() < 96) fr.push_back(f);
+      const bool want = need_deriv || pending_deriv_;
+      pending_.clear();
+      pending_deriv_ = false;
+      std::vector<double> s, ds;
+      batcher_.Evaluate(gw_level_, fr, want, s, ds);
+      for (std::size_t i = 0; i < fr.size(); ++i) {
+        Entry& e = cache_[Key(fr[i])];
+        e.s = s[i];
+        if (!ds.empty()) {
+          e.ds = ds[i];
+          e.has_ds = true;
+        }
+      }
+      return cache_[Key(frequency)];
+    }
+    void Count(double x, EvalStage stage) const {
+      if (!seen_frequencies_.insert(Key(x)).second)
         ++stats_.sigma_repeat_calls;
       else
         ++stats_.sigma_unique_frequencies;
@@ -375,6 +420,9 @@ class GW {
     Index gw_level_;
     double offset_;
     SigmaBatcher& batcher_;
+    mutable std::unordered_map<std::uint64_t, Entry> cache_;
+    mutable std::vector<double> pending_;
+    mutable bool pending_deriv_ = false;
     mutable std::unordered_set<std::uint64_t> seen_frequencies_;
     mutable QPStats stats_;
   };
@@ -520,14 +568,24 @@ class GW {
     std::vector<QPRootCandidate> accepted_roots, rejected_roots;
     if (left_limit < right_limit) {
       double freq_prev = left_limit;
-      double targ_prev = fqp.value(freq_prev, EvalStage::Scan);
       const Index n_steps =
           std::max<Index>(2, static_cast<Index>(std::ceil((right_limit - left_limit) / opt_.qp_dense_spacing)) + 1);
+      auto node = [&](Index i_node) {
+        return (i_node == n_steps - 1)
+                   ? right_limit
+                   : std::min(right_limit, left_limit + static_cast<double>(i_node) * opt_.qp_dense_spacing);
+      };
+      const Index look = 64;  // the scan nodes are known ahead: announce them in blocks
+      auto announce = [&](Index from) {
+        std::vector<double> pts;
+        for (Index i = from; i < std::min(n_steps, from + look); ++i) pts.push_back(node(i));
+        fqp.prefetch(pts.data(), pts.size());
+      };
+      announce(1);
+      double targ_prev = fqp.value(freq_prev, EvalStage::Scan);
       for (Index i_node = 1; i_node < n_steps; ++i_node) {
-        const double freq =
-            (i_node == n_steps - 1)
-                ? right_limit
-                : std::min(right_limit, left_limit + static_cast<double>(i_node) * opt_.qp_dense_spacing);
+        if (i_node > 1 && (i_node - 1) % look == 0) announce(i_node);
+        const double freq = node(i_node);
         const double targ = fqp.value(freq, EvalStage::Scan);
         if (targ_prev * targ < 0.0) {
           auto cand =

@@ -98,9 +98,22 @@ double SolveQP_Bisection(double lowerbound, double f_lowerbound, double upperbou
                          const QPFunc& f, const SolverOptions& opt) {
   if (f_lowerbound * f_upperbound > 0.0)
     throw std::runtime_error("Bisection needs a positive and negative function value");
+  Index step = 0;
   while (true) {
     const double c = 0.5 * (lowerbound + upperbound);
     if (std::abs(upperbound - lowerbound) < opt.g_sc_limit) return c;
+    if (step++ % 3 == 0) {
+      // the next three midpoints lie in this binary tree whatever the signs turn out to be
+      double pts[7];
+      pts[0] = c;
+      pts[1] = 0.5 * (lowerbound + c);
+      pts[2] = 0.5 * (c + upperbound);
+      pts[3] = 0.5 * (lowerbound + pts[1]);
+      pts[4] = 0.5 * (pts[1] + c);
+      pts[5] = 0.5 * (c + pts[2]);
+      pts[6] = 0.5 * (pts[2] + upperbound);
+      f.prefetch(pts, 7);
+    }
     const double y_c = f.value(c, EvalStage::Refine);
     if (std::abs(y_c) < opt.g_sc_limit) return c;
     if (y_c * f_lowerbound > 0.0) {
@@ -209,6 +222,7 @@ std::optional<RootCandidate> RefineQPInterval(double lowerbound, double f_lowerb
     cand.omega = use_brent ? SolveQP_Brent(lowerbound, f_lowerbound, upperbound, f_upperbound, f, opt)
                            : SolveQP_Bisection(lowerbound, f_lowerbound, upperbound, f_upperbound, f, opt);
   }
+  f.prefetch(&cand.omega, 1, true);  // residual and slope at the same frequency: one evaluation
   cand.residual = f.value(cand.omega, EvalStage::Refine);
   cand.deriv = f.deriv(cand.omega);
   cand.Z = (std::abs(cand.deriv) > 1e-14) ? -1.0 / cand.deriv : std::numeric_limits<double>::infinity();
@@ -241,6 +255,7 @@ std::optional<double> SolveQP_Grid_Windowed(QPFunc& fqp, double frequency0, doub
   const double shell_width = EffectiveAdaptiveShellWidth(opt);
   double center = frequency0;
   if (gw_sc_iteration == 0) {
+    fqp.prefetch(&frequency0, 1, true);
     const double f0 = fqp.value(frequency0, EvalStage::Other);
     const double df0 = fqp.deriv(frequency0);
     if (std::isfinite(f0) && std::isfinite(df0) && std::abs(df0) > 1e-6) {
@@ -265,6 +280,11 @@ std::optional<double> SolveQP_Grid_Windowed(QPFunc& fqp, double frequency0, doub
     std::vector<LocalBracket> local_brackets;
     if (b > a) {
       const double dx = (b - a) / static_cast<double>(local_substeps);
+      {
+        std::vector<double> pts;
+        for (Index i = 1; i < local_substeps; ++i) pts.push_back(a + static_cast<double>(i) * dx);
+        fqp.prefetch(pts.data(), pts.size());
+      }
       double x_prev = a, f_prev = fa;
       for (Index i = 1; i <= local_substeps; ++i) {
         const double x_curr = (i == local_substeps) ? b : (a + static_cast<double>(i) * dx);
@@ -308,6 +328,18 @@ std::optional<double> SolveQP_Grid_Windowed(QPFunc& fqp, double frequency0, doub
     }
   };
 
+  {
+    // every shell point is visited below whatever the function values are: announce them all
+    std::vector<double> pts;
+    for (Index shell = 1; shell <= n_shells; ++shell) {
+      const double delta = double(shell) * shell_width;
+      if (center - delta >= left_limit) pts.push_back(center - delta);
+      if (center + delta <= right_limit) pts.push_back(center + delta);
+    }
+    pts.push_back(left_limit);
+    pts.push_back(right_limit);
+    fqp.prefetch(pts.data(), pts.size());
+  }
   Sample center_pt{center, fqp.value(center, EvalStage::Scan)};
   bool left_active = true, right_active = true;
   Sample left_prev = center_pt, right_prev = center_pt;

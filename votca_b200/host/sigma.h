@@ -64,6 +64,15 @@ class Sigma_base {
   virtual void PrepareScreening() = 0;
   virtual void EvalBatch(const std::vector<int>& levels, const std::vector<double>& freqs,
                          std::vector<double>& sigma, std::vector<double>* dsigma) const = 0;
+  // grouped form: level levels[g] at freqs[gptr[g] .. gptr[g+1]); default = flat batch
+  virtual void EvalGroups(const std::vector<int>& levels, const std::vector<int>& gptr,
+                          const std::vector<double>& freqs, std::vector<double>& sigma,
+                          std::vector<double>* dsigma) const {
+    std::vector<int> flat(freqs.size());
+    for (size_t g = 0; g < levels.size(); ++g)
+      for (int i = gptr[g]; i < gptr[g + 1]; ++i) flat[i] = levels[g];
+    EvalBatch(flat, freqs, sigma, dsigma);
+  }
 
   double CalcCorrelationDiagElement(Index gw_level, double frequency) const {
     CountDiagEval();
@@ -164,6 +173,15 @@ class Sigma_PPM : public Sigma_base {
     dev.check(gwbse_sigma_ppm_eval(dev.ctx(), (int)levels.size(), levels.data(), freqs.data(), sigma.data(),
                                    dsigma ? dsigma->data() : nullptr));
   }
+  void EvalGroups(const std::vector<int>& levels, const std::vector<int>& gptr, const std::vector<double>& freqs,
+                  std::vector<double>& sigma, std::vector<double>* dsigma) const final {
+    const Device& dev = Mmn_.device();
+    sigma.resize(freqs.size());
+    if (dsigma) dsigma->resize(freqs.size());
+    dev.check(gwbse_sigma_update_energies(dev.ctx(), 0, rpa_.getRPAInputEnergies().data()));
+    dev.check(gwbse_sigma_eval_groups(dev.ctx(), 0, (int)levels.size(), levels.data(), gptr.data(), freqs.data(),
+                                      sigma.data(), dsigma ? dsigma->data() : nullptr));
+  }
   MatrixXd CalcCorrelationOffDiag(const VectorXd& frequencies) const final {
     MatrixXd out(qptotal_, qptotal_);
     const Device& dev = Mmn_.device();
@@ -200,6 +218,15 @@ class Sigma_Exact : public Sigma_base {
     dev.check(gwbse_sigma_update_energies(dev.ctx(), 1, rpa_.getRPAInputEnergies().data()));
     dev.check(gwbse_sigma_exact_eval(dev.ctx(), (int)levels.size(), levels.data(), freqs.data(), sigma.data(),
                                      dsigma ? dsigma->data() : nullptr));
+  }
+  void EvalGroups(const std::vector<int>& levels, const std::vector<int>& gptr, const std::vector<double>& freqs,
+                  std::vector<double>& sigma, std::vector<double>* dsigma) const final {
+    const Device& dev = Mmn_.device();
+    sigma.resize(freqs.size());
+    if (dsigma) dsigma->resize(freqs.size());
+    dev.check(gwbse_sigma_update_energies(dev.ctx(), 1, rpa_.getRPAInputEnergies().data()));
+    dev.check(gwbse_sigma_eval_groups(dev.ctx(), 1, (int)levels.size(), levels.data(), gptr.data(), freqs.data(),
+                                      sigma.data(), dsigma ? dsigma->data() : nullptr));
   }
   MatrixXd CalcCorrelationOffDiag(const VectorXd& frequencies) const final {
     MatrixXd out(qptotal_, qptotal_);
