@@ -11,7 +11,7 @@ namespace {
 struct Cfg {
   int BM, BN, occ;
 };
-constexpr Cfg kCfg[3] = {{128, 128, 1}, {128, 32, 2}, {64, 64, 2}};
+constexpr Cfg kCfg[6] = {{128, 128, 1}, {128, 32, 2}, {64, 64, 2}, {128, 128, 1}, {128, 64, 2}, {128, 48, 2}};
 
 template <int BM, int BN, int WGM, int WGN, int STAGES, int MINB, bool AK, bool BKM, bool HASW>
 void launch_one(const GemmParams& p, dim3 grid, cudaStream_t stream) {
@@ -74,24 +74,32 @@ struct Plan {
   bool swap;
 };
 
+// Relative throughput of the tile shapes measured on B200 (scratch/gemm_cfgs.py, 4096^3 and the BSE shapes):
+// 128x64 with two co-resident CTAs per SM is the fastest; the narrow tiles exist to fit skinny dimensions.
+constexpr double kCfgEff[6] = {0.88, 0.55, 0.60, 0.90, 1.00, 0.85};
+
 Plan make_plan(const GemmParams& p, int num_sms, int force_cfg, int force_splitk) {
   Plan pl{};
   pl.swap = false;
-  int M = p.M, N = p.N;
-  if (force_cfg < 0 && !p.w && !p.nscale && !p.lower_only && M <= 32 && N > 32) {
-    pl.swap = true;
-    std::swap(M, N);
-  }
+  const bool can_swap = force_cfg < 0 && !p.w && !p.nscale && !p.lower_only;
   int cfg = force_cfg;
   if (cfg < 0) {
-    if (N <= 32)
-      cfg = 1;
-    else if (M <= 64 || N <= 64 || ((long long)ceil_div(M, 128) * ceil_div(N, 128) * p.Z1 * p.Z2 < num_sms / 2 &&
-                                    (long long)p.Ko * p.Ki < 2048))
-      cfg = 2;
-    else
-      cfg = 0;
+    // pick (orientation, tile shape) minimising padded work / throughput
+    double best = 1e300;
+    for (int sw = 0; sw <= (can_swap ? 1 : 0); ++sw) {
+      const int M = sw ? p.N : p.M, N = sw ? p.M : p.N;
+      for (int c : {4, 5, 1, 2}) {
+        const double padded = (double)ceil_div(M, kCfg[c].BM) * kCfg[c].BM * (double)ceil_div(N, kCfg[c].BN) * kCfg[c].BN;
+        const double cost = padded / kCfgEff[c] * (sw ? 1.02 : 1.0);
+        if (cost < best) {
+          best = cost;
+          cfg = c;
+          pl.swap = sw != 0;
+        }
+      }
+    }
   }
+  const int M = pl.swap ? p.N : p.M, N = pl.swap ? p.M : p.N;
   pl.cfg = cfg;
   pl.tiles_m = ceil_div(M, kCfg[cfg].BM);
   pl.tiles_n = ceil_div(N, kCfg[cfg].BN);
@@ -103,8 +111,8 @@ Plan make_plan(const GemmParams& p, int num_sms, int force_cfg, int force_splitk
   if (splitk <= 0) {
     const long long target = (long long)num_sms * kCfg[cfg].occ;
     splitk = 1;
-    if (tiles < target) {
-      long long want = ceil_div(2 * target, tiles);
+    if (tiles < 2 * target) {
+      long long want = ceil_div(3 * target, tiles);
       long long cap = std::max<long long>(1, T_total / 8);
       splitk = (int)std::max<long long>(1, std::min<long long>(std::min(want, cap), 64));
     }
@@ -165,6 +173,15 @@ void gemm_launch(GemmParams p, cudaStream_t stream, double* ws, size_t ws_bytes,
     case 1:
       launch_cfg<128, 32, 4, 1, 4, 2>(p, grid, ak, bk, stream);
       break;
+    case 3:
+      launch_cfg<128, 128, 4, 4, 4, 1>(p, grid, ak, bk, stream);
+      break;
+    case 4:
+      launch_cfg<128, 64, 4, 2, 3, 2>(p, grid, ak, bk, stream);
+      break;
+    case 5:
+      launch_cfg<128, 48, 4, 1, 3, 2>(p, grid, ak, bk, stream);
+      break;
     default:
       launch_cfg<64, 64, 2, 2, 4, 2>(p, grid, ak, bk, stream);
       break;
@@ -179,6 +196,15 @@ void gemm_launch(GemmParams p, cudaStream_t stream, double* ws, size_t ws_bytes,
         break;
       case 1:
         gemm_splitk_reduce_kernel<128, 32><<<rg, rb, 0, stream>>>(p);
+        break;
+      case 3:
+        gemm_splitk_reduce_kernel<128, 128><<<rg, rb, 0, stream>>>(p);
+        break;
+      case 4:
+        gemm_splitk_reduce_kernel<128, 64><<<rg, rb, 0, stream>>>(p);
+        break;
+      case 5:
+        gemm_splitk_reduce_kernel<128, 48><<<rg, rb, 0, stream>>>(p);
         break;
       default:
         gemm_splitk_reduce_kernel<64, 64><<<rg, rb, 0, stream>>>(p);
