@@ -214,13 +214,8 @@ int gwbse_bse_configure(gwbse_ctx* ctx, int homo, int rpamin, int vmin, int cmax
   GW_REQUIRE(st.coff + st.ct <= ctx->mtotal && st.coff + st.ct <= ctx->ntotal, "BSE range exceeds Mmn");
   const int hs = st.vt + st.ct;
   GW_REQUIRE(ldh >= hs, "Hqp leading dimension too small");
-  GW_CUDA(cudaStreamSynchronize(ctx->stream));
-  for (double** p : {&st.eps_inv, &st.hqp}) {
-    if (*p) GW_CUDA(cudaFree(*p));
-    *p = nullptr;
-  }
-  GW_CUDA(cudaMalloc(&st.eps_inv, sizeof(double) * ctx->naux));
-  GW_CUDA(cudaMalloc(&st.hqp, sizeof(double) * (size_t)hs * hs));
+  st.eps_inv = ctx->buf("bse_eps_inv", ctx->naux);
+  st.hqp = ctx->buf("bse_hqp", (size_t)hs * hs);
   GW_CUDA(cudaMemcpyAsync(st.eps_inv, eps_inv, sizeof(double) * ctx->naux, cudaMemcpyHostToDevice, ctx->stream));
   GW_CUDA(cudaMemcpy2DAsync(st.hqp, sizeof(double) * hs, Hqp, sizeof(double) * ldh, sizeof(double) * hs, hs,
                             cudaMemcpyHostToDevice, ctx->stream));

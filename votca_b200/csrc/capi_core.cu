@@ -122,7 +122,9 @@ void gwbse_ctx_destroy(gwbse_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (auto& kv : ctx->bufs)
     if (kv.second.p) cudaFree(kv.second.p);
-  for (double* p : {ctx->X, ctx->X2, ctx->Xsnap, ctx->mos, ctx->exact_res, ctx->bse.eps_inv, ctx->bse.hqp})
+  for (auto& kv : ctx->free_blocks) cudaFree(kv.second);
+  for (auto& kv : ctx->live_blocks) cudaFree(kv.first);
+  for (double* p : {ctx->X, ctx->X2, ctx->Xsnap, ctx->mos, ctx->exact_res})
     if (p) cudaFree(p);
   for (auto* st : {&ctx->sig_ppm, &ctx->sig_exact})
     for (double* p : {st->fac, st->pole, st->energies})
@@ -241,19 +243,48 @@ int gwbse_timer_stop_ms(gwbse_ctx* ctx, float* ms) {
 // ------------------------------ memory ------------------------------------
 int gwbse_dev_malloc(gwbse_ctx* ctx, size_t bytes, double** out_dev) {
   GW_API_BEGIN(ctx)
-  // same pre-check and message style as CudaMatrix::alloc (cudamatrix.cc:97-113)
-  size_t fr = 0, tot = 0;
-  GW_CUDA(cudaMemGetInfo(&fr, &tot));
-  if (bytes > fr)
-    throw std::runtime_error("There were requested : " + std::to_string((double)bytes / 1048576.0) +
-                             " MB but the device has " + std::to_string((double)fr / 1048576.0) + " MB free.");
-  GW_CUDA(cudaMalloc(out_dev, bytes ? bytes : 8));
+  if (bytes == 0) bytes = 8;
+  auto it = ctx->free_blocks.find(bytes);
+  if (it != ctx->free_blocks.end()) {
+    *out_dev = it->second;
+    ctx->free_blocks.erase(it);
+    ctx->cached_bytes -= bytes;
+  } else {
+    // same pre-check and message style as CudaMatrix::alloc (cudamatrix.cc:97-113)
+    size_t fr = 0, tot = 0;
+    GW_CUDA(cudaMemGetInfo(&fr, &tot));
+    if (bytes > fr && ctx->cached_bytes > 0) {  // give cached blocks back before failing
+      GW_CUDA(cudaStreamSynchronize(ctx->stream));
+      for (auto& kv : ctx->free_blocks) cudaFree(kv.second);
+      ctx->free_blocks.clear();
+      ctx->cached_bytes = 0;
+      GW_CUDA(cudaMemGetInfo(&fr, &tot));
+    }
+    if (bytes > fr)
+      throw std::runtime_error("There were requested : " + std::to_string((double)bytes / 1048576.0) +
+                               " MB but the device has " + std::to_string((double)fr / 1048576.0) + " MB free.");
+    GW_CUDA(cudaMalloc(out_dev, bytes));
+  }
+  ctx->live_blocks[*out_dev] = bytes;
   GW_API_END(ctx)
 }
 int gwbse_dev_free(gwbse_ctx* ctx, double* p) {
   GW_API_BEGIN(ctx)
-  GW_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (p) GW_CUDA(cudaFree(p));
+  if (p) {
+    auto it = ctx->live_blocks.find(p);
+    if (it == ctx->live_blocks.end()) throw std::runtime_error("gwbse_dev_free: unknown device pointer");
+    const size_t bytes = it->second;
+    ctx->live_blocks.erase(it);
+    // work queued on the context's stream may still use the block; blocks are only re-used by later work on
+    // the same stream, so no synchronisation is needed to cache it
+    if (ctx->cached_bytes + bytes <= ((size_t)8 << 30)) {
+      ctx->free_blocks.emplace(bytes, p);
+      ctx->cached_bytes += bytes;
+    } else {
+      GW_CUDA(cudaStreamSynchronize(ctx->stream));
+      GW_CUDA(cudaFree(p));
+    }
+  }
   GW_API_END(ctx)
 }
 int gwbse_h2d(gwbse_ctx* ctx, double* dst, const double* src, size_t n) {

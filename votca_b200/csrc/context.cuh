@@ -68,6 +68,11 @@ struct gwbse_ctx {
   int rank = 0, world = 1;
   void* nccl_comm = nullptr;
 
+  // caching allocator behind gwbse_dev_malloc/free: freed blocks are kept and handed out again for
+  // requests of the same size (Davidson / BSE temporaries repeat every iteration)
+  std::multimap<size_t, double*> free_blocks;
+  std::map<double*, size_t> live_blocks;
+  size_t cached_bytes = 0;
   // named grow-only device scratch buffers
   std::map<std::string, DevBuf> bufs;
 
