@@ -74,6 +74,10 @@ int gwbse_comm_init(gwbse_ctx* ctx, int rank, int world, const unsigned char* id
 int gwbse_comm_rank(const gwbse_ctx* ctx);
 int gwbse_comm_world(const gwbse_ctx* ctx);
 int gwbse_comm_allreduce_host(gwbse_ctx* ctx, double* buf, size_t n); /* sum, in place */
+/* the m-cyclic sharding plan (pure functions, usable without a GPU) */
+int gwbse_shard_owner(int m, int world);
+int gwbse_shard_local_index(int m, int world);
+int gwbse_shard_local_count(int total, int rank, int world);
 
 /* ---- raw device memory (CudaMatrix, cudamatrix.h:95-190) ---------------- */
 int gwbse_dev_malloc(gwbse_ctx* ctx, size_t bytes, double** out_dev);

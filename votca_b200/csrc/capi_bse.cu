@@ -19,21 +19,67 @@ namespace {
 
 inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
 
+// replicated copies of the occupied-occupied and virtual-occupied blocks when Mmn is sharded:
+//   vv[chi][v1][v2] = M[voff+v1][voff+v2, chi],  cv[chi][c1][v2] = M[coff+c1][voff+v2, chi]
+struct BlockView {
+  const double* ptr;
+  long long row, pole;  // strides of the slice index and of chi
+};
+
+void ensure_gathered(gwbse_ctx* ctx) {
+  auto& st = ctx->bse;
+  if (ctx->world == 1) return;
+  if (st.gathered_version == ctx->mmn_version && st.gathered_voff == st.voff && st.gathered_vt == st.vt &&
+      st.gathered_ct == st.ct)
+    return;
+  const int vtp = round_up(st.vt, 2);
+  double* gvv = ctx->buf("bse_gvv", (size_t)ctx->naux * st.vt * vtp);
+  double* gcv = ctx->buf("bse_gcv", (size_t)ctx->naux * st.ct * vtp);
+  gather_slices(ctx, st.voff, st.vt, st.voff, st.vt, 0, ctx->naux, gvv, (long long)st.vt * vtp, vtp);
+  gather_slices(ctx, st.coff, st.ct, st.voff, st.vt, 0, ctx->naux, gcv, (long long)st.ct * vtp, vtp);
+  st.gathered_version = ctx->mmn_version;
+  st.gathered_voff = st.voff;
+  st.gathered_vt = st.vt;
+  st.gathered_ct = st.ct;
+}
+
+BlockView vv_view(gwbse_ctx* ctx) {
+  auto& st = ctx->bse;
+  if (ctx->world == 1) return {ctx->X + (long long)st.voff * ctx->npad + st.voff, ctx->npad, ctx->ldx};
+  const int vtp = round_up(st.vt, 2);
+  return {ctx->buf("bse_gvv", (size_t)ctx->naux * st.vt * vtp), vtp, (long long)st.vt * vtp};
+}
+BlockView cv_view(gwbse_ctx* ctx) {
+  auto& st = ctx->bse;
+  if (ctx->world == 1) return {ctx->X + (long long)st.coff * ctx->npad + st.voff, ctx->npad, ctx->ldx};
+  const int vtp = round_up(st.vt, 2);
+  return {ctx->buf("bse_gcv", (size_t)ctx->naux * st.ct * vtp), vtp, (long long)st.ct * vtp};
+}
+
+// Y = H X.  With a sharded Mmn every rank computes the part its slices contribute (v-slices for Hx / Hd2,
+// c-slices for Hd, rank 0 the Hqp term) into disjoint or additive entries of Y, then Y is all-reduced.
 void bse_matmul_dev(gwbse_ctx* ctx, int cqp, int cx, int cd, int cd2, int k, const double* Xin, int ldin, double* Y,
                     int ldy) {
   auto& st = ctx->bse;
   GW_REQUIRE(st.ready, "BSE operator not configured (gwbse_bse_configure)");
   GW_REQUIRE(!(cd != 0 && cd2 != 0), "Hamiltonian cannot contain Hd and Hd2 at the same time");
-  GW_REQUIRE(ctx->world == 1, "gwbse_bse_matmul: single-GPU build");
   const int vt = st.vt, ct = st.ct, B = st.size, naux = ctx->naux, npad = ctx->npad;
-  const int voff = st.voff, coff = st.coff;
+  const int voff = st.voff, coff = st.coff, world = ctx->world;
   const long long ldx = ctx->ldx;
   const double* X = ctx->X;
   GW_REQUIRE(ldin >= B && ldy >= B, "Shape mismatch in BSE matmul");
   if (k <= 0) return;
+  ensure_gathered(ctx);
+  // occupied / virtual slices owned by this rank
+  const int nvloc = ctx->owned_count(voff, vt, ctx->rank);
+  const int v_rel0 = ctx->first_owned(voff, ctx->rank) - voff;
+  const int lvfirst = nvloc ? ctx->local_index(voff + v_rel0) : 0;
+  const int ncloc = ctx->owned_count(coff, ct, ctx->rank);
+  const int c_rel0 = ctx->first_owned(coff, ctx->rank) - coff;
+  const int lcfirst = ncloc ? ctx->local_index(coff + c_rel0) : 0;
   GW_CUDA(cudaMemset2DAsync(Y, sizeof(double) * ldy, 0, sizeof(double) * B, k, ctx->stream));
 
-  if (cqp != 0) {
+  if (cqp != 0 && ctx->rank == 0) {
     const int ldh = vt + ct;
     // Y[(v1,c1)] += cqp sum_c2 Hqp[vt+c2, vt+c1] X[(v1,c2)]
     GemmParams p;
@@ -80,112 +126,133 @@ void bse_matmul_dev(gwbse_ctx* ctx, int cqp, int cx, int cd, int cd2, int k, con
 
   if (cx != 0) {
     double* W = ctx->buf("bse_W", (size_t)naux * k);
-    // W[chi, kv] = sum_{v,c} M[v][c,chi] X[(v,c),kv]
-    GemmParams p;
-    p.M = naux;
-    p.N = k;
-    p.Ko = vt;
-    p.Ki = ct;
-    p.A.ptr = X + (long long)voff * npad + coff;
-    p.A.s_ri = ldx;
-    p.A.s_ki = 1;
-    p.A.s_ko = npad;
-    p.B.ptr = Xin;
-    p.B.s_ri = ldin;
-    p.B.s_ki = 1;
-    p.B.s_ko = ct;
-    p.C = W;
-    p.sC_mi = 1;
-    p.sC_ni = naux;
-    ctx->gemm(p);
-    // Y[(v,c), kv] += cx sum_chi M[v][c,chi] W[chi,kv]
-    GemmParams q;
-    q.M = B;
-    q.N = k;
-    q.Ki = naux;
-    q.A.ptr = X + (long long)voff * npad + coff;
-    q.A.Lr = ct;
-    q.A.s_ri = 1;
-    q.A.s_ro = npad;
-    q.A.s_ki = ldx;
-    q.B.ptr = W;
-    q.B.s_ri = naux;
-    q.B.s_ki = 1;
-    q.C = Y;
-    q.sC_mi = 1;
-    q.sC_ni = ldy;
-    q.alpha = cx;
-    q.beta = 1.0;
-    ctx->gemm(q);
+    if (nvloc > 0) {
+      // W[chi, kv] = sum_{v local, c} M[v][c,chi] X[(v,c),kv]
+      GemmParams p;
+      p.M = naux;
+      p.N = k;
+      p.Ko = nvloc;
+      p.Ki = ct;
+      p.A.ptr = X + (long long)lvfirst * npad + coff;
+      p.A.s_ri = ldx;
+      p.A.s_ki = 1;
+      p.A.s_ko = npad;
+      p.B.ptr = Xin + (long long)v_rel0 * ct;
+      p.B.s_ri = ldin;
+      p.B.s_ki = 1;
+      p.B.s_ko = (long long)world * ct;
+      p.C = W;
+      p.sC_mi = 1;
+      p.sC_ni = naux;
+      ctx->gemm(p);
+    } else {
+      GW_CUDA(cudaMemsetAsync(W, 0, sizeof(double) * (size_t)naux * k, ctx->stream));
+    }
+    allreduce_dev(ctx, W, (size_t)naux * k);
+    if (nvloc > 0) {
+      // Y[(v,c), kv] += cx sum_chi M[v][c,chi] W[chi,kv]   for the local v
+      GemmParams q;
+      q.M = nvloc * ct;
+      q.N = k;
+      q.Ki = naux;
+      q.A.ptr = X + (long long)lvfirst * npad + coff;
+      q.A.Lr = ct;
+      q.A.s_ri = 1;
+      q.A.s_ro = npad;
+      q.A.s_ki = ldx;
+      q.B.ptr = W;
+      q.B.s_ri = naux;
+      q.B.s_ki = 1;
+      q.C = Y + (long long)v_rel0 * ct;
+      q.Lm = ct;
+      q.sC_mi = 1;
+      q.sC_mo = (long long)world * ct;
+      q.sC_ni = ldy;
+      q.alpha = cx;
+      q.beta = 1.0;
+      ctx->gemm(q);
+    }
   }
 
   if (cd != 0 || cd2 != 0) {
     const int vtp = round_up(vt, 2);
     const long long ldU = (long long)vtp * naux;
-    const int nout = cd != 0 ? ct : vt;  // index that is chunked (c1 for Hd, v1 for Hd2)
-    int nc = (int)std::max<long long>(1, (long long)(ctx->bse_chunk_bytes / sizeof(double)) / (ldU * k));
-    nc = std::min(nc, nout);
-    while ((long long)naux * nc >= (1LL << 31) || (long long)nc * k >= (1LL << 31)) nc = std::max(1, nc / 2);
-    double* U = ctx->buf("bse_U", (size_t)ldU * nc * k);
-    for (int a = 0; a < nout; a += nc) {
-      const int n1 = std::min(nc, nout - a);
-      // U[(v2, chi), (l, kv)] = eps_inv[chi] sum_c2 X[c2,(v2,kv)] Mblk[l][c2, chi]
-      GemmParams p;
-      p.M = vt * k;
-      p.N = naux * n1;
-      p.Ki = ct;
-      p.A.ptr = Xin;
-      p.A.Lr = vt;
-      p.A.s_ri = ct;
-      p.A.s_ro = ldin;
-      p.A.s_ki = 1;
-      p.B.ptr = X + (long long)((cd != 0 ? coff : voff) + a) * npad + coff;
-      p.B.Lr = naux;
-      p.B.s_ri = ldx;
-      p.B.s_ro = npad;
-      p.B.s_ki = 1;
-      p.C = U;
-      p.Lm = vt;
-      p.sC_mi = 1;
-      p.sC_mo = ldU * n1;
-      p.Ln = naux;
-      p.sC_ni = vtp;
-      p.sC_no = ldU;
-      p.nscale = st.eps_inv;
-      p.nscale_mod = naux;
-      ctx->gemm(p);
-      GemmParams q;
-      q.Ko = naux;
-      q.Ki = vt;
-      q.N = n1 * k;
-      q.A.s_ri = npad;
-      q.A.s_ki = 1;
-      q.A.s_ko = ldx;
-      q.B.ptr = U;
-      q.B.s_ri = ldU;
-      q.B.s_ki = 1;
-      q.B.s_ko = vtp;
-      q.beta = 1.0;
-      q.Ln = n1;
-      q.sC_no = ldy;
-      if (cd != 0) {
-        // Y[(v1, a+l), kv] -= cd sum_{chi,v2} M[v1][v2,chi] U[(v2,chi),(l,kv)]
-        q.M = vt;
-        q.A.ptr = X + (long long)voff * npad + voff;
-        q.C = Y + a;
-        q.sC_mi = ct;
-        q.sC_ni = 1;
-        q.alpha = -cd;
-      } else {
-        // Y[(a+l, c1), kv] -= cd2 sum_{chi,v2} M[c1][v2,chi] U[(v2,chi),(l,kv)]
-        q.M = ct;
-        q.A.ptr = X + (long long)coff * npad + voff;
-        q.C = Y + (long long)a * ct;
-        q.sC_mi = 1;
-        q.sC_ni = ct;
-        q.alpha = -cd2;
+    const int nout = cd != 0 ? ncloc : nvloc;  // chunked index: local c1 for Hd, local v1 for Hd2
+    if (nout > 0) {
+      int nc = (int)std::max<long long>(1, (long long)(ctx->bse_chunk_bytes / sizeof(double)) / (ldU * k));
+      nc = std::min(nc, nout);
+      while ((long long)naux * nc >= (1LL << 31) || (long long)nc * k >= (1LL << 31)) nc = std::max(1, nc / 2);
+      double* U = ctx->buf("bse_U", (size_t)ldU * nc * k);
+      const BlockView vv = vv_view(ctx), cv = cv_view(ctx);
+      for (int a = 0; a < nout; a += nc) {
+        const int n1 = std::min(nc, nout - a);
+        // U[(v2, chi), (l, kv)] = eps_inv[chi] sum_c2 X[c2,(v2,kv)] Mblk[l][c2, chi]   (l: local slices of the chunk)
+        GemmParams p;
+        p.M = vt * k;
+        p.N = naux * n1;
+        p.Ki = ct;
+        p.A.ptr = Xin;
+        p.A.Lr = vt;
+        p.A.s_ri = ct;
+        p.A.s_ro = ldin;
+        p.A.s_ki = 1;
+        p.B.ptr = X + (long long)((cd != 0 ? lcfirst : lvfirst) + a) * npad + coff;
+        p.B.Lr = naux;
+        p.B.s_ri = ldx;
+        p.B.s_ro = npad;
+        p.B.s_ki = 1;
+        p.C = U;
+        p.Lm = vt;
+        p.sC_mi = 1;
+        p.sC_mo = ldU * n1;
+        p.Ln = naux;
+        p.sC_ni = vtp;
+        p.sC_no = ldU;
+        p.nscale = st.eps_inv;
+        p.nscale_mod = naux;
+        ctx->gemm(p);
+        GemmParams q;
+        q.Ko = naux;
+        q.Ki = vt;
+        q.N = n1 * k;
+        q.A.s_ki = 1;
+        q.B.ptr = U;
+        q.B.s_ri = ldU;
+        q.B.s_ki = 1;
+        q.B.s_ko = vtp;
+        q.beta = 1.0;
+        q.Ln = n1;
+        q.sC_no = ldy;
+        if (cd != 0) {
+          // Y[(v1, c1), kv] -= cd sum_{chi,v2} M[v1][v2,chi] U[(v2,chi),(l,kv)],  c1 = c_rel0 + (a+l) world
+          q.M = vt;
+          q.A.ptr = vv.ptr;
+          q.A.s_ri = vv.row;
+          q.A.s_ko = vv.pole;
+          q.C = Y + c_rel0 + (long long)a * world;
+          q.sC_mi = ct;
+          q.sC_ni = world;
+          q.alpha = -cd;
+        } else {
+          // Y[(v1, c1), kv] -= cd2 sum_{chi,v2} M[c1][v2,chi] U[(v2,chi),(l,kv)],  v1 = v_rel0 + (a+l) world
+          q.M = ct;
+          q.A.ptr = cv.ptr;
+          q.A.s_ri = cv.row;
+          q.A.s_ko = cv.pole;
+          q.C = Y + ((long long)v_rel0 + (long long)a * world) * ct;
+          q.sC_mi = 1;
+          q.sC_ni = (long long)world * ct;
+          q.alpha = -cd2;
+        }
+        ctx->gemm(q);
       }
-      ctx->gemm(q);
+    }
+  }
+  if (world > 1) {
+    if (ldy == B) {
+      allreduce_dev(ctx, Y, (size_t)B * k);
+    } else {
+      for (int j = 0; j < k; ++j) allreduce_dev(ctx, Y + (size_t)j * ldy, (size_t)B);
     }
   }
 }
@@ -258,11 +325,28 @@ int gwbse_bse_diagonal(gwbse_ctx* ctx, int cqp, int cx, int cd, int cd2, double*
   auto& st = ctx->bse;
   GW_REQUIRE(st.ready, "BSE operator not configured (gwbse_bse_configure)");
   GW_REQUIRE(!(cd != 0 && cd2 != 0), "Hamiltonian cannot contain Hd and Hd2 at the same time");
-  GW_REQUIRE(ctx->world == 1, "gwbse_bse_diagonal: single-GPU build");
+  ensure_gathered(ctx);
+  const int vt = st.vt, ct = st.ct, naux = ctx->naux;
   double* d = ctx->buf("bse_diag", st.size);
-  launch_bse_diag(ctx->X, ctx->ldx, ctx->npad, ctx->naux, st.vt, st.ct, st.voff, st.coff, st.eps_inv, st.hqp,
-                  st.vt + st.ct, cqp, cx, cd, cd2, d, ctx->stream);
-  ctx->launches++;
+  double* Dcc = ctx->buf("bse_dcc", (size_t)ct * naux);
+  double* Dvv = ctx->buf("bse_dvv", (size_t)vt * naux);
+  GW_CUDA(cudaMemsetAsync(d, 0, sizeof(double) * st.size, ctx->stream));
+  GW_CUDA(cudaMemsetAsync(Dcc, 0, sizeof(double) * (size_t)ct * naux, ctx->stream));
+  GW_CUDA(cudaMemsetAsync(Dvv, 0, sizeof(double) * (size_t)vt * naux, ctx->stream));
+  launch_slice_diag(ctx->X, ctx->ldx, ctx->npad, naux, st.coff, ct, ctx->rank, ctx->world, Dcc, ctx->stream);
+  launch_slice_diag(ctx->X, ctx->ldx, ctx->npad, naux, st.voff, vt, ctx->rank, ctx->world, Dvv, ctx->stream);
+  if (ctx->world > 1) {
+    allreduce_dev(ctx, Dcc, (size_t)ct * naux);
+    allreduce_dev(ctx, Dvv, (size_t)vt * naux);
+  }
+  const int nvloc = ctx->owned_count(st.voff, vt, ctx->rank);
+  const int v_rel0 = ctx->first_owned(st.voff, ctx->rank) - st.voff;
+  const int lvfirst = nvloc ? ctx->local_index(st.voff + v_rel0) : 0;
+  const BlockView cv = cv_view(ctx);
+  launch_bse_diag(ctx->X, ctx->ldx, ctx->npad, naux, vt, ct, st.voff, st.coff, v_rel0, ctx->world, lvfirst, nvloc,
+                  cv.ptr, cv.row, cv.pole, Dcc, Dvv, st.eps_inv, st.hqp, vt + ct, cqp, cx, cd, cd2, d, ctx->stream);
+  ctx->launches += 3;
+  if (ctx->world > 1) allreduce_dev(ctx, d, (size_t)st.size);
   GW_CUDA(cudaMemcpyAsync(diag, d, sizeof(double) * st.size, cudaMemcpyDeviceToHost, ctx->stream));
   GW_CUDA(cudaStreamSynchronize(ctx->stream));
   GW_API_END(ctx)

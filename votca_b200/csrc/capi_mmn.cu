@@ -62,6 +62,7 @@ void fill_block_dev(gwbse_ctx* ctx, int aux_offset, int aux_count, const double*
     q.sC_z1 = ctx->ldx;
     ctx->gemm(q);
   }
+  ctx->mmn_version++;
 }
 
 void mul_right_dev(gwbse_ctx* ctx, const double* R_dev, int ldr) {
@@ -94,6 +95,7 @@ void mul_right_dev(gwbse_ctx* ctx, const double* R_dev, int ldr) {
   p.sC_ni = ctx->ldx;
   ctx->gemm(p);
   std::swap(ctx->X, ctx->X2);
+  ctx->mmn_version++;
   // evaluators hold pointers into X
   ctx->sig_ppm.ready = false;
 }
@@ -233,6 +235,7 @@ int gwbse_mmn_set_slice(gwbse_ctx* ctx, int m, const double* in, int ld) {
   GW_CUDA(cudaMemcpy2DAsync(dst, sizeof(double) * ctx->ldx, in, sizeof(double) * ld, sizeof(double) * ctx->ntotal,
                             ctx->naux, cudaMemcpyHostToDevice, ctx->stream));
   GW_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->mmn_version++;
   GW_API_END(ctx)
 }
 
@@ -253,6 +256,7 @@ int gwbse_mmn_restore(gwbse_ctx* ctx) {
   GW_REQUIRE(ctx->Xsnap != nullptr, "no Mmn snapshot to restore");
   const size_t bytes = sizeof(double) * (size_t)std::max<long long>(ctx->ldx, 1) * ctx->naux;
   GW_CUDA(cudaMemcpyAsync(ctx->X, ctx->Xsnap, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  ctx->mmn_version++;
   ctx->sig_ppm.ready = false;
   GW_API_END(ctx)
 }
@@ -405,7 +409,6 @@ int gwbse_sigma_x(gwbse_ctx* ctx, int homo, int rpamin, int qpmin, int qpmax, do
   GW_API_BEGIN(ctx)
   GW_PROF(ctx, "sigma_x");
   require_mmn(ctx);
-  GW_REQUIRE(ctx->world == 1, "gwbse_sigma_x: multi-GPU path uses gwbse_sigma_x after gathering (not built yet)");
   GW_REQUIRE(rpamin == ctx->mmin && rpamin == ctx->nmin, "RPA range must match Mmn");
   const int q = qpmax - qpmin + 1;
   const int occ = homo - rpamin + 1;
@@ -418,10 +421,21 @@ int gwbse_sigma_x(gwbse_ctx* ctx, int homo, int rpamin, int qpmin, int qpmax, do
   p.N = q;
   p.Ko = ctx->naux;
   p.Ki = occ;
-  p.A.ptr = ctx->X + (long long)qpoff * ctx->npad;
-  p.A.s_ri = ctx->npad;
+  if (ctx->world == 1) {
+    p.A.ptr = ctx->X + (long long)qpoff * ctx->npad;
+    p.A.s_ri = ctx->npad;
+    p.A.s_ko = ctx->ldx;
+  } else {
+    // occupied-row panels of every qp slice, replicated on all ranks (q * n_occ * naux doubles)
+    const int rpad = (occ + 1) & ~1;
+    const long long ldo = (long long)q * rpad;
+    double* panel = ctx->buf("sigma_x_panel", (size_t)ldo * ctx->naux);
+    gather_slices(ctx, qpoff, q, 0, occ, 0, ctx->naux, panel, ldo, rpad);
+    p.A.ptr = panel;
+    p.A.s_ri = rpad;
+    p.A.s_ko = ldo;
+  }
   p.A.s_ki = 1;
-  p.A.s_ko = ctx->ldx;
   p.B = p.A;
   p.C = sx;
   p.sC_mi = 1;

@@ -23,15 +23,25 @@ void sigma_eval_groups(gwbse_ctx* ctx, gwbse_ctx::SigmaState& st, int ngroups, c
   if (ngroups <= 0) return;
   const int nfreq = gptr[ngroups];
   if (nfreq <= 0) return;
+  // level -> local slice index of the matrix the evaluator reads (sharded Mmn for ppm, residues for exact)
+  const bool sharded = (st.mat == ctx->X);
+  std::vector<int> slices(ngroups);
   for (int i = 0; i < ngroups; ++i) {
     GW_REQUIRE(levels[i] >= 0 && levels[i] < st.q, "gw_level out of range");
     GW_REQUIRE(gptr[i + 1] >= gptr[i], "group offsets must be non-decreasing");
+    const int m = st.qpoff + levels[i];
+    if (sharded) {
+      GW_REQUIRE(ctx->owns(m), "Sigma_c requested for a level this rank does not own");
+      slices[i] = ctx->local_index(m);
+    } else {
+      slices[i] = m;
+    }
   }
   GW_REQUIRE(ngroups <= 65535, "too many sigma request groups in one batch");
   int* lev_d = reinterpret_cast<int*>(ctx->buf("sig_levels", (size_t)ngroups / 2 + 8));
   int* gp_d = reinterpret_cast<int*>(ctx->buf("sig_gptr", (size_t)(ngroups + 1) / 2 + 8));
   double* frq_d = ctx->buf("sig_freqs", nfreq);
-  GW_CUDA(cudaMemcpyAsync(lev_d, levels, sizeof(int) * ngroups, cudaMemcpyHostToDevice, ctx->stream));
+  GW_CUDA(cudaMemcpyAsync(lev_d, slices.data(), sizeof(int) * ngroups, cudaMemcpyHostToDevice, ctx->stream));
   GW_CUDA(cudaMemcpyAsync(gp_d, gptr, sizeof(int) * (ngroups + 1), cudaMemcpyHostToDevice, ctx->stream));
   GW_CUDA(cudaMemcpyAsync(frq_d, freqs, sizeof(double) * nfreq, cudaMemcpyHostToDevice, ctx->stream));
   const int nchunks = sigma_multi_chunks(st.npoles);
@@ -68,20 +78,49 @@ void sigma_offdiag(gwbse_ctx* ctx, gwbse_ctx::SigmaState& st, double pref, int q
                    int ld) {
   GW_REQUIRE(st.ready, "sigma evaluator not prepared");
   GW_REQUIRE(q == st.q && ld >= q, "q does not match the prepared evaluator");
+  const bool sharded = (st.mat == ctx->X) && ctx->world > 1;
   double* frq_d = ctx->buf("sig_freqs", q);
   GW_CUDA(cudaMemcpyAsync(frq_d, freqs, sizeof(double) * q, cudaMemcpyHostToDevice, ctx->stream));
   const int npad = (int)st.lstride;
-  const long long ldo = (long long)q * npad;
+  // levels whose rows this rank computes: all of them on one GPU, the owned ones when Mmn is sharded
+  std::vector<int> slice_idx, freq_idx;
+  int ifirst = 0, istride = 1;
+  if (sharded) {
+    ifirst = ctx->first_owned(st.qpoff, ctx->rank) - st.qpoff;
+    istride = ctx->world;
+    for (int i = ifirst; i < q; i += istride) {
+      slice_idx.push_back(ctx->local_index(st.qpoff + i));
+      freq_idx.push_back(i);
+    }
+  } else {
+    for (int i = 0; i < q; ++i) {
+      slice_idx.push_back((st.mat == ctx->X ? ctx->local_index(st.qpoff + i) : st.qpoff + i));
+      freq_idx.push_back(i);
+    }
+  }
+  const int qloc = (int)slice_idx.size();
+  int* sl_d = reinterpret_cast<int*>(ctx->buf("sig_off_slices", (size_t)q / 2 + 8));
+  int* fi_d = reinterpret_cast<int*>(ctx->buf("sig_off_fidx", (size_t)q / 2 + 8));
+  if (qloc) {
+    GW_CUDA(cudaMemcpyAsync(sl_d, slice_idx.data(), sizeof(int) * qloc, cudaMemcpyHostToDevice, ctx->stream));
+    GW_CUDA(cudaMemcpyAsync(fi_d, freq_idx.data(), sizeof(int) * qloc, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  const long long ldo = (long long)std::max(qloc, 1) * npad;
+  const long long ldg = (long long)q * npad;
   const size_t budget = (size_t)1 << 25;  // doubles (256 MiB)
-  const int chunk = (int)std::max<size_t>(1, std::min<size_t>(std::min(st.npoles, 65535), budget / (size_t)ldo));
+  const int chunk = (int)std::max<size_t>(1, std::min<size_t>(std::min(st.npoles, 65535), budget / (size_t)ldg));
   double* A = ctx->buf("sig_offdiag_A", (size_t)ldo * chunk);
+  double* G = sharded ? ctx->buf("sig_offdiag_G", (size_t)ldg * chunk) : nullptr;
   double* S = ctx->buf("sig_offdiag_S", (size_t)q * q * 2);
-  for (int p0 = 0, it = 0; p0 < st.npoles; p0 += chunk, ++it) {
+  GW_CUDA(cudaMemsetAsync(S, 0, sizeof(double) * (size_t)q * q, ctx->stream));
+  for (int p0 = 0; p0 < st.npoles; p0 += chunk) {
     const int np = std::min(chunk, st.npoles - p0);
-    launch_sigma_offdiag_weight(st, ctx->ntotal, npad, q, p0, np, frq_d, pref, A, ldo, ctx->stream);
+    if (sharded) gather_slices(ctx, st.qpoff, q, 0, ctx->ntotal, p0, np, G, ldg, npad);
+    if (qloc == 0) continue;
+    launch_sigma_offdiag_weight(st, ctx->ntotal, npad, qloc, sl_d, fi_d, p0, np, frq_d, pref, A, ldo, ctx->stream);
     ctx->launches++;
     GemmParams p;
-    p.M = q;
+    p.M = qloc;
     p.N = q;
     p.Ko = np;
     p.Ki = ctx->ntotal;
@@ -89,16 +128,23 @@ void sigma_offdiag(gwbse_ctx* ctx, gwbse_ctx::SigmaState& st, double pref, int q
     p.A.s_ri = npad;
     p.A.s_ki = 1;
     p.A.s_ko = ldo;
-    p.B.ptr = st.mat + (long long)st.qpoff * st.lstride + (long long)p0 * st.ld;
-    p.B.s_ri = st.lstride;
+    if (sharded) {
+      p.B.ptr = G;
+      p.B.s_ri = npad;
+      p.B.s_ko = ldg;
+    } else {
+      p.B.ptr = st.mat + (long long)slice_idx[0] * st.lstride + (long long)p0 * st.ld;
+      p.B.s_ri = st.lstride;
+      p.B.s_ko = st.ld;
+    }
     p.B.s_ki = 1;
-    p.B.s_ko = st.ld;
-    p.C = S;
-    p.sC_mi = 1;
+    p.C = S + ifirst;  // rows land at their global level index
+    p.sC_mi = istride;
     p.sC_ni = q;
-    p.beta = it == 0 ? 0.0 : 1.0;
+    p.beta = 1.0;
     ctx->gemm(p);
   }
+  if (sharded) allreduce_dev(ctx, S, (size_t)q * q);
   launch_offdiag_finish(S, q, S + (size_t)q * q, ctx->stream);
   ctx->launches++;
   GW_CUDA(cudaMemcpy2DAsync(out, sizeof(double) * ld, S + (size_t)q * q, sizeof(double) * q, sizeof(double) * q, q,
@@ -114,7 +160,6 @@ int gwbse_sigma_ppm_set(gwbse_ctx* ctx, const double* ppm_weight, const double* 
                         int homo, int rpamin, int qpmin, double eta) {
   GW_API_BEGIN(ctx)
   GW_REQUIRE(ctx->X != nullptr, "Mmn not allocated");
-  GW_REQUIRE(ctx->world == 1, "sigma evaluators are single-GPU in this build");
   auto& st = ctx->sig_ppm;
   const int naux = ctx->naux;
   std::vector<double> fac(naux);

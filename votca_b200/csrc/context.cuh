@@ -114,6 +114,8 @@ struct gwbse_ctx {
     int voff = 0, coff = 0;  // vmin - rpamin, cmin - rpamin (rows / slices of Mmn)
     double* eps_inv = nullptr;  // naux (device)
     double* hqp = nullptr;      // (vt+ct)^2 device, ld = vt+ct
+    long long gathered_version = -1;  // multi-GPU: version of X the replicated vv / cv blocks were built from
+    int gathered_voff = -1, gathered_vt = -1, gathered_ct = -1;
     std::vector<double> hqp_host;
     std::vector<double> eps_inv_host;
   } bse;
@@ -132,6 +134,13 @@ struct gwbse_ctx {
   }
   // algo_flops < 0: 2*M*N*K per batch (half for lower_only)
   void gemm(const gwbse::GemmParams& p, int cfg = -1, int splitk = 0, double algo_flops = -1.0);
+  long long mmn_version = 0;  // bumped whenever the content of X changes (gathered blocks are cached per version)
+  // first global slice >= s0 owned by rank r, and how many slices of [s0, s0+ns) rank r owns
+  int first_owned(int s0, int r) const { return s0 + ((r - s0 % world) % world + world) % world; }
+  int owned_count(int s0, int ns, int r) const {
+    const int f = first_owned(s0, r);
+    return f >= s0 + ns ? 0 : (s0 + ns - f + world - 1) / world;
+  }
   bool owns(int m) const { return (m % world) == rank; }
   int local_index(int m) const { return m / world; }
   // number of local levels with global storage index in [0, upto)
@@ -179,6 +188,10 @@ struct ProfScope {
   }
 
 namespace gwbse {
+// slice gather (capi_shard.cu): rows [row0,row0+nrows) of global slices [s0,s0+ns), poles [p0,p0+np), from all
+// ranks into out[(p-p0)*ldo + (s-s0)*rpad + (row-row0)] in natural slice order (ldo >= ns*rpad)
+void gather_slices(gwbse_ctx* ctx, int s0, int ns, int row0, int nrows, int p0, int np, double* out, long long ldo,
+                   int rpad);
 // NCCL plumbing (comm.cu)
 void allreduce_dev(gwbse_ctx* ctx, double* buf_dev, size_t n);
 void allgather_dev(gwbse_ctx* ctx, const double* send_dev, double* recv_dev, size_t n_per_rank);
@@ -201,12 +214,16 @@ int sigma_multi_chunks(int npoles);
 void launch_sigma_multi(const gwbse_ctx::SigmaState& st, int ntotal, int ngroups, int nfreq, const int* levels_dev,
                         const int* gptr_dev, const double* freqs_dev, double* partial_dev, double* out_dev,
                         bool want_deriv, cudaStream_t s);
-void launch_sigma_offdiag_weight(const gwbse_ctx::SigmaState& st, int ntotal, int npad, int q, int p0, int np,
+void launch_sigma_offdiag_weight(const gwbse_ctx::SigmaState& st, int ntotal, int npad, int nlevels,
+                                 const int* slice_idx_dev, const int* freq_idx_dev, int p0, int np,
                                  const double* freqs_dev, double pref, double* out, long long ldo, cudaStream_t s);
 void launch_offdiag_finish(const double* S, int q, double* out, cudaStream_t s);
+void launch_slice_diag(const double* X, long long ldx, int npad, int naux, int s0, int ns, int rank, int world,
+                       double* D, cudaStream_t s);
 void launch_bse_diag(const double* X, long long ldx, int npad, int naux, int vt, int ct, int voff, int coff,
-                     const double* eps_inv, const double* hqp, int ldh, int cqp, int cx, int cd, int cd2,
-                     double* out, cudaStream_t s);
+                     int v_rel0, int vstride, int lfirst, int nvloc, const double* cv, long long cv_row,
+                     long long cv_pole, const double* Dcc, const double* Dvv, const double* eps_inv,
+                     const double* hqp, int ldh, int cqp, int cx, int cd, int cd2, double* out, cudaStream_t s);
 void launch_dpr(int rows, int ncols, const double* diag, const double* lambda_dev, const double* R, long long ldr,
                 double* W, long long ldw, cudaStream_t s);
 void launch_olsen_finish(int rows, int ncols, const double* diag, const double* lambda_dev, const double* Q,

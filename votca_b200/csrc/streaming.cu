@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(256) sigma_multi_kernel(const double* __restri
     om[p] = pole[pp];
     fc[p] = (p0 + p < npoles) ? fac[pp] : 0.0;
     any = any || fc[p] != 0.0;
-    cols[p] = mat + (long long)pp * ld + (long long)(qpoff + level) * lstride;
+    cols[p] = mat + (long long)pp * ld + (long long)(qpoff + level) * lstride;  // level = local slice index
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const double two_eta2 = 2.0 * eta2;
@@ -240,24 +240,26 @@ __global__ void sigma_multi_reduce_kernel(const double* partial, int nfreq, int 
   out[nfreq + r] = pref * ds;
 }
 
-// A_i[n, p] = pref * fac_p * M_i[n, p] * t/(t^2+eta^2), t = w_i - e_n +- pole_p  (off-diagonal Sigma_c as a GEMM)
+// A_il[n, p] = pref * fac_p * M[n, p] * t/(t^2+eta^2), t = w - e_n +- pole_p  (off-diagonal Sigma_c as a GEMM);
+// il runs over the levels this rank owns: slice_idx[il] = local slice, freq_idx[il] = index into freqs
 __global__ void sigma_offdiag_weight_kernel(const double* __restrict__ mat, long long ld, long long lstride,
-                                            int qpoff, int ntotal, int npad, int boundary, double eta2, double pref,
+                                            const int* __restrict__ slice_idx, const int* __restrict__ freq_idx,
+                                            int ntotal, int npad, int boundary, double eta2, double pref,
                                             const double* __restrict__ fac, const double* __restrict__ pole,
                                             const double* __restrict__ energies, const double* __restrict__ freqs,
                                             int p0, double* out, long long ldo) {
-  const int level = blockIdx.y;
+  const int il = blockIdx.y;
   const int p = p0 + blockIdx.z;
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= npad) return;
   double v = 0.0;
   if (n < ntotal) {
     const double om = pole[p];
-    const double t = freqs[level] - energies[n] + (n < boundary ? om : -om);
-    const double m = mat[(long long)p * ld + (long long)(qpoff + level) * lstride + n];
+    const double t = freqs[freq_idx[il]] - energies[n] + (n < boundary ? om : -om);
+    const double m = mat[(long long)p * ld + (long long)slice_idx[il] * lstride + n];
     v = pref * fac[p] * m * t / (t * t + eta2);
   }
-  out[(long long)blockIdx.z * ldo + (long long)level * npad + n] = v;
+  out[(long long)blockIdx.z * ldo + (long long)il * npad + n] = v;
 }
 
 __global__ void offdiag_finish_kernel(const double* S, int q, double* out) {
@@ -267,17 +269,30 @@ __global__ void offdiag_finish_kernel(const double* S, int q, double* out) {
   out[i + (long long)j * q] = (i == j) ? 0.0 : S[i + (long long)j * q] + S[j + (long long)i * q];
 }
 
-// BSE_OPERATOR::diagonal, bse_operator.cc:134-175.  One thread per (v, c), c fastest.
+// Diagonal elements M[s][s, chi] of the slices [s0, s0+ns) this rank owns -> D[(s - s0) + ns * chi] (others untouched)
+__global__ void slice_diag_kernel(const double* __restrict__ X, long long ldx, int npad, int naux, int s0, int ns,
+                                  int rank, int world, double* D) {
+  const int chi = blockIdx.x * blockDim.x + threadIdx.x;
+  const int sl = blockIdx.y;
+  const int s = s0 + sl;
+  if (chi >= naux || s % world != rank) return;
+  D[sl + (long long)ns * chi] = X[(long long)chi * ldx + (long long)(s / world) * npad + s];
+}
+
+// BSE_OPERATOR::diagonal, bse_operator.cc:134-175 for the occupied levels v this rank owns; thread = (c, local v).
+// cv(c, v, chi) = M[coff+c][voff+v, chi] comes from X (single GPU) or from the replicated block.
 __global__ void bse_diag_kernel(const double* __restrict__ X, long long ldx, int npad, int naux, int vt, int ct,
-                                int voff, int coff, const double* __restrict__ eps_inv,
-                                const double* __restrict__ hqp, int ldh, int cqp, int cx, int cd, int cd2,
-                                double* out) {
+                                int voff, int coff, int v_rel0, int vstride, int lfirst,
+                                const double* __restrict__ cv, long long cv_row, long long cv_pole,
+                                const double* __restrict__ Dcc, const double* __restrict__ Dvv,
+                                const double* __restrict__ eps_inv, const double* __restrict__ hqp, int ldh, int cqp,
+                                int cx, int cd, int cd2, double* out) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  const int v = blockIdx.y;
-  if (c >= ct) return;
+  const int l = blockIdx.y;
+  const int v = v_rel0 + l * vstride;
+  if (c >= ct || v >= vt) return;
   double entry = 0.0;
-  const double* Mv = X + (long long)(voff + v) * npad;  // slice v
-  const double* Mc = X + (long long)(coff + c) * npad;  // slice c
+  const double* Mv = X + (long long)(lfirst + l) * npad;  // local slice of v
   if (cx != 0) {
     double s = 0.0;
     for (int p = 0; p < naux; ++p) {
@@ -289,14 +304,13 @@ __global__ void bse_diag_kernel(const double* __restrict__ X, long long ldx, int
   if (cqp != 0) entry += cqp * (hqp[(c + vt) + (long long)(c + vt) * ldh] - hqp[v + (long long)v * ldh]);
   if (cd != 0) {
     double s = 0.0;
-    for (int p = 0; p < naux; ++p)
-      s += Mc[(long long)p * ldx + coff + c] * eps_inv[p] * Mv[(long long)p * ldx + voff + v];
+    for (int p = 0; p < naux; ++p) s += Dcc[c + (long long)ct * p] * eps_inv[p] * Dvv[v + (long long)vt * p];
     entry -= cd * s;
   }
   if (cd2 != 0) {
     double s = 0.0;
     for (int p = 0; p < naux; ++p)
-      s += Mc[(long long)p * ldx + voff + v] * eps_inv[p] * Mv[(long long)p * ldx + coff + c];
+      s += cv[(long long)p * cv_pole + (long long)c * cv_row + v] * eps_inv[p] * Mv[(long long)p * ldx + coff + c];
     entry -= cd2 * s;
   }
   out[(long long)ct * v + c] = entry;
@@ -401,23 +415,33 @@ void launch_sigma_multi(const gwbse_ctx::SigmaState& st, int ntotal, int ngroups
                                                                 want_deriv ? 1 : 0, out_dev);
   GW_CUDA(cudaGetLastError());
 }
-void launch_sigma_offdiag_weight(const gwbse_ctx::SigmaState& st, int ntotal, int npad, int q, int p0, int np,
+void launch_sigma_offdiag_weight(const gwbse_ctx::SigmaState& st, int ntotal, int npad, int nlevels,
+                                 const int* slice_idx_dev, const int* freq_idx_dev, int p0, int np,
                                  const double* freqs_dev, double pref, double* out, long long ldo, cudaStream_t s) {
-  if (np <= 0 || q <= 0) return;
-  sigma_offdiag_weight_kernel<<<dim3((npad + 127) / 128, q, np), 128, 0, s>>>(
-      st.mat, st.ld, st.lstride, st.qpoff, ntotal, npad, st.nocc_boundary, st.eta * st.eta, pref, st.fac, st.pole,
-      st.energies, freqs_dev, p0, out, ldo);
+  if (np <= 0 || nlevels <= 0) return;
+  sigma_offdiag_weight_kernel<<<dim3((npad + 127) / 128, nlevels, np), 128, 0, s>>>(
+      st.mat, st.ld, st.lstride, slice_idx_dev, freq_idx_dev, ntotal, npad, st.nocc_boundary, st.eta * st.eta, pref,
+      st.fac, st.pole, st.energies, freqs_dev, p0, out, ldo);
   GW_CUDA(cudaGetLastError());
 }
 void launch_offdiag_finish(const double* S, int q, double* out, cudaStream_t s) {
   offdiag_finish_kernel<<<grid2(q, q, 128), 128, 0, s>>>(S, q, out);
   GW_CUDA(cudaGetLastError());
 }
+void launch_slice_diag(const double* X, long long ldx, int npad, int naux, int s0, int ns, int rank, int world,
+                       double* D, cudaStream_t s) {
+  if (ns <= 0) return;
+  slice_diag_kernel<<<dim3((naux + 127) / 128, ns), 128, 0, s>>>(X, ldx, npad, naux, s0, ns, rank, world, D);
+  GW_CUDA(cudaGetLastError());
+}
 void launch_bse_diag(const double* X, long long ldx, int npad, int naux, int vt, int ct, int voff, int coff,
-                     const double* eps_inv, const double* hqp, int ldh, int cqp, int cx, int cd, int cd2,
-                     double* out, cudaStream_t s) {
-  bse_diag_kernel<<<dim3((ct + 127) / 128, vt), 128, 0, s>>>(X, ldx, npad, naux, vt, ct, voff, coff, eps_inv, hqp,
-                                                              ldh, cqp, cx, cd, cd2, out);
+                     int v_rel0, int vstride, int lfirst, int nvloc, const double* cv, long long cv_row,
+                     long long cv_pole, const double* Dcc, const double* Dvv, const double* eps_inv,
+                     const double* hqp, int ldh, int cqp, int cx, int cd, int cd2, double* out, cudaStream_t s) {
+  if (nvloc <= 0) return;
+  bse_diag_kernel<<<dim3((ct + 127) / 128, nvloc), 128, 0, s>>>(X, ldx, npad, naux, vt, ct, voff, coff, v_rel0,
+                                                                  vstride, lfirst, cv, cv_row, cv_pole, Dcc, Dvv,
+                                                                  eps_inv, hqp, ldh, cqp, cx, cd, cd2, out);
   GW_CUDA(cudaGetLastError());
 }
 void launch_dpr(int rows, int ncols, const double* diag, const double* lambda_dev, const double* R, long long ldr,

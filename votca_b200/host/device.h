@@ -35,6 +35,11 @@ class Device {
   Device(const Device&) = delete;
   Device& operator=(const Device&) = delete;
   gwbse_ctx* ctx() const { return ctx_; }
+  // multi-GPU: one process per GPU, Mmn sharded m-cyclically (gwbse_comm_init)
+  int rank() const { return gwbse_comm_rank(ctx_); }
+  int world() const { return gwbse_comm_world(ctx_); }
+  bool owns_slice(Index m) const { return gwbse_shard_owner((int)m, world()) == rank(); }
+  void allreduce(double* buf, size_t n) const { check(gwbse_comm_allreduce_host(ctx_, buf, n)); }
   void check(int rc) const {
     if (rc != 0) throw std::runtime_error(gwbse_last_error(ctx_));
   }

@@ -462,8 +462,13 @@ class GW {
     SigmaBatcher batcher(*sigma_);
     std::vector<std::thread> workers;
     workers.reserve(qptotal_);
-    for (Index gw_level = 0; gw_level < qptotal_; ++gw_level) batcher.WorkerStarted();
-    for (Index gw_level = 0; gw_level < qptotal_; ++gw_level) {
+    // multi-GPU: every rank searches the roots of the levels whose Mmn slice it owns
+    const Device& dev = Mmn_.device();
+    std::vector<Index> my_levels;
+    for (Index gw_level = 0; gw_level < qptotal_; ++gw_level)
+      if (sigma_->OwnsLevel(gw_level)) my_levels.push_back(gw_level);
+    for (size_t w = 0; w < my_levels.size(); ++w) batcher.WorkerStarted();
+    for (Index gw_level : my_levels) {
       workers.emplace_back([&, gw_level] {
         try {
           double initial_f = frequencies[gw_level];
@@ -494,6 +499,18 @@ class GW {
     for (auto& t : workers) t.join();
     for (const auto& e : errors)
       if (!e.empty()) throw std::runtime_error(e);
+    if (dev.world() > 1) {
+      std::vector<double> pack(2 * qptotal_, 0.0);
+      for (Index gw_level : my_levels) {
+        pack[gw_level] = frequencies_new[gw_level];
+        pack[qptotal_ + gw_level] = converged[gw_level] ? 1.0 : 0.0;
+      }
+      dev.allreduce(pack.data(), pack.size());
+      for (Index i = 0; i < qptotal_; ++i) {
+        frequencies_new[i] = pack[i];
+        converged[i] = pack[qptotal_ + i] > 0.5 ? 1 : 0;
+      }
+    }
     QPStats total_stats;
     for (const auto& s : stats) total_stats.Add(s);
     sigma_batches_ += batcher.batches();

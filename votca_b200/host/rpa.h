@@ -54,6 +54,7 @@ class RPA {
   // rpa.cc:204-264.  The S x S matrices stay on the device; XpY_dev receives (X+Y).
   rpa_eigensolution Diagonalize_H2p(Device::Buffer* XpY_dev = nullptr, bool fetch_XpY = true) const {
     const Device& dev = Mmn_.device();
+    if (dev.world() > 1) throw std::runtime_error("Diagonalize_H2p is single-GPU (S x S matrix not sharded)");
     const Index lumo = homo_ + 1;
     const Index n_occ = lumo - rpamin_;
     const Index n_unocc = rpamax_ - lumo + 1;

@@ -49,14 +49,24 @@ class Sigma_base {
   }
   // sigma_base.cc:54-63 (one batched pass instead of an OpenMP loop)
   VectorXd CalcCorrelationDiag(const VectorXd& frequencies) const {
-    std::vector<int> lv(qptotal_);
-    std::vector<double> fr(qptotal_), s;
+    // every rank evaluates the levels whose Mmn slice it owns; the results are summed over ranks
+    const Device& dev = Mmn_.device();
+    std::vector<int> lv;
+    std::vector<double> fr, s;
     for (Index i = 0; i < qptotal_; ++i) {
-      lv[i] = (int)i;
-      fr[i] = frequencies[i];
+      if (!OwnsLevel(i)) continue;
+      lv.push_back((int)i);
+      fr.push_back(frequencies[i]);
     }
-    EvalBatch(lv, fr, s, nullptr);
-    return VectorXd(s.data(), qptotal_);
+    if (!lv.empty()) EvalBatch(lv, fr, s, nullptr);
+    VectorXd out(qptotal_, 0.0);
+    for (size_t k = 0; k < lv.size(); ++k) out(lv[k]) = s[k];
+    if (dev.world() > 1) dev.allreduce(out.data(), static_cast<size_t>(qptotal_));
+    return out;
+  }
+  // owner of the Mmn slice of a qp level (m-cyclic sharding; always true on one GPU)
+  bool OwnsLevel(Index gw_level) const {
+    return Mmn_.device().owns_slice(gw_level + opt_.qpmin - opt_.rpamin);
   }
   // sigma_base.cc:65-78
   virtual MatrixXd CalcCorrelationOffDiag(const VectorXd& frequencies) const = 0;
@@ -200,6 +210,8 @@ class Sigma_Exact : public Sigma_base {
   Sigma_Exact(TCMatrix_gwbse& Mmn, const RPA& rpa) : Sigma_base(Mmn, rpa) {}
   // sigma_exact.cc:29-38, 109-148
   void PrepareScreening() final {
+    if (Mmn_.device().world() > 1)
+      throw std::runtime_error("sigma_integrator=exact is single-GPU (the S x S two-particle matrix is not sharded)");
     Device::Buffer XpY;
     RPA::rpa_eigensolution sol = rpa_.Diagonalize_H2p(&XpY, false);
     rpa_omegas_ = sol.omega;
@@ -278,6 +290,7 @@ class Sigma_CDA : public Sigma_base {
   // sigma_cda.cc:30-45 + ImaginaryAxisIntegration::CalcDielInvVector (ImaginaryAxisIntegration.cc:90-102)
   void PrepareScreening() final {
     const Device& dev = Mmn_.device();
+    if (dev.world() > 1) throw std::runtime_error("sigma_integrator=cda is single-GPU in this build");
     const Index n = Mmn_.auxsize();
     const size_t nn = static_cast<size_t>(n * n);
     std::vector<double> gx, gw;
