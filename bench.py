@@ -260,7 +260,16 @@ def main():
 
     # ---------------- e2e: AO integrals from pinned host memory, results back to the host ----------------
     e2e = None
-    if not args.no_e2e:
+    try:
+        import psutil
+        host_free = psutil.virtual_memory().available
+    except Exception:
+        host_free = 0
+    ao_bytes = 8 * naux * N * N
+    e2e_fits = host_free > 1.25 * ao_bytes * world  # every rank stages the full AO tensor (m-sharded fill)
+    if not args.no_e2e and not e2e_fits and rank == 0:
+        sys.stderr.write("e2e skipped: host memory cannot hold one pinned AO tensor per rank\n")
+    if not args.no_e2e and e2e_fits:
         try:
             host_ao = torch.empty((naux, N, N), dtype=torch.float64, pin_memory=True)
         except Exception:

@@ -403,11 +403,11 @@ void launch_sigma_multi(const gwbse_ctx::SigmaState& st, int ntotal, int ngroups
   const int nchunks = sigma_multi_chunks(st.npoles);
   dim3 grid(nchunks, ngroups);
   if (want_deriv)
-    sigma_multi_kernel<true><<<grid, 256, 0, s>>>(st.mat, st.ld, st.lstride, st.qpoff, ntotal, st.npoles,
+    sigma_multi_kernel<true><<<grid, 256, 0, s>>>(st.mat, st.ld, st.lstride, 0, ntotal, st.npoles,
                                                   st.nocc_boundary, st.eta * st.eta, st.fac, st.pole, st.energies,
                                                   levels_dev, gptr_dev, freqs_dev, partial_dev, nchunks);
   else
-    sigma_multi_kernel<false><<<grid, 256, 0, s>>>(st.mat, st.ld, st.lstride, st.qpoff, ntotal, st.npoles,
+    sigma_multi_kernel<false><<<grid, 256, 0, s>>>(st.mat, st.ld, st.lstride, 0, ntotal, st.npoles,
                                                    st.nocc_boundary, st.eta * st.eta, st.fac, st.pole, st.energies,
                                                    levels_dev, gptr_dev, freqs_dev, partial_dev, nchunks);
   GW_CUDA(cudaGetLastError());
