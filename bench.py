@@ -148,9 +148,11 @@ def run_reference(args, N, naux, homo, rank):
     from oracle import cpu_baseline
     if rank != 0:
         return
-    counts = {"gw_iterations": 6 if args.mode == "evGW" else 1, "davidson_iterations": 12, "bse_analysis_matmuls": 4}
+    counts = {"gw_iterations": 7 if args.mode == "evGW" else 1, "davidson_iterations": 8, "bse_analysis_matmuls": 4,
+              "bse_operator_products": 4 * 9 + 8}
     q = min(3 * homo + 1, N - 1) + 1
-    counts["sigma_evaluations"] = 110 * q * counts["gw_iterations"]
+    counts["sigma_evaluations"] = 756 * q * counts["gw_iterations"]  # evaluations per level and iteration of the
+    # adaptive QP search on this workload (counted by the GPU run: 325873 per iteration for q = 431)
     for _ in range(max(0, min(args.warmup, 1))):
         cpu_baseline.estimate(N, naux, homo, counts, sample_scale=0.5)
     vals = []
@@ -244,6 +246,7 @@ def main():
               "sigma_evaluations": job.scalar("sigma_evaluations"),
               "davidson_iterations": int(job.scalar("singlet_davidson_iterations")),
               "bse_analysis_matmuls": 4}
+    counts["bse_operator_products"] = 4 * (counts["davidson_iterations"] + 1) + 8  # full BSE (TDA off) + analysis
     stage_times = {k: job.scalar(k) for k in ("time_fill", "time_gw", "time_bse")}
     results = {"QP_homo": float(job.get("QPpert_energies")[homo]), "QP_lumo": float(job.get("QPpert_energies")[homo + 1]),
                "S1": float(job.get("BSE_singlet_eigenvalues")[0]), "singlet_converged": job.scalar("singlet_converged")}
