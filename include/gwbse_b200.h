@@ -53,7 +53,10 @@ long long gwbse_launch_count(const gwbse_ctx* ctx);
 int gwbse_profile_report(gwbse_ctx* ctx, char* buf, size_t buflen); /* also resets the counters */
 int gwbse_device_count(void); /* OpenMP_CUDA::AvailableGPUs, openmp_cuda.cc:30-46 */
 /* tuning knobs: "bse_chunk_bytes" (size of the Hd/Hd2 intermediate held at once), "profile" (0/1: time every
- * entry point with CUDA events on the context's stream; read the table with gwbse_profile_report) */
+ * entry point with CUDA events on the context's stream; read the table with gwbse_profile_report),
+ * "sigma_tree_min_terms" (Sigma_c diagonal elements use the treecode over sorted pole positions when
+ * n * npoles reaches this, the term-by-term kernel below it; default 32768), "sigma_tree_bytes" (budget of
+ * the per-level moment store of the treecode; default 8 GiB) */
 int gwbse_set_option(gwbse_ctx* ctx, const char* key, double value);
 /* Per-kernel accounting of the DMMA GEMM (bench.py roofline): when enabled every GEMM launch is bracketed
  * by CUDA events on the context's stream; stats = summed kernel milliseconds, algorithmic flops, launches. */

@@ -221,3 +221,21 @@ def test_error_convention():
     with pytest.raises(GwbseError, match="homo"):
         job.run()
     job.close()
+
+
+def test_evgw_treecode_sigma(golden, methane):
+    """The same evGW run with the treecode Sigma_c evaluator forced on (sigma_tree.cu): energies unchanged."""
+    e = golden["inline/gw_mo_eigenvalues"]
+    mos, vxc = golden["gw/mo_eigenvectors"], golden["gw/vxc"]
+    opts = dict(GW_OPTS)
+    opts.update(gw__mode="evGW", gw__sigma_integrator="ppm", gw__sc_max_iter=3)
+    res = []
+    for min_terms in (1e18, 0):
+        job = make_job(methane, mos, e, **opts)
+        job.set_array("vxc", vxc)
+        job.kernel_ctx().set_option("sigma_tree_min_terms", min_terms)
+        job.run()
+        res.append((job.get("QPpert_energies"), job.get("RPA_inputenergies")))
+        job.close()
+    assert np.abs(res[0][0] - res[1][0]).max() < 1e-9
+    assert np.abs(res[0][1] - res[1][1]).max() < 1e-9

@@ -229,6 +229,104 @@ def test_sigma_exact(ctx):
     assert rel_frob(s.calc_correlation_offdiag(fq), ctx.sigma_exact_offdiag(fq)) < 1e-10
 
 
+def _direct_sigma(M, fac, pole, e, nocc, eta, pref, level, w):
+    """Term-by-term sum of sigma_ppm.cc:37-91 / sigma_exact.cc:40-83 in NumPy (M: level x n x poles)."""
+    a = np.where(np.arange(M.shape[1])[:, None] < nocc, e[:, None] - pole[None, :], e[:, None] + pole[None, :])
+    r = fac[None, :] * M[level] ** 2
+    t = w - a
+    den = t * t + eta * eta
+    return pref * (r * t / den).sum(), pref * (r * (eta * eta - t * t) / den ** 2).sum()
+
+
+@pytest.mark.parametrize("tree_bytes", [8 << 30, 1 << 20])
+def test_sigma_tree_ppm(ctx, tree_bytes):
+    """Treecode Sigma_c (sigma_tree.cu) against the term-by-term sum, incl. frequencies on and next to poles,
+    and with a moment store too small for all levels (slots recycled)."""
+    rng = np.random.default_rng(70)
+    naux, mtotal, ntotal, homo = 300, 24, 140, 30
+    tc = random_tc(rng, naux, mtotal, ntotal)
+    e = np.sort(np.concatenate([rng.uniform(-1.2, -0.3, homo + 1), rng.uniform(0.05, 2.5, ntotal - homo - 1)]))
+    weight = rng.uniform(0.05, 1.0, naux)
+    weight[::17] = 0.0  # skipped poles (sigma_ppm.cc:47-52)
+    freq = rng.uniform(0.3, 6.0, naux)
+    push(ctx, tc)
+    ctx.set_option("sigma_tree_min_terms", 0)
+    ctx.set_option("sigma_tree_bytes", tree_bytes)
+    try:
+        ctx.sigma_ppm_set(weight, freq, e, homo, 0, 0, 1e-3)
+        fac = np.where(weight < 1e-9, 0.0, weight * freq)
+        levels = np.repeat(np.arange(mtotal), 5)
+        freqs = rng.uniform(-2.0, 4.0, levels.size)
+        freqs[0] = e[3] - freq[1]        # exactly on a pole
+        freqs[1] = e[50] + freq[2] + 1e-5  # next to one
+        freqs[2] = 40.0                   # far outside the pole range
+        sig, dsig = ctx.sigma_ppm_eval(levels, freqs, deriv=True)
+        ref = np.array([_direct_sigma(tc.M, fac, freq, e, homo + 1, 1e-3, 0.5, l, w) for l, w in zip(levels, freqs)])
+        scale = np.abs(ref[:, 0]).max()
+        assert np.abs(ref[:, 0] - sig).max() < 1e-11 * scale
+        assert np.abs(ref[:, 1] - dsig).max() < 1e-10 * np.abs(ref[:, 1]).max()
+        sig2 = ctx.sigma_ppm_eval(levels[::-1].copy(), freqs[::-1].copy())  # batching does not change a result
+        assert np.array_equal(sig2[::-1], sig)
+        # the term-by-term kernel agrees as well
+        ctx.set_option("sigma_tree_min_terms", 1e18)
+        sig3 = ctx.sigma_ppm_eval(levels, freqs)
+        assert np.abs(sig3 - sig).max() < 1e-11 * scale
+        # new energies move the poles: the tree is rebuilt
+        ctx.set_option("sigma_tree_min_terms", 0)
+        e2 = e + 0.01 * rng.standard_normal(ntotal)
+        ctx.sigma_update_energies(0, e2)
+        sig4 = ctx.sigma_ppm_eval(levels, freqs)
+        ref4 = np.array([_direct_sigma(tc.M, fac, freq, e2, homo + 1, 1e-3, 0.5, l, w)[0] for l, w in zip(levels, freqs)])
+        assert np.abs(ref4 - sig4).max() < 1e-11 * np.abs(ref4).max()
+    finally:
+        ctx.set_option("sigma_tree_min_terms", 1 << 15)
+        ctx.set_option("sigma_tree_bytes", 8 << 30)
+
+
+def test_sigma_tree_exact(ctx):
+    rng = np.random.default_rng(8)
+    tc, e, r, s = _sigma_setup(ctx, rng, "exact", naux=40, mtotal=20, ntotal=20, homo=5, qpmin=1, qpmax=18)
+    tc.M *= 0.2
+    push(ctx, tc)
+    omega, XpY, _ = r.diagonalize_h2p()
+    s.rpa_omegas = omega
+    s.residues = [s._calc_residues(i, XpY) for i in range(s.qptotal)]
+    ctx.set_option("sigma_tree_min_terms", 0)
+    try:
+        ctx.sigma_exact_prepare(omega, XpY, e, 5, 0, 19, 1, 18, 1e-3)
+        q = s.qptotal
+        levels = np.repeat(np.arange(q), 2)
+        freqs = np.tile([-0.5, 0.6], q) + 0.013 * levels
+        sig, dsig = ctx.sigma_exact_eval(levels, freqs, deriv=True)
+        ref = np.array([s.calc_correlation_diag_element(l, w) for l, w in zip(levels, freqs)])
+        dref = np.array([s.calc_correlation_diag_element_derivative(l, w) for l, w in zip(levels, freqs)])
+        assert rel_frob(ref, sig) < 1e-10
+        assert rel_frob(dref, dsig) < 1e-10
+    finally:
+        ctx.set_option("sigma_tree_min_terms", 1 << 15)
+
+
+def test_sigma_tree_full_size(ctx):
+    """DCV5T-sized pole set (n = 1249, Naux = 3177, 3.97 M terms per level): treecode == term-by-term kernel."""
+    rng = np.random.default_rng(71)
+    naux, mtotal, ntotal, homo = 3177, 3, 1249, 143
+    tc = random_tc(rng, naux, mtotal, ntotal)
+    e = np.sort(np.concatenate([rng.uniform(-1.2, -0.25, homo + 1), 0.02 + 3.0 * rng.uniform(0, 1, ntotal - homo - 1) ** 2]))
+    weight, freq = rng.uniform(0.05, 1.0, naux), 0.3 + 8.0 * rng.uniform(0, 1, naux) ** 2
+    push(ctx, tc)
+    ctx.sigma_ppm_set(weight, freq, e, homo, 0, 0, 1e-3)
+    levels = np.repeat(np.arange(mtotal), 40)
+    freqs = np.tile(np.linspace(-1.5, 3.5, 40), mtotal) + 1e-3 * levels
+    sig, dsig = ctx.sigma_ppm_eval(levels, freqs, deriv=True)
+    ctx.set_option("sigma_tree_min_terms", 1e18)
+    try:
+        ref, dref = ctx.sigma_ppm_eval(levels, freqs, deriv=True)
+    finally:
+        ctx.set_option("sigma_tree_min_terms", 1 << 15)
+    assert np.abs(ref - sig).max() < 1e-11 * np.abs(ref).max()
+    assert np.abs(dref - dsig).max() < 1e-10 * np.abs(dref).max()
+
+
 def test_sigma_golden(ctx, golden):
     """test_sigma_ppm.cc / test_sigma_exact.cc reference matrices through the CUDA path."""
     for kind in ("ppm", "exact"):

@@ -129,6 +129,8 @@ void gwbse_ctx_destroy(gwbse_ctx* ctx) {
   for (auto* st : {&ctx->sig_ppm, &ctx->sig_exact})
     for (double* p : {st->fac, st->pole, st->energies})
       if (p) cudaFree(p);
+  sigma_tree_destroy(ctx->sig_ppm.tree);
+  sigma_tree_destroy(ctx->sig_exact.tree);
   if (ctx->solver) cusolverDnDestroy(ctx->solver);
   for (auto& e : ctx->gemm_events) {
     cudaEventDestroy(e.first);
@@ -160,6 +162,13 @@ int gwbse_set_option(gwbse_ctx* ctx, const char* key, double value) {
   } else if (k == "bse_chunk_bytes") {
     GW_REQUIRE(value >= 1024, "bse_chunk_bytes too small");
     ctx->bse_chunk_bytes = (size_t)value;
+  } else if (k == "sigma_tree_min_terms") {
+    ctx->sigma_tree_min_terms = (long long)value;
+  } else if (k == "sigma_tree_bytes") {
+    GW_REQUIRE(value >= 1 << 20, "sigma_tree_bytes too small");
+    ctx->sigma_tree_bytes = (size_t)value;
+    sigma_tree_invalidate(ctx->sig_ppm.tree);
+    sigma_tree_invalidate(ctx->sig_exact.tree);
   } else {
     throw std::runtime_error("unknown option '" + k + "'");
   }

@@ -1,5 +1,6 @@
 // C ABI, part 3: Sigma_c evaluators (PPM and exact), batched over (level, frequency).
 #include <algorithm>
+#include <cstring>
 #include <vector>
 
 #include "../../include/gwbse_b200.h"
@@ -44,12 +45,24 @@ void sigma_eval_groups(gwbse_ctx* ctx, gwbse_ctx::SigmaState& st, int ngroups, c
   GW_CUDA(cudaMemcpyAsync(lev_d, slices.data(), sizeof(int) * ngroups, cudaMemcpyHostToDevice, ctx->stream));
   GW_CUDA(cudaMemcpyAsync(gp_d, gptr, sizeof(int) * (ngroups + 1), cudaMemcpyHostToDevice, ctx->stream));
   GW_CUDA(cudaMemcpyAsync(frq_d, freqs, sizeof(double) * nfreq, cudaMemcpyHostToDevice, ctx->stream));
-  const int nchunks = sigma_multi_chunks(st.npoles);
-  double* partial = ctx->buf("sig_partial", (size_t)nfreq * nchunks * 2);
   double* out = ctx->buf("sig_out", (size_t)nfreq * 2);
-  launch_sigma_multi(st, ctx->ntotal, ngroups, nfreq, lev_d, gp_d, frq_d, partial, out, dsigma != nullptr,
-                     ctx->stream);
-  ctx->launches += 2;
+  if ((long long)ctx->ntotal * st.npoles >= ctx->sigma_tree_min_terms) {
+    // treecode over the sorted pole positions (sigma_tree.cu)
+    const int which = (&st == &ctx->sig_ppm) ? 0 : 1;
+    if (sharded && st.seen_mmn_version != ctx->mmn_version) {
+      st.seen_mmn_version = ctx->mmn_version;
+      st.content_version++;
+    }
+    const int nslices_total = sharded ? ctx->mlocal : st.qpoff + st.q;
+    sigma_tree_eval(ctx, st, which, nslices_total, ngroups, slices.data(), gptr, frq_d, nfreq, dsigma != nullptr,
+                    out);
+  } else {
+    const int nchunks = sigma_multi_chunks(st.npoles);
+    double* partial = ctx->buf("sig_partial", (size_t)nfreq * nchunks * 2);
+    launch_sigma_multi(st, ctx->ntotal, ngroups, nfreq, lev_d, gp_d, frq_d, partial, out, dsigma != nullptr,
+                       ctx->stream);
+    ctx->launches += 2;
+  }
   GW_CUDA(cudaMemcpyAsync(sigma, out, sizeof(double) * nfreq, cudaMemcpyDeviceToHost, ctx->stream));
   if (dsigma)
     GW_CUDA(cudaMemcpyAsync(dsigma, out + nfreq, sizeof(double) * nfreq, cudaMemcpyDeviceToHost, ctx->stream));
@@ -178,6 +191,9 @@ int gwbse_sigma_ppm_set(gwbse_ctx* ctx, const double* ppm_weight, const double* 
   st.ld = ctx->ldx;
   st.lstride = ctx->npad;
   st.ready = true;
+  st.energies_host.assign(energies, energies + ctx->ntotal);
+  st.content_version++;
+  sigma_tree_invalidate(st.tree);
   GW_CUDA(cudaStreamSynchronize(ctx->stream));
   GW_API_END(ctx)
 }
@@ -186,6 +202,11 @@ int gwbse_sigma_update_energies(gwbse_ctx* ctx, int which, const double* energie
   GW_API_BEGIN(ctx)
   auto& st = which == 0 ? ctx->sig_ppm : ctx->sig_exact;
   GW_REQUIRE(st.ready && st.energies != nullptr, "sigma evaluator not prepared");
+  if ((int)st.energies_host.size() == ctx->ntotal &&
+      std::memcmp(st.energies_host.data(), energies, sizeof(double) * ctx->ntotal) == 0)
+    return 0;  // unchanged: keep the device copy and the treecode geometry
+  st.energies_host.assign(energies, energies + ctx->ntotal);
+  sigma_tree_invalidate(st.tree);
   GW_CUDA(cudaMemcpyAsync(st.energies, energies, sizeof(double) * ctx->ntotal, cudaMemcpyHostToDevice, ctx->stream));
   GW_CUDA(cudaStreamSynchronize(ctx->stream));
   GW_API_END(ctx)
@@ -292,6 +313,9 @@ int gwbse_sigma_exact_prepare(gwbse_ctx* ctx, const double* rpa_omegas, const do
   st.ld = ldr;
   st.lstride = npad;
   st.ready = true;
+  st.energies_host.assign(energies, energies + ctx->ntotal);
+  st.content_version++;
+  sigma_tree_invalidate(st.tree);
   GW_CUDA(cudaStreamSynchronize(ctx->stream));
   GW_API_END(ctx)
 }

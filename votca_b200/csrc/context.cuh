@@ -11,6 +11,10 @@
 #include "common.cuh"
 #include "gemm_dmma.cuh"
 
+namespace gwbse {
+struct SigmaTree;  // sigma_tree.cu
+}
+
 struct DevBuf {
   double* p = nullptr;
   size_t cap = 0;  // doubles
@@ -103,7 +107,14 @@ struct gwbse_ctx {
     double* fac = nullptr;     // per pole prefactor (device)
     double* pole = nullptr;    // per pole frequency (device)
     double* energies = nullptr;  // ntotal (device)
+    std::vector<double> energies_host;  // last upload (the treecode geometry is rebuilt only when it changes)
+    long long content_version = 0;      // bumped when mat / fac change (treecode moments are rebuilt)
+    long long seen_mmn_version = -1;
+    gwbse::SigmaTree* tree = nullptr;
   } sig_ppm, sig_exact;
+  // treecode evaluator (sigma_tree.cu): used when n * npoles >= sigma_tree_min_terms; moment store budget
+  long long sigma_tree_min_terms = 1 << 15;
+  size_t sigma_tree_bytes = (size_t)8 << 30;
   double* exact_res = nullptr;  // residues (q*npad) x S
 
   // ---- BSE ----
@@ -210,6 +221,12 @@ void launch_coldots(int m, int n, const double* X, long long ldx, const double* 
 void launch_scale_cols(int m, int n, double* A, long long lda, const double* s_dev, cudaStream_t s);
 void launch_copy_block(int m, int n, const double* A, long long lda, double* B, long long ldb, cudaStream_t s);
 void launch_invsqrt_scale(double* out, const double* w, int n, double etol, int* removed_dev, cudaStream_t s);
+// treecode Sigma_c (sigma_tree.cu): slices[g] = local slice of group g, frequencies gptr[g]..gptr[g+1]
+void sigma_tree_eval(gwbse_ctx* ctx, gwbse_ctx::SigmaState& st, int which, int nslices_total, int ngroups,
+                     const int* slices, const int* gptr, const double* freqs_dev, int nfreq, bool want_deriv,
+                     double* out_dev);
+void sigma_tree_invalidate(SigmaTree* t);
+void sigma_tree_destroy(SigmaTree* t);
 int sigma_multi_chunks(int npoles);
 void launch_sigma_multi(const gwbse_ctx::SigmaState& st, int ntotal, int ngroups, int nfreq, const int* levels_dev,
                         const int* gptr_dev, const double* freqs_dev, double* partial_dev, double* out_dev,
