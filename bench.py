@@ -103,9 +103,12 @@ def algorithmic_flops(N, naux, homo, counts, k_bse=15):
     f["epsilon"] = S * naux * (naux + 1.0) * (2 * it + 1)
     f["sigma_x"] = q * (q + 1.0) * n_occ * naux
     f["sigma_c_offdiag"] = 2.0 * q * q * n * naux
-    cols = counts.get("bse_operator_columns", 10 * k_bse)
-    per_col_A = 4.0 * B * naux + 2.0 * naux * vt * ct * (vt + ct) + 2.0 * B * (vt + ct)
-    f["bse_matvec"] = cols * per_col_A
+    if "bse_algorithmic_flops" in counts:  # summed by the library per operator product (F_bse with its flags)
+        f["bse_matvec"] = counts["bse_algorithmic_flops"]
+    else:
+        cols = counts.get("bse_operator_columns", 10 * k_bse)
+        per_col_A = 4.0 * B * naux + 2.0 * naux * vt * ct * (vt + ct) + 2.0 * B * (vt + ct)
+        f["bse_matvec"] = cols * per_col_A
     return f
 
 
@@ -226,6 +229,7 @@ def main():
     if rank == 0:
         sampler.start()
     launches0 = job.launch_count()
+    kctx.bse_stats(reset=True)
     kctx.gemm_profile(True)
     kctx.timer_start()
     t0 = time.perf_counter()
@@ -246,7 +250,12 @@ def main():
               "sigma_evaluations": job.scalar("sigma_evaluations"),
               "davidson_iterations": int(job.scalar("singlet_davidson_iterations")),
               "bse_analysis_matmuls": 4}
-    counts["bse_operator_products"] = 4 * (counts["davidson_iterations"] + 1) + 8  # full BSE (TDA off) + analysis
+    bse_flops, bse_products, bse_columns = kctx.bse_stats()
+    # operator products (A or B block applied to a block of trial vectors) per step: the reference rebuilds
+    # every row of H for each of them whatever the block width
+    counts["bse_operator_products"] = max(1, bse_products // args.steps)
+    counts["bse_operator_columns"] = bse_columns // args.steps
+    counts["bse_algorithmic_flops"] = bse_flops / args.steps
     stage_times = {k: job.scalar(k) for k in ("time_fill", "time_gw", "time_bse")}
     results = {"QP_homo": float(job.get("QPpert_energies")[homo]), "QP_lumo": float(job.get("QPpert_energies")[homo + 1]),
                "S1": float(job.get("BSE_singlet_eigenvalues")[0]), "singlet_converged": job.scalar("singlet_converged")}
@@ -254,8 +263,10 @@ def main():
     if os.environ.get("GWBSE_PROFILE") and rank == 0:
         # one extra, untimed step with the library's region profiler (per entry point device/host ms)
         kctx.set_option("profile", 1)
+        kctx.gemm_profile(True)
         job.run()
-        rep = kctx.profile_report()
+        rep = kctx.profile_report() + "\n" + kctx.gemm_shape_report()
+        kctx.gemm_profile(False)
         kctx.set_option("profile", 0)
         sys.stderr.write(rep + "\n" + "\n".join(l for l in job.log().splitlines()[-40:]) + "\n")
         with open(os.environ["GWBSE_PROFILE"], "w") as fh:

@@ -62,6 +62,8 @@ int gwbse_set_option(gwbse_ctx* ctx, const char* key, double value);
  * by CUDA events on the context's stream; stats = summed kernel milliseconds, algorithmic flops, launches. */
 int gwbse_gemm_profile(gwbse_ctx* ctx, int enable);
 int gwbse_gemm_stats(gwbse_ctx* ctx, double* ms, double* flops, long long* launches);
+/* the same accounting broken down by GEMM shape / tile configuration, as a text table (most expensive first) */
+int gwbse_gemm_shape_report(gwbse_ctx* ctx, char* buf, size_t buflen);
 /* Live FP64 tensor (DMMA) issue-rate probe: register-resident mma.sync loop on every SM -> TFLOP/s.
  * This is the roofline denominator for the contraction kernels (MEASURED_PEAKS.json has no FP64 entry). */
 int gwbse_fp64_peak_probe(gwbse_ctx* ctx, double* tflops);
@@ -212,6 +214,9 @@ int gwbse_bse_matmul(gwbse_ctx* ctx, int cqp, int cx, int cd, int cd2, int k, co
                      int ldy);
 int gwbse_bse_matmul_dev(gwbse_ctx* ctx, int cqp, int cx, int cd, int cd2, int k, const double* X_dev, int ldx,
                          double* Y_dev, int ldy);
+/* accounting for bench.py: algorithmic flops (F_bse), operator products and trial columns applied
+ * through gwbse_bse_matmul(_dev) since the last reset */
+int gwbse_bse_stats(gwbse_ctx* ctx, double* algo_flops, long long* products, long long* columns, int reset);
 /* BSE_OPERATOR::diagonal (bse_operator.cc:134-175) */
 int gwbse_bse_diagonal(gwbse_ctx* ctx, int cqp, int cx, int cd, int cd2, double* diag);
 

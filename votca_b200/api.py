@@ -443,4 +443,18 @@ def _profile_report(self):
     return buf.value.decode()
 
 
+def _gemm_shape_report(self):
+    buf = ctypes.create_string_buffer(65536)
+    self.call("gwbse_gemm_shape_report", buf, ctypes.c_size_t(len(buf)))
+    return buf.value.decode()
+
+
+def _bse_stats(self, reset=False):
+    fl, pr, co = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_longlong()
+    self.call("gwbse_bse_stats", ctypes.byref(fl), ctypes.byref(pr), ctypes.byref(co), int(bool(reset)))
+    return fl.value, pr.value, co.value
+
+
+Context.bse_stats = _bse_stats
 Context.profile_report = _profile_report
+Context.gemm_shape_report = _gemm_shape_report

@@ -69,6 +69,12 @@ void bse_matmul_dev(gwbse_ctx* ctx, int cqp, int cx, int cd, int cd2, int k, con
   const double* X = ctx->X;
   GW_REQUIRE(ldin >= B && ldy >= B, "Shape mismatch in BSE matmul");
   if (k <= 0) return;
+  ctx->bse_algo_flops += (double)k * ((cx != 0 ? 4.0 * B * naux : 0.0) +
+                                      (cd != 0 ? 2.0 * naux * (double)vt * ct * (vt + ct) : 0.0) +
+                                      (cd2 != 0 ? 4.0 * (double)vt * vt * ct * naux : 0.0) +
+                                      (cqp != 0 ? 2.0 * B * (vt + ct) : 0.0));
+  ctx->bse_columns += k;
+  ctx->bse_products++;
   ensure_gathered(ctx);
   // occupied / virtual slices owned by this rank
   const int nvloc = ctx->owned_count(voff, vt, ctx->rank);
@@ -179,9 +185,28 @@ void bse_matmul_dev(gwbse_ctx* ctx, int cqp, int cx, int cd, int cd2, int k, con
     const long long ldU = (long long)vtp * naux;
     const int nout = cd != 0 ? ncloc : nvloc;  // chunked index: local c1 for Hd, local v1 for Hd2
     if (nout > 0) {
-      int nc = (int)std::max<long long>(1, (long long)(ctx->bse_chunk_bytes / sizeof(double)) / (ldU * k));
+      // chunk budget: the configured size, but never more than the buffer already held plus half the free memory
+      size_t budget = ctx->bse_chunk_bytes;
+      {
+        size_t free_b = 0, total_b = 0;
+        GW_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        const size_t held = ctx->bufs["bse_U"].cap * sizeof(double);
+        budget = std::min(budget, std::max(held, held + free_b / 2));
+      }
+      int nc = (int)std::max<long long>(1, (long long)(budget / sizeof(double)) / (ldU * k));
       nc = std::min(nc, nout);
       while ((long long)naux * nc >= (1LL << 31) || (long long)nc * k >= (1LL << 31)) nc = std::max(1, nc / 2);
+      if (nc < nout) {
+        // keep the N extent (nc * k) of the second GEMM a multiple of the 64-wide tile
+        int g = 64, b = k;
+        while (b) {
+          const int t = g % b;
+          g = b;
+          b = t;
+        }
+        const int step = 64 / g;
+        if (nc > step) nc -= nc % step;
+      }
       double* U = ctx->buf("bse_U", (size_t)ldU * nc * k);
       const BlockView vv = vv_view(ctx), cv = cv_view(ctx);
       for (int a = 0; a < nout; a += nc) {
@@ -315,6 +340,18 @@ int gwbse_bse_matmul(gwbse_ctx* ctx, int cqp, int cx, int cd, int cd2, int k, co
     GW_CUDA(cudaMemcpy2DAsync(Y, sizeof(double) * ldy, Yd, sizeof(double) * B, sizeof(double) * B, k,
                               cudaMemcpyDeviceToHost, ctx->stream));
     GW_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  GW_API_END(ctx)
+}
+
+int gwbse_bse_stats(gwbse_ctx* ctx, double* algo_flops, long long* products, long long* columns, int reset) {
+  GW_API_BEGIN(ctx)
+  if (algo_flops) *algo_flops = ctx->bse_algo_flops;
+  if (products) *products = ctx->bse_products;
+  if (columns) *columns = ctx->bse_columns;
+  if (reset) {
+    ctx->bse_algo_flops = 0.0;
+    ctx->bse_products = ctx->bse_columns = 0;
   }
   GW_API_END(ctx)
 }

@@ -36,6 +36,14 @@ void gwbse_ctx::gemm(const GemmParams& p, int cfg, int splitk, double algo_flops
     }
     gemm_flops += algo_flops;
     ++gemm_launches;
+    int pc = 0, psw = 0, psk = 1;
+    gemm_plan_describe(p, num_sms, cfg, splitk, &pc, &psw, &psk);
+    char key[160];
+    snprintf(key, sizeof(key), "M=%-7d N=%-7d K=%-8lld Z=%-4d %s%s%s%s cfg%d%s sk%d", p.M, p.N,
+             (long long)p.Ko * p.Ki, p.Z1 * p.Z2, p.A.s_ki == 1 ? "Ak" : "Am", p.B.s_ki == 1 ? "Bk" : "Bm",
+             p.w ? " w" : "", p.lower_only ? " syrk" : (p.nscale ? " nsc" : ""), pc, psw ? "s" : "", psk);
+    gemm_event_keys.emplace_back(key);
+    gemm_event_flops.push_back(algo_flops);
   }
   launches += (need ? 2 : 1);
 }
@@ -47,7 +55,15 @@ void gwbse_ctx::gemm_collect() {
     float ms = 0.f;
     GW_CUDA(cudaEventElapsedTime(&ms, gemm_events[i].first, gemm_events[i].second));
     gemm_ms += ms;
+    if (i < gemm_event_keys.size()) {
+      auto& st = gemm_shapes[gemm_event_keys[i]];
+      st.ms += ms;
+      st.flops += gemm_event_flops[i];
+      st.calls++;
+    }
   }
+  gemm_event_keys.clear();
+  gemm_event_flops.clear();
   gemm_events_used = 0;
 }
 
@@ -203,6 +219,28 @@ int gwbse_gemm_profile(gwbse_ctx* ctx, int enable) {
   ctx->gemm_ms = 0.0;
   ctx->gemm_flops = 0.0;
   ctx->gemm_launches = 0;
+  ctx->gemm_shapes.clear();
+  GW_API_END(ctx)
+}
+
+int gwbse_gemm_shape_report(gwbse_ctx* ctx, char* buf, size_t buflen) {
+  GW_API_BEGIN(ctx)
+  ctx->gemm_collect();
+  std::vector<std::pair<double, std::string>> rows;
+  for (auto& kv : ctx->gemm_shapes) {
+    char line[256];
+    snprintf(line, sizeof(line), "%-72s %6lld %10.2f %8.2f\n", kv.first.c_str(), kv.second.calls, kv.second.ms,
+             kv.second.ms > 0 ? kv.second.flops / kv.second.ms * 1e-9 : 0.0);
+    rows.emplace_back(-kv.second.ms, line);
+  }
+  std::sort(rows.begin(), rows.end());
+  std::string out = "shape (A/B k- or m-major, flags, tile cfg, split-K)                               calls         ms   TFLOP/s\n";
+  for (auto& r : rows) out += r.second;
+  if (buf && buflen) {
+    const size_t n = std::min(buflen - 1, out.size());
+    std::memcpy(buf, out.data(), n);
+    buf[n] = 0;
+  }
   GW_API_END(ctx)
 }
 

@@ -66,6 +66,14 @@ struct gwbse_ctx {
   size_t gemm_events_used = 0;
   double gemm_ms = 0.0, gemm_flops = 0.0;
   long long gemm_launches = 0;
+  // per-shape breakdown (gwbse_gemm_shape_report)
+  struct ShapeStat {
+    double ms = 0.0, flops = 0.0;
+    long long calls = 0;
+  };
+  std::vector<std::string> gemm_event_keys;
+  std::vector<double> gemm_event_flops;
+  std::map<std::string, ShapeStat> gemm_shapes;
   void gemm_collect();
 
   // multi-GPU
@@ -130,7 +138,9 @@ struct gwbse_ctx {
     std::vector<double> hqp_host;
     std::vector<double> eps_inv_host;
   } bse;
-  size_t bse_chunk_bytes = (size_t)1 << 30;  // size of the Hd intermediate per chunk
+  double bse_algo_flops = 0.0;  // SURVEY.md 8(d) F_bse summed over the operator products so far
+  long long bse_columns = 0, bse_products = 0;
+  size_t bse_chunk_bytes = (size_t)8 << 30;  // size of the Hd intermediate per chunk
 
   double* buf(const std::string& name, size_t n) {
     DevBuf& b = bufs[name];

@@ -78,47 +78,56 @@ struct Plan {
 // 128x64 with two co-resident CTAs per SM is the fastest; the narrow tiles exist to fit skinny dimensions.
 constexpr double kCfgEff[6] = {0.88, 0.55, 0.60, 0.90, 1.00, 0.85};
 
+// Estimated run time (seconds) of one (orientation, tile shape, split-K) choice: CTAs are dealt to the
+// num_sms * occ resident slots wave by wave, a CTA's work is its tile area times its K range plus a fixed
+// prologue/epilogue equivalent, and a split needs one more pass over the partial sums.
+double plan_cost(const GemmParams& p, int num_sms, int cfg, bool swap, int splitk, long long T_total) {
+  const int M = swap ? p.N : p.M, N = swap ? p.M : p.N;
+  const long long tm = ceil_div(M, kCfg[cfg].BM), tn = ceil_div(N, kCfg[cfg].BN);
+  long long tiles = tm * tn;
+  if (p.lower_only) tiles = (tiles + tm) / 2;
+  tiles *= (long long)p.Z1 * p.Z2;
+  const long long ctas = tiles * splitk;
+  const long long slots = (long long)num_sms * kCfg[cfg].occ;
+  const long long waves = ceil_div(ctas, slots);
+  const double ksteps = (double)ceil_div<long long>(T_total, splitk) + 5.0;  // +5: pipeline fill and epilogue
+  const double flops_cta = 2.0 * kCfg[cfg].BM * kCfg[cfg].BN * ksteps * GEMM_BK;
+  const double rate_sm = 30.0e12 / 148.0 * kCfgEff[cfg];  // measured tile-kernel rate per SM
+  double t = (double)waves * kCfg[cfg].occ * flops_cta / rate_sm;
+  if (splitk > 1)
+    t += 3.0e-6 + 16.0 * (double)tm * kCfg[cfg].BM * (double)tn * kCfg[cfg].BN * p.Z1 * p.Z2 * splitk / 5.0e12;
+  if (swap) t *= 1.02;
+  return t;
+}
+
 Plan make_plan(const GemmParams& p, int num_sms, int force_cfg, int force_splitk) {
   Plan pl{};
-  pl.swap = false;
   const bool can_swap = force_cfg < 0 && !p.w && !p.nscale && !p.lower_only;
-  int cfg = force_cfg;
-  if (cfg < 0) {
-    // pick (orientation, tile shape) minimising padded work / throughput
-    double best = 1e300;
-    for (int sw = 0; sw <= (can_swap ? 1 : 0); ++sw) {
-      const int M = sw ? p.N : p.M, N = sw ? p.M : p.N;
-      for (int c : {4, 5, 1, 2}) {
-        const double padded = (double)ceil_div(M, kCfg[c].BM) * kCfg[c].BM * (double)ceil_div(N, kCfg[c].BN) * kCfg[c].BN;
-        const double cost = padded / kCfgEff[c] * (sw ? 1.02 : 1.0);
-        if (cost < best) {
-          best = cost;
-          cfg = c;
+  const long long T_total = (long long)p.Ko * ceil_div(p.Ki, GEMM_BK);
+  static const int kSplits[] = {1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 14, 16, 20, 24, 28, 32, 40, 48, 56, 64};
+  double best = 1e300;
+  for (int sw = 0; sw <= (can_swap ? 1 : 0); ++sw) {
+    for (int c : {4, 5, 1, 2}) {
+      if (force_cfg >= 0) c = force_cfg;
+      for (int sk : kSplits) {
+        if (force_splitk > 0) sk = force_splitk;
+        if (sk > 1 && (long long)sk * 4 > T_total && force_splitk <= 0) break;
+        const double t = plan_cost(p, num_sms, c, sw != 0, sk, T_total);
+        if (t < best) {
+          best = t;
+          pl.cfg = c;
           pl.swap = sw != 0;
+          pl.splitk = sk;
         }
+        if (force_splitk > 0) break;
       }
+      if (force_cfg >= 0) break;
     }
   }
   const int M = pl.swap ? p.N : p.M, N = pl.swap ? p.M : p.N;
-  pl.cfg = cfg;
-  pl.tiles_m = ceil_div(M, kCfg[cfg].BM);
-  pl.tiles_n = ceil_div(N, kCfg[cfg].BN);
-  long long tiles = (long long)pl.tiles_m * pl.tiles_n;
-  if (p.lower_only) tiles = (tiles + pl.tiles_m) / 2;
-  tiles *= (long long)p.Z1 * p.Z2;
-  const long long T_total = (long long)p.Ko * ceil_div(p.Ki, GEMM_BK);
-  int splitk = force_splitk;
-  if (splitk <= 0) {
-    const long long target = (long long)num_sms * kCfg[cfg].occ;
-    splitk = 1;
-    if (tiles < 2 * target) {
-      long long want = ceil_div(3 * target, tiles);
-      long long cap = std::max<long long>(1, T_total / 8);
-      splitk = (int)std::max<long long>(1, std::min<long long>(std::min(want, cap), 64));
-    }
-  }
-  splitk = (int)std::min<long long>(splitk, std::max<long long>(1, T_total));
-  pl.splitk = splitk;
+  pl.tiles_m = ceil_div(M, kCfg[pl.cfg].BM);
+  pl.tiles_n = ceil_div(N, kCfg[pl.cfg].BN);
+  pl.splitk = (int)std::min<long long>(pl.splitk, std::max<long long>(1, T_total));
   return pl;
 }
 
@@ -138,6 +147,14 @@ size_t gemm_ws_bytes_needed(const GemmParams& p, int num_sms, int force_cfg, int
   if (pl.splitk <= 1) return 0;
   return sizeof(double) * (size_t)pl.tiles_m * kCfg[pl.cfg].BM * pl.tiles_n * kCfg[pl.cfg].BN * pl.splitk * p.Z1 *
          p.Z2;
+}
+
+void gemm_plan_describe(const GemmParams& p, int num_sms, int force_cfg, int force_splitk, int* cfg, int* swap,
+                        int* splitk) {
+  Plan pl = make_plan(p, num_sms, force_cfg, force_splitk);
+  *cfg = pl.cfg;
+  *swap = pl.swap ? 1 : 0;
+  *splitk = pl.splitk;
 }
 
 void gemm_launch(GemmParams p, cudaStream_t stream, double* ws, size_t ws_bytes, int num_sms, int force_cfg,

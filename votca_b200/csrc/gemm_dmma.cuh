@@ -332,6 +332,9 @@ struct GemmPlan {
 void gemm_launch(GemmParams p, cudaStream_t stream, double* ws, size_t ws_bytes, int num_sms,
                  int force_cfg = -1, int force_splitk = 0);
 size_t gemm_ws_bytes_needed(const GemmParams& p, int num_sms, int force_cfg = -1, int force_splitk = 0);
+// tile configuration / orientation / split the launcher would pick (profiling reports)
+void gemm_plan_describe(const GemmParams& p, int num_sms, int force_cfg, int force_splitk, int* cfg, int* swap,
+                        int* splitk);
 void gemm_init_attributes();
 
 }  // namespace gwbse
