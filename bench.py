@@ -157,11 +157,11 @@ def run_reference(args, N, naux, homo, rank):
     counts["sigma_evaluations"] = 756 * q * counts["gw_iterations"]  # evaluations per level and iteration of the
     # adaptive QP search on this workload (counted by the GPU run: 325873 per iteration for q = 431)
     for _ in range(max(0, min(args.warmup, 1))):
-        cpu_baseline.estimate(N, naux, homo, counts, sample_scale=0.5)
+        cpu_baseline.estimate(N, naux, homo, counts, sample_scale=1.0)
     vals = []
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        est = cpu_baseline.estimate(N, naux, homo, counts, sample_scale=1.0)
+        est = cpu_baseline.estimate(N, naux, homo, counts, sample_scale=8.0)
         vals.append(est["total_seconds"])
     wall = time.perf_counter() - t0
     v = float(np.mean(vals))
@@ -284,9 +284,11 @@ def main():
     if not args.no_e2e and not e2e_fits and rank == 0:
         sys.stderr.write("e2e skipped: host memory cannot hold one pinned AO tensor per rank\n")
     if not args.no_e2e and e2e_fits:
+        pinned = True
         try:
             host_ao = torch.empty((naux, N, N), dtype=torch.float64, pin_memory=True)
         except Exception:
+            pinned = False
             host_ao = torch.empty((naux, N, N), dtype=torch.float64)
         host_ao.copy_(inp["ao3c_dev"])
         torch.cuda.synchronize()
@@ -304,7 +306,15 @@ def main():
         q = min(3 * homo + 1, N - 1) + 1
         h2d = 8 * (naux * N * N + N * N + 2 * naux * naux)
         d2h = 8 * (2 * q * q + 2 * q + 2 * 10 * (homo + 1) * (q - homo - 1))
-        e2e = {"value": float(te.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
+        e2e = {"value": float(te.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "host_memory": "pinned" if pinned else "pageable",
+               "stage_seconds": {k: job.scalar(k) for k in ("time_fill", "time_gw", "time_bse")}}
+        if os.environ.get("GWBSE_PROFILE") and rank == 0:
+            kctx.set_option("profile", 1)
+            job.run()
+            with open(os.environ["GWBSE_PROFILE"] + ".e2e", "w") as fh:
+                fh.write(kctx.profile_report())
+            kctx.set_option("profile", 0)
         del host_ao
 
     if rank != 0:
@@ -340,7 +350,7 @@ def main():
     }
     if not args.no_cpu:
         from oracle import cpu_baseline
-        est = cpu_baseline.estimate(N, naux, homo, counts)
+        est = cpu_baseline.estimate(N, naux, homo, counts, sample_scale=8.0)
         line["cpu_baseline"] = {
             "value": est["total_seconds"], "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
             "sample": ("reference CPU formulation (NumPy/OpenBLAS port, all host threads) timed per stage on a few "

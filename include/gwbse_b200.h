@@ -144,7 +144,14 @@ int gwbse_mmn_dims(const gwbse_ctx* ctx, int* naux, int* mtotal, int* ntotal, in
  * coefficient matrix (MOs().eigenvectors()).  Contracts
  * M[m](n, aux_offset+k) = sum_{mu,nu} C(mu,nmin+n) ao3c[k](mu,nu) C(nu,mmin+m). */
 int gwbse_mmn_set_mos(gwbse_ctx* ctx, const double* mos, int ldmos, int nbasis, int nmo);
+/* Host variant: the block is streamed through two alternating device staging buffers on a copy stream, so
+ * the transfer of one sub-block overlaps the contraction of the previous one; it returns when the last copy has
+ * left the host buffer (the GEMMs keep running on the context's stream).  Full PCIe rate needs page-locked
+ * memory: gwbse_host_malloc / gwbse_host_free hand out such buffers for the integral producer to write into
+ * (the role of CudaMatrix's staging copies, cudamatrix.cc:60-95). */
 int gwbse_mmn_fill_block(gwbse_ctx* ctx, int aux_offset, int aux_count, const double* ao3c);
+int gwbse_host_malloc(size_t bytes, void** out);
+int gwbse_host_free(void* p);
 int gwbse_mmn_fill_block_dev(gwbse_ctx* ctx, int aux_offset, int aux_count, const double* ao3c_dev);
 /* TCMatrix_gwbse::MultiplyRightWithAuxMatrix (threecenter.cc:54-65,
  * OpenMP_CUDA::MultiplyRight openmp_cuda.cc:131-150): M[m] <- M[m] * R      */

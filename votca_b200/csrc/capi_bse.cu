@@ -309,7 +309,7 @@ int gwbse_bse_configure(gwbse_ctx* ctx, int homo, int rpamin, int vmin, int cmax
   st.eps_inv = ctx->buf("bse_eps_inv", ctx->naux);
   st.hqp = ctx->buf("bse_hqp", (size_t)hs * hs);
   GW_CUDA(cudaMemcpyAsync(st.eps_inv, eps_inv, sizeof(double) * ctx->naux, cudaMemcpyHostToDevice, ctx->stream));
-  GW_CUDA(cudaMemcpy2DAsync(st.hqp, sizeof(double) * hs, Hqp, sizeof(double) * ldh, sizeof(double) * hs, hs,
+  GW_CUDA(copy2d_async(st.hqp, sizeof(double) * hs, Hqp, sizeof(double) * ldh, sizeof(double) * hs, hs,
                             cudaMemcpyHostToDevice, ctx->stream));
   GW_CUDA(cudaStreamSynchronize(ctx->stream));
   st.ready = true;
@@ -334,10 +334,10 @@ int gwbse_bse_matmul(gwbse_ctx* ctx, int cqp, int cx, int cd, int cd2, int k, co
   if (k > 0) {
     double* Xd = ctx->buf("bse_Xin", (size_t)B * k);
     double* Yd = ctx->buf("bse_Yout", (size_t)B * k);
-    GW_CUDA(cudaMemcpy2DAsync(Xd, sizeof(double) * B, X, sizeof(double) * ldx, sizeof(double) * B, k,
+    GW_CUDA(copy2d_async(Xd, sizeof(double) * B, X, sizeof(double) * ldx, sizeof(double) * B, k,
                               cudaMemcpyHostToDevice, ctx->stream));
     bse_matmul_dev(ctx, cqp, cx, cd, cd2, k, Xd, B, Yd, B);
-    GW_CUDA(cudaMemcpy2DAsync(Y, sizeof(double) * ldy, Yd, sizeof(double) * B, sizeof(double) * B, k,
+    GW_CUDA(copy2d_async(Y, sizeof(double) * ldy, Yd, sizeof(double) * B, sizeof(double) * B, k,
                               cudaMemcpyDeviceToHost, ctx->stream));
     GW_CUDA(cudaStreamSynchronize(ctx->stream));
   }

@@ -154,6 +154,11 @@ void gwbse_ctx_destroy(gwbse_ctx* ctx) {
   }
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->fill_copied[i]) cudaEventDestroy(ctx->fill_copied[i]);
+    if (ctx->fill_consumed[i]) cudaEventDestroy(ctx->fill_consumed[i]);
+  }
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -545,7 +550,7 @@ int gwbse_inverse_dev(gwbse_ctx* ctx, int n, double* A, int lda) {
     GW_CUDA(cudaGetLastError());
     int* info = reinterpret_cast<int*>(ctx->buf("solver_info", 8));
     check_solver(cusolverDnDgetrs(ctx->solver, CUBLAS_OP_N, n, n, A, lda, ipiv, I, n, info), "Dgetrs");
-    GW_CUDA(cudaMemcpy2DAsync(A, sizeof(double) * lda, I, sizeof(double) * n, sizeof(double) * n, n,
+    GW_CUDA(copy2d_async(A, sizeof(double) * lda, I, sizeof(double) * n, sizeof(double) * n, n,
                               cudaMemcpyDeviceToDevice, ctx->stream));
   }
   GW_API_END(ctx)

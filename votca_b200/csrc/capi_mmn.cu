@@ -162,7 +162,7 @@ int gwbse_mmn_set_mos(gwbse_ctx* ctx, const double* mos, int ldmos, int nbasis, 
   if (ctx->mos) GW_CUDA(cudaFree(ctx->mos));
   ctx->mos = nullptr;
   GW_CUDA(cudaMalloc(&ctx->mos, sizeof(double) * (size_t)nbasis * nmo));
-  GW_CUDA(cudaMemcpy2DAsync(ctx->mos, sizeof(double) * nbasis, mos, sizeof(double) * ldmos, sizeof(double) * nbasis,
+  GW_CUDA(copy2d_async(ctx->mos, sizeof(double) * nbasis, mos, sizeof(double) * ldmos, sizeof(double) * nbasis,
                             nmo, cudaMemcpyHostToDevice, ctx->stream));
   GW_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->nbasis = nbasis;
@@ -181,18 +181,41 @@ int gwbse_mmn_fill_block(gwbse_ctx* ctx, int aux_offset, int aux_count, const do
   GW_API_BEGIN(ctx)
   GW_PROF(ctx, "mmn_fill_block_h2d");
   const size_t per = (size_t)ctx->nbasis * ctx->nbasis;
-  // stream the block through a bounded staging buffer (<= 1 GiB)
-  const int chunk = (int)std::max<size_t>(1, std::min<size_t>(aux_count, ((size_t)1 << 27) / std::max<size_t>(per, 1)));
+  if (!ctx->copy_stream) {
+    GW_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      GW_CUDA(cudaEventCreateWithFlags(&ctx->fill_copied[i], cudaEventDisableTiming));
+      GW_CUDA(cudaEventCreateWithFlags(&ctx->fill_consumed[i], cudaEventDisableTiming));
+    }
+  }
+  // sub-blocks of <= 256 MiB through two alternating staging buffers: the copy of block i+1 (copy stream)
+  // overlaps the two contraction GEMMs of block i (compute stream)
+  const int chunk = (int)std::max<size_t>(1, std::min<size_t>(aux_count, ((size_t)1 << 25) / std::max<size_t>(per, 1)));
+  double* stage[2] = {ctx->buf("fill_ao0", per * chunk), ctx->buf("fill_ao1", per * chunk)};
   for (int b0 = 0; b0 < aux_count; b0 += chunk) {
     const int nb = std::min(chunk, aux_count - b0);
-    double* stage = ctx->buf("fill_ao", per * nb);
-    GW_CUDA(cudaMemcpyAsync(stage, ao3c + (size_t)b0 * per, sizeof(double) * per * nb, cudaMemcpyHostToDevice,
-                            ctx->stream));
-    fill_block_dev(ctx, aux_offset + b0, nb, stage);
-    GW_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int s = ctx->fill_slot;
+    ctx->fill_slot ^= 1;
+    GW_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->fill_consumed[s], 0));
+    GW_CUDA(cudaMemcpyAsync(stage[s], ao3c + (size_t)b0 * per, sizeof(double) * per * nb, cudaMemcpyHostToDevice,
+                            ctx->copy_stream));
+    GW_CUDA(cudaEventRecord(ctx->fill_copied[s], ctx->copy_stream));
+    GW_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->fill_copied[s], 0));
+    fill_block_dev(ctx, aux_offset + b0, nb, stage[s]);
+    GW_CUDA(cudaEventRecord(ctx->fill_consumed[s], ctx->stream));
   }
+  // the caller may overwrite ao3c as soon as we return; the GEMMs of the last block keep running
+  GW_CUDA(cudaStreamSynchronize(ctx->copy_stream));
   GW_API_END(ctx)
 }
+
+int gwbse_host_malloc(size_t bytes, void** out) {
+  if (!out) return 1;
+  *out = nullptr;
+  return cudaHostAlloc(out, std::max<size_t>(bytes, 1), cudaHostAllocDefault) == cudaSuccess ? 0 : 1;
+}
+
+int gwbse_host_free(void* p) { return (!p || cudaFreeHost(p) == cudaSuccess) ? 0 : 1; }
 
 int gwbse_mmn_mul_right_dev(gwbse_ctx* ctx, const double* R_dev, int ldr) {
   GW_API_BEGIN(ctx)
@@ -207,7 +230,7 @@ int gwbse_mmn_mul_right(gwbse_ctx* ctx, const double* R, int ldr) {
   require_mmn(ctx);
   GW_REQUIRE(ldr >= ctx->naux, "Shape mismatch in MultiplyRight");
   double* Rd = ctx->buf("mulright_R", (size_t)ctx->naux * ctx->naux);
-  GW_CUDA(cudaMemcpy2DAsync(Rd, sizeof(double) * ctx->naux, R, sizeof(double) * ldr, sizeof(double) * ctx->naux,
+  GW_CUDA(copy2d_async(Rd, sizeof(double) * ctx->naux, R, sizeof(double) * ldr, sizeof(double) * ctx->naux,
                             ctx->naux, cudaMemcpyHostToDevice, ctx->stream));
   mul_right_dev(ctx, Rd, ctx->naux);
   GW_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -220,7 +243,7 @@ int gwbse_mmn_get_slice(gwbse_ctx* ctx, int m, double* out, int ld) {
   GW_REQUIRE(m >= 0 && m < ctx->mtotal && ctx->owns(m), "slice index not owned by this rank");
   GW_REQUIRE(ld >= ctx->ntotal, "leading dimension too small");
   const double* src = ctx->X + (long long)ctx->local_index(m) * ctx->npad;
-  GW_CUDA(cudaMemcpy2DAsync(out, sizeof(double) * ld, src, sizeof(double) * ctx->ldx, sizeof(double) * ctx->ntotal,
+  GW_CUDA(copy2d_async(out, sizeof(double) * ld, src, sizeof(double) * ctx->ldx, sizeof(double) * ctx->ntotal,
                             ctx->naux, cudaMemcpyDeviceToHost, ctx->stream));
   GW_CUDA(cudaStreamSynchronize(ctx->stream));
   GW_API_END(ctx)
@@ -232,7 +255,7 @@ int gwbse_mmn_set_slice(gwbse_ctx* ctx, int m, const double* in, int ld) {
   GW_REQUIRE(m >= 0 && m < ctx->mtotal && ctx->owns(m), "slice index not owned by this rank");
   GW_REQUIRE(ld >= ctx->ntotal, "leading dimension too small");
   double* dst = ctx->X + (long long)ctx->local_index(m) * ctx->npad;
-  GW_CUDA(cudaMemcpy2DAsync(dst, sizeof(double) * ctx->ldx, in, sizeof(double) * ld, sizeof(double) * ctx->ntotal,
+  GW_CUDA(copy2d_async(dst, sizeof(double) * ctx->ldx, in, sizeof(double) * ld, sizeof(double) * ctx->ntotal,
                             ctx->naux, cudaMemcpyHostToDevice, ctx->stream));
   GW_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->mmn_version++;
@@ -353,7 +376,7 @@ int gwbse_rpa_epsilon(gwbse_ctx* ctx, int kind, double fre, double fim, double e
   ctx->launches++;
   if (eps_out) {
     GW_REQUIRE(ld >= naux, "leading dimension too small");
-    GW_CUDA(cudaMemcpy2DAsync(eps_out, sizeof(double) * ld, ctx->eps, sizeof(double) * naux, sizeof(double) * naux,
+    GW_CUDA(copy2d_async(eps_out, sizeof(double) * ld, ctx->eps, sizeof(double) * naux, sizeof(double) * naux,
                               naux, cudaMemcpyDeviceToHost, ctx->stream));
   }
   GW_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -445,7 +468,7 @@ int gwbse_sigma_x(gwbse_ctx* ctx, int homo, int rpamin, int qpmin, int qpmax, do
   ctx->gemm(p);
   launch_symmetrize_lower(sx, q, q, ctx->stream);
   ctx->launches++;
-  GW_CUDA(cudaMemcpy2DAsync(out, sizeof(double) * ld, sx, sizeof(double) * q, sizeof(double) * q, q,
+  GW_CUDA(copy2d_async(out, sizeof(double) * ld, sx, sizeof(double) * q, sizeof(double) * q, q,
                             cudaMemcpyDeviceToHost, ctx->stream));
   GW_CUDA(cudaStreamSynchronize(ctx->stream));
   GW_API_END(ctx)

@@ -160,7 +160,7 @@ void sigma_offdiag(gwbse_ctx* ctx, gwbse_ctx::SigmaState& st, double pref, int q
   if (sharded) allreduce_dev(ctx, S, (size_t)q * q);
   launch_offdiag_finish(S, q, S + (size_t)q * q, ctx->stream);
   ctx->launches++;
-  GW_CUDA(cudaMemcpy2DAsync(out, sizeof(double) * ld, S + (size_t)q * q, sizeof(double) * q, sizeof(double) * q, q,
+  GW_CUDA(copy2d_async(out, sizeof(double) * ld, S + (size_t)q * q, sizeof(double) * q, sizeof(double) * q, q,
                             cudaMemcpyDeviceToHost, ctx->stream));
   GW_CUDA(cudaStreamSynchronize(ctx->stream));
 }

@@ -23,6 +23,11 @@ struct DevBuf {
 struct gwbse_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  // host -> device staging of AO blocks (gwbse_mmn_fill_block): copies run on their own stream into two
+  // alternating device buffers so that they overlap the contraction GEMMs of the previous block
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t fill_copied[2] = {nullptr, nullptr}, fill_consumed[2] = {nullptr, nullptr};
+  int fill_slot = 0;
   int num_sms = 148;
   std::string err;
   cusolverDnHandle_t solver = nullptr;

@@ -29,6 +29,9 @@ struct ArraySource : AOIntegralSource {
       std::memcpy(out, ao3c + static_cast<size_t>(aux_offset) * N * N, sizeof(double) * aux_count * N * N);
     }
   }
+  const double* HostBlock(Index aux_offset, Index) const override {
+    return (!fn && ao3c) ? ao3c + static_cast<size_t>(aux_offset) * N * N : nullptr;
+  }
   const double* DeviceBlock(Index aux_offset, Index) const override {
     return ao3c_dev ? ao3c_dev + static_cast<size_t>(aux_offset) * N * N : nullptr;
   }

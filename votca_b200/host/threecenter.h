@@ -18,6 +18,8 @@ struct AOIntegralSource {
   virtual Index BasisSize() const = 0;
   // aux_count symmetric N x N matrices for aux functions [aux_offset, aux_offset+aux_count)
   virtual void ComputeAO3cBlock(Index aux_offset, Index aux_count, double* out) const = 0;
+  // optional: host pointer to the block if the integrals are already stored contiguously (no copy is made)
+  virtual const double* HostBlock(Index /*aux_offset*/, Index /*aux_count*/) const { return nullptr; }
   // optional: device pointer to the same block if the integrals already live on the GPU (nullptr otherwise)
   virtual const double* DeviceBlock(Index /*aux_offset*/, Index /*aux_count*/) const { return nullptr; }
   virtual MatrixXd AuxOverlap() const = 0;  // AOOverlap::Fill(auxbasis)
@@ -109,15 +111,31 @@ class TCMatrix_gwbse {
     if (dft_orbitals.rows() != N) throw std::runtime_error("MO coefficient matrix does not match the basis size");
     dev_.check(gwbse_mmn_set_mos(dev_.ctx(), dft_orbitals.data(), (int)dft_orbitals.rows(), (int)N,
                                  (int)dft_orbitals.cols()));
-    std::vector<double> block(static_cast<size_t>(aux_block_ * N * N));
+    // two page-locked blocks: the producer fills one while the other is on its way to the GPU
+    struct Pinned {
+      double* p = nullptr;
+      ~Pinned() { gwbse_host_free(p); }
+    } block[2];
+    int cur = 0;
     for (Index a0 = 0; a0 < auxbasissize_; a0 += aux_block_) {
       const Index cnt = std::min(aux_block_, auxbasissize_ - a0);
       if (const double* d = ints.DeviceBlock(a0, cnt)) {
         dev_.check(gwbse_mmn_fill_block_dev(dev_.ctx(), (int)a0, (int)cnt, d));
         continue;
       }
-      ints.ComputeAO3cBlock(a0, cnt, block.data());
-      dev_.check(gwbse_mmn_fill_block(dev_.ctx(), (int)a0, (int)cnt, block.data()));
+      if (const double* h = ints.HostBlock(a0, cnt)) {
+        dev_.check(gwbse_mmn_fill_block(dev_.ctx(), (int)a0, (int)cnt, h));
+        continue;
+      }
+      if (!block[cur].p) {
+        void* p = nullptr;
+        if (gwbse_host_malloc(sizeof(double) * static_cast<size_t>(aux_block_ * N * N), &p))
+          throw std::runtime_error("cannot allocate page-locked staging memory for the AO integral blocks");
+        block[cur].p = static_cast<double*>(p);
+      }
+      ints.ComputeAO3cBlock(a0, cnt, block[cur].p);
+      dev_.check(gwbse_mmn_fill_block(dev_.ctx(), (int)a0, (int)cnt, block[cur].p));
+      cur ^= 1;
     }
   }
 
