@@ -126,6 +126,63 @@ __device__ __forceinline__ void stage_tile(double* s, const double* base, const 
   }
 }
 
+// Fast path for 16-byte aligned operands: every thread owns the same (row, k) chunks of each k-tile, so the
+// row offsets, validity and shared-memory destinations are resolved once and a k-tile costs one pointer add
+// and one cp.async per chunk (straight-line code the compiler can interleave with the DMMAs).
+template <int ROWS, bool KMAJOR, int NT>
+struct Stager {
+  static constexpr int TOTAL = ROWS * (GEMM_BK / 2);
+  static constexpr int NCH = (TOTAL + NT - 1) / NT;
+  const double* src[NCH];
+  int bytes[NCH];  // 0, 8 or 16: what the rows of the chunk allow
+  __device__ __forceinline__ void init(const double* base, const GemmOperand& op, const long long* rowoff, int tid) {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int idx = tid + c * NT;
+      src[c] = base;
+      bytes[c] = 0;
+      if (TOTAL % NT == 0 || idx < TOTAL) {
+        if (KMAJOR) {
+          const int r = idx >> 3, k = (idx & 7) * 2;
+          const long long off = rowoff[r];
+          if (off >= 0) {
+            src[c] = base + off + k;
+            bytes[c] = 16;
+          }
+        } else {
+          constexpr int VPR = ROWS / 2;
+          const int k = idx / VPR, r = (idx % VPR) * 2;
+          const long long off = rowoff[r];
+          if (off >= 0) {
+            src[c] = base + off + (long long)k * op.s_ki;
+            bytes[c] = rowoff[r + 1] >= 0 ? 16 : 8;
+          }
+        }
+      }
+    }
+  }
+  // koff = ko * s_ko + k0 * s_ki (element offset of the k-tile), krem = Ki - k0
+  __device__ __forceinline__ void issue(double* s, long long koff, int krem, int tid) const {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int idx = tid + c * NT;
+      if (TOTAL % NT != 0 && idx >= TOTAL) break;
+      if (KMAJOR) {
+        const int r = idx >> 3, k = (idx & 7) * 2;
+        const int rem = krem - k;
+        const int b = rem >= 2 ? bytes[c] : (rem == 1 ? (bytes[c] ? 8 : 0) : 0);
+        cp_async16(s + r * GEMM_LDK + k, b ? src[c] + koff : src[c], b);
+      } else {
+        constexpr int VPR = ROWS / 2;
+        constexpr int LD = ROWS + 4;
+        const int k = idx / VPR, r = (idx % VPR) * 2;
+        const int b = k < krem ? bytes[c] : 0;
+        cp_async16(s + k * LD + r, b ? src[c] + koff : src[c], b);
+      }
+    }
+  }
+};
+
 template <int BM, int BN, int STAGES, bool HASW>
 struct GemmSmem {
   static constexpr int SA = BM * GEMM_LDK;  // >= GEMM_BK * (BM + 4)
@@ -183,24 +240,43 @@ __global__ void __launch_bounds__(WGM* WGN * 32, MINB) gemm_dmma_kernel(const Ge
   const int t_end = min(T_total, t_begin + per);
   const int T = max(0, t_end - t_begin);
 
-  auto issue = [&](int slot, int kt) {
-    const int ko = kt / tiles_per_ko;
-    const int k0 = (kt - ko * tiles_per_ko) * GEMM_BK;
+  const bool fastA = p.A.vec == 2, fastB = p.B.vec == 2;
+  Stager<BM, AK, NT> stA;
+  Stager<BN, BKM, NT> stB;
+  if (fastA) stA.init(Abase, p.A, offA, tid);
+  if (fastB) stB.init(Bbase, p.B, offB, tid);
+  // (ko, k0) of the next k-tile to be issued
+  int iss_ko = t_begin / tiles_per_ko;
+  int iss_k0 = (t_begin - iss_ko * tiles_per_ko) * GEMM_BK;
+
+  auto issue = [&](int slot) {
+    const int ko = iss_ko, k0 = iss_k0;
     double* sA = smem + slot * SM::STAGE;
     double* sB = sA + SM::SA;
-    stage_tile<BM, AK, NT>(sA, Abase + (long long)ko * p.A.s_ko, p.A, offA, k0, p.Ki, tid);
-    stage_tile<BN, BKM, NT>(sB, Bbase + (long long)ko * p.B.s_ko, p.B, offB, k0, p.Ki, tid);
+    if (fastA)
+      stA.issue(sA, (long long)ko * p.A.s_ko + (long long)k0 * p.A.s_ki, p.Ki - k0, tid);
+    else
+      stage_tile<BM, AK, NT>(sA, Abase + (long long)ko * p.A.s_ko, p.A, offA, k0, p.Ki, tid);
+    if (fastB)
+      stB.issue(sB, (long long)ko * p.B.s_ko + (long long)k0 * p.B.s_ki, p.Ki - k0, tid);
+    else
+      stage_tile<BN, BKM, NT>(sB, Bbase + (long long)ko * p.B.s_ko, p.B, offB, k0, p.Ki, tid);
     if (HASW) {
       if (tid < GEMM_BK) {
         const bool ok = (k0 + tid) < p.Ki;
         cp_async8(sB + SM::SB + tid, ok ? Wbase + (long long)ko * p.sW_ko + k0 + tid : Wbase, ok ? 8 : 0);
       }
     }
+    iss_k0 += GEMM_BK;
+    if (iss_k0 >= p.Ki) {
+      iss_k0 = 0;
+      ++iss_ko;
+    }
   };
 
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
-    if (s < T) issue(s, t_begin + s);
+    if (s < T) issue(s);
     cp_async_commit();
   }
 
@@ -218,7 +294,7 @@ __global__ void __launch_bounds__(WGM* WGN * 32, MINB) gemm_dmma_kernel(const Ge
     __syncthreads();
     {
       const int nxt = it + STAGES - 1;
-      if (nxt < T) issue(nxt % STAGES, t_begin + nxt);
+      if (nxt < T) issue(nxt % STAGES);
       cp_async_commit();
     }
     const double* sA = smem + (it % STAGES) * SM::STAGE;
