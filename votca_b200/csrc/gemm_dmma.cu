@@ -1,5 +1,6 @@
 // Launcher + instantiations of the FP64 DMMA GEMM (see gemm_dmma.cuh).
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 
 #include "gemm_dmma.cuh"
@@ -181,8 +182,15 @@ void gemm_launch(GemmParams p, cudaStream_t stream, double* ws, size_t ws_bytes,
     p.ws = ws;
   }
   const long long gz = (long long)p.Z1 * p.Z2 * p.splitk;
-  GW_REQUIRE(gz <= 65535 && pl.tiles_n <= 65535, "GEMM grid too large (batch or N tiles)");
-  dim3 grid(pl.tiles_m, pl.tiles_n, (unsigned)gz);
+  GW_REQUIRE(gz <= 65535 && (long long)pl.tiles_m * pl.tiles_n < (1LL << 31), "GEMM grid too large");
+  {
+    // group height minimising the bytes one wave of resident CTAs streams: group_m*BM + (slots/group_m)*BN
+    const double slots = (double)num_sms * kCfg[pl.cfg].occ;
+    double gm = std::sqrt(slots * kCfg[pl.cfg].BN / kCfg[pl.cfg].BM);
+    gm = std::max(gm, slots / pl.tiles_n);
+    p.group_m = (int)std::max(1.0, std::min<double>(pl.tiles_m, std::round(gm)));
+  }
+  dim3 grid((unsigned)(pl.tiles_m * pl.tiles_n), 1, (unsigned)gz);
   switch (pl.cfg) {
     case 0:
       launch_cfg<128, 128, 2, 4, 4, 1>(p, grid, ak, bk, stream);

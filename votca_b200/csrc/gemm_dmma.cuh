@@ -50,6 +50,7 @@ struct GemmParams {
   int splitk = 1;
   double* ws = nullptr;  // split-K partials
   int tiles_m = 0, tiles_n = 0;
+  int group_m = 1;  // rasterisation: consecutive CTAs sweep group_m m-tiles x all n-tiles (L2 reuse of both panels)
 };
 
 constexpr int GEMM_BK = 16;
@@ -203,7 +204,17 @@ __global__ void __launch_bounds__(WGM* WGN * 32, MINB) gemm_dmma_kernel(const Ge
   using SM = GemmSmem<BM, BN, STAGES, HASW>;
   static_assert(GEMM_BK * (BM + 4) <= SM::SA && GEMM_BK * (BN + 4) <= SM::SB, "tile padding");
 
-  const int tile_m = blockIdx.x, tile_n = blockIdx.y;
+  // grouped rasterisation of the linear tile index: a wave of CTAs covers group_m m-tiles x (wave / group_m)
+  // n-tiles, so the A and the B panels it streams are both shared through L2
+  int tile_m, tile_n;
+  {
+    const int per_group = p.group_m * p.tiles_n;
+    const int group = blockIdx.x / per_group, in_group = blockIdx.x - group * per_group;
+    const int first_m = group * p.group_m;
+    const int gm = min(p.group_m, p.tiles_m - first_m);
+    tile_n = in_group / gm;
+    tile_m = first_m + (in_group - tile_n * gm);
+  }
   const int m_base = tile_m * BM, n_base = tile_n * BN;
   if (p.lower_only && n_base > m_base + BM - 1) return;
 
