@@ -112,8 +112,10 @@ def algorithmic_flops(N, naux, homo, counts, k_bse=15):
     return f
 
 
-def make_inputs_gpu(torch, N, naux, homo, device, seed):
-    """Synthetic tier-S inputs generated on the device with torch (plumbing, not the product)."""
+def make_inputs_gpu(torch, N, naux, homo, device, seed, lo=0, hi=None):
+    """Synthetic tier-S inputs generated on the device with torch (plumbing, not the product).  Every rank draws
+    the same random stream and keeps the aux functions [lo, hi) of the AO tensor (its share of the fill)."""
+    hi = naux if hi is None else hi
     from votca_b200 import synthetic
     g = torch.Generator(device=device)
     g.manual_seed(seed)
@@ -124,12 +126,15 @@ def make_inputs_gpu(torch, N, naux, homo, device, seed):
     V = (A @ A.T / naux + torch.eye(naux, dtype=torch.float64, device=device)).cpu().numpy()
     band = torch.tensor(synthetic.band_profile(N) * synthetic.ao3c_sigma(N, naux, homo), dtype=torch.float64,
                         device=device)
-    ao = torch.empty((naux, N, N), dtype=torch.float64, device=device)
+    ao = torch.empty((hi - lo, N, N), dtype=torch.float64, device=device)
     blk = max(1, (1 << 27) // (N * N))
     for a0 in range(0, naux, blk):
         a1 = min(naux, a0 + blk)
         G = torch.randn(a1 - a0, N, N, dtype=torch.float64, device=device, generator=g) * band
-        ao[a0:a1] = G + G.transpose(1, 2)
+        b0, b1 = max(a0, lo), min(a1, hi)
+        if b1 > b0:
+            G = G[b0 - a0:b1 - a0]
+            ao[b0 - lo:b1 - lo] = G + G.transpose(1, 2)
         del G
     return {"mos": Q.cpu().numpy(), "mo_energies": e, "aux_overlap": np.eye(naux), "aux_coulomb": V,
             "vxc": synthetic.make_vxc(e, homo, rng), "homo": homo, "ao3c_dev": ao}
@@ -208,7 +213,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    inp = make_inputs_gpu(torch, N, naux, homo, device, 20261017)
+    # the fill is sharded over aux functions: a rank holds (and uploads) only its share of the AO tensor
+    aux_lo, aux_hi = rank * naux // world, (rank + 1) * naux // world
+    inp = make_inputs_gpu(torch, N, naux, homo, device, 20261017, aux_lo, aux_hi)
     job = build_job(inp, N, naux, args.mode, local_rank)
     if world > 1:
         from votca_b200.api import Context
@@ -221,7 +228,7 @@ def main():
     peak = kctx.fp64_peak_probe()
 
     # ---------------- value: inputs resident in HBM ----------------
-    job.set_ao3c_dev(N, naux, inp["ao3c_dev"].data_ptr())
+    job.set_ao3c_partial(N, naux, aux_lo, aux_hi - aux_lo, inp["ao3c_dev"].data_ptr(), True)
     for _ in range(args.warmup):
         job.run()
     barrier()
@@ -260,17 +267,20 @@ def main():
     results = {"QP_homo": float(job.get("QPpert_energies")[homo]), "QP_lumo": float(job.get("QPpert_energies")[homo + 1]),
                "S1": float(job.get("BSE_singlet_eigenvalues")[0]), "singlet_converged": job.scalar("singlet_converged")}
 
-    if os.environ.get("GWBSE_PROFILE") and rank == 0:
-        # one extra, untimed step with the library's region profiler (per entry point device/host ms)
+    if os.environ.get("GWBSE_PROFILE"):
+        # one extra, untimed step with the library's region profiler (per entry point device/host ms); every rank
+        # runs it (the step contains collectives), rank 0 writes the report
         kctx.set_option("profile", 1)
         kctx.gemm_profile(True)
         job.run()
         rep = kctx.profile_report() + "\n" + kctx.gemm_shape_report()
         kctx.gemm_profile(False)
         kctx.set_option("profile", 0)
-        sys.stderr.write(rep + "\n" + "\n".join(l for l in job.log().splitlines()[-40:]) + "\n")
-        with open(os.environ["GWBSE_PROFILE"], "w") as fh:
-            fh.write(rep)
+        if rank == 0:
+            sys.stderr.write(rep + "\n" + "\n".join(l for l in job.log().splitlines()[-40:]) + "\n")
+            with open(os.environ["GWBSE_PROFILE"], "w") as fh:
+                fh.write(rep)
+        barrier()
 
     # ---------------- e2e: AO integrals from pinned host memory, results back to the host ----------------
     e2e = None
@@ -280,19 +290,19 @@ def main():
     except Exception:
         host_free = 0
     ao_bytes = 8 * naux * N * N
-    e2e_fits = host_free > 1.25 * ao_bytes * world  # every rank stages the full AO tensor (m-sharded fill)
+    e2e_fits = host_free > 1.25 * ao_bytes  # the ranks together stage one copy of the AO tensor
     if not args.no_e2e and not e2e_fits and rank == 0:
         sys.stderr.write("e2e skipped: host memory cannot hold one pinned AO tensor per rank\n")
     if not args.no_e2e and e2e_fits:
         pinned = True
         try:
-            host_ao = torch.empty((naux, N, N), dtype=torch.float64, pin_memory=True)
+            host_ao = torch.empty((aux_hi - aux_lo, N, N), dtype=torch.float64, pin_memory=True)
         except Exception:
             pinned = False
-            host_ao = torch.empty((naux, N, N), dtype=torch.float64)
+            host_ao = torch.empty((aux_hi - aux_lo, N, N), dtype=torch.float64)
         host_ao.copy_(inp["ao3c_dev"])
         torch.cuda.synchronize()
-        job.set_ao3c_host_ptr(N, naux, host_ao.data_ptr())
+        job.set_ao3c_partial(N, naux, aux_lo, aux_hi - aux_lo, host_ao.data_ptr(), False)
         job.run()  # warm the staging buffers
         barrier()
         t0 = time.perf_counter()
@@ -304,17 +314,20 @@ def main():
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         q = min(3 * homo + 1, N - 1) + 1
-        h2d = 8 * (naux * N * N + N * N + 2 * naux * naux)
+        h2d = 8 * (naux * N * N + world * (N * N + 2 * naux * naux))  # whole job: AO tensor once, small inputs per rank
         d2h = 8 * (2 * q * q + 2 * q + 2 * 10 * (homo + 1) * (q - homo - 1))
         e2e = {"value": float(te.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "host_memory": "pinned" if pinned else "pageable",
                "stage_seconds": {k: job.scalar(k) for k in ("time_fill", "time_gw", "time_bse")}}
-        if os.environ.get("GWBSE_PROFILE") and rank == 0:
+        if os.environ.get("GWBSE_PROFILE"):
             kctx.set_option("profile", 1)
             job.run()
-            with open(os.environ["GWBSE_PROFILE"] + ".e2e", "w") as fh:
-                fh.write(kctx.profile_report())
+            rep = kctx.profile_report()
             kctx.set_option("profile", 0)
+            if rank == 0:
+                with open(os.environ["GWBSE_PROFILE"] + ".e2e", "w") as fh:
+                    fh.write(rep)
+            barrier()
         del host_ao
 
     if rank != 0:

@@ -153,6 +153,16 @@ int gwbse_mmn_fill_block(gwbse_ctx* ctx, int aux_offset, int aux_count, const do
 int gwbse_host_malloc(size_t bytes, void** out);
 int gwbse_host_free(void* p);
 int gwbse_mmn_fill_block_dev(gwbse_ctx* ctx, int aux_offset, int aux_count, const double* ao3c_dev);
+/* Multi-GPU fill sharded over aux functions (the reference's own parallel loop, libint2_calls.cc:621-622):
+ * between fill_begin(ctx, 1) and fill_end every rank passes only the aux functions of its share
+ * [begin, end) = gwbse_shard_aux_range(ctx, rank) to gwbse_mmn_fill_block(_dev); they are contracted for all m
+ * and fill_end (collective) moves them into the m-sharded tensor with one all-to-all over NVLink.  Each rank
+ * then needs 1/world of the AO integrals on its host and over its PCIe link.  fill_begin(ctx, 0), or no call
+ * at all, keeps the replicated mode: every rank passes every aux block and keeps its own m slices. */
+int gwbse_shard_aux_range(const gwbse_ctx* ctx, int rank, int* begin, int* end);
+int gwbse_shard_aux_begin(int naux, int rank, int world); /* share of rank r: [begin(r), begin(r+1)) */
+int gwbse_mmn_fill_begin(gwbse_ctx* ctx, int aux_sharded);
+int gwbse_mmn_fill_end(gwbse_ctx* ctx);
 /* TCMatrix_gwbse::MultiplyRightWithAuxMatrix (threecenter.cc:54-65,
  * OpenMP_CUDA::MultiplyRight openmp_cuda.cc:131-150): M[m] <- M[m] * R      */
 int gwbse_mmn_mul_right(gwbse_ctx* ctx, const double* R, int ldr);

@@ -44,6 +44,11 @@ int gwbse_job_set_ao3c_callback(gwbse_job* job, long nbasis, long naux, gwbse_ao
 
 /* AO integrals already resident on the device (naux contiguous N x N matrices) */
 int gwbse_job_set_ao3c_dev(gwbse_job* job, long nbasis, long naux, const double* ao3c_dev);
+/* Multi-GPU jobs contract the aux functions rank by rank (gwbse_mmn_fill_begin/end): a rank only needs the
+ * integrals of its share [gwbse_shard_aux_begin(naux, rank, world), gwbse_shard_aux_begin(naux, rank + 1, world)).
+ * data holds aux functions [first_aux, first_aux + count) (host memory, or device memory with on_device = 1). */
+int gwbse_job_set_ao3c_partial(gwbse_job* job, long nbasis, long naux, long first_aux, long count, const double* data,
+                               int on_device);
 /* the kernel-library context of this job (gwbse_b200.h), e.g. for gwbse_gemm_stats / timers */
 void* gwbse_job_ctx(gwbse_job* job);
 

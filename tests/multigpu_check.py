@@ -48,6 +48,12 @@ def main():
         uid = [job.kernel_ctx().nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         job.comm_init(rank, world, uid[0])
+        if tda:
+            # hand this rank only its share of the AO integrals (aux-sharded fill + all-to-all);
+            # the other pass keeps the full array on every rank
+            lo, hi = rank * naux // world, (rank + 1) * naux // world
+            share = np.ascontiguousarray(s["ao3c"][lo:hi])
+            job.set_ao3c_partial(N, naux, lo, hi - lo, share.ctypes.data, False)
         job.run()
         if rank == 0:
             for k, v in ref.items():

@@ -404,6 +404,11 @@ def _job_extras():
         self._ck(self.api.gwbse_job_set_array(self.h, b"ao3c", ctypes.c_void_p(int(host_ptr)), int(nbasis) * int(nbasis),
                                               int(naux)))
 
+    def set_ao3c_partial(self, nbasis, naux, first_aux, count, ptr_, on_device):
+        """This rank's share [first_aux, first_aux + count) of the AO tensor by raw host / device address."""
+        self._ck(self.api.gwbse_job_set_ao3c_partial(self.h, int(nbasis), int(naux), int(first_aux), int(count),
+                                                     ctypes.c_void_p(int(ptr_)), int(bool(on_device))))
+
     def kernel_ctx(self):
         """The underlying gwbse_b200 context as a Context-like wrapper (profiling, timers)."""
         c = Context.__new__(Context)
@@ -414,6 +419,7 @@ def _job_extras():
 
     Job.set_ao3c_dev = set_ao3c_dev
     Job.set_ao3c_host_ptr = set_ao3c_host_ptr
+    Job.set_ao3c_partial = set_ao3c_partial
     Job.kernel_ctx = kernel_ctx
 
     def gemm_profile(self, enable=True):

@@ -14,39 +14,60 @@ inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
 void require_mmn(const gwbse_ctx* ctx) { GW_REQUIRE(ctx->X != nullptr, "Mmn not allocated (gwbse_mmn_alloc)"); }
 
 // contraction for a block of aux functions whose AO integrals already sit on the device
+// second Mmn-sized buffer: out-of-place target of MultiplyRight and staging area of the aux-sharded fill
+// (world extra pole rows cover the rounding of the aux partition)
+void ensure_x2(gwbse_ctx* ctx) {
+  if (ctx->X2) return;
+  size_t fr = 0, tot = 0;
+  GW_CUDA(cudaMemGetInfo(&fr, &tot));
+  const size_t bytes = sizeof(double) * (size_t)ctx->ldx * (ctx->naux + ctx->world);
+  if (bytes > fr)
+    throw std::runtime_error("There were requested : " + std::to_string((double)bytes / 1048576.0) +
+                             " MB but the device has " + std::to_string((double)fr / 1048576.0) + " MB free.");
+  GW_CUDA(cudaMalloc(&ctx->X2, bytes));
+}
+
 void fill_block_dev(gwbse_ctx* ctx, int aux_offset, int aux_count, const double* ao3c_dev) {
   require_mmn(ctx);
   GW_REQUIRE(ctx->mos != nullptr, "MO coefficients not set (gwbse_mmn_set_mos)");
   GW_REQUIRE(aux_offset >= 0 && aux_offset + aux_count <= ctx->naux, "aux block out of range");
   const int N = ctx->nbasis;
   GW_REQUIRE(ctx->mmax < ctx->nmo && ctx->nmax < ctx->nmo, "level range exceeds number of MOs");
-  if (ctx->mlocal == 0 || aux_count == 0) return;
+  if (aux_count == 0) return;
+  const bool sh = ctx->fill_sharded;
+  if (sh)
+    GW_REQUIRE(aux_offset >= ctx->fill_lo && aux_offset + aux_count <= ctx->fill_hi,
+               "aux block outside this rank's share of the aux-sharded fill (gwbse_shard_aux_range)");
+  // columns contracted here: the local m slices, or every m when the fill is sharded over aux functions
+  const int mcols = sh ? ctx->mtotal : ctx->mlocal;
+  if (mcols == 0) return;
+  const long long seg = (long long)(ctx->fill_hi - ctx->fill_lo) * ctx->ldx;  // per destination rank
   const int max_batch = 4096;
   for (int b0 = 0; b0 < aux_count; b0 += max_batch) {
     const int nb = std::min(max_batch, aux_count - b0);
-    double* H = ctx->buf("fill_H", (size_t)N * ctx->mlocal * nb);
-    // H_k[nu, ml] = sum_mu T_k[mu, nu] C[mu, m(ml)]      (2 N^2 mlocal flops per aux function)
+    double* H = ctx->buf("fill_H", (size_t)N * mcols * nb);
+    // H_k[nu, ml] = sum_mu T_k[mu, nu] C[mu, m(ml)]      (2 N^2 mcols flops per aux function)
     GemmParams p;
     p.M = N;
-    p.N = ctx->mlocal;
+    p.N = mcols;
     p.Ki = N;
     p.Z1 = nb;
     p.A.ptr = ao3c_dev + (size_t)b0 * N * N;
     p.A.s_ri = N;
     p.A.s_ki = 1;
     p.A.s_z1 = (long long)N * N;
-    p.B.ptr = ctx->mos + (size_t)(ctx->mmin + ctx->rank) * N;
-    p.B.s_ri = (long long)ctx->world * N;
+    p.B.ptr = ctx->mos + (size_t)(ctx->mmin + (sh ? 0 : ctx->rank)) * N;
+    p.B.s_ri = (long long)(sh ? 1 : ctx->world) * N;
     p.B.s_ki = 1;
     p.C = H;
     p.sC_mi = 1;
     p.sC_ni = N;
-    p.sC_z1 = (long long)N * ctx->mlocal;
+    p.sC_z1 = (long long)N * mcols;
     ctx->gemm(p);
-    // M[m](n, k) = sum_nu C[nu, nmin+n] H_k[nu, ml]       (2 n N mlocal flops per aux function)
+    // M[m](n, k) = sum_nu C[nu, nmin+n] H_k[nu, ml]       (2 n N mcols flops per aux function)
     GemmParams q;
     q.M = ctx->ntotal;
-    q.N = ctx->mlocal;
+    q.N = mcols;
     q.Ki = N;
     q.Z1 = nb;
     q.A.ptr = ctx->mos + (size_t)ctx->nmin * N;
@@ -55,11 +76,19 @@ void fill_block_dev(gwbse_ctx* ctx, int aux_offset, int aux_count, const double*
     q.B.ptr = H;
     q.B.s_ri = N;
     q.B.s_ki = 1;
-    q.B.s_z1 = (long long)N * ctx->mlocal;
-    q.C = ctx->X + (long long)(aux_offset + b0) * ctx->ldx;
+    q.B.s_z1 = (long long)N * mcols;
     q.sC_mi = 1;
-    q.sC_ni = ctx->npad;
     q.sC_z1 = ctx->ldx;
+    if (sh) {
+      // X2[dest = m % world][chi - fill_lo][m / world][n]: each destination's part is one contiguous segment
+      q.C = ctx->X2 + (long long)(aux_offset - ctx->fill_lo + b0) * ctx->ldx;
+      q.Ln = ctx->world;
+      q.sC_ni = seg;
+      q.sC_no = ctx->npad;
+    } else {
+      q.C = ctx->X + (long long)(aux_offset + b0) * ctx->ldx;
+      q.sC_ni = ctx->npad;
+    }
     ctx->gemm(q);
   }
   ctx->mmn_version++;
@@ -69,15 +98,7 @@ void mul_right_dev(gwbse_ctx* ctx, const double* R_dev, int ldr) {
   require_mmn(ctx);
   if (ctx->ldx == 0) return;
   GW_REQUIRE(ldr >= ctx->naux, "Shape mismatch in MultiplyRight");
-  if (!ctx->X2) {
-    size_t fr = 0, tot = 0;
-    GW_CUDA(cudaMemGetInfo(&fr, &tot));
-    const size_t bytes = sizeof(double) * (size_t)ctx->ldx * ctx->naux;
-    if (bytes > fr)
-      throw std::runtime_error("There were requested : " + std::to_string((double)bytes / 1048576.0) +
-                               " MB but the device has " + std::to_string((double)fr / 1048576.0) + " MB free.");
-    GW_CUDA(cudaMalloc(&ctx->X2, bytes));
-  }
+  ensure_x2(ctx);
   // X2 = X * R as one flat GEMM over all (m, n) rows (padding rows are zero and stay zero)
   GW_REQUIRE(ctx->ldx < (1LL << 31), "Mmn row count exceeds 2^31");
   GemmParams p;
@@ -121,8 +142,11 @@ int gwbse_mmn_alloc(gwbse_ctx* ctx, int naux, int mmin, int mmax, int nmin, int 
   ctx->ntotal = nmax - nmin + 1;
   ctx->npad = round_up(ctx->ntotal, 16);
   ctx->mlocal = ctx->local_count(ctx->mtotal);
-  ctx->ldx = (long long)ctx->mlocal * ctx->npad;
-  const size_t bytes = sizeof(double) * (size_t)std::max<long long>(ctx->ldx, 1) * naux;
+  ctx->mlmax = (ctx->mtotal + ctx->world - 1) / ctx->world;
+  ctx->ldx = (long long)ctx->mlmax * ctx->npad;
+  ctx->fill_sharded = false;
+  // world extra pole rows: X and X2 trade places in MultiplyRight and X2 stages the aux-sharded fill
+  const size_t bytes = sizeof(double) * (size_t)std::max<long long>(ctx->ldx, 1) * (naux + ctx->world);
   size_t fr = 0, tot = 0;
   GW_CUDA(cudaMemGetInfo(&fr, &tot));
   if (bytes > fr)
@@ -216,6 +240,50 @@ int gwbse_host_malloc(size_t bytes, void** out) {
 }
 
 int gwbse_host_free(void* p) { return (!p || cudaFreeHost(p) == cudaSuccess) ? 0 : 1; }
+
+int gwbse_shard_aux_range(const gwbse_ctx* ctx, int rank, int* begin, int* end) {
+  if (!ctx || rank < 0 || rank >= ctx->world) return 1;
+  if (begin) *begin = ctx->aux_begin(rank);
+  if (end) *end = ctx->aux_begin(rank + 1);
+  return 0;
+}
+
+int gwbse_mmn_fill_begin(gwbse_ctx* ctx, int aux_sharded) {
+  GW_API_BEGIN(ctx)
+  require_mmn(ctx);
+  ctx->fill_sharded = aux_sharded != 0 && ctx->world > 1;
+  if (ctx->fill_sharded) {
+    ctx->fill_lo = ctx->aux_begin(ctx->rank);
+    ctx->fill_hi = ctx->aux_begin(ctx->rank + 1);
+    ensure_x2(ctx);
+    const size_t n = (size_t)(ctx->fill_hi - ctx->fill_lo) * ctx->ldx * ctx->world;
+    GW_CUDA(cudaMemsetAsync(ctx->X2, 0, sizeof(double) * n, ctx->stream));
+  }
+  GW_API_END(ctx)
+}
+
+int gwbse_mmn_fill_end(gwbse_ctx* ctx) {
+  GW_API_BEGIN(ctx)
+  GW_PROF(ctx, "mmn_fill_exchange");
+  if (ctx->fill_sharded) {
+    const int world = ctx->world;
+    const long long seg = (long long)(ctx->fill_hi - ctx->fill_lo) * ctx->ldx;
+    std::vector<const double*> send(world);
+    std::vector<double*> recv(world);
+    std::vector<size_t> ns(world), nr(world);
+    for (int r = 0; r < world; ++r) {
+      send[r] = ctx->X2 + (long long)r * seg;
+      ns[r] = (size_t)seg;
+      const int lo = ctx->aux_begin(r), hi = ctx->aux_begin(r + 1);
+      recv[r] = ctx->X + (long long)lo * ctx->ldx;
+      nr[r] = (size_t)(hi - lo) * ctx->ldx;
+    }
+    alltoallv_dev(ctx, send.data(), ns.data(), recv.data(), nr.data());
+    ctx->fill_sharded = false;
+    ctx->mmn_version++;
+  }
+  GW_API_END(ctx)
+}
 
 int gwbse_mmn_mul_right_dev(gwbse_ctx* ctx, const double* R_dev, int ldr) {
   GW_API_BEGIN(ctx)

@@ -64,6 +64,9 @@ extern "C" {
 
 int gwbse_shard_owner(int m, int world) { return world > 0 ? m % world : 0; }
 int gwbse_shard_local_index(int m, int world) { return world > 0 ? m / world : m; }
+int gwbse_shard_aux_begin(int naux, int rank, int world) {
+  return world > 0 ? (int)((long long)rank * naux / world) : 0;
+}
 int gwbse_shard_local_count(int total, int rank, int world) {
   if (world <= 0 || rank < 0 || rank >= world) return 0;
   return total <= rank ? 0 : (total - rank + world - 1) / world;

@@ -25,6 +25,10 @@ struct NcclApi {
   int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
   int (*AllGather)(const void*, void*, size_t, int, nccl_comm_t, cudaStream_t) = nullptr;
   int (*Broadcast)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+  int (*Send)(const void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
   bool ok = false;
   std::string err;
@@ -47,6 +51,10 @@ NcclApi& nccl() {
     api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
     api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
     api.Broadcast = reinterpret_cast<decltype(api.Broadcast)>(sym("ncclBroadcast"));
+    api.Send = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
+    api.Recv = reinterpret_cast<decltype(api.Recv)>(sym("ncclRecv"));
+    api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
+    api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
     api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
     api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.AllGather && api.Broadcast;
     if (!api.ok) api.err = "NCCL library lacks required symbols";
@@ -82,6 +90,26 @@ void allgather_dev(gwbse_ctx* ctx, const double* send, double* recv, size_t n_pe
   }
   GW_REQUIRE(ctx->nccl_comm != nullptr, "communicator not initialised (gwbse_comm_init)");
   check_nccl(nccl().AllGather(send, recv, n_per_rank, kNcclFloat64, ctx->nccl_comm, ctx->stream), "allgather");
+}
+
+void alltoallv_dev(gwbse_ctx* ctx, const double* const* send, const size_t* send_count, double* const* recv,
+                   const size_t* recv_count) {
+  if (ctx->world <= 1) {
+    if (send_count[0] && send[0] != recv[0])
+      GW_CUDA(cudaMemcpyAsync(recv[0], send[0], sizeof(double) * send_count[0], cudaMemcpyDeviceToDevice,
+                              ctx->stream));
+    return;
+  }
+  GW_REQUIRE(ctx->nccl_comm != nullptr, "communicator not initialised (gwbse_comm_init)");
+  GW_REQUIRE(nccl().Send && nccl().Recv && nccl().GroupStart && nccl().GroupEnd, "NCCL lacks send/recv");
+  check_nccl(nccl().GroupStart(), "ncclGroupStart");
+  for (int r = 0; r < ctx->world; ++r) {
+    if (send_count[r])
+      check_nccl(nccl().Send(send[r], send_count[r], kNcclFloat64, r, ctx->nccl_comm, ctx->stream), "ncclSend");
+    if (recv_count[r])
+      check_nccl(nccl().Recv(recv[r], recv_count[r], kNcclFloat64, r, ctx->nccl_comm, ctx->stream), "ncclRecv");
+  }
+  check_nccl(nccl().GroupEnd(), "ncclGroupEnd");
 }
 
 }  // namespace gwbse

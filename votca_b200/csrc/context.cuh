@@ -96,6 +96,12 @@ struct gwbse_ctx {
   // ---- Mmn ----
   int naux = 0, mmin = 0, mmax = -1, nmin = 0, nmax = -1;
   int mtotal = 0, ntotal = 0, npad = 0, mlocal = 0;
+  int mlmax = 0;  // slices per rank rounded up (ldx = mlmax * npad on every rank: pad slices are zero)
+  // aux-sharded fill (gwbse_mmn_fill_begin/end): this rank contracts aux functions [fill_lo, fill_hi) for ALL m
+  // into X2, laid out per destination rank, and the all-to-all of fill_end lands them in the m-sharded X
+  bool fill_sharded = false;
+  int fill_lo = 0, fill_hi = 0;
+  int aux_begin(int r) const { return (int)((long long)r * naux / world); }
   long long ldx = 0;
   double* X = nullptr;      // current Mmn
   double* X2 = nullptr;     // out-of-place target of MultiplyRight
@@ -221,6 +227,9 @@ void gather_slices(gwbse_ctx* ctx, int s0, int ns, int row0, int nrows, int p0, 
 // NCCL plumbing (comm.cu)
 void allreduce_dev(gwbse_ctx* ctx, double* buf_dev, size_t n);
 void allgather_dev(gwbse_ctx* ctx, const double* send_dev, double* recv_dev, size_t n_per_rank);
+// send[r] / recv[r]: device buffers exchanged with rank r (counts in doubles), one grouped NCCL call
+void alltoallv_dev(gwbse_ctx* ctx, const double* const* send, const size_t* send_count, double* const* recv,
+                   const size_t* recv_count);
 // streaming kernels (streaming.cu)
 void launch_symmetrize_lower(double* A, int n, long long ld, cudaStream_t s);
 void launch_add_diagonal(double* A, int n, long long ld, double v, cudaStream_t s);

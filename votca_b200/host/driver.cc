@@ -18,7 +18,15 @@ struct ArraySource : AOIntegralSource {
   const double* ao3c_dev = nullptr;
   gwbse_ao3c_fn fn = nullptr;
   void* user = nullptr;
+  Index first_aux = 0, held = -1;  // the arrays hold aux functions [first_aux, first_aux + held); -1: all
   MatrixXd S, V;
+  size_t local(Index aux_offset, Index aux_count) const {
+    const Index n = held < 0 ? naux : held;
+    if (aux_offset < first_aux || aux_offset + aux_count > first_aux + n)
+      throw std::runtime_error("AO three-centre integrals for aux functions " + std::to_string(aux_offset) + ".." +
+                               std::to_string(aux_offset + aux_count - 1) + " were not supplied to this rank");
+    return static_cast<size_t>(aux_offset - first_aux) * N * N;
+  }
   Index AuxSize() const override { return naux; }
   Index BasisSize() const override { return N; }
   void ComputeAO3cBlock(Index aux_offset, Index aux_count, double* out) const override {
@@ -26,14 +34,14 @@ struct ArraySource : AOIntegralSource {
       fn(user, aux_offset, aux_count, out);
     } else {
       if (!ao3c) throw std::runtime_error("no AO three-centre integrals supplied (ao3c)");
-      std::memcpy(out, ao3c + static_cast<size_t>(aux_offset) * N * N, sizeof(double) * aux_count * N * N);
+      std::memcpy(out, ao3c + local(aux_offset, aux_count), sizeof(double) * aux_count * N * N);
     }
   }
-  const double* HostBlock(Index aux_offset, Index) const override {
-    return (!fn && ao3c) ? ao3c + static_cast<size_t>(aux_offset) * N * N : nullptr;
+  const double* HostBlock(Index aux_offset, Index aux_count) const override {
+    return (!fn && ao3c) ? ao3c + local(aux_offset, aux_count) : nullptr;
   }
-  const double* DeviceBlock(Index aux_offset, Index) const override {
-    return ao3c_dev ? ao3c_dev + static_cast<size_t>(aux_offset) * N * N : nullptr;
+  const double* DeviceBlock(Index aux_offset, Index aux_count) const override {
+    return ao3c_dev ? ao3c_dev + local(aux_offset, aux_count) : nullptr;
   }
   MatrixXd AuxOverlap() const override { return S; }
   MatrixXd AuxCoulomb() const override { return V; }
@@ -126,6 +134,8 @@ int gwbse_job_set_array(gwbse_job* job, const char* name, const double* data, lo
     job->ints.ao3c = data;
     job->ints.ao3c_dev = nullptr;
     job->ints.fn = nullptr;
+    job->ints.first_aux = 0;
+    job->ints.held = -1;
     job->ints.naux = cols;
     job->ints.N = static_cast<Index>(std::llround(std::sqrt(static_cast<double>(rows))));
     if (job->ints.N * job->ints.N != rows) throw std::runtime_error("ao3c: rows must be N*N");
@@ -150,6 +160,22 @@ int gwbse_job_set_ao3c_dev(gwbse_job* job, long nbasis, long naux, const double*
   job->ints.ao3c_dev = ao3c_dev;
   job->ints.ao3c = nullptr;
   job->ints.fn = nullptr;
+  job->ints.first_aux = 0;
+  job->ints.held = -1;
+  job->ints.N = nbasis;
+  job->ints.naux = naux;
+  JOB_END(job)
+}
+
+int gwbse_job_set_ao3c_partial(gwbse_job* job, long nbasis, long naux, long first_aux, long count, const double* data,
+                               int on_device) {
+  JOB_BEGIN(job)
+  if (first_aux < 0 || count < 0 || first_aux + count > naux) throw std::runtime_error("ao3c: invalid aux range");
+  job->ints.ao3c = on_device ? nullptr : data;
+  job->ints.ao3c_dev = on_device ? data : nullptr;
+  job->ints.fn = nullptr;
+  job->ints.first_aux = first_aux;
+  job->ints.held = count;
   job->ints.N = nbasis;
   job->ints.naux = naux;
   JOB_END(job)

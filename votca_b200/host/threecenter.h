@@ -117,8 +117,14 @@ class TCMatrix_gwbse {
       ~Pinned() { gwbse_host_free(p); }
     } block[2];
     int cur = 0;
-    for (Index a0 = 0; a0 < auxbasissize_; a0 += aux_block_) {
-      const Index cnt = std::min(aux_block_, auxbasissize_ - a0);
+    // several GPUs: every rank contracts its share of the aux functions for all m (the reference's parallel
+    // loop over aux shells, libint2_calls.cc:621-622); fill_end redistributes to the m-sharded layout
+    const bool sharded = dev_.world() > 1;
+    int lo = 0, hi = (int)auxbasissize_;
+    dev_.check(gwbse_mmn_fill_begin(dev_.ctx(), sharded ? 1 : 0));
+    if (sharded) dev_.check(gwbse_shard_aux_range(dev_.ctx(), dev_.rank(), &lo, &hi));
+    for (Index a0 = lo; a0 < hi; a0 += aux_block_) {
+      const Index cnt = std::min<Index>(aux_block_, hi - a0);
       if (const double* d = ints.DeviceBlock(a0, cnt)) {
         dev_.check(gwbse_mmn_fill_block_dev(dev_.ctx(), (int)a0, (int)cnt, d));
         continue;
@@ -137,6 +143,7 @@ class TCMatrix_gwbse {
       dev_.check(gwbse_mmn_fill_block(dev_.ctx(), (int)a0, (int)cnt, block[cur].p));
       cur ^= 1;
     }
+    dev_.check(gwbse_mmn_fill_end(dev_.ctx()));
   }
 
   const Device& dev_;
