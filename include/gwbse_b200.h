@@ -167,6 +167,9 @@ int gwbse_mmn_fill_end(gwbse_ctx* ctx);
  * OpenMP_CUDA::MultiplyRight openmp_cuda.cc:131-150): M[m] <- M[m] * R      */
 int gwbse_mmn_mul_right(gwbse_ctx* ctx, const double* R, int ldr);
 int gwbse_mmn_mul_right_dev(gwbse_ctx* ctx, const double* R_dev, int ldr);
+/* TCMatrix_gwbse::Rotate (threecenter.cc:108-131, QSGW): for the m slices of the QP window,
+ * M[m].middleRows(qpmin - nmin, q) <- U^T * M[m].middleRows(qpmin - nmin, q); U is q x q, q = qpmax - qpmin + 1 */
+int gwbse_mmn_rotate(gwbse_ctx* ctx, const double* U, int ldu, int qpmin, int qpmax);
 /* AOCoulomb::Pseudo_InvSqrt_GWBSE (aomatrix.cc:53-86) on the device; S, V: naux x naux host */
 int gwbse_pseudo_invsqrt(gwbse_ctx* ctx, int naux, const double* S, const double* V, double etol, double* L_out,
                          int* removed);

@@ -126,6 +126,21 @@ def test_mmn_fill_and_mulright(ctx):
     assert rel_frob(tc.M, ctx.mmn_get_all()) < TOL
 
 
+def test_mmn_rotate(ctx):
+    """TCMatrix_gwbse::Rotate (threecenter.cc:108-131): QP-window rows of the QP-window slices only."""
+    rng = np.random.default_rng(41)
+    tc = random_tc(rng, naux=37, mtotal=22, ntotal=31)
+    tc.mmin, tc.mmax, tc.nmin, tc.nmax = 1, 22, 0, 30
+    push(ctx, tc)
+    qpmin, qpmax = 3, 17
+    U, _ = np.linalg.qr(rng.standard_normal((qpmax - qpmin + 1,) * 2))
+    tc.rotate(U, qpmin, qpmax)
+    ctx.mmn_rotate(U, qpmin, qpmax)
+    assert rel_frob(tc.M, ctx.mmn_get_all()) < TOL
+    with pytest.raises(RuntimeError):
+        ctx.mmn_rotate(U, 0, 14)  # window below mmin
+
+
 def test_mmn_golden_threecenter(ctx, golden, methane):
     """test_threecenter_gwbse.cc:36-126 through the CUDA path (AO integrals from the host)."""
     mos = golden["threecenter_gwbse/MOs"]

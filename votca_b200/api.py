@@ -222,6 +222,10 @@ class Context:
         w, f, e = (np.ascontiguousarray(x, dtype=np.float64) for x in (weight, freq, energies))
         self.call("gwbse_sigma_ppm_set", ptr(w), ptr(f), ptr(e), homo, rpamin, qpmin, float(eta))
 
+    def mmn_rotate(self, U, qpmin, qpmax):
+        u = fmat(U)
+        self.call("gwbse_mmn_rotate", ptr(u), u.shape[0], int(qpmin), int(qpmax))
+
     def sigma_update_energies(self, which, energies):
         e = np.ascontiguousarray(energies, dtype=np.float64)
         self.call("gwbse_sigma_update_energies", int(which), ptr(e))

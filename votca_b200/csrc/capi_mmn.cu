@@ -330,6 +330,49 @@ int gwbse_mmn_set_slice(gwbse_ctx* ctx, int m, const double* in, int ld) {
   GW_API_END(ctx)
 }
 
+int gwbse_mmn_rotate(gwbse_ctx* ctx, const double* U, int ldu, int qpmin, int qpmax) {
+  GW_API_BEGIN(ctx)
+  GW_PROF(ctx, "mmn_rotate");
+  require_mmn(ctx);
+  const int q = qpmax - qpmin + 1;
+  GW_REQUIRE(q > 0 && ldu >= q, "invalid rotation matrix");
+  GW_REQUIRE(qpmin >= ctx->nmin && qpmax <= ctx->nmax && qpmin >= ctx->mmin && qpmax <= ctx->mmax,
+             "QP window outside the Mmn ranges");
+  const int row0 = qpmin - ctx->nmin, s0 = qpmin - ctx->mmin;
+  GW_REQUIRE(ctx->naux <= 65535, "too many aux functions for the rotation scatter");
+  double* Ud = ctx->buf("rotate_U", (size_t)q * q);
+  GW_CUDA(copy2d_async(Ud, sizeof(double) * q, U, sizeof(double) * ldu, sizeof(double) * q, q, cudaMemcpyHostToDevice,
+                       ctx->stream));
+  const int nloc = ctx->owned_count(s0, q, ctx->rank);
+  if (nloc > 0) {
+    const int lfirst = ctx->local_index(ctx->first_owned(s0, ctx->rank));
+    // T[n', (il, chi)] = sum_n U[n, n'] X[chi][lfirst + il][row0 + n]
+    double* T = ctx->buf("rotate_T", (size_t)q * nloc * ctx->naux);
+    GemmParams p;
+    p.M = q;
+    p.N = nloc * ctx->naux;
+    p.Ki = q;
+    p.A.ptr = Ud;
+    p.A.s_ri = q;
+    p.A.s_ki = 1;
+    p.B.ptr = ctx->X + (long long)lfirst * ctx->npad + row0;
+    p.B.Lr = nloc;
+    p.B.s_ri = ctx->npad;
+    p.B.s_ro = ctx->ldx;
+    p.B.s_ki = 1;
+    p.C = T;
+    p.sC_mi = 1;
+    p.sC_ni = q;
+    ctx->gemm(p);
+    launch_rotate_scatter(T, q, nloc, ctx->naux, ctx->X, ctx->ldx, ctx->npad, lfirst, row0, ctx->stream);
+    ctx->launches++;
+  }
+  ctx->mmn_version++;
+  ctx->sig_ppm.ready = false;
+  GW_CUDA(cudaStreamSynchronize(ctx->stream));
+  GW_API_END(ctx)
+}
+
 int gwbse_mmn_snapshot(gwbse_ctx* ctx) {
   GW_API_BEGIN(ctx)
   GW_PROF(ctx, "mmn_snapshot");

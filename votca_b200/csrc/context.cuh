@@ -244,6 +244,8 @@ void launch_coldots(int m, int n, const double* X, long long ldx, const double* 
                     cudaStream_t s);
 void launch_scale_cols(int m, int n, double* A, long long lda, const double* s_dev, cudaStream_t s);
 void launch_copy_block(int m, int n, const double* A, long long lda, double* B, long long ldb, cudaStream_t s);
+void launch_rotate_scatter(const double* T, int q, int nloc, int naux, double* X, long long ldx, int npad, int lfirst,
+                           int row0, cudaStream_t s);
 void launch_invsqrt_scale(double* out, const double* w, int n, double etol, int* removed_dev, cudaStream_t s);
 // treecode Sigma_c (sigma_tree.cu): slices[g] = local slice of group g, frequencies gptr[g]..gptr[g+1]
 void sigma_tree_eval(gwbse_ctx* ctx, gwbse_ctx::SigmaState& st, int which, int nslices_total, int ngroups,

@@ -385,6 +385,21 @@ void launch_scale_cols(int m, int n, double* A, long long lda, const double* s_d
   scale_cols_kernel<<<grid2(m, n), 256, 0, s>>>(m, n, A, lda, s_dev);
   GW_CUDA(cudaGetLastError());
 }
+// X[chi * ldx + (lfirst + il) * npad + row0 + n] = T[n + q * (il + nloc * chi)]
+__global__ void rotate_scatter_kernel(const double* __restrict__ T, int q, int nloc, double* __restrict__ X,
+                                      long long ldx, int npad, int lfirst, int row0) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int il = blockIdx.y, chi = blockIdx.z;
+  if (n >= q) return;
+  X[(long long)chi * ldx + (long long)(lfirst + il) * npad + row0 + n] = T[n + (long long)q * (il + (long long)nloc * chi)];
+}
+void launch_rotate_scatter(const double* T, int q, int nloc, int naux, double* X, long long ldx, int npad, int lfirst,
+                           int row0, cudaStream_t s) {
+  if (q <= 0 || nloc <= 0 || naux <= 0) return;
+  dim3 grid((q + 127) / 128, nloc, naux);
+  rotate_scatter_kernel<<<grid, 128, 0, s>>>(T, q, nloc, X, ldx, npad, lfirst, row0);
+  GW_CUDA(cudaGetLastError());
+}
 void launch_copy_block(int m, int n, const double* A, long long lda, double* B, long long ldb, cudaStream_t s) {
   if (m <= 0 || n <= 0) return;
   copy_block_kernel<<<grid2(m, n), 256, 0, s>>>(m, n, A, lda, B, ldb);

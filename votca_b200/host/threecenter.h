@@ -94,6 +94,15 @@ class TCMatrix_gwbse {
   }
   void KeepSnapshot(bool on) { keep_snapshot_ = on; }
 
+  // threecenter.cc:108-131 (QSGW): rotate the n rows of the QP window in the QP-window m slices
+  void Rotate(const MatrixXd& U, Index qpmin, Index qpmax) {
+    const Index qptotal = qpmax - qpmin + 1;
+    if (U.rows() != qptotal || U.cols() != qptotal)
+      throw std::runtime_error("TCMatrix_gwbse::Rotate: rotation matrix does not match the QP window");
+    dev_.check(gwbse_mmn_rotate(dev_.ctx(), U.data(), (int)U.rows(), (int)qpmin, (int)qpmax));
+    mirror_.clear();
+  }
+
   // threecenter.cc:54-65
   void MultiplyRightWithAuxMatrix(const MatrixXd& matrix) {
     if (matrix.rows() != auxbasissize_ || matrix.cols() != auxbasissize_)
