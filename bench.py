@@ -336,10 +336,15 @@ def main():
     total_flops = sum(flops.values())
     achieved = gstats["flops"] / (gstats["ms"] * 1e-3) / 1e12 if gstats["ms"] > 0 else 0.0
     traffic = None
+    traffic_note = None
     prof = os.path.join(ROOT, "profiles", "ncu_summary.json")
     if os.path.exists(prof):
         try:
-            traffic = json.load(open(prof)).get("gemm_dram_bytes_per_launch")
+            ncu = json.load(open(prof))
+            traffic = ncu.get("gemm_dram_bytes_per_launch")
+            traffic_note = ("dram bytes of one ncu --set full capture of the dominant launch shape (" +
+                            str(ncu.get("report")) + f"); algorithmic bytes of that launch "
+                            f"{ncu.get('algorithmic_bytes_per_launch')}")
         except Exception:
             traffic = None
     line = {
@@ -355,6 +360,7 @@ def main():
                    "stages_tflop": {k: round(v / 1e12, 3) for k, v in flops.items()}},
         "roofline": {"bound": "tensor", "kernel": "gemm_dmma_kernel (FP64 DMMA.8x8x4)", "achieved": achieved,
                      "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": traffic,
+                     "traffic_note": traffic_note,
                      "peak_source": "live DMMA issue-rate probe in this run (MEASURED_PEAKS.json has no FP64 entry; "
                                     "cuBLAS Dgemm 8192^3 measured 36.0 TF/s, profiles/r01_fp64_peak_probe.txt)",
                      "launches": gstats["launches"], "kernel_ms_per_step": gstats["ms"] / args.steps,

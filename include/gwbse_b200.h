@@ -170,9 +170,12 @@ int gwbse_mmn_mul_right_dev(gwbse_ctx* ctx, const double* R_dev, int ldr);
 /* TCMatrix_gwbse::Rotate (threecenter.cc:108-131, QSGW): for the m slices of the QP window,
  * M[m].middleRows(qpmin - nmin, q) <- U^T * M[m].middleRows(qpmin - nmin, q); U is q x q, q = qpmax - qpmin + 1 */
 int gwbse_mmn_rotate(gwbse_ctx* ctx, const double* U, int ldu, int qpmin, int qpmax);
-/* AOCoulomb::Pseudo_InvSqrt_GWBSE (aomatrix.cc:53-86) on the device; S, V: naux x naux host */
+/* AOCoulomb::Pseudo_InvSqrt_GWBSE (aomatrix.cc:53-86) on the device; S, V: naux x naux host.  L_out may be
+ * NULL: the result then only stays on the device (gwbse_pseudo_invsqrt_result_dev, valid until the next call)
+ * for gwbse_mmn_mul_right_dev, which is how TCMatrix_gwbse::Fill uses it (threecenter.cc:72-90). */
 int gwbse_pseudo_invsqrt(gwbse_ctx* ctx, int naux, const double* S, const double* V, double etol, double* L_out,
                          int* removed);
+const double* gwbse_pseudo_invsqrt_result_dev(gwbse_ctx* ctx);
 /* operator[] (threecenter.h:125-134): copy slice M[m] (ntotal x naux, col-major, ld) to/from host.
  * m is the global storage index (m_abs - mmin); must be owned by this rank. */
 int gwbse_mmn_get_slice(gwbse_ctx* ctx, int m, double* out, int ld);

@@ -129,10 +129,16 @@ int gwbse_mmn_alloc(gwbse_ctx* ctx, int naux, int mmin, int mmax, int nmin, int 
   GW_API_BEGIN(ctx)
   GW_REQUIRE(naux > 0 && mmax >= mmin && nmax >= nmin && mmin >= 0 && nmin >= 0, "invalid Mmn ranges");
   GW_CUDA(cudaStreamSynchronize(ctx->stream));
-  for (double** p : {&ctx->X, &ctx->X2, &ctx->Xsnap}) {
-    if (*p) GW_CUDA(cudaFree(*p));
-    *p = nullptr;
+  // same shape as the tensor already held (a job run again, Rebuild without snapshot): keep the three buffers
+  const bool same = ctx->X != nullptr && ctx->naux == naux && ctx->mmin == mmin && ctx->mmax == mmax &&
+                    ctx->nmin == nmin && ctx->nmax == nmax && ctx->alloc_world == ctx->world;
+  if (!same) {
+    for (double** p : {&ctx->X, &ctx->X2, &ctx->Xsnap}) {
+      if (*p) GW_CUDA(cudaFree(*p));
+      *p = nullptr;
+    }
   }
+  ctx->alloc_world = ctx->world;
   ctx->naux = naux;
   ctx->mmin = mmin;
   ctx->mmax = mmax;
@@ -147,13 +153,16 @@ int gwbse_mmn_alloc(gwbse_ctx* ctx, int naux, int mmin, int mmax, int nmin, int 
   ctx->fill_sharded = false;
   // world extra pole rows: X and X2 trade places in MultiplyRight and X2 stages the aux-sharded fill
   const size_t bytes = sizeof(double) * (size_t)std::max<long long>(ctx->ldx, 1) * (naux + ctx->world);
-  size_t fr = 0, tot = 0;
-  GW_CUDA(cudaMemGetInfo(&fr, &tot));
-  if (bytes > fr)
-    throw std::runtime_error("There were requested : " + std::to_string((double)bytes / 1048576.0) +
-                             " MB but the device has " + std::to_string((double)fr / 1048576.0) + " MB free.");
-  GW_CUDA(cudaMalloc(&ctx->X, bytes));
+  if (!ctx->X) {
+    size_t fr = 0, tot = 0;
+    GW_CUDA(cudaMemGetInfo(&fr, &tot));
+    if (bytes > fr)
+      throw std::runtime_error("There were requested : " + std::to_string((double)bytes / 1048576.0) +
+                               " MB but the device has " + std::to_string((double)fr / 1048576.0) + " MB free.");
+    GW_CUDA(cudaMalloc(&ctx->X, bytes));
+  }
   GW_CUDA(cudaMemsetAsync(ctx->X, 0, bytes, ctx->stream));
+  ctx->mmn_version++;
   ctx->sig_ppm.ready = ctx->sig_exact.ready = ctx->bse.ready = false;
   GW_API_END(ctx)
 }
@@ -428,11 +437,17 @@ int gwbse_pseudo_invsqrt(gwbse_ctx* ctx, int n, const double* S, const double* V
   if (gwbse_dgemm_dev(ctx, 'N', 'N', n, n, n, 1.0, dSs, n, dS, n, 0.0, dT, n)) throw std::runtime_error(ctx->err);
   ctx->launches += 4;
   int hrem = 0;
-  GW_CUDA(cudaMemcpyAsync(L_out, dT, sizeof(double) * nn, cudaMemcpyDeviceToHost, ctx->stream));
+  if (L_out) GW_CUDA(cudaMemcpyAsync(L_out, dT, sizeof(double) * nn, cudaMemcpyDeviceToHost, ctx->stream));
   GW_CUDA(cudaMemcpyAsync(&hrem, drem, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   GW_CUDA(cudaStreamSynchronize(ctx->stream));
   if (removed) *removed = hrem;
   GW_API_END(ctx)
+}
+
+const double* gwbse_pseudo_invsqrt_result_dev(gwbse_ctx* ctx) {
+  if (!ctx) return nullptr;
+  auto it = ctx->bufs.find("pis_T");
+  return it == ctx->bufs.end() ? nullptr : it->second.p;
 }
 
 // ------------------------------- RPA ---------------------------------------

@@ -96,6 +96,7 @@ struct gwbse_ctx {
   // ---- Mmn ----
   int naux = 0, mmin = 0, mmax = -1, nmin = 0, nmax = -1;
   int mtotal = 0, ntotal = 0, npad = 0, mlocal = 0;
+  int alloc_world = 0;
   int mlmax = 0;  // slices per rank rounded up (ldx = mlmax * npad on every rank: pad slices are zero)
   // aux-sharded fill (gwbse_mmn_fill_begin/end): this rank contracts aux functions [fill_lo, fill_hi) for ALL m
   // into X2, laid out per destination rank, and the all-to-all of fill_end lands them in the m-sharded X

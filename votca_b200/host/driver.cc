@@ -19,7 +19,8 @@ struct ArraySource : AOIntegralSource {
   gwbse_ao3c_fn fn = nullptr;
   void* user = nullptr;
   Index first_aux = 0, held = -1;  // the arrays hold aux functions [first_aux, first_aux + held); -1: all
-  MatrixXd S, V;
+  const MatrixXd* S = nullptr;
+  const MatrixXd* V = nullptr;
   size_t local(Index aux_offset, Index aux_count) const {
     const Index n = held < 0 ? naux : held;
     if (aux_offset < first_aux || aux_offset + aux_count > first_aux + n)
@@ -43,8 +44,8 @@ struct ArraySource : AOIntegralSource {
   const double* DeviceBlock(Index aux_offset, Index aux_count) const override {
     return ao3c_dev ? ao3c_dev + local(aux_offset, aux_count) : nullptr;
   }
-  MatrixXd AuxOverlap() const override { return S; }
-  MatrixXd AuxCoulomb() const override { return V; }
+  const MatrixXd& AuxOverlap() const override { return *S; }
+  const MatrixXd& AuxCoulomb() const override { return *V; }
 };
 
 }  // namespace
@@ -199,9 +200,9 @@ int gwbse_job_run(gwbse_job* job) {
   in.mos = &mos;
   in.mo_energies = &mo_e;
   if (job->in.count("vxc")) in.vxc = &job->in["vxc"];
-  job->ints.S = need("aux_overlap");
-  job->ints.V = need("aux_coulomb");
-  if (job->ints.naux != job->ints.S.rows()) throw std::runtime_error("aux matrices do not match ao3c");
+  job->ints.S = &need("aux_overlap");
+  job->ints.V = &need("aux_coulomb");
+  if (job->ints.naux != job->ints.S->rows()) throw std::runtime_error("aux matrices do not match ao3c");
   in.integrals = &job->ints;
   std::vector<MatrixXd> dip;
   if (job->in.count("dipole_x") && job->in.count("dipole_y") && job->in.count("dipole_z")) {

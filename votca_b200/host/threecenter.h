@@ -22,8 +22,8 @@ struct AOIntegralSource {
   virtual const double* HostBlock(Index /*aux_offset*/, Index /*aux_count*/) const { return nullptr; }
   // optional: device pointer to the same block if the integrals already live on the GPU (nullptr otherwise)
   virtual const double* DeviceBlock(Index /*aux_offset*/, Index /*aux_count*/) const { return nullptr; }
-  virtual MatrixXd AuxOverlap() const = 0;  // AOOverlap::Fill(auxbasis)
-  virtual MatrixXd AuxCoulomb() const = 0;  // AOCoulomb::Fill(auxbasis)
+  virtual const MatrixXd& AuxOverlap() const = 0;  // AOOverlap::Fill(auxbasis)
+  virtual const MatrixXd& AuxCoulomb() const = 0;  // AOCoulomb::Fill(auxbasis)
 };
 
 class TCMatrix_gwbse {
@@ -70,14 +70,15 @@ class TCMatrix_gwbse {
     dft_orbitals_ = &dft_orbitals;
     aux_block_ = aux_block;
     Fill3cMO(ints, dft_orbitals);
-    const MatrixXd S = ints.AuxOverlap();
-    const MatrixXd V = ints.AuxCoulomb();
-    MatrixXd inv_sqrt(auxbasissize_, auxbasissize_);
+    const MatrixXd& S = ints.AuxOverlap();
+    const MatrixXd& V = ints.AuxCoulomb();
+    if (S.rows() != auxbasissize_ || V.rows() != auxbasissize_)
+      throw std::runtime_error("aux overlap / Coulomb matrices do not match the aux basis size");
     int removed = 0;
-    dev_.check(gwbse_pseudo_invsqrt(dev_.ctx(), (int)auxbasissize_, S.data(), V.data(), 5e-7, inv_sqrt.data(),
-                                    &removed));
+    // V^-1/2 stays on the device and is applied from there
+    dev_.check(gwbse_pseudo_invsqrt(dev_.ctx(), (int)auxbasissize_, S.data(), V.data(), 5e-7, nullptr, &removed));
     removedfunctions_ = removed;
-    MultiplyRightWithAuxMatrix(inv_sqrt);
+    MultiplyRightWithAuxMatrix_dev(gwbse_pseudo_invsqrt_result_dev(dev_.ctx()), auxbasissize_);
     if (keep_snapshot_) dev_.check(gwbse_mmn_snapshot(dev_.ctx()));
     have_snapshot_ = keep_snapshot_;
   }
