@@ -166,7 +166,7 @@ def run_reference(args, N, naux, homo, rank):
     vals = []
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        est = cpu_baseline.estimate(N, naux, homo, counts, sample_scale=8.0)
+        est = cpu_baseline.estimate(N, naux, homo, counts, sample_scale=24.0)
         vals.append(est["total_seconds"])
     wall = time.perf_counter() - t0
     v = float(np.mean(vals))
@@ -369,7 +369,7 @@ def main():
     }
     if not args.no_cpu:
         from oracle import cpu_baseline
-        est = cpu_baseline.estimate(N, naux, homo, counts, sample_scale=8.0)
+        est = cpu_baseline.estimate(N, naux, homo, counts, sample_scale=24.0)
         line["cpu_baseline"] = {
             "value": est["total_seconds"], "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
             "sample": ("reference CPU formulation (NumPy/OpenBLAS port, all host threads) timed per stage on a few "

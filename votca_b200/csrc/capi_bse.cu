@@ -209,6 +209,26 @@ void bse_matmul_dev(gwbse_ctx* ctx, int cqp, int cx, int cd, int cd2, int k, con
       }
       double* U = ctx->buf("bse_U", (size_t)ldU * nc * k);
       const BlockView vv = vv_view(ctx), cv = cv_view(ctx);
+      // trial vectors with an even row stride: X[(v2,c2),kv] -> Xp[(kv,v2)][c2], ld = ctp, so that the operand
+      // of the first GEMM is 16-byte aligned row by row (ct is odd for most molecules)
+      const int ctp = round_up(ct, 2);
+      const double* Xa = Xin;
+      long long xa_ri = ct, xa_ro = ldin;
+      if (ct != ctp) {
+        double* Xp = ctx->buf("bse_Xp", (size_t)ctp * vt * k);
+        if (ldin == B) {
+          GW_CUDA(cudaMemcpy2DAsync(Xp, sizeof(double) * ctp, Xin, sizeof(double) * ct, sizeof(double) * ct,
+                                    (size_t)vt * k, cudaMemcpyDeviceToDevice, ctx->stream));
+        } else {
+          for (int j = 0; j < k; ++j)
+            GW_CUDA(cudaMemcpy2DAsync(Xp + (size_t)j * vt * ctp, sizeof(double) * ctp, Xin + (size_t)j * ldin,
+                                      sizeof(double) * ct, sizeof(double) * ct, vt, cudaMemcpyDeviceToDevice,
+                                      ctx->stream));
+        }
+        Xa = Xp;
+        xa_ri = ctp;
+        xa_ro = (long long)vt * ctp;
+      }
       for (int a = 0; a < nout; a += nc) {
         const int n1 = std::min(nc, nout - a);
         // U[(v2, chi), (l, kv)] = eps_inv[chi] sum_c2 X[c2,(v2,kv)] Mblk[l][c2, chi]   (l: local slices of the chunk)
@@ -216,10 +236,10 @@ void bse_matmul_dev(gwbse_ctx* ctx, int cqp, int cx, int cd, int cd2, int k, con
         p.M = vt * k;
         p.N = naux * n1;
         p.Ki = ct;
-        p.A.ptr = Xin;
+        p.A.ptr = Xa;
         p.A.Lr = vt;
-        p.A.s_ri = ct;
-        p.A.s_ro = ldin;
+        p.A.s_ri = xa_ri;
+        p.A.s_ro = xa_ro;
         p.A.s_ki = 1;
         p.B.ptr = X + (long long)((cd != 0 ? lcfirst : lvfirst) + a) * npad + coff;
         p.B.Lr = naux;

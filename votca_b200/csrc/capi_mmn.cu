@@ -1,5 +1,6 @@
 // C ABI, part 2: the Mmn tensor (TCMatrix_gwbse), RPA dielectric matrix, Sigma_x.
 #include <algorithm>
+#include <cstdint>
 #include <vector>
 
 #include "../../include/gwbse_b200.h"
@@ -45,7 +46,8 @@ void fill_block_dev(gwbse_ctx* ctx, int aux_offset, int aux_count, const double*
   const int max_batch = 4096;
   for (int b0 = 0; b0 < aux_count; b0 += max_batch) {
     const int nb = std::min(max_batch, aux_count - b0);
-    double* H = ctx->buf("fill_H", (size_t)N * mcols * nb);
+    const int Np = round_up(N, 2);  // even pitch of the MO matrix and of the half-transformed blocks
+    double* H = ctx->buf("fill_H", (size_t)Np * mcols * nb);
     // H_k[nu, ml] = sum_mu T_k[mu, nu] C[mu, m(ml)]      (2 N^2 mcols flops per aux function)
     GemmParams p;
     p.M = N;
@@ -56,13 +58,13 @@ void fill_block_dev(gwbse_ctx* ctx, int aux_offset, int aux_count, const double*
     p.A.s_ri = N;
     p.A.s_ki = 1;
     p.A.s_z1 = (long long)N * N;
-    p.B.ptr = ctx->mos + (size_t)(ctx->mmin + (sh ? 0 : ctx->rank)) * N;
-    p.B.s_ri = (long long)(sh ? 1 : ctx->world) * N;
+    p.B.ptr = ctx->mos + (size_t)(ctx->mmin + (sh ? 0 : ctx->rank)) * Np;
+    p.B.s_ri = (long long)(sh ? 1 : ctx->world) * Np;
     p.B.s_ki = 1;
     p.C = H;
     p.sC_mi = 1;
-    p.sC_ni = N;
-    p.sC_z1 = (long long)N * mcols;
+    p.sC_ni = Np;
+    p.sC_z1 = (long long)Np * mcols;
     ctx->gemm(p);
     // M[m](n, k) = sum_nu C[nu, nmin+n] H_k[nu, ml]       (2 n N mcols flops per aux function)
     GemmParams q;
@@ -70,13 +72,13 @@ void fill_block_dev(gwbse_ctx* ctx, int aux_offset, int aux_count, const double*
     q.N = mcols;
     q.Ki = N;
     q.Z1 = nb;
-    q.A.ptr = ctx->mos + (size_t)ctx->nmin * N;
-    q.A.s_ri = N;
+    q.A.ptr = ctx->mos + (size_t)ctx->nmin * Np;
+    q.A.s_ri = Np;
     q.A.s_ki = 1;
     q.B.ptr = H;
-    q.B.s_ri = N;
+    q.B.s_ri = Np;
     q.B.s_ki = 1;
-    q.B.s_z1 = (long long)N * mcols;
+    q.B.s_z1 = (long long)Np * mcols;
     q.sC_mi = 1;
     q.sC_z1 = ctx->ldx;
     if (sh) {
@@ -99,6 +101,16 @@ void mul_right_dev(gwbse_ctx* ctx, const double* R_dev, int ldr) {
   if (ctx->ldx == 0) return;
   GW_REQUIRE(ldr >= ctx->naux, "Shape mismatch in MultiplyRight");
   ensure_x2(ctx);
+  // R with an odd leading dimension (Naux is odd for most basis sets) or an unaligned base would force 8-byte
+  // copies for the B operand: re-pitch it to an even ld first (Naux^2 doubles, microseconds)
+  if ((ldr & 1) || (reinterpret_cast<uintptr_t>(R_dev) & 15)) {
+    const int ldp = round_up(ctx->naux, 2);
+    double* Rp = ctx->buf("mulright_Rp", (size_t)ldp * ctx->naux);
+    GW_CUDA(cudaMemcpy2DAsync(Rp, sizeof(double) * ldp, R_dev, sizeof(double) * ldr, sizeof(double) * ctx->naux,
+                              ctx->naux, cudaMemcpyDeviceToDevice, ctx->stream));
+    R_dev = Rp;
+    ldr = ldp;
+  }
   // X2 = X * R as one flat GEMM over all (m, n) rows (padding rows are zero and stay zero)
   GW_REQUIRE(ctx->ldx < (1LL << 31), "Mmn row count exceeds 2^31");
   GemmParams p;
@@ -194,8 +206,10 @@ int gwbse_mmn_set_mos(gwbse_ctx* ctx, const double* mos, int ldmos, int nbasis, 
   GW_CUDA(cudaStreamSynchronize(ctx->stream));
   if (ctx->mos) GW_CUDA(cudaFree(ctx->mos));
   ctx->mos = nullptr;
-  GW_CUDA(cudaMalloc(&ctx->mos, sizeof(double) * (size_t)nbasis * nmo));
-  GW_CUDA(copy2d_async(ctx->mos, sizeof(double) * nbasis, mos, sizeof(double) * ldmos, sizeof(double) * nbasis,
+  const int Np = round_up(nbasis, 2);  // even pitch: 16-byte aligned columns for the fill GEMMs
+  GW_CUDA(cudaMalloc(&ctx->mos, sizeof(double) * (size_t)Np * nmo));
+  GW_CUDA(cudaMemsetAsync(ctx->mos, 0, sizeof(double) * (size_t)Np * nmo, ctx->stream));
+  GW_CUDA(copy2d_async(ctx->mos, sizeof(double) * Np, mos, sizeof(double) * ldmos, sizeof(double) * nbasis,
                             nmo, cudaMemcpyHostToDevice, ctx->stream));
   GW_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->nbasis = nbasis;

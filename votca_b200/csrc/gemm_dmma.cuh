@@ -82,10 +82,17 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
 template <int ROWS, bool KMAJOR, int NT>
 __device__ __forceinline__ void stage_tile(double* s, const double* base, const GemmOperand& op,
                                            const long long* rowoff, int k0, int Ki, int tid) {
+  // generic path: row offsets come from the shared table every time.  Trip counts are compile-time constants and
+  // the loops are fully unrolled so that the copies can be scheduled between the DMMAs (operands with odd row
+  // strides - AO blocks with odd N, trial vectors with odd ct - can only use 8-byte copies).
   if (KMAJOR) {
     // s[r * LDK + k]
     if (op.vec == 2) {
-      for (int idx = tid; idx < ROWS * (GEMM_BK / 2); idx += NT) {
+      constexpr int TOTAL = ROWS * (GEMM_BK / 2);
+#pragma unroll
+      for (int c = 0; c < (TOTAL + NT - 1) / NT; ++c) {
+        const int idx = tid + c * NT;
+        if (TOTAL % NT != 0 && idx >= TOTAL) break;
         const int r = idx >> 3, k = (idx & 7) * 2;
         const long long off = rowoff[r];
         const int rem = Ki - (k0 + k);
@@ -94,7 +101,11 @@ __device__ __forceinline__ void stage_tile(double* s, const double* base, const 
         cp_async16(s + r * GEMM_LDK + k, src, bytes);
       }
     } else {
-      for (int idx = tid; idx < ROWS * GEMM_BK; idx += NT) {
+      constexpr int TOTAL = ROWS * GEMM_BK;
+#pragma unroll
+      for (int c = 0; c < (TOTAL + NT - 1) / NT; ++c) {
+        const int idx = tid + c * NT;
+        if (TOTAL % NT != 0 && idx >= TOTAL) break;
         const int r = idx >> 4, k = idx & 15;
         const long long off = rowoff[r];
         const int bytes = (off >= 0 && k0 + k < Ki) ? 8 : 0;
@@ -107,7 +118,11 @@ __device__ __forceinline__ void stage_tile(double* s, const double* base, const 
     constexpr int LD = ROWS + 4;
     if (op.vec == 2) {
       constexpr int VPR = ROWS / 2;
-      for (int idx = tid; idx < GEMM_BK * VPR; idx += NT) {
+      constexpr int TOTAL = GEMM_BK * VPR;
+#pragma unroll
+      for (int c = 0; c < (TOTAL + NT - 1) / NT; ++c) {
+        const int idx = tid + c * NT;
+        if (TOTAL % NT != 0 && idx >= TOTAL) break;
         const int k = idx / VPR, r = (idx % VPR) * 2;
         const long long off = rowoff[r];
         const bool kin = (k0 + k) < Ki;
@@ -116,7 +131,11 @@ __device__ __forceinline__ void stage_tile(double* s, const double* base, const 
         cp_async16(s + k * LD + r, src, bytes);
       }
     } else {
-      for (int idx = tid; idx < GEMM_BK * ROWS; idx += NT) {
+      constexpr int TOTAL = GEMM_BK * ROWS;
+#pragma unroll
+      for (int c = 0; c < (TOTAL + NT - 1) / NT; ++c) {
+        const int idx = tid + c * NT;
+        if (TOTAL % NT != 0 && idx >= TOTAL) break;
         const int k = idx / ROWS, r = idx % ROWS;
         const long long off = rowoff[r];
         const int bytes = (off >= 0 && (k0 + k) < Ki) ? 8 : 0;
