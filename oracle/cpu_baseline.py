@@ -42,6 +42,14 @@ def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
+def _fast_normal(rng, shape):
+    """Zero-mean unit-variance filler for the timing samples (uniform: the values do not matter, only the sizes)."""
+    a = rng.random(shape)
+    a -= 0.5
+    a *= 3.4641016151377544
+    return a
+
+
 def _best(fn, reps=2):
     best = 1e30
     for _ in range(reps):
@@ -69,9 +77,9 @@ def estimate(nbasis, naux, homo, counts, seed=7, sample_scale=1.0):
 
     # ---- Fill3cMO: per aux function Cn^T * ao3c[k] * Cm (libint2_calls.cc:632-641, openmp_cuda.cc:172-192)
     nk = max(2, int(6 * sample_scale))
-    Cn = rng.standard_normal((N, n))
-    Cm = rng.standard_normal((N, m))
-    ao = rng.standard_normal((nk, N, N))
+    Cn = _fast_normal(rng, (N, n))
+    Cm = _fast_normal(rng, (N, m))
+    ao = _fast_normal(rng, (nk, N, N))
 
     def fill():
         for k in range(nk):
@@ -79,9 +87,9 @@ def estimate(nbasis, naux, homo, counts, seed=7, sample_scale=1.0):
     stages["fill_3c"] = {"sample_s": _best(fill), "sample": f"{nk} of {naux} aux functions", "factor": naux / nk}
 
     # ---- MultiplyRightWithAuxMatrix: M[m] <- M[m] R for every m (threecenter.cc:54-65)
-    nm = max(2, int(4 * sample_scale))
-    M = rng.standard_normal((nm, n, naux))
-    R = rng.standard_normal((naux, naux))
+    nm = max(2, int(2 * sample_scale))
+    M = _fast_normal(rng, (nm, n, naux))
+    R = _fast_normal(rng, (naux, naux))
 
     def mulright():
         for i in range(nm):
@@ -91,8 +99,8 @@ def estimate(nbasis, naux, homo, counts, seed=7, sample_scale=1.0):
                                 "factor": m / nm * calls}
 
     # ---- RPA epsilon: sum over occupied levels of M^T diag(d) M (rpa.cc:75-140, openmp_cuda.cc:218-233)
-    nv = max(2, int(4 * sample_scale))
-    Mv = rng.standard_normal((nv, n_unocc, naux))
+    nv = max(2, int(2 * sample_scale))
+    Mv = _fast_normal(rng, (nv, n_unocc, naux))
     d = rng.uniform(0.5, 2.0, n_unocc)
     acc = np.zeros((naux, naux))
 
@@ -104,7 +112,7 @@ def estimate(nbasis, naux, homo, counts, seed=7, sample_scale=1.0):
                              "factor": n_occ / nv * calls}
 
     # ---- dense auxiliaries on naux x naux: eigh (ppm.cc:37, bse.cc:194, aomatrix.cc:56,73), inverse (ppm.cc:44)
-    A = rng.standard_normal((naux, naux))
+    A = _fast_normal(rng, (naux, naux))
     A = A @ A.T / naux + np.eye(naux)
     stages["sym_eig"] = {"sample_s": _best(lambda: np.linalg.eigh(A), 1), "sample": "one naux x naux eigh",
                          "factor": 2 + it + 1}
@@ -120,8 +128,8 @@ def estimate(nbasis, naux, homo, counts, seed=7, sample_scale=1.0):
     if lib is not None:
         # compiled loops, one OpenMP thread per (level, omega) request like the reference's per-level searches
         nl = min(8, q)
-        Ml = rng.standard_normal((nl, naux, n))
-        nreq = max(cores, int(2 * cores * sample_scale))
+        Ml = _fast_normal(rng, (nl, naux, n))
+        nreq = max(cores, int(16 * cores * sample_scale))
         lv = (np.arange(nreq) % nl).astype(np.int32)
         fr = rng.uniform(-1, 1, nreq)
         out = np.zeros(nreq)
@@ -145,7 +153,7 @@ def estimate(nbasis, naux, homo, counts, seed=7, sample_scale=1.0):
         stages["sigma_x"] = {"sample_s": _best(sigx), "sample": f"{nreq} of {q * (q + 1) // 2} level pairs",
                              "factor": q * (q + 1) / 2 / nreq}
     else:
-        Ma = rng.standard_normal((n, naux))
+        Ma = _fast_normal(rng, (n, naux))
 
         def sigc_one():
             s = 0.0
@@ -166,19 +174,19 @@ def estimate(nbasis, naux, homo, counts, seed=7, sample_scale=1.0):
 
     # ---- BSE matvec, reference formulation: every row of H rebuilt (bse_operator.cc:61-116)
     k = 20
-    Mc = rng.standard_normal((ct, naux))
-    Mvv = rng.standard_normal((vt, naux))
-    X = rng.standard_normal((B, k))
+    Mc = _fast_normal(rng, (ct, naux))
+    Mvv = _fast_normal(rng, (vt, naux))
+    X = _fast_normal(rng, (B, k))
     epsinv = rng.uniform(0.3, 1, naux)
-    nrows = max(2, int(8 * sample_scale))
+    nrows = max(2, int(32 * sample_scale))
 
     def bse_rows():
         T = Mc * epsinv[None, :]
         for _ in range(nrows):
             row = (T @ Mvv.T).reshape(-1, order="F")  # Hd row
             row @ X
-    nblk = max(1, int(2 * sample_scale))
-    Mb1 = rng.standard_normal((ct, naux))
+    nblk = max(1, int(8 * sample_scale))
+    Mb1 = _fast_normal(rng, (ct, naux))
 
     def bse_hx():
         for _ in range(nblk):
