@@ -419,7 +419,43 @@ def test_bse_operator_random(ctx, dims, chunk):
         ref = op.matmul(X)  # reference formulation (row-by-row rebuild of H)
         assert rel_frob(ref, ctx.bse_matmul(co, X)) < TOL, name
         assert rel_frob(op.diagonal(), ctx.bse_diagonal(co)) < TOL, name
-    ctx.set_option("bse_chunk_bytes", 1 << 30)
+    ctx.set_option("bse_chunk_bytes", 8 << 30)
+
+
+def test_properties_medium_size(ctx):
+    """Size-independent properties at a size the oracle does not reach in seconds (Naux = 640, 150 x 301 levels):
+    orthogonal MultiplyRight round trip, symmetry / definiteness of epsilon and Sigma_x, self-adjointness of the
+    BSE blocks for an (m,n)-symmetric tensor, linearity of the operator product."""
+    rng = np.random.default_rng(90)
+    naux, mtotal, ntotal, homo = 640, 150, 301, 49
+    tc = random_tc(rng, naux, mtotal, ntotal)
+    sym = 0.5 * (tc.M[:, :mtotal, :] + tc.M[:, :mtotal, :].transpose(1, 0, 2))
+    tc.M[:, :mtotal, :] = sym  # M[m][n] = M[n][m] inside the m window, as for real three-centre integrals
+    push(ctx, tc)
+    Q, _ = np.linalg.qr(rng.standard_normal((naux, naux)))
+    ctx.mmn_mul_right(Q)
+    assert rel_frob(tc.M @ Q, ctx.mmn_get_all()) < 1e-12
+    ctx.mmn_mul_right(Q.T)
+    assert rel_frob(tc.M, ctx.mmn_get_all()) < 1e-12
+    e = np.sort(np.concatenate([rng.uniform(-1.2, -0.3, homo + 1), rng.uniform(0.05, 2.5, ntotal - homo - 1)]))
+    eps = ctx.rpa_epsilon(0, 0.5, 1e-4, e, homo, 0, ntotal - 1)
+    assert np.abs(eps - eps.T).max() == 0.0
+    assert np.linalg.eigvalsh(eps).min() >= 1.0 - 1e-12  # eps_i(w) - 1 is a sum of weighted Gram matrices
+    sx = ctx.sigma_x(homo, 0, 0, mtotal - 1)
+    assert np.abs(sx - sx.T).max() < 1e-13 and np.linalg.eigvalsh(sx).max() <= 1e-12
+    vmin, cmax, k = 20, 119, 6
+    vt, ct = homo - vmin + 1, cmax - homo
+    Hqp = rng.standard_normal((vt + ct,) * 2)
+    Hqp = Hqp + Hqp.T
+    ctx.bse_configure(homo, 0, vmin, cmax, rng.uniform(0.3, 1.0, naux), Hqp)
+    X, Y = rng.standard_normal((vt * ct, k)), rng.standard_normal((vt * ct, k))
+    for name in ("singlet_tda", "triplet_tda", "singlet_btda_b", "hd2"):
+        co = OPS[name]
+        HX, HY = ctx.bse_matmul(co, X), ctx.bse_matmul(co, Y)
+        a, b = X.T @ HY, (Y.T @ HX).T
+        assert np.abs(a - b).max() < 1e-11 * max(1.0, np.abs(a).max()), name
+        HZ = ctx.bse_matmul(co, 2.0 * X - 3.0 * Y)
+        assert rel_frob(2.0 * HX - 3.0 * HY, HZ) < 1e-12, name
 
 
 def test_bse_operator_errors(ctx):

@@ -80,3 +80,64 @@ def test_shard_plan_pure_functions():
             for m in range(total):
                 r = api.gwbse_shard_owner(m, world)
                 assert 0 <= r < world and api.gwbse_shard_local_index(m, world) < counts[r]
+
+
+def _fill_worker(rank, world, port, out):
+    """Aux-sharded fill (gwbse_mmn_fill_begin/end): rank g contracts its aux share for all m, the exchange moves
+    segment [dest][chi_loc][m_loc][n] to rank dest - emulated with the oracle contraction and gloo."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import threecenter
+    from votca_b200._capi import capi
+    api = capi()
+    rng = np.random.default_rng(11)
+    N, naux, mtotal = 13, 11, 7
+    mos = rng.standard_normal((N, N))
+    ao = rng.standard_normal((naux, N, N))
+    ao = ao + ao.transpose(0, 2, 1)
+    ref = threecenter.TCMatrix(naux, 0, mtotal - 1, 0, N - 1)
+    ref.fill_3c_mo(ao, mos)
+    lo, hi = api.gwbse_shard_aux_begin(naux, rank, world), api.gwbse_shard_aux_begin(naux, rank + 1, world)
+    part = threecenter.TCMatrix(hi - lo, 0, mtotal - 1, 0, N - 1)
+    part.fill_3c_mo(ao[lo:hi], mos)  # all m, own aux functions: part.M[m, n, chi_loc]
+    mlmax = (mtotal + world - 1) // world
+    cnt_max = max(api.gwbse_shard_aux_begin(naux, r + 1, world) - api.gwbse_shard_aux_begin(naux, r, world)
+                  for r in range(world))
+    send = np.zeros((world, cnt_max, mlmax, N))
+    for m in range(mtotal):
+        send[api.gwbse_shard_owner(m, world), :hi - lo, api.gwbse_shard_local_index(m, world), :] = part.M[m].T
+    gathered = [torch.zeros(send.shape, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(gathered, torch.from_numpy(send))
+    # what this rank receives: from every source its segment [rank]
+    local = np.zeros((naux, mlmax, N))
+    for src in range(world):
+        slo, shi = api.gwbse_shard_aux_begin(naux, src, world), api.gwbse_shard_aux_begin(naux, src + 1, world)
+        local[slo:shi] = gathered[src].numpy()[rank, :shi - slo]
+    err = 0.0
+    for m in range(mtotal):
+        if api.gwbse_shard_owner(m, world) == rank:
+            err = max(err, np.abs(local[:, api.gwbse_shard_local_index(m, world), :].T - ref.M[m]).max())
+    out[rank] = err
+    dist.destroy_process_group()
+
+
+def test_aux_sharded_fill_plan_gloo():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_fill_worker, args=(world, port, out), nprocs=world, join=True)
+    assert len(out) == world and all(out[r] < 1e-12 for r in range(world))
+
+
+def test_aux_partition_pure_function():
+    from votca_b200._capi import capi
+    api = capi()
+    for world in (1, 2, 3, 8):
+        for naux in (1, 5, 104, 3177):
+            b = [api.gwbse_shard_aux_begin(naux, r, world) for r in range(world + 1)]
+            assert b[0] == 0 and b[-1] == naux and all(b[i] <= b[i + 1] for i in range(world))
+            sizes = [b[i + 1] - b[i] for i in range(world)]
+            assert max(sizes) - min(sizes) <= 1
