@@ -289,9 +289,13 @@ def solve_qp_grid_windowed(fqp, frequency0, left_limit, right_limit, gw_sc_itera
         if right_prev[1] * end[1] < 0.0:
             refine_and_store(right_prev[0], right_prev[1], end[0], end[1], diag.shells_explored + 1)
     if accepted:
-        return _argmax_first(accepted).omega, accepted, rejected, diag
+        best = _argmax_first(accepted)
+        diag.chosen_shell = int(round(abs(best.omega - center) / shell_width))  # qp_solver_utils.h:660
+        return best.omega, accepted, rejected, diag
     if rejected:
-        return _argmax_first(rejected).omega, accepted, rejected, diag
+        best = _argmax_first(rejected)
+        diag.chosen_shell = int(round(abs(best.omega - center) / shell_width))  # qp_solver_utils.h:682
+        return best.omega, accepted, rejected, diag
     return None, accepted, rejected, diag
 
 

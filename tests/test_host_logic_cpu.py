@@ -1,0 +1,173 @@
+"""CPU tests of the host-side QP root search: the known-answer cases of the reference's
+xtp/src/tests/test_qp_solver_utils.cc:87-316, run against BOTH restatements of qp_solver_utils.h -
+the C++ host layer that ships (votca_b200/host/qp_rootsearch.h, through a small g++-built harness, no GPU
+involved) and the oracle (oracle/qp_solver.py)."""
+import ctypes
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+import pytest
+
+from oracle import qp_solver as oq
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+KTOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def harness():
+    src = os.path.join(HERE, "host_harness", "qp_harness.cc")
+    out = os.path.join(HERE, "host_harness", "build", "libqp_harness.so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    subprocess.run(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-o", out, src], check=True)
+    lib = ctypes.CDLL(out)
+    d, l, i = ctypes.c_double, ctypes.c_long, ctypes.c_int
+    lib.qp_normalize.argtypes = [l, d, d, d, d, l, ctypes.c_void_p]
+    lib.qp_effective_shell_width.argtypes = [d, d, l]
+    lib.qp_effective_shell_width.restype = d
+    lib.qp_accept_root.argtypes = [d, d, d, d, d]
+    lib.qp_windowed.argtypes = [i, d, d, d, d, d, l, d, d, d, d, i, ctypes.c_void_p]
+    return lib
+
+
+@dataclass
+class LegacyOpt:
+    qp_grid_steps: int = 0
+    qp_grid_spacing: float = 0.0
+    qp_full_window_half_width: float = -1.0
+    qp_dense_spacing: float = -1.0
+    qp_adaptive_shell_width: float = -1.0
+    qp_adaptive_shell_count: int = 0
+
+
+def _normalize_cpp(lib, o):
+    out = np.zeros(6)
+    rc = lib.qp_normalize(o.qp_grid_steps, o.qp_grid_spacing, o.qp_full_window_half_width, o.qp_dense_spacing,
+                          o.qp_adaptive_shell_width, o.qp_adaptive_shell_count, out.ctypes.data)
+    assert rc == 0
+    return out
+
+
+def _normalize_py(o):
+    legacy = (oq.legacy_full_window_half_width(o), oq.legacy_adaptive_shell_width(o))
+    oq.normalize_grid_search_options(o)
+    return np.array([o.qp_full_window_half_width, o.qp_dense_spacing, o.qp_adaptive_shell_width,
+                     o.qp_adaptive_shell_count, *legacy])
+
+
+NORMALIZE_CASES = [
+    # (options, expected half width, dense spacing, shell width)      test_qp_solver_utils.cc:87-150
+    (dict(), 0.75, 0.002, 0.025),
+    (dict(qp_grid_steps=201, qp_grid_spacing=0.01), 1.0, 0.01, 2.0 / 49.0),
+    (dict(qp_grid_steps=201, qp_grid_spacing=0.01, qp_full_window_half_width=0.75, qp_dense_spacing=0.002,
+          qp_adaptive_shell_width=0.03), 0.75, 0.002, 0.03),
+]
+
+
+@pytest.mark.parametrize("kw,half,dense,shell", NORMALIZE_CASES)
+def test_normalize_grid_search_options(harness, kw, half, dense, shell):
+    for res in (_normalize_cpp(harness, LegacyOpt(**kw)), _normalize_py(LegacyOpt(**kw))):
+        assert res[0] == pytest.approx(half, rel=KTOL)
+        assert res[1] == pytest.approx(dense, rel=KTOL)
+        assert res[2] == pytest.approx(shell, rel=KTOL)
+        assert res[3] == 0
+    if kw.get("qp_grid_steps"):
+        for res in (_normalize_cpp(harness, LegacyOpt(**kw)), _normalize_py(LegacyOpt(**kw))):
+            assert res[4] == pytest.approx(1.0, rel=KTOL)          # (201 - 1) * 0.01 / 2
+            assert res[5] == pytest.approx(2.0 / 49.0, rel=KTOL)  # full width / (max(21, 201 / 4) - 1)
+
+
+def test_shell_count_overrides_shell_width(harness):
+    assert harness.qp_effective_shell_width(0.75, 0.03, 30) == pytest.approx(0.75 / 30.0, rel=KTOL)
+    o = oq.SolverOptions(qp_full_window_half_width=0.75, qp_adaptive_shell_width=0.03, qp_adaptive_shell_count=30)
+    assert oq.effective_adaptive_shell_width(o) == pytest.approx(0.75 / 30.0, rel=KTOL)
+
+
+@pytest.mark.parametrize("residual,Z,ok", [(1e-7, 0.8, True), (1e-3, 0.8, False), (1e-7, 0.01, False),
+                                           (1e-7, 2.0, False), (1e-7, -0.5, False)])
+def test_accept_root(harness, residual, Z, ok):
+    assert bool(harness.qp_accept_root(residual, Z, 1e-5, 0.05, 1.5)) is ok
+    cand = oq.RootCandidate(omega=0.12, residual=residual, deriv=-1.25, Z=Z, distance_to_ref=0.12)
+    assert oq.accept_root(cand, oq.SolverOptions(g_sc_limit=1e-5, min_accepted_Z=0.05, max_accepted_Z=1.5)) is ok
+
+
+class _Mock:
+    def __init__(self, kind, r1, r2=0.0):
+        self.kind, self.r1, self.r2 = kind, r1, r2
+
+    def value(self, w, *_):
+        if self.kind == 0:
+            return self.r1 - w
+        if self.kind == 1:
+            return w - self.r1
+        return (w - self.r1) * (w - self.r2)
+
+    def deriv(self, w):
+        return 1.0 if self.kind == 1 else -1.0
+
+
+def _windowed_cpp(lib, kind, r1, r2, left, right, half, brent):
+    out = np.zeros(10)
+    lib.qp_windowed(kind, r1, r2, 0.0, left, right, 1, 1e-8, half, 0.002, 0.05, int(brent), out.ctypes.data)
+    return dict(found=bool(out[0]), root=out[1], n_acc=int(out[2]), n_rej=int(out[3]), Z=out[4],
+                shells=int(out[5]), first_interval=int(out[6]), first_accepted=int(out[7]), chosen=int(out[8]),
+                intervals=int(out[9]))
+
+
+def _windowed_py(kind, r1, r2, left, right, half, brent):
+    opt = oq.SolverOptions(g_sc_limit=1e-8, qp_bisection_max_iter=200, qp_full_window_half_width=half,
+                           qp_dense_spacing=0.002, qp_adaptive_shell_width=0.05, qp_adaptive_shell_count=0)
+    root, acc, rej, d = oq.solve_qp_grid_windowed(_Mock(kind, r1, r2), 0.0, left, right, 1, opt, use_brent=brent)
+    return dict(found=root is not None, root=root, n_acc=len(acc), n_rej=len(rej),
+                Z=acc[0].Z if acc else (rej[0].Z if rej else 0.0), shells=d.shells_explored,
+                first_interval=d.first_interval_shell, first_accepted=d.first_accepted_shell, chosen=d.chosen_shell,
+                intervals=d.intervals_found)
+
+
+def _both(harness, *a):
+    return _windowed_cpp(harness, *a), _windowed_py(*a)
+
+
+def test_windowed_solver_simple_root_bisection(harness):
+    for r in _both(harness, 0, 0.23, 0.0, -0.5, 0.5, 0.5, False):
+        assert r["found"] and r["root"] == pytest.approx(0.23, rel=1e-6)
+        assert (r["n_acc"], r["n_rej"]) == (1, 0) and r["Z"] == pytest.approx(1.0, rel=KTOL)
+        assert (r["first_interval"], r["first_accepted"], r["chosen"], r["intervals"]) == (5, 5, 5, 1)
+        assert r["shells"] >= 5
+
+
+def test_windowed_solver_simple_root_brent(harness):
+    for r in _both(harness, 0, 0.23, 0.0, -0.5, 0.5, 0.5, True):
+        assert r["found"] and r["root"] == pytest.approx(0.23, rel=1e-10)
+        assert (r["n_acc"], r["n_rej"], r["intervals"]) == (1, 0, 1) and r["shells"] >= 5
+
+
+def test_windowed_solver_returns_nearest_accepted_root(harness):
+    for r in _both(harness, 2, 0.12, 0.62, -0.2, 0.8, 0.8, False):
+        assert r["found"] and r["root"] == pytest.approx(0.12, rel=1e-6)
+        assert (r["n_acc"], r["n_rej"]) == (2, 0) and r["intervals"] >= 2
+        assert r["first_accepted"] >= 0 and r["chosen"] >= 0
+
+
+def test_windowed_solver_returns_rejected_root_without_accepted_one(harness):
+    for r in _both(harness, 1, 0.23, 0.0, -0.5, 0.5, 0.5, False):
+        assert r["found"] and r["root"] == pytest.approx(0.23, rel=1e-6)
+        assert (r["n_acc"], r["n_rej"]) == (0, 1) and r["Z"] < 0.0
+        assert (r["first_interval"], r["first_accepted"], r["chosen"], r["intervals"]) == (5, -1, 5, 1)
+
+
+def test_host_and_oracle_agree(harness):
+    """Same root and the same shell bookkeeping from both restatements (the C++ search is the product, the Python
+    one the checker) for several window placements, including a pair of roots inside one shell interval that the
+    scan cannot see (no sign change between shell points)."""
+    for (r1, r2, left, right) in [(0.12, 0.62, -0.2, 0.8), (-0.31, 0.44, -0.6, 0.7), (0.06, 0.08, -0.3, 0.3)]:
+        a, b = _both(harness, 2, r1, r2, left, right, 0.8, False)
+        assert a["found"] == b["found"]
+        if a["found"]:
+            assert a["root"] == pytest.approx(b["root"], abs=1e-9)
+        else:
+            assert (r1, r2) == (0.06, 0.08)
+        for k in ("n_acc", "n_rej", "shells", "first_interval", "first_accepted", "chosen", "intervals"):
+            assert a[k] == b[k], k
