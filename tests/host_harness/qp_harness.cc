@@ -3,7 +3,9 @@
 // tests/test_host_logic_cpu.py through these C entry points.
 #include <cstring>
 
+#include "../../votca_b200/host/anderson_mixing.h"
 #include "../../votca_b200/host/qp_rootsearch.h"
+#include "../../votca_b200/host/quadrature.h"
 
 using namespace votca;
 using namespace votca::xtp;
@@ -106,6 +108,51 @@ int qp_windowed(int kind, double r1, double r2, double freq0, double left, doubl
   out[8] = (double)d.chosen_shell;
   out[9] = (double)d.intervals_found;
   return 0;
+}
+
+// Anderson mixing driven like test_anderson.cc:33-100: nsteps (input, output) pairs of length n; the mixed
+// vector of step s is written to mixed[s*n ..] and fed back as the next input when feed_back != 0
+int anderson_run(long order, double alpha, long n, long nsteps, const double* first_input, const double* outputs,
+                 double* mixed) {
+  Anderson mix;
+  mix.Configure(order, alpha);
+  VectorXd in(first_input, n);
+  for (long s = 0; s < nsteps; ++s) {
+    mix.UpdateInput(in);
+    mix.UpdateOutput(VectorXd(outputs + s * n, n));
+    VectorXd m = mix.MixHistory();
+    for (long i = 0; i < n; ++i) mixed[s * n + i] = m(i);
+    in = m;
+  }
+  return 0;
+}
+
+// test_newton_rapson.cc:31-52: f(x) = x^2 - c
+struct SquareMinus {
+  double c;
+  std::pair<double, double> operator()(double x) const { return {x * x - c, 2 * x}; }
+};
+int newton_sqrt(double c, double x0, long iterations, double tolerance, double* root) {
+  SquareMinus f{c};
+  NewtonRapson<SquareMinus> n(iterations, tolerance);
+  *root = n.FindRoot(f, x0);
+  return (int)n.getInfo();
+}
+
+// mapped quadrature points / weights of the CDA integration; returns the symmetry flag (or -1 on error)
+int quadrature_points(const char* scheme, long order, double* pts, double* wts) {
+  try {
+    std::vector<double> p, w;
+    bool sym = false;
+    mapped_gauss_legendre(scheme, order, p, w, sym);
+    for (long i = 0; i < order; ++i) {
+      pts[i] = p[i];
+      wts[i] = w[i];
+    }
+    return sym ? 1 : 0;
+  } catch (const std::exception&) {
+    return -1;
+  }
 }
 
 }  // extern "C"

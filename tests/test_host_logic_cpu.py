@@ -29,6 +29,9 @@ def harness():
     lib.qp_effective_shell_width.restype = d
     lib.qp_accept_root.argtypes = [d, d, d, d, d]
     lib.qp_windowed.argtypes = [i, d, d, d, d, d, l, d, d, d, d, i, ctypes.c_void_p]
+    lib.anderson_run.argtypes = [l, d, l, l, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    lib.newton_sqrt.argtypes = [d, d, l, d, ctypes.c_void_p]
+    lib.quadrature_points.argtypes = [ctypes.c_char_p, l, ctypes.c_void_p, ctypes.c_void_p]
     return lib
 
 
@@ -171,3 +174,84 @@ def test_host_and_oracle_agree(harness):
             assert (r1, r2) == (0.06, 0.08)
         for k in ("n_acc", "n_rej", "shells", "first_interval", "first_accepted", "chosen", "intervals"):
             assert a[k] == b[k], k
+
+
+# test_anderson.cc:33-100
+ANDERSON_IN1 = np.array([-0.580533, -0.535803, -0.476481, -0.380558, 0.0969526, 0.133036, 0.164243])
+ANDERSON_OUT = np.array([[-0.604342, -0.548675, -0.488088, -0.385654, 0.106193, 0.139172, 0.170433],
+                         [-0.605576, -0.549458, -0.488876, -0.385821, 0.106788, 0.139509, 0.170768],
+                         [-0.606242, -0.549887, -0.489296, -0.385898, 0.107162, 0.139718, 0.170977]])
+ANDERSON_REF = np.array([[-0.597199, -0.544813, -0.484606, -0.384126, 0.103421, 0.137331, 0.168576],
+                         [-0.606303, -0.549862, -0.489247, -0.385968, 0.10708, 0.139698, 0.170959],
+                         [-0.606242, -0.549888, -0.489296, -0.385897, 0.107163, 0.139718, 0.170977]])
+
+
+def _approx(a, ref, tol):  # Eigen isApprox: relative Frobenius
+    return np.linalg.norm(a - ref) <= tol * min(np.linalg.norm(a), np.linalg.norm(ref))
+
+
+def test_anderson_mixing_reference_vectors(harness):
+    """Linear step, 2nd- and 3rd-order Anderson steps of the reference's unit test, host C++ class and oracle."""
+    from oracle import gw as ogw
+    mixed = np.zeros((3, 7))
+    out = np.ascontiguousarray(ANDERSON_OUT)
+    harness.anderson_run(3, 0.7, 7, 3, ANDERSON_IN1.ctypes.data, out.ctypes.data, mixed.ctypes.data)
+    mix = ogw.Anderson(3, 0.7)
+    vin, py = ANDERSON_IN1.copy(), []
+    for s in range(3):
+        mix.update_input(vin)
+        mix.update_output(ANDERSON_OUT[s])
+        vin = mix.mix_history()
+        py.append(vin)
+    for s in range(3):
+        assert _approx(mixed[s], ANDERSON_REF[s], 1e-5), s
+        assert _approx(py[s], ANDERSON_REF[s], 1e-5), s
+        assert np.abs(mixed[s] - py[s]).max() < 1e-9
+
+
+def test_newton_rapson_reference_case(harness):
+    root = ctypes.c_double()
+    info = harness.newton_sqrt(612.0, 10.0, 50, 1e-9, ctypes.byref(root))
+    assert info == 0 and root.value == pytest.approx(24.738633753, rel=1e-9)
+
+    class F:
+        def value(self, x):
+            return x * x - 612.0
+
+        def deriv(self, x):
+            return 2.0 * x
+    x, ok = oq.newton_raphson(F(), 10.0, 50, 1e-9, 1.0)
+    assert ok and x == pytest.approx(24.738633753, rel=1e-9)
+
+
+# xtp/src/tests/DataFiles/gaussian_quadratures/{gauss_legendre,modified_gauss_legendre}.mm: integral of
+# exp(-x^2) with orders 8, 10, 12, 14, 16, 18, 20, 40, 100 (test_gaussian_quadratures.cc:36-110, tolerance 1e-10)
+QUAD_ORDERS = [8, 10, 12, 14, 16, 18, 20, 40, 100]
+QUAD_REF = {
+    "legendre": [1.798265329486247, 1.7635524479921414, 1.7755135781619735, 1.7715209261601161, 1.7726581320386712,
+                 1.7724628015402868, 1.7724077952532697, 1.772453824202762, 1.7724538509055152],
+    "modified_legendre": [1.7666951327337739, 1.7769696007269602, 1.7704741425269137, 1.773217660393972,
+                          1.772169769028222, 1.7725597110830396, 1.7724137859609552, 1.7724538549863016,
+                          1.7724538509055152],
+}
+
+
+@pytest.mark.parametrize("scheme", ["legendre", "modified_legendre"])
+def test_cda_quadratures_reference_integrals(harness, scheme):
+    """Gauss-Legendre points/weights (Newton iteration here, 50-digit tables in the reference) and their mapping to
+    the integration domain, for the C++ host layer and the oracle."""
+    from oracle import sigma as osig
+    got_cpp, got_py = [], []
+    for order in QUAD_ORDERS:
+        pts, wts = np.zeros(order), np.zeros(order)
+        sym = harness.quadrature_points(scheme.encode(), order, pts.ctypes.data, wts.ctypes.data)
+        assert sym == (1 if scheme == "modified_legendre" else 0)
+        got_cpp.append(float(np.sum(wts * (2.0 if sym else 1.0) * np.exp(-pts ** 2))))
+        s = osig.SigmaCDA.__new__(osig.SigmaCDA)
+        s.opt = osig.SigmaOptions(order=order, quadrature_scheme=scheme)
+        p, w, sy = s._quadrature()
+        got_py.append(float(np.sum(w * (2.0 if sy else 1.0) * np.exp(-p ** 2))))
+    ref = np.array(QUAD_REF[scheme])
+    assert _approx(np.array(got_cpp), ref, 1e-10)
+    assert _approx(np.array(got_py), ref, 1e-10)
+    assert harness.quadrature_points(b"laguerre", 8, None, None) == -1  # not available in this build: loud error

@@ -11,6 +11,7 @@
 #include <string>
 #include <vector>
 
+#include "quadrature.h"
 #include "rpa.h"
 
 namespace votca {
@@ -255,34 +256,6 @@ class Sigma_Exact : public Sigma_base {
   double ERPA_correlation_ = 0.0;
 };
 
-// Gauss-Legendre nodes/weights on [-1,1] by Newton iteration on P_n (the reference ships the same
-// numbers as 50-digit tables, gaussian_quadrature/gauss_legendre_quadrature.cc:28-561).
-inline void gauss_legendre(Index n, std::vector<double>& x, std::vector<double>& w) {
-  x.assign(n, 0.0);
-  w.assign(n, 0.0);
-  const double pi = 3.14159265358979323846;
-  for (Index i = 0; i < (n + 1) / 2; ++i) {
-    double z = std::cos(pi * (double(i) + 0.75) / (double(n) + 0.5));
-    double pp = 0.0;
-    for (int it = 0; it < 100; ++it) {
-      double p1 = 1.0, p2 = 0.0;
-      for (Index j = 0; j < n; ++j) {
-        const double p3 = p2;
-        p2 = p1;
-        p1 = ((2.0 * double(j) + 1.0) * z * p2 - double(j) * p3) / double(j + 1);
-      }
-      pp = double(n) * (z * p1 - p2) / (z * z - 1.0);
-      const double z1 = z;
-      z = z1 - p1 / pp;
-      if (std::abs(z - z1) < 1e-16) break;
-    }
-    x[i] = -z;
-    x[n - 1 - i] = z;
-    w[i] = 2.0 / ((1.0 - z * z) * pp * pp);
-    w[n - 1 - i] = w[i];
-  }
-}
-
 class Sigma_CDA : public Sigma_base {
  public:
   Sigma_CDA(TCMatrix_gwbse& Mmn, const RPA& rpa) : Sigma_base(Mmn, rpa) {}
@@ -293,27 +266,7 @@ class Sigma_CDA : public Sigma_base {
     if (dev.world() > 1) throw std::runtime_error("sigma_integrator=cda is single-GPU in this build");
     const Index n = Mmn_.auxsize();
     const size_t nn = static_cast<size_t>(n * n);
-    std::vector<double> gx, gw;
-    gauss_legendre(opt_.order, gx, gw);
-    const double halfpi = 0.5 * 3.14159265358979323846;
-    pts_.clear();
-    wts_.clear();
-    if (opt_.quadrature_scheme == "legendre") {
-      symmetry_ = false;
-      for (Index j = 0; j < opt_.order; ++j) {
-        pts_.push_back(std::tan(halfpi * gx[j]));
-        const double c = std::cos(halfpi * gx[j]);
-        wts_.push_back(gw[j] * halfpi / (c * c));
-      }
-    } else if (opt_.quadrature_scheme == "modified_legendre") {
-      symmetry_ = true;
-      for (Index j = 0; j < opt_.order; ++j) {
-        pts_.push_back(0.5 * (1.0 + gx[j]) / (1.0 - gx[j]));
-        wts_.push_back(gw[j] / ((1.0 - gx[j]) * (1.0 - gx[j])));
-      }
-    } else {
-      throw std::runtime_error("quadrature scheme '" + opt_.quadrature_scheme + "' is not available in this build");
-    }
+    mapped_gauss_legendre(opt_.quadrature_scheme, opt_.order, pts_, wts_, symmetry_);
     // kappa_0 = eps(0)^-1 - 1
     kzero_ = dev.alloc(nn);
     double* eps = rpa_.calculate_epsilon_r_dev(std::complex<double>(0.0, 0.0));
