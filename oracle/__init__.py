@@ -11,7 +11,11 @@ Parity pinning: every module below is checked against the reference's own
 MatrixMarket fixtures (xtp/src/tests/DataFiles/{threecenter_gwbse,rpa,
 sigma_exact,sigma_cda,sigma_ppm,gw,bse,bse_operator}) in
 `tests/test_oracle_golden.py` at the tolerances of the reference's unit tests.
-AO integrals for shells above p are *parity unpinned* (no reference fixture
-pins a d/f/g three-centre integral in the GW layout, SURVEY.md section 8c);
-they are validated by internal identities only.
+AO integrals: overlap, 2-centre and 3-centre Coulomb and dipole integrals are pinned on
+the reference's aomatrix/, aomatrix3d/ and threecenter_dft/ fixtures up to l = 6
+(contracted S/P/D/F overlap, G-shell dipoles, I-shell overlap / Coulomb and
+G x G | I three-centre integrals from the shipped "large_l" data, minus the one
+function per I shell that data is self-inconsistent in).  No fixture holds a d/f/g
+integral in the GW layout itself; that layout differs from the
+pinned one only by Pseudo_InvSqrt_GWBSE, which is pinned separately.
 """

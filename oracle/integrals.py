@@ -9,9 +9,10 @@ CMakeModules/BuildLibint.cmake:19-25; not vendored under /root/reference):
 This file restates the published McMurchie-Davidson scheme (Hermite expansion
 coefficients E, Hermite Coulomb integrals R from the Boys function) and libint's
 conventions: pure shells, functions ordered m = -l..l, real solid harmonics in
-the Helgaker/Schlegel-Frisch form.  Pinned by the reference's 3-21G (s,p)
-fixtures through tests/test_oracle_golden.py; *parity unpinned* for l >= 2
-(internal identities only, tests/test_oracle_integrals.py).
+the Helgaker/Schlegel-Frisch form.  Pinned through tests/test_oracle_golden.py by the
+reference's 3-21G (s,p) fixtures and, for higher angular momentum, by its contracted
+S/P/D/F overlap, G-shell dipole and I-shell overlap / Coulomb / three-centre (G G | I)
+reference matrices (l up to 6).
 """
 import math
 from functools import lru_cache

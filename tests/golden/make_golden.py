@@ -4,7 +4,8 @@
 Run in the build container only (needs /root/reference):
     python tests/golden/make_golden.py
 Sources: xtp/src/tests/DataFiles/{threecenter_gwbse,rpa,sigma_exact,sigma_cda,
-sigma_ppm,gw,bse,bse_operator}/*.mm (MatrixMarket, 6 significant digits),
+sigma_ppm,gw,bse,bse_operator}/*.mm (MatrixMarket, 6 significant digits), the AO
+integral references of aomatrix/, aomatrix3d/ and threecenter_dft/,
 molecule.xyz and 3-21G.xml (identical in all of these directories), and the
 inline vectors of test_sigma_*.cc, test_gw.cc, test_bse_operator.cc,
 test_rpa_h2p.cc.  The npz is what the GPU box sees; /root/reference does not
@@ -62,6 +63,20 @@ def main():
          2.40974, 2.42192, 2.42192, 2.46371, 2.85829, 2.8853, 2.8853, 2.90367, 2.90367, 2.92541, 2.94702,
          3.3382, 3.3382, 3.35102, 3.3566, 3.3566, 3.35835, 3.39617, 3.39617, 4.22882, 4.71607, 4.72233,
          4.72233, 4.76567, 16.5917, 17.0793, 17.093, 17.093, 17.1377])
+    # ---- AO integral fixtures (test_aomatrix.cc, test_aomatrix3d.cc, test_threecenter_dft.cc): the host-side
+    # producer of the Fill inputs; these pin the oracle's integrals for d...i shells
+    for d, files in (("aomatrix", ["overlap_ref", "coulomb_ref", "coulombinvsqrtgw_ref", "overlap_ref_contracted",
+                                   "overlap_ref_gi", "coulomb_ref_gi"]),
+                     ("aomatrix3d", ["dip_ref_large_0", "dip_ref_large_1", "dip_ref_large_2"]),
+                     ("threecenter_dft", ["Ref0", "Ref4", "RefList0", "RefList1", "RefList2", "RefList3"])):
+        for fn in files:
+            out[f"{d}/{fn}"] = mmio.read_matrix(os.path.join(REF, d, fn + ".mm"))
+    for name, path in (("contracted", "aomatrix/contracted.xml"), ("G", "aomatrix/G.xml"), ("I", "aomatrix/I.xml")):
+        out[f"basis/{name}.json"] = np.array(json.dumps(obasis.load_basisset(os.path.join(REF, path))))
+    for name, path in (("C", "aomatrix/C.xyz"), ("C2", "aomatrix/C2.xyz")):
+        elems, pos = obasis.read_xyz(os.path.join(REF, path))
+        out[f"molecule_{name}/elements"] = np.array(elems)
+        out[f"molecule_{name}/positions_bohr"] = pos
     np.savez_compressed(os.path.join(HERE, "votca_fixtures.npz"), **out)
     print("wrote", len(out), "arrays")
 

@@ -183,3 +183,77 @@ def test_bse(golden, factorised):
     b2 = obse.BSE(tc)
     b2.configure(_bse_options(nmax=1, qpmin=1, qpmax=15), rpa_e, golden["bse/Hqp_cut"])
     assert rel_frob(golden["bse/Hqp_extended"], b2.Hqp) < 1e-3
+
+
+# ---------------------------------------------------------------------------------------------------------
+# AO integrals (the host-side producer of the Fill inputs): test_aomatrix.cc, test_aomatrix3d.cc,
+# test_threecenter_dft.cc.  These pin the oracle's McMurchie-Davidson integrals beyond the s,p shells of 3-21G.
+# ---------------------------------------------------------------------------------------------------------
+def _basis(golden, name, mol):
+    import json
+
+    from oracle import basis as obasis
+    bs = json.loads(str(golden[f"basis/{name}.json"]))
+    bs = {el: [(int(l), [tuple(p) for p in prims]) for l, prims in shells] for el, shells in bs.items()}
+    return obasis.AOBasis(bs, [str(e) for e in golden[f"molecule_{mol}/elements"]],
+                          golden[f"molecule_{mol}/positions_bohr"])
+
+
+def _pseudo_invsqrt(V, etol=1e-7):
+    w, U = np.linalg.eigh(V)
+    d = np.where(w < etol, 0.0, 1.0 / np.sqrt(np.where(w < etol, 1.0, w)))
+    return (U * d) @ U.T
+
+
+# test_aomatrix.cc:42-122 (methane 3-21G: overlap 1e-4, Coulomb 1e-5, Pseudo_InvSqrt_GWBSE 1e-5)
+def test_aomatrix_methane(golden, methane):
+    from oracle import threecenter
+    assert rel_frob(golden["aomatrix/overlap_ref"], methane["S"]) < 1e-4
+    assert rel_frob(golden["aomatrix/coulomb_ref"], methane["V"]) < 1e-5
+    L, removed = threecenter.pseudo_invsqrt_gwbse(methane["S"], methane["V"], 1e-7)
+    assert removed == 0 and rel_frob(golden["aomatrix/coulombinvsqrtgw_ref"], L) < 1e-5
+
+
+# test_aomatrix.cc:125-149: single-centre overlap of contracted S, P, D, F shells
+def test_aomatrix_contracted_spdf(golden):
+    from oracle import integrals
+    assert rel_frob(golden["aomatrix/overlap_ref_contracted"], integrals.overlap(_basis(golden, "contracted", "C"))) < 1e-4
+
+
+# test_aomatrix3d.cc:91-123: dipole integrals between G shells on two carbon atoms 1 Angstrom apart
+def test_aomatrix3d_g_shell_dipoles(golden):
+    from oracle import integrals
+    D = integrals.dipole(_basis(golden, "G", "C2"))
+    for k in range(3):
+        assert rel_frob(golden[f"aomatrix3d/dip_ref_large_{k}"], D[k]) < 1e-4
+
+
+# test_threecenter_dft.cc:38-73: V^-1/2 (P|mu nu) for methane 3-21G, aux functions 0 and 4
+def test_threecenter_dft_small_basis(golden, methane):
+    Td = np.einsum("pq,qmn->pmn", _pseudo_invsqrt(methane["V"]), methane["ao3c"])
+    assert rel_frob(golden["threecenter_dft/Ref0"], Td[0]) < 1e-5
+    assert rel_frob(golden["threecenter_dft/Ref4"], Td[4]) < 1e-5
+
+
+# test_aomatrix.cc:175-236 and test_threecenter_dft.cc:76-115 ("large_l_test", shipped commented out): I shells
+# (l = 6) as aux functions, G shells (l = 4) as orbitals, two carbon atoms.  The shipped data is self-inconsistent
+# in ONE function per I shell - index 8 has a self-Coulomb of 0.659 where the other twelve m components have
+# 0.17746, and a self-overlap of 0.805 instead of 1 - which is presumably why the test is disabled; everything that
+# does not involve that function is a valid known answer and is pinned here at the test's own tolerance (1e-5).
+def test_large_l_integrals(golden):
+    from oracle import integrals
+    aux, dft = _basis(golden, "I", "C2"), _basis(golden, "G", "C2")
+    keep = [i for i in range(aux.size) if i % 13 != 8]
+    sub = np.ix_(keep, keep)
+    bad = golden["aomatrix/coulomb_ref_gi"]
+    assert abs(bad[8, 8] - 0.659) < 1e-3 and np.allclose(np.delete(np.diag(bad)[:13], 8), 0.17746, atol=1e-5)
+    S, V = integrals.overlap(aux), integrals.coulomb2c(aux)
+    assert np.allclose(np.diag(V), V[0, 0], rtol=1e-12)  # every m component of a shell has the same self-Coulomb
+    assert rel_frob(golden["aomatrix/overlap_ref_gi"][sub], S[sub]) < 1e-5
+    assert rel_frob(bad[sub], V[sub]) < 1e-5
+    # three-centre (P | mu nu) in the DFT layout V^-1/2 (P|mu nu): aux rows 1 and 3 do not couple to function 8
+    # (odd-m sine components), rows 0 and 12 do and inherit the defect of the shipped data
+    Td = np.einsum("pq,qmn->pmn", _pseudo_invsqrt(V), integrals.coulomb3c(aux, dft))
+    assert rel_frob(golden["threecenter_dft/RefList1"], Td[1]) < 1e-5
+    assert rel_frob(golden["threecenter_dft/RefList2"], Td[3]) < 1e-5
+    assert rel_frob(golden["threecenter_dft/RefList0"], Td[0]) > 1e-2  # documents the defect, not a parity claim
