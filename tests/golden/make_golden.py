@@ -77,6 +77,34 @@ def main():
         elems, pos = obasis.read_xyz(os.path.join(REF, path))
         out[f"molecule_{name}/elements"] = np.array(elems)
         out[f"molecule_{name}/positions_bohr"] = pos
+    # ---- integration-test checkpoints (xtp/src/tests/CMakeLists.txt:336-416): inputs and GW-BSE outputs of the
+    # reference's own `xtp_tools -e dftgwbse` runs on water, 3-21G + aux-def2-svp (neutral: G0W0 exact sigma,
+    # full BSE, 5 dynamical-screening iterations; neutral_tda: TDA, 5 states), read with oracle/orbfile.py
+    from oracle.orbfile import OrbFile
+    IT = os.path.join(REF, "xtp_tools_integration_tests")
+    for tag in ("neutral", "neutral_tda"):
+        f = OrbFile(os.path.join(IT, f"molecule_{tag}.orb"))
+        at = f.attrs("/QMdata")
+        for k in ("occupied_levels", "rpamin", "rpamax", "qpmin", "qpmax", "bse_vmin", "bse_cmax", "useTDA",
+                  "use_Hqp_offdiag", "ScaHFX"):
+            out[f"orb/{tag}/attr_{k}"] = np.array(at[k])
+        for name, path in (("mo_energies", "mos/eigenvalues"), ("mos", "mos/eigenvectors"),
+                           ("RPA_inputenergies", "RPA_inputenergies"), ("QPpert_energies", "QPpert_energies"),
+                           ("QPdiag_eigenvalues", "QPdiag/eigenvalues"), ("QPdiag_eigenvectors", "QPdiag/eigenvectors"),
+                           ("BSE_singlet_eigenvalues", "BSE_singlet/eigenvalues"),
+                           ("BSE_singlet_eigenvectors", "BSE_singlet/eigenvectors"),
+                           ("BSE_singlet_eigenvectors2", "BSE_singlet/eigenvectors2"),
+                           ("BSE_singlet_dynamic", "BSE_singlet_dynamic")):
+            out[f"orb/{tag}/{name}"] = f.read("/QMdata/" + path)
+        n = out[f"orb/{tag}/BSE_singlet_eigenvalues"].shape[0]
+        out[f"orb/{tag}/transition_dipoles"] = np.array(
+            [f.read(f"/QMdata/transition_dipoles/ind{i}").ravel() for i in range(n)])
+    elems, pos = obasis.read_xyz(os.path.join(IT, "molecule.xyz"))
+    out["molecule_water/elements"] = np.array(elems)
+    out["molecule_water/positions_bohr"] = pos
+    out["basis/water_3-21G.json"] = np.array(json.dumps(obasis.load_basisset(os.path.join(IT, "3-21G.xml"))))
+    auxbs = obasis.load_basisset("/root/reference/xtp/share/xtp/basis_sets/aux-def2-svp.xml")
+    out["basis/aux-def2-svp_OH.json"] = np.array(json.dumps({el: auxbs[el] for el in ("O", "H")}))
     np.savez_compressed(os.path.join(HERE, "votca_fixtures.npz"), **out)
     print("wrote", len(out), "arrays")
 

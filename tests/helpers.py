@@ -42,3 +42,33 @@ def methane_mmn(mos, mmax=16, nmax=16):
     tc = threecenter.TCMatrix(m["basis"].size, 0, mmax, 0, nmax)
     tc.fill_from_integrals(m["ao3c"], m["S"], m["V"], mos)
     return tc
+
+
+def _basis_from_golden(g, basis_key, mol):
+    bs = json.loads(str(g[basis_key]))
+    bs = {el: [(int(l), [tuple(p) for p in prims]) for l, prims in shells] for el, shells in bs.items()}
+    return obasis.AOBasis(bs, [str(e) for e in g[f"molecule_{mol}/elements"]], g[f"molecule_{mol}/positions_bohr"])
+
+
+@lru_cache(maxsize=None)
+def water_integrals():
+    """Water, 3-21G + aux-def2-svp (s,p,d,f aux shells): the system of the reference's dftgwbse integration tests."""
+    g = load_golden()
+    dft = _basis_from_golden(g, "basis/water_3-21G.json", "water")
+    aux = _basis_from_golden(g, "basis/aux-def2-svp_OH.json", "water")
+    return {"dft": dft, "aux": aux, "S": integrals.overlap(aux), "V": integrals.coulomb2c(aux),
+            "ao3c": integrals.coulomb3c(aux, dft), "dipole": integrals.dipole(dft), "S_dft": integrals.overlap(dft)}
+
+
+def orb_case(tag):
+    """Inputs and reference outputs of one integration-test checkpoint ('neutral' or 'neutral_tda')."""
+    g = load_golden()
+    c = {k.split("/", 2)[2]: g[k] for k in g if k.startswith(f"orb/{tag}/")}
+    c["homo"] = int(c["attr_occupied_levels"]) - 1
+    for k in ("rpamin", "rpamax", "qpmin", "qpmax", "bse_vmin", "bse_cmax"):
+        c[k] = int(c["attr_" + k])
+    c["useTDA"] = bool(c["attr_useTDA"])
+    c["use_Hqp_offdiag"] = bool(c["attr_use_Hqp_offdiag"])
+    V = c["QPdiag_eigenvectors"]
+    c["Hqp"] = V @ np.diag(c["QPdiag_eigenvalues"].ravel()) @ V.T  # QPdiag is the eigendecomposition of Hqp
+    return c

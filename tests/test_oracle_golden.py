@@ -257,3 +257,39 @@ def test_large_l_integrals(golden):
     assert rel_frob(golden["threecenter_dft/RefList1"], Td[1]) < 1e-5
     assert rel_frob(golden["threecenter_dft/RefList2"], Td[3]) < 1e-5
     assert rel_frob(golden["threecenter_dft/RefList0"], Td[0]) > 1e-2  # documents the defect, not a parity claim
+
+
+# ---------------------------------------------------------------------------------------------------------
+# End to end against the reference's own dftgwbse runs (integration-test checkpoints molecule_neutral.orb and
+# molecule_neutral_tda.orb, xtp/src/tests/CMakeLists.txt:336-416; the reference compares BSE_singlet/eigenvalues
+# at 1e-4 and transition dipoles at 1e-4).  From the checkpoint's MOs and Hqp (its QPdiag eigendecomposition;
+# Vxc is not stored, so the QP step itself cannot be replayed) the oracle rebuilds everything else: AO integrals
+# with d and f aux shells, Mmn in the GW layout, eps, the BSE operator, Davidson, transition dipoles and the
+# perturbative dynamical screening.
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["neutral", "neutral_tda"])
+def test_reference_checkpoint_bse_end_to_end(tag):
+    from oracle import threecenter
+    from tests.helpers import orb_case, water_integrals
+    w, c = water_integrals(), orb_case(tag)
+    C = c["mos"]
+    assert np.abs(C.T @ w["S_dft"] @ C - np.eye(C.shape[1])).max() < 1e-10  # own overlap vs the reference's MOs
+    tc = threecenter.TCMatrix(w["aux"].size, c["rpamin"], max(c["bse_cmax"], c["qpmax"]), c["rpamin"], c["rpamax"])
+    tc.fill_from_integrals(w["ao3c"], w["S"], w["V"], C)
+    assert np.abs(np.diag(c["Hqp"]) - c["QPpert_energies"].ravel()).max() < 1e-10
+    ref_e = c["BSE_singlet_eigenvalues"].ravel()
+    b = obse.BSE(tc, factorised=True)
+    b.configure(obse.BSEOptions(useTDA=c["useTDA"], homo=c["homo"], rpamin=c["rpamin"], rpamax=c["rpamax"],
+                                qpmin=c["qpmin"], qpmax=c["qpmax"], vmin=c["bse_vmin"], cmax=c["bse_cmax"],
+                                nmax=len(ref_e), use_Hqp_offdiag=c["use_Hqp_offdiag"], max_dyn_iter=5,
+                                dyn_tolerance=1e-5), c["RPA_inputenergies"].ravel(), c["Hqp"])
+    es = b.solve_singlets()
+    assert np.abs(es["eigenvalues"] - ref_e).max() < 1e-8
+    vt, ct = c["homo"] - c["bse_vmin"] + 1, c["bse_cmax"] - c["homo"]
+    inter = obse.free_transition_dipoles(w["dipole"], C, c["bse_vmin"], vt, c["homo"] + 1, ct)
+    td = obse.coupled_transition_dipoles(es, inter, ct, vt, c["useTDA"])
+    assert np.abs(np.abs(td) - np.abs(c["transition_dipoles"])).max() < 1e-8  # sign of an eigenvector is free
+    f_ref = obse.oscillator_strengths(c["transition_dipoles"], ref_e)
+    assert np.abs(obse.oscillator_strengths(td, es["eigenvalues"]) - f_ref).max() < 1e-8
+    dyn = b.perturbative_dynamical_screening(es, c["RPA_inputenergies"].ravel())
+    assert np.abs(dyn - c["BSE_singlet_dynamic"].ravel()).max() < 1e-8
