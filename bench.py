@@ -367,7 +367,7 @@ def main():
                      "kernel_share_of_step": gstats["ms"] / args.steps / ms_per_step},
         "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e,
     }
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:  # reported at N=1 only
         from oracle import cpu_baseline
         est = cpu_baseline.estimate(N, naux, homo, counts, sample_scale=24.0)
         line["cpu_baseline"] = {
