@@ -340,3 +340,68 @@ def dipole(basis):
                 D[k, sa.start:sa.start + sa.nfunc, sb.start:sb.start + sb.nfunc] = pb
                 D[k, sb.start:sb.start + sb.nfunc, sa.start:sa.start + sa.nfunc] = pb.T
     return D
+
+
+# ----------------------------------------------------------------------------
+# kinetic energy <mu| -1/2 nabla^2 |nu>  (AOKinetic, libint2 Operator::kinetic)
+# ----------------------------------------------------------------------------
+def kinetic(basis):
+    n = basis.size
+    T = np.zeros((n, n))
+    for i, sa in enumerate(basis.shells):
+        for sb in basis.shells[:i + 1]:
+            a = sa.exps[:, None]
+            b = sb.exps[None, :]
+            cc = sa.coefs[:, None] * sb.coefs[None, :]
+            p = a + b
+            AB = sa.center - sb.center
+            pref = cc * (math.pi / p) ** 1.5
+            E = [hermite_E(sa.l, sb.l + 2, a, b, AB[k]) for k in range(3)]
+
+            def s1(k, ia, jb):  # 1-D overlap without the sqrt(pi/p) factor; zero for negative powers
+                return E[k][ia][jb][0] if jb >= 0 else 0.0
+
+            def t1(k, ia, jb):  # 1-D kinetic integral acting on the ket
+                return (-2.0 * b * b * s1(k, ia, jb + 2) + b * (2 * jb + 1) * s1(k, ia, jb)
+                        - 0.5 * jb * (jb - 1) * s1(k, ia, jb - 2))
+
+            ca, cb = cart_components(sa.l), cart_components(sb.l)
+            blk = np.zeros((len(ca), len(cb)))
+            for ia, la in enumerate(ca):
+                for ib, lb in enumerate(cb):
+                    sx, sy, sz = (s1(k, la[k], lb[k]) for k in range(3))
+                    val = t1(0, la[0], lb[0]) * sy * sz + sx * t1(1, la[1], lb[1]) * sz + sx * sy * t1(2, la[2], lb[2])
+                    blk[ia, ib] = np.sum(pref * val)
+            pb = pure_transform(sa.l) @ blk @ pure_transform(sb.l).T
+            T[sa.start:sa.start + sa.nfunc, sb.start:sb.start + sb.nfunc] = pb
+            T[sb.start:sb.start + sb.nfunc, sa.start:sa.start + sa.nfunc] = pb.T
+    return T
+
+
+# ----------------------------------------------------------------------------
+# nuclear attraction sum_C -Z_C <mu| 1/|r - R_C| |nu>  (AOMultipole::FillPotential with the atoms' nuclear charges)
+# ----------------------------------------------------------------------------
+def nuclear_attraction(basis, charges, positions):
+    n = basis.size
+    V = np.zeros((n, n))
+    charges = np.asarray(charges, dtype=np.float64)
+    positions = np.asarray(positions, dtype=np.float64)
+    for i, sa in enumerate(basis.shells):
+        for sb in basis.shells[:i + 1]:
+            p, P, cc, pair = _hermite_pair(sa, sb)
+            L = sa.l + sb.l
+            ca, cb = cart_components(sa.l), cart_components(sb.l)
+            blk = np.zeros((len(ca), len(cb)))
+            for Z, C in zip(charges, positions):
+                R = hermite_R(L, p, P - C[None, :])
+                w = -Z * cc * 2.0 * math.pi / p
+                for ia in range(len(ca)):
+                    for ib in range(len(cb)):
+                        acc = 0.0
+                        for tuv, e in pair[ia][ib].items():
+                            acc = acc + e * R[tuv]
+                        blk[ia, ib] += np.sum(w * acc)
+            pb = pure_transform(sa.l) @ blk @ pure_transform(sb.l).T
+            V[sa.start:sa.start + sa.nfunc, sb.start:sb.start + sb.nfunc] = pb
+            V[sb.start:sb.start + sb.nfunc, sa.start:sa.start + sa.nfunc] = pb.T
+    return V

@@ -52,6 +52,12 @@ def main():
          0.902913584797742, 0.853352878674581, 0.853352727016914, 0.853352541699637, 0.79703468058566,
          0.797034577207669, 0.797034400395582, 0.787701833916331, 0.518976361745313, 0.518975064844033,
          0.518973712898761, 0.459286057710524])
+    out["inline/ppm_freq"] = np.array(  # test_ppm.cc:66-69
+        [19.4503, 12.2429, 10.2167, 10.2167, 10.2167, 17.0832, 12.7117, 12.7117, 12.7117, 10.9455, 10.9455, 10.9455,
+         11.1861, 9.60843, 9.60843, 9.60843, 9.61518])
+    out["inline/ppm_weight"] = np.array(  # test_ppm.cc:70-74
+        [3.59422e-05, 0.00121795, 0.00343632, 0.00343632, 0.00343632, 0.00394659, 0.012066, 0.012066, 0.012066,
+         0.0241118, 0.0241118, 0.0241118, 0.0286786, 0.11036, 0.11036, 0.11036, 0.191732])
     out["inline/rpa_update_dft"] = np.array([-0.5, -0.4, -0.3, -0.2, -0.2, -0.1, 0, 0.1, 0.2, 0.3])  # test_rpa.cc:47-57
     out["inline/rpa_update_gw"] = np.array([-0.15, -0.05, 0.05, 0.15, 0.45, 0.55, 0.65])
     out["inline/rpa_update_ref"] = np.array([-0.85, -0.15, -0.05, 0.05, 0.15, 0.45, 0.55, 0.65, 0.75, 0.85])
@@ -66,7 +72,8 @@ def main():
     # ---- AO integral fixtures (test_aomatrix.cc, test_aomatrix3d.cc, test_threecenter_dft.cc): the host-side
     # producer of the Fill inputs; these pin the oracle's integrals for d...i shells
     for d, files in (("aomatrix", ["overlap_ref", "coulomb_ref", "coulombinvsqrtgw_ref", "overlap_ref_contracted",
-                                   "overlap_ref_gi", "coulomb_ref_gi"]),
+                                   "overlap_ref_gi", "coulomb_ref_gi", "kinetic_ref", "kinetic_ref_gi"]),
+                     ("aopotential", ["esp_ref"]),
                      ("aomatrix3d", ["dip_ref_large_0", "dip_ref_large_1", "dip_ref_large_2"]),
                      ("threecenter_dft", ["Ref0", "Ref4", "RefList0", "RefList1", "RefList2", "RefList3"])):
         for fn in files:

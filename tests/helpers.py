@@ -72,3 +72,17 @@ def orb_case(tag):
     V = c["QPdiag_eigenvectors"]
     c["Hqp"] = V @ np.diag(c["QPdiag_eigenvalues"].ravel()) @ V.T  # QPdiag is the eigendecomposition of Hqp
     return c
+
+
+NUCLEAR_CHARGE = {"H": 1, "C": 6, "N": 7, "O": 8}
+
+
+@lru_cache(maxsize=None)
+def methane_core_hamiltonian_mos():
+    """'MOs' of test_ppm.cc:38-57: eigenvectors / eigenvalues of the AO core Hamiltonian T + V_nuc (ordinary, not
+    generalised, eigenproblem - the test only needs some orthonormal set with methane's symmetry)."""
+    g = load_golden()
+    m = methane_integrals()
+    Z = [NUCLEAR_CHARGE[str(e)] for e in g["molecule/elements"]]
+    H = integrals.kinetic(m["basis"]) + integrals.nuclear_attraction(m["basis"], Z, g["molecule/positions_bohr"])
+    return np.linalg.eigh(H)

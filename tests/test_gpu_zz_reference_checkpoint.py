@@ -43,3 +43,36 @@ def test_bse_matches_reference_checkpoint(tag):
     assert np.abs(np.abs(job.get("transition_dipoles").T) - np.abs(c["transition_dipoles"])).max() < 1e-5
     assert np.abs(job.get("BSE_singlet_dynamic").ravel() - c["BSE_singlet_dynamic"].ravel()).max() < 1e-5
     job.close()
+
+
+def test_ppm_parameters_match_reference_known_answer(golden, methane):
+    """test_ppm.cc:36-108 through the CUDA path: Mmn filled on the device from core-Hamiltonian orbitals, eps_r(0)
+    and eps_i(0.5) assembled and diagonalised / inverted on the device (ppm.cc:30-59), compared with the inline
+    plasmon-pole frequencies and weights of the reference test (1e-4)."""
+    from tests.helpers import methane_core_hamiltonian_mos, rel_frob
+    from votca_b200.api import Context
+    e, C = methane_core_hamiltonian_mos()
+    n = methane["basis"].size
+    ctx = Context(0)
+    try:
+        ctx.mmn_alloc(n, 0, 16, 0, 16)
+        ctx.mmn_set_mos(C)
+        ctx.mmn_fill_block(0, methane["ao3c"])
+        L, removed = ctx.pseudo_invsqrt(methane["S"], methane["V"], 5e-7)
+        assert removed == 0
+        ctx.mmn_mul_right(L)
+        w, phi = ctx.sym_eig(ctx.rpa_epsilon(1, 0.0, 1e-4, e, 4, 0, 16))
+        weight = 1.0 - 1.0 / w
+        eps_i = ctx.rpa_epsilon(0, 0.5, 1e-4, e, 4, 0, 16)
+        inv = ctx.inverse(phi.T @ eps_i @ phi)
+        freq = np.zeros(n)
+        for i in range(n):  # ppm.cc:47-57
+            if weight[i] < 1e-5:
+                weight[i], freq[i] = 0.0, 0.5
+            else:
+                nom = inv[i, i] - 1.0
+                freq[i] = np.sqrt(abs(-nom / (nom + weight[i]) * 0.25))
+        assert rel_frob(golden["inline/ppm_freq"], freq) < 1e-4
+        assert rel_frob(golden["inline/ppm_weight"], weight) < 1e-4
+    finally:
+        ctx.close()

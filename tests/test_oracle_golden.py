@@ -293,3 +293,32 @@ def test_reference_checkpoint_bse_end_to_end(tag):
     assert np.abs(obse.oscillator_strengths(td, es["eigenvalues"]) - f_ref).max() < 1e-8
     dyn = b.perturbative_dynamical_screening(es, c["RPA_inputenergies"].ravel())
     assert np.abs(dyn - c["BSE_singlet_dynamic"].ravel()).max() < 1e-8
+
+
+# test_aomatrix.cc:62-75 (kinetic, methane 3-21G, 1e-5), :226-235 (kinetic between G shells, shipped disabled),
+# test_aopotential.cc:45-56 (nuclear attraction, 1e-5)
+def test_kinetic_and_nuclear_attraction(golden, methane):
+    from oracle import integrals
+    from tests.helpers import NUCLEAR_CHARGE
+    assert rel_frob(golden["aomatrix/kinetic_ref"], integrals.kinetic(methane["basis"])) < 1e-5
+    assert rel_frob(golden["aomatrix/kinetic_ref_gi"], integrals.kinetic(_basis(golden, "G", "C2"))) < 1e-5
+    Z = [NUCLEAR_CHARGE[str(e)] for e in golden["molecule/elements"]]
+    V = integrals.nuclear_attraction(methane["basis"], Z, golden["molecule/positions_bohr"])
+    assert rel_frob(golden["aopotential/esp_ref"], V) < 1e-5
+
+
+# test_ppm.cc:36-108: plasmon-pole frequencies and weights for methane with core-Hamiltonian orbitals (1e-4)
+def test_ppm_parameters(golden, methane):
+    from oracle import threecenter
+    from tests.helpers import methane_core_hamiltonian_mos
+    e, C = methane_core_hamiltonian_mos()
+    tc = threecenter.TCMatrix(methane["basis"].size, 0, 16, 0, 16)
+    tc.fill_from_integrals(methane["ao3c"], methane["S"], methane["V"], C)
+    r = orpa.RPA(tc)
+    r.configure(4, 0, 16)
+    r.set_rpa_input_energies(e)
+    s = osig.create("ppm", tc, r)
+    s.configure(osig.SigmaOptions(homo=4, qpmin=0, qpmax=16, rpamin=0, rpamax=16, eta=1e-3))
+    s.prepare_screening()
+    assert rel_frob(golden["inline/ppm_freq"], s.ppm_freq) < 1e-4
+    assert rel_frob(golden["inline/ppm_weight"], s.ppm_weight) < 1e-4
