@@ -112,6 +112,14 @@ def main():
     out["basis/water_3-21G.json"] = np.array(json.dumps(obasis.load_basisset(os.path.join(IT, "3-21G.xml"))))
     auxbs = obasis.load_basisset("/root/reference/xtp/share/xtp/basis_sets/aux-def2-svp.xml")
     out["basis/aux-def2-svp_OH.json"] = np.array(json.dumps({el: auxbs[el] for el in ("O", "H")}))
+    # ---- BASELINE config 0 (methane, def2-svp + aux-def2-svp, geometry of xtp-tutorials/tools/dftgwbse_CH4):
+    # geometry and basis sets only; orbitals come from oracle/scf.py at test time ("tier R", own integrals)
+    elems, pos = obasis.read_xyz("/root/reference/xtp-tutorials/tools/dftgwbse_CH4/methane.xyz")
+    out["molecule_methane_tutorial/elements"] = np.array(elems)
+    out["molecule_methane_tutorial/positions_bohr"] = pos
+    for name in ("def2-svp", "aux-def2-svp"):
+        bs = obasis.load_basisset(f"/root/reference/xtp/share/xtp/basis_sets/{name}.xml")
+        out[f"basis/{name}_CH.json"] = np.array(json.dumps({el: bs[el] for el in ("C", "H")}))
     np.savez_compressed(os.path.join(HERE, "votca_fixtures.npz"), **out)
     print("wrote", len(out), "arrays")
 

@@ -86,3 +86,19 @@ def methane_core_hamiltonian_mos():
     Z = [NUCLEAR_CHARGE[str(e)] for e in g["molecule/elements"]]
     H = integrals.kinetic(m["basis"]) + integrals.nuclear_attraction(m["basis"], Z, g["molecule/positions_bohr"])
     return np.linalg.eigh(H)
+
+
+@lru_cache(maxsize=None)
+def methane_svp_case():
+    """BASELINE.json config 0 with own integrals ("tier R"): methane, def2-svp + aux-def2-svp (N = 34, Naux = 104,
+    homo = 4, default ranges q = 14), RI-RHF orbitals from oracle/scf.py; Vxc = HF exchange in the MO basis."""
+    from oracle import scf
+    g = load_golden()
+    dft = _basis_from_golden(g, "basis/def2-svp_CH.json", "methane_tutorial")
+    aux = _basis_from_golden(g, "basis/aux-def2-svp_CH.json", "methane_tutorial")
+    Z = [NUCLEAR_CHARGE[str(e)] for e in g["molecule_methane_tutorial/elements"]]
+    hf = scf.rhf_ri(dft, aux, Z, g["molecule_methane_tutorial/positions_bohr"], sum(Z))
+    homo = sum(Z) // 2 - 1
+    q = min(3 * homo + 1, dft.size - 1) + 1
+    return {"dft": dft, "aux": aux, "hf": hf, "homo": homo, "q": q, "S": integrals.overlap(aux),
+            "V": integrals.coulomb2c(aux), "ao3c": integrals.coulomb3c(aux, dft), "dipole": integrals.dipole(dft)}

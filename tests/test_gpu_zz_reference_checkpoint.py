@@ -76,3 +76,53 @@ def test_ppm_parameters_match_reference_known_answer(golden, methane):
         assert rel_frob(golden["inline/ppm_weight"], weight) < 1e-4
     finally:
         ctx.close()
+
+
+def test_config0_methane_svp_tier_r():
+    """BASELINE.json config 0 with own integrals: methane, def2-svp + aux-def2-svp (d shells in the orbital basis, d and
+    f in the aux basis), RI-RHF orbitals, default ranges (q = 14), G0W0(ppm) + full BSE singlets and triplets.
+    CUDA path against the oracle on identical inputs: QP and BSE energies 1e-6 Ha, oscillator strengths 1e-5."""
+    from oracle import gw as ogw
+    from oracle import threecenter
+    from tests.helpers import methane_svp_case
+    from votca_b200.api import Job
+    c = methane_svp_case()
+    N, q, homo = c["dft"].size, c["q"], c["homo"]
+    e, C = c["hf"]["energies"], c["hf"]["mos"]
+    vxc = c["hf"]["exchange_mo"][:q, :q]
+    vt, ct = homo + 1, q - homo - 1
+    inter = obse.free_transition_dipoles(c["dipole"], C, 0, vt, homo + 1, ct)
+    job = Job(0)
+    job.set_scalar("homo", homo)
+    job.set_array("mos", C)
+    job.set_array("mo_energies", e)
+    job.set_array("vxc", vxc)
+    job.set_ao3c(c["ao3c"])
+    job.set_array("aux_overlap", c["S"])
+    job.set_array("aux_coulomb", c["V"])
+    for ax, d in zip("xyz", inter):
+        job.set_array("dipole_" + ax, d)
+    job.set_options(tasks="gw,singlets,triplets", gw__mode="G0W0", gw__sigma_integrator="ppm", bse__exctotal=5,
+                    bse__useTDA=False)
+    job.run()
+    assert (job.scalar("qpmin"), job.scalar("qpmax"), job.scalar("bse_vmin"), job.scalar("bse_cmax")) == (0, q - 1, 0, q - 1)
+    tc = threecenter.TCMatrix(c["aux"].size, 0, q - 1, 0, N - 1)
+    tc.fill_from_integrals(c["ao3c"], c["S"], c["V"], C)
+    g = ogw.GW(tc, vxc, e)
+    g.configure(ogw.GWOptions(homo=homo, qpmin=0, qpmax=q - 1, rpamin=0, rpamax=N - 1, gw_sc_max_iterations=1,
+                              sigma_integration="ppm", g_sc_max_iterations=100))
+    g.calculate_gw_perturbation()
+    g.calculate_hqp()
+    assert np.abs(g.get_gwa_results() - job.get("QPpert_energies").ravel()).max() < 1e-6
+    b = obse.BSE(tc, factorised=True)
+    b.configure(obse.BSEOptions(useTDA=False, homo=homo, rpamin=0, rpamax=N - 1, qpmin=0, qpmax=q - 1, vmin=0,
+                                cmax=q - 1, nmax=5, use_Hqp_offdiag=False), g.rpa_input_energies(), g.get_hqp())
+    et = b.solve_triplets()
+    es = b.solve_singlets()
+    assert np.abs(es["eigenvalues"] - job.get("BSE_singlet_eigenvalues").ravel()).max() < 1e-6
+    assert np.abs(et["eigenvalues"] - job.get("BSE_triplet_eigenvalues").ravel()).max() < 1e-6
+    tdip = obse.coupled_transition_dipoles(es, inter, ct, vt, False)
+    f_ref = obse.oscillator_strengths(tdip, es["eigenvalues"])
+    # the lowest singlets are the three components of a T2 level: compare the sum over the shell
+    assert abs(f_ref.sum() - job.get("oscillator_strengths").sum()) < 1e-5
+    job.close()
