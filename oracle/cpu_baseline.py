@@ -19,19 +19,40 @@ CSRC = os.path.join(HERE, "csrc", "baseline_kernels.c")
 CLIB = os.path.join(HERE, "lib", "liboracle_baseline.so")
 
 
+def _cpu_signature():
+    """ISA of this host (the library is built with -march=native and must not travel between CPU generations)."""
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for line in fh:
+                if line.startswith("flags"):
+                    return str(hash(line.split(":", 1)[1].strip()) & 0xFFFFFFFF)
+    except OSError:
+        pass
+    return "unknown"
+
+
 def build_c_kernels():
     """gcc -O3 -march=native -fopenmp: compiled restatement of the reference's scalar Sigma loops."""
     os.makedirs(os.path.dirname(CLIB), exist_ok=True)
     subprocess.run(["gcc", "-O3", "-march=native", "-fopenmp", "-shared", "-fPIC", CSRC, "-o", CLIB, "-lm"],
                    check=True)
+    with open(CLIB + ".host", "w") as fh:
+        fh.write(_cpu_signature())
 
 
 def _clib():
-    if not os.path.exists(CLIB):
+    stale = True
+    try:
+        with open(CLIB + ".host") as fh:
+            stale = fh.read().strip() != _cpu_signature()
+    except OSError:
+        pass
+    if stale or not os.path.exists(CLIB):
         try:
-            build_c_kernels()
+            build_c_kernels()  # first use on this host (e.g. the GPU box): rebuild for its own ISA
         except Exception:
-            return None
+            if stale:
+                return None
     try:
         return ctypes.CDLL(CLIB)
     except OSError:
