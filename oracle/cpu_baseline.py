@@ -8,6 +8,7 @@ loop iterations (aux functions, m slices, occupied levels, sigma evaluations, BS
 true iteration count of the workload; the per-stage samples and factors are reported.
 """
 import ctypes
+import hashlib
 import os
 import subprocess
 import time
@@ -25,7 +26,7 @@ def _cpu_signature():
         with open("/proc/cpuinfo") as fh:
             for line in fh:
                 if line.startswith("flags"):
-                    return str(hash(line.split(":", 1)[1].strip()) & 0xFFFFFFFF)
+                    return hashlib.md5(line.split(":", 1)[1].strip().encode()).hexdigest()
     except OSError:
         pass
     return "unknown"
