@@ -1,0 +1,138 @@
+// CPU harness of the device AO-integral code: runs votca_b200/csrc/ao3c_core.cuh - the same source the sm_100a
+// kernel compiles - with one std::thread per lane and a std::barrier as the warp barrier.  Test infrastructure
+// only (tests/test_ao3c_core_cpu.py); built with -fsanitize=thread it checks the barrier placement.
+#include <barrier>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "../../votca_b200/csrc/ao3c_core.cuh"
+#include "../../votca_b200/csrc/ao3c_tables.h"
+
+using namespace gwbse::ao;
+
+namespace {
+
+struct Tables {
+  std::vector<double> boys, pure;
+  std::vector<uint8_t> tuv;
+  TableView view{};
+  Tables() {
+    boys = make_boys_table();
+    tuv = make_tuv_table();
+    int off = 0;
+    for (int l = 0; l <= LMAX_SHELL; ++l) {
+      view.pure_off[l] = off;
+      std::vector<double> T = make_pure_matrix(l);
+      pure.insert(pure.end(), T.begin(), T.end());
+      off += (int)T.size();
+    }
+    view.boys = boys.data();
+    view.tuv = tuv.data();
+    view.pure = pure.data();
+    view.boys_orders = BOYS_ORDERS;
+    view.boys_taylor = BOYS_TAYLOR;
+    view.herm1_stride = HERM1_STRIDE;
+    view.herm1_dim = LMAX_SHELL + 1;
+    view.boys_dx = BOYS_DX;
+    view.boys_xmax = BOYS_XMAX;
+  }
+};
+
+BasisView view_of(const HostBasis& b) {
+  BasisView v{};
+  v.nshell = b.nshell;
+  v.nfunc = b.nfunc;
+  v.l = b.l.data();
+  v.np = b.np.data();
+  v.prim0 = b.prim0.data();
+  v.func0 = b.func0.data();
+  v.center = b.center.data();
+  v.exps = b.exps.data();
+  v.coefs = b.coefs.data();
+  v.herm1 = b.herm1.data();
+  return v;
+}
+
+struct BarrierSync {
+  std::barrier<>* b;
+  void operator()() { b->arrive_and_wait(); }
+};
+struct NoSync {
+  void operator()() {}
+};
+
+}  // namespace
+
+extern "C" {
+
+// out[k][nu][mu] (aux function, N x N column-major) for all aux shells; nl lanes (1 = plain serial run)
+int ao3c_host(int nshell, const int* l, const int* nprim, const double* center, const double* exps, const double* coefs,
+              int nshell_aux, const int* l_aux, const int* nprim_aux, const double* center_aux, const double* exps_aux,
+              const double* coefs_aux, int nl, double* out) {
+  try {
+    static Tables tb;
+    HostBasis dft, aux;
+    dft.build(nshell, l, nprim, center, exps, coefs);
+    aux.build(nshell_aux, l_aux, nprim_aux, center_aux, exps_aux, coefs_aux);
+    const BasisView dv = view_of(dft), av = view_of(aux);
+    const long long N = dft.nfunc;
+    OutSpec spec{out, N * N, 1, N, 0, aux.nfunc, 1};
+    const int wsd = workspace_doubles(dft.lmax, dft.lmax, aux.lmax);
+    std::vector<double> ws((size_t)wsd + 8, -7.0e300);  // poisoned: stale reads show up in the result
+    if (nl <= 1) {
+      NoSync s;
+      for (int a = 0; a < dft.nshell; ++a)
+        for (int b = 0; b <= a; ++b)
+          for (int c = 0; c < aux.nshell; ++c) triple_block(dv, av, tb.view, a, b, c, ws.data(), 0, 1, s, spec, 1e-20);
+      return 0;
+    }
+    std::barrier<> bar(nl);
+    std::vector<std::thread> th;
+    for (int lane = 0; lane < nl; ++lane)
+      th.emplace_back([&, lane] {
+        BarrierSync s{&bar};
+        for (int a = 0; a < dft.nshell; ++a)
+          for (int b = 0; b <= a; ++b)
+            for (int c = 0; c < aux.nshell; ++c)
+              triple_block(dv, av, tb.view, a, b, c, ws.data(), lane, nl, s, spec, 1e-20);
+      });
+    for (auto& t : th) t.join();
+    return 0;
+  } catch (...) {
+    return 1;
+  }
+}
+
+// V[q][p] = (p | q) over one basis: unit partner
+int coulomb2c_host(int nshell, const int* l, const int* nprim, const double* center, const double* exps,
+                   const double* coefs, double* out) {
+  try {
+    static Tables tb;
+    HostBasis bs;
+    bs.build(nshell, l, nprim, center, exps, coefs);
+    const BasisView v = view_of(bs);
+    const long long N = bs.nfunc;
+    OutSpec spec{out, N, 1, 0, 0, bs.nfunc, 0};
+    std::vector<double> ws((size_t)workspace_doubles(bs.lmax, 0, bs.lmax) + 8, -7.0e300);
+    NoSync s;
+    for (int a = 0; a < bs.nshell; ++a)
+      for (int c = 0; c < bs.nshell; ++c) triple_block(v, v, tb.view, a, -1, c, ws.data(), 0, 1, s, spec, 1e-20);
+    return 0;
+  } catch (...) {
+    return 1;
+  }
+}
+
+int boys_host(int n, double x, double* out) {
+  static Tables tb;
+  *out = boys_one(tb.view, n, x);
+  return 0;
+}
+
+int pure_matrix_host(int l, double* out) {
+  std::vector<double> T = make_pure_matrix(l);
+  std::memcpy(out, T.data(), sizeof(double) * T.size());
+  return 0;
+}
+}

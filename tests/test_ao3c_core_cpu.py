@@ -1,0 +1,172 @@
+"""CPU tests of the device AO-integral code: votca_b200/csrc/ao3c_core.cuh is __host__ __device__
+and parameterised on the warp barrier, so the very source the sm_100a kernel compiles runs here through a g++-built
+harness (tests/host_harness/ao3c_host.cc) - serially, and with one thread per lane + std::barrier, the latter also
+under ThreadSanitizer (checks that every shared-scratch dependency crosses a barrier).  Compared with the oracle's
+McMurchie-Davidson integrals (oracle/integrals.py), which are pinned on the reference's fixtures up to l = 6.
+
+Replaces on the device: ComputeAO3cBlock (xtp/src/libxtp/libint2_calls.cc:544-593) and AOCoulomb::Fill
+(libint2_calls.cc:224-271)."""
+import ctypes
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import mpmath
+
+from oracle import basis as obasis
+from oracle import integrals
+from tests import helpers
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "host_harness", "ao3c_host.cc")
+BUILD = os.path.join(HERE, "host_harness", "build")
+
+
+def _build(name, extra):
+    os.makedirs(BUILD, exist_ok=True)
+    out = os.path.join(BUILD, name)
+    subprocess.run(["g++", "-std=c++20", "-fPIC", "-shared", "-pthread", "-o", out, SRC] + extra, check=True)
+    return out
+
+
+def _bind(path):
+    lib = ctypes.CDLL(path)
+    p, i = ctypes.c_void_p, ctypes.c_int
+    lib.ao3c_host.argtypes = [i, p, p, p, p, p, i, p, p, p, p, p, i, p]
+    lib.coulomb2c_host.argtypes = [i, p, p, p, p, p, p]
+    lib.boys_host.argtypes = [i, ctypes.c_double, p]
+    lib.pure_matrix_host.argtypes = [i, p]
+    return lib
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return _bind(_build("libao3c_host.so", ["-O2"]))
+
+
+def pack(ao):
+    """Flat shell arrays of an oracle AOBasis, the argument list of gwbse_basis_create."""
+    l = np.array([s.l for s in ao.shells], dtype=np.int32)
+    npr = np.array([len(s.exps) for s in ao.shells], dtype=np.int32)
+    cen = np.ascontiguousarray(np.array([s.center for s in ao.shells], dtype=np.float64))
+    ex = np.concatenate([s.exps for s in ao.shells]).astype(np.float64)
+    co = np.concatenate([s.coefs for s in ao.shells]).astype(np.float64)
+    return l, npr, cen, ex, co
+
+
+def _ptrs(arrs):
+    return [a.ctypes.data for a in arrs]
+
+
+def ao3c(lib, aux, dft, nl=1):
+    d, a = pack(dft), pack(aux)
+    out = np.full((aux.size, dft.size, dft.size), np.nan)
+    rc = lib.ao3c_host(len(d[0]), *_ptrs(d), len(a[0]), *_ptrs(a), nl, out.ctypes.data)
+    assert rc == 0
+    return out
+
+
+def coulomb2c(lib, ao):
+    a = pack(ao)
+    out = np.full((ao.size, ao.size), np.nan)
+    assert lib.coulomb2c_host(len(a[0]), *_ptrs(a), out.ctypes.data) == 0
+    return out
+
+
+def _golden_basis(name, mol):
+    g = helpers.load_golden()
+    bs = json.loads(str(g[f"basis/{name}.json"]))
+    bs = {el: [(int(l), [tuple(p) for p in prims]) for l, prims in shells] for el, shells in bs.items()}
+    return obasis.AOBasis(bs, [str(e) for e in g[f"molecule_{mol}/elements"]], g[f"molecule_{mol}/positions_bohr"])
+
+
+def relmax(ref, val):
+    return np.abs(ref - val).max() / np.abs(ref).max()
+
+
+def test_boys_function(lib):
+    out = ctypes.c_double()
+    worst = 0.0
+    rng = np.random.default_rng(3)
+    xs = np.concatenate([[0.0, 1e-12, 0.05, 0.049999, 35.94, 35.95, 35.96, 36.0, 60.0, 250.0, 4000.0],
+                         rng.uniform(0, 40, 200), rng.uniform(0, 1, 50)])
+    mpmath.mp.dps = 40  # scipy's hyp1f1 (the oracle's Boys function) is itself only good to 5e-13 at large x
+    for n in (0, 1, 2, 5, 8, 10, 14, 16):
+        for x in xs:
+            lib.boys_host(n, float(x), ctypes.byref(out))
+            ref = mpmath.hyp1f1(n + 0.5, n + 1.5, -mpmath.mpf(float(x))) / (2 * n + 1)
+            worst = max(worst, float(abs((mpmath.mpf(out.value) - ref) / ref)))
+    assert worst < 1e-14, worst
+
+
+def test_pure_matrices_match_oracle(lib):
+    for l in range(7):
+        T = np.zeros((2 * l + 1, (l + 1) * (l + 2) // 2))
+        lib.pure_matrix_host(l, T.ctypes.data)
+        assert np.abs(T - integrals.pure_transform(l)).max() < 1e-14
+
+
+def test_methane_321g_matches_oracle(lib):
+    m = helpers.methane_integrals()
+    got = ao3c(lib, m["basis"], m["basis"])
+    assert relmax(m["ao3c"], got) < 1e-12
+    assert relmax(m["V"], coulomb2c(lib, m["basis"])) < 1e-12
+
+
+def test_water_spdf_aux_matches_oracle(lib):
+    w = helpers.water_integrals()
+    got = ao3c(lib, w["aux"], w["dft"])
+    assert relmax(w["ao3c"], got) < 1e-12
+    assert np.abs(got - got.transpose(0, 2, 1)).max() == 0.0 or relmax(got, got.transpose(0, 2, 1)) < 1e-14
+    assert relmax(w["V"], coulomb2c(lib, w["aux"])) < 1e-12
+
+
+def test_methane_def2svp_tier_r_matches_oracle(lib):
+    c = helpers.methane_svp_case()  # d orbital shells, d/f aux shells
+    got = ao3c(lib, c["aux"], c["dft"])
+    assert relmax(c["ao3c"], got) < 1e-12
+    assert relmax(c["V"], coulomb2c(lib, c["aux"])) < 1e-12
+
+
+def test_lanes_with_barriers_equal_serial(lib):
+    w = helpers.water_integrals()
+    serial = ao3c(lib, w["aux"], w["dft"], nl=1)
+    for nl in (2, 5, 32):
+        assert np.array_equal(serial, ao3c(lib, w["aux"], w["dft"], nl=nl)), nl
+
+
+def test_g_orbitals_i_aux_large_l(lib):
+    """(G G | I): la = lb = 4, lc = 6, L = 14 - the extreme class the reference ships data for
+    (test_threecenter_dft.cc:76-115); oracle pinned there in test_oracle_golden.py::test_large_l_integrals."""
+    aux, dft = _golden_basis("I", "C2"), _golden_basis("G", "C2")
+    ref = integrals.coulomb3c(aux, dft)
+    assert relmax(ref, ao3c(lib, aux, dft)) < 1e-11
+    assert relmax(integrals.coulomb2c(aux), coulomb2c(lib, aux)) < 1e-11
+
+
+def test_thread_sanitizer_finds_no_race():
+    """Same source, 8 lanes on threads, under -fsanitize=thread: a missing barrier between two stages that share
+    scratch would be reported as a data race (TSan exits non-zero)."""
+    so = _build("libao3c_host_tsan.so", ["-O1", "-g", "-fsanitize=thread"])
+    m = helpers.methane_integrals()
+    d = pack(m["basis"])
+    np.savez(os.path.join(BUILD, "tsan_in.npz"), l=d[0], np_=d[1], cen=d[2], ex=d[3], co=d[4])
+    code = (
+        "import ctypes, numpy as np, sys\n"
+        f"z = np.load(r'{os.path.join(BUILD, 'tsan_in.npz')}')\n"
+        f"lib = ctypes.CDLL(r'{so}')\n"
+        "p, i = ctypes.c_void_p, ctypes.c_int\n"
+        "lib.ao3c_host.argtypes = [i, p, p, p, p, p, i, p, p, p, p, p, i, p]\n"
+        "a = [np.ascontiguousarray(z[k]) for k in ('l', 'np_', 'cen', 'ex', 'co')]\n"
+        "ns = len(a[0]); n = int((2 * a[0] + 1).sum())\n"
+        "out = np.zeros((n, n, n))\n"
+        "pt = [x.ctypes.data for x in a]\n"
+        "rc = lib.ao3c_host(ns, *pt, ns, *pt, 8, out.ctypes.data)\n"
+        "sys.exit(rc)\n")
+    tsan_rt = subprocess.run(["g++", "-print-file-name=libtsan.so"], capture_output=True, text=True).stdout.strip()
+    env = dict(os.environ, LD_PRELOAD=tsan_rt, TSAN_OPTIONS="exitcode=66 halt_on_error=1")
+    r = subprocess.run([os.sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
+    assert "WARNING: ThreadSanitizer" not in r.stderr, r.stderr[-3000:]
+    assert r.returncode == 0, (r.returncode, r.stderr[-3000:])

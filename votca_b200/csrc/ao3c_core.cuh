@@ -1,0 +1,294 @@
+// Three-centre Coulomb integrals (P | mu nu) over contracted real-solid-harmonic Gaussian shells: the work of
+// ComputeAO3cBlock (xtp/src/libxtp/libint2_calls.cc:544-593, libint2 Operator::coulomb, BraKet::xs_xx) and, with
+// a unit partner, of AOCoulomb::Fill (libint2_calls.cc:224-271, BraKet::xs_xs), restated for one warp per
+// (orbital shell pair, auxiliary shell).
+//
+// Scheme: McMurchie-Davidson.  Per primitive pair the 1-D Hermite coefficients E^{ab}_t of the three directions,
+// per primitive triple the Hermite Coulomb tensor R_{tuv} (Boys function from a grid + 8-term Taylor step, then
+// the level recursion R^n -> R^{n-1}), the auxiliary side folded in first (G), then the pair side; cartesian ->
+// pure transformation of the three indices at the end.  The 32 lanes split the entries of every stage; stages are
+// separated by a warp barrier.  The code is __host__ __device__ and parameterised on the barrier so the CPU
+// harness (tests/host_harness/ao3c_host.cc) runs the same source with std::barrier + one thread per lane
+// (ThreadSanitizer then checks the barrier placement).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define AO_HD __host__ __device__ __forceinline__
+#else
+#define AO_HD inline
+#endif
+
+namespace gwbse {
+namespace ao {
+
+struct BasisView {
+  int nshell, nfunc;
+  const int* l;
+  const int* np;
+  const int* prim0;
+  const int* func0;
+  const double* center;  // 3 per shell
+  const double* exps;
+  const double* coefs;
+  const double* herm1;  // HERM1 per primitive
+};
+
+struct TableView {
+  const double* boys;    // [points][orders]
+  const uint8_t* tuv;    // [nherm][4]
+  const double* pure;    // concatenated (2l+1) x ncart(l) matrices
+  int pure_off[8];
+  int boys_orders, boys_taylor, herm1_stride, herm1_dim;
+  double boys_dx, boys_xmax;
+};
+
+// where a block of integrals goes: element (aux function k, mu, nu) at
+//   base[(k - func_begin) * stride_k + mu * stride_mu + nu * stride_nu]   for func_begin <= k < func_end
+struct OutSpec {
+  double* base;
+  long long stride_k, stride_mu, stride_nu;
+  int func_begin, func_end;
+  int mirror;  // also write (k, nu, mu)
+};
+
+AO_HD int nc_of(int l) { return (l + 1) * (l + 2) / 2; }
+AO_HD int nh_of(int L) { return (L + 1) * (L + 2) * (L + 3) / 6; }
+AO_HD int hidx(int t, int u, int v) {
+  const int N = t + u + v, w = u + v;
+  return N * (N + 1) * (N + 2) / 6 + w * (w + 1) / 2 + v;
+}
+
+// doubles of scratch one warp needs for the class (la, lb, lc)
+AO_HD int workspace_doubles(int la, int lb, int lc) {
+  const int Lab = la + lb, L = Lab + lc;
+  const int nca = nc_of(la), ncb = nc_of(lb), ncc = nc_of(lc);
+  int r = 2 * nh_of(L);
+  const int tmp = (2 * la + 1) * ncb;
+  if (tmp > r) r = tmp;
+  return 3 * (la + 1) * (lb + 1) * (Lab + 1) + r + nh_of(Lab) * ncc + nca * ncb * ncc + (L + 1);
+}
+
+// F_n(x) for one order: Taylor step off the tabulated grid, or erf + upward recursion beyond it
+AO_HD double boys_one(const TableView& tb, int n, double x) {
+  if (x < tb.boys_xmax) {
+    const int j = (int)(x / tb.boys_dx + 0.5);
+    const double d = (double)j * tb.boys_dx - x;  // -(x - x_j)
+    const double* f = tb.boys + (long long)j * tb.boys_orders + n;
+    double term = 1.0, s = f[0];
+    for (int k = 1; k < tb.boys_taylor; ++k) {
+      term *= d / (double)k;
+      s += f[k] * term;
+    }
+    return s;
+  }
+  const double ex = exp(-x);
+  double f = 0.5 * sqrt(3.14159265358979323846 / x) * erf(sqrt(x));
+  const double inv2x = 0.5 / x;
+  for (int k = 0; k < n; ++k) f = ((2 * k + 1) * f - ex) * inv2x;
+  return f;
+}
+
+// sb < 0: unit partner (exponent 0, coefficient 1, s type, on the centre of sa) -> two-centre integrals (sc | sa)
+template <class Sync>
+AO_HD void triple_block(const BasisView& dft, const BasisView& aux, const TableView& tb, int sa, int sb, int sc,
+                        double* ws, int lane, int nl, Sync& sync, const OutSpec& out, double prim_threshold) {
+  const bool unit_b = sb < 0;
+  const int la = dft.l[sa], lb = unit_b ? 0 : dft.l[sb], lc = aux.l[sc];
+  const int Lab = la + lb, L = Lab + lc;
+  const int nca = nc_of(la), ncb = nc_of(lb), ncc = nc_of(lc);
+  const int npa = 2 * la + 1, npb = 2 * lb + 1, npc = 2 * lc + 1;
+  const int nhab = nh_of(Lab), nhL = nh_of(L);
+  const int T1 = Lab + 1, ej = (lb + 1) * T1;  // E[d][(i*(lb+1)+j)*T1 + t]
+  const int esz = (la + 1) * ej;
+
+  double* E = ws;
+  double* R = E + 3 * esz;
+  int rsz = 2 * nhL;
+  if (npa * ncb > rsz) rsz = npa * ncb;
+  double* G = R + rsz;
+  double* acc = G + nhab * ncc;
+  double* seed = acc + nca * ncb * ncc;
+  double* tmp = R;  // free after the primitive loops
+
+  const double Ax = dft.center[3 * sa], Ay = dft.center[3 * sa + 1], Az = dft.center[3 * sa + 2];
+  const int sbb = unit_b ? sa : sb;
+  const double Bx = dft.center[3 * sbb], By = dft.center[3 * sbb + 1], Bz = dft.center[3 * sbb + 2];
+  const double Cx = aux.center[3 * sc], Cy = aux.center[3 * sc + 1], Cz = aux.center[3 * sc + 2];
+  const double ABx = Ax - Bx, ABy = Ay - By, ABz = Az - Bz;
+  const double AB2 = ABx * ABx + ABy * ABy + ABz * ABz;
+  const int pa0 = dft.prim0[sa], npra = dft.np[sa];
+  const int pb0 = unit_b ? 0 : dft.prim0[sb], nprb = unit_b ? 1 : dft.np[sb];
+  const int pc0 = aux.prim0[sc], nprc = aux.np[sc];
+  const uint8_t* cart_a = tb.tuv + 4 * nh_of(la - 1);
+  const uint8_t* cart_b = tb.tuv + 4 * nh_of(lb - 1);
+  const uint8_t* cart_c = tb.tuv + 4 * nh_of(lc - 1);
+  const double sgn_c = (lc & 1) ? -1.0 : 1.0;  // (-1)^(tau+nu+phi): the aux Hermite indices have the parity of lc
+  const int H1 = tb.herm1_dim;
+
+  for (int i = lane; i < nca * ncb * ncc; i += nl) acc[i] = 0.0;
+  sync();
+
+  for (int ia = 0; ia < npra; ++ia) {
+    for (int ib = 0; ib < nprb; ++ib) {
+      const double a = dft.exps[pa0 + ia], b = unit_b ? 0.0 : dft.exps[pb0 + ib];
+      const double cab = dft.coefs[pa0 + ia] * (unit_b ? 1.0 : dft.coefs[pb0 + ib]);
+      const double p = a + b, mu = a * b / p;
+      if (fabs(cab) * exp(-mu * AB2) < prim_threshold) continue;  // same decision in every lane
+      const double inv2p = 0.5 / p;
+      const double Px = (a * Ax + b * Bx) / p, Py = (a * Ay + b * By) / p, Pz = (a * Az + b * Bz) / p;
+      // ---- E^{ab}: row i = 0 serially per direction, rows i > 0 from the row above --------------------------
+      for (int d = lane; d < 3; d += nl) {
+        const double Xab = d == 0 ? ABx : (d == 1 ? ABy : ABz);
+        const double Xpb = a / p * Xab;
+        double* Ed = E + d * esz;
+        Ed[0] = exp(-mu * Xab * Xab);
+        for (int j = 1; j <= lb; ++j) {
+          const double* src = Ed + (j - 1) * T1;
+          double* dst = Ed + j * T1;
+          for (int t = 0; t <= j; ++t) {
+            double v = 0.0;
+            if (t <= j - 1) v += Xpb * src[t];
+            if (t + 1 <= j - 1) v += (t + 1) * src[t + 1];
+            if (t >= 1) v += inv2p * src[t - 1];
+            dst[t] = v;
+          }
+        }
+      }
+      sync();
+      for (int i = 1; i <= la; ++i) {
+        const int nitem = 3 * (lb + 1) * T1;
+        for (int it = lane; it < nitem; it += nl) {
+          const int d = it / ((lb + 1) * T1), rem = it % ((lb + 1) * T1);
+          const int j = rem / T1, t = rem % T1;
+          if (t > i + j) continue;
+          const double Xab = d == 0 ? ABx : (d == 1 ? ABy : ABz);
+          const double Xpa = -b / p * Xab;
+          const double* src = E + d * esz + (i - 1) * ej + j * T1;
+          double v = 0.0;
+          if (t <= i + j - 1) v += Xpa * src[t];
+          if (t + 1 <= i + j - 1) v += (t + 1) * src[t + 1];
+          if (t >= 1) v += inv2p * src[t - 1];
+          E[d * esz + i * ej + j * T1 + t] = v;
+        }
+        sync();
+      }
+      for (int ic = 0; ic < nprc; ++ic) {
+        const double g = aux.exps[pc0 + ic];
+        const double alpha = p * g / (p + g);
+        const double X = Px - Cx, Y = Py - Cy, Z = Pz - Cz;
+        const double pref = cab * aux.coefs[pc0 + ic] * 34.986836655249725 / (p * g * sqrt(p + g));  // 2 pi^(5/2)
+        // ---- seeds (-2 alpha)^n F_n(alpha |PC|^2) ------------------------------------------------------------
+        const double xarg = alpha * (X * X + Y * Y + Z * Z);
+        for (int n = lane; n <= L; n += nl) {
+          double s = boys_one(tb, n, xarg);
+          for (int k = 0; k < n; ++k) s *= -2.0 * alpha;
+          seed[n] = s;
+        }
+        sync();
+        // ---- R^n_{tuv}, n = L .. 0, level n in buffer n & 1 -------------------------------------------------
+        for (int n = L; n >= 0; --n) {
+          double* cur = R + (n & 1) * nhL;
+          const double* prev = R + ((n + 1) & 1) * nhL;
+          const int cnt = nh_of(L - n);
+          for (int h = lane; h < cnt; h += nl) {
+            const int t = tb.tuv[4 * h], u = tb.tuv[4 * h + 1], v = tb.tuv[4 * h + 2];
+            double val;
+            if (h == 0) {
+              val = seed[n];
+            } else if (t > 0) {
+              val = X * prev[hidx(t - 1, u, v)];
+              if (t > 1) val += (t - 1) * prev[hidx(t - 2, u, v)];
+            } else if (u > 0) {
+              val = Y * prev[hidx(t, u - 1, v)];
+              if (u > 1) val += (u - 1) * prev[hidx(t, u - 2, v)];
+            } else {
+              val = Z * prev[hidx(t, u, v - 1)];
+              if (v > 1) val += (v - 1) * prev[hidx(t, u, v - 2)];
+            }
+            cur[h] = val;
+          }
+          sync();
+        }
+        // ---- G[h][c] = pref * sum_{tau nu phi} (-1)^(..) e_c R_{t+tau,u+nu,v+phi} ---------------------------
+        const double* e1 = aux.herm1 + (long long)(pc0 + ic) * tb.herm1_stride;
+        for (int it = lane; it < nhab * ncc; it += nl) {
+          const int h = it / ncc, c = it % ncc;
+          const int t = tb.tuv[4 * h], u = tb.tuv[4 * h + 1], v = tb.tuv[4 * h + 2];
+          const int cx = cart_c[4 * c], cy = cart_c[4 * c + 1], cz = cart_c[4 * c + 2];
+          double s = 0.0;
+          for (int tau = cx & 1; tau <= cx; tau += 2) {
+            const double ex = e1[cx * H1 + tau];
+            for (int nu = cy & 1; nu <= cy; nu += 2) {
+              const double exy = ex * e1[cy * H1 + nu];
+              for (int phi = cz & 1; phi <= cz; phi += 2)
+                s += exy * e1[cz * H1 + phi] * R[hidx(t + tau, u + nu, v + phi)];
+            }
+          }
+          G[it] = pref * sgn_c * s;
+        }
+        sync();
+        // ---- acc[a][b][c] += sum_{tuv} Ex Ey Ez G[tuv][c] ---------------------------------------------------
+        for (int it = lane; it < nca * ncb * ncc; it += nl) {
+          const int c = it % ncc, ab = it / ncc;
+          const int ja = ab / ncb, jb = ab % ncb;
+          const int ax = cart_a[4 * ja], ay = cart_a[4 * ja + 1], az = cart_a[4 * ja + 2];
+          const int bx = cart_b[4 * jb], by = cart_b[4 * jb + 1], bz = cart_b[4 * jb + 2];
+          const double* Ex = E + ax * ej + bx * T1;
+          const double* Ey = E + esz + ay * ej + by * T1;
+          const double* Ez = E + 2 * esz + az * ej + bz * T1;
+          double s = 0.0;
+          for (int t = 0; t <= ax + bx; ++t)
+            for (int u = 0; u <= ay + by; ++u) {
+              const double exy = Ex[t] * Ey[u];
+              for (int v = 0; v <= az + bz; ++v) s += exy * Ez[v] * G[hidx(t, u, v) * ncc + c];
+            }
+          acc[it] += s;
+        }
+        sync();
+      }
+    }
+  }
+
+  // ---- cartesian -> pure: aux index in place (one column per lane) ---------------------------------------------
+  const double* Tc = tb.pure + tb.pure_off[lc];
+  const double* Ta = tb.pure + tb.pure_off[la];
+  const double* Tb = tb.pure + tb.pure_off[lb];
+  for (int ab = lane; ab < nca * ncb; ab += nl) {
+    double col[28];
+    for (int c = 0; c < ncc; ++c) col[c] = acc[ab * ncc + c];
+    for (int m = 0; m < npc; ++m) {
+      double s = 0.0;
+      for (int c = 0; c < ncc; ++c) s += Tc[m * ncc + c] * col[c];
+      acc[ab * ncc + m] = s;
+    }
+  }
+  sync();
+  const int fa = dft.func0[sa], fb = unit_b ? 0 : dft.func0[sb], fc = aux.func0[sc];
+  for (int m = 0; m < npc; ++m) {
+    const int k = fc + m;
+    const bool wanted = k >= out.func_begin && k < out.func_end;  // same in every lane
+    if (!wanted) continue;
+    for (int it = lane; it < npa * ncb; it += nl) {
+      const int ma = it / ncb, jb = it % ncb;
+      double s = 0.0;
+      for (int ja = 0; ja < nca; ++ja) s += Ta[ma * nca + ja] * acc[(ja * ncb + jb) * ncc + m];
+      tmp[it] = s;
+    }
+    sync();
+    double* dst = out.base + (long long)(k - out.func_begin) * out.stride_k;
+    for (int it = lane; it < npa * npb; it += nl) {
+      const int mb = it / npa, ma = it % npa;  // ma fastest: consecutive lanes write consecutive mu
+      double s = 0.0;
+      for (int jb = 0; jb < ncb; ++jb) s += Tb[mb * ncb + jb] * tmp[ma * ncb + jb];
+      const long long mu = fa + ma, nu = fb + mb;
+      dst[mu * out.stride_mu + nu * out.stride_nu] = s;
+      if (out.mirror && sa != sb) dst[nu * out.stride_mu + mu * out.stride_nu] = s;
+    }
+    sync();
+  }
+}
+
+}  // namespace ao
+}  // namespace gwbse

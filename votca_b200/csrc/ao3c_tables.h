@@ -1,0 +1,163 @@
+// Host-side tables of the device AO-integral kernels (ao3c_core.cuh): Boys-function grid, cartesian -> pure
+// (real solid harmonic) matrices in libint's order m = -l..l, the (t,u,v) enumeration of Hermite indices and the
+// single-centre Hermite expansion of a primitive.  Plain C++ (no CUDA) so the CPU test harness
+// (tests/host_harness/ao3c_host.cc) builds the very same tables as capi_ao3c.cu.
+//
+// Conventions restated from the reference's integral provider: libint2 pure shells as built by
+// AOShell::LibintShell (xtp/src/libxtp/aoshell.cc:65-79, contr.pure = true), functions ordered m = -l..l
+// (aoshell.cc:116-133), cartesian components in libint's standard order (lx descending, then ly descending).
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <stdexcept>
+#include <vector>
+
+namespace gwbse {
+namespace ao {
+
+constexpr int LMAX_SHELL = 6;                       // i functions (libint is built with --with-max-am=6)
+constexpr int LMAX_TOTAL = 16;                      // la + lb + lc of one integral class
+constexpr int BOYS_TAYLOR = 8;                      // terms of the Taylor step off the grid
+constexpr int BOYS_ORDERS = LMAX_TOTAL + BOYS_TAYLOR;  // F_0 .. F_{ORDERS-1} tabulated
+constexpr double BOYS_DX = 0.1;
+constexpr int BOYS_POINTS = 361;                    // x = 0 .. 36
+constexpr double BOYS_XMAX = 35.95;                 // beyond: F_0 from erf + upward recursion
+constexpr int HERM1_STRIDE = (LMAX_SHELL + 1) * (LMAX_SHELL + 1);
+
+inline int ncart(int l) { return (l + 1) * (l + 2) / 2; }
+inline int nherm(int L) { return (L + 1) * (L + 2) * (L + 3) / 6; }
+
+// (t,u,v) of Hermite index h in the degree-major order hidx(t,u,v) = N(N+1)(N+2)/6 + (u+v)(u+v+1)/2 + v,
+// N = t+u+v.  The entries of degree l are the cartesian components of a shell in libint order.
+inline std::vector<uint8_t> make_tuv_table() {
+  std::vector<uint8_t> tab((size_t)nherm(LMAX_TOTAL) * 4, 0);
+  for (int N = 0; N <= LMAX_TOTAL; ++N)
+    for (int t = N; t >= 0; --t)
+      for (int u = N - t; u >= 0; --u) {
+        const int v = N - t - u;
+        const int h = N * (N + 1) * (N + 2) / 6 + (u + v) * (u + v + 1) / 2 + v;
+        tab[(size_t)h * 4 + 0] = (uint8_t)t;
+        tab[(size_t)h * 4 + 1] = (uint8_t)u;
+        tab[(size_t)h * 4 + 2] = (uint8_t)v;
+      }
+  return tab;
+}
+
+// F_n(x_j), x_j = j * BOYS_DX: highest order from the (all-positive) series
+//   F_n(x) = e^-x sum_k (2x)^k / ((2n+1)(2n+3)...(2n+2k+1)),
+// the lower ones by the downward recursion F_{n-1} = (2x F_n + e^-x) / (2n-1)  (stable).
+inline std::vector<double> make_boys_table() {
+  std::vector<double> tab((size_t)BOYS_POINTS * BOYS_ORDERS);
+  const int top = BOYS_ORDERS - 1;
+  for (int j = 0; j < BOYS_POINTS; ++j) {
+    const long double x = (long double)j * (long double)BOYS_DX;
+    const long double ex = std::exp(-x);
+    long double term = 1.0L / (2 * top + 1), sum = term;
+    for (int k = 1; k < 2000; ++k) {
+      term *= 2.0L * x / (2 * top + 2 * k + 1);
+      sum += term;
+      if (term < 1e-22L * sum) break;
+    }
+    long double f = ex * sum;
+    tab[(size_t)j * BOYS_ORDERS + top] = (double)f;
+    for (int n = top; n > 0; --n) {
+      f = (2.0L * x * f + ex) / (2 * n - 1);
+      tab[(size_t)j * BOYS_ORDERS + n - 1] = (double)f;
+    }
+  }
+  return tab;
+}
+
+inline double binom(int n, int k) {
+  if (n < 0 || k < 0 || k > n) return 0.0;
+  double r = 1.0;
+  for (int i = 1; i <= k; ++i) r = r * (n - k + i) / i;
+  return r;
+}
+inline double factorial(int n) {
+  double r = 1.0;
+  for (int i = 2; i <= n; ++i) r *= i;
+  return r;
+}
+
+// (2l+1) x ncart(l) row-major: real solid harmonics in Racah normalisation (Helgaker, Jorgensen, Olsen,
+// "Molecular Electronic-Structure Theory", eq. 6.4.47-6.4.50), the form libint2 generates for pure shells.
+inline std::vector<double> make_pure_matrix(int l) {
+  const int nc = ncart(l);
+  std::vector<double> T((size_t)(2 * l + 1) * nc, 0.0);
+  auto cidx = [&](int lx, int ly, int lz) { return (ly + lz) * (ly + lz + 1) / 2 + lz; };
+  for (int m = -l; m <= l; ++m) {
+    const int am = m < 0 ? -m : m;
+    const double norm = (1.0 / (std::pow(2.0, am) * factorial(l))) *
+                        std::sqrt(2.0 * factorial(l + am) * factorial(l - am) / (m == 0 ? 2.0 : 1.0));
+    const int vm2 = m >= 0 ? 0 : 1;  // 2 v_m
+    const int nv = (int)std::floor(am / 2.0 - vm2 / 2.0);
+    for (int t = 0; t <= (l - am) / 2; ++t)
+      for (int u = 0; u <= t; ++u)
+        for (int iv = 0; iv <= nv; ++iv) {
+          const int twov = 2 * iv + vm2;
+          const double c = (((t + iv) & 1) ? -1.0 : 1.0) * std::pow(0.25, t) * binom(l, t) * binom(l - t, am + t) *
+                           binom(t, u) * binom(am, twov);
+          const int lx = 2 * t + am - 2 * u - twov, ly = 2 * u + twov, lz = l - 2 * t - am;
+          if (lx < 0 || ly < 0 || lz < 0) continue;
+          T[(size_t)(m + l) * nc + cidx(lx, ly, lz)] += norm * c;
+        }
+  }
+  return T;
+}
+
+// x^i exp(-g x^2) = sum_t e[i][t] Lambda_t(x; g): the one-centre case of the McMurchie-Davidson recursion
+// (X_PA = 0).  Row-major (LMAX_SHELL+1)^2, zero where i - t is odd or t > i.
+inline void fill_herm1(double g, double* e) {
+  const int S = LMAX_SHELL + 1;
+  for (int k = 0; k < S * S; ++k) e[k] = 0.0;
+  e[0] = 1.0;
+  const double inv2g = 0.5 / g;
+  for (int i = 1; i < S; ++i)
+    for (int t = 0; t <= i; ++t) {
+      double v = 0.0;
+      if (t + 1 <= i - 1) v += (t + 1) * e[(i - 1) * S + t + 1];
+      if (t >= 1) v += inv2g * e[(i - 1) * S + t - 1];
+      e[i * S + t] = v;
+    }
+}
+
+// Flat description of a basis as the kernels read it (host copy; capi_ao3c.cu uploads the vectors).
+struct HostBasis {
+  int nshell = 0, nfunc = 0, nprim = 0, lmax = 0;
+  std::vector<int> l, np, prim0, func0;
+  std::vector<double> center, exps, coefs, herm1;
+
+  // coefs must already hold the primitive normalisation and VOTCA's shell norm (aoshell.cc:81-89)
+  void build(int nshell_, const int* l_, const int* nprim_, const double* center_, const double* exps_,
+             const double* coefs_) {
+    nshell = nshell_;
+    l.assign(l_, l_ + nshell);
+    np.assign(nprim_, nprim_ + nshell);
+    center.assign(center_, center_ + 3 * (size_t)nshell);
+    prim0.resize(nshell);
+    func0.resize(nshell);
+    nprim = 0;
+    nfunc = 0;
+    lmax = 0;
+    for (int s = 0; s < nshell; ++s) {
+      if (l[s] < 0 || l[s] > LMAX_SHELL) throw std::runtime_error("shell angular momentum outside 0..6");
+      if (np[s] < 1) throw std::runtime_error("shell without primitives");
+      prim0[s] = nprim;
+      func0[s] = nfunc;
+      nprim += np[s];
+      nfunc += 2 * l[s] + 1;
+      if (l[s] > lmax) lmax = l[s];
+    }
+    exps.assign(exps_, exps_ + nprim);
+    coefs.assign(coefs_, coefs_ + nprim);
+    herm1.resize((size_t)nprim * HERM1_STRIDE);
+    for (int p = 0; p < nprim; ++p) {
+      if (!(exps[p] > 0.0)) throw std::runtime_error("primitive exponent must be positive");
+      fill_herm1(exps[p], &herm1[(size_t)p * HERM1_STRIDE]);
+    }
+  }
+};
+
+}  // namespace ao
+}  // namespace gwbse
