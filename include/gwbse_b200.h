@@ -163,6 +163,32 @@ int gwbse_shard_aux_range(const gwbse_ctx* ctx, int rank, int* begin, int* end);
 int gwbse_shard_aux_begin(int naux, int rank, int world); /* share of rank r: [begin(r), begin(r+1)) */
 int gwbse_mmn_fill_begin(gwbse_ctx* ctx, int aux_sharded);
 int gwbse_mmn_fill_end(gwbse_ctx* ctx);
+/* ---- AO Coulomb integrals on the device ---------------- */
+/* A basis as AOBasis::Fill lays it out (xtp/src/libxtp/aobasis.cc:85-105): shells in atom order, functions
+ * appended shell by shell, pure (real solid harmonic) functions m = -l..l (aoshell.cc:65-79).  l[s] in 0..6,
+ * nprim[s] primitives per shell, centers: 3 doubles per shell (bohr); exps / coefs run over all primitives in
+ * shell order.  coefs must already contain libint's primitive normalisation and VOTCA's shell norm
+ * (AOShell::normalizeContraction, aoshell.cc:81-89) - i.e. the numbers the libint2::Shell holds. */
+typedef struct gwbse_basis gwbse_basis;
+int gwbse_basis_create(gwbse_ctx* ctx, int nshell, const int* l, const int* nprim, const double* centers,
+                       const double* exps, const double* coefs, gwbse_basis** out);
+int gwbse_basis_destroy(gwbse_ctx* ctx, gwbse_basis* basis);
+int gwbse_basis_size(const gwbse_basis* basis); /* number of functions */
+/* ComputeAO3cBlock (libint2_calls.cc:544-593; libint2 Operator::coulomb, BraKet::xs_xx) for the aux FUNCTIONS
+ * [aux_offset, aux_offset + aux_count): aux_count symmetric N x N matrices (P | mu nu), column-major,
+ * contiguous - exactly what gwbse_mmn_fill_block(_dev) consumes.  McMurchie-Davidson on the GPU, one warp per
+ * (orbital shell pair, aux shell).  The range need not respect shell boundaries. */
+int gwbse_ao3c_block_dev(gwbse_ctx* ctx, const gwbse_basis* aux, const gwbse_basis* dft, int aux_offset,
+                         int aux_count, double* out_dev);
+int gwbse_ao3c_block(gwbse_ctx* ctx, const gwbse_basis* aux, const gwbse_basis* dft, int aux_offset, int aux_count,
+                     double* out);
+/* AOCoulomb::Fill (libint2_calls.cc:224-271; BraKet::xs_xs): V(P, Q) = (P | Q), naux x naux to the host */
+int gwbse_ao_coulomb2c(gwbse_ctx* ctx, const gwbse_basis* aux, double* V, int ld);
+/* TCMatrix_gwbse::Fill3cMO (libint2_calls.cc:595-651) with the integral producer on the GPU: blocks of aux_block
+ * aux functions are computed into a device buffer and contracted from there (gwbse_mmn_fill_block_dev); no AO
+ * integral crosses PCIe.  Needs gwbse_mmn_alloc + gwbse_mmn_set_mos.  Multi-GPU: every rank produces and
+ * contracts its own share of the aux functions, then the all-to-all of gwbse_mmn_fill_end (collective). */
+int gwbse_mmn_fill_from_basis(gwbse_ctx* ctx, const gwbse_basis* aux, const gwbse_basis* dft, int aux_block);
 /* TCMatrix_gwbse::MultiplyRightWithAuxMatrix (threecenter.cc:54-65,
  * OpenMP_CUDA::MultiplyRight openmp_cuda.cc:131-150): M[m] <- M[m] * R      */
 int gwbse_mmn_mul_right(gwbse_ctx* ctx, const double* R, int ldr);

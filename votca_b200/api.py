@@ -169,6 +169,43 @@ class Context:
         R = fmat(R)
         self.call("gwbse_mmn_mul_right", ptr(R), R.shape[0])
 
+    # ---- AO Coulomb integrals on the device ----
+    def basis_create(self, l, nprim, centers, exps, coefs):
+        """Flat shell arrays (see gwbse_basis_create) -> opaque device basis handle."""
+        l = np.ascontiguousarray(l, dtype=np.int32)
+        nprim = np.ascontiguousarray(nprim, dtype=np.int32)
+        centers = np.ascontiguousarray(centers, dtype=np.float64)
+        exps = np.ascontiguousarray(exps, dtype=np.float64)
+        coefs = np.ascontiguousarray(coefs, dtype=np.float64)
+        if centers.shape != (len(l), 3) or len(nprim) != len(l) or len(exps) != nprim.sum() or len(coefs) != len(exps):
+            raise ValueError("inconsistent basis arrays")
+        h = ctypes.c_void_p()
+        self.call("gwbse_basis_create", len(l), ptr(l), ptr(nprim), ptr(centers), ptr(exps), ptr(coefs),
+                  ctypes.byref(h))
+        return h
+
+    def basis_destroy(self, basis):
+        self.call("gwbse_basis_destroy", basis)
+
+    def basis_size(self, basis):
+        return int(self.api.gwbse_basis_size(basis))
+
+    def ao3c_block(self, aux, dft, aux_offset, aux_count):
+        """(aux_count, N, N): the output of ComputeAO3cBlock for aux functions [aux_offset, aux_offset+aux_count)."""
+        n = self.basis_size(dft)
+        out = np.empty((aux_count, n, n), dtype=np.float64)
+        self.call("gwbse_ao3c_block", aux, dft, int(aux_offset), int(aux_count), ptr(out))
+        return out
+
+    def ao_coulomb2c(self, aux):
+        n = self.basis_size(aux)
+        out = np.empty((n, n), order="F")
+        self.call("gwbse_ao_coulomb2c", aux, ptr(out), n)
+        return out
+
+    def mmn_fill_from_basis(self, aux, dft, aux_block=64):
+        self.call("gwbse_mmn_fill_from_basis", aux, dft, int(aux_block))
+
     def mmn_get_slice(self, m):
         out = np.empty((self.ntotal, self.naux), order="F")
         self.call("gwbse_mmn_get_slice", m, ptr(out), self.ntotal)

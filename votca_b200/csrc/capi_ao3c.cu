@@ -1,0 +1,298 @@
+// C ABI, part 6: AO Coulomb integrals on the device.
+//   gwbse_ao3c_block(_dev)   replaces ComputeAO3cBlock          xtp/src/libxtp/libint2_calls.cc:544-593
+//   gwbse_ao_coulomb2c       replaces AOCoulomb::Fill           xtp/src/libxtp/libint2_calls.cc:224-271
+//   gwbse_mmn_fill_from_basis = TCMatrix_gwbse::Fill3cMO with the producer on the GPU (libint2_calls.cc:595-651):
+//                             the (P|mu nu) blocks are written straight into the buffer the contraction GEMMs
+//                             read; no AO integral crosses PCIe.
+// One warp per (orbital shell pair, auxiliary shell); launches are grouped by angular-momentum class (la >= lb, lc)
+// so that each class gets the shared-memory scratch - and therefore the occupancy - of its own size.  The
+// arithmetic is ao3c_core.cuh (shared with the CPU harness).
+#include <algorithm>
+#include <map>
+#include <memory>
+#include <vector>
+
+#include "../../include/gwbse_b200.h"
+#include "ao3c_core.cuh"
+#include "ao3c_tables.h"
+#include "context.cuh"
+
+using namespace gwbse;
+
+namespace {
+
+struct WarpBarrier {
+  __device__ __forceinline__ void operator()() const { __syncwarp(); }
+};
+
+__global__ void __launch_bounds__(256)
+    ao3c_kernel(ao::BasisView dft, ao::BasisView aux, ao::TableView tb, const int2* __restrict__ pairs,
+                long long npairs, const int* __restrict__ aux_shells, int naux_shells, ao::OutSpec out, int ws_doubles,
+                double prim_threshold) {
+  extern __shared__ double ao3c_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (w >= npairs * naux_shells) return;  // whole warps leave; the barriers below are warp-local
+  // consecutive warps share the shell pair (same E coefficients, neighbouring output rows)
+  const long long ip = w / naux_shells;
+  const int ic = (int)(w % naux_shells);
+  const int2 pr = pairs[ip];
+  WarpBarrier sync;
+  ao::triple_block(dft, aux, tb, pr.x, pr.y, aux_shells[ic], ao3c_smem + (size_t)warp * ws_doubles, lane, 32, sync, out,
+                   prim_threshold);
+}
+
+template <typename T>
+T* upload(const std::vector<T>& v) {
+  T* d = nullptr;
+  GW_CUDA(cudaMalloc(&d, std::max<size_t>(1, v.size()) * sizeof(T)));
+  if (!v.empty()) GW_CUDA(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return d;
+}
+
+// Boys grid, (t,u,v) table and cartesian -> pure matrices: built once per device
+struct DeviceTables {
+  double* boys = nullptr;
+  double* pure = nullptr;
+  uint8_t* tuv = nullptr;
+  ao::TableView view{};
+};
+std::map<int, DeviceTables>& table_store() {
+  static std::map<int, DeviceTables> s;
+  return s;
+}
+const ao::TableView& device_tables(int device) {
+  auto& store = table_store();
+  auto it = store.find(device);
+  if (it != store.end()) return it->second.view;
+  DeviceTables t;
+  t.boys = upload(ao::make_boys_table());
+  t.tuv = upload(ao::make_tuv_table());
+  std::vector<double> pure;
+  for (int l = 0; l <= ao::LMAX_SHELL; ++l) {
+    t.view.pure_off[l] = (int)pure.size();
+    const std::vector<double> T = ao::make_pure_matrix(l);
+    pure.insert(pure.end(), T.begin(), T.end());
+  }
+  t.pure = upload(pure);
+  t.view.boys = t.boys;
+  t.view.tuv = t.tuv;
+  t.view.pure = t.pure;
+  t.view.boys_orders = ao::BOYS_ORDERS;
+  t.view.boys_taylor = ao::BOYS_TAYLOR;
+  t.view.herm1_stride = ao::HERM1_STRIDE;
+  t.view.herm1_dim = ao::LMAX_SHELL + 1;
+  t.view.boys_dx = ao::BOYS_DX;
+  t.view.boys_xmax = ao::BOYS_XMAX;
+  return store.emplace(device, t).first->second.view;
+}
+
+}  // namespace
+
+// A basis set on the device, with the shell lists the launches need
+struct gwbse_basis {
+  int device = 0;
+  ao::HostBasis host;
+  ao::BasisView view{};
+  std::vector<void*> owned;
+  // shells of one angular momentum, ascending (a function range maps to a contiguous piece of each list)
+  std::vector<int> by_l[ao::LMAX_SHELL + 1];
+  int* by_l_dev[ao::LMAX_SHELL + 1] = {};
+  // shell pairs (x, y) with l_x >= l_y, every unordered pair once, grouped by (l_x, l_y)
+  struct PairClass {
+    int la, lb;
+    long long count;
+    int2* dev;
+  };
+  std::vector<PairClass> pair_classes;
+  // (x, -1): unit partner, grouped by l_x (two-centre integrals)
+  std::vector<PairClass> unit_classes;
+
+  ~gwbse_basis() {
+    for (void* p : owned) cudaFree(p);
+  }
+  template <typename T>
+  T* keep(T* p) {
+    owned.push_back(p);
+    return p;
+  }
+};
+
+namespace {
+
+void build_basis(gwbse_basis& b, int device) {
+  b.device = device;
+  const ao::HostBasis& h = b.host;
+  b.view.nshell = h.nshell;
+  b.view.nfunc = h.nfunc;
+  b.view.l = b.keep(upload(h.l));
+  b.view.np = b.keep(upload(h.np));
+  b.view.prim0 = b.keep(upload(h.prim0));
+  b.view.func0 = b.keep(upload(h.func0));
+  b.view.center = b.keep(upload(h.center));
+  b.view.exps = b.keep(upload(h.exps));
+  b.view.coefs = b.keep(upload(h.coefs));
+  b.view.herm1 = b.keep(upload(h.herm1));
+  for (int s = 0; s < h.nshell; ++s) b.by_l[h.l[s]].push_back(s);
+  for (int l = 0; l <= ao::LMAX_SHELL; ++l) b.by_l_dev[l] = b.keep(upload(b.by_l[l]));
+  std::map<std::pair<int, int>, std::vector<int2>> groups;
+  std::map<int, std::vector<int2>> units;
+  for (int s = 0; s < h.nshell; ++s) {
+    units[h.l[s]].push_back(make_int2(s, -1));
+    for (int t = 0; t <= s; ++t) {
+      const bool swap = h.l[t] > h.l[s];
+      const int x = swap ? t : s, y = swap ? s : t;
+      groups[{h.l[x], h.l[y]}].push_back(make_int2(x, y));
+    }
+  }
+  // heaviest classes first: the long-running warps start early
+  for (auto it = groups.rbegin(); it != groups.rend(); ++it)
+    b.pair_classes.push_back({it->first.first, it->first.second, (long long)it->second.size(), b.keep(upload(it->second))});
+  for (auto it = units.rbegin(); it != units.rend(); ++it)
+    b.unit_classes.push_back({it->first, 0, (long long)it->second.size(), b.keep(upload(it->second))});
+}
+
+// all (pair class) x (aux l) launches for the aux shells overlapping functions [f0, f1)
+void launch_classes(gwbse_ctx* ctx, const gwbse_basis& orb, const std::vector<gwbse_basis::PairClass>& classes,
+                    const gwbse_basis& aux, int f0, int f1, const ao::OutSpec& out) {
+  GW_REQUIRE(orb.device == ctx->device && aux.device == ctx->device, "basis belongs to another device");
+  GW_REQUIRE(f0 >= 0 && f1 <= aux.host.nfunc && f0 <= f1, "aux function range out of bounds");
+  if (f0 == f1) return;
+  const ao::TableView& tb = device_tables(ctx->device);
+  // shells [s0, s1) overlap the function range
+  const std::vector<int>& fn0 = aux.host.func0;
+  int s0 = int(std::upper_bound(fn0.begin(), fn0.end(), f0) - fn0.begin()) - 1;
+  int s1 = int(std::lower_bound(fn0.begin(), fn0.end(), f1) - fn0.begin());
+  int smem_limit = 0;
+  GW_CUDA(cudaDeviceGetAttribute(&smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+  static int smem_set = -1;
+  if (smem_set != smem_limit) {
+    GW_CUDA(cudaFuncSetAttribute(ao3c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit));
+    smem_set = smem_limit;
+  }
+  for (int lc = ao::LMAX_SHELL; lc >= 0; --lc) {
+    const std::vector<int>& list = aux.by_l[lc];
+    const int i0 = int(std::lower_bound(list.begin(), list.end(), s0) - list.begin());
+    const int i1 = int(std::lower_bound(list.begin(), list.end(), s1) - list.begin());
+    if (i1 <= i0) continue;
+    for (const auto& pc : classes) {
+      GW_REQUIRE(pc.la + pc.lb + lc <= ao::LMAX_TOTAL, "angular momentum class beyond the Boys table");
+      const int wsd = ao::workspace_doubles(pc.la, pc.lb, lc);
+      const size_t per_warp = sizeof(double) * (size_t)wsd;
+      int wpc = 8;
+      // aim at >= 4 resident CTAs per SM where the class is small enough, never exceed the opt-in limit
+      while (wpc > 1 && per_warp * wpc > (size_t)smem_limit / 4) wpc >>= 1;
+      while (wpc > 1 && per_warp * wpc > (size_t)smem_limit) wpc >>= 1;
+      GW_REQUIRE(per_warp * wpc <= (size_t)smem_limit, "integral class does not fit into shared memory");
+      const long long warps = pc.count * (long long)(i1 - i0);
+      const long long blocks = (warps + wpc - 1) / wpc;
+      GW_REQUIRE(blocks < (1LL << 31), "too many shell triples for one launch; use smaller aux blocks");
+      ao3c_kernel<<<(unsigned)blocks, wpc * 32, per_warp * wpc, ctx->stream>>>(
+          orb.view, aux.view, tb, pc.dev, pc.count, aux.by_l_dev[lc] + i0, i1 - i0, out, wsd, 1e-20);
+      GW_CUDA(cudaGetLastError());
+      ctx->launches++;
+    }
+  }
+}
+
+void ao3c_block_dev(gwbse_ctx* ctx, const gwbse_basis* aux, const gwbse_basis* dft, int aux_offset, int aux_count,
+                    double* out_dev) {
+  GW_REQUIRE(aux && dft && out_dev, "null argument");
+  const long long N = dft->host.nfunc;
+  ao::OutSpec out{out_dev, N * N, 1, N, aux_offset, aux_offset + aux_count, 1};
+  launch_classes(ctx, *dft, dft->pair_classes, *aux, aux_offset, aux_offset + aux_count, out);
+}
+
+}  // namespace
+
+extern "C" {
+
+int gwbse_basis_create(gwbse_ctx* ctx, int nshell, const int* l, const int* nprim, const double* centers,
+                       const double* exps, const double* coefs, gwbse_basis** out) {
+  GW_API_BEGIN(ctx)
+  GW_REQUIRE(out && l && nprim && centers && exps && coefs && nshell > 0, "invalid basis description");
+  std::unique_ptr<gwbse_basis> b(new gwbse_basis);
+  b->host.build(nshell, l, nprim, centers, exps, coefs);
+  build_basis(*b, ctx->device);
+  *out = b.release();
+  GW_API_END(ctx)
+}
+
+int gwbse_basis_destroy(gwbse_ctx* ctx, gwbse_basis* basis) {
+  GW_API_BEGIN(ctx)
+  GW_CUDA(cudaStreamSynchronize(ctx->stream));
+  delete basis;
+  GW_API_END(ctx)
+}
+
+int gwbse_basis_size(const gwbse_basis* basis) { return basis ? basis->host.nfunc : -1; }
+
+int gwbse_ao3c_block_dev(gwbse_ctx* ctx, const gwbse_basis* aux, const gwbse_basis* dft, int aux_offset,
+                         int aux_count, double* out_dev) {
+  GW_API_BEGIN(ctx)
+  GW_PROF(ctx, "ao3c_block");
+  ao3c_block_dev(ctx, aux, dft, aux_offset, aux_count, out_dev);
+  GW_API_END(ctx)
+}
+
+int gwbse_ao3c_block(gwbse_ctx* ctx, const gwbse_basis* aux, const gwbse_basis* dft, int aux_offset, int aux_count,
+                     double* out) {
+  GW_API_BEGIN(ctx)
+  GW_PROF(ctx, "ao3c_block_d2h");
+  GW_REQUIRE(aux && dft && out, "null argument");
+  const size_t n = (size_t)dft->host.nfunc * dft->host.nfunc * (size_t)std::max(aux_count, 0);
+  if (n == 0) return 0;
+  double* d = ctx->buf("ao3c_out", n);
+  ao3c_block_dev(ctx, aux, dft, aux_offset, aux_count, d);
+  GW_CUDA(cudaMemcpyAsync(out, d, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  GW_CUDA(cudaStreamSynchronize(ctx->stream));
+  GW_API_END(ctx)
+}
+
+int gwbse_ao_coulomb2c(gwbse_ctx* ctx, const gwbse_basis* aux, double* V, int ld) {
+  GW_API_BEGIN(ctx)
+  GW_PROF(ctx, "ao_coulomb2c");
+  GW_REQUIRE(aux && V, "null argument");
+  const int n = aux->host.nfunc;
+  GW_REQUIRE(ld >= n, "leading dimension too small");
+  double* d = ctx->buf("ao2c_out", (size_t)n * n);
+  // element (k | mu) at d[k * n + mu]; the unit partner contributes no index
+  ao::OutSpec out{d, (long long)n, 1, 0, 0, n, 0};
+  launch_classes(ctx, *aux, aux->unit_classes, *aux, 0, n, out);
+  GW_CUDA(copy2d_async(V, sizeof(double) * ld, d, sizeof(double) * n, sizeof(double) * n, n, cudaMemcpyDeviceToHost,
+                       ctx->stream));
+  GW_CUDA(cudaStreamSynchronize(ctx->stream));
+  GW_API_END(ctx)
+}
+
+int gwbse_mmn_fill_from_basis(gwbse_ctx* ctx, const gwbse_basis* aux, const gwbse_basis* dft, int aux_block) {
+  GW_API_BEGIN(ctx)
+  GW_REQUIRE(aux && dft, "null argument");
+  GW_REQUIRE(ctx->X != nullptr, "Mmn not allocated (gwbse_mmn_alloc)");
+  GW_REQUIRE(aux->host.nfunc == ctx->naux, "aux basis does not match the Mmn tensor");
+  GW_REQUIRE(dft->host.nfunc == ctx->nbasis, "orbital basis does not match the MO coefficients (gwbse_mmn_set_mos)");
+  if (aux_block < 1) aux_block = 64;
+  const size_t per = (size_t)ctx->nbasis * ctx->nbasis;
+  // keep one block below 4 GiB
+  aux_block = (int)std::max<size_t>(1, std::min<size_t>(aux_block, ((size_t)1 << 29) / std::max<size_t>(per, 1)));
+  if (gwbse_mmn_fill_begin(ctx, ctx->world > 1 ? 1 : 0)) return 1;
+  int lo = 0, hi = ctx->naux;
+  if (ctx->world > 1) {
+    lo = ctx->aux_begin(ctx->rank);
+    hi = ctx->aux_begin(ctx->rank + 1);
+  }
+  double* blk = ctx->buf("ao3c_block", per * aux_block);
+  for (int a0 = lo; a0 < hi; a0 += aux_block) {
+    const int cnt = std::min(aux_block, hi - a0);
+    {
+      GW_PROF(ctx, "ao3c_block");
+      ao3c_block_dev(ctx, aux, dft, a0, cnt, blk);
+    }
+    // same stream: the contraction GEMMs of this block run after its integrals, the next block's integrals after them
+    if (gwbse_mmn_fill_block_dev(ctx, a0, cnt, blk)) return 1;
+  }
+  if (gwbse_mmn_fill_end(ctx)) return 1;
+  GW_API_END(ctx)
+}
+
+}  // extern "C"
