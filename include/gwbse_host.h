@@ -49,6 +49,12 @@ int gwbse_job_set_ao3c_dev(gwbse_job* job, long nbasis, long naux, const double*
  * data holds aux functions [first_aux, first_aux + count) (host memory, or device memory with on_device = 1). */
 int gwbse_job_set_ao3c_partial(gwbse_job* job, long nbasis, long naux, long first_aux, long count, const double* data,
                                int on_device);
+/* AO integrals produced on the GPU instead of "ao3c" (gwbse_b200.h: gwbse_basis_create, gwbse_ao3c_block_dev,
+ * gwbse_ao_coulomb2c - the device stand-ins for ComputeAO3cBlock / AOCoulomb::Fill, libint2_calls.cc:544-593,
+ * 224-271): which = "dft" or "aux", arguments as gwbse_basis_create.  Used when both are set and no ao3c array or
+ * callback is; "aux_overlap" is still an input, "aux_coulomb" becomes optional (computed on the device). */
+int gwbse_job_set_basis(gwbse_job* job, const char* which, int nshell, const int* l, const int* nprim,
+                        const double* centers, const double* exps, const double* coefs);
 /* the kernel-library context of this job (gwbse_b200.h), e.g. for gwbse_gemm_stats / timers */
 void* gwbse_job_ctx(gwbse_job* job);
 

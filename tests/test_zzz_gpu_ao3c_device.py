@@ -77,6 +77,37 @@ def test_ao3c_large_l_g_orbitals_i_aux(ctx):
     ctx.basis_destroy(dft)
 
 
+def test_job_from_basis_sets_equals_job_from_arrays():
+    """The whole GW-BSE job with the integral producer on the device (Job.set_basis) against the same job fed with
+    the oracle's integral arrays: QP / BSE energies within 1e-9 Ha."""
+    from votca_b200.api import Job
+    c = helpers.methane_svp_case()
+    hf = c["hf"]
+    N, q, homo = c["dft"].size, c["q"], c["homo"]
+    vxc = hf["exchange_mo"][:q, :q]
+    res = []
+    for from_basis in (False, True):
+        job = Job(0)
+        job.set_scalar("homo", homo)
+        job.set_array("mos", hf["mos"])
+        job.set_array("mo_energies", hf["energies"])
+        job.set_array("vxc", vxc)
+        job.set_array("aux_overlap", c["S"])
+        if from_basis:
+            job.set_basis("dft", *pack(c["dft"]))
+            job.set_basis("aux", *pack(c["aux"]))
+        else:
+            job.set_ao3c(c["ao3c"])
+            job.set_array("aux_coulomb", c["V"])
+        job.set_options(tasks="gw,singlets", gw__mode="G0W0", gw__sigma_integrator="ppm", bse__exctotal=5,
+                        bse__useTDA=True)
+        job.run()
+        res.append((job.get("QPpert_energies").ravel().copy(), job.get("BSE_singlet_eigenvalues").ravel().copy()))
+        job.close()
+    assert np.abs(res[0][0] - res[1][0]).max() < 1e-9
+    assert np.abs(res[0][1] - res[1][1]).max() < 1e-9
+
+
 def test_basis_errors(ctx):
     from votca_b200.api import GwbseError
     with pytest.raises(GwbseError, match="angular momentum"):

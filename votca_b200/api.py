@@ -410,6 +410,18 @@ class Job:
         naux, N = a.shape[0], a.shape[1]
         self._ck(self.api.gwbse_job_set_array(self.h, b"ao3c", ptr(a), N * N, naux))
 
+    def set_basis(self, which, l, nprim, centers, exps, coefs):
+        """which = 'dft' | 'aux': AO integrals are then produced on the device (no ao3c array needed)."""
+        l = np.ascontiguousarray(l, dtype=np.int32)
+        nprim = np.ascontiguousarray(nprim, dtype=np.int32)
+        centers = np.ascontiguousarray(centers, dtype=np.float64)
+        exps = np.ascontiguousarray(exps, dtype=np.float64)
+        coefs = np.ascontiguousarray(coefs, dtype=np.float64)
+        if centers.shape != (len(l), 3) or len(nprim) != len(l) or len(exps) != nprim.sum() or len(coefs) != len(exps):
+            raise ValueError("inconsistent basis arrays")
+        self._ck(self.api.gwbse_job_set_basis(self.h, which.encode(), len(l), ptr(l), ptr(nprim), ptr(centers),
+                                              ptr(exps), ptr(coefs)))
+
     def run(self):
         self._ck(self.api.gwbse_job_run(self.h))
 

@@ -1,0 +1,95 @@
+// AO integrals produced on the GPU: the host-layer side of gwbse_basis_* / gwbse_ao3c_block_dev /
+// gwbse_ao_coulomb2c.  DeviceAOIntegrals is an AOIntegralSource whose blocks never exist on the host:
+// TCMatrix_gwbse::Fill3cMO (threecenter.h) asks DeviceBlock() first and contracts straight from the device buffer.
+// It stands where the reference calls libint: ComputeAO3cBlock (xtp/src/libxtp/libint2_calls.cc:544-593) and
+// AOCoulomb::Fill (libint2_calls.cc:224-271).
+#pragma once
+#include <algorithm>
+#include <vector>
+
+#include "threecenter.h"
+
+namespace votca {
+namespace xtp {
+
+// The numbers AOBasis::Fill / AOShell::LibintShell hold per shell (aobasis.cc:85-105, aoshell.cc:65-89): shells in
+// atom order, pure functions m = -l..l; coefs include libint's primitive normalisation and VOTCA's shell norm.
+struct AOBasisData {
+  std::vector<int> l, nprim;
+  std::vector<double> centers;  // 3 per shell, bohr
+  std::vector<double> exps, coefs;
+  Index AOBasisSize() const {
+    Index n = 0;
+    for (int x : l) n += 2 * x + 1;
+    return n;
+  }
+};
+
+class DeviceAOBasis {
+ public:
+  DeviceAOBasis(const Device& dev, const AOBasisData& d) : dev_(dev) {
+    if (d.l.size() != d.nprim.size() || d.centers.size() != 3 * d.l.size() || d.exps.size() != d.coefs.size())
+      throw std::runtime_error("inconsistent basis description");
+    dev_.check(gwbse_basis_create(dev_.ctx(), (int)d.l.size(), d.l.data(), d.nprim.data(), d.centers.data(),
+                                  d.exps.data(), d.coefs.data(), &h_));
+  }
+  ~DeviceAOBasis() {
+    if (h_) gwbse_basis_destroy(dev_.ctx(), h_);
+  }
+  DeviceAOBasis(const DeviceAOBasis&) = delete;
+  DeviceAOBasis& operator=(const DeviceAOBasis&) = delete;
+  const gwbse_basis* handle() const { return h_; }
+  Index AOBasisSize() const { return gwbse_basis_size(h_); }
+
+ private:
+  const Device& dev_;
+  gwbse_basis* h_ = nullptr;
+};
+
+class DeviceAOIntegrals : public AOIntegralSource {
+ public:
+  // aux_overlap: AOOverlap::Fill(auxbasis) (cheap, stays with the caller); the aux Coulomb matrix is computed on
+  // the device on first use unless supplied
+  DeviceAOIntegrals(const Device& dev, const DeviceAOBasis& aux, const DeviceAOBasis& dft, const MatrixXd& aux_overlap,
+                    const MatrixXd* aux_coulomb = nullptr)
+      : dev_(dev), aux_(aux), dft_(dft), S_(aux_overlap) {
+    if (aux_coulomb) {
+      V_ = *aux_coulomb;
+      have_V_ = true;
+    }
+  }
+  Index AuxSize() const override { return aux_.AOBasisSize(); }
+  Index BasisSize() const override { return dft_.AOBasisSize(); }
+  void ComputeAO3cBlock(Index aux_offset, Index aux_count, double* out) const override {
+    dev_.check(gwbse_ao3c_block(dev_.ctx(), aux_.handle(), dft_.handle(), (int)aux_offset, (int)aux_count, out));
+  }
+  const double* DeviceBlock(Index aux_offset, Index aux_count) const override {
+    const size_t need = static_cast<size_t>(aux_count) * BasisSize() * BasisSize();
+    if (block_.size() < need) block_ = dev_.alloc(need);
+    dev_.check(gwbse_ao3c_block_dev(dev_.ctx(), aux_.handle(), dft_.handle(), (int)aux_offset, (int)aux_count,
+                                    block_.get()));
+    return block_.get();
+  }
+  const MatrixXd& AuxOverlap() const override { return S_; }
+  const MatrixXd& AuxCoulomb() const override {
+    if (!have_V_) {
+      const Index n = AuxSize();
+      V_ = MatrixXd(n, n);
+      dev_.check(gwbse_ao_coulomb2c(dev_.ctx(), aux_.handle(), V_.data(), (int)n));
+      have_V_ = true;
+    }
+    return V_;
+  }
+
+ private:
+  const Device& dev_;
+  const DeviceAOBasis& aux_;
+  const DeviceAOBasis& dft_;
+  const MatrixXd& S_;
+  mutable MatrixXd V_;
+  mutable bool have_V_ = false;
+  mutable Device::Buffer block_;
+};
+
+}  // namespace xtp
+}  // namespace votca

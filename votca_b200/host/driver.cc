@@ -5,6 +5,7 @@
 #include <map>
 #include <memory>
 
+#include "aobasis.h"
 #include "gwbse.h"
 
 using namespace votca;
@@ -59,6 +60,8 @@ struct gwbse_job {
   std::map<std::string, MatrixXd> out;
   std::map<std::string, double> out_scalars;
   ArraySource ints;
+  // AO integrals produced on the device from the basis sets (gwbse_job_set_basis) instead of "ao3c"
+  std::unique_ptr<AOBasisData> basis_data[2];  // 0 = dft, 1 = aux
   std::string err;
   mutable std::string logcache;
 };
@@ -182,6 +185,24 @@ int gwbse_job_set_ao3c_partial(gwbse_job* job, long nbasis, long naux, long firs
   JOB_END(job)
 }
 
+int gwbse_job_set_basis(gwbse_job* job, const char* which, int nshell, const int* l, const int* nprim,
+                        const double* centers, const double* exps, const double* coefs) {
+  JOB_BEGIN(job)
+  const std::string w(which ? which : "");
+  if (w != "dft" && w != "aux") throw std::runtime_error("basis must be 'dft' or 'aux'");
+  if (nshell < 1 || !l || !nprim || !centers || !exps || !coefs) throw std::runtime_error("invalid basis description");
+  auto d = std::make_unique<AOBasisData>();
+  d->l.assign(l, l + nshell);
+  d->nprim.assign(nprim, nprim + nshell);
+  d->centers.assign(centers, centers + 3 * static_cast<size_t>(nshell));
+  size_t np = 0;
+  for (int s = 0; s < nshell; ++s) np += static_cast<size_t>(std::max(nprim[s], 0));
+  d->exps.assign(exps, exps + np);
+  d->coefs.assign(coefs, coefs + np);
+  job->basis_data[w == "aux" ? 1 : 0] = std::move(d);
+  JOB_END(job)
+}
+
 void* gwbse_job_ctx(gwbse_job* job) { return job ? job->dev->ctx() : nullptr; }
 
 int gwbse_job_run(gwbse_job* job) {
@@ -200,10 +221,25 @@ int gwbse_job_run(gwbse_job* job) {
   in.mos = &mos;
   in.mo_energies = &mo_e;
   if (job->in.count("vxc")) in.vxc = &job->in["vxc"];
-  job->ints.S = &need("aux_overlap");
-  job->ints.V = &need("aux_coulomb");
-  if (job->ints.naux != job->ints.S->rows()) throw std::runtime_error("aux matrices do not match ao3c");
-  in.integrals = &job->ints;
+  // integral producer: the device (both basis sets given, no ao3c array / callback), else the supplied arrays
+  std::unique_ptr<DeviceAOBasis> dft_basis, aux_basis;
+  std::unique_ptr<DeviceAOIntegrals> device_ints;
+  const bool have_arrays = job->ints.ao3c || job->ints.ao3c_dev || job->ints.fn;
+  if (!have_arrays && job->basis_data[0] && job->basis_data[1]) {
+    dft_basis = std::make_unique<DeviceAOBasis>(*job->dev, *job->basis_data[0]);
+    aux_basis = std::make_unique<DeviceAOBasis>(*job->dev, *job->basis_data[1]);
+    const MatrixXd& S = need("aux_overlap");
+    if (aux_basis->AOBasisSize() != S.rows()) throw std::runtime_error("aux overlap does not match the aux basis");
+    if (dft_basis->AOBasisSize() != mos.rows()) throw std::runtime_error("MO coefficients do not match the dft basis");
+    device_ints = std::make_unique<DeviceAOIntegrals>(*job->dev, *aux_basis, *dft_basis, S,
+                                                      job->in.count("aux_coulomb") ? &job->in["aux_coulomb"] : nullptr);
+    in.integrals = device_ints.get();
+  } else {
+    job->ints.S = &need("aux_overlap");
+    job->ints.V = &need("aux_coulomb");
+    if (job->ints.naux != job->ints.S->rows()) throw std::runtime_error("aux matrices do not match ao3c");
+    in.integrals = &job->ints;
+  }
   std::vector<MatrixXd> dip;
   if (job->in.count("dipole_x") && job->in.count("dipole_y") && job->in.count("dipole_z")) {
     dip = {job->in["dipole_x"], job->in["dipole_y"], job->in["dipole_z"]};
