@@ -184,6 +184,8 @@ int gwbse_ao3c_block(gwbse_ctx* ctx, const gwbse_basis* aux, const gwbse_basis* 
                      double* out);
 /* AOCoulomb::Fill (libint2_calls.cc:224-271; BraKet::xs_xs): V(P, Q) = (P | Q), naux x naux to the host */
 int gwbse_ao_coulomb2c(gwbse_ctx* ctx, const gwbse_basis* aux, double* V, int ld);
+/* AOOverlap::Fill (libint2_calls.cc:163-165): S(mu, nu) = <mu | nu>, n x n to the host */
+int gwbse_ao_overlap(gwbse_ctx* ctx, const gwbse_basis* basis, double* S, int ld);
 /* TCMatrix_gwbse::Fill3cMO (libint2_calls.cc:595-651) with the integral producer on the GPU: blocks of aux_block
  * aux functions are computed into a device buffer and contracted from there (gwbse_mmn_fill_block_dev); no AO
  * integral crosses PCIe.  Needs gwbse_mmn_alloc + gwbse_mmn_set_mos.  Multi-GPU: every rank produces and

@@ -52,7 +52,8 @@ int gwbse_job_set_ao3c_partial(gwbse_job* job, long nbasis, long naux, long firs
 /* AO integrals produced on the GPU instead of "ao3c" (gwbse_b200.h: gwbse_basis_create, gwbse_ao3c_block_dev,
  * gwbse_ao_coulomb2c - the device stand-ins for ComputeAO3cBlock / AOCoulomb::Fill, libint2_calls.cc:544-593,
  * 224-271): which = "dft" or "aux", arguments as gwbse_basis_create.  Used when both are set and no ao3c array or
- * callback is; "aux_overlap" is still an input, "aux_coulomb" becomes optional (computed on the device). */
+ * callback is; "aux_overlap" and "aux_coulomb" then become optional (computed on the device: gwbse_ao_overlap,
+ * gwbse_ao_coulomb2c). */
 int gwbse_job_set_basis(gwbse_job* job, const char* which, int nshell, const int* l, const int* nprim,
                         const double* centers, const double* exps, const double* coefs);
 /* the kernel-library context of this job (gwbse_b200.h), e.g. for gwbse_gemm_stats / timers */

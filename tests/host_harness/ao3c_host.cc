@@ -124,6 +124,26 @@ int coulomb2c_host(int nshell, const int* l, const int* nprim, const double* cen
   }
 }
 
+// S[nu][mu] = <mu | nu>
+int overlap_host(int nshell, const int* l, const int* nprim, const double* center, const double* exps,
+                 const double* coefs, double* out) {
+  try {
+    static Tables tb;
+    HostBasis bs;
+    bs.build(nshell, l, nprim, center, exps, coefs);
+    const BasisView v = view_of(bs);
+    const long long N = bs.nfunc;
+    OutSpec spec{out, 0, 1, N, 0, 1, 1};
+    std::vector<double> ws((size_t)workspace_doubles(bs.lmax, bs.lmax, 0) + 8, -7.0e300);
+    NoSync s;
+    for (int a = 0; a < bs.nshell; ++a)
+      for (int b = 0; b <= a; ++b) triple_block(v, v, tb.view, a, b, -1, ws.data(), 0, 1, s, spec, 1e-20);
+    return 0;
+  } catch (...) {
+    return 1;
+  }
+}
+
 int boys_host(int n, double x, double* out) {
   static Tables tb;
   *out = boys_one(tb.view, n, x);

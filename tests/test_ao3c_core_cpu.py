@@ -36,6 +36,7 @@ def _bind(path):
     p, i = ctypes.c_void_p, ctypes.c_int
     lib.ao3c_host.argtypes = [i, p, p, p, p, p, i, p, p, p, p, p, i, p]
     lib.coulomb2c_host.argtypes = [i, p, p, p, p, p, p]
+    lib.overlap_host.argtypes = [i, p, p, p, p, p, p]
     lib.boys_host.argtypes = [i, ctypes.c_double, p]
     lib.pure_matrix_host.argtypes = [i, p]
     return lib
@@ -72,6 +73,13 @@ def coulomb2c(lib, ao):
     a = pack(ao)
     out = np.full((ao.size, ao.size), np.nan)
     assert lib.coulomb2c_host(len(a[0]), *_ptrs(a), out.ctypes.data) == 0
+    return out
+
+
+def overlap(lib, ao):
+    a = pack(ao)
+    out = np.full((ao.size, ao.size), np.nan)
+    assert lib.overlap_host(len(a[0]), *_ptrs(a), out.ctypes.data) == 0
     return out
 
 
@@ -121,6 +129,8 @@ def test_water_spdf_aux_matches_oracle(lib):
     assert relmax(w["ao3c"], got) < 1e-12
     assert np.abs(got - got.transpose(0, 2, 1)).max() == 0.0 or relmax(got, got.transpose(0, 2, 1)) < 1e-14
     assert relmax(w["V"], coulomb2c(lib, w["aux"])) < 1e-12
+    assert relmax(w["S"], overlap(lib, w["aux"])) < 1e-13
+    assert relmax(w["S_dft"], overlap(lib, w["dft"])) < 1e-13
 
 
 def test_methane_def2svp_tier_r_matches_oracle(lib):
@@ -144,6 +154,8 @@ def test_g_orbitals_i_aux_large_l(lib):
     ref = integrals.coulomb3c(aux, dft)
     assert relmax(ref, ao3c(lib, aux, dft)) < 1e-11
     assert relmax(integrals.coulomb2c(aux), coulomb2c(lib, aux)) < 1e-11
+    assert relmax(integrals.overlap(aux), overlap(lib, aux)) < 1e-12
+    assert relmax(integrals.overlap(dft), overlap(lib, dft)) < 1e-12
 
 
 def test_thread_sanitizer_finds_no_race():

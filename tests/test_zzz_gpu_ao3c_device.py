@@ -45,6 +45,8 @@ def test_ao3c_water_spdf_aux(ctx):
         if cnt:
             assert relmax(w["ao3c"][lo:lo + cnt], part) < 1e-12
     assert relmax(w["V"], ctx.ao_coulomb2c(aux)) < 1e-12
+    assert relmax(w["S"], ctx.ao_overlap(aux)) < 1e-13
+    assert relmax(w["S_dft"], ctx.ao_overlap(dft)) < 1e-13
     ctx.basis_destroy(aux)
     ctx.basis_destroy(dft)
 
@@ -92,12 +94,12 @@ def test_job_from_basis_sets_equals_job_from_arrays():
         job.set_array("mos", hf["mos"])
         job.set_array("mo_energies", hf["energies"])
         job.set_array("vxc", vxc)
-        job.set_array("aux_overlap", c["S"])
-        if from_basis:
+        if from_basis:  # overlap, two- and three-centre Coulomb integrals all come from the device
             job.set_basis("dft", *pack(c["dft"]))
             job.set_basis("aux", *pack(c["aux"]))
         else:
             job.set_ao3c(c["ao3c"])
+            job.set_array("aux_overlap", c["S"])
             job.set_array("aux_coulomb", c["V"])
         job.set_options(tasks="gw,singlets", gw__mode="G0W0", gw__sigma_integrator="ppm", bse__exctotal=5,
                         bse__useTDA=True)

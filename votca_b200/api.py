@@ -203,6 +203,12 @@ class Context:
         self.call("gwbse_ao_coulomb2c", aux, ptr(out), n)
         return out
 
+    def ao_overlap(self, basis):
+        n = self.basis_size(basis)
+        out = np.empty((n, n), order="F")
+        self.call("gwbse_ao_overlap", basis, ptr(out), n)
+        return out
+
     def mmn_fill_from_basis(self, aux, dft, aux_block=64):
         self.call("gwbse_mmn_fill_from_basis", aux, dft, int(aux_block))
 

@@ -91,11 +91,13 @@ AO_HD double boys_one(const TableView& tb, int n, double x) {
 }
 
 // sb < 0: unit partner (exponent 0, coefficient 1, s type, on the centre of sa) -> two-centre integrals (sc | sa)
+// sc < 0: no Coulomb operator at all -> overlap <sa | sb> (AOOverlap::Fill, libint2_calls.cc:163-165), written as
+//         "aux function" 0
 template <class Sync>
 AO_HD void triple_block(const BasisView& dft, const BasisView& aux, const TableView& tb, int sa, int sb, int sc,
                         double* ws, int lane, int nl, Sync& sync, const OutSpec& out, double prim_threshold) {
-  const bool unit_b = sb < 0;
-  const int la = dft.l[sa], lb = unit_b ? 0 : dft.l[sb], lc = aux.l[sc];
+  const bool unit_b = sb < 0, overlap = sc < 0;
+  const int la = dft.l[sa], lb = unit_b ? 0 : dft.l[sb], lc = overlap ? 0 : aux.l[sc];
   const int Lab = la + lb, L = Lab + lc;
   const int nca = nc_of(la), ncb = nc_of(lb), ncc = nc_of(lc);
   const int npa = 2 * la + 1, npb = 2 * lb + 1, npc = 2 * lc + 1;
@@ -115,12 +117,13 @@ AO_HD void triple_block(const BasisView& dft, const BasisView& aux, const TableV
   const double Ax = dft.center[3 * sa], Ay = dft.center[3 * sa + 1], Az = dft.center[3 * sa + 2];
   const int sbb = unit_b ? sa : sb;
   const double Bx = dft.center[3 * sbb], By = dft.center[3 * sbb + 1], Bz = dft.center[3 * sbb + 2];
-  const double Cx = aux.center[3 * sc], Cy = aux.center[3 * sc + 1], Cz = aux.center[3 * sc + 2];
+  const double Cx = overlap ? 0.0 : aux.center[3 * sc], Cy = overlap ? 0.0 : aux.center[3 * sc + 1],
+               Cz = overlap ? 0.0 : aux.center[3 * sc + 2];
   const double ABx = Ax - Bx, ABy = Ay - By, ABz = Az - Bz;
   const double AB2 = ABx * ABx + ABy * ABy + ABz * ABz;
   const int pa0 = dft.prim0[sa], npra = dft.np[sa];
   const int pb0 = unit_b ? 0 : dft.prim0[sb], nprb = unit_b ? 1 : dft.np[sb];
-  const int pc0 = aux.prim0[sc], nprc = aux.np[sc];
+  const int pc0 = overlap ? 0 : aux.prim0[sc], nprc = overlap ? 0 : aux.np[sc];
   const uint8_t* cart_a = tb.tuv + 4 * nh_of(la - 1);
   const uint8_t* cart_b = tb.tuv + 4 * nh_of(lb - 1);
   const uint8_t* cart_c = tb.tuv + 4 * nh_of(lc - 1);
@@ -171,6 +174,17 @@ AO_HD void triple_block(const BasisView& dft, const BasisView& aux, const TableV
           if (t + 1 <= i + j - 1) v += (t + 1) * src[t + 1];
           if (t >= 1) v += inv2p * src[t - 1];
           E[d * esz + i * ej + j * T1 + t] = v;
+        }
+        sync();
+      }
+      if (overlap) {
+        // <a|b> += c_a c_b (pi/p)^(3/2) E^x_0 E^y_0 E^z_0
+        const double pref = cab * 5.568327996831708 / (p * sqrt(p));  // pi^(3/2)
+        for (int it = lane; it < nca * ncb; it += nl) {
+          const int ja = it / ncb, jb = it % ncb;
+          const int ax = cart_a[4 * ja], ay = cart_a[4 * ja + 1], az = cart_a[4 * ja + 2];
+          const int bx = cart_b[4 * jb], by = cart_b[4 * jb + 1], bz = cart_b[4 * jb + 2];
+          acc[it] += pref * E[ax * ej + bx * T1] * E[esz + ay * ej + by * T1] * E[2 * esz + az * ej + bz * T1];
         }
         sync();
       }
@@ -265,7 +279,7 @@ AO_HD void triple_block(const BasisView& dft, const BasisView& aux, const TableV
     }
   }
   sync();
-  const int fa = dft.func0[sa], fb = unit_b ? 0 : dft.func0[sb], fc = aux.func0[sc];
+  const int fa = dft.func0[sa], fb = unit_b ? 0 : dft.func0[sb], fc = overlap ? 0 : aux.func0[sc];
   for (int m = 0; m < npc; ++m) {
     const int k = fc + m;
     const bool wanted = k >= out.func_begin && k < out.func_end;  // same in every lane

@@ -98,6 +98,7 @@ struct gwbse_basis {
   // shells of one angular momentum, ascending (a function range maps to a contiguous piece of each list)
   std::vector<int> by_l[ao::LMAX_SHELL + 1];
   int* by_l_dev[ao::LMAX_SHELL + 1] = {};
+  int* no_aux_dev = nullptr;  // {-1}: "aux shell list" of the overlap launches
   // shell pairs (x, y) with l_x >= l_y, every unordered pair once, grouped by (l_x, l_y)
   struct PairClass {
     int la, lb;
@@ -135,6 +136,7 @@ void build_basis(gwbse_basis& b, int device) {
   b.view.herm1 = b.keep(upload(h.herm1));
   for (int s = 0; s < h.nshell; ++s) b.by_l[h.l[s]].push_back(s);
   for (int l = 0; l <= ao::LMAX_SHELL; ++l) b.by_l_dev[l] = b.keep(upload(b.by_l[l]));
+  b.no_aux_dev = b.keep(upload(std::vector<int>{-1}));
   std::map<std::pair<int, int>, std::vector<int2>> groups;
   std::map<int, std::vector<int2>> units;
   for (int s = 0; s < h.nshell; ++s) {
@@ -152,17 +154,7 @@ void build_basis(gwbse_basis& b, int device) {
     b.unit_classes.push_back({it->first, 0, (long long)it->second.size(), b.keep(upload(it->second))});
 }
 
-// all (pair class) x (aux l) launches for the aux shells overlapping functions [f0, f1)
-void launch_classes(gwbse_ctx* ctx, const gwbse_basis& orb, const std::vector<gwbse_basis::PairClass>& classes,
-                    const gwbse_basis& aux, int f0, int f1, const ao::OutSpec& out) {
-  GW_REQUIRE(orb.device == ctx->device && aux.device == ctx->device, "basis belongs to another device");
-  GW_REQUIRE(f0 >= 0 && f1 <= aux.host.nfunc && f0 <= f1, "aux function range out of bounds");
-  if (f0 == f1) return;
-  const ao::TableView& tb = device_tables(ctx->device);
-  // shells [s0, s1) overlap the function range
-  const std::vector<int>& fn0 = aux.host.func0;
-  int s0 = int(std::upper_bound(fn0.begin(), fn0.end(), f0) - fn0.begin()) - 1;
-  int s1 = int(std::lower_bound(fn0.begin(), fn0.end(), f1) - fn0.begin());
+int shared_memory_limit(gwbse_ctx* ctx) {
   int smem_limit = 0;
   GW_CUDA(cudaDeviceGetAttribute(&smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
   static int smem_set = -1;
@@ -170,28 +162,45 @@ void launch_classes(gwbse_ctx* ctx, const gwbse_basis& orb, const std::vector<gw
     GW_CUDA(cudaFuncSetAttribute(ao3c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit));
     smem_set = smem_limit;
   }
+  return smem_limit;
+}
+
+// one launch: every pair of the class against n_aux_shells aux shells of angular momentum lc
+void launch_class(gwbse_ctx* ctx, const gwbse_basis& orb, const gwbse_basis::PairClass& pc, const gwbse_basis& aux,
+                  const int* aux_shells_dev, int n_aux_shells, int lc, const ao::OutSpec& out, int smem_limit) {
+  GW_REQUIRE(pc.la + pc.lb + lc <= ao::LMAX_TOTAL, "angular momentum class beyond the Boys table");
+  const int wsd = ao::workspace_doubles(pc.la, pc.lb, lc);
+  const size_t per_warp = sizeof(double) * (size_t)wsd;
+  int wpc = 8;
+  // aim at >= 4 resident CTAs per SM where the class is small enough, never exceed the opt-in limit
+  while (wpc > 1 && per_warp * wpc > (size_t)smem_limit / 4) wpc >>= 1;
+  GW_REQUIRE(per_warp * wpc <= (size_t)smem_limit, "integral class does not fit into shared memory");
+  const long long warps = pc.count * (long long)n_aux_shells;
+  const long long blocks = (warps + wpc - 1) / wpc;
+  GW_REQUIRE(blocks < (1LL << 31), "too many shell triples for one launch; use smaller aux blocks");
+  ao3c_kernel<<<(unsigned)blocks, wpc * 32, per_warp * wpc, ctx->stream>>>(
+      orb.view, aux.view, device_tables(ctx->device), pc.dev, pc.count, aux_shells_dev, n_aux_shells, out, wsd, 1e-20);
+  GW_CUDA(cudaGetLastError());
+  ctx->launches++;
+}
+
+// all (pair class) x (aux l) launches for the aux shells overlapping functions [f0, f1)
+void launch_classes(gwbse_ctx* ctx, const gwbse_basis& orb, const std::vector<gwbse_basis::PairClass>& classes,
+                    const gwbse_basis& aux, int f0, int f1, const ao::OutSpec& out) {
+  GW_REQUIRE(orb.device == ctx->device && aux.device == ctx->device, "basis belongs to another device");
+  GW_REQUIRE(f0 >= 0 && f1 <= aux.host.nfunc && f0 <= f1, "aux function range out of bounds");
+  if (f0 == f1) return;
+  // shells [s0, s1) overlap the function range
+  const std::vector<int>& fn0 = aux.host.func0;
+  const int s0 = int(std::upper_bound(fn0.begin(), fn0.end(), f0) - fn0.begin()) - 1;
+  const int s1 = int(std::lower_bound(fn0.begin(), fn0.end(), f1) - fn0.begin());
+  const int smem_limit = shared_memory_limit(ctx);
   for (int lc = ao::LMAX_SHELL; lc >= 0; --lc) {
     const std::vector<int>& list = aux.by_l[lc];
     const int i0 = int(std::lower_bound(list.begin(), list.end(), s0) - list.begin());
     const int i1 = int(std::lower_bound(list.begin(), list.end(), s1) - list.begin());
     if (i1 <= i0) continue;
-    for (const auto& pc : classes) {
-      GW_REQUIRE(pc.la + pc.lb + lc <= ao::LMAX_TOTAL, "angular momentum class beyond the Boys table");
-      const int wsd = ao::workspace_doubles(pc.la, pc.lb, lc);
-      const size_t per_warp = sizeof(double) * (size_t)wsd;
-      int wpc = 8;
-      // aim at >= 4 resident CTAs per SM where the class is small enough, never exceed the opt-in limit
-      while (wpc > 1 && per_warp * wpc > (size_t)smem_limit / 4) wpc >>= 1;
-      while (wpc > 1 && per_warp * wpc > (size_t)smem_limit) wpc >>= 1;
-      GW_REQUIRE(per_warp * wpc <= (size_t)smem_limit, "integral class does not fit into shared memory");
-      const long long warps = pc.count * (long long)(i1 - i0);
-      const long long blocks = (warps + wpc - 1) / wpc;
-      GW_REQUIRE(blocks < (1LL << 31), "too many shell triples for one launch; use smaller aux blocks");
-      ao3c_kernel<<<(unsigned)blocks, wpc * 32, per_warp * wpc, ctx->stream>>>(
-          orb.view, aux.view, tb, pc.dev, pc.count, aux.by_l_dev[lc] + i0, i1 - i0, out, wsd, 1e-20);
-      GW_CUDA(cudaGetLastError());
-      ctx->launches++;
-    }
+    for (const auto& pc : classes) launch_class(ctx, orb, pc, aux, aux.by_l_dev[lc] + i0, i1 - i0, lc, out, smem_limit);
   }
 }
 
@@ -260,6 +269,23 @@ int gwbse_ao_coulomb2c(gwbse_ctx* ctx, const gwbse_basis* aux, double* V, int ld
   ao::OutSpec out{d, (long long)n, 1, 0, 0, n, 0};
   launch_classes(ctx, *aux, aux->unit_classes, *aux, 0, n, out);
   GW_CUDA(copy2d_async(V, sizeof(double) * ld, d, sizeof(double) * n, sizeof(double) * n, n, cudaMemcpyDeviceToHost,
+                       ctx->stream));
+  GW_CUDA(cudaStreamSynchronize(ctx->stream));
+  GW_API_END(ctx)
+}
+
+int gwbse_ao_overlap(gwbse_ctx* ctx, const gwbse_basis* basis, double* S, int ld) {
+  GW_API_BEGIN(ctx)
+  GW_PROF(ctx, "ao_overlap");
+  GW_REQUIRE(basis && S, "null argument");
+  GW_REQUIRE(basis->device == ctx->device, "basis belongs to another device");
+  const int n = basis->host.nfunc;
+  GW_REQUIRE(ld >= n, "leading dimension too small");
+  double* d = ctx->buf("ao2c_out", (size_t)n * n);
+  ao::OutSpec out{d, 0, 1, (long long)n, 0, 1, 1};
+  const int smem_limit = shared_memory_limit(ctx);
+  for (const auto& pc : basis->pair_classes) launch_class(ctx, *basis, pc, *basis, basis->no_aux_dev, 1, 0, out, smem_limit);
+  GW_CUDA(copy2d_async(S, sizeof(double) * ld, d, sizeof(double) * n, sizeof(double) * n, n, cudaMemcpyDeviceToHost,
                        ctx->stream));
   GW_CUDA(cudaStreamSynchronize(ctx->stream));
   GW_API_END(ctx)

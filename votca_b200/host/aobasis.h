@@ -48,11 +48,15 @@ class DeviceAOBasis {
 
 class DeviceAOIntegrals : public AOIntegralSource {
  public:
-  // aux_overlap: AOOverlap::Fill(auxbasis) (cheap, stays with the caller); the aux Coulomb matrix is computed on
-  // the device on first use unless supplied
-  DeviceAOIntegrals(const Device& dev, const DeviceAOBasis& aux, const DeviceAOBasis& dft, const MatrixXd& aux_overlap,
-                    const MatrixXd* aux_coulomb = nullptr)
-      : dev_(dev), aux_(aux), dft_(dft), S_(aux_overlap) {
+  // aux overlap (AOOverlap::Fill) and aux Coulomb matrix (AOCoulomb::Fill) are computed on the device on first
+  // use unless supplied
+  DeviceAOIntegrals(const Device& dev, const DeviceAOBasis& aux, const DeviceAOBasis& dft,
+                    const MatrixXd* aux_overlap = nullptr, const MatrixXd* aux_coulomb = nullptr)
+      : dev_(dev), aux_(aux), dft_(dft) {
+    if (aux_overlap) {
+      S_ = *aux_overlap;
+      have_S_ = true;
+    }
     if (aux_coulomb) {
       V_ = *aux_coulomb;
       have_V_ = true;
@@ -70,7 +74,15 @@ class DeviceAOIntegrals : public AOIntegralSource {
                                     block_.get()));
     return block_.get();
   }
-  const MatrixXd& AuxOverlap() const override { return S_; }
+  const MatrixXd& AuxOverlap() const override {
+    if (!have_S_) {
+      const Index n = AuxSize();
+      S_ = MatrixXd(n, n);
+      dev_.check(gwbse_ao_overlap(dev_.ctx(), aux_.handle(), S_.data(), (int)n));
+      have_S_ = true;
+    }
+    return S_;
+  }
   const MatrixXd& AuxCoulomb() const override {
     if (!have_V_) {
       const Index n = AuxSize();
@@ -85,11 +97,16 @@ class DeviceAOIntegrals : public AOIntegralSource {
   const Device& dev_;
   const DeviceAOBasis& aux_;
   const DeviceAOBasis& dft_;
-  const MatrixXd& S_;
-  mutable MatrixXd V_;
-  mutable bool have_V_ = false;
+  mutable MatrixXd S_, V_;
+  mutable bool have_S_ = false, have_V_ = false;
   mutable Device::Buffer block_;
 };
+
+inline void TCMatrix_gwbse::Fill(const DeviceAOBasis& auxbasis, const DeviceAOBasis& dftbasis,
+                                 const MatrixXd& dft_orbitals, Index aux_block) {
+  owned_ints_ = std::make_unique<DeviceAOIntegrals>(dev_, auxbasis, dftbasis);
+  Fill(*owned_ints_, dft_orbitals, aux_block);
+}
 
 }  // namespace xtp
 }  // namespace votca

@@ -228,8 +228,8 @@ int gwbse_job_run(gwbse_job* job) {
   if (!have_arrays && job->basis_data[0] && job->basis_data[1]) {
     dft_basis = std::make_unique<DeviceAOBasis>(*job->dev, *job->basis_data[0]);
     aux_basis = std::make_unique<DeviceAOBasis>(*job->dev, *job->basis_data[1]);
-    const MatrixXd& S = need("aux_overlap");
-    if (aux_basis->AOBasisSize() != S.rows()) throw std::runtime_error("aux overlap does not match the aux basis");
+    const MatrixXd* S = job->in.count("aux_overlap") ? &job->in["aux_overlap"] : nullptr;
+    if (S && aux_basis->AOBasisSize() != S->rows()) throw std::runtime_error("aux overlap does not match the aux basis");
     if (dft_basis->AOBasisSize() != mos.rows()) throw std::runtime_error("MO coefficients do not match the dft basis");
     device_ints = std::make_unique<DeviceAOIntegrals>(*job->dev, *aux_basis, *dft_basis, S,
                                                       job->in.count("aux_coulomb") ? &job->in["aux_coulomb"] : nullptr);

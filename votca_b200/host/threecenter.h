@@ -4,6 +4,7 @@
 // libint2_calls.cc:544-593).
 #pragma once
 #include <functional>
+#include <memory>
 #include <vector>
 
 #include "device.h"
@@ -25,6 +26,8 @@ struct AOIntegralSource {
   virtual const MatrixXd& AuxOverlap() const = 0;  // AOOverlap::Fill(auxbasis)
   virtual const MatrixXd& AuxCoulomb() const = 0;  // AOCoulomb::Fill(auxbasis)
 };
+
+class DeviceAOBasis;  // aobasis.h
 
 class TCMatrix_gwbse {
  public:
@@ -82,6 +85,11 @@ class TCMatrix_gwbse {
     if (keep_snapshot_) dev_.check(gwbse_mmn_snapshot(dev_.ctx()));
     have_snapshot_ = keep_snapshot_;
   }
+
+  // threecenter.cc:72-90 with the reference's own argument list (auxbasis, dftbasis, dft_orbitals): overlap, two-
+  // and three-centre Coulomb integrals are all produced on the device (defined in aobasis.h)
+  void Fill(const DeviceAOBasis& auxbasis, const DeviceAOBasis& dftbasis, const MatrixXd& dft_orbitals,
+            Index aux_block = 64);
 
   // gw.cc:242-246 calls Rebuild() every reset_3c iterations.  With a device snapshot this is a D2D copy;
   // otherwise the integrals are contracted again exactly as the reference does.
@@ -160,6 +168,7 @@ class TCMatrix_gwbse {
   Index auxbasissize_ = 0, mmin_ = 0, mmax_ = 0, nmin_ = 0, nmax_ = 0, ntotal_ = 0, mtotal_ = 0;
   Index removedfunctions_ = 0;
   const AOIntegralSource* ints_ = nullptr;
+  std::unique_ptr<AOIntegralSource> owned_ints_;  // producer created by Fill(auxbasis, dftbasis, ...)
   const MatrixXd* dft_orbitals_ = nullptr;
   Index aux_block_ = 64;
   bool keep_snapshot_ = true, have_snapshot_ = false;
