@@ -56,6 +56,12 @@ int gwbse_job_set_ao3c_partial(gwbse_job* job, long nbasis, long naux, long firs
  * gwbse_ao_coulomb2c). */
 int gwbse_job_set_basis(gwbse_job* job, const char* which, int nshell, const int* l, const int* nprim,
                         const double* centers, const double* exps, const double* coefs);
+/* Results as an .orb checkpoint: gwbse_job_run (rank 0) writes /QMdata with the names and HDF5 types of
+ * Orbitals::WriteToCpt (orbitals.cc:990-1063) for everything this stage reads or produces - mos, the level ranges,
+ * RPA_inputenergies, QPpert_energies, QPdiag, BSE_singlet / BSE_triplet (eigenvalues, eigenvectors, eigenvectors2,
+ * info), transition_dipoles (ind0..), BSE_*_dynamic, useTDA, use_Hqp_offdiag, ScaHFX.  Written without an HDF5
+ * library (votca_b200/host/checkpoint.h).  NULL or "" switches it off. */
+int gwbse_job_set_orb_output(gwbse_job* job, const char* path);
 /* the kernel-library context of this job (gwbse_b200.h), e.g. for gwbse_gemm_stats / timers */
 void* gwbse_job_ctx(gwbse_job* job);
 

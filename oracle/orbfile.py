@@ -17,6 +17,44 @@ import numpy as np
 UNDEF = 0xFFFFFFFFFFFFFFFF
 
 
+def lookup3(data, initval=0):
+    """Bob Jenkins' lookup3 hashlittle (public domain), the metadata checksum of the HDF5 file format."""
+    M = 0xFFFFFFFF
+
+    def rot(x, k):
+        return ((x << k) | (x >> (32 - k))) & M
+
+    n = len(data)
+    a = b = c = (0xDEADBEEF + n + initval) & M
+    p = 0
+    while n > 12:
+        a = (a + int.from_bytes(data[p:p + 4], "little")) & M
+        b = (b + int.from_bytes(data[p + 4:p + 8], "little")) & M
+        c = (c + int.from_bytes(data[p + 8:p + 12], "little")) & M
+        a = (a - c) & M; a ^= rot(c, 4); c = (c + b) & M
+        b = (b - a) & M; b ^= rot(a, 6); a = (a + c) & M
+        c = (c - b) & M; c ^= rot(b, 8); b = (b + a) & M
+        a = (a - c) & M; a ^= rot(c, 16); c = (c + b) & M
+        b = (b - a) & M; b ^= rot(a, 19); a = (a + c) & M
+        c = (c - b) & M; c ^= rot(b, 4); b = (b + a) & M
+        p += 12
+        n -= 12
+    if n == 0:
+        return c
+    t = bytes(data[p:p + n]) + b"\0" * (12 - n)
+    a = (a + int.from_bytes(t[0:4], "little")) & M
+    b = (b + int.from_bytes(t[4:8], "little")) & M
+    c = (c + int.from_bytes(t[8:12], "little")) & M
+    c ^= b; c = (c - rot(b, 14)) & M
+    a ^= c; a = (a - rot(c, 11)) & M
+    b ^= a; b = (b - rot(a, 25)) & M
+    c ^= b; c = (c - rot(b, 16)) & M
+    a ^= c; a = (a - rot(c, 4)) & M
+    b ^= a; b = (b - rot(a, 14)) & M
+    c ^= b; c = (c - rot(b, 24)) & M
+    return c
+
+
 class OrbFile:
     def __init__(self, path):
         with open(path, "rb") as fh:
@@ -292,6 +330,38 @@ class OrbFile:
                     self._scan_heaps()
                     out.update(self._heap_attrs.get(heap, {}))
         return out
+
+    def verify_checksums(self):
+        """Recomputes the lookup3 checksum of the superblock and of every object-header chunk reachable from the
+        root group.  Returns the number of blocks checked; raises on the first mismatch."""
+        b = self.b
+        count = 0
+
+        def check(start, end, what):
+            nonlocal count
+            stored = struct.unpack_from("<I", b, end)[0]
+            if lookup3(b[start:end]) != stored:
+                raise ValueError(f"checksum mismatch in {what} at {start}")
+            count += 1
+
+        check(0, 44, "superblock")
+        seen, todo = set(), [self.root]
+        while todo:
+            addr = todo.pop()
+            if addr in seen:
+                continue
+            seen.add(addr)
+            flags = b[addr + 5]
+            p = addr + 6 + (16 if flags & 0x20 else 0) + (4 if flags & 0x10 else 0)
+            nb = 1 << (flags & 3)
+            size0 = int.from_bytes(b[p:p + nb], "little")
+            check(addr, p + nb + size0, "object header")
+            for mtype, _, body in self._messages(addr):
+                if mtype == 0x10:
+                    off, length = struct.unpack_from("<QQ", body, 0)
+                    check(off, off + length - 4, "continuation chunk")
+            todo.extend(self._links(addr).values())
+        return count
 
     def walk(self, path="/"):
         """All dataset paths below path."""

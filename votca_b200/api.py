@@ -428,6 +428,10 @@ class Job:
         self._ck(self.api.gwbse_job_set_basis(self.h, which.encode(), len(l), ptr(l), ptr(nprim), ptr(centers),
                                               ptr(exps), ptr(coefs)))
 
+    def set_orb_output(self, path):
+        """Write the results as an .orb (HDF5) checkpoint at the end of run()."""
+        self._ck(self.api.gwbse_job_set_orb_output(self.h, str(path).encode() if path else None))
+
     def run(self):
         self._ck(self.api.gwbse_job_run(self.h))
 

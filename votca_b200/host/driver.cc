@@ -62,6 +62,7 @@ struct gwbse_job {
   ArraySource ints;
   // AO integrals produced on the device from the basis sets (gwbse_job_set_basis) instead of "ao3c"
   std::unique_ptr<AOBasisData> basis_data[2];  // 0 = dft, 1 = aux
+  std::string orb_path;  // gwbse_job_set_orb_output: results are written there at the end of gwbse_job_run
   std::string err;
   mutable std::string logcache;
 };
@@ -203,6 +204,12 @@ int gwbse_job_set_basis(gwbse_job* job, const char* which, int nshell, const int
   JOB_END(job)
 }
 
+int gwbse_job_set_orb_output(gwbse_job* job, const char* path) {
+  JOB_BEGIN(job)
+  job->orb_path = path ? path : "";
+  JOB_END(job)
+}
+
 void* gwbse_job_ctx(gwbse_job* job) { return job ? job->dev->ctx() : nullptr; }
 
 int gwbse_job_run(gwbse_job* job) {
@@ -254,6 +261,7 @@ int gwbse_job_run(gwbse_job* job) {
   GWBSE gwbse(*job->dev, job->log);
   gwbse.Initialize(job->options, in);
   GWBSE::Results r = gwbse.Evaluate();
+  if (!job->orb_path.empty() && job->dev->rank() == 0) gwbse.WriteToCpt(r, job->orb_path);
   auto& o = job->out;
   o.clear();
   o["RPA_inputenergies"] = vec2mat(r.RPA_inputenergies);

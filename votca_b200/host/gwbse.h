@@ -11,6 +11,7 @@
 #include <sstream>
 
 #include "bse.h"
+#include "checkpoint.h"
 #include "gw.h"
 
 namespace votca {
@@ -379,6 +380,42 @@ class GWBSE {
     }
     log_(" GWBSE calculation finished ");
     return res;
+  }
+
+  // The GW-BSE part of Orbitals::WriteToCpt (orbitals.cc:990-1063): same group (/QMdata), names and HDF5 types
+  // for everything this stage reads or produces.  DFT-side members (atoms, basis-set tables, XC functional ...)
+  // belong to the Orbitals object of the caller and are not written.
+  void WriteToCpt(const Results& r, const std::string& filename) const {
+    CheckpointFile cpf(filename);
+    CheckpointWriter w = cpf.getWriter("/QMdata");
+    w(std::string("gwbse-b200"), "XTPVersion");
+    w(int(9), "version");  // Orbitals::orbitals_version(), orbitals.h:844
+    w(long(in_.homo + 1), "occupied_levels");
+    w(long(in_.homo + 1), "number_alpha_electrons");
+    w(long(in_.homo + 1), "number_beta_electrons");
+    const MatrixXd none;
+    w.WriteEigenSystem(*in_.mo_energies, *in_.mos, none, 0, "mos");
+    w(long(r.rpamin), "rpamin");
+    w(long(r.rpamax), "rpamax");
+    w(long(r.qpmin), "qpmin");
+    w(long(r.qpmax), "qpmax");
+    w(long(r.bse_vmin), "bse_vmin");
+    w(long(r.bse_cmax), "bse_cmax");
+    w(in_.ScaHFX, "ScaHFX");
+    w(bseopt_.useTDA, "useTDA");
+    w(r.RPA_inputenergies, "RPA_inputenergies");
+    w(r.QPpert_energies, "QPpert_energies");
+    w.WriteEigenSystem(r.QPdiag_eigenvalues, r.QPdiag_eigenvectors, none, 0, "QPdiag");
+    w.WriteEigenSystem(r.BSE_singlet.eigenvalues, r.BSE_singlet.eigenvectors, r.BSE_singlet.eigenvectors2,
+                       r.BSE_singlet.eigenvalues.size() && !r.BSE_singlet.success ? 2 : 0, "BSE_singlet");
+    w(r.transition_dipoles, "transition_dipoles");
+    w.WriteEigenSystem(r.BSE_triplet.eigenvalues, r.BSE_triplet.eigenvectors, r.BSE_triplet.eigenvectors2,
+                       r.BSE_triplet.eigenvalues.size() && !r.BSE_triplet.success ? 2 : 0, "BSE_triplet");
+    w(std::uint8_t(bseopt_.use_Hqp_offdiag ? 1u : 0u), "use_Hqp_offdiag");
+    w(std::uint8_t(0u), "is_qsgw");
+    w(r.BSE_singlet_dynamic, "BSE_singlet_dynamic");
+    w(r.BSE_triplet_dynamic, "BSE_triplet_dynamic");
+    cpf.Close();
   }
 
  private:
