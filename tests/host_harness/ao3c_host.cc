@@ -1,6 +1,7 @@
 // CPU harness of the device AO-integral code: runs votca_b200/csrc/ao3c_core.cuh - the same source the sm_100a
 // kernel compiles - with one std::thread per lane and a std::barrier as the warp barrier.  Test infrastructure
 // only (tests/test_ao3c_core_cpu.py); built with -fsanitize=thread it checks the barrier placement.
+#include <algorithm>
 #include <barrier>
 #include <cstring>
 #include <thread>
@@ -80,11 +81,14 @@ int ao3c_host(int nshell, const int* l, const int* nprim, const double* center, 
     OutSpec spec{out, N * N, 1, N, 0, aux.nfunc, 1};
     const int wsd = workspace_doubles(dft.lmax, dft.lmax, aux.lmax);
     std::vector<double> ws((size_t)wsd + 8, -7.0e300);  // poisoned: stale reads show up in the result
+    // as the launcher does (capi_ao3c.cu): shell pairs without a surviving primitive pair are not visited, their
+    // blocks are the zeros of the initial fill
+    std::fill(out, out + (size_t)aux.nfunc * N * N, 0.0);
     if (nl <= 1) {
       NoSync s;
       for (int a = 0; a < dft.nshell; ++a)
         for (int b = 0; b <= a; ++b)
-          for (int c = 0; c < aux.nshell; ++c) triple_block(dv, av, tb.view, a, b, c, ws.data(), 0, 1, s, spec, 1e-20);
+          for (int c = 0; dft.pair_survives(a, b) && c < aux.nshell; ++c) triple_block(dv, av, tb.view, a, b, c, ws.data(), 0, 1, s, spec, PRIM_THRESHOLD);
       return 0;
     }
     std::barrier<> bar(nl);
@@ -95,7 +99,7 @@ int ao3c_host(int nshell, const int* l, const int* nprim, const double* center, 
         for (int a = 0; a < dft.nshell; ++a)
           for (int b = 0; b <= a; ++b)
             for (int c = 0; c < aux.nshell; ++c)
-              triple_block(dv, av, tb.view, a, b, c, ws.data(), lane, nl, s, spec, 1e-20);
+              triple_block(dv, av, tb.view, a, b, c, ws.data(), lane, nl, s, spec, PRIM_THRESHOLD);
       });
     for (auto& t : th) t.join();
     return 0;
@@ -117,7 +121,7 @@ int coulomb2c_host(int nshell, const int* l, const int* nprim, const double* cen
     std::vector<double> ws((size_t)workspace_doubles(bs.lmax, 0, bs.lmax) + 8, -7.0e300);
     NoSync s;
     for (int a = 0; a < bs.nshell; ++a)
-      for (int c = 0; c < bs.nshell; ++c) triple_block(v, v, tb.view, a, -1, c, ws.data(), 0, 1, s, spec, 1e-20);
+      for (int c = 0; c < bs.nshell; ++c) triple_block(v, v, tb.view, a, -1, c, ws.data(), 0, 1, s, spec, PRIM_THRESHOLD);
     return 0;
   } catch (...) {
     return 1;
@@ -137,11 +141,21 @@ int overlap_host(int nshell, const int* l, const int* nprim, const double* cente
     std::vector<double> ws((size_t)workspace_doubles(bs.lmax, bs.lmax, 0) + 8, -7.0e300);
     NoSync s;
     for (int a = 0; a < bs.nshell; ++a)
-      for (int b = 0; b <= a; ++b) triple_block(v, v, tb.view, a, b, -1, ws.data(), 0, 1, s, spec, 1e-20);
+      for (int b = 0; b <= a; ++b) triple_block(v, v, tb.view, a, b, -1, ws.data(), 0, 1, s, spec, PRIM_THRESHOLD);
     return 0;
   } catch (...) {
     return 1;
   }
+}
+
+long surviving_pairs_host(int nshell, const int* l, const int* nprim, const double* center, const double* exps,
+                          const double* coefs) {
+  HostBasis bs;
+  bs.build(nshell, l, nprim, center, exps, coefs);
+  long n = 0;
+  for (int a = 0; a < bs.nshell; ++a)
+    for (int b = 0; b <= a; ++b) n += bs.pair_survives(a, b) ? 1 : 0;
+  return n;
 }
 
 int boys_host(int n, double x, double* out) {

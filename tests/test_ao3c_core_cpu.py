@@ -37,6 +37,8 @@ def _bind(path):
     lib.ao3c_host.argtypes = [i, p, p, p, p, p, i, p, p, p, p, p, i, p]
     lib.coulomb2c_host.argtypes = [i, p, p, p, p, p, p]
     lib.overlap_host.argtypes = [i, p, p, p, p, p, p]
+    lib.surviving_pairs_host.argtypes = [i, p, p, p, p, p]
+    lib.surviving_pairs_host.restype = ctypes.c_long
     lib.boys_host.argtypes = [i, ctypes.c_double, p]
     lib.pure_matrix_host.argtypes = [i, p]
     return lib
@@ -156,6 +158,26 @@ def test_g_orbitals_i_aux_large_l(lib):
     assert relmax(integrals.coulomb2c(aux), coulomb2c(lib, aux)) < 1e-11
     assert relmax(integrals.overlap(aux), overlap(lib, aux)) < 1e-12
     assert relmax(integrals.overlap(dft), overlap(lib, dft)) < 1e-12
+
+
+def test_shell_pair_screening_far_apart_fragments(lib):
+    """Two water molecules 60 bohr apart: shell pairs across the gap have no primitive pair above the kernel's
+    threshold, are dropped from the launch lists and stay exact zeros; everything still matches the oracle."""
+    g = helpers.load_golden()
+    bs = json.loads(str(g["basis/water_3-21G.json"]))
+    bs = {el: [(int(l), [tuple(p) for p in prims]) for l, prims in shells] for el, shells in bs.items()}
+    el = [str(e) for e in g["molecule_water/elements"]]
+    pos = np.asarray(g["molecule_water/positions_bohr"])
+    dimer = obasis.AOBasis(bs, el + el, np.vstack([pos, pos + np.array([60.0, 0.0, 0.0])]))
+    d = pack(dimer)
+    ns = len(d[0])
+    kept = lib.surviving_pairs_host(ns, *_ptrs(d))
+    assert kept == ns * (ns + 1) // 2 - (ns // 2) ** 2  # exactly the cross pairs are gone
+    ref = integrals.coulomb3c(dimer, dimer)
+    got = ao3c(lib, dimer, dimer)
+    assert relmax(ref, got) < 1e-12
+    half = dimer.size // 2
+    assert np.all(got[:, :half, half:] == 0.0) and np.abs(ref[:, :half, half:]).max() < 1e-30
 
 
 def test_thread_sanitizer_finds_no_race():

@@ -23,6 +23,8 @@ constexpr double BOYS_DX = 0.1;
 constexpr int BOYS_POINTS = 361;                    // x = 0 .. 36
 constexpr double BOYS_XMAX = 35.95;                 // beyond: F_0 from erf + upward recursion
 constexpr int HERM1_STRIDE = (LMAX_SHELL + 1) * (LMAX_SHELL + 1);
+// primitive pairs with |c_a c_b| exp(-a b / (a+b) |AB|^2) below this contribute nothing at double precision
+constexpr double PRIM_THRESHOLD = 1e-20;
 
 inline int ncart(int l) { return (l + 1) * (l + 2) / 2; }
 inline int nherm(int L) { return (L + 1) * (L + 2) * (L + 3) / 6; }
@@ -156,6 +158,23 @@ struct HostBasis {
       if (!(exps[p] > 0.0)) throw std::runtime_error("primitive exponent must be positive");
       fill_herm1(exps[p], &herm1[(size_t)p * HERM1_STRIDE]);
     }
+  }
+
+  // does any primitive pair of shells (s, t) pass the screening the kernel applies (ao3c_core.cuh)?  Pairs that
+  // fail are dropped from the launch lists; their integrals are exactly the zeros the kernel would write.
+  bool pair_survives(int s, int t, double threshold = PRIM_THRESHOLD) const {
+    double r2 = 0.0;
+    for (int d = 0; d < 3; ++d) {
+      const double x = center[3 * (size_t)s + d] - center[3 * (size_t)t + d];
+      r2 += x * x;
+    }
+    for (int i = 0; i < np[s]; ++i)
+      for (int j = 0; j < np[t]; ++j) {
+        const double a = exps[prim0[s] + i], b = exps[prim0[t] + j];
+        if (std::fabs(coefs[prim0[s] + i] * coefs[prim0[t] + j]) * std::exp(-a * b / (a + b) * r2) >= threshold)
+          return true;
+      }
+    return false;
   }
 };
 

@@ -106,6 +106,7 @@ struct gwbse_basis {
     int2* dev;
   };
   std::vector<PairClass> pair_classes;
+  long long pairs_total = 0, pairs_kept = 0;  // before / after the shell-pair screening
   // (x, -1): unit partner, grouped by l_x (two-centre integrals)
   std::vector<PairClass> unit_classes;
 
@@ -142,11 +143,14 @@ void build_basis(gwbse_basis& b, int device) {
   for (int s = 0; s < h.nshell; ++s) {
     units[h.l[s]].push_back(make_int2(s, -1));
     for (int t = 0; t <= s; ++t) {
+      if (!h.pair_survives(s, t)) continue;  // far apart: every primitive pair is below the kernel's threshold
       const bool swap = h.l[t] > h.l[s];
       const int x = swap ? t : s, y = swap ? s : t;
       groups[{h.l[x], h.l[y]}].push_back(make_int2(x, y));
     }
   }
+  b.pairs_total = (long long)h.nshell * (h.nshell + 1) / 2;
+  for (const auto& g : groups) b.pairs_kept += (long long)g.second.size();
   // heaviest classes first: the long-running warps start early
   for (auto it = groups.rbegin(); it != groups.rend(); ++it)
     b.pair_classes.push_back({it->first.first, it->first.second, (long long)it->second.size(), b.keep(upload(it->second))});
@@ -179,7 +183,7 @@ void launch_class(gwbse_ctx* ctx, const gwbse_basis& orb, const gwbse_basis::Pai
   const long long blocks = (warps + wpc - 1) / wpc;
   GW_REQUIRE(blocks < (1LL << 31), "too many shell triples for one launch; use smaller aux blocks");
   ao3c_kernel<<<(unsigned)blocks, wpc * 32, per_warp * wpc, ctx->stream>>>(
-      orb.view, aux.view, device_tables(ctx->device), pc.dev, pc.count, aux_shells_dev, n_aux_shells, out, wsd, 1e-20);
+      orb.view, aux.view, device_tables(ctx->device), pc.dev, pc.count, aux_shells_dev, n_aux_shells, out, wsd, ao::PRIM_THRESHOLD);
   GW_CUDA(cudaGetLastError());
   ctx->launches++;
 }
@@ -208,6 +212,8 @@ void ao3c_block_dev(gwbse_ctx* ctx, const gwbse_basis* aux, const gwbse_basis* d
                     double* out_dev) {
   GW_REQUIRE(aux && dft && out_dev, "null argument");
   const long long N = dft->host.nfunc;
+  if (dft->pairs_kept < dft->pairs_total && aux_count > 0)  // blocks of screened-out shell pairs are exact zeros
+    GW_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(double) * (size_t)(N * N) * (size_t)aux_count, ctx->stream));
   ao::OutSpec out{out_dev, N * N, 1, N, aux_offset, aux_offset + aux_count, 1};
   launch_classes(ctx, *dft, dft->pair_classes, *aux, aux_offset, aux_offset + aux_count, out);
 }
@@ -282,6 +288,7 @@ int gwbse_ao_overlap(gwbse_ctx* ctx, const gwbse_basis* basis, double* S, int ld
   const int n = basis->host.nfunc;
   GW_REQUIRE(ld >= n, "leading dimension too small");
   double* d = ctx->buf("ao2c_out", (size_t)n * n);
+  if (basis->pairs_kept < basis->pairs_total) GW_CUDA(cudaMemsetAsync(d, 0, sizeof(double) * (size_t)n * n, ctx->stream));
   ao::OutSpec out{d, 0, 1, (long long)n, 0, 1, 1};
   const int smem_limit = shared_memory_limit(ctx);
   for (const auto& pc : basis->pair_classes) launch_class(ctx, *basis, pc, *basis, basis->no_aux_dev, 1, 0, out, smem_limit);
