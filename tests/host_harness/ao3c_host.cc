@@ -7,7 +7,6 @@
 #include <thread>
 #include <vector>
 
-#include "../../votca_b200/csrc/ao3c_core.cuh"
 #include "../../votca_b200/csrc/ao3c_tables.h"
 
 using namespace gwbse::ao;
@@ -84,11 +83,11 @@ int ao3c_host(int nshell, const int* l, const int* nprim, const double* center, 
     // as the launcher does (capi_ao3c.cu): shell pairs without a surviving primitive pair are not visited, their
     // blocks are the zeros of the initial fill
     std::fill(out, out + (size_t)aux.nfunc * N * N, 0.0);
+    const PairLists pl = make_pair_lists(dft, false);
     if (nl <= 1) {
       NoSync s;
-      for (int a = 0; a < dft.nshell; ++a)
-        for (int b = 0; b <= a; ++b)
-          for (int c = 0; dft.pair_survives(a, b) && c < aux.nshell; ++c) triple_block(dv, av, tb.view, a, b, c, ws.data(), 0, 1, s, spec, PRIM_THRESHOLD);
+      for (const PairEntry& pe : pl.entries)
+        for (int c = 0; c < aux.nshell; ++c) triple_block(dv, av, tb.view, pe, pl.pool.data(), c, ws.data(), 0, 1, s, spec);
       return 0;
     }
     std::barrier<> bar(nl);
@@ -96,10 +95,9 @@ int ao3c_host(int nshell, const int* l, const int* nprim, const double* center, 
     for (int lane = 0; lane < nl; ++lane)
       th.emplace_back([&, lane] {
         BarrierSync s{&bar};
-        for (int a = 0; a < dft.nshell; ++a)
-          for (int b = 0; b <= a; ++b)
-            for (int c = 0; c < aux.nshell; ++c)
-              triple_block(dv, av, tb.view, a, b, c, ws.data(), lane, nl, s, spec, PRIM_THRESHOLD);
+        for (const PairEntry& pe : pl.entries)
+          for (int c = 0; c < aux.nshell; ++c)
+            triple_block(dv, av, tb.view, pe, pl.pool.data(), c, ws.data(), lane, nl, s, spec);
       });
     for (auto& t : th) t.join();
     return 0;
@@ -120,8 +118,9 @@ int coulomb2c_host(int nshell, const int* l, const int* nprim, const double* cen
     OutSpec spec{out, N, 1, 0, 0, bs.nfunc, 0};
     std::vector<double> ws((size_t)workspace_doubles(bs.lmax, 0, bs.lmax) + 8, -7.0e300);
     NoSync s;
-    for (int a = 0; a < bs.nshell; ++a)
-      for (int c = 0; c < bs.nshell; ++c) triple_block(v, v, tb.view, a, -1, c, ws.data(), 0, 1, s, spec, PRIM_THRESHOLD);
+    const PairLists pl = make_pair_lists(bs, true);
+    for (const PairEntry& pe : pl.entries)
+      for (int c = 0; c < bs.nshell; ++c) triple_block(v, v, tb.view, pe, pl.pool.data(), c, ws.data(), 0, 1, s, spec);
     return 0;
   } catch (...) {
     return 1;
@@ -140,8 +139,9 @@ int overlap_host(int nshell, const int* l, const int* nprim, const double* cente
     OutSpec spec{out, 0, 1, N, 0, 1, 1};
     std::vector<double> ws((size_t)workspace_doubles(bs.lmax, bs.lmax, 0) + 8, -7.0e300);
     NoSync s;
-    for (int a = 0; a < bs.nshell; ++a)
-      for (int b = 0; b <= a; ++b) triple_block(v, v, tb.view, a, b, -1, ws.data(), 0, 1, s, spec, PRIM_THRESHOLD);
+    std::fill(out, out + (size_t)N * N, 0.0);
+    const PairLists pl = make_pair_lists(bs, false);
+    for (const PairEntry& pe : pl.entries) triple_block(v, v, tb.view, pe, pl.pool.data(), -1, ws.data(), 0, 1, s, spec);
     return 0;
   } catch (...) {
     return 1;
@@ -152,10 +152,7 @@ long surviving_pairs_host(int nshell, const int* l, const int* nprim, const doub
                           const double* coefs) {
   HostBasis bs;
   bs.build(nshell, l, nprim, center, exps, coefs);
-  long n = 0;
-  for (int a = 0; a < bs.nshell; ++a)
-    for (int b = 0; b <= a; ++b) n += bs.pair_survives(a, b) ? 1 : 0;
-  return n;
+  return (long)make_pair_lists(bs, false).entries.size();
 }
 
 int boys_host(int n, double x, double* out) {

@@ -3,8 +3,9 @@
 // a unit partner, of AOCoulomb::Fill (libint2_calls.cc:224-271, BraKet::xs_xs), restated for one warp per
 // (orbital shell pair, auxiliary shell).
 //
-// Scheme: McMurchie-Davidson.  Per primitive pair the 1-D Hermite coefficients E^{ab}_t of the three directions,
-// per primitive triple the Hermite Coulomb tensor R_{tuv} (Boys function from a grid + 8-term Taylor step, then
+// Scheme: McMurchie-Davidson.  Per primitive pair the 1-D Hermite coefficients E^{ab}_t of the three directions
+// (built once per basis on the host, ao3c_tables.h: only primitive pairs above the screening threshold have a
+// record, shell pairs without any are never launched), per primitive triple the Hermite Coulomb tensor R_{tuv} (Boys function from a grid + 8-term Taylor step, then
 // the level recursion R^n -> R^{n-1}), the auxiliary side folded in first (G), then the pair side; cartesian ->
 // pure transformation of the three indices at the end.  The 32 lanes split the entries of every stage; stages are
 // separated by a warp barrier.  The code is __host__ __device__ and parameterised on the barrier so the CPU
@@ -53,6 +54,16 @@ struct OutSpec {
   int mirror;  // also write (k, nu, mu)
 };
 
+// One shell pair of a launch list.  b < 0: unit partner (exponent 0, coefficient 1, s type, on the centre of a).
+// Its npp surviving primitive pairs have records of rec_doubles doubles each at pool[off ...]:
+//   [0] p = a + b   [1..3] P = (a A + b B) / p   [4] c_a c_b   [5 ...] E[d][i][j][t], d = x, y, z
+// (the Gaussian product factor exp(-mu |AB|^2) is inside E[d][0][0][0], direction by direction)
+struct PairEntry {
+  int a, b;
+  int npp, rec_doubles;
+  long long off;
+};
+
 AO_HD int nc_of(int l) { return (l + 1) * (l + 2) / 2; }
 AO_HD int nh_of(int L) { return (L + 1) * (L + 2) * (L + 3) / 6; }
 AO_HD int hidx(int t, int u, int v) {
@@ -90,12 +101,13 @@ AO_HD double boys_one(const TableView& tb, int n, double x) {
   return f;
 }
 
-// sb < 0: unit partner (exponent 0, coefficient 1, s type, on the centre of sa) -> two-centre integrals (sc | sa)
-// sc < 0: no Coulomb operator at all -> overlap <sa | sb> (AOOverlap::Fill, libint2_calls.cc:163-165), written as
-//         "aux function" 0
+// pe.b < 0: unit partner -> two-centre integrals (sc | a)
+// sc < 0:   no Coulomb operator at all -> overlap <a | b> (AOOverlap::Fill, libint2_calls.cc:163-165), written as
+//           "aux function" 0
 template <class Sync>
-AO_HD void triple_block(const BasisView& dft, const BasisView& aux, const TableView& tb, int sa, int sb, int sc,
-                        double* ws, int lane, int nl, Sync& sync, const OutSpec& out, double prim_threshold) {
+AO_HD void triple_block(const BasisView& dft, const BasisView& aux, const TableView& tb, const PairEntry& pe,
+                        const double* pool, int sc, double* ws, int lane, int nl, Sync& sync, const OutSpec& out) {
+  const int sa = pe.a, sb = pe.b;
   const bool unit_b = sb < 0, overlap = sc < 0;
   const int la = dft.l[sa], lb = unit_b ? 0 : dft.l[sb], lc = overlap ? 0 : aux.l[sc];
   const int Lab = la + lb, L = Lab + lc;
@@ -114,15 +126,8 @@ AO_HD void triple_block(const BasisView& dft, const BasisView& aux, const TableV
   double* seed = acc + nca * ncb * ncc;
   double* tmp = R;  // free after the primitive loops
 
-  const double Ax = dft.center[3 * sa], Ay = dft.center[3 * sa + 1], Az = dft.center[3 * sa + 2];
-  const int sbb = unit_b ? sa : sb;
-  const double Bx = dft.center[3 * sbb], By = dft.center[3 * sbb + 1], Bz = dft.center[3 * sbb + 2];
   const double Cx = overlap ? 0.0 : aux.center[3 * sc], Cy = overlap ? 0.0 : aux.center[3 * sc + 1],
                Cz = overlap ? 0.0 : aux.center[3 * sc + 2];
-  const double ABx = Ax - Bx, ABy = Ay - By, ABz = Az - Bz;
-  const double AB2 = ABx * ABx + ABy * ABy + ABz * ABz;
-  const int pa0 = dft.prim0[sa], npra = dft.np[sa];
-  const int pb0 = unit_b ? 0 : dft.prim0[sb], nprb = unit_b ? 1 : dft.np[sb];
   const int pc0 = overlap ? 0 : aux.prim0[sc], nprc = overlap ? 0 : aux.np[sc];
   const uint8_t* cart_a = tb.tuv + 4 * nh_of(la - 1);
   const uint8_t* cart_b = tb.tuv + 4 * nh_of(lb - 1);
@@ -133,50 +138,13 @@ AO_HD void triple_block(const BasisView& dft, const BasisView& aux, const TableV
   for (int i = lane; i < nca * ncb * ncc; i += nl) acc[i] = 0.0;
   sync();
 
-  for (int ia = 0; ia < npra; ++ia) {
-    for (int ib = 0; ib < nprb; ++ib) {
-      const double a = dft.exps[pa0 + ia], b = unit_b ? 0.0 : dft.exps[pb0 + ib];
-      const double cab = dft.coefs[pa0 + ia] * (unit_b ? 1.0 : dft.coefs[pb0 + ib]);
-      const double p = a + b, mu = a * b / p;
-      if (fabs(cab) * exp(-mu * AB2) < prim_threshold) continue;  // same decision in every lane
-      const double inv2p = 0.5 / p;
-      const double Px = (a * Ax + b * Bx) / p, Py = (a * Ay + b * By) / p, Pz = (a * Az + b * Bz) / p;
-      // ---- E^{ab}: row i = 0 serially per direction, rows i > 0 from the row above --------------------------
-      for (int d = lane; d < 3; d += nl) {
-        const double Xab = d == 0 ? ABx : (d == 1 ? ABy : ABz);
-        const double Xpb = a / p * Xab;
-        double* Ed = E + d * esz;
-        Ed[0] = exp(-mu * Xab * Xab);
-        for (int j = 1; j <= lb; ++j) {
-          const double* src = Ed + (j - 1) * T1;
-          double* dst = Ed + j * T1;
-          for (int t = 0; t <= j; ++t) {
-            double v = 0.0;
-            if (t <= j - 1) v += Xpb * src[t];
-            if (t + 1 <= j - 1) v += (t + 1) * src[t + 1];
-            if (t >= 1) v += inv2p * src[t - 1];
-            dst[t] = v;
-          }
-        }
-      }
+  for (int ipp = 0; ipp < pe.npp; ++ipp) {
+    {
+      const double* rec = pool + pe.off + (long long)ipp * pe.rec_doubles;
+      const double p = rec[0], Px = rec[1], Py = rec[2], Pz = rec[3], cab = rec[4];
+      // ---- E^{ab} of this primitive pair: global -> scratch -------------------------------------------------
+      for (int i = lane; i < 3 * esz; i += nl) E[i] = rec[5 + i];
       sync();
-      for (int i = 1; i <= la; ++i) {
-        const int nitem = 3 * (lb + 1) * T1;
-        for (int it = lane; it < nitem; it += nl) {
-          const int d = it / ((lb + 1) * T1), rem = it % ((lb + 1) * T1);
-          const int j = rem / T1, t = rem % T1;
-          if (t > i + j) continue;
-          const double Xab = d == 0 ? ABx : (d == 1 ? ABy : ABz);
-          const double Xpa = -b / p * Xab;
-          const double* src = E + d * esz + (i - 1) * ej + j * T1;
-          double v = 0.0;
-          if (t <= i + j - 1) v += Xpa * src[t];
-          if (t + 1 <= i + j - 1) v += (t + 1) * src[t + 1];
-          if (t >= 1) v += inv2p * src[t - 1];
-          E[d * esz + i * ej + j * T1 + t] = v;
-        }
-        sync();
-      }
       if (overlap) {
         // <a|b> += c_a c_b (pi/p)^(3/2) E^x_0 E^y_0 E^z_0
         const double pref = cab * 5.568327996831708 / (p * sqrt(p));  // pi^(3/2)

@@ -12,6 +12,8 @@
 #include <stdexcept>
 #include <vector>
 
+#include "ao3c_core.cuh"
+
 namespace gwbse {
 namespace ao {
 
@@ -160,23 +162,85 @@ struct HostBasis {
     }
   }
 
-  // does any primitive pair of shells (s, t) pass the screening the kernel applies (ao3c_core.cuh)?  Pairs that
-  // fail are dropped from the launch lists; their integrals are exactly the zeros the kernel would write.
-  bool pair_survives(int s, int t, double threshold = PRIM_THRESHOLD) const {
-    double r2 = 0.0;
-    for (int d = 0; d < 3; ++d) {
-      const double x = center[3 * (size_t)s + d] - center[3 * (size_t)t + d];
-      r2 += x * x;
-    }
-    for (int i = 0; i < np[s]; ++i)
-      for (int j = 0; j < np[t]; ++j) {
-        const double a = exps[prim0[s] + i], b = exps[prim0[t] + j];
-        if (std::fabs(coefs[prim0[s] + i] * coefs[prim0[t] + j]) * std::exp(-a * b / (a + b) * r2) >= threshold)
-          return true;
+  // Appends the records of shell pair (s, t) to pool - one per primitive pair with
+  // |c_a c_b| exp(-a b / (a+b) |AB|^2) >= threshold, layout as PairEntry (ao3c_core.cuh) documents - and returns
+  // how many were written.  t < 0: unit partner.  E^{ab}_t is the McMurchie-Davidson recursion in i (shell s)
+  // and j (shell t):  E[i+1][j][t] = X_PA E[i][j][t] + (t+1) E[i][j][t+1] + E[i][j][t-1] / 2p, likewise in j.
+  int append_pair_records(int s, int t, std::vector<double>& pool, double threshold = PRIM_THRESHOLD) const {
+    const bool unit = t < 0;
+    const int la = l[s], lb = unit ? 0 : l[t];
+    const int T1 = la + lb + 1, ej = (lb + 1) * T1, esz = (la + 1) * ej;
+    const double* A = &center[3 * (size_t)s];
+    const double* B = unit ? A : &center[3 * (size_t)t];
+    const double AB[3] = {A[0] - B[0], A[1] - B[1], A[2] - B[2]};
+    const double AB2 = AB[0] * AB[0] + AB[1] * AB[1] + AB[2] * AB[2];
+    int written = 0;
+    for (int ia = 0; ia < np[s]; ++ia)
+      for (int ib = 0; ib < (unit ? 1 : np[t]); ++ib) {
+        const double a = exps[prim0[s] + ia], b = unit ? 0.0 : exps[prim0[t] + ib];
+        const double cab = coefs[prim0[s] + ia] * (unit ? 1.0 : coefs[prim0[t] + ib]);
+        const double p = a + b, mu = a * b / p, inv2p = 0.5 / p;
+        if (std::fabs(cab) * std::exp(-mu * AB2) < threshold) continue;
+        const size_t base = pool.size();
+        pool.resize(base + 5 + 3 * (size_t)esz, 0.0);
+        double* rec = &pool[base];
+        rec[0] = p;
+        for (int d = 0; d < 3; ++d) rec[1 + d] = (a * A[d] + b * B[d]) / p;
+        rec[4] = cab;
+        for (int d = 0; d < 3; ++d) {
+          double* E = rec + 5 + (size_t)d * esz;
+          const double Xpa = -b / p * AB[d], Xpb = a / p * AB[d];
+          E[0] = std::exp(-mu * AB[d] * AB[d]);
+          for (int i = 0; i <= la; ++i)
+            for (int j = 0; j <= lb; ++j) {
+              if (i == 0 && j == 0) continue;
+              const double* src = i > 0 ? E + (i - 1) * ej + j * T1 : E + (j - 1) * T1;
+              const double X = i > 0 ? Xpa : Xpb;
+              double* dst = E + i * ej + j * T1;
+              for (int tt = 0; tt <= i + j; ++tt) {
+                double v = 0.0;
+                if (tt <= i + j - 1) v += X * src[tt];
+                if (tt + 1 <= i + j - 1) v += (tt + 1) * src[tt + 1];
+                if (tt >= 1) v += inv2p * src[tt - 1];
+                dst[tt] = v;
+              }
+            }
+        }
+        ++written;
       }
-    return false;
+    return written;
   }
+  static int pair_record_doubles(int la, int lb) { return 5 + 3 * (la + 1) * (lb + 1) * (la + lb + 1); }
 };
+
+// Launch lists of a basis: every unordered shell pair once, oriented so that l_a >= l_b, pairs without a surviving
+// primitive pair dropped; or (unit = true) every shell with the unit partner.  Records go to pool.
+struct PairLists {
+  std::vector<PairEntry> entries;
+  std::vector<double> pool;
+  long long total = 0;  // pairs before screening
+};
+inline PairLists make_pair_lists(const HostBasis& h, bool unit) {
+  PairLists out;
+  for (int s = 0; s < h.nshell; ++s) {
+    if (unit) {
+      ++out.total;
+      PairEntry e{s, -1, 0, HostBasis::pair_record_doubles(h.l[s], 0), (long long)out.pool.size()};
+      e.npp = h.append_pair_records(s, -1, out.pool);
+      if (e.npp) out.entries.push_back(e);
+      continue;
+    }
+    for (int t = 0; t <= s; ++t) {
+      ++out.total;
+      const bool swap = h.l[t] > h.l[s];
+      const int x = swap ? t : s, y = swap ? s : t;
+      PairEntry e{x, y, 0, HostBasis::pair_record_doubles(h.l[x], h.l[y]), (long long)out.pool.size()};
+      e.npp = h.append_pair_records(x, y, out.pool);
+      if (e.npp) out.entries.push_back(e);
+    }
+  }
+  return out;
+}
 
 }  // namespace ao
 }  // namespace gwbse

@@ -26,20 +26,19 @@ struct WarpBarrier {
 };
 
 __global__ void __launch_bounds__(256)
-    ao3c_kernel(ao::BasisView dft, ao::BasisView aux, ao::TableView tb, const int2* __restrict__ pairs,
-                long long npairs, const int* __restrict__ aux_shells, int naux_shells, ao::OutSpec out, int ws_doubles,
-                double prim_threshold) {
+    ao3c_kernel(ao::BasisView dft, ao::BasisView aux, ao::TableView tb, const ao::PairEntry* __restrict__ pairs,
+                long long npairs, const double* __restrict__ pool, const int* __restrict__ aux_shells, int naux_shells,
+                ao::OutSpec out, int ws_doubles) {
   extern __shared__ double ao3c_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   if (w >= npairs * naux_shells) return;  // whole warps leave; the barriers below are warp-local
-  // consecutive warps share the shell pair (same E coefficients, neighbouring output rows)
+  // consecutive warps share the shell pair (same pair records in L1/L2, neighbouring output rows)
   const long long ip = w / naux_shells;
   const int ic = (int)(w % naux_shells);
-  const int2 pr = pairs[ip];
+  const ao::PairEntry pe = pairs[ip];
   WarpBarrier sync;
-  ao::triple_block(dft, aux, tb, pr.x, pr.y, aux_shells[ic], ao3c_smem + (size_t)warp * ws_doubles, lane, 32, sync, out,
-                   prim_threshold);
+  ao::triple_block(dft, aux, tb, pe, pool, aux_shells[ic], ao3c_smem + (size_t)warp * ws_doubles, lane, 32, sync, out);
 }
 
 template <typename T>
@@ -99,15 +98,17 @@ struct gwbse_basis {
   std::vector<int> by_l[ao::LMAX_SHELL + 1];
   int* by_l_dev[ao::LMAX_SHELL + 1] = {};
   int* no_aux_dev = nullptr;  // {-1}: "aux shell list" of the overlap launches
-  // shell pairs (x, y) with l_x >= l_y, every unordered pair once, grouped by (l_x, l_y)
+  // shell pairs (x, y) with l_x >= l_y, every unordered pair once, grouped by (l_x, l_y); their primitive-pair
+  // records (p, P, c_a c_b, E coefficients) in one pool.  Pairs without a surviving primitive pair are absent.
   struct PairClass {
     int la, lb;
     long long count;
-    int2* dev;
+    ao::PairEntry* dev;
+    const double* pool;
   };
   std::vector<PairClass> pair_classes;
   long long pairs_total = 0, pairs_kept = 0;  // before / after the shell-pair screening
-  // (x, -1): unit partner, grouped by l_x (two-centre integrals)
+  // (x, unit partner), grouped by l_x (two-centre integrals)
   std::vector<PairClass> unit_classes;
 
   ~gwbse_basis() {
@@ -138,24 +139,19 @@ void build_basis(gwbse_basis& b, int device) {
   for (int s = 0; s < h.nshell; ++s) b.by_l[h.l[s]].push_back(s);
   for (int l = 0; l <= ao::LMAX_SHELL; ++l) b.by_l_dev[l] = b.keep(upload(b.by_l[l]));
   b.no_aux_dev = b.keep(upload(std::vector<int>{-1}));
-  std::map<std::pair<int, int>, std::vector<int2>> groups;
-  std::map<int, std::vector<int2>> units;
-  for (int s = 0; s < h.nshell; ++s) {
-    units[h.l[s]].push_back(make_int2(s, -1));
-    for (int t = 0; t <= s; ++t) {
-      if (!h.pair_survives(s, t)) continue;  // far apart: every primitive pair is below the kernel's threshold
-      const bool swap = h.l[t] > h.l[s];
-      const int x = swap ? t : s, y = swap ? s : t;
-      groups[{h.l[x], h.l[y]}].push_back(make_int2(x, y));
-    }
-  }
-  b.pairs_total = (long long)h.nshell * (h.nshell + 1) / 2;
-  for (const auto& g : groups) b.pairs_kept += (long long)g.second.size();
-  // heaviest classes first: the long-running warps start early
-  for (auto it = groups.rbegin(); it != groups.rend(); ++it)
-    b.pair_classes.push_back({it->first.first, it->first.second, (long long)it->second.size(), b.keep(upload(it->second))});
-  for (auto it = units.rbegin(); it != units.rend(); ++it)
-    b.unit_classes.push_back({it->first, 0, (long long)it->second.size(), b.keep(upload(it->second))});
+  auto classify = [&](const ao::PairLists& pl, std::vector<gwbse_basis::PairClass>& classes) {
+    const double* pool = b.keep(upload(pl.pool));
+    std::map<std::pair<int, int>, std::vector<ao::PairEntry>> groups;
+    for (const ao::PairEntry& e : pl.entries) groups[{h.l[e.a], e.b < 0 ? 0 : h.l[e.b]}].push_back(e);
+    // heaviest classes first: the long-running warps start early
+    for (auto it = groups.rbegin(); it != groups.rend(); ++it)
+      classes.push_back({it->first.first, it->first.second, (long long)it->second.size(), b.keep(upload(it->second)), pool});
+  };
+  const ao::PairLists regular = ao::make_pair_lists(h, false);
+  b.pairs_total = regular.total;
+  b.pairs_kept = (long long)regular.entries.size();
+  classify(regular, b.pair_classes);
+  classify(ao::make_pair_lists(h, true), b.unit_classes);
 }
 
 int shared_memory_limit(gwbse_ctx* ctx) {
@@ -183,7 +179,7 @@ void launch_class(gwbse_ctx* ctx, const gwbse_basis& orb, const gwbse_basis::Pai
   const long long blocks = (warps + wpc - 1) / wpc;
   GW_REQUIRE(blocks < (1LL << 31), "too many shell triples for one launch; use smaller aux blocks");
   ao3c_kernel<<<(unsigned)blocks, wpc * 32, per_warp * wpc, ctx->stream>>>(
-      orb.view, aux.view, device_tables(ctx->device), pc.dev, pc.count, aux_shells_dev, n_aux_shells, out, wsd, ao::PRIM_THRESHOLD);
+      orb.view, aux.view, device_tables(ctx->device), pc.dev, pc.count, pc.pool, aux_shells_dev, n_aux_shells, out, wsd);
   GW_CUDA(cudaGetLastError());
   ctx->launches++;
 }
