@@ -145,7 +145,7 @@ def test_methane_def2svp_tier_r_matches_oracle(lib):
 def test_lanes_with_barriers_equal_serial(lib):
     w = helpers.water_integrals()
     serial = ao3c(lib, w["aux"], w["dft"], nl=1)
-    for nl in (2, 5, 32):
+    for nl in (2, 4, 5, 8, 16, 32):  # 4 / 8 / 16 / 32 are the lane-group sizes the launcher uses
         assert np.array_equal(serial, ao3c(lib, w["aux"], w["dft"], nl=nl)), nl
 
 

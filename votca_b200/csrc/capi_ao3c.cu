@@ -21,24 +21,31 @@ using namespace gwbse;
 
 namespace {
 
-struct WarpBarrier {
-  __device__ __forceinline__ void operator()() const { __syncwarp(); }
+// barrier of one lane group: the whole warp, or an aligned sub-group of 4 / 8 / 16 lanes that works on its own
+// shell triple (sub-groups may sit in different loop iterations; the mask names only the caller's group)
+struct GroupBarrier {
+  unsigned mask;
+  __device__ __forceinline__ void operator()() const { __syncwarp(mask); }
 };
 
+// group_lanes lanes per (shell pair, aux shell): 32 for the wide classes, fewer for classes whose widest stage has
+// only a handful of entries ((ss|s) has one) so that a warp carries 2 - 8 triples instead of idling 31 lanes
 __global__ void __launch_bounds__(256)
     ao3c_kernel(ao::BasisView dft, ao::BasisView aux, ao::TableView tb, const ao::PairEntry* __restrict__ pairs,
                 long long npairs, const double* __restrict__ pool, const int* __restrict__ aux_shells, int naux_shells,
-                ao::OutSpec out, int ws_doubles) {
+                ao::OutSpec out, int ws_doubles, int group_lanes) {
   extern __shared__ double ao3c_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
-  if (w >= npairs * naux_shells) return;  // whole warps leave; the barriers below are warp-local
-  // consecutive warps share the shell pair (same pair records in L1/L2, neighbouring output rows)
+  const int groups_per_warp = 32 / group_lanes, sub = lane / group_lanes, glane = lane % group_lanes;
+  const long long w = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * groups_per_warp + sub;
+  if (w >= npairs * naux_shells) return;  // whole groups leave; the barriers below are group-local
+  // consecutive groups share the shell pair (same pair records in L1/L2, neighbouring output rows)
   const long long ip = w / naux_shells;
   const int ic = (int)(w % naux_shells);
   const ao::PairEntry pe = pairs[ip];
-  WarpBarrier sync;
-  ao::triple_block(dft, aux, tb, pe, pool, aux_shells[ic], ao3c_smem + (size_t)warp * ws_doubles, lane, 32, sync, out);
+  GroupBarrier sync{group_lanes == 32 ? 0xffffffffu : (((1u << group_lanes) - 1u) << (sub * group_lanes))};
+  ao::triple_block(dft, aux, tb, pe, pool, aux_shells[ic],
+                   ao3c_smem + ((size_t)warp * groups_per_warp + sub) * ws_doubles, glane, group_lanes, sync, out);
 }
 
 template <typename T>
@@ -170,16 +177,23 @@ void launch_class(gwbse_ctx* ctx, const gwbse_basis& orb, const gwbse_basis::Pai
                   const int* aux_shells_dev, int n_aux_shells, int lc, const ao::OutSpec& out, int smem_limit) {
   GW_REQUIRE(pc.la + pc.lb + lc <= ao::LMAX_TOTAL, "angular momentum class beyond the Boys table");
   const int wsd = ao::workspace_doubles(pc.la, pc.lb, lc);
-  const size_t per_warp = sizeof(double) * (size_t)wsd;
+  // lanes per triple: the widest stage of the class (accumulators, aux-folded Hermite tensor, R tensor)
+  const int Lab = pc.la + pc.lb;
+  const int width = std::max({ao::nc_of(pc.la) * ao::nc_of(pc.lb) * ao::nc_of(lc), ao::nh_of(Lab) * ao::nc_of(lc),
+                              ao::nh_of(Lab + lc)});
+  const int gl = width <= 4 ? 4 : width <= 8 ? 8 : width <= 16 ? 16 : 32;
+  const int gpw = 32 / gl;
+  const size_t per_warp = sizeof(double) * (size_t)wsd * gpw;
   int wpc = 8;
   // aim at >= 4 resident CTAs per SM where the class is small enough, never exceed the opt-in limit
   while (wpc > 1 && per_warp * wpc > (size_t)smem_limit / 4) wpc >>= 1;
   GW_REQUIRE(per_warp * wpc <= (size_t)smem_limit, "integral class does not fit into shared memory");
-  const long long warps = pc.count * (long long)n_aux_shells;
-  const long long blocks = (warps + wpc - 1) / wpc;
+  const long long groups = pc.count * (long long)n_aux_shells;
+  const long long blocks = (groups + (long long)wpc * gpw - 1) / ((long long)wpc * gpw);
   GW_REQUIRE(blocks < (1LL << 31), "too many shell triples for one launch; use smaller aux blocks");
   ao3c_kernel<<<(unsigned)blocks, wpc * 32, per_warp * wpc, ctx->stream>>>(
-      orb.view, aux.view, device_tables(ctx->device), pc.dev, pc.count, pc.pool, aux_shells_dev, n_aux_shells, out, wsd);
+      orb.view, aux.view, device_tables(ctx->device), pc.dev, pc.count, pc.pool, aux_shells_dev, n_aux_shells, out, wsd,
+      gl);
   GW_CUDA(cudaGetLastError());
   ctx->launches++;
 }
