@@ -170,6 +170,10 @@ int gwbse_mmn_fill_end(gwbse_ctx* ctx);
  * shell order.  coefs must already contain libint's primitive normalisation and VOTCA's shell norm
  * (AOShell::normalizeContraction, aoshell.cc:81-89) - i.e. the numbers the libint2::Shell holds. */
 typedef struct gwbse_basis gwbse_basis;
+/* host helper (no device work): raw contraction factors of a basis-set file -> the coefs gwbse_basis_create
+ * expects, i.e. AOShell::LibintShell + AOShell::normalizeContraction (aoshell.cc:65-89) */
+int gwbse_basis_normalize(int nshell, const int* l, const int* nprim, const double* exps, const double* contractions,
+                          double* coefs_out);
 int gwbse_basis_create(gwbse_ctx* ctx, int nshell, const int* l, const int* nprim, const double* centers,
                        const double* exps, const double* coefs, gwbse_basis** out);
 int gwbse_basis_destroy(gwbse_ctx* ctx, gwbse_basis* basis);

@@ -155,6 +155,11 @@ long surviving_pairs_host(int nshell, const int* l, const int* nprim, const doub
   return (long)make_pair_lists(bs, false).entries.size();
 }
 
+int normalize_host(int l, int nprim, const double* exps, const double* raw, double* out) {
+  normalize_contraction(l, nprim, exps, raw, out);
+  return 0;
+}
+
 int boys_host(int n, double x, double* out) {
   static Tables tb;
   *out = boys_one(tb.view, n, x);

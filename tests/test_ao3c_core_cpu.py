@@ -39,6 +39,7 @@ def _bind(path):
     lib.overlap_host.argtypes = [i, p, p, p, p, p, p]
     lib.surviving_pairs_host.argtypes = [i, p, p, p, p, p]
     lib.surviving_pairs_host.restype = ctypes.c_long
+    lib.normalize_host.argtypes = [i, i, p, p, p]
     lib.boys_host.argtypes = [i, ctypes.c_double, p]
     lib.pure_matrix_host.argtypes = [i, p]
     return lib
@@ -109,6 +110,28 @@ def test_boys_function(lib):
             ref = mpmath.hyp1f1(n + 0.5, n + 1.5, -mpmath.mpf(float(x))) / (2 * n + 1)
             worst = max(worst, float(abs((mpmath.mpf(out.value) - ref) / ref)))
     assert worst < 1e-14, worst
+
+
+def test_contraction_normalisation_matches_oracle_basis(lib):
+    """normalize_contraction == oracle/basis.py (AOShell::LibintShell + normalizeContraction, aoshell.cc:65-89) for the
+    contracted s/p/d/f shells of def2-svp / aux-def2-svp and the G / I shells of the large-l fixtures."""
+    g = helpers.load_golden()
+    n = 0
+    for key, mol in (("def2-svp_CH", "methane_tutorial"), ("aux-def2-svp_CH", "methane_tutorial"), ("G", "C2"),
+                     ("I", "C2"), ("contracted", "C")):
+        raw = json.loads(str(g[f"basis/{key}.json"]))
+        ao = _golden_basis(key, mol)
+        shells = iter(ao.shells)
+        for el in [str(e) for e in g[f"molecule_{mol}/elements"]]:
+            for l, prims in raw[el]:
+                sh = next(shells)
+                ex = np.array([p[0] for p in prims], dtype=np.float64)
+                co = np.array([p[1] for p in prims], dtype=np.float64)
+                out = np.empty_like(ex)
+                lib.normalize_host(int(l), len(ex), ex.ctypes.data, co.ctypes.data, out.ctypes.data)
+                assert np.allclose(out, sh.coefs, rtol=1e-13, atol=0), (key, l)
+                n += 1
+    assert n > 40
 
 
 def test_pure_matrices_match_oracle(lib):

@@ -126,6 +126,32 @@ inline void fill_herm1(double g, double* e) {
     }
 }
 
+// The coefficients a libint2::Shell built by AOShell::LibintShell holds (xtp/src/libxtp/aoshell.cc:65-79) after
+// AOShell::normalizeContraction (aoshell.cc:81-89, called from AOBasis::Fill, aobasis.cc:99-100): the raw
+// contraction factors of the basis-set file times libint's primitive normalisation of x^l exp(-a r^2), the whole
+// contraction divided by the square root of the self-overlap of the shell's first function (libint's own unit
+// normalisation of contracted shells is switched off, libint2_calls.cc:168).  Racah-normalised solid harmonics
+// share the norm of x^l, so that self-overlap is the one of the x^l component.
+inline double double_factorial(int n) {
+  double r = 1.0;
+  for (int k = n; k > 1; k -= 2) r *= k;
+  return r;
+}
+inline void normalize_contraction(int l, int nprim, const double* exps, const double* raw, double* out) {
+  const double pi = 3.14159265358979323846;
+  const double df = double_factorial(2 * l - 1);
+  for (int p = 0; p < nprim; ++p)
+    out[p] = raw[p] * std::sqrt(std::pow(2.0, l) * std::pow(2.0 * exps[p], l + 1.5) / (std::pow(pi, 1.5) * df));
+  double s = 0.0;
+  for (int p = 0; p < nprim; ++p)
+    for (int q = 0; q < nprim; ++q) {
+      const double g = exps[p] + exps[q];
+      s += out[p] * out[q] * df / std::pow(2.0 * g, l) * std::pow(pi / g, 1.5);
+    }
+  const double inv = 1.0 / std::sqrt(s);
+  for (int p = 0; p < nprim; ++p) out[p] *= inv;
+}
+
 // Flat description of a basis as the kernels read it (host copy; capi_ao3c.cu uploads the vectors).
 struct HostBasis {
   int nshell = 0, nfunc = 0, nprim = 0, lmax = 0;

@@ -232,6 +232,18 @@ void ao3c_block_dev(gwbse_ctx* ctx, const gwbse_basis* aux, const gwbse_basis* d
 
 extern "C" {
 
+int gwbse_basis_normalize(int nshell, const int* l, const int* nprim, const double* exps, const double* contractions,
+                          double* coefs_out) {
+  if (nshell < 0 || !l || !nprim || !exps || !contractions || !coefs_out) return 1;
+  size_t p0 = 0;
+  for (int s = 0; s < nshell; ++s) {
+    if (l[s] < 0 || l[s] > ao::LMAX_SHELL || nprim[s] < 1) return 1;
+    ao::normalize_contraction(l[s], nprim[s], exps + p0, contractions + p0, coefs_out + p0);
+    p0 += (size_t)nprim[s];
+  }
+  return 0;
+}
+
 int gwbse_basis_create(gwbse_ctx* ctx, int nshell, const int* l, const int* nprim, const double* centers,
                        const double* exps, const double* coefs, gwbse_basis** out) {
   GW_API_BEGIN(ctx)

@@ -23,6 +23,13 @@ struct AOBasisData {
     for (int x : l) n += 2 * x + 1;
     return n;
   }
+  // raw contraction factors as they stand in a basis-set XML (basisset.cc:150-199) -> coefs
+  void NormalizeFromRawContractions(const std::vector<double>& contractions) {
+    if (contractions.size() != exps.size()) throw std::runtime_error("inconsistent basis description");
+    coefs.resize(exps.size());
+    if (gwbse_basis_normalize((int)l.size(), l.data(), nprim.data(), exps.data(), contractions.data(), coefs.data()))
+      throw std::runtime_error("invalid shell in basis description");
+  }
 };
 
 class DeviceAOBasis {
