@@ -53,6 +53,15 @@ def test_ao3c_water_spdf_aux(ctx):
     assert relmax(w["V"], ctx.ao_coulomb2c(aux)) < 1e-12
     assert relmax(w["S"], ctx.ao_overlap(aux)) < 1e-13
     assert relmax(w["S_dft"], ctx.ao_overlap(dft)) < 1e-13
+    # odd basis size (N = 13): fill_from_basis pads the device blocks to an even pitch
+    N = w["dft"].size
+    C = np.linalg.qr(np.random.default_rng(2).standard_normal((N, N)))[0]
+    ctx.mmn_alloc(w["aux"].size, 0, N - 1, 0, N - 1)
+    ctx.mmn_set_mos(C)
+    ctx.mmn_fill_from_basis(aux, dft, aux_block=10)
+    tc = threecenter.TCMatrix(w["aux"].size, 0, N - 1, 0, N - 1)
+    tc.fill_3c_mo(w["ao3c"], C)
+    assert helpers.rel_frob(tc.M, ctx.mmn_get_all()) < 1e-10
     ctx.basis_destroy(aux)
     ctx.basis_destroy(dft)
 

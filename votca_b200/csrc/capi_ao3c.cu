@@ -218,13 +218,16 @@ void launch_classes(gwbse_ctx* ctx, const gwbse_basis& orb, const std::vector<gw
   }
 }
 
+// pitch: doubles between consecutive columns of one N x N block (0 = N)
 void ao3c_block_dev(gwbse_ctx* ctx, const gwbse_basis* aux, const gwbse_basis* dft, int aux_offset, int aux_count,
-                    double* out_dev) {
+                    double* out_dev, long long pitch = 0) {
   GW_REQUIRE(aux && dft && out_dev, "null argument");
   const long long N = dft->host.nfunc;
-  if (dft->pairs_kept < dft->pairs_total && aux_count > 0)  // blocks of screened-out shell pairs are exact zeros
-    GW_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(double) * (size_t)(N * N) * (size_t)aux_count, ctx->stream));
-  ao::OutSpec out{out_dev, N * N, 1, N, aux_offset, aux_offset + aux_count, 1};
+  if (pitch == 0) pitch = N;
+  // blocks of screened-out shell pairs are exact zeros; so is the padding of a pitched block
+  if ((dft->pairs_kept < dft->pairs_total || pitch != N) && aux_count > 0)
+    GW_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(double) * (size_t)(pitch * N) * (size_t)aux_count, ctx->stream));
+  ao::OutSpec out{out_dev, pitch * N, 1, pitch, aux_offset, aux_offset + aux_count, 1};
   launch_classes(ctx, *dft, dft->pair_classes, *aux, aux_offset, aux_offset + aux_count, out);
 }
 
@@ -327,7 +330,9 @@ int gwbse_mmn_fill_from_basis(gwbse_ctx* ctx, const gwbse_basis* aux, const gwbs
   GW_REQUIRE(aux->host.nfunc == ctx->naux, "aux basis does not match the Mmn tensor");
   GW_REQUIRE(dft->host.nfunc == ctx->nbasis, "orbital basis does not match the MO coefficients (gwbse_mmn_set_mos)");
   if (aux_block < 1) aux_block = 64;
-  const size_t per = (size_t)ctx->nbasis * ctx->nbasis;
+  // even pitch: the contraction GEMM stages 16-byte vectors (an odd basis size would force 8-byte copies)
+  const long long pitch = (ctx->nbasis + 1) / 2 * 2;
+  const size_t per = (size_t)pitch * ctx->nbasis;
   // keep one block below 4 GiB
   aux_block = (int)std::max<size_t>(1, std::min<size_t>(aux_block, ((size_t)1 << 29) / std::max<size_t>(per, 1)));
   if (gwbse_mmn_fill_begin(ctx, ctx->world > 1 ? 1 : 0)) return 1;
@@ -341,10 +346,10 @@ int gwbse_mmn_fill_from_basis(gwbse_ctx* ctx, const gwbse_basis* aux, const gwbs
     const int cnt = std::min(aux_block, hi - a0);
     {
       GW_PROF(ctx, "ao3c_block");
-      ao3c_block_dev(ctx, aux, dft, a0, cnt, blk);
+      ao3c_block_dev(ctx, aux, dft, a0, cnt, blk, pitch);
     }
     // same stream: the contraction GEMMs of this block run after its integrals, the next block's integrals after them
-    if (gwbse_mmn_fill_block_dev(ctx, a0, cnt, blk)) return 1;
+    mmn_fill_block_pitched(ctx, a0, cnt, blk, pitch);
   }
   if (gwbse_mmn_fill_end(ctx)) return 1;
   GW_API_END(ctx)

@@ -28,11 +28,14 @@ void ensure_x2(gwbse_ctx* ctx) {
   GW_CUDA(cudaMalloc(&ctx->X2, bytes));
 }
 
-void fill_block_dev(gwbse_ctx* ctx, int aux_offset, int aux_count, const double* ao3c_dev) {
+// pitch: doubles between consecutive columns of one N x N block (blocks are pitch * N apart); 0 = N (contiguous)
+void fill_block_dev(gwbse_ctx* ctx, int aux_offset, int aux_count, const double* ao3c_dev, long long pitch = 0) {
   require_mmn(ctx);
   GW_REQUIRE(ctx->mos != nullptr, "MO coefficients not set (gwbse_mmn_set_mos)");
   GW_REQUIRE(aux_offset >= 0 && aux_offset + aux_count <= ctx->naux, "aux block out of range");
   const int N = ctx->nbasis;
+  if (pitch == 0) pitch = N;
+  GW_REQUIRE(pitch >= N, "AO block pitch smaller than the basis size");
   GW_REQUIRE(ctx->mmax < ctx->nmo && ctx->nmax < ctx->nmo, "level range exceeds number of MOs");
   if (aux_count == 0) return;
   const bool sh = ctx->fill_sharded;
@@ -54,10 +57,10 @@ void fill_block_dev(gwbse_ctx* ctx, int aux_offset, int aux_count, const double*
     p.N = mcols;
     p.Ki = N;
     p.Z1 = nb;
-    p.A.ptr = ao3c_dev + (size_t)b0 * N * N;
-    p.A.s_ri = N;
+    p.A.ptr = ao3c_dev + (size_t)b0 * pitch * N;
+    p.A.s_ri = pitch;
     p.A.s_ki = 1;
-    p.A.s_z1 = (long long)N * N;
+    p.A.s_z1 = pitch * N;
     p.B.ptr = ctx->mos + (size_t)(ctx->mmin + (sh ? 0 : ctx->rank)) * Np;
     p.B.s_ri = (long long)(sh ? 1 : ctx->world) * Np;
     p.B.s_ki = 1;
@@ -95,6 +98,18 @@ void fill_block_dev(gwbse_ctx* ctx, int aux_offset, int aux_count, const double*
   }
   ctx->mmn_version++;
 }
+
+}  // namespace
+
+namespace gwbse {
+// capi_ao3c.cu: blocks produced on the device carry an even pitch so the contraction takes 16-byte copies
+void mmn_fill_block_pitched(gwbse_ctx* ctx, int aux_offset, int aux_count, const double* ao3c_dev, long long pitch) {
+  GW_PROF(ctx, "mmn_fill_block");
+  fill_block_dev(ctx, aux_offset, aux_count, ao3c_dev, pitch);
+}
+}  // namespace gwbse
+
+namespace {
 
 void mul_right_dev(gwbse_ctx* ctx, const double* R_dev, int ldr) {
   require_mmn(ctx);

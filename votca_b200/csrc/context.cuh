@@ -225,6 +225,8 @@ namespace gwbse {
 // ranks into out[(p-p0)*ldo + (s-s0)*rpad + (row-row0)] in natural slice order (ldo >= ns*rpad)
 void gather_slices(gwbse_ctx* ctx, int s0, int ns, int row0, int nrows, int p0, int np, double* out, long long ldo,
                    int rpad);
+// Fill3cMO contraction of a device-resident AO block whose columns are pitch doubles apart (capi_mmn.cu)
+void mmn_fill_block_pitched(gwbse_ctx* ctx, int aux_offset, int aux_count, const double* ao3c_dev, long long pitch);
 // NCCL plumbing (comm.cu)
 void allreduce_dev(gwbse_ctx* ctx, double* buf_dev, size_t n);
 void allgather_dev(gwbse_ctx* ctx, const double* send_dev, double* recv_dev, size_t n_per_rank);
