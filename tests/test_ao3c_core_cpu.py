@@ -203,6 +203,49 @@ def test_shell_pair_screening_far_apart_fragments(lib):
     assert np.all(got[:, :half, half:] == 0.0) and np.abs(ref[:, :half, half:]).max() < 1e-30
 
 
+def _rotated(ao, R, shift):
+    import copy
+    out = copy.deepcopy(ao)
+    for sh in out.shells:
+        sh.center = R @ sh.center + shift
+    return out
+
+
+@pytest.mark.parametrize("case", ["methane-def2svp", "G-I"])
+def test_rotational_and_translational_invariance(lib, case):
+    """Independent of any reference data (SURVEY.md 8c asks for it where libint parity is unpinned, i.e. beyond p
+    shells): under a rigid rotation + translation the functions of every pure shell mix by an orthogonal matrix, so
+    the Frobenius norm of each (aux shell | shell, shell) block, and the spectra of the overlap and two-centre
+    Coulomb matrices, must not change.  Exercises the solid-harmonic transformation and the angular recursions of
+    every l combination in the basis (up to f aux / d orbital, and (G G | I))."""
+    if case == "methane-def2svp":
+        c = helpers.methane_svp_case()
+        aux, dft = c["aux"], c["dft"]
+    else:
+        aux, dft = _golden_basis("I", "C2"), _golden_basis("G", "C2")
+    rng = np.random.default_rng(11)
+    R = np.linalg.qr(rng.standard_normal((3, 3)))[0]
+    if np.linalg.det(R) < 0:
+        R[:, 0] *= -1.0
+    shift = np.array([0.7, -1.3, 2.1])
+    aux2, dft2 = _rotated(aux, R, shift), _rotated(dft, R, shift)
+    T0, T1 = ao3c(lib, aux, dft), ao3c(lib, aux2, dft2)
+    worst, scale = 0.0, np.abs(T0).max()
+    for sc in aux.shells:
+        for sa in dft.shells:
+            for sb in dft.shells:
+                blk = (slice(sc.start, sc.start + sc.nfunc), slice(sa.start, sa.start + sa.nfunc),
+                       slice(sb.start, sb.start + sb.nfunc))
+                n0, n1 = np.linalg.norm(T0[blk]), np.linalg.norm(T1[blk])
+                # blocks that vanish by symmetry are 1e-14 noise: measure against the block or 1e-3 of the largest
+                worst = max(worst, abs(n0 - n1) / max(n0, 1e-3 * scale))
+    assert worst < 1e-10, worst
+    assert not np.allclose(T0, T1, atol=1e-3)  # the individual integrals do change
+    for f in (overlap, coulomb2c):
+        w0, w1 = np.linalg.eigvalsh(f(lib, aux)), np.linalg.eigvalsh(f(lib, aux2))
+        assert np.abs(w0 - w1).max() < 1e-10 * np.abs(w0).max()
+
+
 def test_thread_sanitizer_finds_no_race():
     """Same source, 8 lanes on threads, under -fsanitize=thread: a missing barrier between two stages that share
     scratch would be reported as a data race (TSan exits non-zero)."""
