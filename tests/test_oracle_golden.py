@@ -322,3 +322,20 @@ def test_ppm_parameters(golden, methane):
     s.prepare_screening()
     assert rel_frob(golden["inline/ppm_freq"], s.ppm_freq) < 1e-4
     assert rel_frob(golden["inline/ppm_weight"], s.ppm_weight) < 1e-4
+
+
+def test_oracle_boys_function_against_multiprecision():
+    """The oracle's Boys function (series + downward recursion, erf + upward recursion beyond x = 35) against
+    40-digit arithmetic; it anchors every Coulomb integral above."""
+    import mpmath
+    from oracle import integrals
+    mpmath.mp.dps = 40
+    rng = np.random.default_rng(0)
+    xs = np.concatenate([[0.0, 1e-9, 0.3, 34.999, 35.0, 35.001, 80.0, 1000.0], rng.uniform(0, 60, 60)])
+    F = integrals.boys(16, xs)
+    worst = 0.0
+    for n in (0, 1, 5, 10, 16):
+        for i, x in enumerate(xs):
+            ref = mpmath.hyp1f1(n + 0.5, n + 1.5, -mpmath.mpf(float(x))) / (2 * n + 1)
+            worst = max(worst, float(abs((mpmath.mpf(float(F[n, i])) - ref) / ref)))
+    assert worst < 1e-14, worst
