@@ -15,7 +15,7 @@ namespace {
 
 struct Tables {
   std::vector<double> boys, pure;
-  std::vector<uint8_t> tuv;
+  std::vector<uint32_t> tuv;
   TableView view{};
   Tables() {
     boys = make_boys_table();

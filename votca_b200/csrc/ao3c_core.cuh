@@ -38,7 +38,7 @@ struct BasisView {
 
 struct TableView {
   const double* boys;    // [points][orders]
-  const uint8_t* tuv;    // [nherm][4]
+  const uint32_t* tuv;   // [nherm]: t | u << 8 | v << 16
   const double* pure;    // concatenated (2l+1) x ncart(l) matrices
   int pure_off[8];
   int boys_orders, boys_taylor, herm1_stride, herm1_dim;
@@ -66,6 +66,11 @@ struct PairEntry {
 
 AO_HD int nc_of(int l) { return (l + 1) * (l + 2) / 2; }
 AO_HD int nh_of(int L) { return (L + 1) * (L + 2) * (L + 3) / 6; }
+AO_HD void unpack_tuv(uint32_t w, int& t, int& u, int& v) {
+  t = (int)(w & 0xffu);
+  u = (int)((w >> 8) & 0xffu);
+  v = (int)((w >> 16) & 0xffu);
+}
 AO_HD int hidx(int t, int u, int v) {
   const int N = t + u + v, w = u + v;
   return N * (N + 1) * (N + 2) / 6 + w * (w + 1) / 2 + v;
@@ -129,9 +134,14 @@ AO_HD void triple_block(const BasisView& dft, const BasisView& aux, const TableV
   const double Cx = overlap ? 0.0 : aux.center[3 * sc], Cy = overlap ? 0.0 : aux.center[3 * sc + 1],
                Cz = overlap ? 0.0 : aux.center[3 * sc + 2];
   const int pc0 = overlap ? 0 : aux.prim0[sc], nprc = overlap ? 0 : aux.np[sc];
-  const uint8_t* cart_a = tb.tuv + 4 * nh_of(la - 1);
-  const uint8_t* cart_b = tb.tuv + 4 * nh_of(lb - 1);
-  const uint8_t* cart_c = tb.tuv + 4 * nh_of(lc - 1);
+  const uint32_t* cart_a = tb.tuv + nh_of(la - 1);  // the degree-l entries are the cartesian components
+  const uint32_t* cart_b = tb.tuv + nh_of(lb - 1);
+  const uint32_t* cart_c = tb.tuv + nh_of(lc - 1);
+  // lane-strided walks over (h, c) and (ja, jb, c) item spaces without per-item divisions: start decomposition
+  // and step decomposition are fixed per lane and class
+  const int step_q = nl / ncc, step_r = nl % ncc;            // it += nl  ->  (it / ncc, it % ncc) += (q, r) + carry
+  const int step_q2 = step_q / ncb, step_r2 = step_q % ncb;  // ab += q   ->  (ab / ncb, ab % ncb) += (q2, r2)
+  const int c0 = lane % ncc, ab0 = lane / ncc, ja0 = ab0 / ncb, jb0 = ab0 % ncb;
   const double sgn_c = (lc & 1) ? -1.0 : 1.0;  // (-1)^(tau+nu+phi): the aux Hermite indices have the parity of lc
   const int H1 = tb.herm1_dim;
 
@@ -150,8 +160,9 @@ AO_HD void triple_block(const BasisView& dft, const BasisView& aux, const TableV
         const double pref = cab * 5.568327996831708 / (p * sqrt(p));  // pi^(3/2)
         for (int it = lane; it < nca * ncb; it += nl) {
           const int ja = it / ncb, jb = it % ncb;
-          const int ax = cart_a[4 * ja], ay = cart_a[4 * ja + 1], az = cart_a[4 * ja + 2];
-          const int bx = cart_b[4 * jb], by = cart_b[4 * jb + 1], bz = cart_b[4 * jb + 2];
+          int ax, ay, az, bx, by, bz;
+          unpack_tuv(cart_a[ja], ax, ay, az);
+          unpack_tuv(cart_b[jb], bx, by, bz);
           acc[it] += pref * E[ax * ej + bx * T1] * E[esz + ay * ej + by * T1] * E[2 * esz + az * ej + bz * T1];
         }
         sync();
@@ -175,7 +186,8 @@ AO_HD void triple_block(const BasisView& dft, const BasisView& aux, const TableV
           const double* prev = R + ((n + 1) & 1) * nhL;
           const int cnt = nh_of(L - n);
           for (int h = lane; h < cnt; h += nl) {
-            const int t = tb.tuv[4 * h], u = tb.tuv[4 * h + 1], v = tb.tuv[4 * h + 2];
+            int t, u, v;
+            unpack_tuv(tb.tuv[h], t, u, v);
             double val;
             if (h == 0) {
               val = seed[n];
@@ -195,10 +207,10 @@ AO_HD void triple_block(const BasisView& dft, const BasisView& aux, const TableV
         }
         // ---- G[h][c] = pref * sum_{tau nu phi} (-1)^(..) e_c R_{t+tau,u+nu,v+phi} ---------------------------
         const double* e1 = aux.herm1 + (long long)(pc0 + ic) * tb.herm1_stride;
-        for (int it = lane; it < nhab * ncc; it += nl) {
-          const int h = it / ncc, c = it % ncc;
-          const int t = tb.tuv[4 * h], u = tb.tuv[4 * h + 1], v = tb.tuv[4 * h + 2];
-          const int cx = cart_c[4 * c], cy = cart_c[4 * c + 1], cz = cart_c[4 * c + 2];
+        for (int it = lane, h = ab0, c = c0; it < nhab * ncc; it += nl) {
+          int t, u, v, cx, cy, cz;
+          unpack_tuv(tb.tuv[h], t, u, v);
+          unpack_tuv(cart_c[c], cx, cy, cz);
           double s = 0.0;
           for (int tau = cx & 1; tau <= cx; tau += 2) {
             const double ex = e1[cx * H1 + tau];
@@ -209,14 +221,16 @@ AO_HD void triple_block(const BasisView& dft, const BasisView& aux, const TableV
             }
           }
           G[it] = pref * sgn_c * s;
+          h += step_q;
+          c += step_r;
+          if (c >= ncc) c -= ncc, ++h;
         }
         sync();
         // ---- acc[a][b][c] += sum_{tuv} Ex Ey Ez G[tuv][c] ---------------------------------------------------
-        for (int it = lane; it < nca * ncb * ncc; it += nl) {
-          const int c = it % ncc, ab = it / ncc;
-          const int ja = ab / ncb, jb = ab % ncb;
-          const int ax = cart_a[4 * ja], ay = cart_a[4 * ja + 1], az = cart_a[4 * ja + 2];
-          const int bx = cart_b[4 * jb], by = cart_b[4 * jb + 1], bz = cart_b[4 * jb + 2];
+        for (int it = lane, c = c0, ja = ja0, jb = jb0; it < nca * ncb * ncc; it += nl) {
+          int ax, ay, az, bx, by, bz;
+          unpack_tuv(cart_a[ja], ax, ay, az);
+          unpack_tuv(cart_b[jb], bx, by, bz);
           const double* Ex = E + ax * ej + bx * T1;
           const double* Ey = E + esz + ay * ej + by * T1;
           const double* Ez = E + 2 * esz + az * ej + bz * T1;
@@ -227,6 +241,11 @@ AO_HD void triple_block(const BasisView& dft, const BasisView& aux, const TableV
               for (int v = 0; v <= az + bz; ++v) s += exy * Ez[v] * G[hidx(t, u, v) * ncc + c];
             }
           acc[it] += s;
+          c += step_r;
+          jb += step_r2;
+          ja += step_q2;
+          if (c >= ncc) c -= ncc, ++jb;
+          if (jb >= ncb) jb -= ncb, ++ja;
         }
         sync();
       }

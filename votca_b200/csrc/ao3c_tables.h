@@ -33,16 +33,14 @@ inline int nherm(int L) { return (L + 1) * (L + 2) * (L + 3) / 6; }
 
 // (t,u,v) of Hermite index h in the degree-major order hidx(t,u,v) = N(N+1)(N+2)/6 + (u+v)(u+v+1)/2 + v,
 // N = t+u+v.  The entries of degree l are the cartesian components of a shell in libint order.
-inline std::vector<uint8_t> make_tuv_table() {
-  std::vector<uint8_t> tab((size_t)nherm(LMAX_TOTAL) * 4, 0);
+inline std::vector<uint32_t> make_tuv_table() {
+  std::vector<uint32_t> tab((size_t)nherm(LMAX_TOTAL), 0);
   for (int N = 0; N <= LMAX_TOTAL; ++N)
     for (int t = N; t >= 0; --t)
       for (int u = N - t; u >= 0; --u) {
         const int v = N - t - u;
         const int h = N * (N + 1) * (N + 2) / 6 + (u + v) * (u + v + 1) / 2 + v;
-        tab[(size_t)h * 4 + 0] = (uint8_t)t;
-        tab[(size_t)h * 4 + 1] = (uint8_t)u;
-        tab[(size_t)h * 4 + 2] = (uint8_t)v;
+        tab[(size_t)h] = (uint32_t)t | ((uint32_t)u << 8) | ((uint32_t)v << 16);
       }
   return tab;
 }

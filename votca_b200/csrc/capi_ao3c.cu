@@ -60,7 +60,7 @@ T* upload(const std::vector<T>& v) {
 struct DeviceTables {
   double* boys = nullptr;
   double* pure = nullptr;
-  uint8_t* tuv = nullptr;
+  uint32_t* tuv = nullptr;
   ao::TableView view{};
 };
 std::map<int, DeviceTables>& table_store() {
