@@ -160,6 +160,23 @@ int normalize_host(int l, int nprim, const double* exps, const double* raw, doub
   return 0;
 }
 
+// per surviving shell pair: l of both shells and the number of primitive-pair records (workload statistics)
+long pair_stats_host(int nshell, const int* l, const int* nprim, const double* center, const double* exps,
+                     const double* coefs, long cap, int* la, int* lb, int* npp) {
+  HostBasis bs;
+  bs.build(nshell, l, nprim, center, exps, coefs);
+  const PairLists pl = make_pair_lists(bs, false);
+  long n = 0;
+  for (const PairEntry& e : pl.entries) {
+    if (n >= cap) break;
+    la[n] = bs.l[e.a];
+    lb[n] = bs.l[e.b];
+    npp[n] = e.npp;
+    ++n;
+  }
+  return (long)pl.entries.size();
+}
+
 int boys_host(int n, double x, double* out) {
   static Tables tb;
   *out = boys_one(tb.view, n, x);
