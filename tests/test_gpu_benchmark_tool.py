@@ -1,0 +1,36 @@
+"""The gpu_benchmark tool (votca_b200/tools/gpu_benchmark.py), the counterpart of the reference's
+`xtp_tools -e gpu_benchmark` (xtp/src/libxtp/tools/gpu_benchmark.cc): statistics / output format on the CPU, one small
+run on the GPU."""
+import xml.etree.ElementTree as ET
+
+import pytest
+
+from votca_b200.tools import gpu_benchmark as gb
+
+NAMES = ["Filling_ThreeCenter", "Multiplication_of_tensor_with_matrix", "RPA_evaluation", "SingletOperator_TDA",
+         "TripletOperator_TDA", "SingletOperator_BTDA_B", "HxOperator"]
+
+
+def test_statistics_and_xml_layout():
+    mean, std = gb.calc_statistics([1.0, 2.0, 3.0, 4.0])  # population std, gpu_benchmark.cc:45-50
+    assert mean == 2.5 and abs(std - 1.25 ** 0.5) < 1e-15
+    calls = []
+    part = gb.run_part(lambda: calls.append(1), "RPA_evaluation", 3, lambda: None)
+    assert part[0] == "RPA_evaluation" and len(part[3]) == 3 and len(calls) == 3
+    root = ET.fromstring(gb.to_xml({"Repetitions": 3, "GPUs": 1}, [part]))
+    assert root.tag == "GPU_Benchmark" and root.find("Repetitions").text == "3"
+    node = root.find("RPA_evaluation")
+    assert float(node.find("avg").text) >= 0.0 and len(node.find("runs").findall("timing")) == 3
+    # the operator template arguments of bse_operator.h:79-87
+    assert dict(gb.OPERATORS) == {"SingletOperator_TDA": (1, 2, 1, 0), "TripletOperator_TDA": (1, 0, 1, 0),
+                                  "SingletOperator_BTDA_B": (0, 2, 0, 1), "HxOperator": (0, 1, 0, 0)}
+
+
+@pytest.mark.gpu
+def test_small_run_writes_all_parts(tmp_path):
+    out = tmp_path / "gpu_benchmark.xml"
+    parts = gb.main(["--workload", "tiny", "--repetitions", "2", "--outputfile", str(out), "--spacesize", "7"])
+    assert [p[0] for p in parts] == NAMES
+    root = ET.parse(out).getroot()
+    assert [c.tag for c in root if c.find("avg") is not None] == NAMES
+    assert all(float(root.find(n).find("avg").text) > 0.0 for n in NAMES)
