@@ -106,6 +106,38 @@ int ao3c_host(int nshell, const int* l, const int* nprim, const double* center, 
   }
 }
 
+// The launcher's path for a request of aux functions [f0, f1) (capi_ao3c.cu: launch_classes): aux shells picked per
+// angular momentum by aux_shell_range, every pair list entry against each of them, output restricted to the range.
+// out[k - f0][nu][mu], pitch doubles between columns.
+int ao3c_range_host(int nshell, const int* l, const int* nprim, const double* center, const double* exps,
+                    const double* coefs, int nshell_aux, const int* l_aux, const int* nprim_aux, const double* center_aux,
+                    const double* exps_aux, const double* coefs_aux, int f0, int f1, long pitch, double* out) {
+  try {
+    static Tables tb;
+    HostBasis dft, aux;
+    dft.build(nshell, l, nprim, center, exps, coefs);
+    aux.build(nshell_aux, l_aux, nprim_aux, center_aux, exps_aux, coefs_aux);
+    const BasisView dv = view_of(dft), av = view_of(aux);
+    const long long N = dft.nfunc;
+    if (pitch == 0) pitch = N;
+    std::vector<int> by_l[LMAX_SHELL + 1];
+    for (int s = 0; s < aux.nshell; ++s) by_l[aux.l[s]].push_back(s);
+    const AuxShellRange r = aux_shell_range(aux.func0, by_l, f0, f1);
+    OutSpec spec{out, pitch * N, 1, pitch, f0, f1, 1};
+    std::fill(out, out + (size_t)std::max(f1 - f0, 0) * pitch * N, 0.0);
+    std::vector<double> ws((size_t)workspace_doubles(dft.lmax, dft.lmax, aux.lmax) + 8, -7.0e300);
+    const PairLists pl = make_pair_lists(dft, false);
+    NoSync s;
+    for (int lc = LMAX_SHELL; lc >= 0; --lc)
+      for (const PairEntry& pe : pl.entries)
+        for (int i = r.first[lc]; i < r.last[lc]; ++i)
+          triple_block(dv, av, tb.view, pe, pl.pool.data(), by_l[lc][i], ws.data(), 0, 1, s, spec);
+    return 0;
+  } catch (...) {
+    return 1;
+  }
+}
+
 // V[q][p] = (p | q) over one basis: unit partner
 int coulomb2c_host(int nshell, const int* l, const int* nprim, const double* center, const double* exps,
                    const double* coefs, double* out) {

@@ -36,6 +36,7 @@ def _bind(path):
     p, i = ctypes.c_void_p, ctypes.c_int
     lib.ao3c_host.argtypes = [i, p, p, p, p, p, i, p, p, p, p, p, i, p]
     lib.coulomb2c_host.argtypes = [i, p, p, p, p, p, p]
+    lib.ao3c_range_host.argtypes = [i, p, p, p, p, p, i, p, p, p, p, p, i, i, ctypes.c_long, p]
     lib.overlap_host.argtypes = [i, p, p, p, p, p, p]
     lib.surviving_pairs_host.argtypes = [i, p, p, p, p, p]
     lib.surviving_pairs_host.restype = ctypes.c_long
@@ -156,6 +157,23 @@ def test_water_spdf_aux_matches_oracle(lib):
     assert relmax(w["V"], coulomb2c(lib, w["aux"])) < 1e-12
     assert relmax(w["S"], overlap(lib, w["aux"])) < 1e-13
     assert relmax(w["S_dft"], overlap(lib, w["dft"])) < 1e-13
+
+
+def test_function_ranges_cutting_through_shells_and_pitched_blocks(lib):
+    """gwbse_ao3c_block takes aux FUNCTION ranges: shells cut by the range are computed but only the functions inside
+    are written (to the right slot), for every start / length, also with a padded column pitch."""
+    w = helpers.water_integrals()
+    d, a = pack(w["dft"]), pack(w["aux"])
+    N, naux = w["dft"].size, w["aux"].size
+    for f0, f1, pitch in [(0, naux, 0), (3, 10, 0), (0, 1, 0), (naux - 2, naux, 0), (5, 5, 0), (7, 31, N + 1),
+                          (1, naux - 1, N + 3)]:
+        P = pitch or N
+        out = np.full((max(f1 - f0, 0), N, P), np.nan)
+        rc = lib.ao3c_range_host(len(d[0]), *_ptrs(d), len(a[0]), *_ptrs(a), f0, f1, pitch, out.ctypes.data)
+        assert rc == 0
+        if f1 > f0:
+            assert relmax(w["ao3c"][f0:f1], out[:, :, :N]) < 1e-12, (f0, f1, pitch)
+            assert np.all(out[:, :, N:] == 0.0)
 
 
 def test_methane_def2svp_tier_r_matches_oracle(lib):

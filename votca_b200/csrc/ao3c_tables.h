@@ -7,6 +7,7 @@
 // AOShell::LibintShell (xtp/src/libxtp/aoshell.cc:65-79, contr.pure = true), functions ordered m = -l..l
 // (aoshell.cc:116-133), cartesian components in libint's standard order (lx descending, then ly descending).
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <stdexcept>
@@ -236,6 +237,25 @@ struct HostBasis {
   }
   static int pair_record_doubles(int la, int lb) { return 5 + 3 * (la + 1) * (lb + 1) * (la + lb + 1); }
 };
+
+// Which aux shells a request for the aux FUNCTIONS [f0, f1) touches, per angular momentum: shells [s0, s1) overlap
+// the range (shells at the ends may be cut; the kernel writes only functions inside the range), and since by_l[l]
+// lists the shells of one l in ascending order they are the contiguous piece [first[l], last[l]) of each list.
+struct AuxShellRange {
+  int first[LMAX_SHELL + 1], last[LMAX_SHELL + 1];
+};
+inline AuxShellRange aux_shell_range(const std::vector<int>& func0, const std::vector<int> (&by_l)[LMAX_SHELL + 1], int f0,
+                                     int f1) {
+  AuxShellRange r{};
+  const int s0 = int(std::upper_bound(func0.begin(), func0.end(), f0) - func0.begin()) - 1;
+  const int s1 = int(std::lower_bound(func0.begin(), func0.end(), f1) - func0.begin());
+  for (int l = 0; l <= LMAX_SHELL; ++l) {
+    r.first[l] = int(std::lower_bound(by_l[l].begin(), by_l[l].end(), s0) - by_l[l].begin());
+    r.last[l] = int(std::lower_bound(by_l[l].begin(), by_l[l].end(), s1) - by_l[l].begin());
+    if (f1 <= f0) r.last[l] = r.first[l];
+  }
+  return r;
+}
 
 // Launch lists of a basis: every unordered shell pair once, oriented so that l_a >= l_b, pairs without a surviving
 // primitive pair dropped; or (unit = true) every shell with the unit partner.  Records go to pool.

@@ -204,17 +204,12 @@ void launch_classes(gwbse_ctx* ctx, const gwbse_basis& orb, const std::vector<gw
   GW_REQUIRE(orb.device == ctx->device && aux.device == ctx->device, "basis belongs to another device");
   GW_REQUIRE(f0 >= 0 && f1 <= aux.host.nfunc && f0 <= f1, "aux function range out of bounds");
   if (f0 == f1) return;
-  // shells [s0, s1) overlap the function range
-  const std::vector<int>& fn0 = aux.host.func0;
-  const int s0 = int(std::upper_bound(fn0.begin(), fn0.end(), f0) - fn0.begin()) - 1;
-  const int s1 = int(std::lower_bound(fn0.begin(), fn0.end(), f1) - fn0.begin());
+  const ao::AuxShellRange r = ao::aux_shell_range(aux.host.func0, aux.by_l, f0, f1);
   const int smem_limit = shared_memory_limit(ctx);
   for (int lc = ao::LMAX_SHELL; lc >= 0; --lc) {
-    const std::vector<int>& list = aux.by_l[lc];
-    const int i0 = int(std::lower_bound(list.begin(), list.end(), s0) - list.begin());
-    const int i1 = int(std::lower_bound(list.begin(), list.end(), s1) - list.begin());
-    if (i1 <= i0) continue;
-    for (const auto& pc : classes) launch_class(ctx, orb, pc, aux, aux.by_l_dev[lc] + i0, i1 - i0, lc, out, smem_limit);
+    if (r.last[lc] <= r.first[lc]) continue;
+    for (const auto& pc : classes)
+      launch_class(ctx, orb, pc, aux, aux.by_l_dev[lc] + r.first[lc], r.last[lc] - r.first[lc], lc, out, smem_limit);
   }
 }
 
