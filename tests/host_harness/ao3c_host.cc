@@ -209,6 +209,18 @@ long pair_stats_host(int nshell, const int* l, const int* nprim, const double* c
   return (long)pl.entries.size();
 }
 
+// out[6]: group_lanes, groups_per_warp, warps_per_cta, ws_doubles, smem_bytes, fits
+int launch_config_host(int la, int lb, int lc, long smem_limit, long* out) {
+  const LaunchConfig c = launch_config(la, lb, lc, (size_t)smem_limit);
+  out[0] = c.group_lanes;
+  out[1] = c.groups_per_warp;
+  out[2] = c.warps_per_cta;
+  out[3] = c.ws_doubles;
+  out[4] = (long)c.smem_bytes;
+  out[5] = c.fits ? 1 : 0;
+  return 0;
+}
+
 int boys_host(int n, double x, double* out) {
   static Tables tb;
   *out = boys_one(tb.view, n, x);

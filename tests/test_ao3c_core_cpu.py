@@ -37,6 +37,7 @@ def _bind(path):
     lib.ao3c_host.argtypes = [i, p, p, p, p, p, i, p, p, p, p, p, i, p]
     lib.coulomb2c_host.argtypes = [i, p, p, p, p, p, p]
     lib.ao3c_range_host.argtypes = [i, p, p, p, p, p, i, p, p, p, p, p, i, i, ctypes.c_long, p]
+    lib.launch_config_host.argtypes = [i, i, i, ctypes.c_long, p]
     lib.overlap_host.argtypes = [i, p, p, p, p, p, p]
     lib.surviving_pairs_host.argtypes = [i, p, p, p, p, p]
     lib.surviving_pairs_host.restype = ctypes.c_long
@@ -174,6 +175,31 @@ def test_function_ranges_cutting_through_shells_and_pitched_blocks(lib):
         if f1 > f0:
             assert relmax(w["ao3c"][f0:f1], out[:, :, :N]) < 1e-12, (f0, f1, pitch)
             assert np.all(out[:, :, N:] == 0.0)
+
+
+def test_launch_geometry_of_every_class(lib):
+    """Every class up to (g g | i) gets a launch that fits the 227 KB opt-in shared memory of sm_100 and at most 256
+    threads; narrow classes share a warp between 2 - 8 triples, small ones keep several CTAs per SM."""
+    limit = 232448
+    out = (ctypes.c_long * 6)()
+    seen = set()
+    for la in range(5):
+        for lb in range(la + 1):
+            for lc in range(7):
+                lib.launch_config_host(la, lb, lc, limit, out)
+                gl, gpw, wpc, wsd, smem, fits = list(out)
+                assert fits == 1 and smem <= limit and smem == 8 * wsd * gpw * wpc, (la, lb, lc)
+                assert gl in (4, 8, 16, 32) and gl * gpw == 32 and 1 <= wpc <= 8
+                nc = lambda l: (l + 1) * (l + 2) // 2  # noqa: E731
+                assert gl == 32 or nc(la) * nc(lb) * nc(lc) <= gl
+                if smem * 4 <= limit:
+                    assert wpc == 8 or 2 * smem * 4 > limit  # as many warps as the quarter-SM budget allows
+                seen.add(gl)
+    assert seen == {4, 16, 32}  # widths are max(accumulators, G, nherm(L)); nherm(L) = 1, 4, 10, 20, ... skips 8
+    lib.launch_config_host(0, 0, 0, limit, out)
+    assert list(out)[:3] == [4, 8, 8]
+    lib.launch_config_host(4, 4, 6, limit, out)
+    assert list(out)[:3] == [32, 1, 1] and out[4] > 100000
 
 
 def test_methane_def2svp_tier_r_matches_oracle(lib):

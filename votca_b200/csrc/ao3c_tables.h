@@ -238,6 +238,29 @@ struct HostBasis {
   static int pair_record_doubles(int la, int lb) { return 5 + 3 * (la + 1) * (lb + 1) * (la + lb + 1); }
 };
 
+// Launch geometry of one angular-momentum class (l_a >= l_b | l_c): lanes per shell triple = the widest stage of the
+// class (accumulators, aux-folded Hermite tensor G, R tensor) rounded up to 4 / 8 / 16 / 32, warps per CTA so that
+// about four CTAs share an SM's shared memory where the class is small enough, never more than the opt-in limit.
+struct LaunchConfig {
+  int group_lanes, groups_per_warp, warps_per_cta, ws_doubles;
+  size_t smem_bytes;
+  bool fits;
+};
+inline LaunchConfig launch_config(int la, int lb, int lc, size_t smem_limit) {
+  LaunchConfig c{};
+  c.ws_doubles = workspace_doubles(la, lb, lc);
+  const int Lab = la + lb;
+  const int width = std::max({ncart(la) * ncart(lb) * ncart(lc), nherm(Lab) * ncart(lc), nherm(Lab + lc)});
+  c.group_lanes = width <= 4 ? 4 : width <= 8 ? 8 : width <= 16 ? 16 : 32;
+  c.groups_per_warp = 32 / c.group_lanes;
+  const size_t per_warp = sizeof(double) * (size_t)c.ws_doubles * c.groups_per_warp;
+  c.warps_per_cta = 8;
+  while (c.warps_per_cta > 1 && per_warp * c.warps_per_cta > smem_limit / 4) c.warps_per_cta >>= 1;
+  c.smem_bytes = per_warp * c.warps_per_cta;
+  c.fits = c.smem_bytes <= smem_limit;
+  return c;
+}
+
 // Which aux shells a request for the aux FUNCTIONS [f0, f1) touches, per angular momentum: shells [s0, s1) overlap
 // the range (shells at the ends may be cut; the kernel writes only functions inside the range), and since by_l[l]
 // lists the shells of one l in ascending order they are the contiguous piece [first[l], last[l]) of each list.

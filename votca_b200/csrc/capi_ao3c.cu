@@ -176,24 +176,15 @@ int shared_memory_limit(gwbse_ctx* ctx) {
 void launch_class(gwbse_ctx* ctx, const gwbse_basis& orb, const gwbse_basis::PairClass& pc, const gwbse_basis& aux,
                   const int* aux_shells_dev, int n_aux_shells, int lc, const ao::OutSpec& out, int smem_limit) {
   GW_REQUIRE(pc.la + pc.lb + lc <= ao::LMAX_TOTAL, "angular momentum class beyond the Boys table");
-  const int wsd = ao::workspace_doubles(pc.la, pc.lb, lc);
-  // lanes per triple: the widest stage of the class (accumulators, aux-folded Hermite tensor, R tensor)
-  const int Lab = pc.la + pc.lb;
-  const int width = std::max({ao::nc_of(pc.la) * ao::nc_of(pc.lb) * ao::nc_of(lc), ao::nh_of(Lab) * ao::nc_of(lc),
-                              ao::nh_of(Lab + lc)});
-  const int gl = width <= 4 ? 4 : width <= 8 ? 8 : width <= 16 ? 16 : 32;
-  const int gpw = 32 / gl;
-  const size_t per_warp = sizeof(double) * (size_t)wsd * gpw;
-  int wpc = 8;
-  // aim at >= 4 resident CTAs per SM where the class is small enough, never exceed the opt-in limit
-  while (wpc > 1 && per_warp * wpc > (size_t)smem_limit / 4) wpc >>= 1;
-  GW_REQUIRE(per_warp * wpc <= (size_t)smem_limit, "integral class does not fit into shared memory");
+  const ao::LaunchConfig cfg = ao::launch_config(pc.la, pc.lb, lc, (size_t)smem_limit);
+  GW_REQUIRE(cfg.fits, "integral class does not fit into shared memory");
   const long long groups = pc.count * (long long)n_aux_shells;
-  const long long blocks = (groups + (long long)wpc * gpw - 1) / ((long long)wpc * gpw);
+  const long long per_cta = (long long)cfg.warps_per_cta * cfg.groups_per_warp;
+  const long long blocks = (groups + per_cta - 1) / per_cta;
   GW_REQUIRE(blocks < (1LL << 31), "too many shell triples for one launch; use smaller aux blocks");
-  ao3c_kernel<<<(unsigned)blocks, wpc * 32, per_warp * wpc, ctx->stream>>>(
-      orb.view, aux.view, device_tables(ctx->device), pc.dev, pc.count, pc.pool, aux_shells_dev, n_aux_shells, out, wsd,
-      gl);
+  ao3c_kernel<<<(unsigned)blocks, cfg.warps_per_cta * 32, cfg.smem_bytes, ctx->stream>>>(
+      orb.view, aux.view, device_tables(ctx->device), pc.dev, pc.count, pc.pool, aux_shells_dev, n_aux_shells, out,
+      cfg.ws_doubles, cfg.group_lanes);
   GW_CUDA(cudaGetLastError());
   ctx->launches++;
 }
