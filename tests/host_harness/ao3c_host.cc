@@ -4,6 +4,8 @@
 #include <algorithm>
 #include <barrier>
 #include <cstring>
+#include <map>
+#include <memory>
 #include <thread>
 #include <vector>
 
@@ -132,6 +134,66 @@ int ao3c_range_host(int nshell, const int* l, const int* nprim, const double* ce
       for (const PairEntry& pe : pl.entries)
         for (int i = r.first[lc]; i < r.last[lc]; ++i)
           triple_block(dv, av, tb.view, pe, pl.pool.data(), by_l[lc][i], ws.data(), 0, 1, s, spec);
+    return 0;
+  } catch (...) {
+    return 1;
+  }
+}
+
+// The whole launch sequence of capi_ao3c.cu emulated on the CPU for a request of aux functions [f0, f1): pair entries
+// grouped by class exactly as build_basis does, one "launch" per (l_c, class) with launch_config's geometry, every
+// CTA / warp / lane of the grid run through cta_thread - 32 threads play the lanes of a warp and walk over all warps
+// of all CTAs, lane groups synchronise on their own std::barrier.  Only the CUDA runtime calls are left out.
+int ao3c_grid_host(int nshell, const int* l, const int* nprim, const double* center, const double* exps,
+                   const double* coefs, int nshell_aux, const int* l_aux, const int* nprim_aux, const double* center_aux,
+                   const double* exps_aux, const double* coefs_aux, int f0, int f1, long pitch, double* out) {
+  try {
+    static Tables tb;
+    HostBasis dft, aux;
+    dft.build(nshell, l, nprim, center, exps, coefs);
+    aux.build(nshell_aux, l_aux, nprim_aux, center_aux, exps_aux, coefs_aux);
+    const BasisView dv = view_of(dft), av = view_of(aux);
+    const long long N = dft.nfunc;
+    if (pitch == 0) pitch = N;
+    std::vector<int> by_l[LMAX_SHELL + 1];
+    for (int s = 0; s < aux.nshell; ++s) by_l[aux.l[s]].push_back(s);
+    const AuxShellRange r = aux_shell_range(aux.func0, by_l, f0, f1);
+    OutSpec spec{out, pitch * N, 1, pitch, f0, f1, 1};
+    std::fill(out, out + (size_t)std::max(f1 - f0, 0) * pitch * N, 0.0);
+    const PairLists pl = make_pair_lists(dft, false);
+    std::map<std::pair<int, int>, std::vector<PairEntry>> classes;
+    for (const PairEntry& e : pl.entries) classes[{dft.l[e.a], dft.l[e.b]}].push_back(e);
+    const size_t smem_limit = 232448;
+    struct HostSyncFactory {
+      std::vector<std::unique_ptr<std::barrier<>>>* bars;
+      BarrierSync operator()(int sub, int) const { return BarrierSync{(*bars)[sub].get()}; }
+    };
+    for (int lc = LMAX_SHELL; lc >= 0; --lc) {
+      const int naux_shells = r.last[lc] - r.first[lc];
+      if (naux_shells <= 0) continue;
+      for (auto it = classes.rbegin(); it != classes.rend(); ++it) {
+        const LaunchConfig cfg = launch_config(it->first.first, it->first.second, lc, smem_limit);
+        if (!cfg.fits) return 2;
+        const std::vector<PairEntry>& pairs = it->second;
+        const long long groups = (long long)pairs.size() * naux_shells;
+        const long long per_cta = (long long)cfg.warps_per_cta * cfg.groups_per_warp;
+        const long long blocks = (groups + per_cta - 1) / per_cta;
+        std::vector<double> smem(cfg.smem_bytes / sizeof(double), -7.0e300);
+        std::vector<std::unique_ptr<std::barrier<>>> bars;
+        for (int g = 0; g < cfg.groups_per_warp; ++g) bars.emplace_back(new std::barrier<>(cfg.group_lanes));
+        std::vector<std::thread> lanes;
+        for (int lane = 0; lane < 32; ++lane)
+          lanes.emplace_back([&, lane] {
+            HostSyncFactory sf{&bars};
+            for (long long b = 0; b < blocks; ++b)
+              for (int w = 0; w < cfg.warps_per_cta; ++w)
+                cta_thread(b, cfg.warps_per_cta, w * 32 + lane, dv, av, tb.view, pairs.data(), (long long)pairs.size(),
+                           pl.pool.data(), by_l[lc].data() + r.first[lc], naux_shells, spec, cfg.ws_doubles,
+                           cfg.group_lanes, smem.data(), sf);
+          });
+        for (auto& t : lanes) t.join();
+      }
+    }
     return 0;
   } catch (...) {
     return 1;

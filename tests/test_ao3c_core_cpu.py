@@ -37,6 +37,7 @@ def _bind(path):
     lib.ao3c_host.argtypes = [i, p, p, p, p, p, i, p, p, p, p, p, i, p]
     lib.coulomb2c_host.argtypes = [i, p, p, p, p, p, p]
     lib.ao3c_range_host.argtypes = [i, p, p, p, p, p, i, p, p, p, p, p, i, i, ctypes.c_long, p]
+    lib.ao3c_grid_host.argtypes = [i, p, p, p, p, p, i, p, p, p, p, p, i, i, ctypes.c_long, p]
     lib.launch_config_host.argtypes = [i, i, i, ctypes.c_long, p]
     lib.overlap_host.argtypes = [i, p, p, p, p, p, p]
     lib.surviving_pairs_host.argtypes = [i, p, p, p, p, p]
@@ -177,6 +178,21 @@ def test_function_ranges_cutting_through_shells_and_pitched_blocks(lib):
             assert np.all(out[:, :, N:] == 0.0)
 
 
+def test_emulated_launch_grid_equals_oracle(lib):
+    """The launcher's whole sequence on the CPU - classes, launch geometry, CTA / warp / lane-group indexing of
+    ao::cta_thread (the kernel body), group barriers - for the full tensor and for a range that cuts through shells,
+    with a padded pitch.  What stays untested without a device are the CUDA runtime calls themselves."""
+    w = helpers.water_integrals()
+    d, a = pack(w["dft"]), pack(w["aux"])
+    N, naux = w["dft"].size, w["aux"].size
+    for f0, f1, pitch in [(0, naux, 0), (4, 37, N + 1)]:
+        P = pitch or N
+        out = np.full((f1 - f0, N, P), np.nan)
+        assert lib.ao3c_grid_host(len(d[0]), *_ptrs(d), len(a[0]), *_ptrs(a), f0, f1, pitch, out.ctypes.data) == 0
+        assert relmax(w["ao3c"][f0:f1], out[:, :, :N]) < 1e-12
+        assert np.all(out[:, :, N:] == 0.0)
+
+
 def test_launch_geometry_of_every_class(lib):
     """Every class up to (g g | i) gets a launch that fits the 227 KB opt-in shared memory of sm_100 and at most 256
     threads; narrow classes share a warp between 2 - 8 triples, small ones keep several CTAs per SM."""
@@ -308,6 +324,8 @@ def test_thread_sanitizer_finds_no_race():
         "out = np.zeros((n, n, n))\n"
         "pt = [x.ctypes.data for x in a]\n"
         "rc = lib.ao3c_host(ns, *pt, ns, *pt, 8, out.ctypes.data)\n"
+        "lib.ao3c_grid_host.argtypes = [i, p, p, p, p, p, i, p, p, p, p, p, i, i, ctypes.c_long, p]\n"
+        "rc |= lib.ao3c_grid_host(ns, *pt, ns, *pt, 0, n, 0, out.ctypes.data)  # lane groups of 4 / 16 / 32 side by side\n"
         "sys.exit(rc)\n")
     tsan_rt = subprocess.run(["g++", "-print-file-name=libtsan.so"], capture_output=True, text=True).stdout.strip()
     env = dict(os.environ, LD_PRELOAD=tsan_rt, TSAN_OPTIONS="exitcode=66 halt_on_error=1")

@@ -291,5 +291,24 @@ AO_HD void triple_block(const BasisView& dft, const BasisView& aux, const TableV
   }
 }
 
+// What one thread of the launch does: thread tid of CTA `block` (nwarps warps) belongs to lane group `sub` of its warp;
+// group g = (block * nwarps + warp) * groups_per_warp + sub works on shell pair g / naux_shells and aux shell
+// aux_shells[g % naux_shells] (consecutive groups share the pair: same records in L1/L2, neighbouring output rows)
+// with its own slice of the CTA's scratch.  sync_of(sub, group_lanes) hands out the group's barrier.
+template <class SyncFactory>
+AO_HD void cta_thread(long long block, int nwarps, int tid, const BasisView& dft, const BasisView& aux, const TableView& tb,
+                      const PairEntry* pairs, long long npairs, const double* pool, const int* aux_shells,
+                      int naux_shells, const OutSpec& out, int ws_doubles, int group_lanes, double* scratch,
+                      SyncFactory& sync_of) {
+  const int warp = tid >> 5, lane = tid & 31;
+  const int groups_per_warp = 32 / group_lanes, sub = lane / group_lanes, glane = lane % group_lanes;
+  const long long g = (block * nwarps + warp) * groups_per_warp + sub;
+  if (g >= npairs * naux_shells) return;  // whole groups leave; the barriers are group-local
+  const PairEntry pe = pairs[g / naux_shells];
+  auto sync = sync_of(sub, group_lanes);
+  triple_block(dft, aux, tb, pe, pool, aux_shells[(int)(g % naux_shells)],
+               scratch + ((long long)warp * groups_per_warp + sub) * ws_doubles, glane, group_lanes, sync, out);
+}
+
 }  // namespace ao
 }  // namespace gwbse

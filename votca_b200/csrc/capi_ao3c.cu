@@ -21,31 +21,29 @@ using namespace gwbse;
 
 namespace {
 
-// barrier of one lane group: the whole warp, or an aligned sub-group of 4 / 8 / 16 lanes that works on its own
-// shell triple (sub-groups may sit in different loop iterations; the mask names only the caller's group)
+// barrier of one lane group: the whole warp, or an aligned sub-group of 4 / 16 lanes that works on its own shell
+// triple (sub-groups may sit in different loop iterations; the mask names only the caller's group)
 struct GroupBarrier {
   unsigned mask;
   __device__ __forceinline__ void operator()() const { __syncwarp(mask); }
 };
+struct GroupBarrierFactory {
+  __device__ __forceinline__ GroupBarrier operator()(int sub, int group_lanes) const {
+    return GroupBarrier{group_lanes == 32 ? 0xffffffffu : (((1u << group_lanes) - 1u) << (sub * group_lanes))};
+  }
+};
 
 // group_lanes lanes per (shell pair, aux shell): 32 for the wide classes, fewer for classes whose widest stage has
-// only a handful of entries ((ss|s) has one) so that a warp carries 2 - 8 triples instead of idling 31 lanes
+// only a handful of entries ((ss|s) has one) so that a warp carries several triples instead of idling 31 lanes.
+// The indexing lives in ao::cta_thread (shared with the CPU harness).
 __global__ void __launch_bounds__(256)
     ao3c_kernel(ao::BasisView dft, ao::BasisView aux, ao::TableView tb, const ao::PairEntry* __restrict__ pairs,
                 long long npairs, const double* __restrict__ pool, const int* __restrict__ aux_shells, int naux_shells,
                 ao::OutSpec out, int ws_doubles, int group_lanes) {
   extern __shared__ double ao3c_smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int groups_per_warp = 32 / group_lanes, sub = lane / group_lanes, glane = lane % group_lanes;
-  const long long w = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * groups_per_warp + sub;
-  if (w >= npairs * naux_shells) return;  // whole groups leave; the barriers below are group-local
-  // consecutive groups share the shell pair (same pair records in L1/L2, neighbouring output rows)
-  const long long ip = w / naux_shells;
-  const int ic = (int)(w % naux_shells);
-  const ao::PairEntry pe = pairs[ip];
-  GroupBarrier sync{group_lanes == 32 ? 0xffffffffu : (((1u << group_lanes) - 1u) << (sub * group_lanes))};
-  ao::triple_block(dft, aux, tb, pe, pool, aux_shells[ic],
-                   ao3c_smem + ((size_t)warp * groups_per_warp + sub) * ws_doubles, glane, group_lanes, sync, out);
+  GroupBarrierFactory sync_of;
+  ao::cta_thread((long long)blockIdx.x, (int)(blockDim.x >> 5), (int)threadIdx.x, dft, aux, tb, pairs, npairs, pool,
+                 aux_shells, naux_shells, out, ws_doubles, group_lanes, ao3c_smem, sync_of);
 }
 
 template <typename T>
