@@ -3,6 +3,7 @@
 run on the GPU."""
 import xml.etree.ElementTree as ET
 
+import numpy as np
 import pytest
 
 from votca_b200.tools import gpu_benchmark as gb
@@ -24,6 +25,49 @@ def test_statistics_and_xml_layout():
     # the operator template arguments of bse_operator.h:79-87
     assert dict(gb.OPERATORS) == {"SingletOperator_TDA": (1, 2, 1, 0), "TripletOperator_TDA": (1, 0, 1, 0),
                                   "SingletOperator_BTDA_B": (0, 2, 0, 1), "HxOperator": (0, 1, 0, 0)}
+
+
+class _RecordingContext:
+    """Stands in for votca_b200.api.Context on the CPU: records the call sequence, returns arrays of the right shape.
+    It checks the tool's own plumbing (argument order, shapes, part sequence), nothing numerical."""
+
+    def __init__(self, device=0):
+        self.calls = []
+
+    def __getattr__(self, name):
+        def method(*args):
+            self.calls.append(name)
+            if name == "mmn_alloc":
+                self.naux = args[0]
+            if name == "pseudo_invsqrt":
+                return np.eye(args[0].shape[0]), 0
+            if name == "rpa_epsilon":
+                return np.eye(self.naux)
+            if name == "bse_configure":
+                homo, rpamin, vmin, cmax, eps_inv, hqp = args
+                assert eps_inv.shape == (self.naux,) and hqp.shape == (cmax - vmin + 1, cmax - vmin + 1)
+                self.bse_size = (homo - vmin + 1) * (cmax - homo)
+            if name == "bse_matmul":
+                assert args[1].shape[0] == self.bse_size
+                return np.zeros_like(args[1])
+            return None
+        return method
+
+
+def test_tool_plumbing_on_the_cpu(tmp_path, monkeypatch):
+    import votca_b200.api as api
+    made = []
+
+    def factory(device=0):
+        made.append(_RecordingContext(device))
+        return made[-1]
+    monkeypatch.setattr(api, "Context", factory)
+    out = tmp_path / "gb.xml"
+    parts = gb.main(["--workload", "tiny", "--repetitions", "2", "--outputfile", str(out), "--spacesize", "3"])
+    assert [p[0] for p in parts] == NAMES and len(parts[0][3]) == 2
+    calls = made[0].calls
+    assert calls.count("bse_matmul") == 8 and calls.count("rpa_epsilon") == 4 and calls.count("mmn_fill_block") == 3 * 2
+    assert calls[-1] == "close" and ET.parse(out).getroot().find("HxOperator") is not None
 
 
 @pytest.mark.gpu
