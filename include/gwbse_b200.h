@@ -190,6 +190,10 @@ int gwbse_ao3c_block(gwbse_ctx* ctx, const gwbse_basis* aux, const gwbse_basis* 
 int gwbse_ao_coulomb2c(gwbse_ctx* ctx, const gwbse_basis* aux, double* V, int ld);
 /* AOOverlap::Fill (libint2_calls.cc:163-165): S(mu, nu) = <mu | nu>, n x n to the host */
 int gwbse_ao_overlap(gwbse_ctx* ctx, const gwbse_basis* basis, double* S, int ld);
+/* AODipole::Fill (libint2 Operator::emultipole1; input of Orbitals::CalcFreeTransition_Dipoles,
+ * orbitals.cc:742-760): D[k](mu, nu) = <mu | r_k | nu> about the origin, k = x, y, z: three n x n matrices (ld x n
+ * doubles each, one after the other) to the host */
+int gwbse_ao_dipole(gwbse_ctx* ctx, const gwbse_basis* basis, double* D, int ld);
 /* TCMatrix_gwbse::Fill3cMO (libint2_calls.cc:595-651) with the integral producer on the GPU: blocks of aux_block
  * aux functions are computed into a device buffer and contracted from there (gwbse_mmn_fill_block_dev); no AO
  * integral crosses PCIe.  Needs gwbse_mmn_alloc + gwbse_mmn_set_mos.  Multi-GPU: every rank produces and

@@ -53,7 +53,8 @@ int gwbse_job_set_ao3c_partial(gwbse_job* job, long nbasis, long naux, long firs
  * gwbse_ao_coulomb2c - the device stand-ins for ComputeAO3cBlock / AOCoulomb::Fill, libint2_calls.cc:544-593,
  * 224-271): which = "dft" or "aux", arguments as gwbse_basis_create.  Used when both are set and no ao3c array or
  * callback is; "aux_overlap" and "aux_coulomb" then become optional (computed on the device: gwbse_ao_overlap,
- * gwbse_ao_coulomb2c). */
+ * gwbse_ao_coulomb2c), and so do "dipole_x|y|z" (AO dipoles from gwbse_ao_dipole, interlevel dipoles formed as
+ * Orbitals::CalcFreeTransition_Dipoles does). */
 int gwbse_job_set_basis(gwbse_job* job, const char* which, int nshell, const int* l, const int* nprim,
                         const double* centers, const double* exps, const double* coefs);
 /* Results as an .orb checkpoint: gwbse_job_run (rank 0) writes /QMdata with the names and HDF5 types of

@@ -283,6 +283,29 @@ int launch_config_host(int la, int lb, int lc, long smem_limit, long* out) {
   return 0;
 }
 
+// D[k][nu][mu] = <mu | r_k | nu>, k = x, y, z, about the origin
+int dipole_host(int nshell, const int* l, const int* nprim, const double* center, const double* exps,
+                const double* coefs, double* out) {
+  try {
+    static Tables tb;
+    HostBasis bs;
+    bs.build(nshell, l, nprim, center, exps, coefs);
+    const BasisView v = view_of(bs);
+    const long long N = bs.nfunc;
+    std::fill(out, out + (size_t)3 * N * N, 0.0);
+    std::vector<double> ws((size_t)workspace_doubles(bs.lmax, bs.lmax, 0) + 8, -7.0e300);
+    NoSync s;
+    const PairLists pl = make_pair_lists(bs, false);
+    for (int k = 0; k < 3; ++k) {
+      OutSpec spec{out + (size_t)k * N * N, 0, 1, N, 0, 1, 1};
+      for (const PairEntry& pe : pl.entries) triple_block(v, v, tb.view, pe, pl.pool.data(), -2 - k, ws.data(), 0, 1, s, spec);
+    }
+    return 0;
+  } catch (...) {
+    return 1;
+  }
+}
+
 int boys_host(int n, double x, double* out) {
   static Tables tb;
   *out = boys_one(tb.view, n, x);

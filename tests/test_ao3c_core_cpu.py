@@ -39,6 +39,7 @@ def _bind(path):
     lib.ao3c_range_host.argtypes = [i, p, p, p, p, p, i, p, p, p, p, p, i, i, ctypes.c_long, p]
     lib.ao3c_grid_host.argtypes = [i, p, p, p, p, p, i, p, p, p, p, p, i, i, ctypes.c_long, p]
     lib.launch_config_host.argtypes = [i, i, i, ctypes.c_long, p]
+    lib.dipole_host.argtypes = [i, p, p, p, p, p, p]
     lib.overlap_host.argtypes = [i, p, p, p, p, p, p]
     lib.surviving_pairs_host.argtypes = [i, p, p, p, p, p]
     lib.surviving_pairs_host.restype = ctypes.c_long
@@ -86,6 +87,13 @@ def overlap(lib, ao):
     a = pack(ao)
     out = np.full((ao.size, ao.size), np.nan)
     assert lib.overlap_host(len(a[0]), *_ptrs(a), out.ctypes.data) == 0
+    return out
+
+
+def dipole(lib, ao):
+    a = pack(ao)
+    out = np.full((3, ao.size, ao.size), np.nan)
+    assert lib.dipole_host(len(a[0]), *_ptrs(a), out.ctypes.data) == 0
     return out
 
 
@@ -216,6 +224,17 @@ def test_launch_geometry_of_every_class(lib):
     assert list(out)[:3] == [4, 8, 8]
     lib.launch_config_host(4, 4, 6, limit, out)
     assert list(out)[:3] == [32, 1, 1] and out[4] > 100000
+
+
+def test_dipole_integrals_match_oracle(lib):
+    """<mu | r | nu> about the origin (AODipole, the input of Orbitals::CalcFreeTransition_Dipoles, orbitals.cc:742-760)
+    against the oracle, whose dipoles are pinned on the reference's G-shell fixture (test_aomatrix3d.cc:91-123)."""
+    w = helpers.water_integrals()
+    assert relmax(w["dipole"], dipole(lib, w["dft"])) < 1e-13
+    c = helpers.methane_svp_case()
+    assert relmax(c["dipole"], dipole(lib, c["dft"])) < 1e-13
+    g = _golden_basis("G", "C2")
+    assert relmax(integrals.dipole(g), dipole(lib, g)) < 1e-12
 
 
 def test_methane_def2svp_tier_r_matches_oracle(lib):

@@ -53,6 +53,7 @@ def test_ao3c_water_spdf_aux(ctx):
     assert relmax(w["V"], ctx.ao_coulomb2c(aux)) < 1e-12
     assert relmax(w["S"], ctx.ao_overlap(aux)) < 1e-13
     assert relmax(w["S_dft"], ctx.ao_overlap(dft)) < 1e-13
+    assert relmax(w["dipole"], ctx.ao_dipole(dft)) < 1e-13
     # odd basis size (N = 13): fill_from_basis pads the device blocks to an even pitch
     N = w["dft"].size
     C = np.linalg.qr(np.random.default_rng(2).standard_normal((N, N)))[0]
@@ -116,13 +117,21 @@ def test_job_from_basis_sets_equals_job_from_arrays():
             job.set_ao3c(c["ao3c"])
             job.set_array("aux_overlap", c["S"])
             job.set_array("aux_coulomb", c["V"])
+            ct, vt = q - homo - 1, homo + 1
+            C = hf["mos"]
+            for ax, D in zip("xyz", c["dipole"]):
+                job.set_array("dipole_" + ax, C[:, homo + 1:homo + 1 + ct].T @ D @ C[:, :vt])
         job.set_options(tasks="gw,singlets", gw__mode="G0W0", gw__sigma_integrator="ppm", bse__exctotal=5,
                         bse__useTDA=True)
         job.run()
-        res.append((job.get("QPpert_energies").ravel().copy(), job.get("BSE_singlet_eigenvalues").ravel().copy()))
+        res.append((job.get("QPpert_energies").ravel().copy(), job.get("BSE_singlet_eigenvalues").ravel().copy(),
+                    job.get("oscillator_strengths").ravel().copy()))
         job.close()
     assert np.abs(res[0][0] - res[1][0]).max() < 1e-9
     assert np.abs(res[0][1] - res[1][1]).max() < 1e-9
+    # oscillator strengths: interlevel dipoles given (oracle AO dipoles) vs AO dipoles produced on the device; the
+    # lowest singlets of methane are degenerate (T2), so compare the sum over the shell
+    assert res[1][2].size == 5 and abs(res[0][2].sum() - res[1][2].sum()) < 1e-7
 
 
 def test_basis_errors(ctx):

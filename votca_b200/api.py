@@ -209,6 +209,13 @@ class Context:
         self.call("gwbse_ao_overlap", basis, ptr(out), n)
         return out
 
+    def ao_dipole(self, basis):
+        """(3, n, n): <mu | r_k | nu> about the origin."""
+        n = self.basis_size(basis)
+        out = np.empty((3, n, n))
+        self.call("gwbse_ao_dipole", basis, ptr(out), n)
+        return out
+
     def mmn_fill_from_basis(self, aux, dft, aux_block=64):
         self.call("gwbse_mmn_fill_from_basis", aux, dft, int(aux_block))
 

@@ -107,13 +107,16 @@ AO_HD double boys_one(const TableView& tb, int n, double x) {
 }
 
 // pe.b < 0: unit partner -> two-centre integrals (sc | a)
-// sc < 0:   no Coulomb operator at all -> overlap <a | b> (AOOverlap::Fill, libint2_calls.cc:163-165), written as
+// sc = -1:  no Coulomb operator at all -> overlap <a | b> (AOOverlap::Fill, libint2_calls.cc:163-165), written as
 //           "aux function" 0
+// sc = -2, -3, -4:  dipole <a | x | b>, <a | y | b>, <a | z | b> about the origin (AODipole::Fill, libint2
+//           Operator::emultipole1), likewise
 template <class Sync>
 AO_HD void triple_block(const BasisView& dft, const BasisView& aux, const TableView& tb, const PairEntry& pe,
                         const double* pool, int sc, double* ws, int lane, int nl, Sync& sync, const OutSpec& out) {
   const int sa = pe.a, sb = pe.b;
   const bool unit_b = sb < 0, overlap = sc < 0;
+  const int dipole_dir = -2 - sc;  // 0, 1, 2 for the dipole components, -1 for the plain overlap
   const int la = dft.l[sa], lb = unit_b ? 0 : dft.l[sb], lc = overlap ? 0 : aux.l[sc];
   const int Lab = la + lb, L = Lab + lc;
   const int nca = nc_of(la), ncb = nc_of(lb), ncc = nc_of(lc);
@@ -156,14 +159,22 @@ AO_HD void triple_block(const BasisView& dft, const BasisView& aux, const TableV
       for (int i = lane; i < 3 * esz; i += nl) E[i] = rec[5 + i];
       sync();
       if (overlap) {
-        // <a|b> += c_a c_b (pi/p)^(3/2) E^x_0 E^y_0 E^z_0
+        // <a|b> += c_a c_b (pi/p)^(3/2) E^x_0 E^y_0 E^z_0;  dipole along d: E^d_0 -> E^d_1 + P_d E^d_0
         const double pref = cab * 5.568327996831708 / (p * sqrt(p));  // pi^(3/2)
+        const double Pd = dipole_dir == 0 ? Px : (dipole_dir == 1 ? Py : Pz);
         for (int it = lane; it < nca * ncb; it += nl) {
           const int ja = it / ncb, jb = it % ncb;
           int ax, ay, az, bx, by, bz;
           unpack_tuv(cart_a[ja], ax, ay, az);
           unpack_tuv(cart_b[jb], bx, by, bz);
-          acc[it] += pref * E[ax * ej + bx * T1] * E[esz + ay * ej + by * T1] * E[2 * esz + az * ej + bz * T1];
+          const double* Ex = E + ax * ej + bx * T1;
+          const double* Ey = E + esz + ay * ej + by * T1;
+          const double* Ez = E + 2 * esz + az * ej + bz * T1;
+          double fx = Ex[0], fy = Ey[0], fz = Ez[0];
+          if (dipole_dir == 0) fx = (ax + bx >= 1 ? Ex[1] : 0.0) + Pd * Ex[0];
+          if (dipole_dir == 1) fy = (ay + by >= 1 ? Ey[1] : 0.0) + Pd * Ey[0];
+          if (dipole_dir == 2) fz = (az + bz >= 1 ? Ez[1] : 0.0) + Pd * Ez[0];
+          acc[it] += pref * fx * fy * fz;
         }
         sync();
       }

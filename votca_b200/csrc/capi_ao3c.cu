@@ -102,7 +102,7 @@ struct gwbse_basis {
   // shells of one angular momentum, ascending (a function range maps to a contiguous piece of each list)
   std::vector<int> by_l[ao::LMAX_SHELL + 1];
   int* by_l_dev[ao::LMAX_SHELL + 1] = {};
-  int* no_aux_dev = nullptr;  // {-1}: "aux shell list" of the overlap launches
+  int* no_aux_dev = nullptr;  // {-1, -2, -3, -4}: "aux shell" codes of the overlap and the three dipole launches
   // shell pairs (x, y) with l_x >= l_y, every unordered pair once, grouped by (l_x, l_y); their primitive-pair
   // records (p, P, c_a c_b, E coefficients) in one pool.  Pairs without a surviving primitive pair are absent.
   struct PairClass {
@@ -143,7 +143,7 @@ void build_basis(gwbse_basis& b, int device) {
   b.view.herm1 = b.keep(upload(h.herm1));
   for (int s = 0; s < h.nshell; ++s) b.by_l[h.l[s]].push_back(s);
   for (int l = 0; l <= ao::LMAX_SHELL; ++l) b.by_l_dev[l] = b.keep(upload(b.by_l[l]));
-  b.no_aux_dev = b.keep(upload(std::vector<int>{-1}));
+  b.no_aux_dev = b.keep(upload(std::vector<int>{-1, -2, -3, -4}));
   auto classify = [&](const ao::PairLists& pl, std::vector<gwbse_basis::PairClass>& classes) {
     const double* pool = b.keep(upload(pl.pool));
     std::map<std::pair<int, int>, std::vector<ao::PairEntry>> groups;
@@ -304,6 +304,28 @@ int gwbse_ao_overlap(gwbse_ctx* ctx, const gwbse_basis* basis, double* S, int ld
   GW_CUDA(copy2d_async(S, sizeof(double) * ld, d, sizeof(double) * n, sizeof(double) * n, n, cudaMemcpyDeviceToHost,
                        ctx->stream));
   GW_CUDA(cudaStreamSynchronize(ctx->stream));
+  GW_API_END(ctx)
+}
+
+int gwbse_ao_dipole(gwbse_ctx* ctx, const gwbse_basis* basis, double* D, int ld) {
+  GW_API_BEGIN(ctx)
+  GW_PROF(ctx, "ao_dipole");
+  GW_REQUIRE(basis && D, "null argument");
+  GW_REQUIRE(basis->device == ctx->device, "basis belongs to another device");
+  const int n = basis->host.nfunc;
+  GW_REQUIRE(ld >= n, "leading dimension too small");
+  double* d = ctx->buf("ao2c_out", (size_t)n * n);
+  const int smem_limit = shared_memory_limit(ctx);
+  for (int k = 0; k < 3; ++k) {
+    if (basis->pairs_kept < basis->pairs_total)
+      GW_CUDA(cudaMemsetAsync(d, 0, sizeof(double) * (size_t)n * n, ctx->stream));
+    ao::OutSpec out{d, 0, 1, (long long)n, 0, 1, 1};
+    for (const auto& pc : basis->pair_classes)
+      launch_class(ctx, *basis, pc, *basis, basis->no_aux_dev + 1 + k, 1, 0, out, smem_limit);
+    GW_CUDA(copy2d_async(D + (size_t)k * ld * n, sizeof(double) * ld, d, sizeof(double) * n, sizeof(double) * n, n,
+                         cudaMemcpyDeviceToHost, ctx->stream));
+    GW_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
   GW_API_END(ctx)
 }
 

@@ -46,6 +46,15 @@ class DeviceAOBasis {
   DeviceAOBasis(const DeviceAOBasis&) = delete;
   DeviceAOBasis& operator=(const DeviceAOBasis&) = delete;
   const gwbse_basis* handle() const { return h_; }
+  // AODipole::Fill: <mu | r_k | nu> about the origin, k = x, y, z
+  std::vector<MatrixXd> Dipoles() const {
+    const Index n = AOBasisSize();
+    std::vector<double> buf(static_cast<size_t>(3 * n * n));
+    dev_.check(gwbse_ao_dipole(dev_.ctx(), h_, buf.data(), (int)n));
+    std::vector<MatrixXd> out;
+    for (int k = 0; k < 3; ++k) out.emplace_back(buf.data() + static_cast<size_t>(k) * n * n, n, n, n);
+    return out;
+  }
   Index AOBasisSize() const { return gwbse_basis_size(h_); }
 
  private:

@@ -247,7 +247,11 @@ int gwbse_job_run(gwbse_job* job) {
     if (job->ints.naux != job->ints.S->rows()) throw std::runtime_error("aux matrices do not match ao3c");
     in.integrals = &job->ints;
   }
-  std::vector<MatrixXd> dip;
+  std::vector<MatrixXd> dip, ao_dip;
+  if (dft_basis && !job->in.count("dipole_x")) {  // AO dipoles from the device, interlevel dipoles formed by GWBSE
+    ao_dip = dft_basis->Dipoles();
+    in.ao_dipoles = &ao_dip;
+  }
   if (job->in.count("dipole_x") && job->in.count("dipole_y") && job->in.count("dipole_z")) {
     dip = {job->in["dipole_x"], job->in["dipole_y"], job->in["dipole_z"]};
     in.interlevel_dipoles = &dip;

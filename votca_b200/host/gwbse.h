@@ -129,6 +129,9 @@ class GWBSE {
     double ScaHFX = 0.0;                   // Orbitals::getScaHFX()
     const AOIntegralSource* integrals = nullptr;
     const std::vector<MatrixXd>* interlevel_dipoles = nullptr;  // optional: CalcFreeTransition_Dipoles
+    // optional alternative: AO dipole matrices <mu|r_k|nu> (AODipole::Fill, e.g. DeviceAOBasis::Dipoles()); the
+    // interlevel dipoles are then formed here as Orbitals::CalcFreeTransition_Dipoles does (orbitals.cc:742-760)
+    const std::vector<MatrixXd>* ao_dipoles = nullptr;
     // BSE-only runs (do_gw == false): orbitals_.QPdiag / RPAInputEnergies from a previous run
     const MatrixXd* Hqp = nullptr;
     const VectorXd* rpa_input_energies = nullptr;
@@ -363,8 +366,14 @@ class GWBSE {
       if (do_bse_singlets_) {
         res.BSE_singlet = bse.Solve_singlets();
         res.singlet_davidson_iterations = bse.last_davidson_iterations();
-        if (in_.interlevel_dipoles) {
-          res.transition_dipoles = bse.CalcCoupledTransition_Dipoles(res.BSE_singlet, *in_.interlevel_dipoles);
+        std::vector<MatrixXd> free_dipoles;
+        const std::vector<MatrixXd>* interlevel = in_.interlevel_dipoles;
+        if (!interlevel && in_.ao_dipoles) {
+          free_dipoles = CalcFreeTransition_Dipoles(*in_.ao_dipoles);
+          interlevel = &free_dipoles;
+        }
+        if (interlevel) {
+          res.transition_dipoles = bse.CalcCoupledTransition_Dipoles(res.BSE_singlet, *interlevel);
           res.oscillator_strengths = BSE::Oscillatorstrengths(res.transition_dipoles, res.BSE_singlet.eigenvalues);
         }
         res.singlet_analysis = bse.Analyze_eh_interaction(true, res.BSE_singlet);
@@ -380,6 +389,25 @@ class GWBSE {
     }
     log_(" GWBSE calculation finished ");
     return res;
+  }
+
+  // Orbitals::CalcFreeTransition_Dipoles (orbitals.cc:742-760): interlevel[k] = empty^T * D_k * occ with
+  // empty = MOs(:, bse_cmin..bse_cmax), occ = MOs(:, bse_vmin..homo); two small GEMMs per direction on the device
+  std::vector<MatrixXd> CalcFreeTransition_Dipoles(const std::vector<MatrixXd>& ao_dipoles) const {
+    const MatrixXd& C = *in_.mos;
+    const Index N = C.rows(), vt = bseopt_.homo - bseopt_.vmin + 1, ct = bseopt_.cmax - bseopt_.homo;
+    if (ao_dipoles.size() != 3) throw std::runtime_error("three AO dipole matrices expected");
+    Device::Buffer Cd = dev_.upload(C), T = dev_.alloc(static_cast<size_t>(N * vt)),
+                   I = dev_.alloc(static_cast<size_t>(std::max<Index>(ct * vt, 1)));
+    std::vector<MatrixXd> out;
+    for (const MatrixXd& D : ao_dipoles) {
+      if (D.rows() != N || D.cols() != N) throw std::runtime_error("AO dipole matrix does not match the basis size");
+      Device::Buffer Dd = dev_.upload(D);
+      dev_.gemm('N', 'N', N, vt, N, 1.0, Dd.get(), N, Cd.get() + bseopt_.vmin * N, N, 0.0, T.get(), N);
+      dev_.gemm('T', 'N', ct, vt, N, 1.0, Cd.get() + (bseopt_.homo + 1) * N, N, T.get(), N, 0.0, I.get(), ct);
+      out.push_back(dev_.download(I.get(), ct, vt));
+    }
+    return out;
   }
 
   // The GW-BSE part of Orbitals::WriteToCpt (orbitals.cc:990-1063): same group (/QMdata), names and HDF5 types
