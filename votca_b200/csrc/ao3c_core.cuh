@@ -249,7 +249,14 @@ AO_HD void triple_block(const BasisView& dft, const BasisView& aux, const TableV
           for (int t = 0; t <= ax + bx; ++t)
             for (int u = 0; u <= ay + by; ++u) {
               const double exy = Ex[t] * Ey[u];
-              for (int v = 0; v <= az + bz; ++v) s += exy * Ez[v] * G[hidx(t, u, v) * ncc + c];
+              // hidx(t, u, v + 1) - hidx(t, u, v) = (N+1)(N+2)/2 + (u+v) + 2 with N = t+u+v: walk it, no division
+              int N = t + u, w = u, h = hidx(t, u, 0);
+              for (int v = 0; v <= az + bz; ++v) {
+                s += exy * Ez[v] * G[h * ncc + c];
+                h += (N + 1) * (N + 2) / 2 + w + 2;
+                ++N;
+                ++w;
+              }
             }
           acc[it] += s;
           c += step_r;
