@@ -6,6 +6,7 @@
 #include "../../votca_b200/host/anderson_mixing.h"
 #include "../../votca_b200/host/qp_rootsearch.h"
 #include "../../votca_b200/host/quadrature.h"
+#include "../../votca_b200/host/vc2index.h"
 
 using namespace votca;
 using namespace votca::xtp;
@@ -155,4 +156,9 @@ int quadrature_points(const char* scheme, long order, double* pts, double* wts) 
   }
 }
 
+// vc2index: what = 0 -> I(a, b), 1 -> v(a), 2 -> c(a)
+long vc2index_eval(long vmin, long cmin, long ctotal, int what, long a, long b) {
+  votca::xtp::vc2index vc(vmin, cmin, ctotal);
+  return what == 0 ? vc.I(a, b) : what == 1 ? vc.v(a) : vc.c(a);
+}
 }  // extern "C"

@@ -32,6 +32,8 @@ def harness():
     lib.anderson_run.argtypes = [l, d, l, l, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     lib.newton_sqrt.argtypes = [d, d, l, d, ctypes.c_void_p]
     lib.quadrature_points.argtypes = [ctypes.c_char_p, l, ctypes.c_void_p, ctypes.c_void_p]
+    lib.vc2index_eval.argtypes = [l, l, l, i, l, l]
+    lib.vc2index_eval.restype = l
     return lib
 
 
@@ -255,3 +257,15 @@ def test_cda_quadratures_reference_integrals(harness, scheme):
     assert _approx(np.array(got_cpp), ref, 1e-10)
     assert _approx(np.array(got_py), ref, 1e-10)
     assert harness.quadrature_points(b"laguerre", 8, None, None) == -1  # not available in this build: loud error
+
+
+def test_vc2index_known_answers(harness):
+    """test_vc2index.cc:33-68: I(3, 12) = 32 for vmin 0, cmin 10, ctotal 10; v(I), c(I) invert it over all pairs."""
+    vmin, cmin, ctotal, vtotal = 0, 10, 10, 9
+    ev = lambda what, a, b=0: harness.vc2index_eval(vmin, cmin, ctotal, what, a, b)  # noqa: E731
+    assert ev(0, 3, 12) == 32 and ev(2, 32) == 12 and ev(1, 32) == 3
+    j = 0
+    for v2 in range(vtotal):
+        for c2 in range(ctotal):
+            assert ev(1, j) == vmin + v2 and ev(2, j) == cmin + c2 and ev(0, vmin + v2, cmin + c2) == j
+            j += 1
