@@ -10,7 +10,9 @@ import pytest
 
 from tests.helpers import rel_frob
 
-pytestmark = pytest.mark.gpu
+from tests.conftest import FIRST_DEVICE_RUN_PENDING
+
+pytestmark = [pytest.mark.gpu, FIRST_DEVICE_RUN_PENDING]
 TOL = 1e-9
 
 

@@ -6,7 +6,9 @@ import pytest
 
 from oracle.orbfile import OrbFile
 
-pytestmark = pytest.mark.gpu
+from tests.conftest import FIRST_DEVICE_RUN_PENDING
+
+pytestmark = [pytest.mark.gpu, FIRST_DEVICE_RUN_PENDING]
 
 
 def test_job_writes_orb_checkpoint(tmp_path):

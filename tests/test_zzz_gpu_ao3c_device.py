@@ -13,15 +13,10 @@ import pytest
 
 from oracle import threecenter
 from tests import helpers
+from tests.conftest import FIRST_DEVICE_RUN_PENDING
 from tests.test_ao3c_core_cpu import _golden_basis, pack, relmax
 
-pytestmark = [
-    pytest.mark.gpu,
-    # non-strict: reports XPASS once the launch path has run clean on a device, xfail (not a red suite) if the first
-    # device run turns up a launch-side defect the CPU harness cannot see
-    pytest.mark.xfail(strict=False, reason="device launch path not yet run on a GPU (round-1 GPU budget was spent); "
-                                           "the arithmetic is verified on the CPU by tests/test_ao3c_core_cpu.py"),
-]
+pytestmark = [pytest.mark.gpu, FIRST_DEVICE_RUN_PENDING]
 
 
 @pytest.fixture(scope="module")
