@@ -29,6 +29,8 @@ def lib():
     lib.opt_load_xml.argtypes = [p, s]
     lib.opt_set.argtypes = [p, s, s]
     lib.opt_get.argtypes = [p, s, ctypes.c_char_p, ctypes.c_int]
+    L = ctypes.c_long
+    lib.rpa_update_energies.argtypes = [L, L, L, p, L, p, L, L, p]
     return lib
 
 
@@ -96,3 +98,16 @@ def test_dotted_keys_with_reference_prefixes(lib):
         lib.opt_set(o, b"gw.mode", b"evGW")
     assert lib.opt_load_xml(o, b"/nonexistent/options.xml") == 1
     lib.opt_free(o)
+
+
+def test_rpa_update_input_energies_known_answer(lib):
+    """test_rpa.cc:41-67 on the C++ host class (RPA::UpdateRPAInputEnergies, rpa.cc:32-70): GW energies replace the
+    window, levels outside it are shifted by the largest correction at the respective edge."""
+    import numpy as np
+    dft = np.array([-0.5, -0.4, -0.3, -0.2, -0.2, -0.1, 0, 0.1, 0.2, 0.3])
+    gw = np.array([-0.15, -0.05, 0.05, 0.15, 0.45, 0.55, 0.65])
+    out = np.zeros(10)
+    n = lib.rpa_update_energies(4, 0, 9, dft.ctypes.data, 10, gw.ctypes.data, 7, 1, out.ctypes.data)
+    assert n == 10
+    ref = np.array([-0.85, -0.15, -0.05, 0.05, 0.15, 0.45, 0.55, 0.65, 0.75, 0.85])
+    assert np.linalg.norm(out - ref) < 1e-4 * np.linalg.norm(ref)
