@@ -27,6 +27,47 @@ int rpa_update_energies(long homo, long rpamin, long rpamax, const double* dft, 
   }
 }
 
+// BuildFullBSEXRankedInitialGuess (bse_initialization.h:47-93): out is 2n x nguess column-major; returns nguess
+long bse_ranked_guess(const double* adiag, const double* bdiag, long n, long nroots, double* out, long cap) {
+  try {
+    const MatrixXd g = BuildFullBSEXRankedInitialGuess(VectorXd(adiag, n), VectorXd(bdiag, n), nroots);
+    if (g.rows() * g.cols() > cap) return -2;
+    for (long j = 0; j < g.cols(); ++j)
+      for (long i = 0; i < g.rows(); ++i) out[j * g.rows() + i] = g(i, j);
+    return g.cols();
+  } catch (...) {
+    return -1;
+  }
+}
+
+// GWBSE::Initialize (gwbse.cc:60-233): level ranges and derived sizes from the options; ranges[6] = rpamin, rpamax,
+// qpmin, qpmax, bse_vmin, bse_cmax; returns 0, or 1 with the exception text in err
+int gwbse_initialize_ranges(void* options, long homo, long nlevels, long* ranges, long* bse_nmax, char* err, int cap) {
+  try {
+    alignas(Device) static unsigned char no_device[sizeof(Device)];
+    const Device& dev = *reinterpret_cast<const Device*>(no_device);
+    Logger log;
+    GWBSE g(dev, log);
+    MatrixXd mos(nlevels, nlevels);
+    VectorXd e(nlevels);
+    GWBSE::Inputs in;
+    in.homo = homo;
+    in.mos = &mos;
+    in.mo_energies = &e;
+    g.Initialize(*static_cast<Options*>(options), in);
+    const GW::options& gw = g.gw_options();
+    const BSE::options& bse = g.bse_options();
+    const long r[6] = {gw.rpamin, gw.rpamax, gw.qpmin, gw.qpmax, bse.vmin, bse.cmax};
+    for (int i = 0; i < 6; ++i) ranges[i] = r[i];
+    *bse_nmax = bse.nmax;
+    return 0;
+  } catch (const std::exception& e) {
+    std::strncpy(err, e.what(), cap - 1);
+    err[cap - 1] = 0;
+    return 1;
+  }
+}
+
 void* opt_new() { return new Options(); }
 void opt_free(void* o) { delete static_cast<Options*>(o); }
 int opt_load_xml(void* o, const char* path) {

@@ -31,6 +31,9 @@ def lib():
     lib.opt_get.argtypes = [p, s, ctypes.c_char_p, ctypes.c_int]
     L = ctypes.c_long
     lib.rpa_update_energies.argtypes = [L, L, L, p, L, p, L, L, p]
+    lib.bse_ranked_guess.argtypes = [p, p, L, L, p, L]
+    lib.bse_ranked_guess.restype = L
+    lib.gwbse_initialize_ranges.argtypes = [p, L, L, p, p, ctypes.c_char_p, ctypes.c_int]
     return lib
 
 
@@ -111,3 +114,50 @@ def test_rpa_update_input_energies_known_answer(lib):
     assert n == 10
     ref = np.array([-0.85, -0.15, -0.05, 0.05, 0.15, 0.45, 0.55, 0.65, 0.75, 0.85])
     assert np.linalg.norm(out - ref) < 1e-4 * np.linalg.norm(ref)
+
+
+def _ranges(lib, homo, nlevels, **opts):
+    import numpy as np
+    o = lib.opt_new()
+    for k, v in opts.items():
+        lib.opt_set(o, k.replace("__", ".").encode(), str(v).encode())
+    r = np.zeros(6, dtype=np.int64)
+    nmax = ctypes.c_long()
+    err = ctypes.create_string_buffer(256)
+    rc = lib.gwbse_initialize_ranges(o, homo, nlevels, r.ctypes.data, ctypes.byref(nmax), err, 256)
+    lib.opt_free(o)
+    return (tuple(int(x) for x in r), nmax.value) if rc == 0 else err.value.decode()
+
+
+def test_level_ranges_as_gwbse_initialize(lib):
+    """GWBSE::Initialize (gwbse.cc:60-233) on the C++ host: the four `ranges` modes, clamping, exctotal against the BSE
+    size, and the reference's error texts.  Water of the reference's integration tests (13 levels, homo 4, default
+    ranges) must give the ranges stored in its checkpoint: rpa 0..12, qp 0..12, bse 0..12."""
+    assert _ranges(lib, 4, 13) == ((0, 12, 0, 12, 0, 12), 10)
+    # default: qpmax = bse_cmax = 3 homo + 1 (SURVEY.md section 8 sizes: DCV5T homo 143 -> 431 levels in the window)
+    assert _ranges(lib, 143, 1249)[0] == (0, 1248, 0, 430, 0, 430)
+    assert _ranges(lib, 4, 17, ranges="full") == ((0, 16, 0, 16, 0, 16), 10)
+    assert _ranges(lib, 4, 17, ranges="explicit", rpamax=14, qpmin=1, qpmax=9, bsemin=2, bsemax=40)[0] == (0, 14, 1, 9, 2, 16)
+    assert _ranges(lib, 9, 40, ranges="factor", rpamax=0.5, qpmin=0.5, qpmax=0.5, bsemin=0.2, bsemax=1.0)[0] == \
+        (0, 19, 4, 14, 7, 19)
+    assert _ranges(lib, 4, 17, bse__exctotal=1000)[1] == 5 * 9  # capped at the number of transitions
+    assert "unknown ranges" in _ranges(lib, 4, 17, ranges="nonsense")
+    assert "Invalid GW level range" in _ranges(lib, 4, 17, ranges="explicit", rpamax=16, qpmin=9, qpmax=3, bsemin=0, bsemax=8)
+    assert "must be given together" in _ranges(lib, 4, 17, gw__qp_grid_steps=201)
+    assert "unknown gw.mode" in _ranges(lib, 4, 17, gw__mode="scGW")
+
+
+def test_full_bse_ranked_initial_guess_equals_oracle(lib):
+    """BuildFullBSEXRankedInitialGuess (bse_initialization.h:47-93): max(4 nroots, 8) unit vectors on the X block,
+    ranked by sqrt(a^2 - b^2) with ties broken by a."""
+    import numpy as np
+    from oracle.bse import build_full_bse_x_ranked_initial_guess
+    rng = np.random.default_rng(4)
+    for n, nroots in ((45, 3), (12, 5), (6, 1), (30, 10)):
+        a = np.round(rng.uniform(0.2, 1.5, n), 2)  # rounding makes ties
+        b = rng.uniform(-0.2, 0.2, n)
+        ref = build_full_bse_x_ranked_initial_guess(a, b, nroots)
+        out = np.zeros(ref.size)
+        k = lib.bse_ranked_guess(a.ctypes.data, b.ctypes.data, n, nroots, out.ctypes.data, out.size)
+        assert k == ref.shape[1]
+        assert np.array_equal(out.reshape(ref.shape[1], ref.shape[0]).T, ref)
