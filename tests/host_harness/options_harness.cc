@@ -68,6 +68,42 @@ int gwbse_initialize_ranges(void* options, long homo, long nlevels, long* ranges
   }
 }
 
+// GWBSE::WriteToCpt on made-up results of the given sizes (values i + 0.5): checks names / types / shapes of the file
+int gwbse_write_results(const char* path, long nlevels, long homo, long q, long bse_size, long nstates, int tda) {
+  try {
+    alignas(Device) static unsigned char no_device[sizeof(Device)];
+    const Device& dev = *reinterpret_cast<const Device*>(no_device);
+    Logger log;
+    GWBSE g(dev, log);
+    MatrixXd mos(nlevels, nlevels, 0.25);
+    VectorXd e(nlevels, -0.5);
+    GWBSE::Inputs in;
+    in.homo = homo;
+    in.mos = &mos;
+    in.mo_energies = &e;
+    in.ScaHFX = 0.25;
+    Options opt;
+    opt.set("bse.useTDA", tda ? "true" : "false");
+    g.Initialize(opt, in);
+    GWBSE::Results r;
+    r.rpamin = 0, r.rpamax = nlevels - 1, r.qpmin = 0, r.qpmax = q - 1, r.bse_vmin = 0, r.bse_cmax = q - 1;
+    r.RPA_inputenergies = VectorXd(nlevels, 1.5);
+    r.QPpert_energies = VectorXd(q, 2.5);
+    r.QPdiag_eigenvalues = VectorXd(q, 3.5);
+    r.QPdiag_eigenvectors = MatrixXd(q, q, 4.5);
+    r.BSE_singlet.eigenvalues = VectorXd(nstates, 5.5);
+    r.BSE_singlet.eigenvectors = MatrixXd(bse_size, nstates, 6.5);
+    if (!tda) r.BSE_singlet.eigenvectors2 = MatrixXd(bse_size, nstates, 7.5);
+    r.BSE_singlet.success = true;
+    for (long s2 = 0; s2 < nstates; ++s2) r.transition_dipoles.emplace_back(3, 8.5 + (double)s2);
+    r.BSE_singlet_dynamic = VectorXd(nstates, 9.5);
+    g.WriteToCpt(r, path);
+    return 0;
+  } catch (...) {
+    return 1;
+  }
+}
+
 void* opt_new() { return new Options(); }
 void opt_free(void* o) { delete static_cast<Options*>(o); }
 int opt_load_xml(void* o, const char* path) {

@@ -33,6 +33,7 @@ def lib():
     lib.rpa_update_energies.argtypes = [L, L, L, p, L, p, L, L, p]
     lib.bse_ranked_guess.argtypes = [p, p, L, L, p, L]
     lib.bse_ranked_guess.restype = L
+    lib.gwbse_write_results.argtypes = [s, L, L, L, L, L, ctypes.c_int]
     lib.gwbse_initialize_ranges.argtypes = [p, L, L, p, p, ctypes.c_char_p, ctypes.c_int]
     return lib
 
@@ -161,3 +162,48 @@ def test_full_bse_ranked_initial_guess_equals_oracle(lib):
         k = lib.bse_ranked_guess(a.ctypes.data, b.ctypes.data, n, nroots, out.ctypes.data, out.size)
         assert k == ref.shape[1]
         assert np.array_equal(out.reshape(ref.shape[1], ref.shape[0]).T, ref)
+
+
+def test_results_checkpoint_uses_the_names_and_types_of_the_reference(lib, tmp_path):
+    """GWBSE::WriteToCpt (the GW-BSE part of Orbitals::WriteToCpt, orbitals.cc:990-1063): every attribute and dataset
+    it writes exists under the same path, with the same HDF5 type and rank, in the .orb files the reference's own
+    dftgwbse run produced (names / types recorded from molecule_neutral.orb and molecule_neutral_tda.orb)."""
+    import numpy as np
+    from oracle.orbfile import OrbFile
+    path = tmp_path / "res.orb"
+    assert lib.gwbse_write_results(str(path).encode(), 13, 4, 13, 40, 5, 0) == 0
+    f = OrbFile(str(path))
+    f.verify_checksums()
+    # (name, numpy kind + size) of the scalar attributes of /QMdata in the reference's files
+    ref_attrs = {"XTPVersion": "str", "version": "i4", "occupied_levels": "i8", "number_alpha_electrons": "i8",
+                 "number_beta_electrons": "i8", "rpamin": "i8", "rpamax": "i8", "qpmin": "i8", "qpmax": "i8",
+                 "bse_vmin": "i8", "bse_cmax": "i8", "ScaHFX": "f8", "useTDA": "i8", "use_Hqp_offdiag": "u1"}
+    at = f.attrs("/QMdata")
+    for name, val in at.items():
+        if name == "is_qsgw":  # orbitals_version 9 (orbitals.h:842-844); the checked-in files are version 8
+            assert np.asarray(val).dtype == np.uint8
+            continue
+        kind = ref_attrs[name]
+        assert (isinstance(val, str) and kind == "str") or np.asarray(val).dtype == np.dtype(kind), name
+    assert set(ref_attrs) <= set(at)
+    ref_sets = {"RPA_inputenergies": (13, 1), "QPpert_energies": (13, 1), "BSE_singlet_dynamic": (5, 1),
+                "BSE_triplet_dynamic": (0, 1), "mos/eigenvalues": (13, 1), "mos/eigenvectors": (13, 13),
+                "mos/eigenvectors2": (0, 1), "QPdiag/eigenvalues": (13, 1), "QPdiag/eigenvectors": (13, 13),
+                "QPdiag/eigenvectors2": (0, 1), "BSE_singlet/eigenvalues": (5, 1), "BSE_singlet/eigenvectors": (40, 5),
+                "BSE_singlet/eigenvectors2": (40, 5), "BSE_triplet/eigenvalues": (0, 1),
+                "BSE_triplet/eigenvectors": (0, 1), "BSE_triplet/eigenvectors2": (0, 1)}
+    ref_sets.update({f"transition_dipoles/ind{i}": (3, 1) for i in range(5)})
+    got = {p[len("/QMdata/"):]: f.read(p).shape for p in f.walk("/QMdata")}
+    assert got == ref_sets
+    for grp in ("mos", "QPdiag", "BSE_singlet", "BSE_triplet"):
+        assert f.attrs("/QMdata/" + grp)["info"].dtype == np.int64
+    assert f.read("/QMdata/BSE_singlet/eigenvectors2")[0, 0] == 7.5 and at["useTDA"] == 0 and at["occupied_levels"] == 5
+    IT = "/root/reference/xtp/src/tests/DataFiles/xtp_tools_integration_tests/molecule_neutral.orb"
+    if os.path.exists(IT):  # the expectations above are the reference file's own
+        r = OrbFile(IT)
+        rat = r.attrs("/QMdata")
+        for name, kind in ref_attrs.items():
+            assert (isinstance(rat[name], str) and kind == "str") or np.asarray(rat[name]).dtype == np.dtype(kind), name
+        rsets = {p[len("/QMdata/"):] for p in r.walk("/QMdata")}
+        assert {k for k in ref_sets if not k.startswith("transition_dipoles/")} <= rsets
+        assert r.read("/QMdata/BSE_singlet/eigenvectors").shape[0] == r.read("/QMdata/BSE_singlet/eigenvectors2").shape[0]
