@@ -5,8 +5,8 @@
 // the oracle.  Nothing under votca_b200/ builds, links or loads it; tests/test_host_layer_on_mock_cpu.py builds it
 // into tests/host_harness/build/mock/ together with a copy of the host library linked against it and runs both in a
 // separate process.  Arithmetic follows the same reference formulas the oracle cites (rpa.cc, sigma_base.cc,
-// sigma_ppm.cc, bse_operator.cc, davidsonsolver.cc, threecenter.cc, aomatrix.cc).  Not covered (return an error):
-// exact Sigma, multi-GPU.  The small general eigenproblem of the full-BSE Davidson is delegated to the test
+// sigma_ppm.cc, sigma_exact.cc, bse_operator.cc, davidsonsolver.cc, threecenter.cc, aomatrix.cc).  Not covered:
+// multi-GPU.  The small general eigenproblem of the full-BSE Davidson is delegated to the test
 // process's LAPACK through mock_set_gen_eig.
 #include <algorithm>
 #include <cmath>
@@ -35,6 +35,11 @@ struct gwbse_ctx {
   std::vector<double> fac, pole, energies;
   int lumo = 0, qpoff = 0, q = 0;
   double eta = 0.0;
+  // exact Sigma: residues R[level][n][s], poles
+  bool exact_ready = false;
+  std::vector<double> residues, rpa_omegas, energies_exact;
+  int ex_S = 0, ex_q = 0, ex_nocc = 0;
+  double ex_eta = 0.0;
   // BSE
   bool bse_ready = false;
   int homo = 0, vt = 0, ct = 0, voff = 0, coff = 0;
@@ -202,6 +207,24 @@ void ppm_eval(gwbse_ctx* ctx, int level, double w, double* sigma, double* dsigma
       ds += 0.5 * ctx->fac[chi] * Mv * Mv * (eta2 - t * t) / (den * den);
     }
   }
+  *sigma = s;
+  if (dsigma) *dsigma = ds;
+}
+
+// Sigma_Exact::CalcCorrelationDiagElement / ...Derivative, sigma_exact.cc:40-83
+void exact_eval(gwbse_ctx* ctx, int level, double w, double* sigma, double* dsigma) {
+  REQUIRE(ctx->exact_ready, "sigma evaluator not prepared");
+  REQUIRE(level >= 0 && level < ctx->ex_q, "gw_level out of range");
+  const double eta2 = ctx->ex_eta * ctx->ex_eta;
+  const int S = ctx->ex_S, ntot = ctx->ntotal;
+  double s = 0.0, ds = 0.0;
+  for (int n = 0; n < ntot; ++n)
+    for (int p = 0; p < S; ++p) {
+      const double t = w - ctx->energies_exact[n] + (n < ctx->ex_nocc ? ctx->rpa_omegas[p] : -ctx->rpa_omegas[p]);
+      const double r = ctx->residues[((size_t)level * ntot + n) * S + p], den = t * t + eta2;
+      s += 2.0 * r * r * t / den;
+      ds += 2.0 * r * r * (eta2 - t * t) / (den * den);
+    }
   *sigma = s;
   if (dsigma) *dsigma = ds;
 }
@@ -404,7 +427,10 @@ int gwbse_host_free(void* p) {
 int gwbse_dgemm_dev(gwbse_ctx* ctx, char ta, char tb, int m, int n, int k, double alpha, const double* A, int lda,
                     const double* B, int ldb, double beta, double* C, int ldc) {
   MOCK_BEGIN(ctx)
-  REQUIRE(m >= 0 && n >= 0 && k >= 0 && ldc >= std::max(m, 1), "Shape mismatch in Cublas gemm");
+  const bool tA = ta == 'T' || ta == 't', tB = tb == 'T' || tb == 't';
+  REQUIRE(m >= 0 && n >= 0 && k >= 0 && ldc >= std::max(m, 1) && lda >= std::max(tA ? k : m, 1) &&
+              ldb >= std::max(tB ? n : k, 1),
+          "Shape mismatch in Cublas gemm");
   gemm(ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
   MOCK_END(ctx)
 }
@@ -634,12 +660,14 @@ int gwbse_rpa_epsilon(gwbse_ctx* ctx, int kind, double fre, double fim, double e
       }
     }
     for (int c2 = 0; c2 < naux; ++c2)
-      for (int c1 = 0; c1 < naux; ++c1) {
+      for (int c1 = c2; c1 < naux; ++c1) {  // lower triangle, mirrored below
         double s = 0.0;
         for (int c = 0; c < n_unocc; ++c) s += ctx->M(v, ntot - n_unocc + c, c1) * d[c] * ctx->M(v, ntot - n_unocc + c, c2);
         ctx->eps[c1 + (size_t)c2 * naux] += s;
       }
   }
+  for (int c2 = 0; c2 < naux; ++c2)
+    for (int c1 = c2 + 1; c1 < naux; ++c1) ctx->eps[c2 + (size_t)c1 * naux] = ctx->eps[c1 + (size_t)c2 * naux];
   for (int i = 0; i < naux; ++i) ctx->eps[i + (size_t)i * naux] += 1.0;
   if (eps_out) {
     REQUIRE(ld >= naux, "leading dimension too small");
@@ -648,9 +676,23 @@ int gwbse_rpa_epsilon(gwbse_ctx* ctx, int kind, double fre, double fim, double e
   MOCK_END(ctx)
 }
 double* gwbse_rpa_epsilon_ptr(gwbse_ctx* ctx) { return ctx ? ctx->eps.data() : nullptr; }
-int gwbse_rpa_h2p_apb(gwbse_ctx* ctx, const double*, int, int, int, double*, int) {
-  if (ctx) ctx->err = "exact Sigma (H2p) is not available in the test mock";
-  return 1;
+int gwbse_rpa_h2p_apb(gwbse_ctx* ctx, const double* e, int homo, int rpamin, int rpamax, double* apb, int ld) {
+  MOCK_BEGIN(ctx)
+  // RPA::Calculate_H2p_ApB, rpa.cc:281-326 (+ the A-B diagonal)
+  require_mmn(ctx);
+  const int n_occ = homo - rpamin + 1, n_unocc = rpamax - homo, S = n_occ * n_unocc;
+  REQUIRE(ld >= S, "leading dimension too small");
+  for (int v2 = 0; v2 < n_occ; ++v2)
+    for (int c2 = 0; c2 < n_unocc; ++c2)
+      for (int v1 = 0; v1 < n_occ; ++v1)
+        for (int c1 = 0; c1 < n_unocc; ++c1) {
+          double s = 0.0;
+          for (int chi = 0; chi < ctx->naux; ++chi) s += ctx->M(v1, n_occ + c1, chi) * ctx->M(v2, n_occ + c2, chi);
+          double h = 4.0 * s;
+          if (v1 == v2 && c1 == c2) h += e[n_occ + c1] - e[v1];
+          apb[(v1 * n_unocc + c1) + (size_t)(v2 * n_unocc + c2) * ld] = h;
+        }
+  MOCK_END(ctx)
 }
 
 // ---- Sigma -------------------------------------------------------------------------------------------------------------
@@ -685,8 +727,7 @@ int gwbse_sigma_ppm_set(gwbse_ctx* ctx, const double* w, const double* f, const 
 }
 int gwbse_sigma_update_energies(gwbse_ctx* ctx, int which, const double* e) {
   MOCK_BEGIN(ctx)
-  REQUIRE(which == 0, "exact Sigma is not available in the test mock");
-  ctx->energies.assign(e, e + ctx->ntotal);
+  (which == 0 ? ctx->energies : ctx->energies_exact).assign(e, e + ctx->ntotal);
   MOCK_END(ctx)
 }
 int gwbse_sigma_ppm_eval(gwbse_ctx* ctx, int nreq, const int* levels, const double* freqs, double* sigma, double* dsigma) {
@@ -697,15 +738,15 @@ int gwbse_sigma_ppm_eval(gwbse_ctx* ctx, int nreq, const int* levels, const doub
 int gwbse_sigma_eval_groups(gwbse_ctx* ctx, int which, int ngroups, const int* levels, const int* gptr, const double* freqs,
                             double* sigma, double* dsigma) {
   MOCK_BEGIN(ctx)
-  REQUIRE(which == 0, "exact Sigma is not available in the test mock");
   for (int g = 0; g < ngroups; ++g)
-    for (int i = gptr[g]; i < gptr[g + 1]; ++i) ppm_eval(ctx, levels[g], freqs[i], sigma + i, dsigma ? dsigma + i : nullptr);
+    for (int i = gptr[g]; i < gptr[g + 1]; ++i)
+      (which == 0 ? ppm_eval : exact_eval)(ctx, levels[g], freqs[i], sigma + i, dsigma ? dsigma + i : nullptr);
   MOCK_END(ctx)
 }
 int gwbse_sigma_ppm_offdiag(gwbse_ctx* ctx, int q, const double* freqs, double* out, int ld) {
   MOCK_BEGIN(ctx)
   REQUIRE(ctx->ppm_ready, "sigma evaluator not prepared");
-  REQUIRE(q == ctx->q && ld >= q, "q does not match the prepared evaluator");
+  REQUIRE(q > 0 && ctx->qpoff + q <= ctx->mtotal && ld >= q, "q does not match the prepared evaluator");
   const double eta2 = ctx->eta * ctx->eta;
   for (int i = 0; i < q; ++i)
     for (int j = 0; j < q; ++j) {
@@ -724,18 +765,65 @@ int gwbse_sigma_ppm_offdiag(gwbse_ctx* ctx, int q, const double* freqs, double* 
     }
   MOCK_END(ctx)
 }
-int gwbse_sigma_exact_prepare(gwbse_ctx* ctx, const double*, const double*, int, const double*, int, int, int, int, int,
-                              double) {
-  if (ctx) ctx->err = "exact Sigma is not available in the test mock";
-  return 1;
+int gwbse_sigma_exact_prepare(gwbse_ctx* ctx, const double* omegas, const double* XpY, int ldxpy, const double* e,
+                              int homo, int rpamin, int rpamax, int qpmin, int qpmax, double eta) {
+  MOCK_BEGIN(ctx)
+  // Sigma_Exact::PrepareScreening / CalcResidues, sigma_exact.cc:29-38, 109-148
+  require_mmn(ctx);
+  REQUIRE(rpamin == ctx->mmin && rpamin == ctx->nmin && rpamax == ctx->nmax, "RPA range must match Mmn");
+  const int n_occ = homo + 1 - rpamin, n_unocc = rpamax - homo, S = n_occ * n_unocc;
+  const int q = qpmax - qpmin + 1, qpoff = qpmin - rpamin, ntot = ctx->ntotal;
+  REQUIRE(ldxpy >= S && q > 0 && qpoff >= 0 && qpoff + q <= ctx->mtotal, "invalid sizes");
+  ctx->residues.assign((size_t)q * ntot * S, 0.0);
+  std::vector<double> fc((size_t)S);
+  for (int i = 0; i < q; ++i)
+    for (int n = 0; n < ntot; ++n) {
+      for (int v = 0; v < n_occ; ++v)
+        for (int c = 0; c < n_unocc; ++c) {
+          double t = 0.0;
+          for (int chi = 0; chi < ctx->naux; ++chi) t += ctx->M(v, n_occ + c, chi) * ctx->M(qpoff + i, n, chi);
+          fc[(size_t)v * n_unocc + c] = t;
+        }
+      for (int s2 = 0; s2 < S; ++s2) {
+        double r = 0.0;
+        for (int vc = 0; vc < S; ++vc) r += fc[vc] * XpY[vc + (size_t)s2 * ldxpy];
+        ctx->residues[((size_t)i * ntot + n) * S + s2] = r;
+      }
+    }
+  ctx->rpa_omegas.assign(omegas, omegas + S);
+  ctx->energies_exact.assign(e, e + ntot);
+  ctx->ex_S = S;
+  ctx->ex_q = q;
+  ctx->ex_nocc = n_occ;
+  ctx->ex_eta = eta;
+  ctx->exact_ready = true;
+  MOCK_END(ctx)
 }
-int gwbse_sigma_exact_eval(gwbse_ctx* ctx, int, const int*, const double*, double*, double*) {
-  if (ctx) ctx->err = "exact Sigma is not available in the test mock";
-  return 1;
+int gwbse_sigma_exact_eval(gwbse_ctx* ctx, int nreq, const int* levels, const double* freqs, double* sigma, double* dsigma) {
+  MOCK_BEGIN(ctx)
+  for (int i = 0; i < nreq; ++i) exact_eval(ctx, levels[i], freqs[i], sigma + i, dsigma ? dsigma + i : nullptr);
+  MOCK_END(ctx)
 }
-int gwbse_sigma_exact_offdiag(gwbse_ctx* ctx, int, const double*, double*, int) {
-  if (ctx) ctx->err = "exact Sigma is not available in the test mock";
-  return 1;
+int gwbse_sigma_exact_offdiag(gwbse_ctx* ctx, int q, const double* freqs, double* out, int ld) {
+  MOCK_BEGIN(ctx)
+  REQUIRE(ctx->exact_ready, "sigma evaluator not prepared");
+  REQUIRE(q == ctx->ex_q && ld >= q, "q does not match the prepared evaluator");
+  const double eta2 = ctx->ex_eta * ctx->ex_eta;
+  const int S = ctx->ex_S, ntot = ctx->ntotal;
+  for (int i = 0; i < q; ++i)
+    for (int j = 0; j < q; ++j) {
+      double s = 0.0;
+      if (i != j)
+        for (int n = 0; n < ntot; ++n)
+          for (int p = 0; p < S; ++p) {
+            const double sh = n < ctx->ex_nocc ? ctx->rpa_omegas[p] : -ctx->rpa_omegas[p];
+            const double t1 = freqs[i] - ctx->energies_exact[n] + sh, t2 = freqs[j] - ctx->energies_exact[n] + sh;
+            s += ctx->residues[((size_t)i * ntot + n) * S + p] * ctx->residues[((size_t)j * ntot + n) * S + p] *
+                 (t1 / (t1 * t1 + eta2) + t2 / (t2 * t2 + eta2));
+          }
+      out[i + (size_t)j * ld] = s;
+    }
+  MOCK_END(ctx)
 }
 
 // ---- BSE ---------------------------------------------------------------------------------------------------------------

@@ -3,7 +3,8 @@ basis-set path) on the CPU: the GPU tests of that layer are re-run, unchanged, i
 kernel library is replaced by tests/host_harness/mock_b200_for_tests.cc - a naive single-rank CPU restatement of
 the C ABI that exists for this purpose only (the product has no CPU fallback and nothing
 under votca_b200/ references the mock).  This checks the host logic every round without a GPU; the kernels
-themselves are only ever checked on the device."""
+themselves are only ever checked on the device.  The mock's own fidelity is checked by running the kernel tests
+against it as well."""
 import os
 import re
 import subprocess
@@ -36,13 +37,23 @@ def run_gpu_tests_on_mock(mock_dir, args):
     return r.returncode, int(m.group(1)) if m else 0, tail
 
 
+def test_mock_is_faithful_on_the_kernel_tests(mock_dir):
+    """The stand-in passes the tests the CUDA kernels are checked with (tests/test_gpu_kernels.py: every C ABI entry
+    point against the oracle and the reference's golden matrices; only the two large property tests are left out for
+    time) - so what the host layer sees from it is what it sees from the device."""
+    rc, passed, tail = run_gpu_tests_on_mock(mock_dir, ["tests/test_gpu_kernels.py", "-k",
+                                                        "not medium_size and not full_size"])
+    assert rc == 0 and passed >= 40, tail
+
+
 def test_gw_and_bse_host_tests_pass_on_the_mock(mock_dir):
-    """tests/test_gpu_host.py: golden G0W0 (test_gw.cc), canonical / Brent root search, evGW(ppm) against the oracle,
-    BSE TDA singlets / triplets with dynamical screening (test_bse.cc), oscillator strengths, options XML, error
-    convention, full BSE (small general eigenproblem through the test process's LAPACK).  Deselected: what the mock
-    does not restate (exact / CDA Sigma) and the treecode switch, which is a kernel-side option."""
-    rc, passed, tail = run_gpu_tests_on_mock(mock_dir, ["tests/test_gpu_host.py", "-k", "not exact and not cda"])
-    assert rc == 0 and passed >= 10, tail
+    """tests/test_gpu_host.py, all of it: golden G0W0 (test_gw.cc), canonical / Brent root search, evGW with the ppm,
+    exact and cda integrators against the oracle, BSE TDA / full / triplets with dynamical screening (test_bse.cc),
+    oscillator strengths, options XML, error convention; and tests/test_gpu_zz_reference_checkpoint.py: BSE on the
+    reference's own dftgwbse checkpoints (water, d/f aux shells), the PPM known answer, the tier-R methane case."""
+    rc, passed, tail = run_gpu_tests_on_mock(mock_dir, ["tests/test_gpu_host.py",
+                                                        "tests/test_gpu_zz_reference_checkpoint.py"])
+    assert rc == 0 and passed >= 17, tail
 
 
 def test_basis_set_job_and_checkpoint_pass_on_the_mock(mock_dir):
