@@ -73,3 +73,18 @@ def test_late_gpu_test_files_are_sound_on_the_mock(mock_dir):
     rc, passed, tail = run_gpu_tests_on_mock(mock_dir, [
         "tests/test_zz_gpu_cudapipeline_cases.py", "tests/test_zz_gpu_benchmark_tool.py", "--runxfail"])
     assert rc == 0 and passed >= 5, tail
+
+
+def test_smoke_entry_point_logic_on_the_mock(mock_dir):
+    """__graft_entry__.smoke() - the first thing the driver runs on the GPU box - executed against the mock: its own
+    plumbing and its oracle comparison are sound (on the box it runs on the CUDA library, as everything else)."""
+    code = (
+        "import os, sys\n"
+        f"sys.path.insert(0, r'{ROOT}')\n"
+        "from votca_b200 import _capi\n"
+        f"_capi._api = _capi.CApi(os.path.join(r'{mock_dir}', 'libgwbse_b200.so'), _capi.HEADER)\n"
+        f"_capi._host_api = _capi.CApi(os.path.join(r'{mock_dir}', 'libgwbse_host.so'), _capi.HOST_HEADER)\n"
+        "import __graft_entry__ as g\n"
+        "g.smoke()\n")
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "smoke: max|dQP|" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
