@@ -80,3 +80,14 @@ def test_small_run_writes_all_parts(tmp_path):
     root = ET.parse(out).getroot()
     assert [c.tag for c in root if c.find("avg") is not None] == NAMES
     assert all(float(root.find(n).find("avg").text) > 0.0 for n in NAMES)
+
+
+@pytest.mark.gpu
+@FIRST_DEVICE_RUN_PENDING
+def test_small_run_from_basis_sets(tmp_path):
+    """--system: Filling_ThreeCenter includes the integrals (produced on the device), as the reference's Fill does."""
+    out = tmp_path / "gpu_benchmark.xml"
+    parts = gb.main(["--system", "methane-svp", "--repetitions", "1", "--outputfile", str(out), "--spacesize", "5"])
+    assert [p[0] for p in parts] == NAMES
+    root = ET.parse(out).getroot()
+    assert root.find("Basisset").text == "def2-svp" and root.find("AuxBasissetsize").text == "104"
