@@ -56,7 +56,7 @@ def main():
         ms = ctx.timer_stop_ms()
         if rep:
             best = min(best, ms)
-        print(f"  pass {rep}: {ms:.1f} ms  ({naux * N * N / ms / 1e6:.1f} G integrals/s incl. mirror)")
+        print(f"  pass {rep}: {ms:.1f} ms  ({naux * N * N / max(ms, 1e-9) / 1e6:.1f} G integrals/s incl. mirror)")
     print(f"best {best:.1f} ms; launches so far {ctx.launch_count()}")
     print(ctx.profile_report())
     if a.check:
