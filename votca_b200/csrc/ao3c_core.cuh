@@ -80,10 +80,11 @@ AO_HD int hidx(int t, int u, int v) {
 AO_HD int workspace_doubles(int la, int lb, int lc) {
   const int Lab = la + lb, L = Lab + lc;
   const int nca = nc_of(la), ncb = nc_of(lb), ncc = nc_of(lc);
-  int r = 2 * nh_of(L);
-  const int tmp = (2 * la + 1) * ncb;
-  if (tmp > r) r = tmp;
-  return 3 * (la + 1) * (lb + 1) * (Lab + 1) + r + nh_of(Lab) * ncc + nca * ncb * ncc + (L + 1);
+  // E, R (two levels) and G; after the primitive loops the same region holds the half-transformed block
+  int erg = 3 * (la + 1) * (lb + 1) * (Lab + 1) + 2 * nh_of(L) + nh_of(Lab) * ncc;
+  const int half = (2 * lc + 1) * (2 * la + 1) * ncb;
+  if (half > erg) erg = half;
+  return erg + nca * ncb * ncc + (L + 1);
 }
 
 // F_n(x) for one order: Taylor step off the tabulated grid, or erf + upward recursion beyond it
@@ -127,12 +128,11 @@ AO_HD void triple_block(const BasisView& dft, const BasisView& aux, const TableV
 
   double* E = ws;
   double* R = E + 3 * esz;
-  int rsz = 2 * nhL;
-  if (npa * ncb > rsz) rsz = npa * ncb;
-  double* G = R + rsz;
-  double* acc = G + nhab * ncc;
+  double* G = R + 2 * nhL;
+  int erg = 3 * esz + 2 * nhL + nhab * ncc;
+  if (npc * npa * ncb > erg) erg = npc * npa * ncb;
+  double* acc = ws + erg;
   double* seed = acc + nca * ncb * ncc;
-  double* tmp = R;  // free after the primitive loops
 
   const double Cx = overlap ? 0.0 : aux.center[3 * sc], Cy = overlap ? 0.0 : aux.center[3 * sc + 1],
                Cz = overlap ? 0.0 : aux.center[3 * sc + 2];
@@ -285,28 +285,31 @@ AO_HD void triple_block(const BasisView& dft, const BasisView& aux, const TableV
   }
   sync();
   const int fa = dft.func0[sa], fb = unit_b ? 0 : dft.func0[sb], fc = overlap ? 0 : aux.func0[sc];
-  for (int m = 0; m < npc; ++m) {
-    const int k = fc + m;
-    const bool wanted = k >= out.func_begin && k < out.func_end;  // same in every lane
-    if (!wanted) continue;
-    for (int it = lane; it < npa * ncb; it += nl) {
-      const int ma = it / ncb, jb = it % ncb;
-      double s = 0.0;
-      for (int ja = 0; ja < nca; ++ja) s += Ta[ma * nca + ja] * acc[(ja * ncb + jb) * ncc + m];
-      tmp[it] = s;
-    }
-    sync();
-    double* dst = out.base + (long long)(k - out.func_begin) * out.stride_k;
-    for (int it = lane; it < npa * npb; it += nl) {
-      const int mb = it / npa, ma = it % npa;  // ma fastest: consecutive lanes write consecutive mu
-      double s = 0.0;
-      for (int jb = 0; jb < ncb; ++jb) s += Tb[mb * ncb + jb] * tmp[ma * ncb + jb];
-      const long long mu = fa + ma, nu = fb + mb;
-      dst[mu * out.stride_mu + nu * out.stride_nu] = s;
-      if (out.mirror && sa != sb) dst[nu * out.stride_mu + mu * out.stride_nu] = s;
-    }
-    sync();
+  // shell a for all aux components at once: half[(m * npa + ma) * ncb + jb]; E, R and G are free now and
+  // npc * npa * ncb <= nherm(la + lb) * ncart(lc) for l_a >= l_b (workspace_doubles keeps the general bound)
+  double* half = E;
+  for (int it = lane; it < npc * npa * ncb; it += nl) {
+    const int jb = it % ncb, mm = it / ncb, ma = mm % npa, m = mm / npa;
+    double s = 0.0;
+    for (int ja = 0; ja < nca; ++ja) s += Ta[ma * nca + ja] * acc[(ja * ncb + jb) * ncc + m];
+    half[it] = s;
   }
+  sync();
+  // shell b, and out (only the aux functions inside the requested range); ma fastest: consecutive lanes write
+  // consecutive mu
+  for (int it = lane; it < npc * npb * npa; it += nl) {
+    const int ma = it % npa, mm = it / npa, mb = mm % npb, m = mm / npb;
+    const int k = fc + m;
+    if (k < out.func_begin || k >= out.func_end) continue;
+    double s = 0.0;
+    const double* h = half + (m * npa + ma) * ncb;
+    for (int jb = 0; jb < ncb; ++jb) s += Tb[mb * ncb + jb] * h[jb];
+    double* dst = out.base + (long long)(k - out.func_begin) * out.stride_k;
+    const long long mu = fa + ma, nu = fb + mb;
+    dst[mu * out.stride_mu + nu * out.stride_nu] = s;
+    if (out.mirror && sa != sb) dst[nu * out.stride_mu + mu * out.stride_nu] = s;
+  }
+  sync();  // the scratch may be reused by the caller's next triple
 }
 
 // What one thread of the launch does: thread tid of CTA `block` (nwarps warps) belongs to lane group `sub` of its warp;
