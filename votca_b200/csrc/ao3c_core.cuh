@@ -80,10 +80,10 @@ AO_HD int hidx(int t, int u, int v) {
 AO_HD int workspace_doubles(int la, int lb, int lc) {
   const int Lab = la + lb, L = Lab + lc;
   const int nca = nc_of(la), ncb = nc_of(lb), ncc = nc_of(lc);
-  // E, R (two levels) and G; after the primitive loops the same region holds the half-transformed block
+  // E, R (two levels) and G; after the primitive loops the same region holds the block with its aux index transformed
   int erg = 3 * (la + 1) * (lb + 1) * (Lab + 1) + 2 * nh_of(L) + nh_of(Lab) * ncc;
-  const int half = (2 * lc + 1) * (2 * la + 1) * ncb;
-  if (half > erg) erg = half;
+  const int pc = (2 * lc + 1) * nca * ncb;
+  if (pc > erg) erg = pc;
   return erg + nca * ncb * ncc + (L + 1);
 }
 
@@ -130,7 +130,7 @@ AO_HD void triple_block(const BasisView& dft, const BasisView& aux, const TableV
   double* R = E + 3 * esz;
   double* G = R + 2 * nhL;
   int erg = 3 * esz + 2 * nhL + nhab * ncc;
-  if (npc * npa * ncb > erg) erg = npc * npa * ncb;
+  if (npc * nca * ncb > erg) erg = npc * nca * ncb;
   double* acc = ws + erg;
   double* seed = acc + nca * ncb * ncc;
 
@@ -270,28 +270,26 @@ AO_HD void triple_block(const BasisView& dft, const BasisView& aux, const TableV
     }
   }
 
-  // ---- cartesian -> pure: aux index in place (one column per lane) ---------------------------------------------
+  // ---- cartesian -> pure, one index after the other.  E, R and G are free now: the aux index goes
+  //      acc[(ja, jb), c] -> pc[(m * nca + ja) * ncb + jb] in that region, shell a pc -> half[(m * npa + ma) * ncb + jb]
+  //      back in the accumulator region (npc * npa * ncb <= nca * ncb * ncc), shell b from half straight to memory
   const double* Tc = tb.pure + tb.pure_off[lc];
   const double* Ta = tb.pure + tb.pure_off[la];
   const double* Tb = tb.pure + tb.pure_off[lb];
-  for (int ab = lane; ab < nca * ncb; ab += nl) {
-    double col[28];
-    for (int c = 0; c < ncc; ++c) col[c] = acc[ab * ncc + c];
-    for (int m = 0; m < npc; ++m) {
-      double s = 0.0;
-      for (int c = 0; c < ncc; ++c) s += Tc[m * ncc + c] * col[c];
-      acc[ab * ncc + m] = s;
-    }
+  double* pc = ws;
+  double* half = acc;
+  for (int it = lane; it < npc * nca * ncb; it += nl) {
+    const int ab = it % (nca * ncb), m = it / (nca * ncb);
+    double s = 0.0;
+    for (int c = 0; c < ncc; ++c) s += Tc[m * ncc + c] * acc[ab * ncc + c];
+    pc[it] = s;
   }
   sync();
   const int fa = dft.func0[sa], fb = unit_b ? 0 : dft.func0[sb], fc = overlap ? 0 : aux.func0[sc];
-  // shell a for all aux components at once: half[(m * npa + ma) * ncb + jb]; E, R and G are free now and
-  // npc * npa * ncb <= nherm(la + lb) * ncart(lc) for l_a >= l_b (workspace_doubles keeps the general bound)
-  double* half = E;
   for (int it = lane; it < npc * npa * ncb; it += nl) {
     const int jb = it % ncb, mm = it / ncb, ma = mm % npa, m = mm / npa;
     double s = 0.0;
-    for (int ja = 0; ja < nca; ++ja) s += Ta[ma * nca + ja] * acc[(ja * ncb + jb) * ncc + m];
+    for (int ja = 0; ja < nca; ++ja) s += Ta[ma * nca + ja] * pc[(m * nca + ja) * ncb + jb];
     half[it] = s;
   }
   sync();
