@@ -325,6 +325,40 @@ def test_rotational_and_translational_invariance(lib, case):
         assert np.abs(w0 - w1).max() < 1e-10 * np.abs(w0).max()
 
 
+def test_invariance_benzene_def2_tzvp_every_class_up_to_ff_g(lib):
+    """BASELINE config 1 basis (benzene, def2-tzvp + aux-def2-tzvp: s..f orbital shells, s..g aux shells, 27 M
+    integrals): every angular-momentum class the benchmark molecules produce, checked by rigid-motion invariance of the
+    per-shell-triple norms, permutational symmetry, and positive definiteness of the two-centre metric."""
+    from votca_b200 import realsys
+    el, pos = realsys.benzene()
+    rng = np.random.default_rng(21)
+    R = np.linalg.qr(rng.standard_normal((3, 3)))[0]
+    if np.linalg.det(R) < 0:
+        R[:, 0] *= -1.0
+    pos2 = pos @ R.T + np.array([1.1, -0.4, 0.9])
+    res = []
+    for p in (pos, pos2):
+        d, a = realsys.shell_arrays("def2-tzvp", el, p), realsys.shell_arrays("aux-def2-tzvp", el, p)
+        N, naux = realsys.nfunc(d[0]), realsys.nfunc(a[0])
+        out = np.empty((naux, N, N))
+        assert lib.ao3c_host(len(d[0]), *_ptrs(d), len(a[0]), *_ptrs(a), 1, out.ctypes.data) == 0
+        res.append((out, d, a))
+    (T0, d, a), (T1, _, _) = res
+    assert (T0.shape[1], T0.shape[0]) == (222, 546) and max(d[0]) == 3 and max(a[0]) == 4
+    assert np.abs(T0 - T0.transpose(0, 2, 1)).max() < 1e-13 * np.abs(T0).max()
+    fo = np.concatenate([[0], np.cumsum(2 * d[0] + 1)])
+    fa = np.concatenate([[0], np.cumsum(2 * a[0] + 1)])
+    n0 = np.add.reduceat(np.add.reduceat(np.add.reduceat(T0 ** 2, fa[:-1], 0), fo[:-1], 1), fo[:-1], 2)
+    n1 = np.add.reduceat(np.add.reduceat(np.add.reduceat(T1 ** 2, fa[:-1], 0), fo[:-1], 1), fo[:-1], 2)
+    scale = n0.max()
+    assert np.abs(np.sqrt(n0) - np.sqrt(n1)).max() < 1e-10 * np.sqrt(scale)
+    classes = {(int(lc), int(max(la, lb)), int(min(la, lb))) for lc in a[0] for la in d[0] for lb in d[0]}
+    assert (4, 3, 3) in classes and len(classes) == 5 * 10
+    V = np.full((naux, naux), np.nan)  # two-centre metric of the aux basis: symmetric positive definite
+    assert lib.coulomb2c_host(len(a[0]), *_ptrs(a), V.ctypes.data) == 0
+    assert np.abs(V - V.T).max() < 1e-12 * np.abs(V).max() and np.linalg.eigvalsh(V).min() > 0.0
+
+
 def test_thread_sanitizer_finds_no_race():
     """Same source, 8 lanes on threads, under -fsanitize=thread: a missing barrier between two stages that share
     scratch would be reported as a data race (TSan exits non-zero)."""
