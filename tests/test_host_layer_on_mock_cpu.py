@@ -88,3 +88,51 @@ def test_smoke_entry_point_logic_on_the_mock(mock_dir):
         "g.smoke()\n")
     r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "smoke: max|dQP|" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_fill_with_the_reference_argument_list_on_the_mock(mock_dir):
+    """TCMatrix_gwbse::Fill(auxbasis, dftbasis, dft_orbitals) (threecenter.cc:72-90) of the C++ host layer, from RAW
+    basis-set contractions (AOBasisData::NormalizeFromRawContractions): overlap, two- and three-centre integrals and
+    V^-1/2 all behind the one call; result equals the oracle's TCMatrix.fill on methane def2-svp."""
+    so = os.path.join(mock_dir, "libfill_overload.so")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-o", so,
+                    os.path.join(HERE, "host_harness", "fill_overload_harness.cc"), "-L" + mock_dir, "-lgwbse_b200",
+                    "-Wl,-rpath,$ORIGIN"], check=True)
+    code = (
+        "import ctypes, json, sys\n"
+        "import numpy as np\n"
+        f"sys.path.insert(0, r'{ROOT}')\n"
+        "from oracle import threecenter\n"
+        "from tests import helpers\n"
+        "from votca_b200 import realsys\n"
+        f"lib = ctypes.CDLL(r'{so}')\n"
+        "c = helpers.methane_svp_case()\n"
+        "g = helpers.load_golden()\n"
+        "el = [str(e) for e in g['molecule_methane_tutorial/elements']]\n"
+        "pos = np.asarray(g['molecule_methane_tutorial/positions_bohr'])\n"
+        "def raw(name):\n"
+        "    bs = realsys.basis_set(name)\n"
+        "    l, npr, cen, ex, co = [], [], [], [], []\n"
+        "    for e, p in zip(el, pos):\n"
+        "        for sl, prims in bs[e]:\n"
+        "            l.append(sl); npr.append(len(prims)); cen.append(p)\n"
+        "            ex += [q[0] for q in prims]; co += [q[1] for q in prims]\n"
+        "    return (np.array(l, dtype=np.int32), np.array(npr, dtype=np.int32), np.ascontiguousarray(cen, dtype=np.float64),\n"
+        "            np.array(ex), np.array(co))\n"
+        "d, a = raw('def2-svp'), raw('aux-def2-svp')\n"
+        "N, naux, q = c['dft'].size, c['aux'].size, c['q']\n"
+        "C = np.asfortranarray(c['hf']['mos'])\n"
+        "out = np.zeros((q, naux, N)); removed = ctypes.c_long(); err = ctypes.create_string_buffer(256)\n"
+        "P = ctypes.c_void_p\n"
+        "lib.fill_from_bases.argtypes = [ctypes.c_int] + [P] * 5 + [ctypes.c_int] + [P] * 5 + [P, ctypes.c_long, ctypes.c_long, P, P, ctypes.c_char_p, ctypes.c_int]\n"
+        "rc = lib.fill_from_bases(len(d[0]), *[x.ctypes.data for x in d], len(a[0]), *[x.ctypes.data for x in a],\n"
+        "                         C.ctypes.data, N, q - 1, out.ctypes.data, ctypes.addressof(removed), err, 256)\n"
+        "assert rc == 0, err.value\n"
+        "tc = threecenter.TCMatrix(naux, 0, q - 1, 0, N - 1)\n"
+        "tc.fill_from_integrals(c['ao3c'], c['S'], c['V'], c['hf']['mos'])\n"
+        "got = out.transpose(0, 2, 1)\n"
+        "rel = np.linalg.norm(got - tc.M) / np.linalg.norm(tc.M)\n"
+        "assert rel < 1e-10 and removed.value == tc.removed, (rel, removed.value, tc.removed)\n"
+        "print('fill ok', rel)\n")
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "fill ok" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
