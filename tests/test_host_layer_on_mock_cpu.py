@@ -68,11 +68,12 @@ def test_basis_set_job_and_checkpoint_pass_on_the_mock(mock_dir):
 
 def test_late_gpu_test_files_are_sound_on_the_mock(mock_dir):
     """The GPU test files written after the round's GPU budget was spent (the reference's cudapipeline / cudamatrix
-    cases, the gpu_benchmark tool) run clean against the mock: their own code - argument order, shapes, pointer
+    cases, the gpu_benchmark tool, the less-travelled host options against the oracle) run clean against the mock: their own code - argument order, shapes, pointer
     offsets, expectations - is right, so a failure on the device would be the library's."""
     rc, passed, tail = run_gpu_tests_on_mock(mock_dir, [
-        "tests/test_zz_gpu_cudapipeline_cases.py", "tests/test_zz_gpu_benchmark_tool.py", "--runxfail"])
-    assert rc == 0 and passed >= 6, tail
+        "tests/test_zz_gpu_cudapipeline_cases.py", "tests/test_zz_gpu_benchmark_tool.py",
+        "tests/test_zz_gpu_host_options.py", "--runxfail"])
+    assert rc == 0 and passed >= 9, tail
 
 
 def test_smoke_entry_point_logic_on_the_mock(mock_dir):

@@ -1,0 +1,78 @@
+"""Less-travelled options of the C++ host layer against the oracle on identical inputs (methane / 3-21G of the
+reference's unit tests): fixed-point QP solver, scissor shift, linear mixing, Rebuild of the three-centre tensor every
+iteration, explicit level ranges with a BSE window that sticks out of the QP window on both sides (AdjustHqpSize,
+bse.cc:147-186), Olsen correction.  Runs on the GPU like tests/test_gpu_host.py, and in the CPU suite against the
+test-only mock (tests/test_host_layer_on_mock_cpu.py)."""
+import numpy as np
+import pytest
+
+from oracle import bse as obse
+from oracle import gw as ogw
+from tests.conftest import FIRST_DEVICE_RUN_PENDING
+from tests.helpers import methane_mmn
+from tests.test_gpu_host import GW_OPTS, make_job
+
+pytestmark = [pytest.mark.gpu, FIRST_DEVICE_RUN_PENDING]
+
+
+def _oracle_gw(golden, mmax=16, **kw):
+    tc = methane_mmn(golden["gw/mo_eigenvectors"], mmax=mmax)
+    opt = dict(homo=4, qpmin=0, qpmax=16, rpamin=0, rpamax=16, gw_sc_max_iterations=1, eta=1e-3,
+               sigma_integration="ppm", gw_mixing_order=0, g_sc_limit=1e-5, g_sc_max_iterations=50)
+    opt.update(kw)
+    q0, q1 = opt["qpmin"], opt["qpmax"]
+    g = ogw.GW(tc, golden["gw/vxc"][q0:q1 + 1, q0:q1 + 1], golden["inline/gw_mo_eigenvalues"])
+    g.configure(ogw.GWOptions(**opt))
+    g.calculate_gw_perturbation()
+    return tc, g
+
+
+def _job(golden, methane, **options):
+    opts = dict(GW_OPTS)
+    opts.update(options)
+    job = make_job(methane, golden["gw/mo_eigenvectors"], golden["inline/gw_mo_eigenvalues"], **opts)
+    job.set_array("vxc", golden["gw/vxc"])
+    return job
+
+
+def test_fixedpoint_qp_solver(golden, methane):
+    job = _job(golden, methane, gw__qp_solver="fixedpoint")
+    job.run()
+    _, g = _oracle_gw(golden, qp_solver="fixedpoint")
+    assert np.abs(g.get_gwa_results() - job.get("QPpert_energies")).max() < 1e-6
+    job.close()
+
+
+def test_scissor_shift_linear_mixing_and_rebuild_every_iteration(golden, methane):
+    res = {}
+    for rebuild in (1, 5):
+        job = _job(golden, methane, gw__mode="evGW", gw__sc_max_iter=3, gw__scissor_shift=0.05, gw__mixing_order=1,
+                   gw__mixing_alpha=0.6, gw__rebuild_3c_freq=rebuild)
+        job.run()
+        res[rebuild] = (job.get("QPpert_energies").copy(), job.get("RPA_inputenergies").copy(), job.scalar("gw_iterations"))
+        job.close()
+    _, g = _oracle_gw(golden, gw_sc_max_iterations=3, shift=0.05, gw_mixing_order=1, gw_mixing_alpha=0.6, reset_3c=5)
+    assert np.abs(g.get_gwa_results() - res[5][0]).max() < 1e-6
+    assert np.abs(g.rpa_input_energies() - res[5][1]).max() < 1e-6 and res[5][2] == g.iterations
+    # rebuilding the tensor from the integrals (or the device snapshot) every iteration changes nothing
+    assert np.abs(res[1][0] - res[5][0]).max() < 1e-9
+
+
+def test_bse_window_beyond_the_qp_window(golden, methane):
+    """ranges = explicit: QP window 1..12, BSE window 0..14 - Hqp is padded with RPA input energies on both sides."""
+    job = _job(golden, methane, tasks="gw,singlets,triplets", bse__useTDA=True, bse__exctotal=3,
+               bse__davidson__tolerance="strict", bse__davidson__correction="OLSEN", bse__use_Hqp_offdiag=True)
+    job.set_options(ranges="explicit", rpamax=16, qpmin=1, qpmax=12, bsemin=0, bsemax=14)  # overrides make_job's "full"
+    job.set_array("vxc", golden["gw/vxc"][1:13, 1:13])
+    job.run()
+    assert (job.scalar("qpmin"), job.scalar("qpmax"), job.scalar("bse_vmin"), job.scalar("bse_cmax")) == (1, 12, 0, 14)
+    tc, g = _oracle_gw(golden, mmax=14, qpmin=1, qpmax=12)
+    assert np.abs(g.get_gwa_results() - job.get("QPpert_energies")).max() < 1e-6
+    g.calculate_hqp()
+    b = obse.BSE(tc, factorised=True)
+    b.configure(obse.BSEOptions(useTDA=True, homo=4, rpamin=0, rpamax=16, qpmin=1, qpmax=12, vmin=0, cmax=14, nmax=3,
+                                davidson_tolerance="strict", davidson_correction="OLSEN", use_Hqp_offdiag=True),
+                g.rpa_input_energies(), g.get_hqp())
+    assert np.abs(b.solve_singlets()["eigenvalues"] - job.get("BSE_singlet_eigenvalues")).max() < 1e-6
+    assert np.abs(b.solve_triplets()["eigenvalues"] - job.get("BSE_triplet_eigenvalues")).max() < 1e-6
+    job.close()
