@@ -76,3 +76,32 @@ def test_bse_window_beyond_the_qp_window(golden, methane):
     assert np.abs(b.solve_singlets()["eigenvalues"] - job.get("BSE_singlet_eigenvalues")).max() < 1e-6
     assert np.abs(b.solve_triplets()["eigenvalues"] - job.get("BSE_triplet_eigenvalues")).max() < 1e-6
     job.close()
+
+
+def test_integral_producer_callback(golden, methane):
+    """The path a maintainer's libint loop takes (INTEGRATION.md): TCMatrix_gwbse::Fill3cMO asks an AOIntegralSource
+    for blocks of aux functions (here a callback, gwbse_job_set_ao3c_callback), stages them in page-locked memory and
+    contracts them; same result as handing the whole tensor over."""
+    from votca_b200.api import Job
+    res, calls = [], []
+    for use_callback in (False, True):
+        job = Job(0)
+        job.set_scalar("homo", 4)
+        job.set_array("mos", golden["gw/mo_eigenvectors"])
+        job.set_array("mo_energies", golden["inline/gw_mo_eigenvalues"])
+        job.set_array("vxc", golden["gw/vxc"])
+        job.set_array("aux_overlap", methane["S"])
+        job.set_array("aux_coulomb", methane["V"])
+        if use_callback:
+            def producer(off, cnt):
+                calls.append((off, cnt))
+                return methane["ao3c"][off:off + cnt]
+            job.set_ao3c_callback(17, 17, producer)
+        else:
+            job.set_ao3c(methane["ao3c"])
+        job.set_options(ranges="full", **GW_OPTS)
+        job.run()
+        res.append(job.get("QPpert_energies").copy())
+        job.close()
+    assert sum(c for _, c in calls) == 17 and [o for o, _ in calls] == sorted(o for o, _ in calls)
+    assert np.abs(res[0] - res[1]).max() < 1e-12

@@ -479,6 +479,20 @@ def _job_extras():
         self._ck(self.api.gwbse_job_set_ao3c_partial(self.h, int(nbasis), int(naux), int(first_aux), int(count),
                                                      ctypes.c_void_p(int(ptr_)), int(bool(on_device))))
 
+    def set_ao3c_callback(self, nbasis, naux, producer):
+        """AO integral producer called block by block, as the reference's libint loop would be
+        (gwbse_job_set_ao3c_callback): producer(aux_offset, aux_count) -> array (aux_count, N, N)."""
+        proto = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_long, ctypes.c_long, ctypes.POINTER(ctypes.c_double))
+        n2 = int(nbasis) * int(nbasis)
+
+        def trampoline(_user, aux_offset, aux_count, out):
+            blk = np.ascontiguousarray(producer(int(aux_offset), int(aux_count)), dtype=np.float64)
+            ctypes.memmove(out, blk.ctypes.data, 8 * n2 * int(aux_count))
+
+        cb = proto(trampoline)
+        self._keep.append(cb)
+        self._ck(self.api.gwbse_job_set_ao3c_callback(self.h, int(nbasis), int(naux), cb, None))
+
     def kernel_ctx(self):
         """The underlying gwbse_b200 context as a Context-like wrapper (profiling, timers)."""
         c = Context.__new__(Context)
@@ -490,6 +504,7 @@ def _job_extras():
     Job.set_ao3c_dev = set_ao3c_dev
     Job.set_ao3c_host_ptr = set_ao3c_host_ptr
     Job.set_ao3c_partial = set_ao3c_partial
+    Job.set_ao3c_callback = set_ao3c_callback
     Job.kernel_ctx = kernel_ctx
 
     def gemm_profile(self, enable=True):
