@@ -137,3 +137,28 @@ def test_fill_with_the_reference_argument_list_on_the_mock(mock_dir):
         "print('fill ok', rel)\n")
     r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "fill ok" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_host_layer_is_clean_under_address_and_ub_sanitizers(tmp_path):
+    """Host library and mock rebuilt with -fsanitize=address,undefined; a selection of the host-layer tests (GW golden,
+    evGW, BSE TDA / full, options, callback producer, basis-set job, .orb output) re-run in a child process with the
+    sanitizer runtimes preloaded: no out-of-bounds access, use-after-free or undefined behaviour in votca_b200/host."""
+    d = str(tmp_path)
+    flags = ["-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-fPIC", "-shared"]
+    subprocess.run(["g++"] + flags + ["-o", os.path.join(d, "libgwbse_b200.so"),
+                                      os.path.join(HERE, "host_harness", "mock_b200_for_tests.cc")], check=True)
+    subprocess.run(["g++"] + flags + ["-pthread", "-o", os.path.join(d, "libgwbse_host.so"),
+                                      os.path.join(ROOT, "votca_b200", "host", "driver.cc"), "-L" + d, "-lgwbse_b200",
+                                      "-Wl,-rpath,$ORIGIN"], check=True)
+    rt = [subprocess.run(["g++", "-print-file-name=" + n], capture_output=True, text=True).stdout.strip()
+          for n in ("libasan.so", "libubsan.so")]
+    env = dict(os.environ, GWBSE_B200_TEST_MOCK_DIR=d, LD_PRELOAD=":".join(rt),
+               ASAN_OPTIONS="detect_leaks=0:halt_on_error=1", UBSAN_OPTIONS="print_stacktrace=1")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider", "--runxfail",
+                        "tests/test_gpu_host.py", "tests/test_zz_gpu_host_options.py", "tests/test_zz_gpu_orb_output.py",
+                        "tests/test_zzz_gpu_ao3c_device.py", "-k",
+                        "not large_l and not cda and not exact and not water and not fill_from_basis"],
+                       cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
+    out = r.stdout + r.stderr
+    assert r.returncode == 0 and "AddressSanitizer" not in out and "runtime error:" not in out, out[-4000:]
+    assert int(re.search(r"(\d+) passed", r.stdout).group(1)) >= 15
