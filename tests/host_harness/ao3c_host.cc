@@ -200,6 +200,50 @@ int ao3c_grid_host(int nshell, const int* l, const int* nprim, const double* cen
   }
 }
 
+// Every triple with a scratch buffer of exactly workspace_doubles(la, lb, lc) doubles on the heap: built with
+// -fsanitize=address this flags any access outside the region the launcher reserves per lane group.  Also runs the
+// two-centre, overlap and dipole modes that way.  out as ao3c_host.
+int ao3c_exact_scratch_host(int nshell, const int* l, const int* nprim, const double* center, const double* exps,
+                            const double* coefs, int nshell_aux, const int* l_aux, const int* nprim_aux,
+                            const double* center_aux, const double* exps_aux, const double* coefs_aux, double* out) {
+  try {
+    static Tables tb;
+    HostBasis dft, aux;
+    dft.build(nshell, l, nprim, center, exps, coefs);
+    aux.build(nshell_aux, l_aux, nprim_aux, center_aux, exps_aux, coefs_aux);
+    const BasisView dv = view_of(dft), av = view_of(aux);
+    const long long N = dft.nfunc, M = aux.nfunc;
+    OutSpec spec{out, N * N, 1, N, 0, aux.nfunc, 1};
+    std::fill(out, out + (size_t)aux.nfunc * N * N, 0.0);
+    NoSync s;
+    const PairLists pl = make_pair_lists(dft, false);
+    for (const PairEntry& pe : pl.entries)
+      for (int c = 0; c < aux.nshell; ++c) {
+        std::vector<double> ws((size_t)workspace_doubles(dft.l[pe.a], dft.l[pe.b], aux.l[c]));
+        triple_block(dv, av, tb.view, pe, pl.pool.data(), c, ws.data(), 0, 1, s, spec);
+      }
+    std::vector<double> small((size_t)std::max(M * M, 3 * N * N));
+    const PairLists units = make_pair_lists(aux, true), auxpairs = make_pair_lists(aux, false);
+    OutSpec s2{small.data(), M, 1, 0, 0, aux.nfunc, 0};
+    for (const PairEntry& pe : units.entries)
+      for (int c = 0; c < aux.nshell; ++c) {
+        std::vector<double> ws((size_t)workspace_doubles(aux.l[pe.a], 0, aux.l[c]));
+        triple_block(av, av, tb.view, pe, units.pool.data(), c, ws.data(), 0, 1, s, s2);
+      }
+    for (int code = -1; code >= -4; --code) {
+      OutSpec s1{small.data(), 0, 1, N, 0, 1, 1};
+      for (const PairEntry& pe : pl.entries) {
+        std::vector<double> ws((size_t)workspace_doubles(dft.l[pe.a], dft.l[pe.b], 0));
+        triple_block(dv, dv, tb.view, pe, pl.pool.data(), code, ws.data(), 0, 1, s, s1);
+      }
+    }
+    (void)auxpairs;
+    return 0;
+  } catch (...) {
+    return 1;
+  }
+}
+
 // V[q][p] = (p | q) over one basis: unit partner
 int coulomb2c_host(int nshell, const int* l, const int* nprim, const double* center, const double* exps,
                    const double* coefs, double* out) {

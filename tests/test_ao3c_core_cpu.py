@@ -385,3 +385,34 @@ def test_thread_sanitizer_finds_no_race():
     r = subprocess.run([os.sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
     assert "WARNING: ThreadSanitizer" not in r.stderr, r.stderr[-3000:]
     assert r.returncode == 0, (r.returncode, r.stderr[-3000:])
+
+
+def test_scratch_bounds_under_address_sanitizer():
+    """Each shell triple gets a heap scratch of exactly workspace_doubles(la, lb, lc) - the size the launcher reserves
+    per lane group in shared memory - and the harness is built with -fsanitize=address: an access past that region in
+    any stage (three-centre, two-centre, overlap, dipole modes; s..f orbital, s..f aux, and the (G G | I) class) would
+    abort the child process."""
+    so = _build("libao3c_host_asan.so", ["-O1", "-g", "-fsanitize=address", "-fno-omit-frame-pointer"])
+    w, c = helpers.water_integrals(), helpers.methane_svp_case()
+    cases = {"water": (pack(w["dft"]), pack(w["aux"])), "methane": (pack(c["dft"]), pack(c["aux"])),
+             "gi": (pack(_golden_basis("G", "C2")), pack(_golden_basis("I", "C2")))}
+    arrs = {f"{k}_{s}_{i}": a for k, (d, x) in cases.items() for s, t in (("d", d), ("a", x)) for i, a in enumerate(t)}
+    np.savez(os.path.join(BUILD, "asan_in.npz"), **arrs)
+    code = (
+        "import ctypes, numpy as np, sys\n"
+        f"z = np.load(r'{os.path.join(BUILD, 'asan_in.npz')}')\n"
+        f"lib = ctypes.CDLL(r'{so}')\n"
+        "p, i = ctypes.c_void_p, ctypes.c_int\n"
+        "lib.ao3c_exact_scratch_host.argtypes = [i, p, p, p, p, p, i, p, p, p, p, p, p]\n"
+        "for k in ('water', 'methane', 'gi'):\n"
+        "    d = [np.ascontiguousarray(z[f'{k}_d_{j}']) for j in range(5)]\n"
+        "    a = [np.ascontiguousarray(z[f'{k}_a_{j}']) for j in range(5)]\n"
+        "    N, M = int((2 * d[0] + 1).sum()), int((2 * a[0] + 1).sum())\n"
+        "    out = np.zeros((M, N, N))\n"
+        "    rc = lib.ao3c_exact_scratch_host(len(d[0]), *[x.ctypes.data for x in d], len(a[0]), *[x.ctypes.data for x in a], out.ctypes.data)\n"
+        "    assert rc == 0 and np.isfinite(out).all() and np.abs(out).max() > 0\n"
+        "print('asan clean')\n")
+    rt = subprocess.run(["g++", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    env = dict(os.environ, LD_PRELOAD=rt, ASAN_OPTIONS="detect_leaks=0:halt_on_error=1")
+    r = subprocess.run([os.sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "asan clean" in r.stdout and "AddressSanitizer" not in r.stderr, r.stderr[-3000:]
