@@ -28,52 +28,63 @@ def mock_dir():
     return MOCK
 
 
-def run_gpu_tests_on_mock(mock_dir, args):
+MOCK_RUN_FILES = ["tests/test_gpu_kernels.py", "tests/test_gpu_host.py", "tests/test_gpu_zz_reference_checkpoint.py",
+                  "tests/test_zzz_gpu_ao3c_device.py", "tests/test_zz_gpu_orb_output.py",
+                  "tests/test_zz_gpu_cudapipeline_cases.py", "tests/test_zz_gpu_benchmark_tool.py",
+                  "tests/test_zz_gpu_host_options.py"]
+
+
+@pytest.fixture(scope="module")
+def mock_run(mock_dir):
+    """One child process runs every GPU test file against the mock (shared oracle caches); {test id: outcome}.
+    Left out for time: the two large property tests of the kernels and the (G G | I) integrals through the oracle."""
     env = dict(os.environ, GWBSE_B200_TEST_MOCK_DIR=mock_dir)
-    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider", "-rxXfE"] + args,
-                       cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
-    tail = r.stdout[-4000:] + r.stderr[-2000:]
-    m = re.search(r"(\d+) passed", r.stdout)
-    return r.returncode, int(m.group(1)) if m else 0, tail
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider", "--runxfail", "-rA",
+                        "-k", "not medium_size and not full_size and not large_l"] + MOCK_RUN_FILES,
+                       cwd=ROOT, env=env, capture_output=True, text=True, timeout=2400)
+    outcomes = dict((m.group(2), m.group(1)) for m in re.finditer(r"^(PASSED|FAILED|ERROR) (\S+)", r.stdout, re.M))
+    return outcomes, r.stdout[-6000:] + r.stderr[-2000:]
 
 
-def test_mock_is_faithful_on_the_kernel_tests(mock_dir):
+def _check(mock_run, prefix, at_least):
+    outcomes, tail = mock_run
+    mine = {k: v for k, v in outcomes.items() if k.startswith(prefix)}
+    bad = {k: v for k, v in mine.items() if v != "PASSED"}
+    assert not bad and len(mine) >= at_least, (bad, len(mine), tail)
+
+
+def test_mock_is_faithful_on_the_kernel_tests(mock_run):
     """The stand-in passes the tests the CUDA kernels are checked with (tests/test_gpu_kernels.py: every C ABI entry
-    point against the oracle and the reference's golden matrices; only the two large property tests are left out for
-    time) - so what the host layer sees from it is what it sees from the device."""
-    rc, passed, tail = run_gpu_tests_on_mock(mock_dir, ["tests/test_gpu_kernels.py", "-k",
-                                                        "not medium_size and not full_size"])
-    assert rc == 0 and passed >= 40, tail
+    point against the oracle and the reference's golden matrices) - so what the host layer sees from it is what it
+    sees from the device."""
+    _check(mock_run, "tests/test_gpu_kernels.py", 40)
 
 
-def test_gw_and_bse_host_tests_pass_on_the_mock(mock_dir):
+def test_gw_and_bse_host_tests_pass_on_the_mock(mock_run):
     """tests/test_gpu_host.py, all of it: golden G0W0 (test_gw.cc), canonical / Brent root search, evGW with the ppm,
     exact and cda integrators against the oracle, BSE TDA / full / triplets with dynamical screening (test_bse.cc),
     oscillator strengths, options XML, error convention; and tests/test_gpu_zz_reference_checkpoint.py: BSE on the
     reference's own dftgwbse checkpoints (water, d/f aux shells), the PPM known answer, the tier-R methane case."""
-    rc, passed, tail = run_gpu_tests_on_mock(mock_dir, ["tests/test_gpu_host.py",
-                                                        "tests/test_gpu_zz_reference_checkpoint.py"])
-    assert rc == 0 and passed >= 17, tail
+    _check(mock_run, "tests/test_gpu_host.py", 13)
+    _check(mock_run, "tests/test_gpu_zz_reference_checkpoint.py", 4)
 
 
-def test_basis_set_job_and_checkpoint_pass_on_the_mock(mock_dir):
+def test_basis_set_job_and_checkpoint_pass_on_the_mock(mock_run):
     """Jobs fed with basis sets only (integrals from the shared ao3c_core source, interlevel dipoles formed by the
     host layer) against jobs fed with the oracle's arrays, the error texts of gwbse_basis_create, and the .orb
     checkpoint a job writes (tests/test_zzz_gpu_ao3c_device.py, tests/test_zz_gpu_orb_output.py)."""
-    rc, passed, tail = run_gpu_tests_on_mock(mock_dir, [
-        "tests/test_zzz_gpu_ao3c_device.py", "tests/test_zz_gpu_orb_output.py", "--runxfail", "-k",
-        "not large_l"])
-    assert rc == 0 and passed >= 4, tail
+    _check(mock_run, "tests/test_zzz_gpu_ao3c_device.py", 4)
+    _check(mock_run, "tests/test_zz_gpu_orb_output.py", 1)
 
 
-def test_late_gpu_test_files_are_sound_on_the_mock(mock_dir):
+def test_late_gpu_test_files_are_sound_on_the_mock(mock_run):
     """The GPU test files written after the round's GPU budget was spent (the reference's cudapipeline / cudamatrix
-    cases, the gpu_benchmark tool, the less-travelled host options against the oracle) run clean against the mock: their own code - argument order, shapes, pointer
-    offsets, expectations - is right, so a failure on the device would be the library's."""
-    rc, passed, tail = run_gpu_tests_on_mock(mock_dir, [
-        "tests/test_zz_gpu_cudapipeline_cases.py", "tests/test_zz_gpu_benchmark_tool.py",
-        "tests/test_zz_gpu_host_options.py", "--runxfail"])
-    assert rc == 0 and passed >= 10, tail
+    cases, the gpu_benchmark tool, the less-travelled host options against the oracle) run clean against the mock:
+    their own code - argument order, shapes, pointer offsets, expectations - is right, so a failure on the device
+    would be the library's."""
+    _check(mock_run, "tests/test_zz_gpu_cudapipeline_cases.py", 4)
+    _check(mock_run, "tests/test_zz_gpu_benchmark_tool.py", 2)
+    _check(mock_run, "tests/test_zz_gpu_host_options.py", 4)
 
 
 def test_smoke_entry_point_logic_on_the_mock(mock_dir):
