@@ -88,7 +88,7 @@ inline double factorial(int n) {
 inline std::vector<double> make_pure_matrix(int l) {
   const int nc = ncart(l);
   std::vector<double> T((size_t)(2 * l + 1) * nc, 0.0);
-  auto cidx = [&](int lx, int ly, int lz) { return (ly + lz) * (ly + lz + 1) / 2 + lz; };
+  auto cidx = [&](int ly, int lz) { return (ly + lz) * (ly + lz + 1) / 2 + lz; };  // libint order within a shell
   for (int m = -l; m <= l; ++m) {
     const int am = m < 0 ? -m : m;
     const double norm = (1.0 / (std::pow(2.0, am) * factorial(l))) *
@@ -103,7 +103,7 @@ inline std::vector<double> make_pure_matrix(int l) {
                            binom(t, u) * binom(am, twov);
           const int lx = 2 * t + am - 2 * u - twov, ly = 2 * u + twov, lz = l - 2 * t - am;
           if (lx < 0 || ly < 0 || lz < 0) continue;
-          T[(size_t)(m + l) * nc + cidx(lx, ly, lz)] += norm * c;
+          T[(size_t)(m + l) * nc + cidx(ly, lz)] += norm * c;
         }
   }
   return T;
