@@ -365,7 +365,9 @@ def main():
                    "l2_policy": "inputs larger than L2 (Mmn 13.9 GB, AO tensor 39.6 GB)" if N > 1000 else
                    "small workload, L2-resident", "gw_iterations": counts["gw_iterations"],
                    "davidson_iterations": counts["davidson_iterations"], "results": results,
-                   "stage_seconds": stage_times},
+                   "stage_seconds": stage_times,
+                   "ao_integrals": "supplied as a synthetic tensor (the reference's libint stage, row a2, is an input; "
+                                   "the device producer gwbse_mmn_fill_from_basis is not on this path)"},
         "tflops": {"value": total_flops / (ms_per_step * 1e-3) / 1e12, "algorithmic_tflop_per_step": total_flops / 1e12,
                    "stages_tflop": {k: round(v / 1e12, 3) for k, v in flops.items()}},
         "roofline": {"bound": "tensor", "kernel": "gemm_dmma_kernel (FP64 DMMA.8x8x4)", "achieved": achieved,
