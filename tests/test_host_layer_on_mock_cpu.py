@@ -87,6 +87,15 @@ def test_late_gpu_test_files_are_sound_on_the_mock(mock_run):
     _check(mock_run, "tests/test_zz_gpu_host_options.py", 4)
 
 
+def test_every_pending_gpu_test_file_runs_on_the_mock():
+    """A GPU test file that has not had its device run yet (FIRST_DEVICE_RUN_PENDING) must at least be exercised
+    against the mock above, so that its own code is known to be sound."""
+    import glob
+    pending = [os.path.relpath(p, ROOT) for p in glob.glob(os.path.join(HERE, "test_*.py"))
+               if "FIRST_DEVICE_RUN_PENDING" in open(p).read() and os.path.basename(p) != os.path.basename(__file__)]
+    assert pending and set(pending) <= set(MOCK_RUN_FILES), sorted(set(pending) - set(MOCK_RUN_FILES))
+
+
 def test_smoke_entry_point_logic_on_the_mock(mock_dir):
     """__graft_entry__.smoke() - the first thing the driver runs on the GPU box - executed against the mock: its own
     plumbing and its oracle comparison are sound (on the box it runs on the CUDA library, as everything else)."""
