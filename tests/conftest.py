@@ -64,13 +64,6 @@ def _install_mock_lapack_hook(lib):
     lib.mock_set_gen_eig(cb)
 
 
-# GPU tests written after the round's GPU budget was spent: non-strict xfail until a device run is on record, so that
-# they report XPASS when they run clean and cannot turn the suite red through a defect that only a device can show.
-# Everything they exercise is verified on the CPU as far as a CPU can (see the docstring of each file).
-FIRST_DEVICE_RUN_PENDING = pytest.mark.xfail(
-    strict=False, reason="written after the round-1 GPU budget was spent: first device run pending")
-
-
 @pytest.fixture(scope="session")
 def golden():
     from tests.helpers import load_golden

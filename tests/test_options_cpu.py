@@ -12,8 +12,8 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 IT = "/root/reference/xtp/src/tests/DataFiles/xtp_tools_integration_tests"
 
-# options of gwbse.xml this path does not consume: QSGW (out of scope), sigma plotting, fragment analysis
-NOT_CONSUMED = ("gw.do_qsgw", "gw.qsgw_", "gw.sigma_plot", "bse.fragments", "auxbasisset")
+# options of gwbse.xml this path does not consume (it rejects them when they are set): sigma plotting, fragment analysis
+NOT_CONSUMED = ("gw.sigma_plot", "bse.fragments", "auxbasisset")
 
 
 @pytest.fixture(scope="module")
@@ -102,6 +102,21 @@ def test_dotted_keys_with_reference_prefixes(lib):
         lib.opt_set(o, b"gw.mode", b"evGW")
     assert lib.opt_load_xml(o, b"/nonexistent/options.xml") == 1
     lib.opt_free(o)
+
+
+def test_unknown_and_unsupported_keys_are_rejected(lib):
+    """A key that gwbse.xml does not have is an error (the reference validates options against that file), and a key
+    it has but this path does not implement must not be swallowed: silently different physics is worse than a throw."""
+    o = lib.opt_new()
+    assert lib.opt_set(o, b"gw.moed", b"G0W0") == 1  # misspelled
+    assert lib.opt_set(o, b"bse.davidson.tolerence", b"strict") == 1
+    assert lib.opt_set(o, b"gw.sigma_plot.states", b"1 3 5") == 1
+    assert lib.opt_set(o, b"bse.fragments.fragment.indices", b"1:3") == 1
+    assert lib.opt_set(o, b"gw.sigma_plot.steps", b"201") == 0  # harmless without a state list
+    assert lib.opt_set(o, b"gw.qsgw_max_iterations", b"7") == 0 and get(lib, o, "gw.qsgw_max_iterations") == "7"
+    lib.opt_free(o)
+    assert "exciton" in _ranges(lib, 4, 17, tasks="gw,excitons")
+    assert "exciton" in _ranges(lib, 4, 17, tasks="exciton_uks")
 
 
 def test_rpa_update_input_energies_known_answer(lib):

@@ -6,7 +6,6 @@ import xml.etree.ElementTree as ET
 import numpy as np
 import pytest
 
-from tests.conftest import FIRST_DEVICE_RUN_PENDING
 from votca_b200.tools import gpu_benchmark as gb
 
 NAMES = ["Filling_ThreeCenter", "Multiplication_of_tensor_with_matrix", "RPA_evaluation", "SingletOperator_TDA",
@@ -72,7 +71,6 @@ def test_tool_plumbing_on_the_cpu(tmp_path, monkeypatch):
 
 
 @pytest.mark.gpu
-@FIRST_DEVICE_RUN_PENDING
 def test_small_run_writes_all_parts(tmp_path):
     out = tmp_path / "gpu_benchmark.xml"
     parts = gb.main(["--workload", "tiny", "--repetitions", "2", "--outputfile", str(out), "--spacesize", "7"])
@@ -83,7 +81,6 @@ def test_small_run_writes_all_parts(tmp_path):
 
 
 @pytest.mark.gpu
-@FIRST_DEVICE_RUN_PENDING
 def test_small_run_from_basis_sets(tmp_path):
     """--system: Filling_ThreeCenter includes the integrals (produced on the device), as the reference's Fill does."""
     out = tmp_path / "gpu_benchmark.xml"

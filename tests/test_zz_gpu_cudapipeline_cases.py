@@ -10,9 +10,8 @@ import pytest
 
 from tests.helpers import rel_frob
 
-from tests.conftest import FIRST_DEVICE_RUN_PENDING
 
-pytestmark = [pytest.mark.gpu, FIRST_DEVICE_RUN_PENDING]
+pytestmark = pytest.mark.gpu
 TOL = 1e-9
 
 

@@ -8,11 +8,10 @@ import pytest
 
 from oracle import bse as obse
 from oracle import gw as ogw
-from tests.conftest import FIRST_DEVICE_RUN_PENDING
 from tests.helpers import methane_mmn
 from tests.test_gpu_host import GW_OPTS, make_job
 
-pytestmark = [pytest.mark.gpu, FIRST_DEVICE_RUN_PENDING]
+pytestmark = pytest.mark.gpu
 
 
 def _oracle_gw(golden, mmax=16, **kw):

@@ -6,9 +6,8 @@ import pytest
 
 from oracle.orbfile import OrbFile
 
-from tests.conftest import FIRST_DEVICE_RUN_PENDING
 
-pytestmark = [pytest.mark.gpu, FIRST_DEVICE_RUN_PENDING]
+pytestmark = pytest.mark.gpu
 
 
 def test_job_writes_orb_checkpoint(tmp_path):

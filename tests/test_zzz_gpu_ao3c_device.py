@@ -13,10 +13,9 @@ import pytest
 
 from oracle import threecenter
 from tests import helpers
-from tests.conftest import FIRST_DEVICE_RUN_PENDING
 from tests.test_ao3c_core_cpu import _golden_basis, pack, relmax
 
-pytestmark = [pytest.mark.gpu, FIRST_DEVICE_RUN_PENDING]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")

@@ -155,6 +155,9 @@ int gwbse_job_set_ao3c_callback(gwbse_job* job, long nbasis, long naux, gwbse_ao
   job->ints.fn = fn;
   job->ints.user = user;
   job->ints.ao3c = nullptr;
+  job->ints.ao3c_dev = nullptr;  // an earlier set_ao3c_dev / set_ao3c_partial must not shadow the callback
+  job->ints.first_aux = 0;
+  job->ints.held = -1;
   job->ints.N = nbasis;
   job->ints.naux = naux;
   JOB_END(job)

@@ -31,7 +31,8 @@ class Options {
         {"gw.qp_root_finder", "bisection"}, {"gw.qp_restrict_search", "true"}, {"gw.qp_zero_margin", "1e-6"},
         {"gw.qp_virtual_min_energy", "-0.1"}, {"gw.qp_sc_max_iter", "100"}, {"gw.qp_sc_limit", "1e-5"},
         {"gw.sc_max_iter", "50"}, {"gw.mixing_order", "20"}, {"gw.sc_limit", "1e-5"}, {"gw.mixing_alpha", "0.7"},
-        {"gw.rebuild_3c_freq", "5"}, {"bse.exctotal", "10"}, {"bse.useTDA", "false"},
+        {"gw.rebuild_3c_freq", "5"}, {"gw.do_qsgw", "false"}, {"gw.qsgw_max_iterations", "20"},
+        {"gw.qsgw_sc_limit", "1e-5"}, {"gw.qsgw_max_virt_correction", "0.5"}, {"bse.exctotal", "10"}, {"bse.useTDA", "false"},
         {"bse.dyn_screen_max_iter", "0"}, {"bse.dyn_screen_tol", "1e-5"}, {"bse.davidson.correction", "DPR"},
         {"bse.davidson.tolerance", "normal"}, {"bse.davidson.update", "safe"}, {"bse.davidson.maxiter", "50"},
         {"bse.use_Hqp_offdiag", "false"}, {"bse.print_weight", "0.5"}};
@@ -44,7 +45,33 @@ class Options {
         k = k.substr(std::string(pre).size());
         break;
       }
+    check_key(k, value);
     kv_[k] = value;
+  }
+  // Keys of share/xtp/xml/subpackages/gwbse.xml.  An unknown key is an error (the reference's OptionsHandler rejects
+  // it against the same file), and a known key that asks for something this path does not implement is an error
+  // too instead of silently different physics.
+  static void check_key(const std::string& k, const std::string& value) {
+    static const char* known[] = {
+        "tasks", "ranges", "rpamax", "qpmin", "qpmax", "bsemin", "bsemax", "ignore_corelevels", "auxbasisset",
+        "gw.mode", "gw.scissor_shift", "gw.sigma_integrator", "gw.eta", "gw.alpha", "gw.quadrature_scheme",
+        "gw.quadrature_order", "gw.qp_solver", "gw.qp_grid_search_mode", "gw.qp_root_finder",
+        "gw.qp_full_window_half_width", "gw.qp_dense_spacing", "gw.qp_adaptive_shell_width",
+        "gw.qp_adaptive_shell_count", "gw.qp_grid_steps", "gw.qp_grid_spacing", "gw.qp_restrict_search",
+        "gw.qp_zero_margin", "gw.qp_virtual_min_energy", "gw.qp_sc_max_iter", "gw.qp_sc_limit", "gw.sc_max_iter",
+        "gw.mixing_order", "gw.sc_limit", "gw.mixing_alpha", "gw.do_qsgw", "gw.qsgw_max_iterations",
+        "gw.qsgw_sc_limit", "gw.qsgw_max_virt_correction", "gw.rebuild_3c_freq", "gw.sigma_plot.states",
+        "gw.sigma_plot.steps", "gw.sigma_plot.spacing", "gw.sigma_plot.filename", "bse.exctotal", "bse.useTDA",
+        "bse.dyn_screen_max_iter", "bse.dyn_screen_tol", "bse.davidson.correction", "bse.davidson.tolerance",
+        "bse.davidson.update", "bse.davidson.maxiter", "bse.use_Hqp_offdiag", "bse.print_weight"};
+    bool ok = k.rfind("bse.fragments", 0) == 0;
+    for (const char* n : known) ok = ok || k == n;
+    if (!ok) throw std::runtime_error("unknown option '" + k + "' (not a key of gwbse.xml)");
+    if (value.empty()) return;
+    if (k == "gw.sigma_plot.states")
+      throw std::runtime_error("gw.sigma_plot is not implemented on this path (GW::PlotSigma, gw.cc:778-796)");
+    if (k.rfind("bse.fragments", 0) == 0)
+      throw std::runtime_error("bse.fragments needs the atom tables of the host package (not on this path)");
   }
   bool exists(const std::string& key) const {
     auto it = kv_.find(key);
@@ -99,7 +126,10 @@ class Options {
               if (in_gwbse) key += (key.empty() ? "" : ".") + e;
               if (e == "gwbse") in_gwbse = true;
             }
-            if (in_gwbse && !key.empty()) kv_[key] = t;
+            if (in_gwbse && !key.empty()) {
+              check_key(key, t);
+              kv_[key] = t;
+            }
           }
           text.clear();
           if (!stack.empty()) stack.pop_back();
@@ -256,6 +286,10 @@ class GWBSE {
     bseopt_.min_print_weight = options.dbl("bse.print_weight");
     std::string tasks = options.str("tasks");
     for (char& c : tasks) c = static_cast<char>(std::tolower(static_cast<unsigned char>(c)));
+    if (tasks.find("exciton") != std::string::npos)
+      throw std::runtime_error("tasks 'excitons' / 'exciton_uks' (unrestricted BSE, bse_uks.cc) are not on this path");
+    if (options.flag("gw.do_qsgw"))
+      throw std::runtime_error("gw.do_qsgw is not implemented on this path (GW::CalculateQSGW, gw.cc:798-1130)");
     do_gw_ = tasks.find("gw") != std::string::npos;
     if (tasks.find("all") != std::string::npos) do_gw_ = do_bse_singlets_ = do_bse_triplets_ = true;
     if (tasks.find("singlets") != std::string::npos) do_bse_singlets_ = true;
