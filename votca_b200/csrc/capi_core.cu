@@ -6,6 +6,7 @@
 
 #include "../../include/gwbse_b200.h"
 #include "context.cuh"
+#include "gemm_tma.cuh"
 
 using namespace gwbse;
 
@@ -180,6 +181,9 @@ int gwbse_set_option(gwbse_ctx* ctx, const char* key, double value) {
     ctx->collect_regions();
     ctx->regions.clear();
     ctx->profile = value != 0.0;
+  } else if (k == "tma") {
+    // process-wide switch between the TMA-staged GEMM and the cp.async kernel for operands both can take (A/B timing)
+    gwbse::gemm_tma_set_enabled(value != 0.0);
   } else if (k == "bse_chunk_bytes") {
     GW_REQUIRE(value >= 1024, "bse_chunk_bytes too small");
     ctx->bse_chunk_bytes = (size_t)value;

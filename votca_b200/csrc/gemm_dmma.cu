@@ -4,6 +4,7 @@
 #include <cstdint>
 
 #include "gemm_dmma.cuh"
+#include "gemm_tma.cuh"
 
 namespace gwbse {
 
@@ -143,7 +144,23 @@ GemmParams apply_swap(GemmParams p) {
 
 }  // namespace
 
+// force_cfg: -1 auto (TMA kernel when the operands allow it), 0..5 cp.async tile shapes, 10..13 TMA tile shapes
+static bool wants_tma(const GemmParams& p, int num_sms, int force_cfg, int force_splitk) {
+  if (force_cfg >= 0 && force_cfg < 10) return false;
+  int c, sw, sk;
+  return gemm_tma_describe(p, num_sms, force_cfg >= 10 ? force_cfg - 10 : -1, force_splitk, &c, &sw, &sk);
+}
+
 size_t gemm_ws_bytes_needed(const GemmParams& p, int num_sms, int force_cfg, int force_splitk) {
+  if (wants_tma(p, num_sms, force_cfg, force_splitk)) {
+    // the cp.async kernel is the fallback if a tensor map cannot be encoded: reserve for whichever needs more
+    const size_t t = gemm_tma_ws_bytes(p, num_sms, force_cfg >= 10 ? force_cfg - 10 : -1, force_splitk);
+    Plan pl = make_plan(p, num_sms, -1, force_splitk);
+    const size_t o = pl.splitk <= 1 ? 0
+                                    : sizeof(double) * (size_t)pl.tiles_m * kCfg[pl.cfg].BM * pl.tiles_n *
+                                          kCfg[pl.cfg].BN * pl.splitk * p.Z1 * p.Z2;
+    return std::max(t, o);
+  }
   Plan pl = make_plan(p, num_sms, force_cfg, force_splitk);
   if (pl.splitk <= 1) return 0;
   return sizeof(double) * (size_t)pl.tiles_m * kCfg[pl.cfg].BM * pl.tiles_n * kCfg[pl.cfg].BN * pl.splitk * p.Z1 *
@@ -152,6 +169,11 @@ size_t gemm_ws_bytes_needed(const GemmParams& p, int num_sms, int force_cfg, int
 
 void gemm_plan_describe(const GemmParams& p, int num_sms, int force_cfg, int force_splitk, int* cfg, int* swap,
                         int* splitk) {
+  if (wants_tma(p, num_sms, force_cfg, force_splitk)) {
+    gemm_tma_describe(p, num_sms, force_cfg >= 10 ? force_cfg - 10 : -1, force_splitk, cfg, swap, splitk);
+    *cfg += 10;
+    return;
+  }
   Plan pl = make_plan(p, num_sms, force_cfg, force_splitk);
   *cfg = pl.cfg;
   *swap = pl.swap ? 1 : 0;
@@ -162,6 +184,10 @@ void gemm_launch(GemmParams p, cudaStream_t stream, double* ws, size_t ws_bytes,
                  int force_splitk) {
   if (p.M <= 0 || p.N <= 0 || p.Z1 <= 0 || p.Z2 <= 0) return;
   GW_REQUIRE(p.Ko >= 1 && p.Ki >= 0, "bad K extents");
+  if (wants_tma(p, num_sms, force_cfg, force_splitk)) {
+    if (gemm_tma_try_launch(p, stream, ws, ws_bytes, num_sms, force_cfg >= 10 ? force_cfg - 10 : -1, force_splitk)) return;
+    force_cfg = -1;  // tensor map not encodable: cp.async kernel
+  }
   Plan pl = make_plan(p, num_sms, force_cfg, force_splitk);
   if (pl.swap) p = apply_swap(p);
   const bool ak = is_kmajor(p.A, p.Ki), bk = is_kmajor(p.B, p.Ki);
