@@ -3,28 +3,46 @@
 measured DMMA peak, and the host-CPU reference beside it.
 
 One "step" = the full GW-BSE stage of one molecule: Mmn fill (AO->MO three-centre transform + V^-1/2),
-evGW with the plasmon-pole model (RPA epsilon, PPM rotation, batched QP root search, Hqp), then BSE
-(static screening, 10 singlets by Davidson, TDA off = full BSE as the reference default).  The workload
-is the DCV5T def2-tzvp size of SURVEY.md section 8 (N=1249, Naux=3177, homo=143 -> m=q=431, B=41328) on
-synthetic tier-S inputs (votca_b200/synthetic.py).
+GW with the plasmon-pole model (RPA epsilon, PPM rotation, batched QP root search, Hqp), then BSE
+(static screening, 10 singlets by Davidson, TDA off = full BSE as the reference default).
 
-  python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--workload NAME]
+Workloads (SURVEY.md section 8 sizes):
+  dcv5t-tzvp  BASELINE config 3: N=1249, Naux=3177, homo=143 -> m=q=431, B=41328; evGW.  Synthetic tier-S inputs
+              (votca_b200/synthetic.py): the AO three-centre tensor is an input (39.6 GB, resident in HBM for `value`,
+              in pinned host memory for `e2e`).
+  c60-tzvp    BASELINE config 4: C60 def2-tzvp + aux-def2-tzvp, N=1860, Naux=4560, homo=179 -> m=q=539, B=64620; G0W0.
+              Tier R: real geometry and basis sets, the AO Coulomb integrals are produced on the device
+              (gwbse_mmn_fill_from_basis path: the 126 GB AO tensor never exists), synthetic orthonormal MOs.
+  benzene-tzvp, small, medium: short runs of the same two kinds.
+
+  python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--workload NAME] [--mode evGW|G0W0]
 """
-import argparse
-import json
 import os
-import subprocess
 import sys
-import threading
-import time
 
-import numpy as np
+if "--impl" in sys.argv and sys.argv[sys.argv.index("--impl") + 1:][:1] == ["reference"]:
+    # the CPU arm uses every host core whatever the launcher exported (torchrun sets OMP_NUM_THREADS=1);
+    # must happen before NumPy / OpenBLAS / libgomp are loaded
+    _n = str(os.cpu_count() or 1)
+    for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_k] = _n
+
+import argparse  # noqa: E402
+import json  # noqa: E402
+import subprocess  # noqa: E402
+import threading  # noqa: E402
+import time  # noqa: E402
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "gwbse_wall_seconds_per_molecule"
 UNIT = "s/molecule"
+TIER_R = ("c60-tzvp", "benzene-tzvp", "methane-svp")
+DEFAULT_MODE = {"c60-tzvp": "G0W0"}
+COUNTS_FILE = os.path.join(ROOT, "votca_b200", "data", "bench_counts.json")
 
 
 def parse_args():
@@ -34,10 +52,16 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="dcv5t-tzvp")
-    ap.add_argument("--mode", default="evGW", choices=["evGW", "G0W0"])
+    ap.add_argument("--mode", default=None, choices=["evGW", "G0W0"])
+    ap.add_argument("--also", default="", help="second workload measured with 1 warm-up + 2 steps (reported under 'also')")
+    ap.add_argument("--e2e-steps", type=int, default=3, help="upper bound on the timed steps of the end-to-end arm")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-parity", action="store_true")
+    a = ap.parse_args()
+    if a.mode is None:
+        a.mode = DEFAULT_MODE.get(a.workload, "evGW")
+    return a
 
 
 class ClockSampler:
@@ -88,6 +112,13 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def sizes(workload):
+    from votca_b200 import synthetic
+    N, naux, homo = synthetic.CONFIGS[workload]
+    q = min(3 * homo + 1, N - 1) + 1
+    return N, naux, homo, q
+
+
 def algorithmic_flops(N, naux, homo, counts, k_bse=15):
     """mathematically necessary dense work of the contraction stages."""
     q = min(3 * homo + 1, N - 1) + 1
@@ -112,6 +143,92 @@ def algorithmic_flops(N, naux, homo, counts, k_bse=15):
     return f
 
 
+def workload_name(workload, mode, N, naux, homo):
+    q = min(3 * homo + 1, N - 1) + 1
+    kind = ("tier-R: real geometry + basis sets, AO integrals on the device, synthetic orthonormal MOs"
+            if workload in TIER_R else "synthetic tier-S")
+    return (f"{workload}: {kind}, N={N} basis, Naux={naux}, homo={homo}, m=q={q}, "
+            f"{mode}(ppm) + full BSE 10 singlets (Davidson)")
+
+
+def l2_policy(N, naux, q):
+    mmn = 8.0 * q * ((N + 15) // 16 * 16) * naux
+    ao = 8.0 * naux * N * N
+    if mmn > 4 * 126e6:
+        return f"inputs larger than L2 (Mmn {mmn / 1e9:.1f} GB, AO tensor {ao / 1e9:.1f} GB, L2 0.126 GB)"
+    return f"small workload (Mmn {mmn / 1e6:.0f} MB): partly L2-resident, not a headline size"
+
+
+# ------------------------------------------------------------------------------------------- reference arm
+def reference_counts(workload, mode, q):
+    """Iteration counts of the workload as counted by a GPU run (votca_b200/data/bench_counts.json); generic
+    estimates for a (workload, mode) that has none on record."""
+    try:
+        with open(COUNTS_FILE) as fh:
+            rec = json.load(fh).get(f"{workload}/{mode}")
+    except OSError:
+        rec = None
+    if rec:
+        return dict(rec), rec.get("source", "bench_counts.json")
+    it = 7 if mode == "evGW" else 1
+    return ({"gw_iterations": it, "sigma_evaluations": 756 * q * it, "davidson_iterations": 8,
+             "bse_analysis_matmuls": 4, "bse_operator_products": 44, "bse_operator_columns": 1047},
+            "generic estimate (no GPU run of this workload / mode on record)")
+
+
+def thread_report():
+    info = {"os_cpu_count": os.cpu_count(), "OMP_NUM_THREADS": os.environ.get("OMP_NUM_THREADS")}
+    try:
+        from threadpoolctl import threadpool_info
+        info["blas"] = [{"api": t.get("internal_api"), "threads": t.get("num_threads")} for t in threadpool_info()]
+    except Exception:
+        pass
+    return info
+
+
+def run_reference(args, rank):
+    """--impl reference: the CPU formulation of the reference on the host cores (oracle port, bounded sample)."""
+    if rank != 0:
+        return
+    from oracle import cpu_baseline
+    N, naux, homo, q = sizes(args.workload)
+    counts, source = reference_counts(args.workload, args.mode, q)
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_baseline.estimate(N, naux, homo, counts, sample_scale=1.0)
+    vals = []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        est = cpu_baseline.estimate(N, naux, homo, counts, sample_scale=24.0)
+        vals.append(est["total_seconds"])
+    wall = time.perf_counter() - t0
+    v = float(np.mean(vals))
+    threads = thread_report()
+    sample = ("per stage a few loop iterations of the reference CPU formulation (aux functions / m slices / "
+              "occupied levels / sigma evaluations / BSE rows), scaled by the iteration counts of the workload; "
+              f"{est['sampled_seconds']:.1f} s of CPU work per step")
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": False,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "extrapolated": True,
+            "value_is": "sampled stage times x iteration counts of the workload (ms_per_step is the sampler's own wall time)",
+            "config": {"workload": workload_name(args.workload, args.mode, N, naux, homo), "mode": args.mode},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample,
+                             "threads": threads, "counts": counts, "counts_source": source,
+                             "stages": {k: round(s["sample_s"] * s["factor"], 3) for k, s in est["stages"].items()},
+                             "factorised": factorised_summary(est)},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def factorised_summary(est):
+    """CPU time of the same workload in the factorised formulation the GPU path uses (fill in the cheaper order, BSE
+    operator without rebuilding H): reference-formulation value / this = algorithmic part of the speed-up."""
+    return {"value": est["factorised_total_seconds"], "unit": UNIT,
+            "stages": {k: round(s["sample_s"] * s["factor"], 3) for k, s in est["factorised_stages"].items()},
+            "note": "replaces fill_3c, bse_hd_rows, bse_hx_blocks of the reference formulation; other stages unchanged"}
+
+
+# ------------------------------------------------------------------------------------------- inputs
 def make_inputs_gpu(torch, N, naux, homo, device, seed, lo=0, hi=None):
     """Synthetic tier-S inputs generated on the device with torch (plumbing, not the product).  Every rank draws
     the same random stream and keeps the aux functions [lo, hi) of the AO tensor (its share of the fill)."""
@@ -140,213 +257,321 @@ def make_inputs_gpu(torch, N, naux, homo, device, seed, lo=0, hi=None):
             "vxc": synthetic.make_vxc(e, homo, rng), "homo": homo, "ao3c_dev": ao}
 
 
-def build_job(inp, N, naux, mode, device_index):
+def make_inputs_tier_r(torch, workload, device, local_rank, seed):
+    """Real geometry and basis sets; MOs = S^-1/2 Q (orthonormal in the real AO metric, Q from a seeded QR), gapped
+    synthetic spectrum, Vxc from the run's own exchange self-energy (set by calibrate_vxc)."""
+    from votca_b200 import realsys, synthetic
+    from votca_b200.api import Context
+    s = realsys.system(workload)
+    N, naux, homo, q = sizes(workload)
+    assert (N, naux) == (s["nbasis"], s["naux"]), (N, naux, s["nbasis"], s["naux"])
+    ctx = Context(local_rank)
+    dft = ctx.basis_create(*s["dft"])
+    S = torch.tensor(ctx.ao_overlap(dft), dtype=torch.float64, device=device)
+    ctx.basis_destroy(dft)
+    ctx.close()
+    w, U = torch.linalg.eigh(S)
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    Q, _ = torch.linalg.qr(torch.randn(N, N, dtype=torch.float64, device=device, generator=g))
+    C = (U * w.rsqrt()) @ (U.T @ Q)
+    rng = np.random.default_rng(seed)
+    e = synthetic.spectrum(N, homo, rng)
+    return {"mos": C.cpu().numpy(), "mo_energies": e, "vxc": synthetic.make_vxc(e, homo, rng), "homo": homo,
+            "basis": s, "min_overlap_eigenvalue": float(w.min().item())}
+
+
+def build_job(inp, mode, device_index, exctotal=10):
     from votca_b200.api import Job
     job = Job(device_index)
     job.set_scalar("homo", inp["homo"])
     for name in ("mos", "mo_energies", "vxc", "aux_overlap", "aux_coulomb"):
-        job.set_array(name, inp[name])
-    job.set_options(tasks="gw,singlets", gw__mode=mode, gw__sigma_integrator="ppm", bse__exctotal=10,
+        if name in inp:
+            job.set_array(name, inp[name])
+    job.set_options(tasks="gw,singlets", gw__mode=mode, gw__sigma_integrator="ppm", bse__exctotal=exctotal,
                     bse__useTDA=False)
     return job
 
 
-def run_reference(args, N, naux, homo, rank):
-    """--impl reference: the CPU formulation of the reference on the host cores (oracle port, bounded sample)."""
-    from oracle import cpu_baseline
-    if rank != 0:
-        return
-    counts = {"gw_iterations": 7 if args.mode == "evGW" else 1, "davidson_iterations": 8, "bse_analysis_matmuls": 4,
-              "bse_operator_products": 4 * 9 + 8,
-              "bse_operator_columns": 1047}  # trial columns through the operator, counted by the GPU run (119 TFLOP)
-    q = min(3 * homo + 1, N - 1) + 1
-    counts["sigma_evaluations"] = 756 * q * counts["gw_iterations"]  # evaluations per level and iteration of the
-    # adaptive QP search on this workload (counted by the GPU run: 325873 per iteration for q = 431)
-    for _ in range(max(0, min(args.warmup, 1))):
-        cpu_baseline.estimate(N, naux, homo, counts, sample_scale=1.0)
-    vals = []
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        est = cpu_baseline.estimate(N, naux, homo, counts, sample_scale=24.0)
-        vals.append(est["total_seconds"])
-    wall = time.perf_counter() - t0
-    v = float(np.mean(vals))
-    cores = os.cpu_count()
-    sample = ("per stage a few loop iterations of the reference CPU formulation (aux functions / m slices / "
-              "occupied levels / sigma evaluations / BSE rows), scaled by the iteration counts of the workload; "
-              f"{est['sampled_seconds']:.1f} s of CPU work per step")
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": False,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args, N, naux, homo), "mode": args.mode},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                             "stages": {k: round(s["sample_s"] * s["factor"], 3) for k, s in est["stages"].items()},
-                             "factorised": factorised_summary(est)},
-            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+def set_basis(job, inp):
+    job.set_basis("dft", *inp["basis"]["dft"])
+    job.set_basis("aux", *inp["basis"]["aux"])
 
 
-def factorised_summary(est):
-    """CPU time of the same workload in the factorised formulation the GPU path uses (fill in the cheaper order, BSE
-    operator without rebuilding H): reference-formulation value / this = algorithmic part of the speed-up."""
-    return {"value": est["factorised_total_seconds"], "unit": UNIT,
-            "stages": {k: round(s["sample_s"] * s["factor"], 3) for k, s in est["factorised_stages"].items()},
-            "note": "replaces fill_3c, bse_hd_rows, bse_hx_blocks of the reference formulation; other stages unchanged"}
+def calibrate_vxc(job, inp, rng_seed=11):
+    """Tier R: Vxc := 0.9 diag(Sigma_x) + small symmetric noise, Sigma_x from one exchange-only pre-run, so that the
+    quasiparticle corrections have the size they have on a real system (as tier S does by construction)."""
+    job.set_option("tasks", "gw")
+    job.set_option("gw.mode", "G0W0")
+    job.run()
+    sx = np.diag(job.get("Sigma_x")).copy()
+    q = sx.size
+    R = 0.005 * np.random.default_rng(rng_seed).standard_normal((q, q))
+    inp["vxc"] = np.diag(0.9 * sx) + 0.5 * (R + R.T)
+    job.set_array("vxc", inp["vxc"])
+    job.set_option("tasks", "gw,singlets")
+    return sx
 
 
-def workload_name(args, N, naux, homo):
-    q = min(3 * homo + 1, N - 1) + 1
-    return (f"{args.workload}: synthetic tier-S, N={N} basis, Naux={naux}, homo={homo}, m=q={q}, "
-            f"{args.mode}(ppm) + full BSE 10 singlets (Davidson)")
+# ------------------------------------------------------------------------------------------- one workload
+class Bench:
+    def __init__(self, args, torch, dist, rank, local_rank, world):
+        self.args, self.torch, self.dist = args, torch, dist
+        self.rank, self.local_rank, self.world = rank, local_rank, world
+        self.device = torch.device("cuda", local_rank)
+        self.uid = None
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def maxf(self, v):
+        t = self.torch.tensor([v], dtype=self.torch.float64, device=self.device)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def connect(self, job):
+        if self.world > 1:
+            uid = [None]
+            if self.rank == 0:
+                uid[0] = job.kernel_ctx().nccl_unique_id()
+            self.dist.broadcast_object_list(uid, src=0)
+            job.comm_init(self.rank, self.world, uid[0])
+
+    def run(self, workload, mode, steps, warmup, e2e_steps, with_e2e, profile_path=None):
+        torch, args = self.torch, self.args
+        N, naux, homo, q = sizes(workload)
+        rank, world = self.rank, self.world
+        tier_r = workload in TIER_R
+        aux_lo, aux_hi = rank * naux // world, (rank + 1) * naux // world
+        if tier_r:
+            inp = make_inputs_tier_r(torch, workload, self.device, self.local_rank, 20261017)
+        else:
+            inp = make_inputs_gpu(torch, N, naux, homo, self.device, 20261017, aux_lo, aux_hi)
+        job = build_job(inp, mode, self.local_rank)
+        self.connect(job)
+        kctx = job.kernel_ctx()
+        peak = kctx.fp64_peak_probe()
+        if tier_r:
+            set_basis(job, inp)
+            calibrate_vxc(job, inp)
+            job.set_option("gw.mode", mode)
+        else:
+            job.set_ao3c_partial(N, naux, aux_lo, aux_hi - aux_lo, inp["ao3c_dev"].data_ptr(), True)
+
+        # ---------------- value: inputs resident in HBM ----------------
+        for _ in range(warmup):
+            job.run()
+        self.barrier()
+        sampler = ClockSampler(self.local_rank)
+        if rank == 0:
+            sampler.start()
+        launches0 = job.launch_count()
+        kctx.bse_stats(reset=True)
+        kctx.gemm_profile(True)
+        kctx.timer_start()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            job.run()
+        dev_ms = kctx.timer_stop_ms()
+        self.barrier()
+        wall = time.perf_counter() - t0
+        gstats = kctx.gemm_stats()
+        kctx.gemm_profile(False)
+        launches = job.launch_count() - launches0
+        clocks = sampler.stop() if rank == 0 else None
+        ms_per_step = self.maxf(max(dev_ms, wall * 1e3)) / steps
+        counts = {"gw_iterations": int(job.scalar("gw_iterations")),
+                  "sigma_evaluations": job.scalar("sigma_evaluations"),
+                  "davidson_iterations": int(job.scalar("singlet_davidson_iterations")),
+                  "bse_analysis_matmuls": 4}
+        bse_flops, bse_products, bse_columns = kctx.bse_stats()
+        counts["bse_operator_products"] = max(1, bse_products // steps)
+        counts["bse_operator_columns"] = bse_columns // steps
+        counts["bse_algorithmic_flops"] = bse_flops / steps
+        stage_times = {k: job.scalar(k) for k in ("time_fill", "time_gw", "time_bse")}
+        qp = job.get("QPpert_energies")
+        results = {"QP_homo": float(qp[homo]), "QP_lumo": float(qp[homo + 1]),
+                   "S1": float(job.get("BSE_singlet_eigenvalues")[0]),
+                   "singlet_converged": job.scalar("singlet_converged")}
+
+        if profile_path:
+            # one extra, untimed step with the library's region profiler (per entry point device/host ms); every rank
+            # runs it (the step contains collectives), rank 0 writes the report
+            kctx.set_option("profile", 1)
+            kctx.gemm_profile(True)
+            job.run()
+            rep = kctx.profile_report() + "\n" + kctx.gemm_shape_report()
+            kctx.gemm_profile(False)
+            kctx.set_option("profile", 0)
+            if rank == 0:
+                sys.stderr.write(rep + "\n" + "\n".join(ln for ln in job.log().splitlines()[-40:]) + "\n")
+                with open(profile_path, "w") as fh:
+                    fh.write(rep)
+            self.barrier()
+
+        # ---------------- e2e: every input from host memory, results back to the host ----------------
+        e2e = None
+        if with_e2e:
+            e2e = self.run_e2e(job, inp, workload, N, naux, homo, q, aux_lo, aux_hi, min(steps, e2e_steps), profile_path)
+        job.close()
+        del inp
+
+        flops = algorithmic_flops(N, naux, homo, counts)
+        total_flops = sum(flops.values())
+        achieved = gstats["flops"] / (gstats["ms"] * 1e-3) / 1e12 if gstats["ms"] > 0 else 0.0
+        rec = {"workload": workload, "mode": mode, "N": N, "naux": naux, "homo": homo, "q": q,
+               "ms_per_step": ms_per_step, "steps": steps, "warmup": warmup, "counts": counts,
+               "stage_seconds": stage_times, "results": results, "launches": int(launches), "clocks": clocks,
+               "flops": flops, "total_flops": total_flops, "gemm": gstats, "gemm_tflops": achieved, "peak": peak,
+               "e2e": e2e}
+        return rec
+
+    def run_e2e(self, job, inp, workload, N, naux, homo, q, aux_lo, aux_hi, steps, profile_path):
+        torch, world = self.torch, self.world
+        tier_r = workload in TIER_R
+        host_ao = None
+        if not tier_r:
+            try:
+                import psutil
+                host_free = psutil.virtual_memory().available
+            except Exception:
+                host_free = 0
+            ao_bytes = 8 * naux * N * N
+            if host_free <= 1.25 * ao_bytes:  # the ranks together stage one copy of the AO tensor
+                if self.rank == 0:
+                    sys.stderr.write("e2e skipped: host memory cannot hold the pinned AO tensor\n")
+                return None
+            pinned = True
+            try:
+                host_ao = torch.empty((aux_hi - aux_lo, N, N), dtype=torch.float64, pin_memory=True)
+            except Exception:
+                pinned = False
+                host_ao = torch.empty((aux_hi - aux_lo, N, N), dtype=torch.float64)
+            host_ao.copy_(inp["ao3c_dev"])
+            torch.cuda.synchronize()
+            job.set_ao3c_partial(N, naux, aux_lo, aux_hi - aux_lo, host_ao.data_ptr(), False)
+            h2d = 8 * (naux * N * N + world * (N * N + 2 * naux * naux))  # AO tensor once, small inputs per rank
+        else:
+            pinned = None
+            nb = sum(a.nbytes for a in inp["basis"]["dft"]) + sum(a.nbytes for a in inp["basis"]["aux"])
+            h2d = world * (8 * (N * N + N + q * q) + nb)  # MOs, energies, Vxc, basis tables per rank
+
+        def one_step():
+            if tier_r:  # the basis tables go host -> device again (pair records are rebuilt from them)
+                set_basis(job, inp)
+            for name in ("mos", "mo_energies", "vxc"):
+                job.set_array(name, inp[name])
+            job.run()
+            return job.get("QPpert_energies"), job.get("BSE_singlet_eigenvalues"), job.get("BSE_singlet_eigenvectors")
+
+        one_step()  # warm the staging buffers
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            one_step()
+        self.barrier()
+        e2e_s = self.maxf((time.perf_counter() - t0) / steps)
+        d2h = 8 * (2 * q * q + 2 * q + 2 * 10 * (homo + 1) * (q - homo - 1))
+        e2e = {"value": e2e_s, "unit": UNIT, "steps": steps, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "host_memory": "pinned" if pinned else ("pageable" if pinned is False else "n/a"),
+               "stage_seconds": {k: job.scalar(k) for k in ("time_fill", "time_gw", "time_bse")}}
+        if profile_path:
+            kctx = job.kernel_ctx()
+            kctx.set_option("profile", 1)
+            one_step()
+            rep = kctx.profile_report()
+            kctx.set_option("profile", 0)
+            if self.rank == 0:
+                with open(profile_path + ".e2e", "w") as fh:
+                    fh.write(rep)
+            self.barrier()
+        del host_ao
+        return e2e
+
+    def sharded_vs_single(self):
+        """The sharded path against a single-GPU recomputation on rank 0 (small synthetic workload, seconds): the
+        largest deviation of the QP and BSE energies goes into the JSON line."""
+        from votca_b200 import synthetic
+        N, naux, homo = synthetic.CONFIGS["small"]
+        s = synthetic.make_small(N, naux, homo)
+        lo, hi = self.rank * naux // self.world, (self.rank + 1) * naux // self.world
+        share = np.ascontiguousarray(s["ao3c"][lo:hi])
+        job = build_job(s, "evGW", self.local_rank, exctotal=5)
+        self.connect(job)
+        job.set_ao3c_partial(N, naux, lo, hi - lo, share.ctypes.data, False)
+        job.run()
+        got = (job.get("QPpert_energies").copy(), job.get("BSE_singlet_eigenvalues").copy())
+        job.close()
+        dev = None
+        if self.rank == 0:
+            single = build_job(s, "evGW", self.local_rank, exctotal=5)
+            single.set_ao3c(s["ao3c"])
+            single.run()
+            dev = {"workload": f"small: synthetic tier-S N={N}, Naux={naux}, evGW(ppm) + full BSE 5 singlets",
+                   "ranks": self.world,
+                   "max_abs_dev_QP_Ha": float(np.abs(got[0] - single.get("QPpert_energies")).max()),
+                   "max_abs_dev_BSE_Ha": float(np.abs(got[1] - single.get("BSE_singlet_eigenvalues")).max())}
+            single.close()
+        self.barrier()
+        return dev
+
+
+def summarize(rec):
+    """Nested record of a secondary workload."""
+    out = {"value": rec["ms_per_step"] / 1e3, "unit": UNIT, "steps": rec["steps"], "warmup": rec["warmup"],
+           "config": {"workload": workload_name(rec["workload"], rec["mode"], rec["N"], rec["naux"], rec["homo"]),
+                      "mode": rec["mode"], "gw_iterations": rec["counts"]["gw_iterations"],
+                      "davidson_iterations": rec["counts"]["davidson_iterations"], "results": rec["results"],
+                      "stage_seconds": rec["stage_seconds"]},
+           "tflops": rec["total_flops"] / (rec["ms_per_step"] * 1e-3) / 1e12,
+           "gemm_tflops": rec["gemm_tflops"], "gemm_frac_of_peak": rec["gemm_tflops"] / rec["peak"] if rec["peak"] else None,
+           "e2e": rec["e2e"]}
+    return out
 
 
 def main():
     args = parse_args()
-    from votca_b200 import synthetic
-    N, naux, homo = synthetic.CONFIGS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        run_reference(args, N, naux, homo, rank)
+        run_reference(args, rank)
         return
 
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
-    device = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=device)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # the fill is sharded over aux functions: a rank holds (and uploads) only its share of the AO tensor
-    aux_lo, aux_hi = rank * naux // world, (rank + 1) * naux // world
-    inp = make_inputs_gpu(torch, N, naux, homo, device, 20261017, aux_lo, aux_hi)
-    job = build_job(inp, N, naux, args.mode, local_rank)
-    if world > 1:
-        from votca_b200.api import Context
-        uid = [None]
-        if rank == 0:
-            uid[0] = job.kernel_ctx().nccl_unique_id()
-        dist.broadcast_object_list(uid, src=0)
-        job.comm_init(rank, world, uid[0])
-    kctx = job.kernel_ctx()
-    peak = kctx.fp64_peak_probe()
-
-    # ---------------- value: inputs resident in HBM ----------------
-    job.set_ao3c_partial(N, naux, aux_lo, aux_hi - aux_lo, inp["ao3c_dev"].data_ptr(), True)
-    for _ in range(args.warmup):
-        job.run()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    launches0 = job.launch_count()
-    kctx.bse_stats(reset=True)
-    kctx.gemm_profile(True)
-    kctx.timer_start()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        job.run()
-    dev_ms = kctx.timer_stop_ms()
-    barrier()
-    wall = time.perf_counter() - t0
-    gstats = kctx.gemm_stats()
-    kctx.gemm_profile(False)
-    launches = job.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
-    tms = torch.tensor([max(dev_ms, wall * 1e3)], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms_per_step = float(tms.item()) / args.steps
-    counts = {"gw_iterations": int(job.scalar("gw_iterations")),
-              "sigma_evaluations": job.scalar("sigma_evaluations"),
-              "davidson_iterations": int(job.scalar("singlet_davidson_iterations")),
-              "bse_analysis_matmuls": 4}
-    bse_flops, bse_products, bse_columns = kctx.bse_stats()
-    # operator products (A or B block applied to a block of trial vectors) per step: the reference rebuilds
-    # every row of H for each of them whatever the block width
-    counts["bse_operator_products"] = max(1, bse_products // args.steps)
-    counts["bse_operator_columns"] = bse_columns // args.steps
-    counts["bse_algorithmic_flops"] = bse_flops / args.steps
-    stage_times = {k: job.scalar(k) for k in ("time_fill", "time_gw", "time_bse")}
-    results = {"QP_homo": float(job.get("QPpert_energies")[homo]), "QP_lumo": float(job.get("QPpert_energies")[homo + 1]),
-               "S1": float(job.get("BSE_singlet_eigenvalues")[0]), "singlet_converged": job.scalar("singlet_converged")}
-
-    if os.environ.get("GWBSE_PROFILE"):
-        # one extra, untimed step with the library's region profiler (per entry point device/host ms); every rank
-        # runs it (the step contains collectives), rank 0 writes the report
-        kctx.set_option("profile", 1)
-        kctx.gemm_profile(True)
-        job.run()
-        rep = kctx.profile_report() + "\n" + kctx.gemm_shape_report()
-        kctx.gemm_profile(False)
-        kctx.set_option("profile", 0)
-        if rank == 0:
-            sys.stderr.write(rep + "\n" + "\n".join(l for l in job.log().splitlines()[-40:]) + "\n")
-            with open(os.environ["GWBSE_PROFILE"], "w") as fh:
-                fh.write(rep)
-        barrier()
-
-    # ---------------- e2e: AO integrals from pinned host memory, results back to the host ----------------
-    e2e = None
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    b = Bench(args, torch, dist, rank, local_rank, world)
     try:
-        import psutil
-        host_free = psutil.virtual_memory().available
-    except Exception:
-        host_free = 0
-    ao_bytes = 8 * naux * N * N
-    e2e_fits = host_free > 1.25 * ao_bytes  # the ranks together stage one copy of the AO tensor
-    if not args.no_e2e and not e2e_fits and rank == 0:
-        sys.stderr.write("e2e skipped: host memory cannot hold one pinned AO tensor per rank\n")
-    if not args.no_e2e and e2e_fits:
-        pinned = True
-        try:
-            host_ao = torch.empty((aux_hi - aux_lo, N, N), dtype=torch.float64, pin_memory=True)
-        except Exception:
-            pinned = False
-            host_ao = torch.empty((aux_hi - aux_lo, N, N), dtype=torch.float64)
-        host_ao.copy_(inp["ao3c_dev"])
-        torch.cuda.synchronize()
-        job.set_ao3c_partial(N, naux, aux_lo, aux_hi - aux_lo, host_ao.data_ptr(), False)
-        job.run()  # warm the staging buffers
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            job.run()
-        barrier()
-        e2e_s = (time.perf_counter() - t0) / args.steps
-        te = torch.tensor([e2e_s], dtype=torch.float64, device=device)
+        parity = None
+        if world > 1 and not args.no_parity:
+            parity = b.sharded_vs_single()
+        rec = b.run(args.workload, args.mode, args.steps, args.warmup, args.e2e_steps, not args.no_e2e,
+                    os.environ.get("GWBSE_PROFILE"))
+        also = None
+        if args.also:
+            torch.cuda.empty_cache()
+            amode = DEFAULT_MODE.get(args.also, "evGW")
+            prof = os.environ.get("GWBSE_PROFILE")
+            also = b.run(args.also, amode, 2, 1, 1, not args.no_e2e, prof + ".also" if prof else None)
+        if rank == 0:
+            print(json.dumps(make_line(args, rec, also, parity, world)))
+    finally:
         if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        q = min(3 * homo + 1, N - 1) + 1
-        h2d = 8 * (naux * N * N + world * (N * N + 2 * naux * naux))  # whole job: AO tensor once, small inputs per rank
-        d2h = 8 * (2 * q * q + 2 * q + 2 * 10 * (homo + 1) * (q - homo - 1))
-        e2e = {"value": float(te.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "host_memory": "pinned" if pinned else "pageable",
-               "stage_seconds": {k: job.scalar(k) for k in ("time_fill", "time_gw", "time_bse")}}
-        if os.environ.get("GWBSE_PROFILE"):
-            kctx.set_option("profile", 1)
-            job.run()
-            rep = kctx.profile_report()
-            kctx.set_option("profile", 0)
-            if rank == 0:
-                with open(os.environ["GWBSE_PROFILE"] + ".e2e", "w") as fh:
-                    fh.write(rep)
-            barrier()
-        del host_ao
+            dist.destroy_process_group()
 
-    if rank != 0:
-        return
-    flops = algorithmic_flops(N, naux, homo, counts)
-    total_flops = sum(flops.values())
-    achieved = gstats["flops"] / (gstats["ms"] * 1e-3) / 1e12 if gstats["ms"] > 0 else 0.0
-    traffic = None
-    traffic_note = None
+
+def make_line(args, rec, also, parity, world):
+    N, naux, homo, q = rec["N"], rec["naux"], rec["homo"], rec["q"]
+    counts, flops, gstats = rec["counts"], rec["flops"], rec["gemm"]
+    ms_per_step, peak, achieved = rec["ms_per_step"], rec["peak"], rec["gemm_tflops"]
+    tier_r = rec["workload"] in TIER_R
+    traffic = traffic_note = None
     prof = os.path.join(ROOT, "profiles", "ncu_summary.json")
     if os.path.exists(prof):
         try:
@@ -357,41 +582,51 @@ def main():
                             f"{ncu.get('algorithmic_bytes_per_launch')}")
         except Exception:
             traffic = None
+    ao_note = ("produced on the device from the basis sets (gwbse_ao3c_block_dev inside the fill; the AO tensor never "
+               "exists)" if tier_r else
+               "supplied as a synthetic tensor (the reference's libint stage, row a2, is an input of this workload)")
     line = {
-        "metric": METRIC, "value": ms_per_step / 1e3, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "strong",
+        "metric": METRIC, "value": ms_per_step / 1e3, "unit": UNIT, "n_gpus": world, "steps": rec["steps"],
+        "warmup": rec["warmup"], "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args, N, naux, homo), "mode": args.mode,
-                   "l2_policy": "inputs larger than L2 (Mmn 13.9 GB, AO tensor 39.6 GB)" if N > 1000 else
-                   "small workload, L2-resident", "gw_iterations": counts["gw_iterations"],
-                   "davidson_iterations": counts["davidson_iterations"], "results": results,
-                   "stage_seconds": stage_times,
-                   "ao_integrals": "supplied as a synthetic tensor (the reference's libint stage, row a2, is an input; "
-                                   "the device producer gwbse_mmn_fill_from_basis is not on this path)"},
-        "tflops": {"value": total_flops / (ms_per_step * 1e-3) / 1e12, "algorithmic_tflop_per_step": total_flops / 1e12,
+        "config": {"workload": workload_name(rec["workload"], rec["mode"], N, naux, homo), "mode": rec["mode"],
+                   "l2_policy": l2_policy(N, naux, q), "gw_iterations": counts["gw_iterations"],
+                   "davidson_iterations": counts["davidson_iterations"], "results": rec["results"],
+                   "stage_seconds": rec["stage_seconds"], "ao_integrals": ao_note},
+        "tflops": {"value": rec["total_flops"] / (ms_per_step * 1e-3) / 1e12,
+                   "algorithmic_tflop_per_step": rec["total_flops"] / 1e12,
                    "stages_tflop": {k: round(v / 1e12, 3) for k, v in flops.items()}},
-        "roofline": {"bound": "tensor", "kernel": "gemm_dmma_kernel (FP64 DMMA.8x8x4)", "achieved": achieved,
-                     "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": traffic,
-                     "traffic_note": traffic_note,
+        "roofline": {"bound": "tensor", "kernel": "gemm_tma_kernel / gemm_dmma_kernel (FP64 DMMA.8x8x4)",
+                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                     "traffic": traffic, "traffic_note": traffic_note,
                      "peak_source": "live DMMA issue-rate probe in this run (MEASURED_PEAKS.json has no FP64 entry; "
                                     "cuBLAS Dgemm 8192^3 measured 36.0 TF/s, profiles/r01_fp64_peak_probe.txt)",
-                     "launches": gstats["launches"], "kernel_ms_per_step": gstats["ms"] / args.steps,
-                     "kernel_share_of_step": gstats["ms"] / args.steps / ms_per_step},
-        "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e,
+                     "launches": gstats["launches"], "kernel_ms_per_step": gstats["ms"] / rec["steps"],
+                     "kernel_share_of_step": gstats["ms"] / rec["steps"] / ms_per_step},
+        "gpu_launches": rec["launches"], "clocks": rec["clocks"], "e2e": rec["e2e"],
     }
+    if parity is not None:
+        line["sharded_vs_single"] = parity
+    if also is not None:
+        line["also"] = summarize(also)
+    # iteration counts for the CPU arm (copied into votca_b200/data/bench_counts.json by the maintainer)
+    try:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", f"bench_counts_{rec['workload']}_{rec['mode']}_{world}gpu.json"), "w") as fh:
+            json.dump({f"{rec['workload']}/{rec['mode']}": {k: v for k, v in counts.items() if k != "bse_algorithmic_flops"}}, fh)
+    except OSError:
+        pass
     if not args.no_cpu and world == 1:  # reported at N=1 only
         from oracle import cpu_baseline
         est = cpu_baseline.estimate(N, naux, homo, counts, sample_scale=24.0)
         line["cpu_baseline"] = {
-            "value": est["total_seconds"], "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            "value": est["total_seconds"], "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "extrapolated": True,
             "sample": ("reference CPU formulation (NumPy/OpenBLAS port, all host threads) timed per stage on a few "
                        f"loop iterations and scaled by the run's iteration counts; {est['sampled_seconds']:.1f} s "
                        "of CPU work"),
             "stages": {k: round(s["sample_s"] * s["factor"], 3) for k, s in est["stages"].items()},
             "factorised": factorised_summary(est)}
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    return line
 
 
 if __name__ == "__main__":

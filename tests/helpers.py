@@ -102,3 +102,34 @@ def methane_svp_case():
     q = min(3 * homo + 1, dft.size - 1) + 1
     return {"dft": dft, "aux": aux, "hf": hf, "homo": homo, "q": q, "S": integrals.overlap(aux),
             "V": integrals.coulomb2c(aux), "ao3c": integrals.coulomb3c(aux, dft), "dipole": integrals.dipole(dft)}
+
+
+def oracle_basis(name, elements, positions):
+    """oracle AOBasis of a basis set shipped in votca_b200/data/basis_sets.json (extracted from the reference's
+    basis-set library by votca_b200/data/make_basis_data.py)."""
+    from votca_b200 import realsys
+    bs = {el: [(int(l), [tuple(p) for p in prims]) for l, prims in shells]
+          for el, shells in realsys.basis_set(name).items()}
+    return obasis.AOBasis(bs, elements, positions)
+
+
+@lru_cache(maxsize=None)
+def benzene_tzvp_case():
+    """BASELINE.json config 2: benzene, def2-tzvp + aux-def2-tzvp (N = 222, Naux = 546, homo = 20, q = 62, RPA size
+    4221).  Inputs (RI-RHF orbitals) and the oracle's evGW(exact) + full-BSE results come from
+    tests/golden/benzene_tzvp_evgw_exact.npz (tests/golden/make_benzene_tzvp.py); the AO integrals are recomputed
+    with the compiled host harness of the integral code and checked against the sample stored in the fixture."""
+    from tests import test_ao3c_core_cpu as hh
+    from votca_b200 import realsys
+    path = os.path.join(os.path.dirname(GOLDEN), "benzene_tzvp_evgw_exact.npz")
+    with np.load(path) as z:
+        c = {k: z[k] for k in z.files}
+    el, pos = realsys.benzene()
+    dft, aux = oracle_basis("def2-tzvp", el, pos), oracle_basis("aux-def2-tzvp", el, pos)
+    lib = hh._bind(hh._build("libao3c_host.so", ["-O2"]))
+    c["ao3c"] = hh.ao3c(lib, aux, dft)
+    assert np.abs(c["ao3c"][::97, ::13, ::7] - c["ao3c_sample"]).max() < 1e-12
+    c["S"], c["V"], c["dipole"] = hh.overlap(lib, aux), hh.coulomb2c(lib, aux), hh.dipole(lib, dft)
+    c["dft"], c["aux"], c["elements"], c["positions"] = dft, aux, el, pos
+    c["homo"], c["q"] = int(c["homo"]), int(c["q"])
+    return c

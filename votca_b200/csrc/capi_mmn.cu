@@ -497,8 +497,9 @@ int gwbse_rpa_epsilon(gwbse_ctx* ctx, int kind, double fre, double fim, double e
   double* e_dev = ctx->buf("rpa_e", rpatotal);
   GW_CUDA(cudaMemcpyAsync(e_dev, energies, sizeof(double) * rpatotal, cudaMemcpyHostToDevice, ctx->stream));
   const int nloc_occ = ctx->local_count(n_occ);
-  double* w = ctx->buf("rpa_w", (size_t)std::max(nloc_occ, 1) * n_unocc);
-  launch_rpa_weights(w, e_dev, kind, fre, fim, eta, n_occ, n_unocc, ctx->rank, ctx->world, nloc_occ, ctx->stream);
+  const long long ldw = (n_unocc + 1) & ~1;
+  double* w = ctx->buf("rpa_w", (size_t)std::max(nloc_occ, 1) * ldw);
+  launch_rpa_weights(w, ldw, e_dev, kind, fre, fim, eta, n_occ, n_unocc, ctx->rank, ctx->world, nloc_occ, ctx->stream);
   ctx->launches++;
   if (nloc_occ > 0) {
     GemmParams p;
@@ -516,7 +517,7 @@ int gwbse_rpa_epsilon(gwbse_ctx* ctx, int kind, double fre, double fim, double e
     p.sC_ni = naux;
     p.alpha = (kind == 2) ? -2.0 : 1.0;
     p.w = w;
-    p.sW_ko = n_unocc;
+    p.sW_ko = ldw;
     p.lower_only = 1;
     ctx->gemm(p);
     launch_symmetrize_lower(ctx->eps, naux, naux, ctx->stream);

@@ -236,8 +236,9 @@ void alltoallv_dev(gwbse_ctx* ctx, const double* const* send, const size_t* send
 // streaming kernels (streaming.cu)
 void launch_symmetrize_lower(double* A, int n, long long ld, cudaStream_t s);
 void launch_add_diagonal(double* A, int n, long long ld, double v, cudaStream_t s);
-void launch_rpa_weights(double* w, const double* e, int kind, double fre, double fim, double eta, int n_occ,
-                        int n_unocc, int rank, int world, int nloc_occ, cudaStream_t s);
+// w[ml * ldw + c]: rows padded to an even pitch so that the weight tile of a k-step is a 16-byte aligned TMA box
+void launch_rpa_weights(double* w, long long ldw, const double* e, int kind, double fre, double fim, double eta,
+                        int n_occ, int n_unocc, int rank, int world, int nloc_occ, cudaStream_t s);
 void launch_diag_scale(char side, int m, int n, const double* A, long long lda, const double* d, double* C,
                        long long ldc, cudaStream_t s);
 void launch_axpy(int m, int n, double alpha, const double* X, long long ldx, double* Y, long long ldy,

@@ -145,10 +145,15 @@ GemmParams apply_swap(GemmParams p) {
 }  // namespace
 
 // force_cfg: -1 auto (TMA kernel when the operands allow it), 0..5 cp.async tile shapes, 10..13 TMA tile shapes
-static bool wants_tma(const GemmParams& p, int num_sms, int force_cfg, int force_splitk) {
+static bool wants_tma(const GemmParams& p, int num_sms, int& force_cfg, int force_splitk) {
+  if (force_cfg >= 15 || (force_cfg >= 6 && force_cfg < 10)) force_cfg = -1;  // not a tile shape of either kernel
   if (force_cfg >= 0 && force_cfg < 10) return false;
-  int c, sw, sk;
-  return gemm_tma_describe(p, num_sms, force_cfg >= 10 ? force_cfg - 10 : -1, force_splitk, &c, &sw, &sk);
+  int c0, sw0, sk0;
+  if (!gemm_tma_describe(p, num_sms, force_cfg >= 10 ? force_cfg - 10 : -1, force_splitk, &c0, &sw0, &sk0)) {
+    force_cfg = -1;  // a TMA tile shape was asked for but the operands need the cp.async kernel
+    return false;
+  }
+  return true;
 }
 
 size_t gemm_ws_bytes_needed(const GemmParams& p, int num_sms, int force_cfg, int force_splitk) {

@@ -73,12 +73,11 @@ bool make_operand_map(const GemmOperand& op, int rows, int Ko, int Ki, int Z1, i
   RowShape rs;
   if (!operand_shape(op, rows, &rs)) return false;
   const bool kmajor = rs.kmajor;
-  // a view that starts 8 bytes into a 16-byte aligned allocation: move the base down one element and start the
-  // contiguous coordinate at 1
-  const uintptr_t addr = reinterpret_cast<uintptr_t>(op.ptr);
-  if (addr % 8 != 0) return false;
-  const int shift = (addr % 16 != 0) ? 1 : 0;
-  const double* base = op.ptr - shift;
+  // TMA wants the start of every box 16-byte aligned: an 8-byte offset view cannot be expressed by a shifted
+  // coordinate either (the innermost coordinate must itself be a multiple of 16 bytes) - cp.async kernel then
+  if (reinterpret_cast<uintptr_t>(op.ptr) % 16 != 0) return false;
+  const int shift = 0;
+  const double* base = op.ptr;
   const long long rows_in = rs.compound ? rs.Lr : rows;  // extent of the inner row index
   const long long s_row = kmajor ? op.s_ri : 1, s_k = kmajor ? 1 : op.s_ki;
   // (ro, ko, z1): broadcast / absent dimensions collapse to extent 1
@@ -145,7 +144,7 @@ bool make_weight_map(const GemmParams& p, CUtensorMap* map, int* use_ko, int* us
 // cheap host-side test (no encoding) of what make_operand_map will accept
 bool operand_ok(const GemmOperand& op, int rows, int Ko, int Z1, RowShape* rs) {
   if (!operand_shape(op, rows, rs)) return false;
-  if (reinterpret_cast<uintptr_t>(op.ptr) % 8 != 0) return false;
+  if (reinterpret_cast<uintptr_t>(op.ptr) % 16 != 0) return false;
   const long long rows_in = rs->compound ? rs->Lr : rows;
   if (rs->kmajor) {
     if (rows_in > 1 && (!even(op.s_ri) || op.s_ri <= 0)) return false;

@@ -29,8 +29,9 @@ constexpr int TMA_BK = 16;  // one 128-byte swizzle row of doubles
 //   M-major: (ri, k, ro, ko, z1)      box (16, 16, 1, 1, 1)     ROWS/16 loads per tile
 // The row index may be compound, row = ro * Lr + ri (the (slice, chi) index of the BSE intermediate): tiles then
 // never straddle an ro boundary (tiles_per_ro tiles per ro, the last one zero-filled by TMA beyond Lr).
-// row0/k0 are offsets for views that start one element into a 16-byte aligned base; dimensions that do not exist
-// (or are broadcast) have extent 1 and their coordinate multiplier is 0.
+// row0/k0 are coordinate offsets of the view inside the tensor map (multiples of two elements: TMA wants every box
+// start 16-byte aligned); dimensions that do not exist (or are broadcast) have extent 1 and their coordinate
+// multiplier is 0.
 struct TmaOperand {
   int row0 = 0, k0 = 0;
   int use_ko = 0, use_z1 = 0;
@@ -83,7 +84,9 @@ __device__ __forceinline__ void tma_load_5d(void* smem, const CUtensorMap* map, 
       : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+#ifndef GWBSE_TMA_NO_PREFETCH
   asm volatile("prefetch.tensormap [%0];\n" ::"l"(map) : "memory");
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------- tile schedule
@@ -135,11 +138,15 @@ struct TmaSmem {
 // registers, more than an even split of the register file over all threads leaves.
 template <int REGS>
 __device__ __forceinline__ void setmaxnreg_inc() {
+#ifndef GWBSE_TMA_NO_SETMAXNREG
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(REGS));
+#endif
 }
 template <int REGS>
 __device__ __forceinline__ void setmaxnreg_dec() {
+#ifndef GWBSE_TMA_NO_SETMAXNREG
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(REGS));
+#endif
 }
 
 template <int BM, int BN, int WGM, int WGN, int STAGES, int MINB, bool AK, bool BKM, bool HASW>
@@ -283,6 +290,13 @@ __global__ void __launch_bounds__((WGM * WGN + 4) * 32, MINB) gemm_tma_kernel(co
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
         double a[MI], b[NI];
+#if defined(GWBSE_TMA_PROBE_NO_LDS)
+#pragma unroll
+        for (int i = 0; i < MI; ++i) a[i] = 1.0 + i + kk + 1e-9 * lane;
+#pragma unroll
+        for (int j = 0; j < NI; ++j) b[j] = 0.5 + j - kk + 1e-9 * lane;
+        if (false)
+#endif
 #pragma unroll
         for (int i = 0; i < MI; ++i) {
           // K-major: rows advance by 8 -> +1024 B.  M-major: row%16 = (i&1)*8 + g flips chunk bit 2 (byte 64),
@@ -295,15 +309,33 @@ __global__ void __launch_bounds__((WGM * WGN + 4) * 32, MINB) gemm_tma_kernel(co
 #pragma unroll
           for (int i = 0; i < MI; ++i) a[i] *= wv;
         }
+#if defined(GWBSE_TMA_PROBE_NO_LDS)
+        if (false)
+#endif
 #pragma unroll
         for (int j = 0; j < NI; ++j) {
           const int o = BKM ? offB[kk] + j * 1024 : ((offB[kk] ^ ((j & 1) << 6)) + (j >> 1) * 2048);
           b[j] = *reinterpret_cast<const double*>(sB + o);
         }
+#if defined(GWBSE_TMA_ORDER_JI)
+#pragma unroll
+        for (int j = 0; j < NI; ++j)
+#pragma unroll
+          for (int i = 0; i < MI; ++i) dmma884(acc[i][j], a[i], b[j]);
+#elif defined(GWBSE_TMA_ORDER_SNAKE)
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+          for (int jj = 0; jj < NI; ++jj) {
+            const int j = (i & 1) ? NI - 1 - jj : jj;
+            dmma884(acc[i][j], a[i], b[j]);
+          }
+#else
 #pragma unroll
         for (int i = 0; i < MI; ++i)
 #pragma unroll
           for (int j = 0; j < NI; ++j) dmma884(acc[i][j], a[i], b[j]);
+#endif
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(empty_bar + stage);

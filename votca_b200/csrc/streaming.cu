@@ -50,8 +50,8 @@ __global__ void add_diagonal_kernel(double* A, int n, long long ld, double v) {
 }
 
 // RPA transition weights, rpa.cc:115-127 (imag / real) and rpa.cc:178-190 (complex)
-__global__ void rpa_weights_kernel(double* w, const double* e, int kind, double fre, double fim, double eta,
-                                   int n_occ, int n_unocc, int rank, int world) {
+__global__ void rpa_weights_kernel(double* w, long long ldw, const double* e, int kind, double fre, double fim,
+                                   double eta, int n_occ, int n_unocc, int rank, int world) {
   const int ml = blockIdx.y;
   const int v = rank + ml * world;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -69,7 +69,7 @@ __global__ void rpa_weights_kernel(double* w, const double* e, int kind, double 
     const double s1 = (fim + eta) * (fim + eta), s2 = (fim - eta) * (fim - eta);
     d = dm / (dm * dm + s1) - dp / (dp * dp + s2);
   }
-  w[(long long)ml * n_unocc + c] = d;
+  w[(long long)ml * ldw + c] = d;
 }
 
 __global__ void diag_scale_kernel(int side_right, int m, int n, const double* A, long long lda, const double* d,
@@ -350,11 +350,11 @@ void launch_add_diagonal(double* A, int n, long long ld, double v, cudaStream_t 
   add_diagonal_kernel<<<(n + 255) / 256, 256, 0, s>>>(A, n, ld, v);
   GW_CUDA(cudaGetLastError());
 }
-void launch_rpa_weights(double* w, const double* e, int kind, double fre, double fim, double eta, int n_occ,
-                        int n_unocc, int rank, int world, int nloc_occ, cudaStream_t s) {
+void launch_rpa_weights(double* w, long long ldw, const double* e, int kind, double fre, double fim, double eta,
+                        int n_occ, int n_unocc, int rank, int world, int nloc_occ, cudaStream_t s) {
   if (nloc_occ <= 0) return;
-  rpa_weights_kernel<<<dim3((n_unocc + 255) / 256, nloc_occ), 256, 0, s>>>(w, e, kind, fre, fim, eta, n_occ, n_unocc,
-                                                                            rank, world);
+  rpa_weights_kernel<<<dim3((n_unocc + 255) / 256, nloc_occ), 256, 0, s>>>(w, ldw, e, kind, fre, fim, eta, n_occ,
+                                                                            n_unocc, rank, world);
   GW_CUDA(cudaGetLastError());
 }
 void launch_diag_scale(char side, int m, int n, const double* A, long long lda, const double* d, double* C,

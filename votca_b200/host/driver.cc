@@ -62,6 +62,9 @@ struct gwbse_job {
   ArraySource ints;
   // AO integrals produced on the device from the basis sets (gwbse_job_set_basis) instead of "ao3c"
   std::unique_ptr<AOBasisData> basis_data[2];  // 0 = dft, 1 = aux
+  // device copies of the basis tables (shell data + primitive-pair records), kept across runs until the basis is
+  // set again: they are inputs resident in HBM, not results
+  std::unique_ptr<DeviceAOBasis> dev_basis[2];
   std::string orb_path;  // gwbse_job_set_orb_output: results are written there at the end of gwbse_job_run
   std::string err;
   mutable std::string logcache;
@@ -204,6 +207,7 @@ int gwbse_job_set_basis(gwbse_job* job, const char* which, int nshell, const int
   d->exps.assign(exps, exps + np);
   d->coefs.assign(coefs, coefs + np);
   job->basis_data[w == "aux" ? 1 : 0] = std::move(d);
+  job->dev_basis[w == "aux" ? 1 : 0].reset();
   JOB_END(job)
 }
 
@@ -232,12 +236,14 @@ int gwbse_job_run(gwbse_job* job) {
   in.mo_energies = &mo_e;
   if (job->in.count("vxc")) in.vxc = &job->in["vxc"];
   // integral producer: the device (both basis sets given, no ao3c array / callback), else the supplied arrays
-  std::unique_ptr<DeviceAOBasis> dft_basis, aux_basis;
+  DeviceAOBasis *dft_basis = nullptr, *aux_basis = nullptr;
   std::unique_ptr<DeviceAOIntegrals> device_ints;
   const bool have_arrays = job->ints.ao3c || job->ints.ao3c_dev || job->ints.fn;
   if (!have_arrays && job->basis_data[0] && job->basis_data[1]) {
-    dft_basis = std::make_unique<DeviceAOBasis>(*job->dev, *job->basis_data[0]);
-    aux_basis = std::make_unique<DeviceAOBasis>(*job->dev, *job->basis_data[1]);
+    for (int b = 0; b < 2; ++b)
+      if (!job->dev_basis[b]) job->dev_basis[b] = std::make_unique<DeviceAOBasis>(*job->dev, *job->basis_data[b]);
+    dft_basis = job->dev_basis[0].get();
+    aux_basis = job->dev_basis[1].get();
     const MatrixXd* S = job->in.count("aux_overlap") ? &job->in["aux_overlap"] : nullptr;
     if (S && aux_basis->AOBasisSize() != S->rows()) throw std::runtime_error("aux overlap does not match the aux basis");
     if (dft_basis->AOBasisSize() != mos.rows()) throw std::runtime_error("MO coefficients do not match the dft basis");

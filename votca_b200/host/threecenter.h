@@ -43,7 +43,6 @@ class TCMatrix_gwbse {
     mtotal_ = mmax - mmin + 1;
     auxbasissize_ = basissize;
     dev_.check(gwbse_mmn_alloc(dev_.ctx(), (int)basissize, (int)mmin, (int)mmax, (int)nmin, (int)nmax));
-    mirror_.clear();
   }
 
   Index auxsize() const { return auxbasissize_; }
@@ -109,7 +108,6 @@ class TCMatrix_gwbse {
     if (U.rows() != qptotal || U.cols() != qptotal)
       throw std::runtime_error("TCMatrix_gwbse::Rotate: rotation matrix does not match the QP window");
     dev_.check(gwbse_mmn_rotate(dev_.ctx(), U.data(), (int)U.rows(), (int)qpmin, (int)qpmax));
-    mirror_.clear();
   }
 
   // threecenter.cc:54-65
@@ -172,7 +170,6 @@ class TCMatrix_gwbse {
   const MatrixXd* dft_orbitals_ = nullptr;
   Index aux_block_ = 64;
   bool keep_snapshot_ = true, have_snapshot_ = false;
-  mutable std::vector<MatrixXd> mirror_;
 };
 
 }  // namespace xtp
