@@ -229,6 +229,11 @@ int gwbse_mmn_restore(gwbse_ctx* ctx);
 int gwbse_rpa_epsilon(gwbse_ctx* ctx, int kind, double freq_re, double freq_im, double eta,
                       const double* energies, int homo, int rpamin, int rpamax, double* eps_out, int ld);
 double* gwbse_rpa_epsilon_ptr(gwbse_ctx* ctx);
+/* RPA::setQSGWRotation (rpa.h:59-66) and Sigma_base::setQSGWRotation (sigma_base.h:51-58): while a rotation U
+ * (qptotal x qptotal, DFT-MOs -> QP wavefunctions) is registered, every RPA sum over hole slices - epsilon
+ * (rpa.cc:95-118, 162-181), A+B (rpa.cc:288-310), the exact-sigma residues (sigma_exact.cc:119-145) - uses
+ * sum_vp U(vp, v) Mmn[vp + qpmin - rpamin] for the occupied slices v inside the QP window.  U = NULL clears it. */
+int gwbse_rpa_set_qsgw_rotation(gwbse_ctx* ctx, const double* U, int ldu, int qptotal, int qpmin, int homo);
 /* RPA::Calculate_H2p_ApB (rpa.cc:281-326): (A+B) two-particle matrix, S x S, lower triangle */
 int gwbse_rpa_h2p_apb(gwbse_ctx* ctx, const double* energies, int homo, int rpamin, int rpamax,
                       double* apb_out_dev, int ld);
@@ -263,6 +268,25 @@ int gwbse_sigma_exact_prepare(gwbse_ctx* ctx, const double* rpa_omegas, const do
 int gwbse_sigma_exact_eval(gwbse_ctx* ctx, int nreq, const int* levels, const double* freqs, double* sigma,
                            double* dsigma);
 int gwbse_sigma_exact_offdiag(gwbse_ctx* ctx, int q, const double* freqs, double* out, int ld);
+
+/* ---- Sigma_CDA: contour deformation (device resident) ---------------------
+ * Sigma_CDA::PrepareScreening (self_energy_evaluators/sigma_cda.cc:30-45) +
+ * ImaginaryAxisIntegration::CalcDielInvVector (ImaginaryAxisIntegration.cc:90-102):
+ * kappa_0 = eps(0)^-1 - 1, kappa_j = -(eps(i w_j)^-1 - 1) + kappa_0 exp(-(alpha w_j)^2)
+ * for the `order` mapped quadrature nodes (points / weights, host), and the row
+ * forms Q_j[level][n] = (I kappa_j)[n,:] . I[n,:], I = Mmn[level], for every local
+ * level of the qp window (one DMMA GEMM per node over the whole Mmn).  eta is
+ * RPA::getEta() (rpa.h:90).  `energies`: RPA input energies (rpamax-rpamin+1).  */
+int gwbse_sigma_cda_prepare(gwbse_ctx* ctx, int order, const double* points, const double* weights, int symmetry,
+                            double alpha, const double* energies, int homo, int rpamin, int rpamax, int qpmin,
+                            int qpmax, double eta);
+/* Sigma_CDA::CalcCorrelationDiagElement (sigma_cda.cc:118-124) for nreq (level,
+ * frequency) requests: SigmaGQDiag (ImaginaryAxisIntegration.cc:145-176) and the
+ * Gaussian tail from the Q tables, CalcResidueContribution (sigma_cda.cc:81-116)
+ * with one eps(|e_n - w| + i eta) assembly + LU solve per pole inside the contour.
+ * levels are relative to qpmin and must be owned by this rank.                    */
+int gwbse_sigma_cda_eval(gwbse_ctx* ctx, int nreq, const int* levels, const double* freqs, const double* energies,
+                         double* sigma);
 
 /* ---- BSE operator (bse_operator.h:32-87) --------------------------------- */
 /* BSE_OPERATOR::configure + ctor data (bse_operator.cc:29-38): eps_inv (naux), Hqp ((vt+ct)^2, ld) */

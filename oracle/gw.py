@@ -1,7 +1,6 @@
 """Oracle for GW (test infrastructure).  Follows xtp/src/libxtp/gwbse/gw.cc:35-78,
 210-776, xtp/include/votca/xtp/gw.h:214-300 (QPFunc) and
-xtp/src/libxtp/anderson_mixing.cc:28-95.  QSGW (gw.cc:778-1184) is outside the
-BASELINE.json configs and is not restated.
+xtp/src/libxtp/anderson_mixing.cc:28-95; QSGW: gw.cc:798-1130 (calculate_qsgw).
 """
 import math
 from dataclasses import dataclass
@@ -29,6 +28,9 @@ class GWOptions:
     ScaHFX: float = 0.0
     sigma_integration: str = "ppm"
     reset_3c: int = 5
+    qsgw_max_iterations: int = 20
+    qsgw_sc_limit: float = 1e-5
+    qsgw_max_virt_correction: float = 0.5
     qp_solver: str = "grid"
     qp_solver_alpha: float = 0.75
     qp_grid_steps: int = 0
@@ -144,6 +146,8 @@ class GW:
 
     def get_gwa_results(self):
         o = self.opt
+        if getattr(self, "qsgw_final_energies", None) is not None:  # gw.cc:312-318
+            return self.qsgw_final_energies
         return (np.diag(self.Sigma_x) + np.diag(self.Sigma_c) - np.diag(self.vxc)
                 + self.dft_energies[o.qpmin:o.qpmin + self.qptotal])
 
@@ -189,6 +193,88 @@ class GW:
                 elif i_gw == o.gw_sc_max_iterations - 1:
                     break
         self.Sigma_c[np.diag_indices(self.qptotal)] = self.sigma.calc_correlation_diag(freqs)
+
+    # gw.cc:798-1130
+    def calculate_qsgw(self):
+        """Quasiparticle self-consistent GW.  The caller has restored Mmn to the DFT-MO basis (Mmn.rebuild())."""
+        o = self.opt
+        e_qp_full = self.get_gwa_results().copy()
+        self.qsgw_seed_energies = e_qp_full.copy()
+        self.qsgw_final_energies = None
+        qsgw_qpmax = o.qpmax
+        lumo_local = o.homo - o.qpmin + 1
+        for n in range(lumo_local, self.qptotal):
+            if abs(e_qp_full[n] - self.dft_energies[o.qpmin + n]) > o.qsgw_max_virt_correction:
+                qsgw_qpmax = o.qpmin + n - 1
+                break
+        nq = qsgw_qpmax - o.qpmin + 1
+        trimmed = qsgw_qpmax < o.qpmax
+
+        def sigma_options(qpmax):
+            return osigma.SigmaOptions(homo=o.homo, qpmin=o.qpmin, qpmax=qpmax, rpamin=o.rpamin, rpamax=o.rpamax,
+                                       eta=o.eta, quadrature_scheme=o.quadrature_scheme, order=o.order, alpha=o.alpha)
+        if trimmed:
+            self.sigma.configure(sigma_options(qsgw_qpmax))
+            self.Sigma_x = np.zeros((nq, nq))
+            self.Sigma_c = np.zeros((nq, nq))
+        e_qp = e_qp_full[:nq].copy()
+        self.qsgw_rotation = np.eye(nq)
+        if o.ScaHFX > 0.0:
+            raise RuntimeError("GW::CalculateQSGW: QSGW is not compatible with hybrid DFT starting points")
+        if o.sigma_integration == "cda":
+            raise RuntimeError("GW::CalculateQSGW: QSGW is not supported with the CDA sigma integration method.")
+        H0 = -self.vxc[:nq, :nq] + np.diag(self.dft_energies[o.qpmin:o.qpmin + nq])
+        M_orig = self.Mmn.M.copy()
+        mixer = Anderson(o.gw_mixing_order, o.gw_mixing_alpha)
+        U = self.qsgw_rotation
+        self.rpa.set_qsgw_rotation(U, o.qpmin, o.homo)
+        diff_prev = np.finfo(float).max
+        tilde = None
+        self.qsgw_iterations = 0
+        for it in range(o.qsgw_max_iterations):
+            self.qsgw_iterations = it + 1
+            self.Mmn.M[...] = M_orig
+            if it > 0:
+                self.Mmn.rotate(self.qsgw_rotation, o.qpmin, qsgw_qpmax)
+            self.rpa.set_qsgw_rotation(self.qsgw_rotation, o.qpmin, o.homo)
+            self.sigma.prepare_screening()
+            self.Sigma_x = self.sigma.calc_exchange_matrix()
+            sc_row = self.sigma.calc_correlation_offdiag(e_qp)
+            tilde = self.Sigma_x + 0.5 * (sc_row + sc_row.T)
+            tilde[np.diag_indices(nq)] += self.sigma.calc_correlation_diag(e_qp)
+            s_flat = tilde.reshape(-1, order="F").copy()
+            if it > 0:
+                mixer.update_output(s_flat)
+                s_flat = mixer.mix_history()
+            _, dU = np.linalg.eigh(H0 + s_flat.reshape(nq, nq, order="F"))
+            e_new = np.linalg.eigvalsh(H0 + tilde)
+            diff = np.abs(e_new - e_qp).max()
+            if it > 1 and diff > 2.0 * diff_prev:
+                mixer = Anderson(o.gw_mixing_order, o.gw_mixing_alpha)
+            diff_prev = diff
+            if diff < o.qsgw_sc_limit:
+                e_qp = e_new
+                self.qsgw_rotation = dU
+                self.rpa.update_rpa_input_energies(self.dft_energies, e_qp, o.qpmin)
+                break
+            e_qp = e_new
+            self.qsgw_rotation = dU
+            mixer.update_input(tilde.reshape(-1, order="F").copy())
+            self.rpa.update_rpa_input_energies(self.dft_energies, e_qp, o.qpmin)
+        self.Sigma_c[np.diag_indices(nq)] = self.sigma.calc_correlation_diag(e_qp)
+        self.rpa.set_qsgw_rotation(None)
+        self.qsgw_energies = e_qp
+        if trimmed:
+            Ufull = np.eye(self.qptotal)
+            Ufull[:nq, :nq] = self.qsgw_rotation
+            self.qsgw_rotation = Ufull
+            merged = e_qp_full.copy()
+            merged[:nq] = e_qp
+            self.qsgw_final_energies = merged
+            self.rpa.update_rpa_input_energies(self.dft_energies, merged, o.qpmin)
+            self.Sigma_x = np.zeros((self.qptotal, self.qptotal))
+            self.Sigma_c = np.zeros((self.qptotal, self.qptotal))
+            self.sigma.configure(sigma_options(o.qpmax))
 
     # gw.cc:772-776
     def calculate_hqp(self):

@@ -1,7 +1,7 @@
 """Oracle for RPA (test infrastructure).  Follows xtp/src/libxtp/gwbse/rpa.cc.
 
-QSGW on-the-fly rotation (rpa.cc:92-113) is out of the hot-path scope named by
-BASELINE.json (G0W0/evGW) and is not restated.
+The QSGW on-the-fly m-rotation of the hole slices (rpa.cc:95-118, 162-181, 288-310; rpa.h:59-66) is restated in
+hole_slice().
 """
 import numpy as np
 
@@ -15,6 +15,26 @@ class RPA:
 
     def configure(self, homo, rpamin, rpamax):
         self.homo, self.rpamin, self.rpamax = homo, rpamin, rpamax
+        self.qsgw_U = None
+
+    # rpa.h:59-66
+    def set_qsgw_rotation(self, U, qpmin=0, homo=0):
+        self.qsgw_U, self.qsgw_qpmin, self.qsgw_homo = U, qpmin, homo
+
+    def hole_slice(self, m_level, n_unocc):
+        """Unoccupied rows of hole slice m_level; inside the QP window they are rotated to the current QP
+        wavefunctions: sum_vp U(vp, v_qp) Mmn[vp + qp_offset] (rpa.cc:95-118)."""
+        nt = self.Mmn.nsize()
+        if self.qsgw_U is not None:
+            off = self.qsgw_qpmin - self.rpamin
+            qptotal = self.qsgw_U.shape[1]
+            end_occ = min(self.qsgw_homo - self.rpamin + 1, off + qptotal)
+            if off <= m_level < end_occ:
+                out = np.zeros((n_unocc, self.Mmn.auxsize()))
+                for vp in range(qptotal):
+                    out += self.qsgw_U[vp, m_level - off] * self.Mmn[vp + off][nt - n_unocc:, :]
+                return out
+        return self.Mmn[m_level][nt - n_unocc:, :]
 
     def get_eta(self):
         return self.ETA
@@ -59,7 +79,7 @@ class RPA:
         res = np.zeros((naux, naux))
         e = self.energies
         for m in range(n_occ):
-            Mv = self.Mmn[m][self.Mmn.nsize() - n_unocc:, :]
+            Mv = self.hole_slice(m, n_unocc)
             dE = e[len(e) - n_unocc:] - e[m]
             if imag:
                 d = 4.0 * dE / (dE * dE + frequency * frequency)
@@ -89,7 +109,7 @@ class RPA:
         res = np.zeros((naux, naux))
         e = self.energies
         for m in range(n_occ):
-            Mv = self.Mmn[m][self.Mmn.nsize() - n_unocc:, :]
+            Mv = self.hole_slice(m, n_unocc)
             dE = e[len(e) - n_unocc:] - e[m]
             dEm = frequency.real - dE
             dEp = frequency.real + dE
@@ -114,10 +134,11 @@ class RPA:
         n_occ, n_unocc = self._sizes()
         S = n_occ * n_unocc
         apb = np.zeros((S, S))
+        rot = [self.hole_slice(v, n_unocc) for v in range(n_occ)]  # rpa.cc:288-310
         for v2 in range(n_occ):
-            M2 = self.Mmn[v2][n_occ:n_occ + n_unocc, :]
+            M2 = rot[v2]
             for v1 in range(v2, n_occ):
-                M1 = self.Mmn[v1][n_occ:n_occ + n_unocc, :]
+                M1 = rot[v1]
                 apb[v1 * n_unocc:(v1 + 1) * n_unocc, v2 * n_unocc:(v2 + 1) * n_unocc] = 4.0 * M1 @ M2.T
         apb[np.diag_indices(S)] += self.h2p_amb()
         return apb  # lower triangle filled (Eigen solver uses the lower triangle)

@@ -138,7 +138,7 @@ class SigmaExact(SigmaBase):
         Mi = self.Mmn[level + off]
         res = np.zeros((self.rpatotal, n_occ * n_unocc))
         for v in range(n_occ):
-            Mv = self.Mmn[v][n_occ:n_occ + n_unocc, :]
+            Mv = self.rpa.hole_slice(v, n_unocc)  # QSGW: rotated inside the QP window (sigma_exact.cc:119-145)
             fc = Mv @ Mi.T
             res += fc.T @ XpY[v * n_unocc:(v + 1) * n_unocc, :]
         return res

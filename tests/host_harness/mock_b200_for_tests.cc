@@ -10,6 +10,7 @@
 // process's LAPACK through mock_set_gen_eig.
 #include <algorithm>
 #include <cmath>
+#include <complex>
 #include <cstdlib>
 #include <cstring>
 #include <stdexcept>
@@ -40,6 +41,11 @@ struct gwbse_ctx {
   std::vector<double> residues, rpa_omegas, energies_exact;
   int ex_S = 0, ex_q = 0, ex_nocc = 0;
   double ex_eta = 0.0;
+  // CDA: kappa matrices [order + 1][naux * naux] (last: kappa_0), quadrature, ranges
+  bool cda_ready = false;
+  std::vector<double> cda_kappa, cda_pts, cda_wts;
+  int cda_order = 0, cda_sym = 0, cda_homo = 0, cda_rpamin = 0, cda_rpamax = 0, cda_qpmin = 0, cda_q = 0;
+  double cda_alpha = 0.0, cda_eta = 0.0;
   // BSE
   bool bse_ready = false;
   int homo = 0, vt = 0, ct = 0, voff = 0, coff = 0;
@@ -47,7 +53,23 @@ struct gwbse_ctx {
   double bse_flops = 0.0;
   long long bse_products = 0, bse_columns = 0;
 
+  // QSGW rotation of the hole slices (rpa.h:59-66)
+  std::vector<double> qsgw_U;
+  int qsgw_q = 0, qsgw_qpmin = 0, qsgw_homo = 0;
+
   double& M(int m, int n, int chi) { return X[((size_t)chi * mtotal + m) * ntotal + n]; }
+  // element (v, n, chi) of hole slice v as the RPA sums see it (rpa.cc:95-118)
+  double hole(int v, int n, int chi) {
+    if (!qsgw_U.empty()) {
+      const int off = qsgw_qpmin - mmin, end_occ = std::min(qsgw_homo - mmin + 1, off + qsgw_q);
+      if (v >= off && v < end_occ) {
+        double s = 0.0;
+        for (int vp = 0; vp < qsgw_q; ++vp) s += qsgw_U[vp + (size_t)(v - off) * qsgw_q] * M(vp + off, n, chi);
+        return s;
+      }
+    }
+    return M(v, n, chi);
+  }
 };
 
 struct gwbse_basis {
@@ -645,7 +667,7 @@ int gwbse_rpa_epsilon(gwbse_ctx* ctx, int kind, double fre, double fim, double e
   REQUIRE(rpamin == ctx->mmin && rpamin == ctx->nmin && rpamax - rpamin + 1 == ctx->ntotal, "RPA range must match Mmn");
   const int naux = ctx->naux, n_occ = homo - rpamin + 1, n_unocc = rpamax - homo, ntot = ctx->ntotal;
   ctx->eps.assign((size_t)naux * naux, 0.0);
-  std::vector<double> d(n_unocc);
+  std::vector<double> d(n_unocc), Hv((size_t)n_unocc * naux);
   for (int v = 0; v < n_occ; ++v) {
     for (int c = 0; c < n_unocc; ++c) {
       const double dE = e[ntot - n_unocc + c] - e[v];
@@ -659,10 +681,12 @@ int gwbse_rpa_epsilon(gwbse_ctx* ctx, int kind, double fre, double fim, double e
         d[c] = -2.0 * (dm / (dm * dm + (fim + eta) * (fim + eta)) - dp / (dp * dp + (fim - eta) * (fim - eta)));
       }
     }
+    for (int c = 0; c < n_unocc; ++c)
+      for (int a = 0; a < naux; ++a) Hv[(size_t)c * naux + a] = ctx->hole(v, ntot - n_unocc + c, a);
     for (int c2 = 0; c2 < naux; ++c2)
       for (int c1 = c2; c1 < naux; ++c1) {  // lower triangle, mirrored below
         double s = 0.0;
-        for (int c = 0; c < n_unocc; ++c) s += ctx->M(v, ntot - n_unocc + c, c1) * d[c] * ctx->M(v, ntot - n_unocc + c, c2);
+        for (int c = 0; c < n_unocc; ++c) s += Hv[(size_t)c * naux + c1] * d[c] * Hv[(size_t)c * naux + c2];
         ctx->eps[c1 + (size_t)c2 * naux] += s;
       }
   }
@@ -676,6 +700,20 @@ int gwbse_rpa_epsilon(gwbse_ctx* ctx, int kind, double fre, double fim, double e
   MOCK_END(ctx)
 }
 double* gwbse_rpa_epsilon_ptr(gwbse_ctx* ctx) { return ctx ? ctx->eps.data() : nullptr; }
+int gwbse_rpa_set_qsgw_rotation(gwbse_ctx* ctx, const double* U, int ldu, int qptotal, int qpmin, int homo) {
+  MOCK_BEGIN(ctx)
+  ctx->qsgw_U.clear();
+  if (U) {
+    REQUIRE(qptotal > 0 && ldu >= qptotal, "invalid QSGW rotation");
+    ctx->qsgw_U.resize((size_t)qptotal * qptotal);
+    for (int j = 0; j < qptotal; ++j)
+      for (int i = 0; i < qptotal; ++i) ctx->qsgw_U[i + (size_t)j * qptotal] = U[i + (size_t)j * ldu];
+    ctx->qsgw_q = qptotal;
+    ctx->qsgw_qpmin = qpmin;
+    ctx->qsgw_homo = homo;
+  }
+  MOCK_END(ctx)
+}
 int gwbse_rpa_h2p_apb(gwbse_ctx* ctx, const double* e, int homo, int rpamin, int rpamax, double* apb, int ld) {
   MOCK_BEGIN(ctx)
   // RPA::Calculate_H2p_ApB, rpa.cc:281-326 (+ the A-B diagonal)
@@ -687,7 +725,7 @@ int gwbse_rpa_h2p_apb(gwbse_ctx* ctx, const double* e, int homo, int rpamin, int
       for (int v1 = 0; v1 < n_occ; ++v1)
         for (int c1 = 0; c1 < n_unocc; ++c1) {
           double s = 0.0;
-          for (int chi = 0; chi < ctx->naux; ++chi) s += ctx->M(v1, n_occ + c1, chi) * ctx->M(v2, n_occ + c2, chi);
+          for (int chi = 0; chi < ctx->naux; ++chi) s += ctx->hole(v1, n_occ + c1, chi) * ctx->hole(v2, n_occ + c2, chi);
           double h = 4.0 * s;
           if (v1 == v2 && c1 == c2) h += e[n_occ + c1] - e[v1];
           apb[(v1 * n_unocc + c1) + (size_t)(v2 * n_unocc + c2) * ld] = h;
@@ -781,7 +819,7 @@ int gwbse_sigma_exact_prepare(gwbse_ctx* ctx, const double* omegas, const double
       for (int v = 0; v < n_occ; ++v)
         for (int c = 0; c < n_unocc; ++c) {
           double t = 0.0;
-          for (int chi = 0; chi < ctx->naux; ++chi) t += ctx->M(v, n_occ + c, chi) * ctx->M(qpoff + i, n, chi);
+          for (int chi = 0; chi < ctx->naux; ++chi) t += ctx->hole(v, n_occ + c, chi) * ctx->M(qpoff + i, n, chi);
           fc[(size_t)v * n_unocc + c] = t;
         }
       for (int s2 = 0; s2 < S; ++s2) {
@@ -823,6 +861,113 @@ int gwbse_sigma_exact_offdiag(gwbse_ctx* ctx, int q, const double* freqs, double
           }
       out[i + (size_t)j * ld] = s;
     }
+  MOCK_END(ctx)
+}
+
+// ---- Sigma_CDA (sigma_cda.cc:30-141, ImaginaryAxisIntegration.cc:90-176), evaluated the reference's way: one
+//      I kappa_j product per node and evaluation ------------------------------------------------------------------
+int gwbse_sigma_cda_prepare(gwbse_ctx* ctx, int order, const double* points, const double* weights, int symmetry,
+                            double alpha, const double* energies, int homo, int rpamin, int rpamax, int qpmin,
+                            int qpmax, double eta) {
+  MOCK_BEGIN(ctx)
+  require_mmn(ctx);
+  const int n = ctx->naux;
+  const size_t nn = (size_t)n * n;
+  ctx->cda_ready = false;
+  ctx->cda_kappa.assign(nn * (order + 1), 0.0);
+  double* kzero = ctx->cda_kappa.data() + nn * order;
+  auto inverse_minus_one = [&](double* dst) {
+    std::vector<double> A(ctx->eps), I(nn, 0.0);
+    for (int i = 0; i < n; ++i) I[i + (size_t)i * n] = 1.0;
+    solve(n, n, A.data(), n, I.data(), n);
+    for (int i = 0; i < n; ++i) I[i + (size_t)i * n] -= 1.0;
+    std::copy(I.begin(), I.end(), dst);
+  };
+  if (gwbse_rpa_epsilon(ctx, 2, 0.0, 0.0, eta, energies, homo, rpamin, rpamax, nullptr, 0)) throw std::runtime_error(ctx->err);
+  inverse_minus_one(kzero);
+  for (int j = 0; j < order; ++j) {
+    if (gwbse_rpa_epsilon(ctx, 0, points[j], 0.0, eta, energies, homo, rpamin, rpamax, nullptr, 0))
+      throw std::runtime_error(ctx->err);
+    double* k = ctx->cda_kappa.data() + nn * j;
+    inverse_minus_one(k);
+    const double sc = std::exp(-std::pow(alpha * points[j], 2));
+    for (size_t i = 0; i < nn; ++i) k[i] = -k[i] + sc * kzero[i];
+  }
+  ctx->cda_pts.assign(points, points + order);
+  ctx->cda_wts.assign(weights, weights + order);
+  ctx->cda_order = order;
+  ctx->cda_sym = symmetry;
+  ctx->cda_alpha = alpha;
+  ctx->cda_eta = eta;
+  ctx->cda_homo = homo;
+  ctx->cda_rpamin = rpamin;
+  ctx->cda_rpamax = rpamax;
+  ctx->cda_qpmin = qpmin;
+  ctx->cda_q = qpmax - qpmin + 1;
+  ctx->cda_ready = true;
+  MOCK_END(ctx)
+}
+
+int gwbse_sigma_cda_eval(gwbse_ctx* ctx, int nreq, const int* levels, const double* freqs, const double* energies,
+                         double* sigma) {
+  MOCK_BEGIN(ctx)
+  REQUIRE(ctx->cda_ready, "CDA screening not prepared (gwbse_sigma_cda_prepare)");
+  const int n = ctx->naux, nt = ctx->ntotal, order = ctx->cda_order;
+  const size_t nn = (size_t)n * n;
+  const int occ = ctx->cda_homo + 1 - ctx->cda_rpamin;
+  const int homo = ctx->cda_homo - ctx->cda_rpamin;
+  const double fermi = 0.5 * (energies[homo + 1] + energies[homo]);
+  const double pi = 3.14159265358979323846;
+  for (int r = 0; r < nreq; ++r) {
+    REQUIRE(levels[r] >= 0 && levels[r] < ctx->cda_q, "level outside the qp window");
+    const int m = levels[r] + ctx->cda_qpmin - ctx->cda_rpamin;
+    const double w = freqs[r];
+    auto rowform = [&](const double* kappa, int i) {  // (I kappa)[i,:] . I[i,:]
+      double s = 0.0;
+      for (int a = 0; a < n; ++a) {
+        double t = 0.0;
+        for (int b = 0; b < n; ++b) t += ctx->M(m, i, b) * kappa[b + (size_t)a * n];
+        s += t * ctx->M(m, i, a);
+      }
+      return s;
+    };
+    double total = 0.0;
+    for (int j = 0; j < order; ++j) {
+      const double* kappa = ctx->cda_kappa.data() + nn * j;
+      double acc = 0.0;
+      for (int i = 0; i < nt; ++i) {
+        const std::complex<double> dE(w - energies[i], i < occ ? ctx->cda_eta : -ctx->cda_eta), cp(0.0, ctx->cda_pts[j]);
+        std::complex<double> den = 1.0 / (dE + cp);
+        if (ctx->cda_sym) den += 1.0 / (dE - cp);
+        acc += den.real() * rowform(kappa, i);
+      }
+      total += ctx->cda_wts[j] * 0.5 / pi * acc;
+    }
+    const double* kzero = ctx->cda_kappa.data() + nn * order;
+    for (int i = 0; i < nt; ++i) {
+      const double delta = energies[i] - w, ad = std::fabs(delta);
+      double factor = 0.0;
+      if (fermi < energies[i] && energies[i] < w) factor = 1.0;
+      else if (fermi > energies[i] && energies[i] > w) factor = -1.0;
+      else if (ad < 1e-10 && fermi > energies[i]) factor = -0.5;
+      else if (ad < 1e-10 && fermi < energies[i]) factor = 0.5;
+      if (std::fabs(factor) > 1e-10) {
+        if (gwbse_rpa_epsilon(ctx, 2, ad, ctx->cda_eta, ctx->cda_eta, energies, ctx->cda_homo, ctx->cda_rpamin,
+                              ctx->cda_rpamax, nullptr, 0))
+          throw std::runtime_error(ctx->err);
+        std::vector<double> A(ctx->eps), x(n), row(n);
+        for (int a = 0; a < n; ++a) x[a] = row[a] = ctx->M(m, i, a);
+        solve(n, 1, A.data(), n, x.data(), n);
+        double dot = 0.0;
+        for (int a = 0; a < n; ++a) dot += (x[a] - row[a]) * row[a];
+        total += factor * dot;
+      }
+      if (ad > 1e-10)
+        total += 0.5 * std::copysign(1.0, delta) * std::exp(std::pow(ctx->cda_alpha * delta, 2)) *
+                 std::erfc(std::fabs(ctx->cda_alpha * delta)) * rowform(kzero, i);
+    }
+    sigma[r] = total;
+  }
   MOCK_END(ctx)
 }
 

@@ -150,6 +150,56 @@ void mul_right_dev(gwbse_ctx* ctx, const double* R_dev, int ldr) {
 
 }  // namespace
 
+namespace gwbse {
+HoleView hole_view(gwbse_ctx* ctx, int n_occ) {
+  auto& qs = ctx->qsgw;
+  if (!qs.active) return {ctx->X + n_occ, ctx->ldx, ctx->npad};
+  GW_REQUIRE(ctx->world == 1, "QSGW is single-GPU (the hole rotation mixes slices of every rank)");
+  const int npad = ctx->npad, naux = ctx->naux;
+  const long long ldo = (long long)n_occ * npad;
+  double* Xo = ctx->buf("qsgw_Xocc", (size_t)ldo * naux);
+  if (qs.built_version != ctx->mmn_version || qs.built_nocc != n_occ) {
+    const int off = qs.qpmin - ctx->mmin;
+    const int end_occ = std::min(qs.homo - ctx->mmin + 1, off + qs.qptotal);
+    GW_REQUIRE(off >= 0 && off + qs.qptotal <= ctx->mtotal, "QSGW rotation outside the Mmn range");
+    // occupied slices outside the QP window: unchanged
+    GW_CUDA(cudaMemcpy2DAsync(Xo, sizeof(double) * ldo, ctx->X, sizeof(double) * ctx->ldx, sizeof(double) * ldo, naux,
+                              cudaMemcpyDeviceToDevice, ctx->stream));
+    if (end_occ > off) {
+      // Xo[chi][off + v][n] = sum_vp U(vp, v) X[chi][off + vp][n]: rows (chi, n), k = vp
+      GemmParams p;
+      GW_REQUIRE((long long)naux * npad < (1LL << 31), "Mmn too large for the hole rotation");
+      p.M = naux * npad;
+      p.N = end_occ - off;
+      p.Ki = qs.qptotal;
+      p.A.ptr = ctx->X + (long long)off * npad;
+      p.A.Lr = npad;
+      p.A.s_ri = 1;
+      p.A.s_ro = ctx->ldx;
+      p.A.s_ki = npad;
+      p.B.ptr = qs.U;
+      p.B.s_ri = qs.qptotal;
+      p.B.s_ki = 1;
+      p.C = Xo + (long long)off * npad;
+      p.Lm = npad;
+      p.sC_mi = 1;
+      p.sC_mo = ldo;
+      p.sC_ni = npad;
+      ctx->gemm(p);
+    }
+    qs.built_version = ctx->mmn_version;
+    qs.built_nocc = n_occ;
+  }
+  return {Xo + n_occ, ldo, npad};
+}
+
+double* mmn_scratch_x2(gwbse_ctx* ctx) {
+  require_mmn(ctx);
+  ensure_x2(ctx);
+  return ctx->X2;
+}
+}  // namespace gwbse
+
 extern "C" {
 
 int gwbse_mmn_alloc(gwbse_ctx* ctx, int naux, int mmin, int mmax, int nmin, int nmax) {
@@ -411,6 +461,27 @@ int gwbse_mmn_rotate(gwbse_ctx* ctx, const double* U, int ldu, int qpmin, int qp
   GW_API_END(ctx)
 }
 
+// RPA::setQSGWRotation (rpa.h:59-66) / Sigma_base::setQSGWRotation (sigma_base.h:51-58): U == NULL clears it
+int gwbse_rpa_set_qsgw_rotation(gwbse_ctx* ctx, const double* U, int ldu, int qptotal, int qpmin, int homo) {
+  GW_API_BEGIN(ctx)
+  auto& qs = ctx->qsgw;
+  qs.built_version = -1;
+  if (!U) {
+    qs.active = false;
+  } else {
+    GW_REQUIRE(qptotal > 0 && ldu >= qptotal, "invalid QSGW rotation");
+    qs.U = ctx->buf("qsgw_U", (size_t)qptotal * qptotal);
+    GW_CUDA(copy2d_async(qs.U, sizeof(double) * qptotal, U, sizeof(double) * ldu, sizeof(double) * qptotal, qptotal,
+                         cudaMemcpyHostToDevice, ctx->stream));
+    GW_CUDA(cudaStreamSynchronize(ctx->stream));
+    qs.qptotal = qptotal;
+    qs.qpmin = qpmin;
+    qs.homo = homo;
+    qs.active = true;
+  }
+  GW_API_END(ctx)
+}
+
 int gwbse_mmn_snapshot(gwbse_ctx* ctx) {
   GW_API_BEGIN(ctx)
   GW_PROF(ctx, "mmn_snapshot");
@@ -507,10 +578,11 @@ int gwbse_rpa_epsilon(gwbse_ctx* ctx, int kind, double fre, double fim, double e
     p.N = naux;
     p.Ko = nloc_occ;
     p.Ki = n_unocc;
-    p.A.ptr = ctx->X + n_occ;
-    p.A.s_ri = ctx->ldx;
+    const HoleView hv = hole_view(ctx, n_occ);
+    p.A.ptr = hv.ptr;
+    p.A.s_ri = hv.s_chi;
     p.A.s_ki = 1;
-    p.A.s_ko = ctx->npad;
+    p.A.s_ko = hv.s_v;
     p.B = p.A;
     p.C = ctx->eps;
     p.sC_mi = 1;
@@ -557,11 +629,12 @@ int gwbse_rpa_h2p_apb(gwbse_ctx* ctx, const double* energies, int homo, int rpam
   p.M = S;
   p.N = S;
   p.Ki = ctx->naux;
-  p.A.ptr = ctx->X + n_occ;
+  const HoleView hv = hole_view(ctx, n_occ);
+  p.A.ptr = hv.ptr;
   p.A.Lr = n_unocc;
   p.A.s_ri = 1;
-  p.A.s_ro = ctx->npad;
-  p.A.s_ki = ctx->ldx;
+  p.A.s_ro = hv.s_v;
+  p.A.s_ki = hv.s_chi;
   p.B = p.A;
   p.C = apb_dev;
   p.sC_mi = 1;

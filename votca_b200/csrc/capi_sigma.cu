@@ -267,10 +267,11 @@ int gwbse_sigma_exact_prepare(gwbse_ctx* ctx, const double* rpa_omegas, const do
   p.N = S;
   p.Ko = n_occ;
   p.Ki = n_unocc;
-  p.A.ptr = ctx->X + n_occ;
-  p.A.s_ri = ctx->ldx;
+  const HoleView hv = hole_view(ctx, n_occ);  // QSGW: rotated inside the QP window (sigma_exact.cc:119-145)
+  p.A.ptr = hv.ptr;
+  p.A.s_ri = hv.s_chi;
   p.A.s_ki = 1;
-  p.A.s_ko = npad;
+  p.A.s_ko = hv.s_v;
   p.B.ptr = XpY_dev;
   p.B.s_ri = ldxpy;
   p.B.s_ki = 1;

@@ -137,6 +137,27 @@ struct gwbse_ctx {
   size_t sigma_tree_bytes = (size_t)8 << 30;
   double* exact_res = nullptr;  // residues (q*npad) x S
 
+  // ---- QSGW (rpa.h:59-66): rotation of the hole slices inside the QP window, applied in the RPA sums ----
+  struct QsgwState {
+    bool active = false;
+    int qptotal = 0, qpmin = 0, homo = 0;
+    double* U = nullptr;              // qptotal x qptotal (device, ld = qptotal)
+    long long built_version = -1;     // mmn_version the rotated copy of the occupied slices was built from
+    int built_nocc = 0;
+  } qsgw;
+
+  // ---- Sigma_CDA (capi_cda.cu) ----
+  struct CdaState {
+    bool ready = false;
+    int order = 0, symmetry = 0;
+    double alpha = 0.0, eta = 0.0;
+    int homo = 0, rpamin = 0, rpamax = 0, qpmin = 0, q = 0;
+    int nq_local = 0, lfirst = 0;  // local slices of the qp window: count and first local index
+    long long node_stride = 0;     // doubles between the Q tables of consecutive quadrature nodes
+    long long mmn_version = -1;
+    std::vector<double> pts, wts;
+  } cda;
+
   // ---- BSE ----
   struct BseState {
     bool ready = false;
@@ -225,6 +246,16 @@ namespace gwbse {
 // ranks into out[(p-p0)*ldo + (s-s0)*rpad + (row-row0)] in natural slice order (ldo >= ns*rpad)
 void gather_slices(gwbse_ctx* ctx, int s0, int ns, int row0, int nrows, int p0, int np, double* out, long long ldo,
                    int rpad);
+// Hole slices as the RPA sums see them (rpa.cc:92-118): element (v, c, chi) at ptr[chi * s_chi + v * s_v + c], c
+// counting the unoccupied rows.  Plain view into X, or - with a QSGW rotation registered - a copy of the occupied
+// slices in which those inside the QP window are sum_vp U(vp, v) Mmn[vp] (capi_mmn.cu).
+struct HoleView {
+  const double* ptr;
+  long long s_chi, s_v;
+};
+HoleView hole_view(gwbse_ctx* ctx, int n_occ);
+// the second Mmn buffer (out-of-place target of MultiplyRight) as scratch of the same shape as X (capi_mmn.cu)
+double* mmn_scratch_x2(gwbse_ctx* ctx);
 // Fill3cMO contraction of a device-resident AO block whose columns are pitch doubles apart (capi_mmn.cu)
 void mmn_fill_block_pitched(gwbse_ctx* ctx, int aux_offset, int aux_count, const double* ao3c_dev, long long pitch);
 // NCCL plumbing (comm.cu)

@@ -18,7 +18,9 @@ struct TCfg {
 // 0: 128x128 (8 consumer warps of 64x32, one CTA per SM)   1: 128x64 (4 warps of 64x32, two CTAs per SM)
 // 2: 128x32  (4 warps of 32x32, two CTAs per SM)           3: 64x64  (4 warps of 32x32, three CTAs per SM)
 // 4: 128x48  (4 warps of 32x48, two CTAs per SM): the 144- and 287-wide dimensions of the BSE legs
-constexpr TCfg kT[5] = {{128, 128, 1, 1.00}, {128, 64, 2, 0.97}, {128, 32, 2, 0.62}, {64, 64, 3, 0.60}, {128, 48, 2, 0.80}};
+// eff: 4096^3 NN / TN and the long-K shapes on B200 (profiles/r02_gemm_tile_sweep.txt): every 128-row tile runs
+// within 2 % of 33 TFLOP/s, the 64 x 64 tile at 29
+constexpr TCfg kT[5] = {{128, 128, 1, 1.00}, {128, 64, 2, 0.985}, {128, 32, 2, 0.99}, {64, 64, 3, 0.88}, {128, 48, 2, 0.975}};
 constexpr int kNT = 5;
 
 using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -210,7 +212,7 @@ double tplan_cost(const GemmParams& p, const RowShape& ra_in, const RowShape& rb
   const double fixed = kT[cfg].occ == 1 ? 6.0 : 3.0;
   const double ksteps = (double)ceil_div<long long>(T_total, splitk) + fixed;
   const double flops_item = 2.0 * kT[cfg].BM * kT[cfg].BN * ksteps * TMA_BK;
-  const double rate_sm = 34.0e12 / 148.0 * kT[cfg].eff;
+  const double rate_sm = 33.5e12 / 148.0 * kT[cfg].eff;
   double t = (double)rounds * kT[cfg].occ * flops_item / rate_sm;
   if (splitk > 1) {
     const long long tm = tiles_along(M, ra, kT[cfg].BM), tn = tiles_along(N, rb, kT[cfg].BN);
@@ -313,10 +315,17 @@ size_t gemm_tma_ws_bytes(const GemmParams& p, int num_sms, int force_cfg, int fo
   return sizeof(double) * (size_t)pl.tiles_m * kT[pl.cfg].BM * pl.tiles_n * kT[pl.cfg].BN * pl.splitk * p.Z1 * p.Z2;
 }
 
+// Short K (the K = ct leg of the BSE intermediate, 18 k-steps): the tile's epilogue is a fifth of its run time and
+// the persistent kernel has nothing to overlap it with (4 consumer warps per co-resident CTA cannot keep the DMMA
+// pipe busy alone) - measured 26.4 against 29.9 TFLOP/s of the cp.async kernel with its 2 x 8 warps per SM
+// (scratch/tma_probe.cu, 4320 x 50816 x 288).  Unless a TMA tile shape is forced, those go to the cp.async kernel.
+constexpr long long kMinKStepsForTma = 48;
+
 bool gemm_tma_describe(const GemmParams& p, int num_sms, int force_cfg, int force_splitk, int* cfg, int* swap,
                        int* splitk) {
   RowShape ra, rb;
   if (!eligible(p, &ra, &rb)) return false;
+  if (force_cfg < 0 && (long long)p.Ko * ceil_div(p.Ki, TMA_BK) < kMinKStepsForTma) return false;
   const TPlan pl = make_tplan(p, ra, rb, num_sms, force_cfg, force_splitk);
   *cfg = pl.cfg;
   *swap = pl.swap ? 1 : 0;

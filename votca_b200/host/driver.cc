@@ -311,6 +311,8 @@ int gwbse_job_run(gwbse_job* job) {
   s["bse_cmax"] = r.bse_cmax;
   s["removed_functions"] = r.removed_functions;
   s["gw_iterations"] = r.gw_iterations;
+  s["qsgw_iterations"] = r.qsgw_iterations;
+  s["is_qsgw"] = r.is_qsgw ? 1.0 : 0.0;
   s["singlet_davidson_iterations"] = r.singlet_davidson_iterations;
   s["triplet_davidson_iterations"] = r.triplet_davidson_iterations;
   s["singlet_converged"] = r.BSE_singlet.success;

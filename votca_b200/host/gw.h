@@ -6,6 +6,7 @@
 #pragma once
 #include <condition_variable>
 #include <cstring>
+#include <limits>
 #include <mutex>
 #include <thread>
 #include <unordered_map>
@@ -144,6 +145,11 @@ class GW {
     double qp_virtual_min_energy = -0.1;
     std::string qp_root_finder = "bisection";
     std::string qp_grid_search_mode = "adaptive_with_dense_fallback";
+    // QSGW (gw.h options of the reference, gwbse.xml:41-44)
+    bool do_qsgw = false;
+    Index qsgw_max_iterations = 20;
+    double qsgw_sc_limit = 1e-5;
+    double qsgw_max_virt_correction = 0.5;
   };
 
   // gw.cc:35-58
@@ -176,6 +182,8 @@ class GW {
   }
   // gw.cc:312-321
   VectorXd getGWAResults() const {
+    // QSGW with a trimmed virtual window: converged energies of the window, seed energies above it
+    if (qsgw_final_energies_.size() > 0) return qsgw_final_energies_;
     VectorXd r(qptotal_);
     for (Index i = 0; i < qptotal_; ++i)
       r(i) = Sigma_x_(i, i) + Sigma_c_(i, i) - vxc_(i, i) + dft_energies_(opt_.qpmin + i);
@@ -240,6 +248,138 @@ class GW {
     }
     VectorXd diag = sigma_->CalcCorrelationDiag(frequencies);
     for (Index i = 0; i < qptotal_; ++i) Sigma_c_(i, i) = diag(i);
+  }
+
+  const MatrixXd& getQSGWRotation() const { return qsgw_rotation_; }
+  const VectorXd& getQSGWSeedEnergies() const { return qsgw_seed_energies_; }
+  Index qsgw_iterations() const { return qsgw_iterations_; }
+
+  // GW::CalculateQSGW, gw.cc:798-1130.  Per iteration: Mmn back to the DFT-MO basis (device snapshot), rotation of
+  // the QP-window rows (gwbse_mmn_rotate), screening with the hole slices rotated inside the RPA sums
+  // (gwbse_rpa_set_qsgw_rotation), the symmetrised static self-energy from the evaluators' batched kernels, Anderson
+  // mixing and two qptotal x qptotal eigenproblems on the host side.  The caller has put Mmn back into the DFT-MO
+  // basis (Mmn.Rebuild()) as gwbse.cc does before this call.
+  void CalculateQSGW() {
+    const Device& dev = Mmn_.device();
+    if (dev.world() > 1) throw std::runtime_error("GW::CalculateQSGW: QSGW is single-GPU in this build");
+    log_(" Starting QSGW self-consistency loop  ");
+    const VectorXd e_qp_full = getGWAResults();
+    qsgw_seed_energies_ = e_qp_full;
+    qsgw_final_energies_ = VectorXd();
+    // virtual-level threshold: trim the window at the first virtual whose perturbative correction is too large
+    Index qsgw_qpmax = opt_.qpmax;
+    const Index lumo_local = opt_.homo - opt_.qpmin + 1;
+    for (Index n = lumo_local; n < qptotal_; ++n) {
+      const double corr = std::abs(e_qp_full(n) - dft_energies_(opt_.qpmin + n));
+      if (corr > opt_.qsgw_max_virt_correction) {
+        qsgw_qpmax = opt_.qpmin + n - 1;
+        log_("  QSGW virtual threshold: level " + std::to_string(opt_.qpmin + n) + " exceeds the limit. Trimming QSGW " +
+             "window to [" + std::to_string(opt_.qpmin) + "," + std::to_string(qsgw_qpmax) + "].");
+        break;
+      }
+    }
+    const Index nq = qsgw_qpmax - opt_.qpmin + 1;
+    const bool window_trimmed = qsgw_qpmax < opt_.qpmax;
+    auto sigma_options = [&](Index qpmax) {
+      Sigma_base::options so;
+      so.homo = opt_.homo;
+      so.qpmin = opt_.qpmin;
+      so.qpmax = qpmax;
+      so.rpamin = opt_.rpamin;
+      so.rpamax = opt_.rpamax;
+      so.eta = opt_.eta;
+      so.quadrature_scheme = opt_.quadrature_scheme;
+      so.order = opt_.order;
+      so.alpha = opt_.alpha;
+      return so;
+    };
+    if (window_trimmed) {
+      sigma_->configure(sigma_options(qsgw_qpmax));
+      Sigma_x_ = MatrixXd::Zero(nq, nq);
+      Sigma_c_ = MatrixXd::Zero(nq, nq);
+    }
+    VectorXd e_qp = e_qp_full.head(nq);
+    qsgw_rotation_ = MatrixXd::Identity(nq, nq);
+    if (opt_.ScaHFX > 0.0)
+      throw std::runtime_error(
+          "GW::CalculateQSGW: QSGW is not compatible with hybrid DFT starting points (ScaHFX = " +
+          std::to_string(opt_.ScaHFX) + "). Use a pure GGA or LDA functional as the DFT starting point.");
+    if (opt_.sigma_integration == "cda")
+      throw std::runtime_error(
+          "GW::CalculateQSGW: QSGW is not supported with the CDA sigma integration method. Use sigma_integration=ppm or "
+          "sigma_integration=exact instead.");
+    MatrixXd H0 = -1.0 * vxc_.block(0, 0, nq, nq);
+    for (Index i = 0; i < nq; ++i) H0(i, i) += dft_energies_(opt_.qpmin + i);
+    Anderson qsgw_mixer;
+    qsgw_mixer.Configure(opt_.gw_mixing_order, opt_.gw_mixing_alpha);
+    auto register_rotation = [&](const MatrixXd* U) {
+      dev.check(gwbse_rpa_set_qsgw_rotation(dev.ctx(), U ? U->data() : nullptr, U ? (int)U->rows() : 0,
+                                            U ? (int)U->cols() : 0, (int)opt_.qpmin, (int)opt_.homo));
+    };
+    auto flat = [&](const MatrixXd& m) { return VectorXd(m.data(), m.size()); };
+    double diff_max_prev = std::numeric_limits<double>::max();
+    MatrixXd tilde_Sigma;
+    for (Index iter = 0; iter < opt_.qsgw_max_iterations; ++iter) {
+      qsgw_iterations_ = iter + 1;
+      // Step 1: DFT-MO basis again, then the full rotation in one shot
+      Mmn_.Rebuild();
+      if (iter > 0) Mmn_.Rotate(qsgw_rotation_, opt_.qpmin, qsgw_qpmax);
+      register_rotation(&qsgw_rotation_);
+      sigma_->PrepareScreening();
+      Sigma_x_ = sigma_->CalcExchangeMatrix();
+      const MatrixXd Sc_row = sigma_->CalcCorrelationOffDiag(e_qp);
+      tilde_Sigma = Sigma_x_ + 0.5 * (Sc_row + Sc_row.transpose());
+      const VectorXd Sc_diag = sigma_->CalcCorrelationDiag(e_qp);
+      for (Index i = 0; i < nq; ++i) tilde_Sigma(i, i) += Sc_diag(i);
+      // Step 2: Anderson mixing of the flattened self-energy
+      VectorXd S_flat = flat(tilde_Sigma);
+      if (iter > 0) {
+        qsgw_mixer.UpdateOutput(S_flat);
+        S_flat = qsgw_mixer.MixHistory();
+      }
+      // Step 3: rotation from the mixed Hamiltonian, energies (convergence) from the unmixed one
+      MatrixXd dU = H0 + MatrixXd(S_flat.data(), nq, nq, nq);
+      dev.sym_eig(dU);
+      MatrixXd H_new = H0 + tilde_Sigma;
+      const VectorXd e_new = dev.sym_eig(H_new);
+      const double diff_max = (e_new - e_qp).maxAbs();
+      log_("  QSGW iter " + std::to_string(iter) + "  max|dE_QP| = " + std::to_string(diff_max * 27.211386) + " eV");
+      if (iter > 1 && diff_max > 2.0 * diff_max_prev) {
+        qsgw_mixer = Anderson();
+        qsgw_mixer.Configure(opt_.gw_mixing_order, opt_.gw_mixing_alpha);
+      }
+      diff_max_prev = diff_max;
+      if (diff_max < opt_.qsgw_sc_limit) {
+        log_("  QSGW converged in " + std::to_string(iter + 1) + " iterations.");
+        e_qp = e_new;
+        qsgw_rotation_ = dU;
+        rpa_.UpdateRPAInputEnergies(dft_energies_, e_qp, opt_.qpmin);
+        break;
+      }
+      if (iter == opt_.qsgw_max_iterations - 1)
+        log_("  WARNING: QSGW did not converge in " + std::to_string(opt_.qsgw_max_iterations) +
+             " iterations. Inspect results carefully.");
+      e_qp = e_new;
+      qsgw_rotation_ = dU;
+      qsgw_mixer.UpdateInput(flat(tilde_Sigma));
+      rpa_.UpdateRPAInputEnergies(dft_energies_, e_qp, opt_.qpmin);
+    }
+    const VectorXd diag = sigma_->CalcCorrelationDiag(e_qp);
+    for (Index i = 0; i < nq; ++i) Sigma_c_(i, i) = diag(i);
+    register_rotation(nullptr);
+    if (window_trimmed) {
+      MatrixXd U_full = MatrixXd::Identity(qptotal_, qptotal_);
+      U_full.setBlock(0, 0, qsgw_rotation_);
+      qsgw_rotation_ = U_full;
+      VectorXd e_merged = e_qp_full;
+      for (Index i = 0; i < nq; ++i) e_merged(i) = e_qp(i);
+      qsgw_final_energies_ = e_merged;
+      rpa_.UpdateRPAInputEnergies(dft_energies_, e_merged, opt_.qpmin);
+      Sigma_x_ = MatrixXd::Zero(qptotal_, qptotal_);
+      Sigma_c_ = MatrixXd::Zero(qptotal_, qptotal_);
+      sigma_->configure(sigma_options(opt_.qpmax));
+    }
+    log_(" QSGW loop complete.");
   }
 
   // gw.cc:772-776
@@ -341,6 +481,10 @@ class GW {
     mutable std::unordered_set<std::uint64_t> seen_frequencies_;
     mutable QPStats stats_;
   };
+
+  MatrixXd qsgw_rotation_;
+  VectorXd qsgw_seed_energies_, qsgw_final_energies_;
+  Index qsgw_iterations_ = 0;
 
   double CalcHomoLumoShift(const VectorXd& frequencies) const {
     double DFTgap = dft_energies_(opt_.homo + 1) - dft_energies_(opt_.homo);

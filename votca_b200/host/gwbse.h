@@ -176,7 +176,8 @@ class GWBSE {
     std::vector<VectorXd> transition_dipoles;
     VectorXd oscillator_strengths;
     BSE::Interaction singlet_analysis, triplet_analysis;
-    Index removed_functions = 0, gw_iterations = 0;
+    Index removed_functions = 0, gw_iterations = 0, qsgw_iterations = 0;
+    bool is_qsgw = false;
     Index singlet_davidson_iterations = 0, triplet_davidson_iterations = 0;
     std::size_t sigma_batches = 0, sigma_evaluations = 0;
     double time_fill = 0, time_gw = 0, time_bse = 0;
@@ -288,8 +289,14 @@ class GWBSE {
     for (char& c : tasks) c = static_cast<char>(std::tolower(static_cast<unsigned char>(c)));
     if (tasks.find("exciton") != std::string::npos)
       throw std::runtime_error("tasks 'excitons' / 'exciton_uks' (unrestricted BSE, bse_uks.cc) are not on this path");
-    if (options.flag("gw.do_qsgw"))
-      throw std::runtime_error("gw.do_qsgw is not implemented on this path (GW::CalculateQSGW, gw.cc:798-1130)");
+    // gwbse.cc:531-547
+    gwopt_.do_qsgw = options.flag("gw.do_qsgw");
+    gwopt_.qsgw_max_iterations = options.idx("gw.qsgw_max_iterations");
+    gwopt_.qsgw_sc_limit = options.dbl("gw.qsgw_sc_limit");
+    gwopt_.qsgw_max_virt_correction = options.dbl("gw.qsgw_max_virt_correction");
+    if (gwopt_.do_qsgw)
+      log_(" QSGW enabled: max_iter=" + std::to_string(gwopt_.qsgw_max_iterations) +
+           " sc_limit=" + std::to_string(gwopt_.qsgw_sc_limit) + " Ha");
     do_gw_ = tasks.find("gw") != std::string::npos;
     if (tasks.find("all") != std::string::npos) do_gw_ = do_bse_singlets_ = do_bse_triplets_ = true;
     if (tasks.find("singlets") != std::string::npos) do_bse_singlets_ = true;
@@ -367,11 +374,33 @@ class GWBSE {
       gw.CalculateGWPerturbation();
       res.QPpert_energies = gw.getGWAResults();
       res.RPA_inputenergies = gw.RPAInputEnergies();
-      gw.CalculateHQP();
-      Hqp = gw.getHQP();
-      auto es = gw.DiagonalizeQPHamiltonian();
-      res.QPdiag_eigenvalues = es.first;
-      res.QPdiag_eigenvectors = es.second;
+      if (gwopt_.do_qsgw) {
+        // gwbse.cc:1019-1075: QSGW loop, then Mmn rebuilt in the QP wavefunction basis for the BSE, Hqp diagonal
+        gw.CalculateQSGW();
+        const VectorXd qsgw_energies = gw.getGWAResults();
+        const MatrixXd& U = gw.getQSGWRotation();
+        const Index qptotal = gwopt_.qpmax - gwopt_.qpmin + 1;
+        qsgw_mos_ = *in_.mos;
+        {
+          // C_qp[:, qp window] = C[:, qp window] U (small host product: N x q x q)
+          const MatrixXd Cw = in_.mos->block(0, gwopt_.qpmin, in_.mos->rows(), qptotal) * U;
+          qsgw_mos_.setBlock(0, gwopt_.qpmin, Cw);
+        }
+        log_(" Rebuilding Mmn in QSGW QP wavefunction basis");
+        Mmn.Fill(*in_.integrals, qsgw_mos_);
+        Hqp = asDiagonal(qsgw_energies);
+        res.QPdiag_eigenvalues = qsgw_energies;
+        res.QPdiag_eigenvectors = U;
+        res.is_qsgw = true;
+        res.qsgw_iterations = gw.qsgw_iterations();
+        res.RPA_inputenergies = gw.RPAInputEnergies();
+      } else {
+        gw.CalculateHQP();
+        Hqp = gw.getHQP();
+        auto es = gw.DiagonalizeQPHamiltonian();
+        res.QPdiag_eigenvalues = es.first;
+        res.QPdiag_eigenvectors = es.second;
+      }
       res.Sigma_x = gw.Sigma_x();
       res.Sigma_c = gw.Sigma_c();
       res.gw_iterations = gw.iterations();
@@ -474,7 +503,7 @@ class GWBSE {
     w.WriteEigenSystem(r.BSE_triplet.eigenvalues, r.BSE_triplet.eigenvectors, r.BSE_triplet.eigenvectors2,
                        r.BSE_triplet.eigenvalues.size() && !r.BSE_triplet.success ? 2 : 0, "BSE_triplet");
     w(std::uint8_t(bseopt_.use_Hqp_offdiag ? 1u : 0u), "use_Hqp_offdiag");
-    w(std::uint8_t(0u), "is_qsgw");
+    w(std::uint8_t(r.is_qsgw ? 1u : 0u), "is_qsgw");
     w(r.BSE_singlet_dynamic, "BSE_singlet_dynamic");
     w(r.BSE_triplet_dynamic, "BSE_triplet_dynamic");
     cpf.Close();
@@ -486,6 +515,7 @@ class GWBSE {
   Inputs in_;
   GW::options gwopt_;
   BSE::options bseopt_;
+  MatrixXd qsgw_mos_;  // MO coefficients with the QP-window columns rotated to the QSGW wavefunctions
   bool do_gw_ = false, do_bse_singlets_ = false, do_bse_triplets_ = false, do_dynamical_screening_bse_ = false;
 };
 

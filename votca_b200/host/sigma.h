@@ -260,162 +260,54 @@ class Sigma_CDA : public Sigma_base {
  public:
   Sigma_CDA(TCMatrix_gwbse& Mmn, const RPA& rpa) : Sigma_base(Mmn, rpa) {}
 
-  // sigma_cda.cc:30-45 + ImaginaryAxisIntegration::CalcDielInvVector (ImaginaryAxisIntegration.cc:90-102)
+  // sigma_cda.cc:30-45 + ImaginaryAxisIntegration::CalcDielInvVector (ImaginaryAxisIntegration.cc:90-102): the
+  // kappa matrices and, new here, the frequency-independent row forms (I kappa_j)[n,:] . I[n,:] of every level are
+  // built on the device (gwbse_sigma_cda_prepare); nothing of Mmn crosses PCIe
   void PrepareScreening() final {
     const Device& dev = Mmn_.device();
-    if (dev.world() > 1) throw std::runtime_error("sigma_integrator=cda is single-GPU in this build");
-    const Index n = Mmn_.auxsize();
-    const size_t nn = static_cast<size_t>(n * n);
-    mapped_gauss_legendre(opt_.quadrature_scheme, opt_.order, pts_, wts_, symmetry_);
-    // kappa_0 = eps(0)^-1 - 1
-    kzero_ = dev.alloc(nn);
-    double* eps = rpa_.calculate_epsilon_r_dev(std::complex<double>(0.0, 0.0));
-    dev.check(gwbse_d2d(dev.ctx(), kzero_.get(), eps, nn));
-    dev.check(gwbse_inverse_dev(dev.ctx(), (int)n, kzero_.get(), (int)n));
-    add_identity(kzero_.get(), n, -1.0);
-    dielinv_.clear();
-    for (Index j = 0; j < opt_.order; ++j) {
-      Device::Buffer k = dev.alloc(nn);
-      double* e = rpa_.calculate_epsilon_i_dev(pts_[j]);
-      dev.check(gwbse_d2d(dev.ctx(), k.get(), e, nn));
-      dev.check(gwbse_inverse_dev(dev.ctx(), (int)n, k.get(), (int)n));
-      add_identity(k.get(), n, -1.0);
-      // k <- -k + kzero * exp(-(alpha w)^2)
-      VectorXd m1(n, -1.0);
-      dev.check(gwbse_scale_cols_dev(dev.ctx(), (int)n, (int)n, k.get(), (int)n, m1.data()));
-      dev.check(gwbse_axpy_dev(dev.ctx(), (int)n, (int)n, std::exp(-std::pow(opt_.alpha * pts_[j], 2)),
-                               kzero_.get(), (int)n, k.get(), (int)n));
-      dielinv_.push_back(std::move(k));
-    }
+    if (dev.world() > 1)
+      throw std::runtime_error(
+          "sigma_integrator=cda is single-GPU: every residue needs a collective eps(z) assembly, and the per-rank QP "
+          "searches ask for them at different times");
+    bool symmetry = false;
+    mapped_gauss_legendre(opt_.quadrature_scheme, opt_.order, pts_, wts_, symmetry);
+    dev.check(gwbse_sigma_cda_prepare(dev.ctx(), (int)pts_.size(), pts_.data(), wts_.data(), symmetry ? 1 : 0,
+                                      opt_.alpha, rpa_.getRPAInputEnergies().data(), (int)opt_.homo, (int)opt_.rpamin,
+                                      (int)opt_.rpamax, (int)opt_.qpmin, (int)opt_.qpmax, rpa_.getEta()));
   }
 
-  // sigma_cda.cc:118-124 for a batch of requests (each request is evaluated independently)
+  // sigma_cda.cc:118-124 for a batch of requests; the derivative is the reference's central difference with
+  // h = 1e-3 (sigma_cda.h:57-63), its two extra evaluations ride in the same batch
   void EvalBatch(const std::vector<int>& levels, const std::vector<double>& freqs, std::vector<double>& sigma,
                  std::vector<double>* dsigma) const final {
-    sigma.resize(levels.size());
-    if (dsigma) dsigma->resize(levels.size());
-    for (size_t r = 0; r < levels.size(); ++r) {
-      sigma[r] = Element(levels[r], freqs[r]);
-      if (dsigma) {  // sigma_cda.h:57-63: central difference with h = 1e-3
-        const double h = 1e-3;
-        (*dsigma)[r] = (Element(levels[r], freqs[r] + h) - Element(levels[r], freqs[r] - h)) / (2 * h);
+    const Device& dev = Mmn_.device();
+    const size_t n = levels.size();
+    sigma.resize(n);
+    std::vector<int> lv(levels);
+    std::vector<double> fr(freqs);
+    const double h = 1e-3;
+    if (dsigma) {
+      dsigma->resize(n);
+      for (size_t r = 0; r < n; ++r) {
+        lv.push_back(levels[r]);
+        fr.push_back(freqs[r] + h);
+        lv.push_back(levels[r]);
+        fr.push_back(freqs[r] - h);
       }
+    }
+    std::vector<double> out(lv.size());
+    dev.check(gwbse_sigma_cda_eval(dev.ctx(), (int)lv.size(), lv.data(), fr.data(), rpa_.getRPAInputEnergies().data(),
+                                   out.data()));
+    for (size_t r = 0; r < n; ++r) {
+      sigma[r] = out[r];
+      if (dsigma) (*dsigma)[r] = (out[n + 2 * r] - out[n + 2 * r + 1]) / (2 * h);
     }
   }
   // sigma_cda.h:64-67
   MatrixXd CalcCorrelationOffDiag(const VectorXd&) const final { return MatrixXd::Zero(qptotal_, qptotal_); }
 
  private:
-  void add_identity(double* A, Index n, double v) const {
-    const Device& dev = Mmn_.device();
-    VectorXd ones(n, v);
-    Device::Buffer d = dev.upload(ones);
-    dev.check(gwbse_axpy_dev(dev.ctx(), 1, (int)n, 1.0, d.get(), 1, A, (int)(n + 1)));
-  }
-
-  double Element(Index gw_level, double frequency) const {
-    const Index gw_level_offset = gw_level + opt_.qpmin - opt_.rpamin;
-    const MatrixXd Imx = Mmn_[gw_level_offset];  // ntotal x naux
-    return CalcResidueContribution(frequency, Imx) + SigmaGQDiag(frequency, Imx, rpa_.getEta());
-  }
-
-  // ImaginaryAxisIntegration.cc:104-176
-  double SigmaGQDiag(double frequency, const MatrixXd& Imx, double eta) const {
-    const Device& dev = Mmn_.device();
-    const Index n = Mmn_.auxsize(), nt = Imx.rows();
-    const Index lumo = opt_.homo + 1;
-    const Index occ = lumo - opt_.rpamin;
-    const Index unocc = opt_.rpamax - opt_.homo;
-    const VectorXd& e = rpa_.getRPAInputEnergies();
-    std::vector<std::complex<double>> dE(nt);
-    for (Index i = 0; i < nt; ++i) dE[i] = std::complex<double>(frequency - e(i), 0.0);
-    for (Index i = 0; i < occ; ++i) dE[i] = std::complex<double>(dE[i].real(), eta);
-    for (Index i = nt - unocc; i < nt; ++i) dE[i] = std::complex<double>(dE[i].real(), -eta);
-    Device::Buffer dI = dev.upload(Imx);
-    Device::Buffer dT = dev.alloc(static_cast<size_t>(nt * n));
-    const double pi = 3.14159265358979323846;
-    double result = 0.0;
-    for (size_t j = 0; j < pts_.size(); ++j) {
-      const std::complex<double> cp(0.0, pts_[j]);
-      dev.gemm('N', 'N', nt, n, n, 1.0, dI.get(), nt, dielinv_[j].get(), n, 0.0, dT.get(), nt);
-      const MatrixXd T = dev.download(dT.get(), nt, n);
-      double acc = 0.0;
-      for (Index i = 0; i < nt; ++i) {
-        std::complex<double> den = 1.0 / (dE[i] + cp);
-        if (symmetry_) den += 1.0 / (dE[i] - cp);
-        double rowdot = 0.0;
-        for (Index a = 0; a < n; ++a) rowdot += T(i, a) * Imx(i, a);
-        acc += (den * rowdot).real();
-      }
-      result += wts_[j] * 0.5 / pi * acc;
-    }
-    return result;
-  }
-
-  // sigma_cda.cc:62-77
-  static double CalcResiduePrefactor(double e_f, double e_m, double frequency) {
-    double factor = 0.0;
-    double tolerance = 1e-10;
-    if (e_f < e_m && e_m < frequency) {
-      factor = 1.0;
-    } else if (e_f > e_m && e_m > frequency) {
-      factor = -1.0;
-    } else if (std::abs(e_m - frequency) < tolerance && e_f > e_m) {
-      factor = -0.5;
-    } else if (std::abs(e_m - frequency) < tolerance && e_f < e_m) {
-      factor = 0.5;
-    }
-    return factor;
-  }
-
-  // sigma_cda.cc:81-116 with CalcDiagContribution (:52-60) and the tail (:128-141)
-  double CalcResidueContribution(double frequency, const MatrixXd& Imx) const {
-    const Device& dev = Mmn_.device();
-    const VectorXd& rpa_energies = rpa_.getRPAInputEnergies();
-    const Index rpatotal = rpa_energies.size();
-    const Index n = Mmn_.auxsize();
-    double sigma_c = 0.0, sigma_c_tail = 0.0;
-    const Index homo = opt_.homo - opt_.rpamin;
-    const Index lumo = homo + 1;
-    const double fermi_rpa = (rpa_energies(lumo) + rpa_energies(homo)) / 2.0;
-    // tail: (Imx_row * kappa_0) . Imx_row for all rows at once
-    Device::Buffer dI = dev.upload(Imx);
-    Device::Buffer dT = dev.alloc(static_cast<size_t>(rpatotal * n));
-    dev.gemm('N', 'N', rpatotal, n, n, 1.0, dI.get(), rpatotal, kzero_.get(), n, 0.0, dT.get(), rpatotal);
-    const MatrixXd T = dev.download(dT.get(), rpatotal, n);
-    for (Index i = 0; i < rpatotal; ++i) {
-      const double delta = rpa_energies(i) - frequency;
-      const double abs_delta = std::abs(delta);
-      const double factor = CalcResiduePrefactor(fermi_rpa, rpa_energies(i), frequency);
-      if (std::abs(factor) > 1e-10) {
-        // x = eps(|delta| + i eta)^-1 row - row ; contribution = x . row
-        double* eps = rpa_.calculate_epsilon_r_dev(std::complex<double>(abs_delta, rpa_.getEta()));
-        Device::Buffer A = dev.alloc(static_cast<size_t>(n * n));
-        dev.check(gwbse_d2d(dev.ctx(), A.get(), eps, static_cast<size_t>(n * n)));
-        VectorXd row(n);
-        for (Index a = 0; a < n; ++a) row(a) = Imx(i, a);
-        Device::Buffer b = dev.upload(row);
-        dev.check(gwbse_lu_solve_dev(dev.ctx(), (int)n, 1, A.get(), (int)n, b.get(), (int)n));
-        const MatrixXd x = dev.download(b.get(), n, 1);
-        double dot = 0.0;
-        for (Index a = 0; a < n; ++a) dot += (x(a, 0) - row(a)) * row(a);
-        sigma_c += factor * dot;
-      }
-      if (abs_delta > 1e-10) {
-        const double erfc_factor = 0.5 * std::copysign(1.0, delta) * std::exp(std::pow(opt_.alpha * delta, 2)) *
-                                   std::erfc(std::abs(opt_.alpha * delta));
-        double value = 0.0;
-        for (Index a = 0; a < n; ++a) value += T(i, a) * Imx(i, a);
-        sigma_c_tail += value * erfc_factor;
-      }
-    }
-    return sigma_c + sigma_c_tail;
-  }
-
   std::vector<double> pts_, wts_;
-  bool symmetry_ = false;
-  Device::Buffer kzero_;
-  std::vector<Device::Buffer> dielinv_;
 };
 
 // SigmaFactory, xtp/src/libxtp/factories/sigmafactory.cc:32-36
