@@ -198,7 +198,8 @@ def run_reference(args, rank):
     vals = []
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        est = cpu_baseline.estimate(N, naux, homo, counts, sample_scale=24.0)
+        est = cpu_baseline.estimate(N, naux, homo, counts, sample_scale=24.0,
+                                    ao_system=args.workload if args.workload in TIER_R else None)
         vals.append(est["total_seconds"])
     wall = time.perf_counter() - t0
     v = float(np.mean(vals))
@@ -618,7 +619,8 @@ def make_line(args, rec, also, parity, world):
         pass
     if not args.no_cpu and world == 1:  # reported at N=1 only
         from oracle import cpu_baseline
-        est = cpu_baseline.estimate(N, naux, homo, counts, sample_scale=24.0)
+        est = cpu_baseline.estimate(N, naux, homo, counts, sample_scale=24.0,
+                                    ao_system=rec["workload"] if tier_r else None)
         line["cpu_baseline"] = {
             "value": est["total_seconds"], "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "extrapolated": True,
             "sample": ("reference CPU formulation (NumPy/OpenBLAS port, all host threads) timed per stage on a few "

@@ -63,6 +63,10 @@ int gwbse_job_set_basis(gwbse_job* job, const char* which, int nshell, const int
  * info), transition_dipoles (ind0..), BSE_*_dynamic, useTDA, use_Hqp_offdiag, ScaHFX.  Written without an HDF5
  * library (votca_b200/host/checkpoint.h).  NULL or "" switches it off. */
 int gwbse_job_set_orb_output(gwbse_job* job, const char* path);
+/* GWBSE::addoutput (gwbse.cc:580-738) written as the dftgwbse tool does (tools/dftgwbse.cc:120-128,
+ * <job>_summary.xml): DFT / GW / QP level energies, singlet and triplet excitation energies, oscillator strengths
+ * and transition dipoles, eV.  The input scalar "dft_total_energy" (Hartree) fills the DFTEnergy attribute.      */
+int gwbse_job_set_summary_output(gwbse_job* job, const char* path);
 /* the kernel-library context of this job (gwbse_b200.h), e.g. for gwbse_gemm_stats / timers */
 void* gwbse_job_ctx(gwbse_job* job);
 

@@ -81,7 +81,57 @@ def _best(fn, reps=2):
     return best
 
 
-def estimate(nbasis, naux, homo, counts, seed=7, sample_scale=1.0):
+AO_SRC = os.path.join(os.path.dirname(HERE), "tests", "host_harness", "ao3c_host.cc")
+AO_LIB = os.path.join(HERE, "lib", "libao3c_host_baseline.so")
+
+
+def _ao_lib():
+    """g++ build of the CPU port of the AO-integral code (tests/host_harness/ao3c_host.cc: the McMurchie-Davidson
+    source of votca_b200/csrc/ao3c_core.cuh compiled for the host), the stand-in for the reference's libint calls
+    (ComputeAO3cBlock, libint2_calls.cc:544-593) in the CPU baseline."""
+    if not os.path.exists(AO_LIB) or os.path.getmtime(AO_LIB) < os.path.getmtime(AO_SRC):
+        os.makedirs(os.path.dirname(AO_LIB), exist_ok=True)
+        subprocess.run(["g++", "-std=c++20", "-O2", "-march=native", "-fPIC", "-shared", "-pthread", "-o", AO_LIB, AO_SRC],
+                       check=True)
+    lib = ctypes.CDLL(AO_LIB)
+    p, i = ctypes.c_void_p, ctypes.c_int
+    lib.ao3c_range_host.argtypes = [i, p, p, p, p, p, i, p, p, p, p, p, i, i, ctypes.c_long, p]
+    return lib
+
+
+def ao_integral_stage(system_name, sample_scale=1.0):
+    """Seconds for all (P|mu nu) of a tier-R system on every host core: each thread computes a few aux functions
+    (the reference parallelises over aux shells, libint2_calls.cc:621-622); the fixed cost of a call (primitive-pair
+    tables) is measured with an empty range and taken out."""
+    import threading
+    from votca_b200 import realsys
+    s = realsys.system(system_name)
+    lib = _ao_lib()
+    N, naux = s["nbasis"], s["naux"]
+    cores = os.cpu_count() or 1
+    nf = max(1, int(round(0.25 * sample_scale * 1860.0 * 1860.0 / (N * N))))  # ~0.2 s of work per thread
+    args = [len(s["dft"][0])] + [a.ctypes.data for a in s["dft"]] + [len(s["aux"][0])] + [a.ctypes.data for a in s["aux"]]
+    bufs = [np.empty((nf, N, N)) for _ in range(cores)]
+
+    def run(n_functions):
+        def work(t):
+            f0 = (t * 37 * nf) % max(1, naux - nf)
+            lib.ao3c_range_host(*args, f0, f0 + n_functions, 0, bufs[t].ctypes.data)
+        th = [threading.Thread(target=work, args=(t,)) for t in range(cores)]
+        t0 = time.perf_counter()
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        return time.perf_counter() - t0
+    t_empty = min(run(0), run(0))
+    t_full = run(nf)
+    work_s = max(t_full - t_empty, 1e-6)
+    return {"sample_s": work_s, "sample": f"{cores} threads x {nf} of {naux} aux functions (C++ port of the integral "
+            f"code, call overhead {t_empty:.2f} s taken out)", "factor": naux / float(cores * nf)}
+
+
+def estimate(nbasis, naux, homo, counts, seed=7, sample_scale=1.0, ao_system=None):
     """Returns dict(total_seconds, stages={...}) for a G0W0/evGW(ppm) + BSE(TDA singlets) run.
 
     counts: iteration counts of the run being mirrored (taken from the GPU run so both arms do the same
@@ -224,6 +274,8 @@ def estimate(nbasis, naux, homo, counts, seed=7, sample_scale=1.0):
     stages["bse_hx_blocks"] = {"sample_s": _best(bse_hx), "sample": f"{nblk} of {vt * (vt + 1) // 2} (v1,v2) blocks",
                                "factor": vt * (vt + 1) / 2 / nblk * dav}
 
+    if ao_system:
+        stages["ao_integrals"] = ao_integral_stage(ao_system, sample_scale / 24.0)
     total = sum(s["sample_s"] * s["factor"] for s in stages.values())
     sampled = sum(s["sample_s"] for s in stages.values())
 

@@ -439,6 +439,10 @@ class Job:
         """Write the results as an .orb (HDF5) checkpoint at the end of run()."""
         self._ck(self.api.gwbse_job_set_orb_output(self.h, str(path).encode() if path else None))
 
+    def set_summary_output(self, path):
+        """Write <job>_summary.xml (GWBSE::addoutput) at the end of run()."""
+        self._ck(self.api.gwbse_job_set_summary_output(self.h, str(path).encode() if path else None))
+
     def run(self):
         self._ck(self.api.gwbse_job_run(self.h))
 

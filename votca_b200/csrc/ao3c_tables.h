@@ -8,6 +8,7 @@
 // (aoshell.cc:116-133), cartesian components in libint's standard order (lx descending, then ly descending).
 #pragma once
 #include <algorithm>
+#include <cstdlib>
 #include <cmath>
 #include <cstdint>
 #include <stdexcept>
@@ -246,12 +247,26 @@ struct LaunchConfig {
   size_t smem_bytes;
   bool fits;
 };
+inline int lane_div() {
+  static const int d = [] {
+    const char* e = std::getenv("GWBSE_AO3C_LANEDIV");
+    const int v = e ? std::atoi(e) : 4;
+    return v < 1 ? 1 : v;
+  }();
+  return d;
+}
+
 inline LaunchConfig launch_config(int la, int lb, int lc, size_t smem_limit) {
   LaunchConfig c{};
   c.ws_doubles = workspace_doubles(la, lb, lc);
   const int Lab = la + lb;
   const int width = std::max({ncart(la) * ncart(lb) * ncart(lc), nherm(Lab) * ncart(lc), nherm(Lab + lc)});
-  c.group_lanes = width <= 4 ? 4 : width <= 8 ? 8 : width <= 16 ? 16 : 32;
+  // lanes per shell triple: the widest stage divided by lane_div() (rounded up to a power of two).  One lane per
+  // entry of the widest stage minimises the rounds of a triple but leaves most lanes idle in the narrow stages (the
+  // R recursion has nh(L - n) entries at level n); the arithmetic is throughput bound at fixed occupancy, so a
+  // group takes a few rounds per stage and a warp carries more triples.
+  const int target = (width + lane_div() - 1) / lane_div();
+  c.group_lanes = target <= 1 ? 1 : target <= 2 ? 2 : target <= 4 ? 4 : target <= 8 ? 8 : target <= 16 ? 16 : 32;
   c.groups_per_warp = 32 / c.group_lanes;
   const size_t per_warp = sizeof(double) * (size_t)c.ws_doubles * c.groups_per_warp;
   c.warps_per_cta = 8;

@@ -8,6 +8,7 @@
 // so that each class gets the shared-memory scratch - and therefore the occupancy - of its own size.  The
 // arithmetic is ao3c_core.cuh (shared with the CPU harness).
 #include <algorithm>
+#include <cstdlib>
 #include <map>
 #include <memory>
 #include <vector>
@@ -36,7 +37,11 @@ struct GroupBarrierFactory {
 // group_lanes lanes per (shell pair, aux shell): 32 for the wide classes, fewer for classes whose widest stage has
 // only a handful of entries ((ss|s) has one) so that a warp carries several triples instead of idling 31 lanes.
 // The indexing lives in ao::cta_thread (shared with the CPU harness).
-__global__ void __launch_bounds__(256)
+// MINB: resident CTAs per SM the register allocation is sized for.  The arithmetic is latency bound (dependent
+// recursions through shared memory), so classes whose scratch leaves room run four CTAs of 64-register threads
+// instead of two of 128 (a few spilled index registers against twice the warps in flight).
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB)
     ao3c_kernel(ao::BasisView dft, ao::BasisView aux, ao::TableView tb, const ao::PairEntry* __restrict__ pairs,
                 long long npairs, const double* __restrict__ pool, const int* __restrict__ aux_shells, int naux_shells,
                 ao::OutSpec out, int ws_doubles, int group_lanes) {
@@ -164,7 +169,8 @@ int shared_memory_limit(gwbse_ctx* ctx) {
   GW_CUDA(cudaDeviceGetAttribute(&smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
   static int smem_set = -1;
   if (smem_set != smem_limit) {
-    GW_CUDA(cudaFuncSetAttribute(ao3c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit));
+    GW_CUDA(cudaFuncSetAttribute(ao3c_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit));
+    GW_CUDA(cudaFuncSetAttribute(ao3c_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit));
     smem_set = smem_limit;
   }
   return smem_limit;
@@ -180,9 +186,21 @@ void launch_class(gwbse_ctx* ctx, const gwbse_basis& orb, const gwbse_basis::Pai
   const long long per_cta = (long long)cfg.warps_per_cta * cfg.groups_per_warp;
   const long long blocks = (groups + per_cta - 1) / per_cta;
   GW_REQUIRE(blocks < (1LL << 31), "too many shell triples for one launch; use smaller aux blocks");
-  ao3c_kernel<<<(unsigned)blocks, cfg.warps_per_cta * 32, cfg.smem_bytes, ctx->stream>>>(
-      orb.view, aux.view, device_tables(ctx->device), pc.dev, pc.count, pc.pool, aux_shells_dev, n_aux_shells, out,
-      cfg.ws_doubles, cfg.group_lanes);
+  // region profiler: one line per angular-momentum class (set_option "profile")
+  char cls[32];
+  std::snprintf(cls, sizeof(cls), "ao3c (%d %d|%d)", pc.la, pc.lb, lc);
+  GW_PROF(ctx, cls);
+  // four CTAs per SM when threads and scratch allow it (1 KB per CTA is reserved by the driver)
+  static const bool force2 = [] { const char* e = std::getenv("GWBSE_AO3C_MINB2"); return e && e[0] == '1'; }();
+  const bool four = !force2 && (size_t)(cfg.smem_bytes + 1024) * 4 <= (size_t)smem_limit + 1024;
+  if (four)
+    ao3c_kernel<4><<<(unsigned)blocks, cfg.warps_per_cta * 32, cfg.smem_bytes, ctx->stream>>>(
+        orb.view, aux.view, device_tables(ctx->device), pc.dev, pc.count, pc.pool, aux_shells_dev, n_aux_shells, out,
+        cfg.ws_doubles, cfg.group_lanes);
+  else
+    ao3c_kernel<2><<<(unsigned)blocks, cfg.warps_per_cta * 32, cfg.smem_bytes, ctx->stream>>>(
+        orb.view, aux.view, device_tables(ctx->device), pc.dev, pc.count, pc.pool, aux_shells_dev, n_aux_shells, out,
+        cfg.ws_doubles, cfg.group_lanes);
   GW_CUDA(cudaGetLastError());
   ctx->launches++;
 }

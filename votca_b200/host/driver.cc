@@ -66,6 +66,7 @@ struct gwbse_job {
   // set again: they are inputs resident in HBM, not results
   std::unique_ptr<DeviceAOBasis> dev_basis[2];
   std::string orb_path;  // gwbse_job_set_orb_output: results are written there at the end of gwbse_job_run
+  std::string summary_path;  // gwbse_job_set_summary_output: <job>_summary.xml of the dftgwbse tool
   std::string err;
   mutable std::string logcache;
 };
@@ -217,6 +218,12 @@ int gwbse_job_set_orb_output(gwbse_job* job, const char* path) {
   JOB_END(job)
 }
 
+int gwbse_job_set_summary_output(gwbse_job* job, const char* path) {
+  JOB_BEGIN(job)
+  job->summary_path = path ? path : "";
+  JOB_END(job)
+}
+
 void* gwbse_job_ctx(gwbse_job* job) { return job ? job->dev->ctx() : nullptr; }
 
 int gwbse_job_run(gwbse_job* job) {
@@ -275,6 +282,9 @@ int gwbse_job_run(gwbse_job* job) {
   gwbse.Initialize(job->options, in);
   GWBSE::Results r = gwbse.Evaluate();
   if (!job->orb_path.empty() && job->dev->rank() == 0) gwbse.WriteToCpt(r, job->orb_path);
+  if (!job->summary_path.empty() && job->dev->rank() == 0)
+    gwbse.WriteSummaryXML(r, job->summary_path,
+                          job->scalars.count("dft_total_energy") ? job->scalars["dft_total_energy"] : 0.0);
   auto& o = job->out;
   o.clear();
   o["RPA_inputenergies"] = vec2mat(r.RPA_inputenergies);

@@ -473,6 +473,63 @@ class GWBSE {
     return out;
   }
 
+  // GWBSE::addoutput (gwbse.cc:580-738) as the dftgwbse tool writes it to <job>_summary.xml
+  // (tools/dftgwbse.cc:120-128: the "output" property, tab-indented, attributes in alphabetical order; energies in
+  // eV with boost::format("%+1.6f ")).  dft_total_energy: Orbitals::getDFTTotalEnergy() in Hartree.
+  void WriteSummaryXML(const Results& r, const std::string& filename, double dft_total_energy) const {
+    const double hrt2ev = 27.21138602;  // tools::conv::hrt2ev, tools/include/votca/tools/constants.h:53
+    auto ev = [&](double x) {
+      char b[48];
+      std::snprintf(b, sizeof(b), "%+1.6f ", x * hrt2ev);
+      return std::string(b);
+    };
+    std::ofstream f(filename);
+    if (!f) throw std::runtime_error("cannot write summary file " + filename);
+    f << "<output>\n";
+    if (do_gw_) {
+      f << "\t<GWBSE DFTEnergy=\"" << ev(dft_total_energy) << "\" units=\"eV\">\n";
+      f << "\t\t<dft HOMO=\"" << gwopt_.homo << "\" LUMO=\"" << gwopt_.homo + 1 << "\">\n";
+      for (Index state = 0; state < gwopt_.qpmax + 1 - gwopt_.qpmin; ++state) {
+        f << "\t\t\t<level number=\"" << state + gwopt_.qpmin << "\">\n";
+        f << "\t\t\t\t<dft_energy>" << ev((*in_.mo_energies)(state + gwopt_.qpmin)) << "</dft_energy>\n";
+        f << "\t\t\t\t<gw_energy>" << ev(r.QPpert_energies(state)) << "</gw_energy>\n";
+        f << "\t\t\t\t<qp_energy>" << ev(r.QPdiag_eigenvalues(state)) << "</qp_energy>\n";
+        f << "\t\t\t</level>\n";
+      }
+      f << "\t\t</dft>\n";
+    } else {
+      f << "\t<GWBSE>\n";
+    }
+    if (do_bse_singlets_) {
+      f << "\t\t<singlets>\n";
+      for (Index state = 0; state < std::min<Index>(bseopt_.nmax, r.BSE_singlet.eigenvalues.size()); ++state) {
+        f << "\t\t\t<level number=\"" << state + 1 << "\">\n";
+        f << "\t\t\t\t<omega>" << ev(r.BSE_singlet.eigenvalues(state)) << "</omega>\n";
+        if (static_cast<size_t>(state) < r.transition_dipoles.size()) {
+          const VectorXd& d = r.transition_dipoles[static_cast<size_t>(state)];
+          const double fosc = 2 * (d(0) * d(0) + d(1) * d(1) + d(2) * d(2)) * r.BSE_singlet.eigenvalues(state) / 3.0;
+          char b[96];
+          std::snprintf(b, sizeof(b), "%+1.6f ", fosc);
+          f << "\t\t\t\t<f>" << b << "</f>\n";
+          std::snprintf(b, sizeof(b), "%+1.4f %+1.4f %+1.4f", d(0), d(1), d(2));
+          f << "\t\t\t\t<Trdipole gauge=\"length\" unit=\"e*bohr\">" << b << "</Trdipole>\n";
+        }
+        f << "\t\t\t</level>\n";
+      }
+      f << "\t\t</singlets>\n";
+    }
+    if (do_bse_triplets_) {
+      f << "\t\t<triplets>\n";
+      for (Index state = 0; state < std::min<Index>(bseopt_.nmax, r.BSE_triplet.eigenvalues.size()); ++state) {
+        f << "\t\t\t<level number=\"" << state + 1 << "\">\n";
+        f << "\t\t\t\t<omega>" << ev(r.BSE_triplet.eigenvalues(state)) << "</omega>\n";
+        f << "\t\t\t</level>\n";
+      }
+      f << "\t\t</triplets>\n";
+    }
+    f << "\t</GWBSE>\n</output>\n";
+  }
+
   // The GW-BSE part of Orbitals::WriteToCpt (orbitals.cc:990-1063): same group (/QMdata), names and HDF5 types
   // for everything this stage reads or produces.  DFT-side members (atoms, basis-set tables, XC functional ...)
   // belong to the Orbitals object of the caller and are not written.
