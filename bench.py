@@ -53,7 +53,9 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="dcv5t-tzvp")
     ap.add_argument("--mode", default=None, choices=["evGW", "G0W0"])
-    ap.add_argument("--also", default="", help="second workload measured with 1 warm-up + 2 steps (reported under 'also')")
+    ap.add_argument("--also", default="auto",
+                    help="second workload measured with 1 warm-up + 2 steps and reported under 'also' "
+                         "(auto: c60-tzvp beside the default dcv5t-tzvp headline, none otherwise; '' switches it off)")
     ap.add_argument("--e2e-steps", type=int, default=3, help="upper bound on the timed steps of the end-to-end arm")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -61,6 +63,8 @@ def parse_args():
     a = ap.parse_args()
     if a.mode is None:
         a.mode = DEFAULT_MODE.get(a.workload, "evGW")
+    if a.also == "auto":
+        a.also = "c60-tzvp" if a.workload == "dcv5t-tzvp" else ""
     return a
 
 
@@ -520,8 +524,16 @@ class Bench:
         return dev
 
 
-def summarize(rec):
+def summarize(rec, with_cpu):
     """Nested record of a secondary workload."""
+    cpu = None
+    if with_cpu:
+        from oracle import cpu_baseline
+        est = cpu_baseline.estimate(rec["N"], rec["naux"], rec["homo"], rec["counts"], sample_scale=12.0,
+                                    ao_system=rec["workload"] if rec["workload"] in TIER_R else None)
+        cpu = {"value": est["total_seconds"], "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "extrapolated": True,
+               "stages": {k: round(s["sample_s"] * s["factor"], 3) for k, s in est["stages"].items()},
+               "factorised": est["factorised_total_seconds"]}
     out = {"value": rec["ms_per_step"] / 1e3, "unit": UNIT, "steps": rec["steps"], "warmup": rec["warmup"],
            "config": {"workload": workload_name(rec["workload"], rec["mode"], rec["N"], rec["naux"], rec["homo"]),
                       "mode": rec["mode"], "gw_iterations": rec["counts"]["gw_iterations"],
@@ -529,7 +541,7 @@ def summarize(rec):
                       "stage_seconds": rec["stage_seconds"]},
            "tflops": rec["total_flops"] / (rec["ms_per_step"] * 1e-3) / 1e12,
            "gemm_tflops": rec["gemm_tflops"], "gemm_frac_of_peak": rec["gemm_tflops"] / rec["peak"] if rec["peak"] else None,
-           "e2e": rec["e2e"]}
+           "e2e": rec["e2e"], "gpu_launches": rec["launches"], "cpu_baseline": cpu}
     return out
 
 
@@ -609,7 +621,7 @@ def make_line(args, rec, also, parity, world):
     if parity is not None:
         line["sharded_vs_single"] = parity
     if also is not None:
-        line["also"] = summarize(also)
+        line["also"] = summarize(also, not args.no_cpu and world == 1)
     # iteration counts for the CPU arm (copied into votca_b200/data/bench_counts.json by the maintainer)
     try:
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)

@@ -530,19 +530,41 @@ class GWBSE {
     f << "\t</GWBSE>\n</output>\n";
   }
 
-  // The GW-BSE part of Orbitals::WriteToCpt (orbitals.cc:990-1063): same group (/QMdata), names and HDF5 types
-  // for everything this stage reads or produces.  DFT-side members (atoms, basis-set tables, XC functional ...)
-  // belong to the Orbitals object of the caller and are not written.
+  // The GW-BSE part of Orbitals::WriteToCpt (orbitals.cc:990-1063): same group (/QMdata), names and HDF5 types for
+  // everything this stage reads or produces, and the scalar / empty members of an Orbitals object that has no
+  // unrestricted, embedding or localised-orbital data (defaults of orbitals.h).  NOT written: the compound tables of
+  // the DFT side - qmmolecule (atoms), dft / aux (basis shells) - which belong to the caller's Orbitals object.
+  // Orbitals::ReadFromCpt opens "qmmolecule" unconditionally (orbitals.cc:1093-1094), so this file alone is a results
+  // dump (read it with any HDF5 tool, or merge it into the .orb of the DFT run); in an integrated build the
+  // reference's own CheckpointWriter serialises the Orbitals object the shim fills.
   void WriteToCpt(const Results& r, const std::string& filename) const {
     CheckpointFile cpf(filename);
     CheckpointWriter w = cpf.getWriter("/QMdata");
     w(std::string("gwbse-b200"), "XTPVersion");
     w(int(9), "version");  // Orbitals::orbitals_version(), orbitals.h:844
     w(long(in_.homo + 1), "occupied_levels");
+    w(long(in_.homo + 1), "occupied_levels_beta");
     w(long(in_.homo + 1), "number_alpha_electrons");
     w(long(in_.homo + 1), "number_beta_electrons");
+    w(long(0), "charge");
+    w(long(1), "spin");
     const MatrixXd none;
+    const VectorXd nov;
     w.WriteEigenSystem(*in_.mo_energies, *in_.mos, none, 0, "mos");
+    w.WriteEigenSystem(nov, none, none, 0, "mos_beta");
+    w(nov, "occupations");
+    w(long(0), "active_electrons");
+    w.WriteEigenSystem(nov, none, none, 0, "mos_embedding");
+    w(none, "LMOs");
+    w(nov, "LMOs_energies");
+    w(none, "inactivedensity");
+    w(none, "TruncMOsFullBasis");
+    w(0.0, "qm_energy");
+    w(std::string("gwbse-b200"), "qm_package");
+    w(std::string(""), "XCFunctional");
+    w(std::string("medium"), "XC_grid_quality");
+    w(std::string(""), "ECP");
+    w(std::string("NoEmbedding"), "CalcType");
     w(long(r.rpamin), "rpamin");
     w(long(r.rpamax), "rpamax");
     w(long(r.qpmin), "qpmin");
@@ -563,6 +585,15 @@ class GWBSE {
     w(std::uint8_t(r.is_qsgw ? 1u : 0u), "is_qsgw");
     w(r.BSE_singlet_dynamic, "BSE_singlet_dynamic");
     w(r.BSE_triplet_dynamic, "BSE_triplet_dynamic");
+    // spin-resolved GW / BSE members (gw_uks, bse_uks): empty on the restricted path
+    w(nov, "RPA_inputenergies_alpha");
+    w(nov, "RPA_inputenergies_beta");
+    w(nov, "QPpert_energies_alpha");
+    w(nov, "QPpert_energies_beta");
+    w.WriteEigenSystem(nov, none, none, 0, "QPdiag_alpha");
+    w.WriteEigenSystem(nov, none, none, 0, "QPdiag_beta");
+    w.WriteEigenSystem(nov, none, none, 0, "BSE_uks");
+    w(nov, "BSE_uks_dynamic");
     cpf.Close();
   }
 
