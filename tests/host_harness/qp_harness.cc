@@ -24,8 +24,6 @@ struct MockFunc {
     return (w - r1) * (w - r2);
   }
   double deriv(double) const { return kind == 1 ? 1.0 : -1.0; }
-  void prefetch(const double*, std::size_t, bool = false) const {}
-  void prefetch(const std::vector<double>&, int) const {}
 };
 struct LegacyOpt {
   Index qp_grid_steps = 0;

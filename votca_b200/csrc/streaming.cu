@@ -2,6 +2,9 @@
 // alignment allows, warp-shuffle reductions.  SURVEY.md section 8a rows a7 (weights),
 // a12/a14 (Sigma_c evaluation), a18 (BSE diagonal), a20 (Davidson corrections).
 #include <cmath>
+#include <cstdint>
+
+#include <cooperative_groups.h>
 
 #include "context.cuh"
 
@@ -95,6 +98,49 @@ __global__ void coldots_kernel(int m, const double* X, long long ldx, const doub
   for (int i = threadIdx.x; i < m; i += blockDim.x) s += x[i] * y[i];
   s = block_sum(s, sh);
   if (threadIdx.x == 0) out[j] = take_sqrt ? sqrt(s) : s;
+}
+
+// Long columns (Davidson vectors: rows = BSE size, 20-30 columns): one CTA per column would leave most SMs idle, so a
+// cluster of COLDOT_CL CTAs shares a column; the partial sums meet in rank 0 through distributed shared memory in a
+// fixed order (no atomics, no scratch buffer: the result depends on m only).
+constexpr int COLDOT_CL = 8;
+
+__global__ void __cluster_dims__(COLDOT_CL, 1, 1) __launch_bounds__(256)
+    coldots_cluster_kernel(int m, const double* X, long long ldx, const double* Y, long long ldy, double* out,
+                           int take_sqrt) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cl = cg::this_cluster();
+  __shared__ double sh[32];
+  __shared__ double part;
+  const int j = blockIdx.x / COLDOT_CL;
+  const int r = (int)cl.block_rank();
+  const double* x = X + j * ldx;
+  const double* y = Y + j * ldy;
+  const int chunk = ((m + COLDOT_CL - 1) / COLDOT_CL + 1) & ~1;  // even: chunk starts keep the column's alignment
+  const int i0 = min(m, r * chunk), i1 = min(m, i0 + chunk);
+  double s0 = 0.0, s1 = 0.0;
+  if ((((uintptr_t)(x + i0) | (uintptr_t)(y + i0)) & 15) == 0) {
+    const int n2 = (i1 - i0) >> 1;
+    const double2* x2 = reinterpret_cast<const double2*>(x + i0);
+    const double2* y2 = reinterpret_cast<const double2*>(y + i0);
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+      const double2 a = x2[i], b = y2[i];
+      s0 += a.x * b.x;
+      s1 += a.y * b.y;
+    }
+    if (threadIdx.x == 0 && ((i1 - i0) & 1)) s0 += x[i1 - 1] * y[i1 - 1];
+  } else {
+    for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) s0 += x[i] * y[i];
+  }
+  const double s = block_sum(s0 + s1, sh);
+  if (threadIdx.x == 0) part = s;
+  cl.sync();
+  if (r == 0 && threadIdx.x == 0) {
+    double t = 0.0;
+    for (int b = 0; b < COLDOT_CL; ++b) t += *cl.map_shared_rank(&part, b);
+    out[j] = take_sqrt ? sqrt(t) : t;
+  }
+  cl.sync();  // no CTA may exit while rank 0 still reads its shared memory
 }
 
 __global__ void scale_cols_kernel(int m, int n, double* A, long long lda, const double* s) {
@@ -337,6 +383,8 @@ __global__ void olsen_finish_kernel(int rows, const double* Q, long long ldq, co
   W[i + j * ldw] = isfinite(v) ? v : 0.0;
 }
 
+constexpr int kColdotClusterRows = 8192;  // below this one CTA per column is latency-optimal
+
 inline dim3 grid2(int m, int n, int bx = 256) { return dim3((m + bx - 1) / bx, n); }
 
 }  // namespace
@@ -371,13 +419,19 @@ void launch_axpy(int m, int n, double alpha, const double* X, long long ldx, dou
 }
 void launch_colnorms(int m, int n, const double* A, long long lda, double* out_dev, cudaStream_t s) {
   if (n <= 0) return;
-  coldots_kernel<<<n, 256, 0, s>>>(m, A, lda, A, lda, out_dev, 1);
+  if (m >= kColdotClusterRows)
+    coldots_cluster_kernel<<<n * COLDOT_CL, 256, 0, s>>>(m, A, lda, A, lda, out_dev, 1);
+  else
+    coldots_kernel<<<n, 256, 0, s>>>(m, A, lda, A, lda, out_dev, 1);
   GW_CUDA(cudaGetLastError());
 }
 void launch_coldots(int m, int n, const double* X, long long ldx, const double* Y, long long ldy, double* out_dev,
                     cudaStream_t s) {
   if (n <= 0) return;
-  coldots_kernel<<<n, 256, 0, s>>>(m, X, ldx, Y, ldy, out_dev, 0);
+  if (m >= kColdotClusterRows)
+    coldots_cluster_kernel<<<n * COLDOT_CL, 256, 0, s>>>(m, X, ldx, Y, ldy, out_dev, 0);
+  else
+    coldots_kernel<<<n, 256, 0, s>>>(m, X, ldx, Y, ldy, out_dev, 0);
   GW_CUDA(cudaGetLastError());
 }
 void launch_scale_cols(int m, int n, double* A, long long lda, const double* s_dev, cudaStream_t s) {

@@ -1,16 +1,12 @@
-// GW - host mirror of xtp/include/votca/xtp/gw.h:37-300 and xtp/src/libxtp/gwbse/gw.cc:35-78,210-776
-// (G0W0 / evGW; QSGW is outside the BASELINE configs).  Control flow (iteration order, mixing, convergence,
-// root selection) is kept; what changes is how Sigma_c is evaluated: the per-level QP searches run on host
-// threads exactly as in the reference's `omp parallel for` (gw.cc:344), but their Sigma_c requests are
-// collected by a batcher and served by ONE batched kernel pass per round instead of one Eigen loop each.
+// GW - host mirror of xtp/include/votca/xtp/gw.h:37-300 and xtp/src/libxtp/gwbse/gw.cc:35-78,210-1130
+// (G0W0 / evGW / QSGW).  Iteration order, mixing, convergence and root selection give the reference's results; what
+// changes is how Sigma_c is evaluated: the per-level QP searches (the reference's `omp parallel for`, gw.cc:344) are
+// resumable objects (qp_rootsearch.h) advanced in lock step, so every round of all searches is ONE grouped kernel
+// pass over the Mmn slices instead of one Eigen loop per level and frequency.
 #pragma once
-#include <condition_variable>
 #include <cstring>
 #include <limits>
-#include <mutex>
-#include <thread>
-#include <unordered_map>
-#include <unordered_set>
+#include <memory>
 
 #include "anderson_mixing.h"
 #include "qp_rootsearch.h"
@@ -19,92 +15,6 @@
 namespace votca {
 namespace xtp {
 
-
-// Collects Sigma_c requests of the concurrently running per-level searches into batches.  A request is one
-// level with a SET of frequencies (the one needed now plus the ones the search is known to need next), so
-// the kernel streams the level's data once for all of them.
-class SigmaBatcher {
- public:
-  explicit SigmaBatcher(const Sigma_base& sigma) : sigma_(sigma) {}
-
-  // called by worker threads: evaluates Sigma_c (and d/dw if want_deriv) at freqs for this level
-  void Evaluate(Index level, const std::vector<double>& freqs, bool want_deriv, std::vector<double>& s,
-                std::vector<double>& ds) {
-    std::unique_lock<std::mutex> lk(mu_);
-    Request r{(int)level, &freqs, want_deriv, &s, &ds, false};
-    queue_.push_back(&r);
-    cv_server_.notify_one();
-    cv_workers_.wait(lk, [&] { return r.done; });
-    if (!error_.empty()) throw std::runtime_error(error_);
-  }
-  void WorkerStarted() {
-    std::lock_guard<std::mutex> lk(mu_);
-    ++running_;
-  }
-  void WorkerFinished() {
-    std::lock_guard<std::mutex> lk(mu_);
-    --running_;
-    cv_server_.notify_one();
-  }
-  // run on the calling thread until all workers have finished
-  void Serve() {
-    std::unique_lock<std::mutex> lk(mu_);
-    while (true) {
-      cv_server_.wait(lk, [&] { return running_ == 0 || (Index)queue_.size() == running_; });
-      if (running_ == 0 && queue_.empty()) return;
-      std::vector<Request*> batch;
-      batch.swap(queue_);
-      std::vector<int> lv(batch.size()), gp(batch.size() + 1, 0);
-      std::vector<double> fr, s, ds;
-      bool any_deriv = false;
-      for (size_t i = 0; i < batch.size(); ++i) {
-        lv[i] = batch[i]->level;
-        fr.insert(fr.end(), batch[i]->freqs->begin(), batch[i]->freqs->end());
-        gp[i + 1] = (int)fr.size();
-        any_deriv = any_deriv || batch[i]->want_deriv;
-      }
-      lk.unlock();
-      try {
-        sigma_.EvalGroups(lv, gp, fr, s, any_deriv ? &ds : nullptr);
-      } catch (const std::exception& e) {
-        error_ = e.what();
-        s.assign(fr.size(), 0.0);
-        ds.assign(fr.size(), 0.0);
-      }
-      lk.lock();
-      ++batches_;
-      evaluations_ += fr.size();
-      for (size_t i = 0; i < batch.size(); ++i) {
-        batch[i]->s->assign(s.begin() + gp[i], s.begin() + gp[i + 1]);
-        if (any_deriv)
-          batch[i]->ds->assign(ds.begin() + gp[i], ds.begin() + gp[i + 1]);
-        else
-          batch[i]->ds->clear();
-        batch[i]->done = true;
-      }
-      cv_workers_.notify_all();
-    }
-  }
-  std::size_t batches() const { return batches_; }
-  std::size_t evaluations() const { return evaluations_; }
-
- private:
-  struct Request {
-    int level;
-    const std::vector<double>* freqs;
-    bool want_deriv;
-    std::vector<double>* s;
-    std::vector<double>* ds;
-    bool done;
-  };
-  const Sigma_base& sigma_;
-  std::mutex mu_;
-  std::condition_variable cv_server_, cv_workers_;
-  std::vector<Request*> queue_;
-  Index running_ = 0;
-  std::size_t batches_ = 0, evaluations_ = 0;
-  std::string error_;
-};
 
 class GW {
   using EvalStage = qp_solver::EvalStage;
@@ -390,96 +300,104 @@ class GW {
   }
 
  private:
-  // f(w) = Sigma_c(w) + offset - w, gw.h:214-300.  Sigma_c requests go through the batcher.  Every value the
-  // GPU returns is cached under the frequency's bit pattern (the key the reference already uses for its
-  // statistics, gw.h:261-267); prefetch() announces frequencies the search will ask for next so that they
-  // ride along with the current request.  The cache only removes round trips: each Sigma_c(w) is computed
-  // by the same kernel arithmetic whether it was prefetched or not.
-  class QPFunc {
+  // The search for one level: f(w) = Sigma_c(w) + offset - w (gw.h:214-300 of the reference) on a tape, and the
+  // ladder of strategies gw.cc:323-410 + :618-757 climbs until one yields a frequency - Newton iteration when
+  // qp_solver=fixedpoint, the shell scan and / or the dense sweep on the window restricted to the physical side of
+  // zero, the dense sweep on the full window, and the linearised estimate as the last resort (not "converged").
+  class LevelSearch {
    public:
-    QPFunc(Index gw_level, SigmaBatcher& batcher, double offset)
-        : gw_level_(gw_level), offset_(offset), batcher_(batcher) {}
-    std::pair<double, double> operator()(double frequency) const {
-      Count(frequency, EvalStage::Other);
-      ++stats_.deriv_calls;
-      const Entry& e = Fetch(frequency, true);
-      return {e.s + offset_ - frequency, e.ds - 1.0};
-    }
-    double sigma(double frequency, EvalStage stage = EvalStage::Other) const {
-      Count(frequency, stage);
-      return Fetch(frequency, false).s;
-    }
-    double value(double frequency, EvalStage stage = EvalStage::Other) const {
-      return sigma(frequency, stage) + offset_ - frequency;
-    }
-    double deriv(double frequency) const {
-      ++stats_.deriv_calls;
-      return Fetch(frequency, true).ds - 1.0;
-    }
-    // hint: these frequencies will be requested soon (with_deriv: value and derivative)
-    void prefetch(const double* freqs, std::size_t n, bool with_deriv = false) const {
-      for (std::size_t i = 0; i < n; ++i) {
-        auto it = cache_.find(Key(freqs[i]));
-        if (it != cache_.end() && (!with_deriv || it->second.has_ds)) continue;
-        pending_.push_back(freqs[i]);
-        pending_deriv_ = pending_deriv_ || with_deriv;
+    LevelSearch(Index gw_level, double offset, double frequency0, const options& opt, Index gw_iteration)
+        : level_(gw_level), offset_(offset), w0_(frequency0) {
+      qp_solver::SolverOptions so;
+      so.g_sc_limit = opt.g_sc_limit;
+      so.qp_bisection_max_iter = opt.g_sc_max_iterations;
+      so.qp_full_window_half_width = opt.qp_full_window_half_width;
+      so.qp_dense_spacing = opt.qp_dense_spacing;
+      so.qp_adaptive_shell_width = opt.qp_adaptive_shell_width;
+      so.qp_adaptive_shell_count = opt.qp_adaptive_shell_count;
+      const bool brent = opt.qp_root_finder == "brent";
+      const std::string& mode = opt.qp_grid_search_mode;
+      const bool shells = mode == "adaptive" || mode == "adaptive_with_dense_fallback";
+      const bool sweep = mode == "dense" || mode == "adaptive_with_dense_fallback";
+      if (!shells && !sweep) throw std::runtime_error("Unknown gw.qp_grid_search_mode '" + mode + "'");
+      if (opt.qp_solver == "fixedpoint")
+        ladder_.push_back(std::make_unique<qp_solver::NewtonHunt>(w0_, opt.g_sc_max_iterations, opt.g_sc_limit,
+                                                                  opt.qp_solver_alpha));
+      // the window, and its part on the physical side of zero (occupied below -margin, virtual above the floor)
+      const double lo = w0_ - opt.qp_full_window_half_width, hi = w0_ + opt.qp_full_window_half_width;
+      double rlo = lo, rhi = hi;
+      if (opt.qp_restrict_search) {
+        if (gw_level + opt.qpmin <= opt.homo)
+          rhi = std::min(hi, -opt.qp_zero_margin);
+        else
+          rlo = std::max(lo, opt.qp_virtual_min_energy);
+      }
+      const bool restricted = (std::abs(rlo - lo) > 1e-12 || std::abs(rhi - hi) > 1e-12) && rlo < rhi;
+      auto window = [&](double a, double b, bool allow_rejected) {
+        if (shells)
+          ladder_.push_back(std::make_unique<qp_solver::ShellHunt>(w0_, a, b, gw_iteration, so, brent, allow_rejected));
+        if (sweep) ladder_.push_back(std::make_unique<qp_solver::SweepHunt>(w0_, a, b, so, brent, allow_rejected));
+      };
+      if (restricted) {
+        window(rlo, rhi, false);
+        ladder_.push_back(std::make_unique<qp_solver::SweepHunt>(w0_, lo, hi, so, brent, true));
+      } else {
+        window(lo, hi, true);
       }
     }
-    const QPStats& GetStats() const { return stats_; }
+
+    // true when the level is settled; otherwise `ask` holds the frequencies the current rung is blocked on
+    bool advance(qp_solver::Ask& ask) {
+      while (rung_ < ladder_.size()) {
+        if (!ladder_[rung_]->advance(tape_, ask)) return false;
+        if (ladder_[rung_]->root()) {
+          answer_ = ladder_[rung_]->root();
+          converged_ = true;
+          return true;
+        }
+        ++rung_;
+      }
+      // gw.cc:412-431: w = w0 + (offset - w0 + Sigma_c(w0)) / Z.  The reference forms Z = 1 - fqp.deriv(w0) with
+      // fqp.deriv = dSigma_c/dw - 1, i.e. Z = 2 - dSigma_c/dw; kept as it is (results must match the reference's)
+      const qp_solver::Sample* s = tape_.find(w0_, true);
+      if (!s) {
+        ask.want(tape_, w0_, true);
+        ask.stage = EvalStage::Other;
+        return false;
+      }
+      const double Z = 1.0 - s->df;
+      if (std::abs(Z) > 1e-9) answer_ = w0_ + (offset_ - w0_ + s->sigma) / Z;
+      return true;
+    }
+    // Sigma_c (and dSigma_c/dw when ds != nullptr) at the frequencies of the last ask
+    void absorb(const qp_solver::Ask& ask, const double* s, const double* ds) {
+      for (std::size_t i = 0; i < ask.w.size(); ++i) {
+        qp_solver::Sample smp;
+        smp.sigma = s[i];
+        smp.f = s[i] + offset_ - ask.w[i];
+        if (ds) {
+          smp.dsigma = ds[i];
+          smp.df = ds[i] - 1.0;
+          smp.has_slope = true;
+        }
+        tape_.record(ask.w[i], smp);
+      }
+      stats_.Tally(ask.stage, ask.w.size(), ds != nullptr);
+    }
+    Index level() const { return level_; }
+    const std::optional<double>& answer() const { return answer_; }
+    bool converged() const { return converged_; }
+    const QPStats& stats() const { return stats_; }
 
    private:
-    struct Entry {
-      double s = 0.0, ds = 0.0;
-      bool has_ds = false;
-    };
-    static std::uint64_t Key(double x) {
-      std::uint64_t key = 0;
-      std::memcpy(&key, &x, sizeof(double));
-      return key;
-    }
-    const Entry& Fetch(double frequency, bool need_deriv) const {
-      auto it = cache_.find(Key(frequency));
-      if (it != cache_.end() && (!need_deriv || it->second.has_ds)) return it->second;
-      std::vector<double> fr;
-      fr.push_back(frequency);
-      std::unordered_set<std::uint64_t> in_req{Key(frequency)};
-      for (double f : pending_)
-        if (in_req.insert(Key(f)).second && fr.size() < 96) fr.push_back(f);
-      const bool want = need_deriv || pending_deriv_;
-      pending_.clear();
-      pending_deriv_ = false;
-      std::vector<double> s, ds;
-      batcher_.Evaluate(gw_level_, fr, want, s, ds);
-      for (std::size_t i = 0; i < fr.size(); ++i) {
-        Entry& e = cache_[Key(fr[i])];
-        e.s = s[i];
-        if (!ds.empty()) {
-          e.ds = ds[i];
-          e.has_ds = true;
-        }
-      }
-      return cache_[Key(frequency)];
-    }
-    void Count(double x, EvalStage stage) const {
-      if (!seen_frequencies_.insert(Key(x)).second)
-        ++stats_.sigma_repeat_calls;
-      else
-        ++stats_.sigma_unique_frequencies;
-      switch (stage) {
-        case EvalStage::Scan: ++stats_.sigma_scan_calls; break;
-        case EvalStage::Refine: ++stats_.sigma_refine_calls; break;
-        case EvalStage::Derivative: ++stats_.sigma_derivative_calls; break;
-        default: ++stats_.sigma_other_calls; break;
-      }
-    }
-    Index gw_level_;
-    double offset_;
-    SigmaBatcher& batcher_;
-    mutable std::unordered_map<std::uint64_t, Entry> cache_;
-    mutable std::vector<double> pending_;
-    mutable bool pending_deriv_ = false;
-    mutable std::unordered_set<std::uint64_t> seen_frequencies_;
-    mutable QPStats stats_;
+    Index level_;
+    double offset_, w0_;
+    std::vector<std::unique_ptr<qp_solver::Hunt>> ladder_;
+    std::size_t rung_ = 0;
+    qp_solver::Tape tape_;
+    std::optional<double> answer_;
+    bool converged_ = false;
+    QPStats stats_;
   };
 
   MatrixXd qsgw_rotation_;
@@ -508,61 +426,59 @@ class GW {
     return !(diff_max > epsilon);
   }
 
-  // gw.cc:323-410: one host thread per level (the reference's dynamic OpenMP loop), batched Sigma_c
+  // gw.cc:323-410.  The reference runs one OpenMP task per level, each calling Sigma_c point by point; here the
+  // searches of all levels this rank owns advance together and every round is ONE grouped kernel call
+  // (Sigma_base::EvalGroups: a level's Mmn slice is streamed once for all of its frequencies).
   VectorXd SolveQP(const VectorXd& frequencies) {
     sigma_->ResetDiagEvalCounter();
-    VectorXd intercepts(qptotal_);
-    for (Index i = 0; i < qptotal_; ++i)
-      intercepts(i) = dft_energies_(opt_.qpmin + i) + Sigma_x_(i, i) - vxc_(i, i);
+    const Device& dev = Mmn_.device();
+    std::vector<LevelSearch> searches;
+    for (Index gw_level = 0; gw_level < qptotal_; ++gw_level)
+      if (sigma_->OwnsLevel(gw_level))  // multi-GPU: the rank that holds the level's Mmn slice searches its root
+        searches.emplace_back(gw_level, dft_energies_(opt_.qpmin + gw_level) + Sigma_x_(gw_level, gw_level) -
+                                            vxc_(gw_level, gw_level),
+                              frequencies[gw_level], opt_, gw_sc_iteration_);
+    std::vector<qp_solver::Ask> asks(searches.size());
+    std::vector<char> settled(searches.size(), 0);
+    std::size_t rounds = 0, evaluations = 0;
+    for (;;) {
+      std::vector<int> levels, group_ptr{0};
+      std::vector<std::size_t> who;
+      std::vector<double> freqs, s, ds;
+      bool slope = false;
+      for (std::size_t i = 0; i < searches.size(); ++i) {
+        if (settled[i]) continue;
+        asks[i] = qp_solver::Ask();
+        if (searches[i].advance(asks[i])) {
+          settled[i] = 1;
+          continue;
+        }
+        who.push_back(i);
+        levels.push_back((int)searches[i].level());
+        freqs.insert(freqs.end(), asks[i].w.begin(), asks[i].w.end());
+        group_ptr.push_back((int)freqs.size());
+        slope = slope || asks[i].slope;
+      }
+      if (who.empty()) break;
+      sigma_->EvalGroups(levels, group_ptr, freqs, s, slope ? &ds : nullptr);
+      for (std::size_t g = 0; g < who.size(); ++g)
+        searches[who[g]].absorb(asks[who[g]], s.data() + group_ptr[g], slope ? ds.data() + group_ptr[g] : nullptr);
+      ++rounds;
+      evaluations += freqs.size();
+    }
     VectorXd frequencies_new = frequencies;
     std::vector<char> converged(qptotal_, 0);
-    std::vector<QPStats> stats(qptotal_);
-    std::vector<std::string> errors(qptotal_);
-    SigmaBatcher batcher(*sigma_);
-    std::vector<std::thread> workers;
-    workers.reserve(qptotal_);
-    // multi-GPU: every rank searches the roots of the levels whose Mmn slice it owns
-    const Device& dev = Mmn_.device();
-    std::vector<Index> my_levels;
-    for (Index gw_level = 0; gw_level < qptotal_; ++gw_level)
-      if (sigma_->OwnsLevel(gw_level)) my_levels.push_back(gw_level);
-    for (size_t w = 0; w < my_levels.size(); ++w) batcher.WorkerStarted();
-    for (Index gw_level : my_levels) {
-      workers.emplace_back([&, gw_level] {
-        try {
-          double initial_f = frequencies[gw_level];
-          double intercept = intercepts[gw_level];
-          std::optional<double> newf;
-          if (opt_.qp_solver == "fixedpoint")
-            newf = SolveQP_FixedPoint(batcher, intercept, initial_f, gw_level, &stats[gw_level]);
-          if (newf) {
-            frequencies_new[gw_level] = *newf;
-            converged[gw_level] = 1;
-          } else {
-            newf = SolveQP_Grid(batcher, intercept, initial_f, gw_level, &stats[gw_level]);
-            if (newf) {
-              frequencies_new[gw_level] = *newf;
-              converged[gw_level] = 1;
-            } else {
-              newf = SolveQP_Linearisation(batcher, intercept, initial_f, gw_level, &stats[gw_level]);
-              if (newf) frequencies_new[gw_level] = *newf;
-            }
-          }
-        } catch (const std::exception& e) {
-          errors[gw_level] = e.what();
-        }
-        batcher.WorkerFinished();
-      });
+    QPStats total_stats;
+    for (const LevelSearch& ls : searches) {
+      if (ls.answer()) frequencies_new[ls.level()] = *ls.answer();
+      converged[ls.level()] = ls.converged() ? 1 : 0;
+      total_stats.Add(ls.stats());
     }
-    batcher.Serve();
-    for (auto& t : workers) t.join();
-    for (const auto& e : errors)
-      if (!e.empty()) throw std::runtime_error(e);
     if (dev.world() > 1) {
       std::vector<double> pack(2 * qptotal_, 0.0);
-      for (Index gw_level : my_levels) {
-        pack[gw_level] = frequencies_new[gw_level];
-        pack[qptotal_ + gw_level] = converged[gw_level] ? 1.0 : 0.0;
+      for (const LevelSearch& ls : searches) {
+        pack[ls.level()] = frequencies_new[ls.level()];
+        pack[qptotal_ + ls.level()] = converged[ls.level()] ? 1.0 : 0.0;
       }
       dev.allreduce(pack.data(), pack.size());
       for (Index i = 0; i < qptotal_; ++i) {
@@ -570,185 +486,24 @@ class GW {
         converged[i] = pack[qptotal_ + i] > 0.5 ? 1 : 0;
       }
     }
-    QPStats total_stats;
-    for (const auto& s : stats) total_stats.Add(s);
-    sigma_batches_ += batcher.batches();
-    sigma_evaluations_ += batcher.evaluations();
+    sigma_batches_ += rounds;
+    sigma_evaluations_ += evaluations;
     std::string notconv;
-    for (Index s = 0; s < qptotal_; ++s)
-      if (!converged[s]) notconv += " " + std::to_string(s);
+    for (Index lvl = 0; lvl < qptotal_; ++lvl)
+      if (!converged[lvl]) notconv += " " + std::to_string(lvl);
     if (!notconv.empty()) {
       log_(" Not converged PQP states are:" + notconv);
       log_(" Increase the grid search interval");
     }
-    log_(" Sigma diagonal evaluations in SolveQP: " + std::to_string(batcher.evaluations()) + " in " +
-         std::to_string(batcher.batches()) + " batched kernel passes");
+    log_(" Sigma diagonal evaluations in SolveQP: " + std::to_string(evaluations) + " in " + std::to_string(rounds) +
+         " batched kernel passes");
     log_(" QP diagnostics: scan=" + std::to_string(total_stats.sigma_scan_calls) +
          " refine=" + std::to_string(total_stats.sigma_refine_calls) +
          " other=" + std::to_string(total_stats.sigma_other_calls) +
          " total_sigma=" + std::to_string(total_stats.TotalSigmaCalls()) +
          " unique_omega=" + std::to_string(total_stats.sigma_unique_frequencies) +
-         " repeat_sigma=" + std::to_string(total_stats.sigma_repeat_calls) +
          " deriv_calls=" + std::to_string(total_stats.deriv_calls));
     return frequencies_new;
-  }
-
-  qp_solver::SolverOptions MakeSolverOptions() const {
-    qp_solver::SolverOptions s;
-    s.g_sc_limit = opt_.g_sc_limit;
-    s.qp_bisection_max_iter = opt_.g_sc_max_iterations;
-    s.qp_full_window_half_width = opt_.qp_full_window_half_width;
-    s.qp_dense_spacing = opt_.qp_dense_spacing;
-    s.qp_adaptive_shell_width = opt_.qp_adaptive_shell_width;
-    s.qp_adaptive_shell_count = opt_.qp_adaptive_shell_count;
-    return s;
-  }
-
-  // gw.cc:412-431
-  std::optional<double> SolveQP_Linearisation(SigmaBatcher& b, double intercept0, double frequency0, Index gw_level,
-                                              QPStats* stats) const {
-    std::optional<double> newf;
-    QPFunc fqp(gw_level, b, intercept0);
-    double sigma = fqp.sigma(frequency0, EvalStage::Other);
-    double dsigma_domega = fqp.deriv(frequency0);
-    double Z = 1.0 - dsigma_domega;
-    if (std::abs(Z) > 1e-9) newf = frequency0 + (intercept0 - frequency0 + sigma) / Z;
-    if (stats) *stats = fqp.GetStats();
-    return newf;
-  }
-
-  // gw.cc:433-502
-  std::optional<double> SolveQP_Grid_Windowed_Adaptive(SigmaBatcher& b, double intercept0, double frequency0,
-                                                       Index gw_level, double left_limit, double right_limit,
-                                                       bool allow_rejected_return, QPStats* stats) const {
-    QPFunc fqp(gw_level, b, intercept0);
-    qp_solver::SolverOptions solver_opt = MakeSolverOptions();
-    QPWindowDiagnostics wdiag;
-    std::vector<QPRootCandidate> accepted_roots, rejected_roots;
-    const bool use_brent = (opt_.qp_root_finder == "brent");
-    auto result = qp_solver::SolveQP_Grid_Windowed(fqp, frequency0, left_limit, right_limit, gw_sc_iteration_,
-                                                   solver_opt, &wdiag, &accepted_roots, &rejected_roots, use_brent);
-    if (stats) *stats = fqp.GetStats();
-    if (!accepted_roots.empty()) return result;
-    if (!rejected_roots.empty() && !allow_rejected_return) return std::nullopt;
-    return result;
-  }
-
-  // gw.cc:504-616
-  std::optional<double> SolveQP_Grid_Windowed_Dense(SigmaBatcher& b, double intercept0, double frequency0,
-                                                    Index gw_level, double left_limit, double right_limit,
-                                                    bool allow_rejected_return, QPStats* stats) const {
-    QPFunc fqp(gw_level, b, intercept0);
-    qp_solver::SolverOptions solver_opt = MakeSolverOptions();
-    const bool use_brent = (opt_.qp_root_finder == "brent");
-    std::vector<QPRootCandidate> accepted_roots, rejected_roots;
-    if (left_limit < right_limit) {
-      double freq_prev = left_limit;
-      const Index n_steps =
-          std::max<Index>(2, static_cast<Index>(std::ceil((right_limit - left_limit) / opt_.qp_dense_spacing)) + 1);
-      auto node = [&](Index i_node) {
-        return (i_node == n_steps - 1)
-                   ? right_limit
-                   : std::min(right_limit, left_limit + static_cast<double>(i_node) * opt_.qp_dense_spacing);
-      };
-      const Index look = 64;  // the scan nodes are known ahead: announce them in blocks
-      auto announce = [&](Index from) {
-        std::vector<double> pts;
-        for (Index i = from; i < std::min(n_steps, from + look); ++i) pts.push_back(node(i));
-        fqp.prefetch(pts.data(), pts.size());
-      };
-      announce(1);
-      double targ_prev = fqp.value(freq_prev, EvalStage::Scan);
-      for (Index i_node = 1; i_node < n_steps; ++i_node) {
-        if (i_node > 1 && (i_node - 1) % look == 0) announce(i_node);
-        const double freq = node(i_node);
-        const double targ = fqp.value(freq, EvalStage::Scan);
-        if (targ_prev * targ < 0.0) {
-          auto cand =
-              qp_solver::RefineQPInterval(freq_prev, targ_prev, freq, targ, fqp, frequency0, solver_opt, use_brent);
-          if (cand) (cand->accepted ? accepted_roots : rejected_roots).push_back(*cand);
-        }
-        freq_prev = freq;
-        targ_prev = targ;
-      }
-    }
-    if (stats) *stats = fqp.GetStats();
-    if (!accepted_roots.empty()) return qp_solver::BestRoot(accepted_roots).omega;
-    if (!rejected_roots.empty()) {
-      if (!allow_rejected_return) return std::nullopt;
-      return qp_solver::BestRoot(rejected_roots).omega;
-    }
-    return std::nullopt;
-  }
-
-  // gw.cc:618-675
-  std::optional<double> SolveQP_Grid_Windowed(SigmaBatcher& b, double intercept0, double frequency0, Index gw_level,
-                                              double left_limit, double right_limit, bool allow_rejected_return,
-                                              QPStats* stats) const {
-    if (opt_.qp_grid_search_mode == "adaptive")
-      return SolveQP_Grid_Windowed_Adaptive(b, intercept0, frequency0, gw_level, left_limit, right_limit,
-                                            allow_rejected_return, stats);
-    if (opt_.qp_grid_search_mode == "dense")
-      return SolveQP_Grid_Windowed_Dense(b, intercept0, frequency0, gw_level, left_limit, right_limit,
-                                         allow_rejected_return, stats);
-    if (opt_.qp_grid_search_mode == "adaptive_with_dense_fallback") {
-      QPStats total_stats;
-      auto adaptive = SolveQP_Grid_Windowed_Adaptive(b, intercept0, frequency0, gw_level, left_limit, right_limit,
-                                                     allow_rejected_return, &total_stats);
-      if (adaptive) {
-        if (stats) *stats = total_stats;
-        return adaptive;
-      }
-      QPStats dense_stats;
-      auto dense = SolveQP_Grid_Windowed_Dense(b, intercept0, frequency0, gw_level, left_limit, right_limit,
-                                               allow_rejected_return, &dense_stats);
-      total_stats.Add(dense_stats);
-      if (stats) *stats = total_stats;
-      return dense;
-    }
-    throw std::runtime_error("Unknown gw.qp_grid_search_mode '" + opt_.qp_grid_search_mode + "'");
-  }
-
-  // gw.cc:677-739
-  std::optional<double> SolveQP_Grid(SigmaBatcher& b, double intercept0, double frequency0, Index gw_level,
-                                     QPStats* stats) const {
-    const double range = opt_.qp_full_window_half_width;
-    const double full_left_limit = frequency0 - range;
-    const double full_right_limit = frequency0 + range;
-    double restricted_left_limit = full_left_limit;
-    double restricted_right_limit = full_right_limit;
-    bool use_restricted_window = false;
-    if (opt_.qp_restrict_search) {
-      const Index mo_level = gw_level + opt_.qpmin;
-      const bool is_occupied = (mo_level <= opt_.homo);
-      if (is_occupied)
-        restricted_right_limit = std::min(full_right_limit, -opt_.qp_zero_margin);
-      else
-        restricted_left_limit = std::max(full_left_limit, opt_.qp_virtual_min_energy);
-      const double tol = 1e-12;
-      use_restricted_window = (std::abs(restricted_left_limit - full_left_limit) > tol) ||
-                              (std::abs(restricted_right_limit - full_right_limit) > tol);
-    }
-    if (use_restricted_window && restricted_left_limit < restricted_right_limit) {
-      auto restricted = SolveQP_Grid_Windowed(b, intercept0, frequency0, gw_level, restricted_left_limit,
-                                              restricted_right_limit, false, stats);
-      if (restricted) return restricted;
-      return SolveQP_Grid_Windowed_Dense(b, intercept0, frequency0, gw_level, full_left_limit, full_right_limit,
-                                         true, stats);
-    }
-    return SolveQP_Grid_Windowed(b, intercept0, frequency0, gw_level, full_left_limit, full_right_limit, true, stats);
-  }
-
-  // gw.cc:741-757
-  std::optional<double> SolveQP_FixedPoint(SigmaBatcher& b, double intercept0, double frequency0, Index gw_level,
-                                           QPStats* stats) const {
-    std::optional<double> newf;
-    QPFunc f(gw_level, b, intercept0);
-    NewtonRapson<QPFunc> newton(opt_.g_sc_max_iterations, opt_.g_sc_limit, opt_.qp_solver_alpha);
-    double freq_new = newton.FindRoot(f, frequency0);
-    if (newton.getInfo() == NewtonRapson<QPFunc>::success) newf = freq_new;
-    if (stats) *stats = f.GetStats();
-    return newf;
   }
 
   Index qptotal_ = 0;
