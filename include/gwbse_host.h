@@ -72,6 +72,19 @@ void* gwbse_job_ctx(gwbse_job* job);
 
 int gwbse_job_run(gwbse_job* job);
 
+/* BSECoupling::CalculateCouplings + Addoutput (xtp/src/libxtp/bsecoupling.cc:356-612, 127-254; the calculator behind
+ * `xtp_tools -e bsecoupling` / the iexcitoncl job type): exciton couplings between monomers A and B from the GW-BSE
+ * results of the dimer.  Dimer inputs are the job's own ("mos", "Hqp" = QPdiag eigenvectors * eigenvalues *
+ * eigenvectors^T, "RPA_inputenergies", AO integrals as arrays or basis sets, "dft_overlap" unless a dft basis is set,
+ * scalars homo, rpamin, rpamax, qpmin, qpmax, bse_vmin, bse_cmax, use_Hqp_offdiag); monomer X in {A, B}: arrays
+ * "X.mos", "X.BSE_singlet_eigenvectors" / "X.BSE_triplet_eigenvectors" (+ "_eigenvalues"), scalars "X.bse_vmin",
+ * "X.bse_vmax", "X.bse_cmin", "X.bse_cmax".  Options: gwbse_job_set_option with the keys of bsecoupling.xml prefixed
+ * "bsecoupling." (spin, use_perturbation, output_tb, moleculeA.states, moleculeA.occLevels, ...).
+ * Outputs: arrays JAB_{singlet,triplet}_{pert,diag} (Hartree, (levA+levB)^2), J_dimer_*, S_dimer_*; scalars xi_*,
+ * pt_rm_discrepancy_*, downfolding_safe_*, levA, levB; gwbse_job_coupling_xml = the <bsecoupling> output subtree. */
+int gwbse_job_run_coupling(gwbse_job* job);
+const char* gwbse_job_coupling_xml(const gwbse_job* job);
+
 int gwbse_job_array_dims(const gwbse_job* job, const char* name, long* rows, long* cols);
 int gwbse_job_get_array(const gwbse_job* job, const char* name, double* out);
 int gwbse_job_get_scalar(const gwbse_job* job, const char* name, double* out);

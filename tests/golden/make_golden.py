@@ -4,7 +4,7 @@
 Run in the build container only (needs /root/reference):
     python tests/golden/make_golden.py
 Sources: xtp/src/tests/DataFiles/{threecenter_gwbse,rpa,sigma_exact,sigma_cda,
-sigma_ppm,gw,bse,bse_operator}/*.mm (MatrixMarket, 6 significant digits), the AO
+sigma_ppm,gw,bse,bse_operator,bsecoupling}/*.mm (MatrixMarket, 6 significant digits), the AO
 integral references of aomatrix/, aomatrix3d/ and threecenter_dft/,
 molecule.xyz and 3-21G.xml (identical in all of these directories), and the
 inline vectors of test_sigma_*.cc, test_gw.cc, test_bse_operator.cc,
@@ -120,6 +120,20 @@ def main():
     for name in ("def2-svp", "aux-def2-svp"):
         bs = obasis.load_basisset(f"/root/reference/xtp/share/xtp/basis_sets/{name}.xml")
         out[f"basis/{name}_CH.json"] = np.array(json.dumps({el: bs[el] for el in ("C", "H")}))
+    # ---- BSECoupling (test_bsecoupling.cc): methane monomer / dimer (B = A shifted by 4 bohr along x), 3-21G for
+    # both the orbital and the auxiliary basis, monomer and dimer MOs, the dimer's QP eigenvectors, three monomer
+    # singlets; inline eigenvalues of :84-88 (dimer MOs, unused by the coupling) and :113-119 (QPdiag)
+    for fn in ("A_MOs", "AB_MOs", "Hqp", "spsi_ref"):
+        out[f"bsecoupling/{fn}"] = mmio.read_matrix(os.path.join(REF, "bsecoupling", fn + ".mm"))
+    elems, pos = obasis.read_xyz(os.path.join(REF, "bsecoupling", "molecule.xyz"))
+    out["bsecoupling/elements"] = np.array(elems)
+    out["bsecoupling/positions_bohr"] = pos
+    out["bsecoupling/qpdiag_eigenvalues"] = np.array(
+        [-10.504, -10.5038, -0.923616, -0.775673, -0.549084, -0.530193, -0.530193, -0.430293, -0.430293, -0.322766,
+         0.267681, 0.307809, 0.326961, 0.326961, 0.36078, 0.381947, 0.414845, 0.414845, 0.906609, 0.906609, 0.993798,
+         1.09114, 1.14639, 1.14639, 1.1966, 1.25629, 1.25629, 1.27991, 1.29122, 1.35945, 1.36705, 1.36705, 1.93286,
+         2.11739])
+    out["bsecoupling/known_answers_eV"] = np.array([23.662750, 9.529579])  # |j_diag|, |j_pert|, :138-139
     np.savez_compressed(os.path.join(HERE, "votca_fixtures.npz"), **out)
     print("wrote", len(out), "arrays")
 

@@ -133,3 +133,22 @@ def benzene_tzvp_case():
     c["dft"], c["aux"], c["elements"], c["positions"] = dft, aux, el, pos
     c["homo"], c["q"] = int(c["homo"]), int(c["q"])
     return c
+
+
+@lru_cache(maxsize=None)
+def bsecoupling_case():
+    """The system of the reference's test_bsecoupling.cc: methane monomers A and B (B = A shifted by 4 bohr along x),
+    3-21G as orbital and auxiliary basis, dimer levels 0..33 for RPA / GW / BSE, homo = 9, Hqp with off-diagonals."""
+    g = load_golden()
+    bs = json.loads(str(g["basis/3-21G.json"]))
+    bs = {el: [(int(l), [tuple(p) for p in prims]) for l, prims in shells] for el, shells in bs.items()}
+    el = [str(e) for e in g["bsecoupling/elements"]]
+    posA = g["bsecoupling/positions_bohr"]
+    posB = posA + np.array([4.0, 0.0, 0.0])
+    dimer = obasis.AOBasis(bs, el + el, np.vstack([posA, posB]))
+    qp_vec, qp_val = g["bsecoupling/Hqp"], g["bsecoupling/qpdiag_eigenvalues"]
+    Hqp = qp_vec @ np.diag(qp_val) @ qp_vec.T
+    return {"basis": dimer, "A_mos": g["bsecoupling/A_MOs"], "AB_mos": g["bsecoupling/AB_MOs"], "Hqp": Hqp,
+            "rpa_energies": np.diag(Hqp).copy(), "spsi": g["bsecoupling/spsi_ref"], "homo": 9,
+            "S_dft": integrals.overlap(dimer), "S": integrals.overlap(dimer), "V": integrals.coulomb2c(dimer),
+            "ao3c": integrals.coulomb3c(dimer, dimer), "known_eV": g["bsecoupling/known_answers_eV"]}

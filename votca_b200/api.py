@@ -446,6 +446,14 @@ class Job:
     def run(self):
         self._ck(self.api.gwbse_job_run(self.h))
 
+    def run_coupling(self):
+        """BSECoupling::CalculateCouplings on the job's dimer inputs and the "A.*" / "B.*" monomer inputs
+        (include/gwbse_host.h: gwbse_job_run_coupling); options: set_option("bsecoupling.<key>", value)."""
+        self._ck(self.api.gwbse_job_run_coupling(self.h))
+
+    def coupling_xml(self):
+        return self.api.gwbse_job_coupling_xml(self.h).decode()
+
     def get(self, name):
         r, c = ctypes.c_long(), ctypes.c_long()
         if self.api.gwbse_job_array_dims(self.h, name.encode(), ctypes.byref(r), ctypes.byref(c)) != 0:

@@ -78,6 +78,17 @@ class BSE {
   }
 
   const MatrixXd& getHqp() const { return Hqp_; }
+  // bse.cc:206-232: the TDA operators as BSECoupling uses them (they refer to this object's screening and Hqp)
+  SingletOperator_TDA getSingletOperator_TDA() const {
+    SingletOperator_TDA H(epsilon_0_inv_, Mmn_, Hqp_);
+    configureBSEOperator(H);
+    return H;
+  }
+  TripletOperator_TDA getTripletOperator_TDA() const {
+    TripletOperator_TDA H(epsilon_0_inv_, Mmn_, Hqp_);
+    configureBSEOperator(H);
+    return H;
+  }
   const VectorXd& getEpsilonInv() const { return epsilon_0_inv_; }
   Index last_davidson_iterations() const { return last_iterations_; }
   Index last_operator_columns() const { return last_op_columns_; }

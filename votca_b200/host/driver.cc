@@ -6,6 +6,7 @@
 #include <memory>
 
 #include "aobasis.h"
+#include "bsecoupling.h"
 #include "gwbse.h"
 
 using namespace votca;
@@ -67,6 +68,8 @@ struct gwbse_job {
   std::unique_ptr<DeviceAOBasis> dev_basis[2];
   std::string orb_path;  // gwbse_job_set_orb_output: results are written there at the end of gwbse_job_run
   std::string summary_path;  // gwbse_job_set_summary_output: <job>_summary.xml of the dftgwbse tool
+  std::map<std::string, std::string> coupling_options;  // "bsecoupling.*" keys (bsecoupling.xml)
+  std::string coupling_xml;                             // BSECoupling::Addoutput of the last gwbse_job_run_coupling
   std::string err;
   mutable std::string logcache;
 };
@@ -120,7 +123,20 @@ int gwbse_job_comm_init(gwbse_job* job, int rank, int world, const unsigned char
 
 int gwbse_job_set_option(gwbse_job* job, const char* key, const char* value) {
   JOB_BEGIN(job)
-  job->options.set(key, value);
+  const std::string k(key ? key : "");
+  const size_t at = k.find("bsecoupling.");
+  if (at != std::string::npos) {
+    static const char* known[] = {"spin", "use_perturbation", "output_tb", "moleculeA.states", "moleculeA.occLevels",
+                                  "moleculeA.unoccLevels", "moleculeB.states", "moleculeB.occLevels",
+                                  "moleculeB.unoccLevels"};
+    const std::string sub = k.substr(at + 12);
+    bool ok = false;
+    for (const char* n : known) ok = ok || sub == n;
+    if (!ok) throw std::runtime_error("unknown option '" + k + "' (not a key of bsecoupling.xml)");
+    job->coupling_options[sub] = value ? value : "";
+  } else {
+    job->options.set(key, value);
+  }
   JOB_END(job)
 }
 
@@ -334,6 +350,129 @@ int gwbse_job_run(gwbse_job* job) {
   s["time_bse"] = r.time_bse;
   JOB_END(job)
 }
+
+// BSECoupling through the job facade: the dimer uses the job's own inputs (mos, Hqp, RPA_inputenergies, integrals or
+// basis sets, scalars homo / rpamin / rpamax / qpmin / qpmax / bse_vmin / bse_cmax / use_Hqp_offdiag), the monomers
+// the arrays "A.mos", "A.BSE_singlet_eigenvectors", ... and the scalars "A.bse_vmin" ... "A.bse_cmax" (same for B).
+int gwbse_job_run_coupling(gwbse_job* job) {
+  JOB_BEGIN(job)
+  auto need = [&](const std::string& n) -> const MatrixXd& {
+    auto it = job->in.find(n);
+    if (it == job->in.end()) throw std::runtime_error("input array '" + n + "' not set");
+    return it->second;
+  };
+  auto opt = [&](const std::string& n) -> const MatrixXd* {
+    auto it = job->in.find(n);
+    return it == job->in.end() ? nullptr : &it->second;
+  };
+  auto scalar = [&](const std::string& n) -> Index {
+    auto it = job->scalars.find(n);
+    if (it == job->scalars.end()) throw std::runtime_error("input scalar '" + n + "' not set");
+    return static_cast<Index>(std::llround(it->second));
+  };
+  BSECoupling::options co;
+  auto copt = [&](const char* k, const std::string& dflt) {
+    auto it = job->coupling_options.find(k);
+    return it == job->coupling_options.end() ? dflt : it->second;
+  };
+  auto truth = [](const std::string& v) { return v == "true" || v == "1"; };
+  co.spin = copt("spin", co.spin);
+  co.use_perturbation = truth(copt("use_perturbation", "true"));
+  co.output_tb = truth(copt("output_tb", "false"));
+  co.statesA = std::stol(copt("moleculeA.states", "5"));
+  co.occLevelsA = std::stol(copt("moleculeA.occLevels", "5"));
+  co.unoccLevelsA = std::stol(copt("moleculeA.unoccLevels", "5"));
+  co.statesB = std::stol(copt("moleculeB.states", "5"));
+  co.occLevelsB = std::stol(copt("moleculeB.occLevels", "5"));
+  co.unoccLevelsB = std::stol(copt("moleculeB.unoccLevels", "5"));
+
+  std::vector<VectorXd> keep;  // energies as vectors, alive until the end of the run
+  keep.reserve(8);
+  auto fragment = [&](const std::string& tag) {
+    CouplingOrbitals f;
+    f.mos = &need(tag + ".mos");
+    f.bse_vmin = scalar(tag + ".bse_vmin");
+    f.bse_vmax = scalar(tag + ".bse_vmax");
+    f.bse_cmin = scalar(tag + ".bse_cmin");
+    f.bse_cmax = scalar(tag + ".bse_cmax");
+    f.singlets = opt(tag + ".BSE_singlet_eigenvectors");
+    f.triplets = opt(tag + ".BSE_triplet_eigenvectors");
+    if (const MatrixXd* e = opt(tag + ".BSE_singlet_eigenvalues")) {
+      keep.push_back(mat2vec(*e));
+      f.singlet_energies = &keep.back();
+    }
+    if (const MatrixXd* e = opt(tag + ".BSE_triplet_eigenvalues")) {
+      keep.push_back(mat2vec(*e));
+      f.triplet_energies = &keep.back();
+    }
+    return f;
+  };
+  const CouplingOrbitals A = fragment("A"), B = fragment("B");
+  CouplingOrbitals AB;
+  AB.mos = &need("mos");
+  AB.homo = scalar("homo");
+  AB.rpamin = scalar("rpamin");
+  AB.rpamax = scalar("rpamax");
+  AB.qpmin = scalar("qpmin");
+  AB.qpmax = scalar("qpmax");
+  AB.bse_vmin = scalar("bse_vmin");
+  AB.bse_cmax = scalar("bse_cmax");
+  AB.bse_vmax = AB.homo;
+  AB.bse_cmin = AB.homo + 1;
+  AB.use_Hqp_offdiag = !job->scalars.count("use_Hqp_offdiag") || job->scalars["use_Hqp_offdiag"] != 0.0;
+  AB.Hqp = &need("Hqp");
+  keep.push_back(mat2vec(need("RPA_inputenergies")));
+  AB.rpa_input_energies = &keep.back();
+
+  // integrals of the dimer: produced on the device from the basis sets, else the supplied arrays (as in gwbse_job_run)
+  std::unique_ptr<DeviceAOIntegrals> device_ints;
+  const AOIntegralSource* ints = nullptr;
+  MatrixXd overlap;
+  const bool have_arrays = job->ints.ao3c || job->ints.ao3c_dev || job->ints.fn;
+  if (!have_arrays && job->basis_data[0] && job->basis_data[1]) {
+    for (int b = 0; b < 2; ++b)
+      if (!job->dev_basis[b]) job->dev_basis[b] = std::make_unique<DeviceAOBasis>(*job->dev, *job->basis_data[b]);
+    device_ints = std::make_unique<DeviceAOIntegrals>(*job->dev, *job->dev_basis[1], *job->dev_basis[0], opt("aux_overlap"),
+                                                      opt("aux_coulomb"));
+    ints = device_ints.get();
+    if (!opt("dft_overlap")) {  // CouplingBase::CalculateOverlapMatrix on the device
+      const Index n = job->dev_basis[0]->AOBasisSize();
+      overlap = MatrixXd(n, n);
+      job->dev->check(gwbse_ao_overlap(job->dev->ctx(), job->dev_basis[0]->handle(), overlap.data(), (int)n));
+    }
+  } else {
+    job->ints.S = &need("aux_overlap");
+    job->ints.V = &need("aux_coulomb");
+    ints = &job->ints;
+  }
+  AB.overlap = opt("dft_overlap") ? opt("dft_overlap") : &overlap;
+  if (AB.overlap->rows() != AB.mos->rows()) throw std::runtime_error("input array 'dft_overlap' not set");
+
+  BSECoupling coupling(*job->dev, job->log);
+  coupling.Initialize(co);
+  coupling.CalculateCouplings(A, B, AB, *ints);
+  job->coupling_xml = coupling.Addoutput();
+  auto& o = job->out;
+  o.clear();
+  job->out_scalars.clear();
+  for (int spin = 0; spin < 2; ++spin) {
+    if (!(spin == 0 ? coupling.doSinglets() : coupling.doTriplets())) continue;
+    const BSECoupling::Channel& ch = spin == 0 ? coupling.singlet() : coupling.triplet();
+    const std::string s = spin == 0 ? "singlet" : "triplet";
+    o["JAB_" + s + "_pert"] = ch.JAB[0];
+    o["JAB_" + s + "_diag"] = ch.JAB[1];
+    o["J_dimer_" + s] = ch.J_dimer;
+    o["S_dimer_" + s] = ch.S_dimer;
+    job->out_scalars["xi_" + s] = ch.diag.xi;
+    job->out_scalars["pt_rm_discrepancy_" + s] = ch.diag.pt_rm_discrepancy;
+    job->out_scalars["downfolding_safe_" + s] = ch.diag.downfolding_safe ? 1.0 : 0.0;
+  }
+  job->out_scalars["levA"] = (double)coupling.levA();
+  job->out_scalars["levB"] = (double)coupling.levB();
+  JOB_END(job)
+}
+
+const char* gwbse_job_coupling_xml(const gwbse_job* job) { return job ? job->coupling_xml.c_str() : ""; }
 
 int gwbse_job_array_dims(const gwbse_job* job, const char* name, long* rows, long* cols) {
   if (!job) return 1;
