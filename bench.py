@@ -7,12 +7,13 @@ GW with the plasmon-pole model (RPA epsilon, PPM rotation, batched QP root searc
 (static screening, 10 singlets by Davidson, TDA off = full BSE as the reference default).
 
 Workloads (SURVEY.md section 8 sizes):
-  dcv5t-tzvp  BASELINE config 3: N=1249, Naux=3177, homo=143 -> m=q=431, B=41328; evGW.  Synthetic tier-S inputs
-              (votca_b200/synthetic.py): the AO three-centre tensor is an input (39.6 GB, resident in HBM for `value`,
-              in pinned host memory for `e2e`).
-  c60-tzvp    BASELINE config 4: C60 def2-tzvp + aux-def2-tzvp, N=1860, Naux=4560, homo=179 -> m=q=539, B=64620; G0W0.
+  c60-tzvp    (headline) BASELINE config 4, the largest configuration that fits one GPU and the one BASELINE.json
+              shards over 8: C60 def2-tzvp + aux-def2-tzvp, N=1860, Naux=4560, homo=179 -> m=q=539, B=64620; G0W0.
               Tier R: real geometry and basis sets, the AO Coulomb integrals are produced on the device
               (gwbse_mmn_fill_from_basis path: the 126 GB AO tensor never exists), synthetic orthonormal MOs.
+  dcv5t-tzvp  (reported under "also") BASELINE config 3: N=1249, Naux=3177, homo=143 -> m=q=431, B=41328; evGW.
+              Synthetic tier-S inputs (votca_b200/synthetic.py): the AO three-centre tensor is an input (39.6 GB,
+              resident in HBM for `value`, in pinned host memory for `e2e`).
   benzene-tzvp, small, medium: short runs of the same two kinds.
 
   python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--workload NAME] [--mode evGW|G0W0]
@@ -51,11 +52,11 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="dcv5t-tzvp")
+    ap.add_argument("--workload", default="c60-tzvp")
     ap.add_argument("--mode", default=None, choices=["evGW", "G0W0"])
     ap.add_argument("--also", default="auto",
                     help="second workload measured with 1 warm-up + 2 steps and reported under 'also' "
-                         "(auto: c60-tzvp beside the default dcv5t-tzvp headline, none otherwise; '' switches it off)")
+                         "(auto: dcv5t-tzvp beside the default c60-tzvp headline, none otherwise; '' switches it off)")
     ap.add_argument("--e2e-steps", type=int, default=3, help="upper bound on the timed steps of the end-to-end arm")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -64,7 +65,7 @@ def parse_args():
     if a.mode is None:
         a.mode = DEFAULT_MODE.get(a.workload, "evGW")
     if a.also == "auto":
-        a.also = "c60-tzvp" if a.workload == "dcv5t-tzvp" else ""
+        a.also = "dcv5t-tzvp" if a.workload == "c60-tzvp" else ""
     return a
 
 
@@ -197,26 +198,37 @@ def run_reference(args, rank):
     from oracle import cpu_baseline
     N, naux, homo, q = sizes(args.workload)
     counts, source = reference_counts(args.workload, args.mode, q)
-    for _ in range(max(0, min(args.warmup, 1))):
-        cpu_baseline.estimate(N, naux, homo, counts, sample_scale=1.0)
+    ao_system = args.workload if args.workload in TIER_R else None
+    # Bounded: the whole run is to end within a few minutes whatever --steps is.  The first (untimed) call times the
+    # single-call samples (naux x naux eigh / inverse, AO-integral shell triples) once and keeps them; a second one
+    # measures what a unit of loop sampling costs on this box, and the sample size of the timed steps follows from
+    # the budget (GWBSE_REF_BUDGET_S seconds, default 240).
+    once = {}
+    cpu_baseline.estimate(N, naux, homo, counts, sample_scale=1.0, ao_system=ao_system, once=once)
+    t0 = time.perf_counter()
+    cpu_baseline.estimate(N, naux, homo, counts, sample_scale=1.0, ao_system=ao_system, once=once)
+    unit_s = max(time.perf_counter() - t0, 1e-3)
+    budget = float(os.environ.get("GWBSE_REF_BUDGET_S", "240"))
+    scale = float(min(24.0, max(1.0, np.floor(budget / max(args.steps, 1) / unit_s))))
     vals = []
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        est = cpu_baseline.estimate(N, naux, homo, counts, sample_scale=24.0,
-                                    ao_system=args.workload if args.workload in TIER_R else None)
+        est = cpu_baseline.estimate(N, naux, homo, counts, sample_scale=scale, ao_system=ao_system, once=once)
         vals.append(est["total_seconds"])
     wall = time.perf_counter() - t0
     v = float(np.mean(vals))
     threads = thread_report()
     sample = ("per stage a few loop iterations of the reference CPU formulation (aux functions / m slices / "
               "occupied levels / sigma evaluations / BSE rows), scaled by the iteration counts of the workload; "
-              f"{est['sampled_seconds']:.1f} s of CPU work per step")
+              f"{est['sampled_seconds']:.1f} s of CPU work per step (sample scale {scale:g} of 24, chosen for a "
+              f"{budget:.0f} s run; eigh / inverse / AO-integral samples timed once per run)")
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": False,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "extrapolated": True,
             "value_is": "sampled stage times x iteration counts of the workload (ms_per_step is the sampler's own wall time)",
-            "config": {"workload": workload_name(args.workload, args.mode, N, naux, homo), "mode": args.mode},
+            "config": {"workload": workload_name(args.workload, args.mode, N, naux, homo), "mode": args.mode,
+                       "l2_policy": l2_policy(N, naux, q)},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample,
                              "threads": threads, "counts": counts, "counts_source": source,
                              "stages": {k: round(s["sample_s"] * s["factor"], 3) for k, s in est["stages"].items()},
@@ -529,7 +541,7 @@ def summarize(rec, with_cpu):
     cpu = None
     if with_cpu:
         from oracle import cpu_baseline
-        est = cpu_baseline.estimate(rec["N"], rec["naux"], rec["homo"], rec["counts"], sample_scale=12.0,
+        est = cpu_baseline.estimate(rec["N"], rec["naux"], rec["homo"], rec["counts"], sample_scale=6.0,
                                     ao_system=rec["workload"] if rec["workload"] in TIER_R else None)
         cpu = {"value": est["total_seconds"], "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "extrapolated": True,
                "stages": {k: round(s["sample_s"] * s["factor"], 3) for k, s in est["stages"].items()},
@@ -603,9 +615,9 @@ def make_line(args, rec, also, parity, world):
         "warmup": rec["warmup"], "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(rec["workload"], rec["mode"], N, naux, homo), "mode": rec["mode"],
-                   "l2_policy": l2_policy(N, naux, q), "gw_iterations": counts["gw_iterations"],
-                   "davidson_iterations": counts["davidson_iterations"], "results": rec["results"],
-                   "stage_seconds": rec["stage_seconds"], "ao_integrals": ao_note},
+                   "l2_policy": l2_policy(N, naux, q)},  # the reference arm prints the same three keys
+        "run": {"gw_iterations": counts["gw_iterations"], "davidson_iterations": counts["davidson_iterations"],
+                "results": rec["results"], "stage_seconds": rec["stage_seconds"], "ao_integrals": ao_note},
         "tflops": {"value": rec["total_flops"] / (ms_per_step * 1e-3) / 1e12,
                    "algorithmic_tflop_per_step": rec["total_flops"] / 1e12,
                    "stages_tflop": {k: round(v / 1e12, 3) for k, v in flops.items()}},
@@ -631,7 +643,7 @@ def make_line(args, rec, also, parity, world):
         pass
     if not args.no_cpu and world == 1:  # reported at N=1 only
         from oracle import cpu_baseline
-        est = cpu_baseline.estimate(N, naux, homo, counts, sample_scale=24.0,
+        est = cpu_baseline.estimate(N, naux, homo, counts, sample_scale=12.0,
                                     ao_system=rec["workload"] if tier_r else None)
         line["cpu_baseline"] = {
             "value": est["total_seconds"], "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "extrapolated": True,

@@ -131,11 +131,14 @@ def ao_integral_stage(system_name, sample_scale=1.0):
             f"code, call overhead {t_empty:.2f} s taken out)", "factor": naux / float(cores * nf)}
 
 
-def estimate(nbasis, naux, homo, counts, seed=7, sample_scale=1.0, ao_system=None):
+def estimate(nbasis, naux, homo, counts, seed=7, sample_scale=1.0, ao_system=None, once=None):
     """Returns dict(total_seconds, stages={...}) for a G0W0/evGW(ppm) + BSE(TDA singlets) run.
 
     counts: iteration counts of the run being mirrored (taken from the GPU run so both arms do the same
     algorithmic work): gw_iterations, sigma_evaluations, davidson_iterations, bse_analysis_matmuls.
+    once: optional dict kept by the caller across calls.  The stages whose sample is one whole call of a library
+    routine or a fixed shell-triple sample (naux x naux eigh and inverse, AO integrals) are timed on the first call and
+    re-used afterwards, so that a run of many steps stays bounded; every loop-sampled stage is timed again per call.
     """
     rng = np.random.default_rng(seed)
     N, n = nbasis, nbasis
@@ -184,12 +187,19 @@ def estimate(nbasis, naux, homo, counts, seed=7, sample_scale=1.0, ao_system=Non
                              "factor": n_occ / nv * calls}
 
     # ---- dense auxiliaries on naux x naux: eigh (ppm.cc:37, bse.cc:194, aomatrix.cc:56,73), inverse (ppm.cc:44)
-    A = _fast_normal(rng, (naux, naux))
-    A = A @ A.T / naux + np.eye(naux)
-    stages["sym_eig"] = {"sample_s": _best(lambda: np.linalg.eigh(A), 1), "sample": "one naux x naux eigh",
-                         "factor": 2 + it + 1}
-    stages["inverse"] = {"sample_s": _best(lambda: np.linalg.inv(A), 1), "sample": "one naux x naux inverse",
-                         "factor": it}
+    if once is not None and "sym_eig" in once:
+        stages["sym_eig"] = dict(once["sym_eig"], factor=2 + it + 1)
+        stages["inverse"] = dict(once["inverse"], factor=it)
+    else:
+        A = _fast_normal(rng, (naux, naux))
+        A = A @ A.T / naux + np.eye(naux)
+        stages["sym_eig"] = {"sample_s": _best(lambda: np.linalg.eigh(A), 1), "sample": "one naux x naux eigh",
+                             "factor": 2 + it + 1}
+        stages["inverse"] = {"sample_s": _best(lambda: np.linalg.inv(A), 1), "sample": "one naux x naux inverse",
+                             "factor": it}
+        del A
+        if once is not None:
+            once["sym_eig"], once["inverse"] = dict(stages["sym_eig"]), dict(stages["inverse"])
 
     lib = _clib()
     cores = os.cpu_count() or 1
@@ -275,7 +285,12 @@ def estimate(nbasis, naux, homo, counts, seed=7, sample_scale=1.0, ao_system=Non
                                "factor": vt * (vt + 1) / 2 / nblk * dav}
 
     if ao_system:
-        stages["ao_integrals"] = ao_integral_stage(ao_system, sample_scale / 24.0)
+        if once is not None and "ao_integrals" in once:
+            stages["ao_integrals"] = dict(once["ao_integrals"])
+        else:
+            stages["ao_integrals"] = ao_integral_stage(ao_system, sample_scale / 24.0)
+            if once is not None:
+                once["ao_integrals"] = dict(stages["ao_integrals"])
     total = sum(s["sample_s"] * s["factor"] for s in stages.values())
     sampled = sum(s["sample_s"] for s in stages.values())
 
