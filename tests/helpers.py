@@ -152,3 +152,22 @@ def bsecoupling_case():
             "rpa_energies": np.diag(Hqp).copy(), "spsi": g["bsecoupling/spsi_ref"], "homo": 9,
             "S_dft": integrals.overlap(dimer), "S": integrals.overlap(dimer), "V": integrals.coulomb2c(dimer),
             "ao3c": integrals.coulomb3c(dimer, dimer), "known_eV": g["bsecoupling/known_answers_eV"]}
+
+
+@lru_cache(maxsize=None)
+def uks_case():
+    """Open-shell test system for the UKS twins (no reference fixture exists for them): methane 3-21G of the reference
+    unit tests, alpha orbitals = gw/mo_eigenvectors, beta orbitals = the same set rotated among neighbours by a seeded
+    orthogonal matrix close to 1, beta energies shifted; doublet occupation homo_alpha = 4, homo_beta = 3."""
+    g = load_golden()
+    Ca = g["gw/mo_eigenvectors"]
+    ea = g["inline/gw_mo_eigenvalues"].copy()
+    rng = np.random.default_rng(1917)
+    K = 0.08 * rng.standard_normal((17, 17))
+    Q, _ = np.linalg.qr(np.eye(17) + K - K.T)
+    Cb = Ca @ Q
+    eb = ea + 0.03 * np.arange(17) / 17.0 + 0.01
+    vxc_a = g["gw/vxc"]
+    Rv = 0.01 * rng.standard_normal((17, 17))
+    vxc_b = vxc_a + 0.5 * (Rv + Rv.T)
+    return {"Ca": Ca, "Cb": Cb, "ea": ea, "eb": eb, "vxc_a": vxc_a, "vxc_b": vxc_b, "homo_a": 4, "homo_b": 3}

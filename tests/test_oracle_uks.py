@@ -1,0 +1,102 @@
+"""oracle/uks.py (the UKS twins).  The reference has no unit test for these classes, so the restatement is held to the
+restricted oracle - itself pinned on the reference's rpa/, sigma_ppm/, gw/ and bse_operator/ fixtures - in the
+closed-shell limit, where every UKS formula must collapse to its restricted counterpart."""
+import numpy as np
+
+from oracle import bse as obse
+from oracle import bse_operator as bop
+from oracle import gw as ogw
+from oracle import rpa as orpa
+from oracle import uks
+from tests.helpers import load_golden, methane_mmn, uks_case
+from tests.test_oracle_golden import _gw_options
+
+
+def test_spin_summed_epsilon_equals_restricted_in_the_closed_shell_limit():
+    g = load_golden()
+    C, e = g["gw/mo_eigenvectors"], g["inline/gw_mo_eigenvalues"]
+    r = orpa.RPA(methane_mmn(C))
+    r.configure(4, 0, 16)
+    r.set_rpa_input_energies(e)
+    u = uks.RPAUKS(methane_mmn(C), methane_mmn(C))
+    u.configure(4, 4, 0, 16)
+    u.set_rpa_input_energies(e, e)
+    for f in (0.0, 0.5):
+        assert np.abs(u.calculate_epsilon_i(f) - r.calculate_epsilon_i(f)).max() < 1e-12
+        assert np.abs(u.calculate_epsilon_r(f) - r.calculate_epsilon_r(f)).max() < 1e-12
+    z = complex(0.3, 0.2)
+    assert np.abs(u.calculate_epsilon_r(z) - r.calculate_epsilon_r(z)).max() < 1e-12
+    # energies update: identical to the restricted rule when rpamin = 0 (rpa.cc:52-62 counts the head from 0)
+    gwa = e[2:12] + 0.01 * np.arange(10)
+    r.update_rpa_input_energies(e, gwa, 2)
+    u.update_rpa_input_energies(e, e, gwa, gwa, 2)
+    assert np.abs(u.energies(0) - r.get_rpa_input_energies()).max() < 1e-15
+    assert np.abs(u.energies(1) - r.get_rpa_input_energies()).max() < 1e-15
+
+
+def test_gw_uks_reproduces_restricted_gw_in_the_closed_shell_limit():
+    """evGW on both: the restricted result is the reference's gw/ref fixture (tests/test_oracle_golden.py)."""
+    g = load_golden()
+    C, e, vxc = g["gw/mo_eigenvectors"], g["inline/gw_mo_eigenvalues"], g["gw/vxc"]
+    opt = _gw_options(qp_grid_steps=601, qp_grid_spacing=0.005)
+    rg = ogw.GW(methane_mmn(C), vxc, e)
+    rg.configure(opt)
+    rg.calculate_gw_perturbation()
+    rg.calculate_hqp()
+    ug = uks.GWUKS(methane_mmn(C), methane_mmn(C), vxc, vxc, e, e)
+    ug.configure(_gw_options(qp_grid_steps=601, qp_grid_spacing=0.005), 4, 4)
+    ug.calculate_gw_perturbation()
+    ug.calculate_hqp()
+    for s in range(2):
+        assert np.abs(ug.get_gwa_results(s) - rg.get_gwa_results()).max() < 1e-10
+        assert np.abs(ug.get_hqp(s) - rg.get_hqp()).max() < 1e-10
+    assert np.abs(np.diag(g["gw/ref"]) - ug.get_gwa_results(0)).max() / np.abs(np.diag(g["gw/ref"])).max() < 1e-4
+
+
+def test_uks_operator_blocks_reduce_to_the_restricted_operators():
+    """Same-spin blocks of <1,1,1,0> against the sum of the restricted <1,0,0,0>, <0,1,0,0>, <0,0,1,0> operators (pinned on bse_operator/*_ref), the
+    cross-spin block against the screened transition-density form, diagonal against the dense matrix, symmetry."""
+    g = load_golden()
+    C = g["bse_operator/MOs"]
+    eps = g["inline/bse_operator_epsilon_inv"]
+    Hqp = g["bse_operator/Hqp"]
+    Ma = methane_mmn(C)
+    Ma.multiply_right(g["bse_operator/rpa_op"])
+    Mb = methane_mmn(C)
+    Mb.multiply_right(g["bse_operator/rpa_op"])
+    op = uks.exciton_uks_tda(eps, Ma, Mb, Hqp, Hqp)
+    op.configure(4, 4, 0, 0, 8)
+    D = op.dense()
+    n = op.blk[0].size
+    ropt = bop.BSEOperatorOptions(cmax=8, homo=4, qpmin=0, rpamin=0, vmin=0)
+    parts = {}
+    for name, mk in (("hqp", bop.hqp_op), ("hx", bop.hx_op), ("hd", bop.hd_op)):
+        r = mk(eps, Ma, Hqp)
+        r.configure(ropt)
+        parts[name] = r.dense()
+    same = parts["hqp"] + parts["hx"] + parts["hd"]  # BSE_OPERATOR<0,0,1,0> is -Hd already
+    assert np.abs(D[:n, :n] - same).max() < 1e-12 and np.abs(D[n:, n:] - same).max() < 1e-12
+    A = np.vstack([Ma[v][5:9, :] for v in range(5)])  # rows (v, c), the transition densities
+    cross = -(A * eps) @ A.T
+    assert np.abs(D[:n, n:] - cross).max() < 1e-12 and np.abs(D[n:, :n] - cross).max() < 1e-12
+    assert np.abs(D - D.T).max() < 1e-12
+    assert np.abs(np.diag(D) - op.diagonal()).max() < 1e-12
+
+
+def test_open_shell_case_runs_and_is_spin_asymmetric():
+    c = uks_case()
+    ug = uks.GWUKS(methane_mmn(c["Ca"]), methane_mmn(c["Cb"]), c["vxc_a"], c["vxc_b"], c["ea"], c["eb"])
+    ug.configure(_gw_options(qp_grid_steps=601, qp_grid_spacing=0.005, gw_sc_max_iterations=1), c["homo_a"], c["homo_b"])
+    ug.calculate_gw_perturbation()
+    qa, qb = ug.get_gwa_results(0), ug.get_gwa_results(1)
+    assert np.all(np.isfinite(qa)) and np.all(np.isfinite(qb)) and np.abs(qa - qb).max() > 1e-3
+    ug.calculate_hqp()
+    bs = uks.BSEUKS(methane_mmn(c["Ca"]), methane_mmn(c["Cb"]))
+    o = obse.BSEOptions(cmax=16, rpamax=16, rpamin=0, vmin=0, nmax=3, useTDA=True, homo=4, qpmin=0, qpmax=16,
+                        davidson_tolerance="lapack", davidson_maxiter=50)
+    bs.configure(o, c["homo_a"], c["homo_b"], ug.rpa.energies(0), ug.rpa.energies(1), ug.get_hqp(0), ug.get_hqp(1))
+    res = bs.solve_excitons_uks_tda()
+    H = bs.operator_tda().dense()
+    assert H.shape == (5 * 12 + 4 * 13,) * 2
+    w = np.linalg.eigvalsh(H)
+    assert np.abs(res["eigenvalues"][:3] - w[:3]).max() < 1e-8
