@@ -297,6 +297,16 @@ int gwbse_bse_matmul(gwbse_ctx* ctx, int cqp, int cx, int cd, int cd2, int k, co
                      int ldy);
 int gwbse_bse_matmul_dev(gwbse_ctx* ctx, int cqp, int cx, int cd, int cd2, int k, const double* X_dev, int ldx,
                          double* Y_dev, int ldy);
+/* The two halves of the exchange term as separate calls - what BSE_OPERATOR_UKS needs for the coupling between the
+ * spin channels (add_direct_cross_tda_block, bse_operator_uks.cc:174-211: transition densities of the input channel
+ * contracted with the trial vectors, screened, expanded in the transition densities of the output channel), each
+ * half on the context that holds that channel's Mmn:
+ *   project: W[chi, kv]     = sum_{v,c} M[v][c, chi] X[(v,c), kv]                       W_dev: naux x k, ld naux
+ *   expand : Y[(v,c), kv] += alpha sum_chi M[v][c, chi] (screened ? eps_inv[chi] : 1) W[chi, kv]
+ * with the level ranges / eps_inv of the last gwbse_bse_configure of that context.                                */
+int gwbse_bse_vc_project_dev(gwbse_ctx* ctx, int k, const double* X_dev, int ldx, double* W_dev);
+int gwbse_bse_vc_expand_dev(gwbse_ctx* ctx, double alpha, int screened, int k, const double* W_dev, double* Y_dev,
+                            int ldy);
 /* accounting for bench.py: algorithmic flops (F_bse), operator products and trial columns applied
  * through gwbse_bse_matmul(_dev) since the last reset */
 int gwbse_bse_stats(gwbse_ctx* ctx, double* algo_flops, long long* products, long long* columns, int reset);

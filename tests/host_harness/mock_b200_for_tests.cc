@@ -1001,6 +1001,35 @@ int gwbse_bse_matmul_dev(gwbse_ctx* ctx, int cqp, int cx, int cd, int cd2, int k
                          int ldy) {
   return gwbse_bse_matmul(ctx, cqp, cx, cd, cd2, k, X, ldx, Y, ldy);
 }
+int gwbse_bse_vc_project_dev(gwbse_ctx* ctx, int k, const double* X, int ldx, double* W) {
+  MOCK_BEGIN(ctx)
+  REQUIRE(ctx->bse_ready, "BSE operator not configured (gwbse_bse_configure)");
+  const int vt = ctx->vt, ct = ctx->ct, vo = ctx->voff, co = ctx->coff, naux = ctx->naux;
+  REQUIRE(ldx >= vt * ct, "Shape mismatch in BSE projection");
+  for (int j = 0; j < k; ++j)
+    for (int chi = 0; chi < naux; ++chi) {
+      double s = 0.0;
+      for (int v = 0; v < vt; ++v)
+        for (int c = 0; c < ct; ++c) s += ctx->M(vo + v, co + c, chi) * X[(size_t)j * ldx + ct * v + c];
+      W[(size_t)j * naux + chi] = s;
+    }
+  MOCK_END(ctx)
+}
+int gwbse_bse_vc_expand_dev(gwbse_ctx* ctx, double alpha, int screened, int k, const double* W, double* Y, int ldy) {
+  MOCK_BEGIN(ctx)
+  REQUIRE(ctx->bse_ready, "BSE operator not configured (gwbse_bse_configure)");
+  const int vt = ctx->vt, ct = ctx->ct, vo = ctx->voff, co = ctx->coff, naux = ctx->naux;
+  REQUIRE(ldy >= vt * ct, "Shape mismatch in BSE expansion");
+  for (int j = 0; j < k; ++j)
+    for (int v = 0; v < vt; ++v)
+      for (int c = 0; c < ct; ++c) {
+        double s = 0.0;
+        for (int chi = 0; chi < naux; ++chi)
+          s += ctx->M(vo + v, co + c, chi) * (screened ? ctx->eps_inv[chi] : 1.0) * W[(size_t)j * naux + chi];
+        Y[(size_t)j * ldy + ct * v + c] += alpha * s;
+      }
+  MOCK_END(ctx)
+}
 int gwbse_bse_stats(gwbse_ctx* ctx, double* fl, long long* p, long long* c, int reset) {
   if (!ctx) return 1;
   if (fl) *fl = ctx->bse_flops;

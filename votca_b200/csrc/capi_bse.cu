@@ -56,6 +56,70 @@ BlockView cv_view(gwbse_ctx* ctx) {
   return {ctx->buf("bse_gcv", (size_t)ctx->naux * st.ct * vtp), vtp, (long long)st.ct * vtp};
 }
 
+// The two halves of the exchange term, also the building blocks of the cross-spin coupling of the unrestricted
+// operator (BSE_OPERATOR_UKS::add_direct_cross_tda_block, bse_operator_uks.cc:174-211), where the projection of one
+// spin channel is expanded in the other:
+//   project: W[chi, kv]     = sum_{v, c} M[v][c, chi] X[(v, c), kv]          (all-reduced over the ranks)
+//   expand : Y[(v, c), kv] += alpha sum_chi M[v][c, chi] W[chi, kv]           (rows of the v slices this rank owns)
+void vc_project(gwbse_ctx* ctx, int k, const double* Xin, int ldin, double* W) {
+  auto& st = ctx->bse;
+  const int ct = st.ct, naux = ctx->naux, npad = ctx->npad, world = ctx->world;
+  const int nvloc = ctx->owned_count(st.voff, st.vt, ctx->rank);
+  const int v_rel0 = ctx->first_owned(st.voff, ctx->rank) - st.voff;
+  const int lvfirst = nvloc ? ctx->local_index(st.voff + v_rel0) : 0;
+  if (nvloc > 0) {
+    GemmParams p;
+    p.M = naux;
+    p.N = k;
+    p.Ko = nvloc;
+    p.Ki = ct;
+    p.A.ptr = ctx->X + (long long)lvfirst * npad + st.coff;
+    p.A.s_ri = ctx->ldx;
+    p.A.s_ki = 1;
+    p.A.s_ko = npad;
+    p.B.ptr = Xin + (long long)v_rel0 * ct;
+    p.B.s_ri = ldin;
+    p.B.s_ki = 1;
+    p.B.s_ko = (long long)world * ct;
+    p.C = W;
+    p.sC_mi = 1;
+    p.sC_ni = naux;
+    ctx->gemm(p);
+  } else {
+    GW_CUDA(cudaMemsetAsync(W, 0, sizeof(double) * (size_t)naux * k, ctx->stream));
+  }
+  allreduce_dev(ctx, W, (size_t)naux * k);
+}
+
+void vc_expand(gwbse_ctx* ctx, double alpha, int k, const double* W, double* Y, int ldy) {
+  auto& st = ctx->bse;
+  const int ct = st.ct, naux = ctx->naux, npad = ctx->npad, world = ctx->world;
+  const int nvloc = ctx->owned_count(st.voff, st.vt, ctx->rank);
+  const int v_rel0 = ctx->first_owned(st.voff, ctx->rank) - st.voff;
+  const int lvfirst = nvloc ? ctx->local_index(st.voff + v_rel0) : 0;
+  if (nvloc <= 0) return;
+  GemmParams q;
+  q.M = nvloc * ct;
+  q.N = k;
+  q.Ki = naux;
+  q.A.ptr = ctx->X + (long long)lvfirst * npad + st.coff;
+  q.A.Lr = ct;
+  q.A.s_ri = 1;
+  q.A.s_ro = npad;
+  q.A.s_ki = ctx->ldx;
+  q.B.ptr = W;
+  q.B.s_ri = naux;
+  q.B.s_ki = 1;
+  q.C = Y + (long long)v_rel0 * ct;
+  q.Lm = ct;
+  q.sC_mi = 1;
+  q.sC_mo = (long long)world * ct;
+  q.sC_ni = ldy;
+  q.alpha = alpha;
+  q.beta = 1.0;
+  ctx->gemm(q);
+}
+
 // Y = H X.  With a sharded Mmn every rank computes the part its slices contribute (v-slices for Hx / Hd2,
 // c-slices for Hd, rank 0 the Hqp term) into disjoint or additive entries of Y, then Y is all-reduced.
 void bse_matmul_dev(gwbse_ctx* ctx, int cqp, int cx, int cd, int cd2, int k, const double* Xin, int ldin, double* Y,
@@ -132,52 +196,8 @@ void bse_matmul_dev(gwbse_ctx* ctx, int cqp, int cx, int cd, int cd2, int k, con
 
   if (cx != 0) {
     double* W = ctx->buf("bse_W", (size_t)naux * k);
-    if (nvloc > 0) {
-      // W[chi, kv] = sum_{v local, c} M[v][c,chi] X[(v,c),kv]
-      GemmParams p;
-      p.M = naux;
-      p.N = k;
-      p.Ko = nvloc;
-      p.Ki = ct;
-      p.A.ptr = X + (long long)lvfirst * npad + coff;
-      p.A.s_ri = ldx;
-      p.A.s_ki = 1;
-      p.A.s_ko = npad;
-      p.B.ptr = Xin + (long long)v_rel0 * ct;
-      p.B.s_ri = ldin;
-      p.B.s_ki = 1;
-      p.B.s_ko = (long long)world * ct;
-      p.C = W;
-      p.sC_mi = 1;
-      p.sC_ni = naux;
-      ctx->gemm(p);
-    } else {
-      GW_CUDA(cudaMemsetAsync(W, 0, sizeof(double) * (size_t)naux * k, ctx->stream));
-    }
-    allreduce_dev(ctx, W, (size_t)naux * k);
-    if (nvloc > 0) {
-      // Y[(v,c), kv] += cx sum_chi M[v][c,chi] W[chi,kv]   for the local v
-      GemmParams q;
-      q.M = nvloc * ct;
-      q.N = k;
-      q.Ki = naux;
-      q.A.ptr = X + (long long)lvfirst * npad + coff;
-      q.A.Lr = ct;
-      q.A.s_ri = 1;
-      q.A.s_ro = npad;
-      q.A.s_ki = ldx;
-      q.B.ptr = W;
-      q.B.s_ri = naux;
-      q.B.s_ki = 1;
-      q.C = Y + (long long)v_rel0 * ct;
-      q.Lm = ct;
-      q.sC_mi = 1;
-      q.sC_mo = (long long)world * ct;
-      q.sC_ni = ldy;
-      q.alpha = cx;
-      q.beta = 1.0;
-      ctx->gemm(q);
-    }
+    vc_project(ctx, k, Xin, ldin, W);
+    vc_expand(ctx, (double)cx, k, W, Y, ldy);
   }
 
   if (cd != 0 || cd2 != 0) {
@@ -360,6 +380,35 @@ int gwbse_bse_matmul(gwbse_ctx* ctx, int cqp, int cx, int cd, int cd2, int k, co
     GW_CUDA(copy2d_async(Y, sizeof(double) * ldy, Yd, sizeof(double) * B, sizeof(double) * B, k,
                               cudaMemcpyDeviceToHost, ctx->stream));
     GW_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  GW_API_END(ctx)
+}
+
+int gwbse_bse_vc_project_dev(gwbse_ctx* ctx, int k, const double* X_dev, int ldx, double* W_dev) {
+  GW_API_BEGIN(ctx)
+  GW_PROF(ctx, "bse_vc_project");
+  GW_REQUIRE(ctx->bse.ready, "BSE operator not configured (gwbse_bse_configure)");
+  GW_REQUIRE(ldx >= ctx->bse.size, "Shape mismatch in BSE projection");
+  if (k > 0) vc_project(ctx, k, X_dev, ldx, W_dev);
+  GW_API_END(ctx)
+}
+
+int gwbse_bse_vc_expand_dev(gwbse_ctx* ctx, double alpha, int screened, int k, const double* W_dev, double* Y_dev,
+                            int ldy) {
+  GW_API_BEGIN(ctx)
+  GW_PROF(ctx, "bse_vc_expand");
+  GW_REQUIRE(ctx->bse.ready, "BSE operator not configured (gwbse_bse_configure)");
+  GW_REQUIRE(ldy >= ctx->bse.size, "Shape mismatch in BSE expansion");
+  GW_REQUIRE(ctx->world == 1, "gwbse_bse_vc_expand_dev accumulates into Y in place: single-GPU (the UKS operator)");
+  if (k > 0) {
+    const double* W = W_dev;
+    if (screened) {  // W <- diag(eps^-1) W
+      double* Ws = ctx->buf("bse_Ws", (size_t)ctx->naux * k);
+      launch_diag_scale('L', ctx->naux, k, W_dev, ctx->naux, ctx->bse.eps_inv, Ws, ctx->naux, ctx->stream);
+      ctx->launches++;
+      W = Ws;
+    }
+    vc_expand(ctx, alpha, k, W, Y_dev, ldy);
   }
   GW_API_END(ctx)
 }

@@ -43,6 +43,7 @@ class Device {
   void check(int rc) const {
     if (rc != 0) throw std::runtime_error(gwbse_last_error(ctx_));
   }
+  void sync() const { check(gwbse_sync(ctx_)); }
 
   // device buffer with RAII (CudaMatrix analogue, cudamatrix.h:95-190)
   class Buffer {

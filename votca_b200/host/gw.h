@@ -17,6 +17,7 @@ namespace xtp {
 
 
 class GW {
+  friend class GW_UKS;  // uks.h: two GW objects are the spin channels of the unrestricted loop
   using EvalStage = qp_solver::EvalStage;
   using QPStats = qp_solver::Stats;
   using QPRootCandidate = qp_solver::RootCandidate;
@@ -62,13 +63,14 @@ class GW {
     double qsgw_max_virt_correction = 0.5;
   };
 
-  // gw.cc:35-58
-  void configure(const options& opt) {
+  // gw.cc:35-58.  `evaluator`: a ready-made self-energy evaluator instead of the factory's (GW_UKS installs the
+  // spin channel's Sigma_PPM_UKS, gw_uks.cc:46-49)
+  void configure(const options& opt, std::unique_ptr<Sigma_base> evaluator = nullptr) {
     opt_ = opt;
     qp_solver::NormalizeGridSearchOptions(opt_);
     qptotal_ = opt_.qpmax - opt_.qpmin + 1;
     rpa_.configure(opt_.homo, opt_.rpamin, opt_.rpamax);
-    sigma_ = SigmaFactory_Create(opt_.sigma_integration, Mmn_, rpa_);
+    sigma_ = evaluator ? std::move(evaluator) : SigmaFactory_Create(opt_.sigma_integration, Mmn_, rpa_);
     Sigma_base::options sigma_opt;
     sigma_opt.homo = opt_.homo;
     sigma_opt.qpmax = opt_.qpmax;

@@ -117,7 +117,9 @@ class PPM {
  public:
   PPM() : screening_r(0.0), screening_i(0.5) {}
   // ppm.cc:30-59; phi stays on the device (phi_dev) and is consumed by MultiplyRight without a PCIe trip
-  void PPM_construct_parameters(const RPA& rpa, const TCMatrix_gwbse& Mmn) {
+  // RPA_T: RPA, or RPA_UKS (uks.h) whose dielectric matrix is the sum over both spin channels
+  template <class RPA_T>
+  void PPM_construct_parameters(const RPA_T& rpa, const TCMatrix_gwbse& Mmn) {
     const Device& dev = Mmn.device();
     const Index n = Mmn.auxsize();
     double* eps = rpa.calculate_epsilon_r_dev(screening_r);
@@ -166,14 +168,10 @@ class Sigma_PPM : public Sigma_base {
  public:
   Sigma_PPM(TCMatrix_gwbse& Mmn, const RPA& rpa) : Sigma_base(Mmn, rpa) {}
   // sigma_ppm.cc:32-35
-  void PrepareScreening() final {
+  void PrepareScreening() override {
     ppm_.PPM_construct_parameters(rpa_, Mmn_);
-    Mmn_.MultiplyRightWithAuxMatrix_dev(ppm_.getPpm_phi_dev(), Mmn_.auxsize());
+    InstallPPM(ppm_);
     ppm_.FreeMatrix();
-    const Device& dev = Mmn_.device();
-    dev.check(gwbse_sigma_ppm_set(dev.ctx(), ppm_.getPpm_weight().data(), ppm_.getPpm_freq().data(),
-                                  rpa_.getRPAInputEnergies().data(), (int)opt_.homo, (int)opt_.rpamin,
-                                  (int)opt_.qpmin, opt_.eta));
   }
   void EvalBatch(const std::vector<int>& levels, const std::vector<double>& freqs, std::vector<double>& sigma,
                  std::vector<double>* dsigma) const final {
@@ -201,6 +199,16 @@ class Sigma_PPM : public Sigma_base {
     return out;
   }
   const PPM& ppm() const { return ppm_; }
+
+ protected:
+  // rotate Mmn into the plasmon-pole basis and hand weights / frequencies to the evaluator kernels
+  void InstallPPM(const PPM& ppm) {
+    Mmn_.MultiplyRightWithAuxMatrix_dev(ppm.getPpm_phi_dev(), Mmn_.auxsize());
+    const Device& dev = Mmn_.device();
+    dev.check(gwbse_sigma_ppm_set(dev.ctx(), ppm.getPpm_weight().data(), ppm.getPpm_freq().data(),
+                                  rpa_.getRPAInputEnergies().data(), (int)opt_.homo, (int)opt_.rpamin,
+                                  (int)opt_.qpmin, opt_.eta));
+  }
 
  private:
   PPM ppm_;
