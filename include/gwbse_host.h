@@ -83,6 +83,16 @@ int gwbse_job_run(gwbse_job* job);
  * Outputs: arrays JAB_{singlet,triplet}_{pert,diag} (Hartree, (levA+levB)^2), J_dimer_*, S_dimer_*; scalars xi_*,
  * pt_rm_discrepancy_*, downfolding_safe_*, levA, levB; gwbse_job_coupling_xml = the <bsecoupling> output subtree. */
 int gwbse_job_run_coupling(gwbse_job* job);
+
+/* GWBSE::Evaluate for an unrestricted reference (the is_uks branches of gwbse.cc:896-997, 1150-1190): GW_UKS
+ * (xtp/src/libxtp/gwbse/gw_uks.cc: spin-summed RPA screening rpa_uks.cc, one shared plasmon-pole model, per-spin
+ * Sigma_x / Sigma_c / QP search) and, for the task "exciton_uks" ("excitons"), the combined exciton problem of BSE_UKS
+ * (bse_uks.cc, bse_operator_uks.cc).  Alpha channel: the restricted inputs; beta channel: arrays "mos_beta",
+ * "mo_energies_beta", "vxc_beta", scalar "homo_beta".  Outputs: the restricted names with "_alpha" / "_beta"
+ * appended (RPA_inputenergies, QPpert_energies, QPdiag_eigenvalues / _eigenvectors, Hqp, Sigma_x, Sigma_c),
+ * "BSE_uks_eigenvalues" / "BSE_uks_eigenvectors" (rows: alpha (v c) then beta (v c)), scalars bse_alpha_size,
+ * bse_beta_size, gw_iterations, uks_converged.  Scope: sigma_integrator=ppm, bse.useTDA=true, one GPU.            */
+int gwbse_job_run_uks(gwbse_job* job);
 const char* gwbse_job_coupling_xml(const gwbse_job* job);
 
 int gwbse_job_array_dims(const gwbse_job* job, const char* name, long* rows, long* cols);

@@ -1,0 +1,122 @@
+"""UKS twins through the CUDA path: GW_UKS and BSE_UKS of votca_b200/host/uks.h behind
+gwbse_job_run_uks, against the oracle (oracle/uks.py) on an open-shell case and against the restricted CUDA path in the
+closed-shell limit.  Two kernel-library contexts (one per spin channel) run on the same GPU."""
+import numpy as np
+import pytest
+
+from oracle import bse as obse
+from oracle import uks
+from tests.helpers import load_golden, methane_integrals, methane_mmn, uks_case
+from tests.test_oracle_golden import _gw_options
+
+pytestmark = pytest.mark.gpu
+
+GRID = dict(gw__qp_grid_steps=601, gw__qp_grid_spacing=0.005)
+
+
+def make_job(c, mode="G0W0", tasks="gw", **opts):
+    from votca_b200.api import Job
+    m = methane_integrals()
+    job = Job(0)
+    job.set_ao3c(m["ao3c"])
+    job.set_array("aux_overlap", m["S"])
+    job.set_array("aux_coulomb", m["V"])
+    job.set_array("mos", c["Ca"])
+    job.set_array("mos_beta", c["Cb"])
+    job.set_array("mo_energies", c["ea"])
+    job.set_array("mo_energies_beta", c["eb"])
+    job.set_array("vxc", c["vxc_a"])
+    job.set_array("vxc_beta", c["vxc_b"])
+    job.set_scalar("homo", c["homo_a"])
+    job.set_scalar("homo_beta", c["homo_b"])
+    job.set_options(tasks=tasks, ranges="full", gw__mode=mode, gw__sigma_integrator="ppm", gw__mixing_order=0,
+                    gw__qp_sc_limit=1e-5, gw__qp_sc_max_iter=50, gw__sc_limit=1e-5, bse__exctotal=3, bse__useTDA=True,
+                    bse__use_Hqp_offdiag=True, bse__davidson__tolerance="lapack", **GRID)
+    for k, v in opts.items():
+        job.set_option(k.replace("__", "."), v)
+    return job
+
+
+def test_closed_shell_limit_equals_the_restricted_path():
+    g = load_golden()
+    c = {"Ca": g["gw/mo_eigenvectors"], "Cb": g["gw/mo_eigenvectors"], "ea": g["inline/gw_mo_eigenvalues"],
+         "eb": g["inline/gw_mo_eigenvalues"], "vxc_a": g["gw/vxc"], "vxc_b": g["gw/vxc"], "homo_a": 4, "homo_b": 4}
+    for mode in ("G0W0", "evGW"):
+        u = make_job(c, mode)
+        u.run_uks()
+        r = make_job(c, mode)
+        r.run()
+        for s in ("_alpha", "_beta"):
+            assert np.abs(u.get("QPpert_energies" + s) - r.get("QPpert_energies")).max() < 1e-9
+            assert np.abs(u.get("Hqp" + s) - r.get("Hqp")).max() < 1e-9
+            assert np.abs(u.get("RPA_inputenergies" + s) - r.get("RPA_inputenergies")).max() < 1e-9
+        # the reference's own fixture of this restricted case (test_gw.cc: gw/ref.mm, 1e-4 relative)
+        if mode == "G0W0":
+            ref = np.diag(g["gw/ref"])
+            assert np.abs(u.get("QPpert_energies_alpha") - ref).max() / np.abs(ref).max() < 1e-4
+        u.close()
+        r.close()
+
+
+@pytest.mark.parametrize("mode", ["G0W0", "evGW"])
+def test_open_shell_gw_and_excitons_against_the_oracle(mode):
+    c = uks_case()
+    iters = 1 if mode == "G0W0" else 50
+    og = uks.GWUKS(methane_mmn(c["Ca"]), methane_mmn(c["Cb"]), c["vxc_a"], c["vxc_b"], c["ea"], c["eb"])
+    og.configure(_gw_options(qp_grid_steps=601, qp_grid_spacing=0.005, gw_sc_max_iterations=iters), c["homo_a"],
+                 c["homo_b"])
+    og.calculate_gw_perturbation()
+    og.calculate_hqp()
+    job = make_job(c, mode, tasks="gw,exciton_uks")
+    job.run_uks()
+    for s, tag in enumerate(("_alpha", "_beta")):
+        assert np.abs(job.get("QPpert_energies" + tag) - og.get_gwa_results(s)).max() < 1e-6  # Hartree
+        assert np.abs(job.get("Hqp" + tag) - og.get_hqp(s)).max() < 1e-6
+        assert np.abs(job.get("RPA_inputenergies" + tag) - og.rpa.energies(s)).max() < 1e-6
+    assert np.abs(job.get("QPpert_energies_alpha") - job.get("QPpert_energies_beta")).max() > 1e-3
+    ob = uks.BSEUKS(methane_mmn(c["Ca"]), methane_mmn(c["Cb"]))
+    o = obse.BSEOptions(cmax=16, rpamax=16, rpamin=0, vmin=0, nmax=3, useTDA=True, homo=4, qpmin=0, qpmax=16,
+                        davidson_tolerance="lapack", davidson_maxiter=50, use_Hqp_offdiag=True)
+    ob.configure(o, c["homo_a"], c["homo_b"], og.rpa.energies(0), og.rpa.energies(1), og.get_hqp(0), og.get_hqp(1))
+    w = np.linalg.eigvalsh(ob.operator_tda().dense())
+    got = job.get("BSE_uks_eigenvalues")
+    assert job.scalar("uks_converged") == 1.0
+    assert (job.scalar("bse_alpha_size"), job.scalar("bse_beta_size")) == (5 * 12, 4 * 13)
+    assert np.abs(got - w[:3]).max() < 1e-6
+    X = job.get("BSE_uks_eigenvectors")
+    assert X.shape == (112, 3) and np.abs(X.T @ X - np.eye(3)).max() < 1e-8
+    job.close()
+
+
+def test_unrestricted_operator_against_the_oracle_matrix():
+    """BSE_OPERATOR_UKS<1,1,1,0> (gwbse_bse_matmul_dev per channel + gwbse_bse_vc_project_dev / _vc_expand_dev across
+    them) with Hqp reduced to its diagonal: the ten lowest excitons against the oracle's dense operator."""
+    c = uks_case()
+    job = make_job(c, "G0W0", tasks="gw,exciton_uks", bse__exctotal=10, bse__use_Hqp_offdiag=False)
+    job.run_uks()
+    og = uks.GWUKS(methane_mmn(c["Ca"]), methane_mmn(c["Cb"]), c["vxc_a"], c["vxc_b"], c["ea"], c["eb"])
+    og.configure(_gw_options(qp_grid_steps=601, qp_grid_spacing=0.005), c["homo_a"], c["homo_b"])
+    og.calculate_gw_perturbation()
+    og.calculate_hqp()
+    ob = uks.BSEUKS(methane_mmn(c["Ca"]), methane_mmn(c["Cb"]))
+    o = obse.BSEOptions(cmax=16, rpamax=16, rpamin=0, vmin=0, nmax=10, useTDA=True, homo=4, qpmin=0, qpmax=16,
+                        use_Hqp_offdiag=False)
+    ob.configure(o, c["homo_a"], c["homo_b"], og.rpa.energies(0), og.rpa.energies(1), og.get_hqp(0), og.get_hqp(1))
+    w = np.linalg.eigvalsh(ob.operator_tda().dense())
+    assert np.abs(np.sort(job.get("BSE_uks_eigenvalues")) - w[:10]).max() < 1e-6
+    job.close()
+
+
+def test_what_is_not_on_this_path_is_refused():
+    c = uks_case()
+    for kw, msg in ((dict(tasks="gw,singlets"), "not defined for open-shell"),
+                    (dict(tasks="gw,exciton_uks", bse__useTDA=False), "not on this path"),
+                    (dict(gw__sigma_integrator="exact"), "not available for unrestricted")):
+        job = make_job(c, **kw)
+        with pytest.raises(Exception, match=msg):
+            job.run_uks()
+        job.close()
+    job = make_job(c, tasks="gw,exciton_uks")
+    with pytest.raises(Exception, match="unrestricted reference"):
+        job.run()  # the restricted driver refuses the unrestricted task
+    job.close()

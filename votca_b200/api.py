@@ -451,6 +451,11 @@ class Job:
         (include/gwbse_host.h: gwbse_job_run_coupling); options: set_option("bsecoupling.<key>", value)."""
         self._ck(self.api.gwbse_job_run_coupling(self.h))
 
+    def run_uks(self):
+        """GW_UKS (+ BSE_UKS for the task exciton_uks) on an unrestricted reference: beta channel inputs "mos_beta",
+        "mo_energies_beta", "vxc_beta", scalar "homo_beta" (include/gwbse_host.h: gwbse_job_run_uks)."""
+        self._ck(self.api.gwbse_job_run_uks(self.h))
+
     def coupling_xml(self):
         return self.api.gwbse_job_coupling_xml(self.h).decode()
 

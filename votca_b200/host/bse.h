@@ -77,6 +77,40 @@ class BSE {
     SetupDirectInteractionOperator(RPAInputEnergies, 0.0);
   }
 
+  // bse.cc:147-186 (and bse_uks.cc:92-133, the same routine with the spin channel's homo in `o`): Hqp cut or
+  // extended to the BSE window; levels outside the GW window get their RPA input energies on the diagonal
+  static MatrixXd AdjustHqpSizeFor(const options& o, const MatrixXd& Hqp, const VectorXd& RPAInputEnergies) {
+    const Index vtotal = o.homo - o.vmin + 1, ctotal = o.cmax - o.homo;
+    Index hqp_size = vtotal + ctotal;
+    Index gwsize = o.qpmax - o.qpmin + 1;
+    Index RPAoffset = o.vmin - o.rpamin;
+    MatrixXd Hqp_BSE = MatrixXd::Zero(hqp_size, hqp_size);
+    if (o.vmin >= o.qpmin) {
+      Index start = o.vmin - o.qpmin;
+      if (o.cmax <= o.qpmax) {
+        Hqp_BSE = Hqp.block(start, start, hqp_size, hqp_size);
+      } else {
+        Index virtoffset = gwsize - start;
+        Hqp_BSE.setBlock(0, 0, Hqp.block(start, start, virtoffset, virtoffset));
+        Index virt_extra = o.cmax - o.qpmax;
+        for (Index i = 0; i < virt_extra; ++i)
+          Hqp_BSE(hqp_size - virt_extra + i, hqp_size - virt_extra + i) = RPAInputEnergies(RPAoffset + virtoffset + i);
+      }
+    }
+    if (o.vmin < o.qpmin) {
+      Index occ_extra = o.qpmin - o.vmin;
+      for (Index i = 0; i < occ_extra; ++i) Hqp_BSE(i, i) = RPAInputEnergies(RPAoffset + i);
+      Hqp_BSE.setBlock(occ_extra, occ_extra, Hqp.block(0, 0, gwsize, gwsize));
+      if (o.cmax > o.qpmax) {
+        Index virtoffset = occ_extra + gwsize;
+        Index virt_extra = o.cmax - o.qpmax;
+        for (Index i = 0; i < virt_extra; ++i)
+          Hqp_BSE(hqp_size - virt_extra + i, hqp_size - virt_extra + i) = RPAInputEnergies(RPAoffset + virtoffset + i);
+      }
+    }
+    return Hqp_BSE;
+  }
+
   const MatrixXd& getHqp() const { return Hqp_; }
   // bse.cc:206-232: the TDA operators as BSECoupling uses them (they refer to this object's screening and Hqp)
   SingletOperator_TDA getSingletOperator_TDA() const {
@@ -202,34 +236,7 @@ class BSE {
  private:
   // bse.cc:147-186
   MatrixXd AdjustHqpSize(const MatrixXd& Hqp, const VectorXd& RPAInputEnergies) {
-    Index hqp_size = bse_vtotal_ + bse_ctotal_;
-    Index gwsize = opt_.qpmax - opt_.qpmin + 1;
-    Index RPAoffset = opt_.vmin - opt_.rpamin;
-    MatrixXd Hqp_BSE = MatrixXd::Zero(hqp_size, hqp_size);
-    if (opt_.vmin >= opt_.qpmin) {
-      Index start = opt_.vmin - opt_.qpmin;
-      if (opt_.cmax <= opt_.qpmax) {
-        Hqp_BSE = Hqp.block(start, start, hqp_size, hqp_size);
-      } else {
-        Index virtoffset = gwsize - start;
-        Hqp_BSE.setBlock(0, 0, Hqp.block(start, start, virtoffset, virtoffset));
-        Index virt_extra = opt_.cmax - opt_.qpmax;
-        for (Index i = 0; i < virt_extra; ++i)
-          Hqp_BSE(hqp_size - virt_extra + i, hqp_size - virt_extra + i) = RPAInputEnergies(RPAoffset + virtoffset + i);
-      }
-    }
-    if (opt_.vmin < opt_.qpmin) {
-      Index occ_extra = opt_.qpmin - opt_.vmin;
-      for (Index i = 0; i < occ_extra; ++i) Hqp_BSE(i, i) = RPAInputEnergies(RPAoffset + i);
-      Hqp_BSE.setBlock(occ_extra, occ_extra, Hqp.block(0, 0, gwsize, gwsize));
-      if (opt_.cmax > opt_.qpmax) {
-        Index virtoffset = occ_extra + gwsize;
-        Index virt_extra = opt_.cmax - opt_.qpmax;
-        for (Index i = 0; i < virt_extra; ++i)
-          Hqp_BSE(hqp_size - virt_extra + i, hqp_size - virt_extra + i) = RPAInputEnergies(RPAoffset + virtoffset + i);
-      }
-    }
-    return Hqp_BSE;
+    return AdjustHqpSizeFor(opt_, Hqp, RPAInputEnergies);
   }
 
   // bse.cc:188-204: eps(energy) -> eigen-decomposition -> rotate Mmn, all on the device

@@ -28,9 +28,10 @@ class Logger {
 
 class Device {
  public:
-  explicit Device(int device = 0) {
+  explicit Device(int device = 0) : index_(device) {
     if (gwbse_ctx_create(device, &ctx_) != 0) throw std::runtime_error(gwbse_create_error());
   }
+  int index() const { return index_; }  // CUDA device ordinal: a second context on the same GPU (UKS beta channel)
   ~Device() { gwbse_ctx_destroy(ctx_); }
   Device(const Device&) = delete;
   Device& operator=(const Device&) = delete;
@@ -104,6 +105,7 @@ class Device {
   }
 
  private:
+  int index_ = 0;
   gwbse_ctx* ctx_ = nullptr;
 };
 

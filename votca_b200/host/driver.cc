@@ -472,6 +472,82 @@ int gwbse_job_run_coupling(gwbse_job* job) {
   JOB_END(job)
 }
 
+// Unrestricted reference: GW_UKS + BSE_UKS (tasks "gw" / "exciton_uks").  Alpha channel = the restricted inputs
+// ("mos", "mo_energies", "vxc", scalar "homo"), beta channel = "mos_beta", "mo_energies_beta", "vxc_beta", "homo_beta".
+int gwbse_job_run_uks(gwbse_job* job) {
+  JOB_BEGIN(job)
+  auto need = [&](const char* n) -> const MatrixXd& {
+    auto it = job->in.find(n);
+    if (it == job->in.end()) throw std::runtime_error(std::string("input array '") + n + "' not set");
+    return it->second;
+  };
+  GWBSE::Inputs in;
+  in.unrestricted = true;
+  if (!job->scalars.count("homo") || !job->scalars.count("homo_beta"))
+    throw std::runtime_error("input scalars 'homo' and 'homo_beta' not set");
+  in.homo = static_cast<Index>(job->scalars["homo"]);
+  in.homo_beta = static_cast<Index>(job->scalars["homo_beta"]);
+  in.ScaHFX = job->scalars.count("ScaHFX") ? job->scalars["ScaHFX"] : 0.0;
+  const MatrixXd& mos = need("mos");
+  const MatrixXd& mos_b = need("mos_beta");
+  const VectorXd mo_e = mat2vec(need("mo_energies")), mo_e_b = mat2vec(need("mo_energies_beta"));
+  in.mos = &mos;
+  in.mos_beta = &mos_b;
+  in.mo_energies = &mo_e;
+  in.mo_energies_beta = &mo_e_b;
+  in.vxc = &need("vxc");
+  in.vxc_beta = &need("vxc_beta");
+  std::unique_ptr<DeviceAOIntegrals> device_ints;
+  const bool have_arrays = job->ints.ao3c || job->ints.ao3c_dev || job->ints.fn;
+  if (!have_arrays && job->basis_data[0] && job->basis_data[1]) {
+    for (int b = 0; b < 2; ++b)
+      if (!job->dev_basis[b]) job->dev_basis[b] = std::make_unique<DeviceAOBasis>(*job->dev, *job->basis_data[b]);
+    device_ints = std::make_unique<DeviceAOIntegrals>(
+        *job->dev, *job->dev_basis[1], *job->dev_basis[0], job->in.count("aux_overlap") ? &job->in["aux_overlap"] : nullptr,
+        job->in.count("aux_coulomb") ? &job->in["aux_coulomb"] : nullptr);
+    in.integrals = device_ints.get();
+  } else {
+    job->ints.S = &need("aux_overlap");
+    job->ints.V = &need("aux_coulomb");
+    in.integrals = &job->ints;
+  }
+  GWBSE gwbse(*job->dev, job->log);
+  gwbse.Initialize(job->options, in);
+  GWBSE::ResultsUKS r = gwbse.EvaluateUKS();
+  auto& o = job->out;
+  o.clear();
+  for (int s = 0; s < 2; ++s) {
+    const std::string sp = s == 0 ? "_alpha" : "_beta";
+    o["RPA_inputenergies" + sp] = vec2mat(r.RPA_inputenergies[s]);
+    o["QPpert_energies" + sp] = vec2mat(r.QPpert_energies[s]);
+    o["QPdiag_eigenvalues" + sp] = vec2mat(r.QPdiag_eigenvalues[s]);
+    o["QPdiag_eigenvectors" + sp] = r.QPdiag_eigenvectors[s];
+    o["Hqp" + sp] = r.Hqp[s];
+    o["Sigma_x" + sp] = r.Sigma_x[s];
+    o["Sigma_c" + sp] = r.Sigma_c[s];
+  }
+  o["BSE_uks_eigenvalues"] = vec2mat(r.BSE_uks.eigenvalues);
+  o["BSE_uks_eigenvectors"] = r.BSE_uks.eigenvectors;
+  auto& sc = job->out_scalars;
+  sc.clear();
+  sc["rpamin"] = r.rpamin;
+  sc["rpamax"] = r.rpamax;
+  sc["qpmin"] = r.qpmin;
+  sc["qpmax"] = r.qpmax;
+  sc["bse_vmin"] = r.bse_vmin;
+  sc["bse_cmax"] = r.bse_cmax;
+  sc["bse_alpha_size"] = r.alpha_size;
+  sc["bse_beta_size"] = r.beta_size;
+  sc["gw_iterations"] = r.gw_iterations;
+  sc["uks_davidson_iterations"] = r.davidson_iterations;
+  sc["uks_converged"] = r.BSE_uks.success;
+  sc["removed_functions"] = r.removed_functions;
+  sc["time_fill"] = r.time_fill;
+  sc["time_gw"] = r.time_gw;
+  sc["time_bse"] = r.time_bse;
+  JOB_END(job)
+}
+
 const char* gwbse_job_coupling_xml(const gwbse_job* job) { return job ? job->coupling_xml.c_str() : ""; }
 
 int gwbse_job_array_dims(const gwbse_job* job, const char* name, long* rows, long* cols) {

@@ -13,6 +13,7 @@
 #include "bse.h"
 #include "checkpoint.h"
 #include "gw.h"
+#include "uks.h"
 
 namespace votca {
 namespace xtp {
@@ -165,6 +166,22 @@ class GWBSE {
     // BSE-only runs (do_gw == false): orbitals_.QPdiag / RPAInputEnergies from a previous run
     const MatrixXd* Hqp = nullptr;
     const VectorXd* rpa_input_energies = nullptr;
+    // unrestricted reference (Orbitals::hasUnrestrictedOrbitals): homo / mos / mo_energies / vxc above are the alpha
+    // channel's, these the beta channel's; evaluated by EvaluateUKS
+    bool unrestricted = false;
+    Index homo_beta = -1;
+    const MatrixXd* mos_beta = nullptr;
+    const VectorXd* mo_energies_beta = nullptr;
+    const MatrixXd* vxc_beta = nullptr;
+  };
+  // what GWBSE::Evaluate stores in an unrestricted Orbitals object (gwbse.cc:976-997, 1186-1190)
+  struct ResultsUKS {
+    Index rpamin = 0, rpamax = 0, qpmin = 0, qpmax = 0, bse_vmin = 0, bse_cmax = 0;
+    VectorXd RPA_inputenergies[2], QPpert_energies[2], QPdiag_eigenvalues[2];
+    MatrixXd QPdiag_eigenvectors[2], Hqp[2], Sigma_x[2], Sigma_c[2];
+    EigenSystem BSE_uks;
+    Index alpha_size = 0, beta_size = 0, gw_iterations = 0, davidson_iterations = 0, removed_functions = 0;
+    double time_fill = 0, time_gw = 0, time_bse = 0;
   };
   struct Results {
     Index rpamin = 0, rpamax = 0, qpmin = 0, qpmax = 0, bse_vmin = 0, bse_cmax = 0;
@@ -190,7 +207,10 @@ class GWBSE {
     in_ = in;
     if (!in.mos || !in.mo_energies || in.homo < 0) throw std::runtime_error("GWBSE: MOs, energies and homo required");
     Index rpamax = 0, rpamin = 0, qpmin = 0, qpmax = 0, bse_vmin = 0, bse_cmax = 0;
-    const Index homo = in.homo;
+    if (in.unrestricted && (!in.mos_beta || !in.mo_energies_beta || in.homo_beta < 0))
+      throw std::runtime_error("GWBSE: an unrestricted reference needs beta MOs, energies and homo");
+    // gwbse.cc:70-79: the level ranges of an unrestricted reference follow the larger of the two occupations
+    const Index homo = in.unrestricted ? std::max(in.homo, in.homo_beta) : in.homo;
     const Index num_of_levels = in.mos->cols();
     const Index num_of_occlevels = homo + 1;
     const std::string ranges = options.str("ranges");
@@ -287,8 +307,15 @@ class GWBSE {
     bseopt_.min_print_weight = options.dbl("bse.print_weight");
     std::string tasks = options.str("tasks");
     for (char& c : tasks) c = static_cast<char>(std::tolower(static_cast<unsigned char>(c)));
-    if (tasks.find("exciton") != std::string::npos)
-      throw std::runtime_error("tasks 'excitons' / 'exciton_uks' (unrestricted BSE, bse_uks.cc) are not on this path");
+    // gwbse.cc:345-358: the unrestricted task is driven by GWBSE_UKS (gwbse_job_run_uks); here it is an error as it
+    // is in the reference for a restricted Orbitals object
+    do_bse_exciton_uks_ = tasks.find("exciton") != std::string::npos;
+    if (do_bse_exciton_uks_ && !in.unrestricted)
+      throw std::runtime_error("tasks 'excitons' / 'exciton_uks' need an unrestricted reference (gwbse_job_run_uks)");
+    if (in.unrestricted && (tasks.find("singlets") != std::string::npos || tasks.find("triplets") != std::string::npos))
+      throw std::runtime_error(
+          "Invalid gwbse task for UKS reference: 'singlets' and 'triplets' are not defined for open-shell systems.\n"
+          "Use 'exciton_uks' (or 'excitons') instead.");
     // gwbse.cc:531-547
     gwopt_.do_qsgw = options.flag("gw.do_qsgw");
     gwopt_.qsgw_max_iterations = options.idx("gw.qsgw_max_iterations");
@@ -298,7 +325,8 @@ class GWBSE {
       log_(" QSGW enabled: max_iter=" + std::to_string(gwopt_.qsgw_max_iterations) +
            " sc_limit=" + std::to_string(gwopt_.qsgw_sc_limit) + " Ha");
     do_gw_ = tasks.find("gw") != std::string::npos;
-    if (tasks.find("all") != std::string::npos) do_gw_ = do_bse_singlets_ = do_bse_triplets_ = true;
+    if (do_bse_exciton_uks_) do_gw_ = true;
+    if (tasks.find("all") != std::string::npos && !in.unrestricted) do_gw_ = do_bse_singlets_ = do_bse_triplets_ = true;
     if (tasks.find("singlets") != std::string::npos) do_bse_singlets_ = true;
     if (tasks.find("triplets") != std::string::npos) do_bse_triplets_ = true;
     gwopt_.sigma_integration = options.str("gw.sigma_integrator");
@@ -341,6 +369,81 @@ class GWBSE {
 
   const GW::options& gw_options() const { return gwopt_; }
   const BSE::options& bse_options() const { return bseopt_; }
+
+  // gwbse.cc:896-997 + 1150-1190, the is_uks branches: two Mmn tensors (one kernel-library context per spin channel
+  // on the same GPU), GW_UKS, then the combined exciton problem
+  ResultsUKS EvaluateUKS() {
+    using clock = std::chrono::system_clock;
+    if (!in_.unrestricted) throw std::runtime_error("GWBSE::EvaluateUKS needs an unrestricted reference");
+    if (dev_.world() > 1) throw std::runtime_error("the unrestricted path is single-GPU in this build");
+    if (!in_.integrals) throw std::runtime_error("GWBSE: AO integral source required");
+    if (!in_.vxc || !in_.vxc_beta) throw std::runtime_error("GWBSE: vxc (alpha and beta) is an input of this path");
+    ResultsUKS res;
+    res.rpamin = gwopt_.rpamin;
+    res.rpamax = gwopt_.rpamax;
+    res.qpmin = gwopt_.qpmin;
+    res.qpmax = gwopt_.qpmax;
+    res.bse_vmin = bseopt_.vmin;
+    res.bse_cmax = bseopt_.cmax;
+    auto t0 = clock::now();
+    Device dev_beta(dev_.index());
+    TCMatrix_gwbse_spin Mmn(dev_, dev_beta);
+    const Index max_3c = std::max(bseopt_.cmax, gwopt_.qpmax);
+    for (int s = 0; s < 2; ++s) {
+      TCMatrix_gwbse& M = s == 0 ? Mmn.alpha : Mmn.beta;
+      M.Initialize(in_.integrals->AuxSize(), gwopt_.rpamin, max_3c, gwopt_.rpamin, gwopt_.rpamax);
+      log_(s == 0 ? " Calculating alpha spin Mmn " : " Calculating beta spin Mmn ");
+      M.Fill(*in_.integrals, s == 0 ? *in_.mos : *in_.mos_beta);
+      M.device().sync();
+    }
+    res.removed_functions = Mmn.alpha.Removedfunctions();
+    res.time_fill = std::chrono::duration<double>(clock::now() - t0).count();
+    t0 = clock::now();
+    GW_UKS::options o;
+    static_cast<GW::options&>(o) = gwopt_;
+    o.homo_alpha = in_.homo;
+    o.homo_beta = in_.homo_beta;
+    GW_UKS gw(log_, Mmn, *in_.vxc, *in_.vxc_beta, *in_.mo_energies, *in_.mo_energies_beta);
+    gw.configure(o);
+    gw.CalculateGWPerturbation();
+    res.QPpert_energies[0] = gw.getGWAResultsAlpha();
+    res.QPpert_energies[1] = gw.getGWAResultsBeta();
+    res.RPA_inputenergies[0] = gw.RPAInputEnergiesAlpha();
+    res.RPA_inputenergies[1] = gw.RPAInputEnergiesBeta();
+    gw.CalculateHQP();
+    res.Hqp[0] = gw.getHQPAlpha();
+    res.Hqp[1] = gw.getHQPBeta();
+    auto ea = gw.DiagonalizeQPHamiltonianAlpha(), eb = gw.DiagonalizeQPHamiltonianBeta();
+    res.QPdiag_eigenvalues[0] = ea.first;
+    res.QPdiag_eigenvectors[0] = ea.second;
+    res.QPdiag_eigenvalues[1] = eb.first;
+    res.QPdiag_eigenvectors[1] = eb.second;
+    for (int s = 0; s < 2; ++s) {
+      res.Sigma_x[s] = gw.Sigma_x(s == 0 ? Spin::Alpha : Spin::Beta);
+      res.Sigma_c[s] = gw.Sigma_c(s == 0 ? Spin::Alpha : Spin::Beta);
+    }
+    res.gw_iterations = gw.iterations();
+    res.time_gw = std::chrono::duration<double>(clock::now() - t0).count();
+    log_(" UKS GW calculation took " + std::to_string(res.time_gw) + " seconds.");
+    if (do_bse_exciton_uks_) {
+      t0 = clock::now();
+      // Mmn still carries the orthogonal plasmon-pole rotation of the last GW iteration; eps(0), its spectrum and
+      // the operator are invariant under it (as in the restricted path, where BSE follows GW on the same tensor)
+      BSE_UKS bse(log_, Mmn);
+      bse.configure(bseopt_, in_.homo, in_.homo_beta, res.RPA_inputenergies[0], res.RPA_inputenergies[1], res.Hqp[0],
+                    res.Hqp[1]);
+      res.BSE_uks = bse.Solve_excitons_uks();
+      log_(" Solved combined UKS BSE exciton problem ");
+      ExcitonUKSOperator_TDA H = bse.getExcitonOperator_TDA();
+      res.alpha_size = H.alpha_size();
+      res.beta_size = H.beta_size();
+      res.davidson_iterations = bse.last_davidson_iterations();
+      res.time_bse = std::chrono::duration<double>(clock::now() - t0).count();
+      log_(" BSE calculation took " + std::to_string(res.time_bse) + " seconds.");
+    }
+    log_(" GWBSE calculation finished ");
+    return res;
+  }
 
   // gwbse.cc:822-1250
   Results Evaluate() {
@@ -605,6 +708,7 @@ class GWBSE {
   BSE::options bseopt_;
   MatrixXd qsgw_mos_;  // MO coefficients with the QP-window columns rotated to the QSGW wavefunctions
   bool do_gw_ = false, do_bse_singlets_ = false, do_bse_triplets_ = false, do_dynamical_screening_bse_ = false;
+  bool do_bse_exciton_uks_ = false;
 };
 
 }  // namespace xtp

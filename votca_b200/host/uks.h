@@ -1,0 +1,450 @@
+// Unrestricted (UKS) twins of the GW-BSE classes - host mirror of xtp/include/votca/xtp/{rpa_uks,sigma_base_uks,
+// gw_uks,bse_operator_uks,bse_uks}.h and their sources.
+//
+// The reference duplicates every restricted class with a spin index.  Here a spin channel IS a restricted pipeline
+// on its own kernel-library context: the alpha and the beta Mmn tensor live in two gwbse_ctx objects on the same GPU
+// (two streams, one address space), and every per-spin operation - exchange, plasmon-pole rotation, batched
+// self-energy evaluation, the lock-step root search, the same-spin blocks of the BSE operator - is the restricted
+// code path on that context, unchanged.  What is genuinely unrestricted is small and lives in this file:
+//   * the dielectric matrix is the sum over both channels.  The restricted weights carry the closed-shell factor 2
+//     (rpa.cc:115-127 against rpa_uks.cc:243-269, :351-363), so eps_uks = (eps_alpha + eps_beta) / 2, combined on the
+//     device from the two contexts' own eps buffers;
+//   * ONE plasmon-pole model, built from eps_uks, shared by both evaluators (gw_uks.cc:107-122);
+//   * the RPA input energies of both channels are updated together (rpa_uks.cc:41-71);
+//   * the BSE operator acts on [alpha (v c) | beta (v c)]; its same-spin blocks are gwbse_bse_matmul_dev per context,
+//     the coupling between the channels (bse_operator_uks.cc:174-211) is one projection on the input channel's
+//     context and one screened expansion on the output channel's (gwbse_bse_vc_project_dev / _expand_dev).
+// Scope: sigma_integrator = ppm (the default), BSE in the Tamm-Dancoff approximation, one GPU.
+#pragma once
+#include "bse.h"
+#include "gw.h"
+
+namespace votca {
+namespace xtp {
+
+enum class Spin { Alpha = 0, Beta = 1 };
+
+// threecenter.h:185-199 of the reference (TCMatrix_gwbse_spin)
+struct TCMatrix_gwbse_spin {
+  TCMatrix_gwbse_spin(const Device& dev_alpha, const Device& dev_beta) : alpha(dev_alpha), beta(dev_beta) {}
+  TCMatrix_gwbse alpha, beta;
+  TCMatrix_gwbse& operator[](Spin s) { return s == Spin::Alpha ? alpha : beta; }
+  const TCMatrix_gwbse& operator[](Spin s) const { return s == Spin::Alpha ? alpha : beta; }
+};
+
+class RPA_UKS {
+ public:
+  RPA_UKS(Logger& log, const TCMatrix_gwbse_spin& Mmn) : Mmn_(Mmn), alpha_(log, Mmn.alpha), beta_(log, Mmn.beta) {}
+
+  void configure(Index homo_alpha, Index homo_beta, Index rpamin, Index rpamax) {
+    rpamin_ = rpamin;
+    rpamax_ = rpamax;
+    alpha_.configure(homo_alpha, rpamin, rpamax);
+    beta_.configure(homo_beta, rpamin, rpamax);
+  }
+  void setRPAInputEnergies(const VectorXd& e_alpha, const VectorXd& e_beta) {
+    alpha_.setRPAInputEnergies(e_alpha);
+    beta_.setRPAInputEnergies(e_beta);
+  }
+  const VectorXd& getRPAInputEnergiesAlpha() const { return alpha_.getRPAInputEnergies(); }
+  const VectorXd& getRPAInputEnergiesBeta() const { return beta_.getRPAInputEnergies(); }
+  RPA& channel(Spin s) { return s == Spin::Alpha ? alpha_ : beta_; }
+  const RPA& channel(Spin s) const { return s == Spin::Alpha ? alpha_ : beta_; }
+
+  // rpa_uks.cc:41-71 with ShiftUncorrectedEnergies / getMaxCorrection (:163-201): GW energies inside the qp window,
+  // everything below / above it shifted by the largest correction seen among the occupied / virtual levels
+  void UpdateRPAInputEnergies(const VectorXd& dft_alpha, const VectorXd& dft_beta, const VectorXd& gwa_alpha,
+                              const VectorXd& gwa_beta, Index qpmin) {
+    const Index rpatotal = rpamax_ - rpamin_ + 1;
+    for (int s = 0; s < 2; ++s) {
+      RPA& ch = s == 0 ? alpha_ : beta_;
+      const VectorXd& dft = s == 0 ? dft_alpha : dft_beta;
+      const VectorXd& gwa = s == 0 ? gwa_alpha : gwa_beta;
+      VectorXd e = dft.segment(rpamin_, rpatotal);
+      const Index gwsize = gwa.size(), qpmax = qpmin + gwsize - 1, lumo = ch.homo() + 1;
+      for (Index i = 0; i < gwsize; ++i) e(qpmin - rpamin_ + i) = gwa(i);
+      auto largest = [&](Index lo, Index hi) {
+        double m = 0.0;
+        for (Index i = lo; i <= hi; ++i) m = std::max(m, std::abs(e(i - rpamin_) - dft(i)));
+        return m;
+      };
+      const double occ = largest(qpmin, ch.homo()), virt = largest(lumo, qpmax);
+      for (Index i = 0; i < qpmin - rpamin_; ++i) e(i) -= occ;
+      for (Index i = e.size() - (rpamax_ - qpmax); i < e.size(); ++i) e(i) += virt;
+      ch.setRPAInputEnergies(e);
+    }
+  }
+
+  // eps_uks on the alpha context's device; valid until the next call
+  double* calculate_epsilon_i_dev(double frequency) const {
+    return combine(alpha_.calculate_epsilon_i_dev(frequency), [&] { return beta_.calculate_epsilon_i_dev(frequency); });
+  }
+  double* calculate_epsilon_r_dev(double frequency) const {
+    return combine(alpha_.calculate_epsilon_r_dev(frequency), [&] { return beta_.calculate_epsilon_r_dev(frequency); });
+  }
+  double* calculate_epsilon_r_dev(std::complex<double> f) const {
+    return combine(alpha_.calculate_epsilon_r_dev(f), [&] { return beta_.calculate_epsilon_r_dev(f); });
+  }
+  MatrixXd calculate_epsilon_i(double frequency) const { return fetch(calculate_epsilon_i_dev(frequency)); }
+  MatrixXd calculate_epsilon_r(double frequency) const { return fetch(calculate_epsilon_r_dev(frequency)); }
+  MatrixXd calculate_epsilon_r(std::complex<double> f) const { return fetch(calculate_epsilon_r_dev(f)); }
+
+ private:
+  template <class BetaCall>
+  double* combine(double* eps_alpha, BetaCall beta_call) const {
+    const Device& da = Mmn_.alpha.device();
+    const Device& db = Mmn_.beta.device();
+    const Index n = Mmn_.alpha.auxsize();
+    double* eps_beta = beta_call();
+    db.sync();  // the beta context's stream has produced its matrix before the alpha context reads it
+    if (eps_.size() < static_cast<size_t>(n * n)) eps_ = da.alloc(static_cast<size_t>(n * n));
+    da.check(gwbse_dev_memset_zero(da.ctx(), eps_.get(), static_cast<size_t>(n * n)));
+    da.check(gwbse_axpy_dev(da.ctx(), (int)n, (int)n, 0.5, eps_alpha, (int)n, eps_.get(), (int)n));
+    da.check(gwbse_axpy_dev(da.ctx(), (int)n, (int)n, 0.5, eps_beta, (int)n, eps_.get(), (int)n));
+    da.sync();
+    return eps_.get();
+  }
+  MatrixXd fetch(const double* p) const {
+    const Index n = Mmn_.alpha.auxsize();
+    return Mmn_.alpha.device().download(p, n, n);
+  }
+
+  const TCMatrix_gwbse_spin& Mmn_;
+  RPA alpha_, beta_;
+  Index rpamin_ = 0, rpamax_ = 0;
+  mutable Device::Buffer eps_;
+};
+
+// sigma_ppm_uks.h / .cc: the restricted evaluator of one channel with the plasmon-pole model handed in
+class Sigma_PPM_UKS final : public Sigma_PPM {
+ public:
+  Sigma_PPM_UKS(TCMatrix_gwbse& Mmn, const RPA& rpa_channel) : Sigma_PPM(Mmn, rpa_channel) {}
+  void SetSharedPPM(const PPM& ppm) { shared_ = &ppm; }
+  void PrepareScreening() override {  // sigma_ppm_uks.cc:30-37
+    if (!shared_)
+      throw std::runtime_error("Sigma_PPM_UKS: shared PPM parameters were not set before PrepareScreening().");
+    InstallPPM(*shared_);
+  }
+
+ private:
+  const PPM* shared_ = nullptr;
+};
+
+class GW_UKS {
+ public:
+  struct options : GW::options {
+    Index homo_alpha = 0, homo_beta = 0;
+  };
+
+  GW_UKS(Logger& log, TCMatrix_gwbse_spin& Mmn, const MatrixXd& vxc_alpha, const MatrixXd& vxc_beta,
+         const VectorXd& dft_energies_alpha, const VectorXd& dft_energies_beta)
+      : log_(log), Mmn_(Mmn), dft_{&dft_energies_alpha, &dft_energies_beta}, rpa_(log, Mmn),
+        gw_{std::make_unique<GW>(log, Mmn.alpha, vxc_alpha, dft_energies_alpha),
+            std::make_unique<GW>(log, Mmn.beta, vxc_beta, dft_energies_beta)} {}
+
+  // gw_uks.cc:38-123
+  void configure(const options& opt) {
+    opt_ = opt;
+    if (opt_.sigma_integration != "ppm")
+      throw std::runtime_error("GW_UKS: sigma_integrator=" + opt_.sigma_integration +
+                               " is not available for unrestricted references on this path (ppm is)");
+    if (opt_.do_qsgw) throw std::runtime_error("GW_UKS: QSGW is defined for restricted references only");
+    rpa_.configure(opt_.homo_alpha, opt_.homo_beta, opt_.rpamin, opt_.rpamax);
+    for (int s = 0; s < 2; ++s) {
+      GW::options o = opt_;
+      o.homo = s == 0 ? opt_.homo_alpha : opt_.homo_beta;
+      TCMatrix_gwbse& M = s == 0 ? Mmn_.alpha : Mmn_.beta;
+      auto sigma = std::make_unique<Sigma_PPM_UKS>(M, gw_[s]->rpa_);
+      sigma->SetSharedPPM(ppm_);
+      gw_[s]->configure(o, std::move(sigma));
+      log_(std::string(" UKS ") + (s == 0 ? "alpha" : "beta") + " effective ranges: HOMO=" + std::to_string(o.homo) +
+           " LUMO=" + std::to_string(o.homo + 1) + " | RPA [" + std::to_string(o.rpamin) + ":" +
+           std::to_string(o.rpamax) + "] | GW [" + std::to_string(o.qpmin) + ":" + std::to_string(o.qpmax) + "]");
+    }
+    qptotal_ = opt_.qpmax - opt_.qpmin + 1;
+  }
+
+  // gw_uks.cc:188-295
+  void CalculateGWPerturbation() {
+    VectorXd freq[2];
+    VectorXd shifted[2];
+    for (int s = 0; s < 2; ++s) {
+      GW& g = *gw_[s];
+      g.Sigma_x_ = (1 - opt_.ScaHFX) * g.sigma_->CalcExchangeMatrix();
+      shifted[s] = *dft_[s];
+      for (Index i = g.opt_.homo + 1; i < shifted[s].size(); ++i) shifted[s](i) += opt_.shift;
+      freq[s] = shifted[s].segment(opt_.qpmin, qptotal_);
+    }
+    log_(" Calculated spin-resolved Hartree exchange contribution");
+    log_(" Scissor shifting alpha/beta DFT energies by: " + std::to_string(opt_.shift) + " Hrt");
+    const Index rpatotal = opt_.rpamax - opt_.rpamin + 1;
+    rpa_energies(shifted[0].segment(opt_.rpamin, rpatotal), shifted[1].segment(opt_.rpamin, rpatotal));
+    Anderson mixing[2];
+    for (Anderson& m : mixing) m.Configure(opt_.gw_mixing_order, opt_.gw_mixing_alpha);
+    for (Index i_gw = 0; i_gw < opt_.gw_sc_max_iterations; ++i_gw) {
+      iterations_ = i_gw + 1;
+      for (auto& g : gw_) g->gw_sc_iteration_ = i_gw;
+      if (i_gw % opt_.reset_3c == 0 && i_gw != 0) {
+        Mmn_.alpha.Rebuild();
+        Mmn_.beta.Rebuild();
+        log_(" Rebuilding alpha/beta 3c integrals");
+      }
+      // one plasmon-pole model from the spin-summed dielectric matrix, installed in both channels
+      ppm_.PPM_construct_parameters(rpa_, Mmn_.alpha);
+      Mmn_.alpha.device().sync();
+      for (auto& g : gw_) g->sigma_->PrepareScreening();
+      Mmn_.beta.device().sync();
+      ppm_.FreeMatrix();
+      log_(" Calculated unrestricted screening via RPA");
+      if (opt_.gw_mixing_order > 0 && i_gw > 0)
+        for (int s = 0; s < 2; ++s) mixing[s].UpdateInput(freq[s]);
+      for (int s = 0; s < 2; ++s) freq[s] = gw_[s]->SolveQP(freq[s]);
+      if (opt_.gw_sc_max_iterations > 1) {
+        const VectorXd old[2] = {rpa_.getRPAInputEnergiesAlpha(), rpa_.getRPAInputEnergiesBeta()};
+        if (opt_.gw_mixing_order > 0 && i_gw > 0)
+          for (int s = 0; s < 2; ++s) {
+            mixing[s].UpdateOutput(freq[s]);
+            freq[s] = mixing[s].MixHistory();
+          }
+        rpa_.UpdateRPAInputEnergies(*dft_[0], *dft_[1], freq[0], freq[1], opt_.qpmin);
+        sync_channel_energies();
+        log_(" GW_Iteration:" + std::to_string(i_gw));
+        const bool conv_a = gw_[0]->Converged(rpa_.getRPAInputEnergiesAlpha(), old[0], opt_.gw_sc_limit);
+        const bool conv_b = gw_[1]->Converged(rpa_.getRPAInputEnergiesBeta(), old[1], opt_.gw_sc_limit);
+        if (conv_a && conv_b) {
+          log_(" Converged after " + std::to_string(i_gw + 1) + " unrestricted GW iterations.");
+          break;
+        } else if (i_gw == opt_.gw_sc_max_iterations - 1) {
+          log_(" WARNING! UKS GW-self-consistency cycle not converged after " +
+               std::to_string(opt_.gw_sc_max_iterations) + " iterations.");
+          break;
+        }
+      }
+    }
+    for (int s = 0; s < 2; ++s) {
+      const VectorXd diag = gw_[s]->sigma_->CalcCorrelationDiag(freq[s]);
+      for (Index i = 0; i < qptotal_; ++i) gw_[s]->Sigma_c_(i, i) = diag(i);
+    }
+  }
+
+  VectorXd getGWAResultsAlpha() const { return gw_[0]->getGWAResults(); }
+  VectorXd getGWAResultsBeta() const { return gw_[1]->getGWAResults(); }
+  const VectorXd& RPAInputEnergiesAlpha() const { return rpa_.getRPAInputEnergiesAlpha(); }
+  const VectorXd& RPAInputEnergiesBeta() const { return rpa_.getRPAInputEnergiesBeta(); }
+  // gw_uks.cc:758-790
+  void CalculateHQP() {
+    for (auto& g : gw_) g->CalculateHQP();
+  }
+  MatrixXd getHQPAlpha() const { return gw_[0]->getHQP(); }
+  MatrixXd getHQPBeta() const { return gw_[1]->getHQP(); }
+  std::pair<VectorXd, MatrixXd> DiagonalizeQPHamiltonianAlpha() const { return gw_[0]->DiagonalizeQPHamiltonian(); }
+  std::pair<VectorXd, MatrixXd> DiagonalizeQPHamiltonianBeta() const { return gw_[1]->DiagonalizeQPHamiltonian(); }
+  const MatrixXd& Sigma_x(Spin s) const { return gw_[(int)s]->Sigma_x(); }
+  const MatrixXd& Sigma_c(Spin s) const { return gw_[(int)s]->Sigma_c(); }
+  Index iterations() const { return iterations_; }
+
+ private:
+  // the two channels' RPA objects inside the GW halves ARE the channel energies of rpa_: keep both views equal
+  void rpa_energies(const VectorXd& ea, const VectorXd& eb) {
+    rpa_.setRPAInputEnergies(ea, eb);
+    sync_channel_energies();
+  }
+  void sync_channel_energies() {
+    gw_[0]->rpa_.setRPAInputEnergies(rpa_.getRPAInputEnergiesAlpha());
+    gw_[1]->rpa_.setRPAInputEnergies(rpa_.getRPAInputEnergiesBeta());
+  }
+
+  Logger& log_;
+  TCMatrix_gwbse_spin& Mmn_;
+  const VectorXd* dft_[2];
+  RPA_UKS rpa_;
+  PPM ppm_;
+  std::unique_ptr<GW> gw_[2];
+  options opt_;
+  Index qptotal_ = 0, iterations_ = 0;
+};
+
+struct BSEOperatorUKS_Options {
+  Index homo_alpha, homo_beta, rpamin, qpmin, vmin, cmax;
+};
+
+// bse_operator_uks.h / .cc on the combined space [alpha | beta], each channel ordered ctotal * v + c
+template <Index cqp, Index cx, Index cd, Index cd2>
+class BSE_OPERATOR_UKS final : public MatrixFreeOperator {
+ public:
+  BSE_OPERATOR_UKS(const VectorXd& Hd_operator, const TCMatrix_gwbse_spin& Mmn, const MatrixXd& Hqp_alpha,
+                   const MatrixXd& Hqp_beta)
+      : epsilon_0_inv_(Hd_operator), Mmn_(Mmn), Hqp_{&Hqp_alpha, &Hqp_beta} {
+    static_assert(!(cd2 != 0 && cd != 0), "Hamiltonian cannot contain Hd and Hd2 at the same time");
+    static_assert(cd2 == 0, "the cross-spin Hd2 block (full BSE, bse_operator_uks.cc:252-255) is not on this path");
+  }
+  // bse_operator_uks.cc:26-45
+  void configure(BSEOperatorUKS_Options opt) {
+    opt_ = opt;
+    Index offset = 0;
+    for (int s = 0; s < 2; ++s) {
+      const Index homo = s == 0 ? opt.homo_alpha : opt.homo_beta;
+      blk_[s].homo = homo;
+      blk_[s].vtotal = homo - opt.vmin + 1;
+      blk_[s].ctotal = opt.cmax - homo;
+      blk_[s].size = blk_[s].vtotal * blk_[s].ctotal;
+      blk_[s].offset = offset;
+      offset += blk_[s].size;
+    }
+    this->set_size(offset);
+  }
+  Index alpha_size() const { return blk_[0].size; }
+  Index beta_size() const { return blk_[1].size; }
+
+  // bse_operator_uks.cc:277-352: the diagonal has no contribution from the coupling between the channels
+  VectorXd diagonal() const override {
+    VectorXd d(this->size());
+    for (int s = 0; s < 2; ++s) {
+      bind(s);
+      const Device& dev = channel(s).device();
+      dev.check(gwbse_bse_diagonal(dev.ctx(), (int)cqp, (int)cx, (int)cd, (int)cd2, d.data() + blk_[s].offset));
+    }
+    return d;
+  }
+
+  void apply_dev(const double* X_dev, Index ldx, Index k, double* Y_dev, Index ldy) const override {
+    const Index naux = Mmn_.alpha.auxsize();
+    for (int s = 0; s < 2; ++s) {  // same-spin blocks: the restricted operator of the channel (:228-246)
+      bind(s);
+      const Device& dev = channel(s).device();
+      dev.check(gwbse_bse_matmul_dev(dev.ctx(), (int)cqp, (int)cx, (int)cd, (int)cd2, (int)k, X_dev + blk_[s].offset,
+                                     (int)ldx, Y_dev + blk_[s].offset, (int)ldy));
+      dev.sync();
+    }
+    if (cd != 0) {  // coupling between the channels, transition-density form, screened (:174-211, :248-252)
+      if (W_.size() < static_cast<size_t>(naux * k)) W_ = channel(0).device().alloc(static_cast<size_t>(naux * k));
+      for (int in = 0; in < 2; ++in) {
+        const int out = 1 - in;
+        const Device& din = channel(in).device();
+        const Device& dout = channel(out).device();
+        din.check(gwbse_bse_vc_project_dev(din.ctx(), (int)k, X_dev + blk_[in].offset, (int)ldx, W_.get()));
+        din.sync();
+        dout.check(gwbse_bse_vc_expand_dev(dout.ctx(), -double(cd), 1, (int)k, W_.get(), Y_dev + blk_[out].offset,
+                                           (int)ldy));
+        dout.sync();
+      }
+    }
+  }
+
+  MatrixXd matmul(const MatrixXd& input) const override {
+    if (input.rows() != this->size()) throw std::runtime_error("Shape mismatch in BSE_OPERATOR_UKS::matmul");
+    const Device& dev = device();
+    Device::Buffer X = dev.upload(input);
+    Device::Buffer Y = dev.alloc(static_cast<size_t>(std::max<Index>(input.size(), 1)));
+    apply_dev(X.get(), input.rows(), input.cols(), Y.get(), input.rows());
+    return dev.download(Y.get(), input.rows(), input.cols());
+  }
+  const Device& device() const override { return Mmn_.alpha.device(); }
+
+ private:
+  struct Block {
+    Index homo = 0, vtotal = 0, ctotal = 0, size = 0, offset = 0;
+  };
+  const TCMatrix_gwbse& channel(int s) const { return s == 0 ? Mmn_.alpha : Mmn_.beta; }
+  void bind(int s) const {
+    const Device& dev = channel(s).device();
+    const MatrixXd& H = *Hqp_[s];
+    if (H.rows() < blk_[s].vtotal + blk_[s].ctotal) throw std::runtime_error("Hqp is smaller than the BSE window");
+    dev.check(gwbse_bse_configure(dev.ctx(), (int)blk_[s].homo, (int)opt_.rpamin, (int)opt_.vmin, (int)opt_.cmax,
+                                  epsilon_0_inv_.data(), H.data(), (int)H.rows()));
+  }
+  BSEOperatorUKS_Options opt_;
+  Block blk_[2];
+  const VectorXd& epsilon_0_inv_;
+  const TCMatrix_gwbse_spin& Mmn_;
+  const MatrixXd* Hqp_[2];
+  mutable Device::Buffer W_;
+};
+
+typedef BSE_OPERATOR_UKS<1, 1, 1, 0> ExcitonUKSOperator_TDA;
+typedef BSE_OPERATOR_UKS<1, 0, 0, 0> HqpUKSOperator;
+typedef BSE_OPERATOR_UKS<0, 1, 0, 0> HxUKSOperator;
+typedef BSE_OPERATOR_UKS<0, 0, 1, 0> HdUKSOperator;
+
+class BSE_UKS {
+ public:
+  using options = BSE::options;
+  BSE_UKS(Logger& log, TCMatrix_gwbse_spin& Mmn) : log_(log), Mmn_(Mmn) {}
+
+  // bse_uks.cc:51-90 with the screening of gwbse.cc:1157-1175 (spin-summed eps(0), eigen-decomposition, both Mmn
+  // rotated into its eigenbasis); everything stays on the device
+  void configure(const options& opt, Index homo_alpha, Index homo_beta, const VectorXd& RPAInputEnergiesAlpha,
+                 const VectorXd& RPAInputEnergiesBeta, const MatrixXd& Hqp_alpha_in, const MatrixXd& Hqp_beta_in) {
+    opt_ = opt;
+    if (!opt_.useTDA)
+      throw std::runtime_error("BSE_UKS: the full (non-TDA) unrestricted BSE is not on this path; set bse.useTDA=true");
+    homo_[0] = homo_alpha;
+    homo_[1] = homo_beta;
+    for (int s = 0; s < 2; ++s) {
+      // AdjustHqpSize (bse_uks.cc:92-133) is the restricted routine with the channel's homo
+      BSE::options o = opt_;
+      o.homo = homo_[s];
+      MatrixXd H = BSE::AdjustHqpSizeFor(o, s == 0 ? Hqp_alpha_in : Hqp_beta_in,
+                                         s == 0 ? RPAInputEnergiesAlpha : RPAInputEnergiesBeta);
+      Hqp_[s] = opt_.use_Hqp_offdiag ? H : asDiagonal(H.diagonal());
+    }
+    RPA_UKS rpa(log_, Mmn_);
+    rpa.configure(homo_alpha, homo_beta, opt_.rpamin, opt_.rpamax);
+    rpa.setRPAInputEnergies(RPAInputEnergiesAlpha, RPAInputEnergiesBeta);
+    const Device& da = Mmn_.alpha.device();
+    const Index n = Mmn_.alpha.auxsize();
+    double* eps = rpa.calculate_epsilon_r_dev(0.0);
+    Device::Buffer U = da.alloc(static_cast<size_t>(n * n));
+    da.check(gwbse_d2d(da.ctx(), U.get(), eps, static_cast<size_t>(n * n)));
+    VectorXd ev(n);
+    da.check(gwbse_sym_eig_dev(da.ctx(), (int)n, U.get(), (int)n, ev.data()));
+    da.sync();
+    Mmn_.alpha.MultiplyRightWithAuxMatrix_dev(U.get(), n);
+    Mmn_.beta.MultiplyRightWithAuxMatrix_dev(U.get(), n);
+    Mmn_.alpha.device().sync();
+    Mmn_.beta.device().sync();
+    epsilon_0_inv_ = VectorXd::Zero(n);
+    for (Index i = 0; i < n; ++i)
+      if (ev(i) > 1e-8) epsilon_0_inv_(i) = 1.0 / ev(i);
+  }
+
+  ExcitonUKSOperator_TDA getExcitonOperator_TDA() const {
+    ExcitonUKSOperator_TDA H(epsilon_0_inv_, Mmn_, Hqp_[0], Hqp_[1]);
+    H.configure({homo_[0], homo_[1], opt_.rpamin, opt_.qpmin, opt_.vmin, opt_.cmax});
+    return H;
+  }
+
+  // bse_uks.cc:218-235, 453-479
+  EigenSystem Solve_excitons_uks() const {
+    ExcitonUKSOperator_TDA H = getExcitonOperator_TDA();
+    log_(" Setup combined UKS TDA Hamiltonian ");
+    EigenSystem result;
+    DavidsonSolver DS(log_);
+    DS.set_correction(opt_.davidson_correction);
+    DS.set_tolerance(opt_.davidson_tolerance);
+    DS.set_size_update(opt_.davidson_update);
+    DS.set_iter_max(opt_.davidson_maxiter);
+    DS.set_max_search_space(10 * opt_.nmax);
+    DS.solve(H, opt_.nmax);
+    result.eigenvalues = DS.eigenvalues();
+    result.eigenvectors = DS.eigenvectors();
+    result.success = DS.success();
+    iterations_ = DS.num_iterations();
+    return result;
+  }
+  const VectorXd& getEpsilonInv() const { return epsilon_0_inv_; }
+  const MatrixXd& getHqp(Spin s) const { return Hqp_[(int)s]; }
+  Index last_davidson_iterations() const { return iterations_; }
+
+ private:
+  Logger& log_;
+  TCMatrix_gwbse_spin& Mmn_;
+  options opt_;
+  Index homo_[2] = {0, 0};
+  MatrixXd Hqp_[2];
+  VectorXd epsilon_0_inv_;
+  mutable Index iterations_ = 0;
+};
+
+}  // namespace xtp
+}  // namespace votca
