@@ -1,5 +1,6 @@
 // Internal state of a gwbse_ctx (one per process / GPU).
 #pragma once
+#include <nvtx3/nvToolsExt.h>
 #include <cuda_runtime.h>
 #include <cusolverDn.h>
 
@@ -201,18 +202,22 @@ struct gwbse_ctx {
   int local_count(int upto) const { return upto <= rank ? 0 : (upto - rank + world - 1) / world; }
 };
 
+// Every C-ABI entry point is an NVTX range (nvtx3 is header-only and a no-op unless a tool is attached: nsys / ncu
+// --nvtx show the reference's stage names) and, with the option "profile", a CUDA-event region.
 struct ProfScope {
   gwbse_ctx* ctx;
   const char* name;
   cudaEvent_t e0 = nullptr;
   std::chrono::steady_clock::time_point t0;
   ProfScope(gwbse_ctx* c, const char* n) : ctx(c), name(n) {
+    nvtxRangePushA(n);
     if (!ctx->profile) return;
     e0 = ctx->get_event();
     cudaEventRecord(e0, ctx->stream);
     t0 = std::chrono::steady_clock::now();
   }
   ~ProfScope() {
+    nvtxRangePop();
     if (!e0) return;
     cudaEvent_t e1 = ctx->get_event();
     cudaEventRecord(e1, ctx->stream);
