@@ -31,7 +31,7 @@ def mock_dir():
 MOCK_RUN_FILES = ["tests/test_gpu_kernels.py", "tests/test_gpu_host.py", "tests/test_gpu_zz_reference_checkpoint.py",
                   "tests/test_zzz_gpu_ao3c_device.py", "tests/test_zz_gpu_orb_output.py",
                   "tests/test_zz_gpu_cudapipeline_cases.py", "tests/test_zz_gpu_benchmark_tool.py",
-                  "tests/test_zz_gpu_host_options.py", "tests/test_gpu_zz_qsgw.py", "tests/test_zz_gpu_bsecoupling.py", "tests/test_zz_gpu_uks.py"]
+                  "tests/test_zz_gpu_host_options.py", "tests/test_gpu_zz_qsgw.py", "tests/test_zz_gpu_bsecoupling.py", "tests/test_zz_gpu_uks.py", "tests/test_zz_gpu_dftgwbse_tool.py"]
 
 
 @pytest.fixture(scope="module")
@@ -103,6 +103,10 @@ def test_uks_twins_pass_on_the_mock(mock_run):
     """GW_UKS / BSE_UKS (votca_b200/host/uks.h, two contexts) against oracle/uks.py and, in the closed-shell limit,
     against the restricted path and the reference's gw/ref.mm (tests/test_zz_gpu_uks.py)."""
     _check(mock_run, "tests/test_zz_gpu_uks.py", 5)
+
+
+def test_dftgwbse_tool_passes_on_the_mock(mock_run):
+    _check(mock_run, "tests/test_zz_gpu_dftgwbse_tool.py", 2)
 
 
 def test_every_host_layer_gpu_test_file_runs_on_the_mock():

@@ -104,3 +104,37 @@ def test_integral_producer_callback(golden, methane):
         job.close()
     assert sum(c for _, c in calls) == 17 and [o for o, _ in calls] == sorted(o for o, _ in calls)
     assert np.abs(res[0] - res[1]).max() < 1e-12
+
+
+def test_switching_the_integral_producer_on_one_job(golden, methane):
+    """One Job, three producers in a row - a partial host range, then the callback, then the whole array: a later
+    producer must not be shadowed by state of an earlier one (a stale device pointer or 'held' range once made the
+    callback silently unused)."""
+    from votca_b200.api import Job
+    job = Job(0)
+    job.set_scalar("homo", 4)
+    job.set_array("mos", golden["gw/mo_eigenvectors"])
+    job.set_array("mo_energies", golden["inline/gw_mo_eigenvalues"])
+    job.set_array("vxc", golden["gw/vxc"])
+    job.set_array("aux_overlap", methane["S"])
+    job.set_array("aux_coulomb", methane["V"])
+    job.set_options(ranges="full", **GW_OPTS)
+    whole = np.ascontiguousarray(methane["ao3c"])
+    job.set_ao3c_partial(17, 17, 0, 17, whole.ctypes.data, False)
+    job.run()
+    first = job.get("QPpert_energies").copy()
+    calls = []
+
+    def producer(off, cnt):
+        calls.append((off, cnt))
+        return 2.0 * whole[off:off + cnt]  # deliberately different integrals: the callback has to be what is used
+
+    job.set_ao3c_callback(17, 17, producer)
+    job.run()
+    second = job.get("QPpert_energies").copy()
+    assert sum(c for _, c in calls) == 17
+    assert np.abs(second - first).max() > 1e-3
+    job.set_ao3c(whole)
+    job.run()
+    assert np.abs(job.get("QPpert_energies") - first).max() < 1e-12
+    job.close()
