@@ -31,17 +31,10 @@ class Device {
   explicit Device(int device = 0) : index_(device) {
     if (gwbse_ctx_create(device, &ctx_) != 0) throw std::runtime_error(gwbse_create_error());
   }
-  int index() const { return index_; }  // CUDA device ordinal: a second context on the same GPU (UKS beta channel)
-  // A second kernel-library context on the same GPU (own stream, cuSOLVER handle and buffers), created on first use
-  // and kept for this object's lifetime: work that may run beside this context's stream from another host thread
-  // (V^-1/2 beside the three-centre fill, threecenter.h).
-  const Device& side() const {
-    if (!side_) side_ = std::make_unique<Device>(index_);
-    return *side_;
-  }
   ~Device() { gwbse_ctx_destroy(ctx_); }
   Device(const Device&) = delete;
   Device& operator=(const Device&) = delete;
+  int index() const { return index_; }  // CUDA device ordinal: a second context on the same GPU (UKS beta channel)
   gwbse_ctx* ctx() const { return ctx_; }
   // multi-GPU: one process per GPU, Mmn sharded m-cyclically (gwbse_comm_init)
   int rank() const { return gwbse_comm_rank(ctx_); }
@@ -114,7 +107,6 @@ class Device {
  private:
   int index_ = 0;
   gwbse_ctx* ctx_ = nullptr;
-  mutable std::unique_ptr<Device> side_;
 };
 
 }  // namespace xtp

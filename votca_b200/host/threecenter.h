@@ -3,11 +3,8 @@
 // are replaced by an AOIntegralSource (the reference-side shim implements it with ComputeAO3cBlock,
 // libint2_calls.cc:544-593).
 #pragma once
-#include <cstdlib>
-#include <exception>
 #include <functional>
 #include <memory>
-#include <thread>
 #include <vector>
 
 #include "device.h"
@@ -69,53 +66,24 @@ class TCMatrix_gwbse {
     dev_.check(gwbse_mmn_set_slice(dev_.ctx(), (int)i, m.data(), (int)m.rows()));
   }
 
-  // threecenter.cc:72-90.  V^-1/2 (AOCoulomb::Pseudo_InvSqrt_GWBSE: two Naux x Naux symmetric eigensolves, chains of
-  // small latency-bound cuSOLVER kernels) does not depend on the three-centre fill, so it runs beside it: on a
-  // second kernel-library context of the same GPU (own stream, own cuSOLVER handle, own buffers), driven by a
-  // second host thread while this one feeds the fill.  The result stays in that context's buffer and MultiplyRight
-  // reads it from there.  It is work every rank repeats, i.e. part of what bounds multi-GPU scaling.
+  // threecenter.cc:72-90.  (Running V^-1/2 on a second context beside the fill was tried in round 2 and withdrawn:
+  // the TMA-staged GEMM produced wrong tiles when another stream's grids shared the SMs)
   void Fill(const AOIntegralSource& ints, const MatrixXd& dft_orbitals, Index aux_block = 64) {
     ints_ = &ints;
     dft_orbitals_ = &dft_orbitals;
     aux_block_ = aux_block;
-    const MatrixXd& S = ints.AuxOverlap();  // device-produced sources compute these on dev_: before the side thread
+    Fill3cMO(ints, dft_orbitals);
+    const MatrixXd& S = ints.AuxOverlap();
     const MatrixXd& V = ints.AuxCoulomb();
     if (S.rows() != auxbasissize_ || V.rows() != auxbasissize_)
       throw std::runtime_error("aux overlap / Coulomb matrices do not match the aux basis size");
     int removed = 0;
-    static const bool overlap = [] {
-      const char* e = std::getenv("GWBSE_NO_FILL_OVERLAP");
-      return !(e && e[0] == '1');
-    }();
-    if (overlap) {
-      const Device* side_ = &dev_.side();
-      std::exception_ptr side_error;
-      std::thread side([&] {
-        try {
-          side_->check(gwbse_pseudo_invsqrt(side_->ctx(), (int)auxbasissize_, S.data(), V.data(), 5e-7, nullptr, &removed));
-          side_->sync();
-        } catch (...) {
-          side_error = std::current_exception();
-        }
-      });
-      try {
-        Fill3cMO(ints, dft_orbitals);
-      } catch (...) {
-        side.join();
-        throw;
-      }
-      side.join();
-      if (side_error) std::rethrow_exception(side_error);
-      MultiplyRightWithAuxMatrix_dev(gwbse_pseudo_invsqrt_result_dev(side_->ctx()), auxbasissize_);
-    } else {
-      Fill3cMO(ints, dft_orbitals);
-      dev_.check(gwbse_pseudo_invsqrt(dev_.ctx(), (int)auxbasissize_, S.data(), V.data(), 5e-7, nullptr, &removed));
-      MultiplyRightWithAuxMatrix_dev(gwbse_pseudo_invsqrt_result_dev(dev_.ctx()), auxbasissize_);
-    }
+    // V^-1/2 stays on the device and is applied from there
+    dev_.check(gwbse_pseudo_invsqrt(dev_.ctx(), (int)auxbasissize_, S.data(), V.data(), 5e-7, nullptr, &removed));
     removedfunctions_ = removed;
+    MultiplyRightWithAuxMatrix_dev(gwbse_pseudo_invsqrt_result_dev(dev_.ctx()), auxbasissize_);
     if (keep_snapshot_) dev_.check(gwbse_mmn_snapshot(dev_.ctx()));
     have_snapshot_ = keep_snapshot_;
-    dev_.sync();  // MultiplyRight has consumed the side context's buffer
   }
 
   // threecenter.cc:72-90 with the reference's own argument list (auxbasis, dftbasis, dft_orbitals): overlap, two-

@@ -14,6 +14,9 @@
 //   * the BSE operator acts on [alpha (v c) | beta (v c)]; its same-spin blocks are gwbse_bse_matmul_dev per context,
 //     the coupling between the channels (bse_operator_uks.cc:174-211) is one projection on the input channel's
 //     context and one screened expansion on the output channel's (gwbse_bse_vc_project_dev / _expand_dev).
+// The two contexts take turns: every call on one is completed (stream synchronised) before the other gets work.  That
+// costs nothing here (the channels' work is sequential in the reference too) and it is required: the TMA-staged GEMM
+// was found to write wrong tiles when grids of another stream share the SMs with it.
 // Scope: sigma_integrator = ppm (the default), BSE in the Tamm-Dancoff approximation, one GPU.
 #pragma once
 #include "bse.h"
@@ -186,14 +189,19 @@ class GW_UKS {
       for (auto& g : gw_) g->gw_sc_iteration_ = i_gw;
       if (i_gw % opt_.reset_3c == 0 && i_gw != 0) {
         Mmn_.alpha.Rebuild();
+        Mmn_.alpha.device().sync();
         Mmn_.beta.Rebuild();
+        Mmn_.beta.device().sync();
         log_(" Rebuilding alpha/beta 3c integrals");
       }
       // one plasmon-pole model from the spin-summed dielectric matrix, installed in both channels
       ppm_.PPM_construct_parameters(rpa_, Mmn_.alpha);
       Mmn_.alpha.device().sync();
-      for (auto& g : gw_) g->sigma_->PrepareScreening();
-      Mmn_.beta.device().sync();
+      // one channel after the other, never both contexts' grids on the GPU at once (see the note on streams below)
+      for (int s = 0; s < 2; ++s) {
+        gw_[s]->sigma_->PrepareScreening();
+        (s == 0 ? Mmn_.alpha : Mmn_.beta).device().sync();
+      }
       ppm_.FreeMatrix();
       log_(" Calculated unrestricted screening via RPA");
       if (opt_.gw_mixing_order > 0 && i_gw > 0)
@@ -400,8 +408,8 @@ class BSE_UKS {
     da.check(gwbse_sym_eig_dev(da.ctx(), (int)n, U.get(), (int)n, ev.data()));
     da.sync();
     Mmn_.alpha.MultiplyRightWithAuxMatrix_dev(U.get(), n);
-    Mmn_.beta.MultiplyRightWithAuxMatrix_dev(U.get(), n);
     Mmn_.alpha.device().sync();
+    Mmn_.beta.MultiplyRightWithAuxMatrix_dev(U.get(), n);
     Mmn_.beta.device().sync();
     epsilon_0_inv_ = VectorXd::Zero(n);
     for (Index i = 0; i < n; ++i)
