@@ -307,6 +307,14 @@ int gwbse_bse_matmul_dev(gwbse_ctx* ctx, int cqp, int cx, int cd, int cd2, int k
 int gwbse_bse_vc_project_dev(gwbse_ctx* ctx, int k, const double* X_dev, int ldx, double* W_dev);
 int gwbse_bse_vc_expand_dev(gwbse_ctx* ctx, double alpha, int screened, int k, const double* W_dev, double* Y_dev,
                             int ldy);
+/* Cross-spin block of the unrestricted full-BSE B operator (BSE_OPERATOR_UKS::add_direct2_block with different
+ * output and input channels, bse_operator_uks.cc:136-172, 252-255):
+ *   Y[(v1,c1), kv] += alpha sum_{v2,c2,chi} M_ctx[c1][v2,chi] eps_inv[chi] M_other[v1][c2,chi] X[(v2,c2), kv]
+ * (v1, c1) in the ranges of `ctx` (its last gwbse_bse_configure), (v2, c2) in those of the other channel
+ * (homo_other with the same vmin / cmax).  `other` is the context holding the other channel's Mmn on the same GPU;
+ * it must be idle (synchronised) during the call.                                                               */
+int gwbse_bse_hd2_cross_dev(gwbse_ctx* ctx, gwbse_ctx* other, int homo_other, double alpha, int k,
+                            const double* X_dev, int ldx, double* Y_dev, int ldy);
 /* accounting for bench.py: algorithmic flops (F_bse), operator products and trial columns applied
  * through gwbse_bse_matmul(_dev) since the last reset */
 int gwbse_bse_stats(gwbse_ctx* ctx, double* algo_flops, long long* products, long long* columns, int reset);

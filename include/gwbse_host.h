@@ -91,7 +91,8 @@ int gwbse_job_run_coupling(gwbse_job* job);
  * "mo_energies_beta", "vxc_beta", scalar "homo_beta".  Outputs: the restricted names with "_alpha" / "_beta"
  * appended (RPA_inputenergies, QPpert_energies, QPdiag_eigenvalues / _eigenvectors, Hqp, Sigma_x, Sigma_c),
  * "BSE_uks_eigenvalues" / "BSE_uks_eigenvectors" (rows: alpha (v c) then beta (v c)), scalars bse_alpha_size,
- * bse_beta_size, gw_iterations, uks_converged.  Scope: sigma_integrator=ppm, bse.useTDA=true, one GPU.            */
+ * bse_beta_size, gw_iterations, uks_converged; "BSE_uks_eigenvectors2" (Y) for bse.useTDA=false.
+ * Scope: sigma_integrator=ppm, one GPU.                                                                            */
 int gwbse_job_run_uks(gwbse_job* job);
 const char* gwbse_job_coupling_xml(const gwbse_job* job);
 

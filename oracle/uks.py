@@ -359,8 +359,12 @@ def exciton_uks_tda(eps_inv, Ma, Mb, Hqp_a, Hqp_b):  # bse_operator_uks.h: Excit
     return BSEOperatorUKS(1, 1, 1, 0, eps_inv, Ma, Mb, Hqp_a, Hqp_b)
 
 
+def exciton_uks_btda_b(eps_inv, Ma, Mb, Hqp_a, Hqp_b):  # ExcitonUKSOperator_BTDA_B = <0, 1, 0, 1>
+    return BSEOperatorUKS(0, 1, 0, 1, eps_inv, Ma, Mb, Hqp_a, Hqp_b)
+
+
 class BSEUKS:
-    """bse_uks.cc, TDA branch.  Mmn_alpha / Mmn_beta are rotated in place by the screening eigenvectors."""
+    """bse_uks.cc.  Mmn_alpha / Mmn_beta are rotated in place by the screening eigenvectors."""
 
     def __init__(self, Mmn_alpha, Mmn_beta):
         self.M = (Mmn_alpha, Mmn_beta)
@@ -392,6 +396,30 @@ class BSEUKS:
         op = exciton_uks_tda(self.eps_inv, self.M[0], self.M[1], self.Hqp[0], self.Hqp[1])
         op.configure(self.homo[0], self.homo[1], self.opt.rpamin, self.opt.vmin, self.opt.cmax)
         return op
+
+    def operator_btda_b(self):
+        op = exciton_uks_btda_b(self.eps_inv, self.M[0], self.M[1], self.Hqp[0], self.Hqp[1])
+        op.configure(self.homo[0], self.homo[1], self.opt.rpamin, self.opt.vmin, self.opt.cmax)
+        return op
+
+    def solve_excitons_uks_btda_dense(self):
+        """bse_uks.cc:310-398, the dense branch (dim <= 128): [A B; -B -A], positive real roots ascending, phase with the
+        largest |X_k| positive, normalisation X.X - Y.Y = 1."""
+        A, B = self.operator_tda().dense(), self.operator_btda_b().dense()
+        n = A.shape[0]
+        w, V = np.linalg.eig(np.block([[A, B], [-B, -A]]))
+        roots = sorted((w[i].real, i) for i in range(2 * n) if abs(w[i].imag) < 1e-8 and w[i].real > 0.0)
+        nroots = min(self.opt.nmax, len(roots))
+        ev = np.zeros(nroots)
+        X, Y = np.zeros((n, nroots)), np.zeros((n, nroots))
+        for r in range(nroots):
+            vec = V[:, roots[r][1]].real
+            x, y = vec[:n], vec[n:]
+            if x[np.argmax(np.abs(x))] < 0.0:
+                x, y = -x, -y
+            f = 1.0 / math.sqrt(abs(x @ x - y @ y))
+            ev[r], X[:, r], Y[:, r] = roots[r][0], x * f, y * f
+        return {"eigenvalues": ev, "eigenvectors": X, "eigenvectors2": Y}
 
     def solve_excitons_uks_tda(self):  # bse_uks.cc:218-235, 453-479
         o = self.opt

@@ -49,6 +49,7 @@ struct gwbse_ctx {
   // BSE
   bool bse_ready = false;
   int homo = 0, vt = 0, ct = 0, voff = 0, coff = 0;
+  int bse_vmin = 0, bse_cmax = 0, bse_rpamin = 0;
   std::vector<double> eps_inv, hqp;
   double bse_flops = 0.0;
   long long bse_products = 0, bse_columns = 0;
@@ -981,6 +982,9 @@ int gwbse_bse_configure(gwbse_ctx* ctx, int homo, int rpamin, int vmin, int cmax
   ctx->vt = homo - vmin + 1;
   ctx->ct = cmax - homo;
   ctx->voff = vmin - rpamin;
+  ctx->bse_vmin = vmin;
+  ctx->bse_cmax = cmax;
+  ctx->bse_rpamin = rpamin;
   ctx->coff = homo + 1 - rpamin;
   REQUIRE(ctx->vt > 0 && ctx->ct > 0 && ctx->voff >= 0, "invalid BSE level ranges");
   REQUIRE(ctx->coff + ctx->ct <= ctx->mtotal && ctx->coff + ctx->ct <= ctx->ntotal, "BSE range exceeds Mmn");
@@ -1027,6 +1031,28 @@ int gwbse_bse_vc_expand_dev(gwbse_ctx* ctx, double alpha, int screened, int k, c
         for (int chi = 0; chi < naux; ++chi)
           s += ctx->M(vo + v, co + c, chi) * (screened ? ctx->eps_inv[chi] : 1.0) * W[(size_t)j * naux + chi];
         Y[(size_t)j * ldy + ct * v + c] += alpha * s;
+      }
+  MOCK_END(ctx)
+}
+int gwbse_bse_hd2_cross_dev(gwbse_ctx* ctx, gwbse_ctx* other, int homo_other, double alpha, int k, const double* X,
+                            int ldx, double* Y, int ldy) {
+  MOCK_BEGIN(ctx)
+  REQUIRE(ctx->bse_ready && other, "BSE operator not configured (gwbse_bse_configure)");
+  const int vt = ctx->vt, ct = ctx->ct, vo = ctx->voff, co = ctx->coff, naux = ctx->naux;
+  const int vti = homo_other - ctx->bse_vmin + 1, cti = ctx->bse_cmax - homo_other, coi = homo_other + 1 - ctx->bse_rpamin;
+  REQUIRE(ldx >= vti * cti && ldy >= vt * ct, "Shape mismatch in the cross-spin BSE block");
+  for (int j = 0; j < k; ++j)
+    for (int v1 = 0; v1 < vt; ++v1)
+      for (int c1 = 0; c1 < ct; ++c1) {
+        double s = 0.0;
+        for (int v2 = 0; v2 < vti; ++v2)
+          for (int c2 = 0; c2 < cti; ++c2) {
+            double b = 0.0;
+            for (int chi = 0; chi < naux; ++chi)
+              b += ctx->M(co + c1, vo + v2, chi) * ctx->eps_inv[chi] * other->M(vo + v1, coi + c2, chi);
+            s += b * X[(size_t)j * ldx + cti * v2 + c2];
+          }
+        Y[(size_t)j * ldy + ct * v1 + c1] += alpha * s;
       }
   MOCK_END(ctx)
 }

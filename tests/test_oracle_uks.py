@@ -100,3 +100,37 @@ def test_open_shell_case_runs_and_is_spin_asymmetric():
     assert H.shape == (5 * 12 + 4 * 13,) * 2
     w = np.linalg.eigvalsh(H)
     assert np.abs(res["eigenvalues"][:3] - w[:3]).max() < 1e-8
+
+
+def test_uks_b_operator_reduces_to_restricted_blocks_and_full_bse_is_consistent():
+    """<0,1,0,1>: same-spin blocks = restricted <0,1,0,0> + <0,0,0,1>; in the closed-shell limit the cross-spin block
+    equals the same-spin Hd2 block (both channels' tensors are the same); the dense full-BSE roots are real and positive
+    and normalised to |X.X - Y.Y| = 1 (the reference divides by sqrt(abs(norm)), bse_uks.cc:386-392)."""
+    g = load_golden()
+    C, eps, Hqp = g["bse_operator/MOs"], g["inline/bse_operator_epsilon_inv"], g["bse_operator/Hqp"]
+    Ma, Mb = methane_mmn(C), methane_mmn(C)
+    Ma.multiply_right(g["bse_operator/rpa_op"])
+    Mb.multiply_right(g["bse_operator/rpa_op"])
+    op = uks.exciton_uks_btda_b(eps, Ma, Mb, Hqp, Hqp)
+    op.configure(4, 4, 0, 0, 8)
+    D = op.dense()
+    n = op.blk[0].size
+    ropt = bop.BSEOperatorOptions(cmax=8, homo=4, qpmin=0, rpamin=0, vmin=0)
+    hx, hd2 = bop.hx_op(eps, Ma, Hqp), bop.hd2_op(eps, Ma, Hqp)
+    hx.configure(ropt)
+    hd2.configure(ropt)
+    assert np.abs(D[:n, :n] - (hx.dense() + hd2.dense())).max() < 1e-12
+    assert np.abs(D[:n, n:] - hd2.dense()).max() < 1e-12 and np.abs(D[n:, :n] - hd2.dense()).max() < 1e-12
+    assert np.abs(np.diag(D) - op.diagonal()).max() < 1e-12
+    c = uks_case()
+    ug = uks.GWUKS(methane_mmn(c["Ca"]), methane_mmn(c["Cb"]), c["vxc_a"], c["vxc_b"], c["ea"], c["eb"])
+    ug.configure(_gw_options(qp_grid_steps=601, qp_grid_spacing=0.005), c["homo_a"], c["homo_b"])
+    ug.calculate_gw_perturbation()
+    ug.calculate_hqp()
+    bs = uks.BSEUKS(methane_mmn(c["Ca"]), methane_mmn(c["Cb"]))
+    o = obse.BSEOptions(cmax=16, rpamax=16, rpamin=0, vmin=0, nmax=5, useTDA=False, homo=4, qpmin=0, qpmax=16)
+    bs.configure(o, c["homo_a"], c["homo_b"], ug.rpa.energies(0), ug.rpa.energies(1), ug.get_hqp(0), ug.get_hqp(1))
+    full = bs.solve_excitons_uks_btda_dense()
+    assert np.all(full["eigenvalues"] > 0) and np.all(np.diff(full["eigenvalues"]) >= 0)
+    X, Y = full["eigenvectors"], full["eigenvectors2"]
+    assert np.abs(np.abs(np.sum(X * X, axis=0) - np.sum(Y * Y, axis=0)) - 1.0).max() < 1e-10

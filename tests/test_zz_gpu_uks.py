@@ -107,10 +107,36 @@ def test_unrestricted_operator_against_the_oracle_matrix():
     job.close()
 
 
+def test_full_unrestricted_bse_against_the_oracle():
+    """bse.useTDA=false: [A B; -B -A] with A = <1,1,1,0>, B = <0,1,0,1> (cross-spin Hd2 block through
+    gwbse_bse_hd2_cross_dev); 112 excitations -> the dense branch, as in the reference."""
+    c = uks_case()
+    og = uks.GWUKS(methane_mmn(c["Ca"]), methane_mmn(c["Cb"]), c["vxc_a"], c["vxc_b"], c["ea"], c["eb"])
+    og.configure(_gw_options(qp_grid_steps=601, qp_grid_spacing=0.005), c["homo_a"], c["homo_b"])
+    og.calculate_gw_perturbation()
+    og.calculate_hqp()
+    ob = uks.BSEUKS(methane_mmn(c["Ca"]), methane_mmn(c["Cb"]))
+    o = obse.BSEOptions(cmax=16, rpamax=16, rpamin=0, vmin=0, nmax=5, useTDA=False, homo=4, qpmin=0, qpmax=16,
+                        use_Hqp_offdiag=True)
+    ob.configure(o, c["homo_a"], c["homo_b"], og.rpa.energies(0), og.rpa.energies(1), og.get_hqp(0), og.get_hqp(1))
+    ref = ob.solve_excitons_uks_btda_dense()
+    job = make_job(c, "G0W0", tasks="gw,exciton_uks", bse__useTDA=False, bse__exctotal=5)
+    job.run_uks()
+    assert np.abs(job.get("BSE_uks_eigenvalues") - ref["eigenvalues"]).max() < 1e-6
+    X, Y = job.get("BSE_uks_eigenvectors"), job.get("BSE_uks_eigenvectors2")
+    assert np.abs(np.abs(np.sum(X * X, axis=0) - np.sum(Y * Y, axis=0)) - 1.0).max() < 1e-8  # 1 / sqrt(abs(norm))
+    for r in range(5):  # same state up to the degeneracy-free phase convention
+        if r + 1 < 5 and abs(ref["eigenvalues"][r + 1] - ref["eigenvalues"][r]) < 1e-6:
+            continue
+        if r > 0 and abs(ref["eigenvalues"][r] - ref["eigenvalues"][r - 1]) < 1e-6:
+            continue
+        assert abs(abs(X[:, r] @ ref["eigenvectors"][:, r] - Y[:, r] @ ref["eigenvectors2"][:, r]) - 1.0) < 1e-5
+    job.close()
+
+
 def test_what_is_not_on_this_path_is_refused():
     c = uks_case()
     for kw, msg in ((dict(tasks="gw,singlets"), "not defined for open-shell"),
-                    (dict(tasks="gw,exciton_uks", bse__useTDA=False), "not on this path"),
                     (dict(gw__sigma_integrator="exact"), "not available for unrestricted")):
         job = make_job(c, **kw)
         with pytest.raises(Exception, match=msg):

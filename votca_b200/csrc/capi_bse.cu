@@ -322,6 +322,102 @@ void bse_matmul_dev(gwbse_ctx* ctx, int cqp, int cx, int cd, int cd2, int k, con
   }
 }
 
+// Cross-spin Hd2 block of the unrestricted full-BSE B operator (BSE_OPERATOR_UKS::add_direct2_block with out != in,
+// bse_operator_uks.cc:136-172, 252-255): the output channel's tensor (this context) supplies M_out[c1][v2, chi], the
+// input channel's tensor (other_X, same layout, the other context's Mmn) supplies M_in[v1][c2, chi]:
+//   Y[(v1, c1), kv] += alpha sum_{v2, c2, chi} M_out[c1][v2, chi] eps_inv[chi] M_in[v1][c2, chi] X[(v2, c2), kv]
+// v1, c1 run over the output channel's ranges, v2, c2 over the input channel's.  Same two-leg factorisation as Hd2.
+void hd2_cross(gwbse_ctx* ctx, const double* other_X, int homo_in, double alpha, int k, const double* Xin, int ldin,
+               double* Y, int ldy) {
+  auto& st = ctx->bse;
+  GW_REQUIRE(st.ready, "BSE operator not configured (gwbse_bse_configure)");
+  GW_REQUIRE(ctx->world == 1, "the unrestricted operator is single-GPU");
+  const int naux = ctx->naux, npad = ctx->npad;
+  const long long ldx = ctx->ldx;
+  const int vt_o = st.vt, ct_o = st.ct, voff = st.voff, coff_o = st.coff;
+  const int vt_i = homo_in - st.vmin + 1, ct_i = st.cmax - homo_in, coff_i = homo_in + 1 - st.rpamin;
+  GW_REQUIRE(vt_i > 0 && ct_i > 0 && coff_i + ct_i <= ctx->ntotal, "invalid input-channel ranges");
+  GW_REQUIRE(ldin >= vt_i * ct_i && ldy >= vt_o * ct_o, "Shape mismatch in the cross-spin BSE block");
+  if (k <= 0) return;
+  const int vtp = round_up(vt_i, 2);
+  const long long ldU = (long long)vtp * naux;
+  size_t budget = ctx->bse_chunk_bytes;
+  {
+    size_t free_b = 0, total_b = 0;
+    GW_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const size_t held = ctx->bufs["bse_U"].cap * sizeof(double);
+    budget = std::min(budget, std::max(held, held + free_b / 2));
+  }
+  int nc = (int)std::max<long long>(1, (long long)(budget / sizeof(double)) / (ldU * k));
+  nc = std::min(nc, vt_o);
+  while ((long long)naux * nc >= (1LL << 31) || (long long)nc * k >= (1LL << 31)) nc = std::max(1, nc / 2);
+  double* U = ctx->buf("bse_U", (size_t)ldU * nc * k);
+  // trial vectors at an even row pitch (16-byte copies), as in the same-spin term
+  const int ctp = round_up(ct_i, 2);
+  const double* Xa = Xin;
+  long long xa_ri = ct_i, xa_ro = ldin;
+  if (ct_i != ctp) {
+    double* Xp = ctx->buf("bse_Xp", (size_t)ctp * vt_i * k);
+    for (int j = 0; j < k; ++j)
+      GW_CUDA(cudaMemcpy2DAsync(Xp + (size_t)j * vt_i * ctp, sizeof(double) * ctp, Xin + (size_t)j * ldin,
+                                sizeof(double) * ct_i, sizeof(double) * ct_i, vt_i, cudaMemcpyDeviceToDevice,
+                                ctx->stream));
+    Xa = Xp;
+    xa_ri = ctp;
+    xa_ro = (long long)vt_i * ctp;
+  }
+  for (int a = 0; a < vt_o; a += nc) {
+    const int n1 = std::min(nc, vt_o - a);
+    // U[(v2, chi), (l, kv)] = eps_inv[chi] sum_c2 X[c2, (v2, kv)] M_in[voff + a + l][coff_i + c2, chi]
+    GemmParams p;
+    p.M = vt_i * k;
+    p.N = naux * n1;
+    p.Ki = ct_i;
+    p.A.ptr = Xa;
+    p.A.Lr = vt_i;
+    p.A.s_ri = xa_ri;
+    p.A.s_ro = xa_ro;
+    p.A.s_ki = 1;
+    p.B.ptr = other_X + (long long)(voff + a) * npad + coff_i;
+    p.B.Lr = naux;
+    p.B.s_ri = ldx;
+    p.B.s_ro = npad;
+    p.B.s_ki = 1;
+    p.C = U;
+    p.Lm = vt_i;
+    p.sC_mi = 1;
+    p.sC_mo = ldU * n1;
+    p.Ln = naux;
+    p.sC_ni = vtp;
+    p.sC_no = ldU;
+    p.nscale = st.eps_inv;
+    p.nscale_mod = naux;
+    ctx->gemm(p);
+    // Y[(a + l, c1), kv] += alpha sum_{chi, v2} M_out[coff_o + c1][voff + v2, chi] U[(v2, chi), (l, kv)]
+    GemmParams q;
+    q.Ko = naux;
+    q.Ki = vt_i;
+    q.M = ct_o;
+    q.N = n1 * k;
+    q.A.ptr = ctx->X + (long long)coff_o * npad + voff;
+    q.A.s_ri = npad;
+    q.A.s_ki = 1;
+    q.A.s_ko = ldx;
+    q.B.ptr = U;
+    q.B.s_ri = ldU;
+    q.B.s_ki = 1;
+    q.B.s_ko = vtp;
+    q.C = Y + (long long)a * ct_o;
+    q.sC_mi = 1;
+    q.Ln = n1;
+    q.sC_ni = ct_o;
+    q.sC_no = ldy;
+    q.alpha = alpha;
+    q.beta = 1.0;
+    ctx->gemm(q);
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -410,6 +506,18 @@ int gwbse_bse_vc_expand_dev(gwbse_ctx* ctx, double alpha, int screened, int k, c
     }
     vc_expand(ctx, alpha, k, W, Y_dev, ldy);
   }
+  GW_API_END(ctx)
+}
+
+int gwbse_bse_hd2_cross_dev(gwbse_ctx* ctx, gwbse_ctx* other, int homo_other, double alpha, int k,
+                            const double* X_dev, int ldx, double* Y_dev, int ldy) {
+  GW_API_BEGIN(ctx)
+  GW_PROF(ctx, "bse_hd2_cross");
+  GW_REQUIRE(other && other->X && ctx->X, "both contexts need a filled Mmn");
+  GW_REQUIRE(other->naux == ctx->naux && other->ldx == ctx->ldx && other->npad == ctx->npad &&
+                 other->mmin == ctx->mmin && other->nmin == ctx->nmin && other->device == ctx->device,
+             "the two Mmn tensors must have the same shape and live on the same GPU");
+  hd2_cross(ctx, other->X, homo_other, alpha, k, X_dev, ldx, Y_dev, ldy);
   GW_API_END(ctx)
 }
 

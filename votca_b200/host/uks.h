@@ -13,11 +13,13 @@
 //   * the RPA input energies of both channels are updated together (rpa_uks.cc:41-71);
 //   * the BSE operator acts on [alpha (v c) | beta (v c)]; its same-spin blocks are gwbse_bse_matmul_dev per context,
 //     the coupling between the channels (bse_operator_uks.cc:174-211) is one projection on the input channel's
-//     context and one screened expansion on the output channel's (gwbse_bse_vc_project_dev / _expand_dev).
+//     context and one screened expansion on the output channel's (gwbse_bse_vc_project_dev / _expand_dev); the
+//     cross-spin block of the full-BSE B operator (:136-172, :252-255) contracts both channels' tensors in one
+//     two-leg GEMM chain (gwbse_bse_hd2_cross_dev).
 // The two contexts take turns: every call on one is completed (stream synchronised) before the other gets work.  That
 // costs nothing here (the channels' work is sequential in the reference too) and it is required: the TMA-staged GEMM
 // was found to write wrong tiles when grids of another stream share the SMs with it.
-// Scope: sigma_integrator = ppm (the default), BSE in the Tamm-Dancoff approximation, one GPU.
+// Scope: sigma_integrator = ppm (the default), BSE in the Tamm-Dancoff approximation and in full, one GPU.
 #pragma once
 #include "bse.h"
 #include "gw.h"
@@ -284,7 +286,6 @@ class BSE_OPERATOR_UKS final : public MatrixFreeOperator {
                    const MatrixXd& Hqp_beta)
       : epsilon_0_inv_(Hd_operator), Mmn_(Mmn), Hqp_{&Hqp_alpha, &Hqp_beta} {
     static_assert(!(cd2 != 0 && cd != 0), "Hamiltonian cannot contain Hd and Hd2 at the same time");
-    static_assert(cd2 == 0, "the cross-spin Hd2 block (full BSE, bse_operator_uks.cc:252-255) is not on this path");
   }
   // bse_operator_uks.cc:26-45
   void configure(BSEOperatorUKS_Options opt) {
@@ -337,6 +338,16 @@ class BSE_OPERATOR_UKS final : public MatrixFreeOperator {
         dout.sync();
       }
     }
+    if (cd2 != 0) {  // cross-spin block of the full-BSE B operator: both channels' tensors in one contraction (:252-255)
+      for (int in = 0; in < 2; ++in) {
+        const int out = 1 - in;
+        const Device& din = channel(in).device();
+        const Device& dout = channel(out).device();
+        dout.check(gwbse_bse_hd2_cross_dev(dout.ctx(), din.ctx(), (int)blk_[in].homo, -double(cd2), (int)k,
+                                           X_dev + blk_[in].offset, (int)ldx, Y_dev + blk_[out].offset, (int)ldy));
+        dout.sync();
+      }
+    }
   }
 
   MatrixXd matmul(const MatrixXd& input) const override {
@@ -370,6 +381,8 @@ class BSE_OPERATOR_UKS final : public MatrixFreeOperator {
 };
 
 typedef BSE_OPERATOR_UKS<1, 1, 1, 0> ExcitonUKSOperator_TDA;
+typedef BSE_OPERATOR_UKS<0, 1, 0, 1> ExcitonUKSOperator_BTDA_B;
+typedef BSE_OPERATOR_UKS<0, 0, 0, 1> Hd2UKSOperator;
 typedef BSE_OPERATOR_UKS<1, 0, 0, 0> HqpUKSOperator;
 typedef BSE_OPERATOR_UKS<0, 1, 0, 0> HxUKSOperator;
 typedef BSE_OPERATOR_UKS<0, 0, 1, 0> HdUKSOperator;
@@ -384,8 +397,6 @@ class BSE_UKS {
   void configure(const options& opt, Index homo_alpha, Index homo_beta, const VectorXd& RPAInputEnergiesAlpha,
                  const VectorXd& RPAInputEnergiesBeta, const MatrixXd& Hqp_alpha_in, const MatrixXd& Hqp_beta_in) {
     opt_ = opt;
-    if (!opt_.useTDA)
-      throw std::runtime_error("BSE_UKS: the full (non-TDA) unrestricted BSE is not on this path; set bse.useTDA=true");
     homo_[0] = homo_alpha;
     homo_[1] = homo_beta;
     for (int s = 0; s < 2; ++s) {
@@ -422,17 +433,22 @@ class BSE_UKS {
     return H;
   }
 
+  ExcitonUKSOperator_BTDA_B getExcitonOperator_BTDA_B() const {
+    ExcitonUKSOperator_BTDA_B H(epsilon_0_inv_, Mmn_, Hqp_[0], Hqp_[1]);
+    H.configure({homo_[0], homo_[1], opt_.rpamin, opt_.qpmin, opt_.vmin, opt_.cmax});
+    return H;
+  }
+
+  // bse_uks.cc:442-451
+  EigenSystem Solve_excitons_uks() const { return opt_.useTDA ? Solve_excitons_uks_TDA() : Solve_excitons_uks_BTDA(); }
+
   // bse_uks.cc:218-235, 453-479
-  EigenSystem Solve_excitons_uks() const {
+  EigenSystem Solve_excitons_uks_TDA() const {
     ExcitonUKSOperator_TDA H = getExcitonOperator_TDA();
     log_(" Setup combined UKS TDA Hamiltonian ");
     EigenSystem result;
     DavidsonSolver DS(log_);
-    DS.set_correction(opt_.davidson_correction);
-    DS.set_tolerance(opt_.davidson_tolerance);
-    DS.set_size_update(opt_.davidson_update);
-    DS.set_iter_max(opt_.davidson_maxiter);
-    DS.set_max_search_space(10 * opt_.nmax);
+    configureDavidson(DS);
     DS.solve(H, opt_.nmax);
     result.eigenvalues = DS.eigenvalues();
     result.eigenvectors = DS.eigenvectors();
@@ -440,11 +456,109 @@ class BSE_UKS {
     iterations_ = DS.num_iterations();
     return result;
   }
+
+  // bse_uks.cc:291-440: [A B; -B -A] with A = <1,1,1,0>, B = <0,1,0,1>; dense for up to 128 excitations (the
+  // reference's choice for small systems), Davidson on the Hamiltonian operator otherwise
+  EigenSystem Solve_excitons_uks_BTDA() const {
+    ExcitonUKSOperator_TDA A = getExcitonOperator_TDA();
+    ExcitonUKSOperator_BTDA_B B = getExcitonOperator_BTDA_B();
+    log_(" Setup combined UKS full BSE exciton hamiltonian ");
+    const Index n = A.rows();
+    EigenSystem result;
+    if (n <= 128) {
+      log_(" Using dense full UKS-BSE solve for small system (dim=" + std::to_string(n) + ")");
+      const MatrixXd I = MatrixXd::Identity(n, n);
+      const MatrixXd Ad = A.matmul(I), Bd = B.matmul(I);
+      MatrixXd H(2 * n, 2 * n), One = MatrixXd::Identity(2 * n, 2 * n);
+      for (Index j = 0; j < n; ++j)
+        for (Index i = 0; i < n; ++i) {
+          H(i, j) = Ad(i, j);
+          H(i, n + j) = Bd(i, j);
+          H(n + i, j) = -Bd(i, j);
+          H(n + i, n + j) = -Ad(i, j);
+        }
+      VectorXd wr(2 * n), wi(2 * n);
+      MatrixXd VR(2 * n, 2 * n);
+      const Device& dev = Mmn_.alpha.device();
+      try {
+        dev.check(gwbse_gen_eig_host(dev.ctx(), (int)(2 * n), H.data(), One.data(), wr.data(), wi.data(), VR.data()));
+      } catch (const std::exception&) {
+        throw std::runtime_error("Dense full UKS-BSE diagonalization failed.");
+      }
+      std::vector<std::pair<double, Index>> roots;  // positive real roots, ascending
+      for (Index i = 0; i < 2 * n; ++i)
+        if (std::abs(wi(i)) < 1e-8 && wr(i) > 0.0) roots.emplace_back(wr(i), i);
+      std::stable_sort(roots.begin(), roots.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+      if (roots.empty())
+        throw std::runtime_error("Dense full UKS-BSE diagonalization produced no positive real roots.");
+      const Index nroots = std::min<Index>(opt_.nmax, (Index)roots.size());
+      result.eigenvalues = VectorXd(nroots);
+      result.eigenvectors = MatrixXd(n, nroots);
+      result.eigenvectors2 = MatrixXd(n, nroots);
+      for (Index r = 0; r < nroots; ++r) {
+        const Index col = roots[r].second;
+        Index imax = 0;  // phase convention: the largest |X_k| positive
+        for (Index i = 1; i < n; ++i)
+          if (std::abs(VR(i, col)) > std::abs(VR(imax, col))) imax = i;
+        const double sign = VR(imax, col) < 0.0 ? -1.0 : 1.0;
+        double nx = 0.0, ny = 0.0;
+        for (Index i = 0; i < n; ++i) {
+          nx += VR(i, col) * VR(i, col);
+          ny += VR(n + i, col) * VR(n + i, col);
+        }
+        const double norm = nx - ny;
+        if (std::abs(norm) < 1e-12)
+          throw std::runtime_error("Dense full UKS-BSE eigenvector has near-zero (X^2-Y^2) norm.");
+        const double f = sign / std::sqrt(std::abs(norm));
+        result.eigenvalues(r) = roots[r].first;
+        for (Index i = 0; i < n; ++i) {
+          result.eigenvectors(i, r) = f * VR(i, col);
+          result.eigenvectors2(i, r) = f * VR(n + i, col);
+        }
+      }
+      result.success = true;
+      iterations_ = 0;
+      return result;
+    }
+    HamiltonianOperator<ExcitonUKSOperator_TDA, ExcitonUKSOperator_BTDA_B> Hop(A, B);
+    DavidsonSolver DS(log_);
+    configureDavidson(DS);
+    DS.set_matrix_type("HAM");
+    const MatrixXd initial_guess = BuildFullBSEXRankedInitialGuess(A.diagonal(), B.diagonal(), opt_.nmax);
+    DS.solve(Hop, opt_.nmax, initial_guess);
+    result.eigenvalues = DS.eigenvalues();
+    result.success = DS.success();
+    iterations_ = DS.num_iterations();
+    const MatrixXd ev = DS.eigenvectors();
+    const Index cols = ev.cols();
+    result.eigenvectors = MatrixXd(n, cols);
+    result.eigenvectors2 = MatrixXd(n, cols);
+    for (Index j = 0; j < cols; ++j) {
+      double nx = 0.0, ny = 0.0;
+      for (Index i = 0; i < n; ++i) {
+        nx += ev(i, j) * ev(i, j);
+        ny += ev(n + i, j) * ev(n + i, j);
+      }
+      const double f = std::sqrt(1.0 / (nx - ny));
+      for (Index i = 0; i < n; ++i) {
+        result.eigenvectors(i, j) = f * ev(i, j);
+        result.eigenvectors2(i, j) = f * ev(n + i, j);
+      }
+    }
+    return result;
+  }
   const VectorXd& getEpsilonInv() const { return epsilon_0_inv_; }
   const MatrixXd& getHqp(Spin s) const { return Hqp_[(int)s]; }
   Index last_davidson_iterations() const { return iterations_; }
 
  private:
+  void configureDavidson(DavidsonSolver& DS) const {
+    DS.set_correction(opt_.davidson_correction);
+    DS.set_tolerance(opt_.davidson_tolerance);
+    DS.set_size_update(opt_.davidson_update);
+    DS.set_iter_max(opt_.davidson_maxiter);
+    DS.set_max_search_space(10 * opt_.nmax);
+  }
   Logger& log_;
   TCMatrix_gwbse_spin& Mmn_;
   options opt_;
