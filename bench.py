@@ -408,6 +408,9 @@ class Bench:
         counts["bse_operator_products"] = max(1, bse_products // steps)
         counts["bse_operator_columns"] = bse_columns // steps
         counts["bse_algorithmic_flops"] = bse_flops / steps
+        dn_builds, dn_columns, dn_bytes = kctx.bse_dense_stats()
+        bse_dense = {"blocks_built": dn_builds, "columns_from_resident_blocks": dn_columns,
+                     "resident_GB_this_rank": round(dn_bytes / 1e9, 2)}
         stage_times = {k: job.scalar(k) for k in ("time_fill", "time_gw", "time_bse")}
         qp = job.get("QPpert_energies")
         results = {"QP_homo": float(qp[homo]), "QP_lumo": float(qp[homo + 1]),
@@ -443,7 +446,7 @@ class Bench:
                "ms_per_step": ms_per_step, "steps": steps, "warmup": warmup, "counts": counts,
                "stage_seconds": stage_times, "results": results, "launches": int(launches), "clocks": clocks,
                "flops": flops, "total_flops": total_flops, "gemm": gstats, "gemm_tflops": achieved, "peak": peak,
-               "e2e": e2e}
+               "e2e": e2e, "bse_dense": bse_dense}
         return rec
 
     def run_e2e(self, job, inp, workload, N, naux, homo, q, aux_lo, aux_hi, steps, profile_path):
@@ -617,7 +620,10 @@ def make_line(args, rec, also, parity, world):
         "config": {"workload": workload_name(rec["workload"], rec["mode"], N, naux, homo), "mode": rec["mode"],
                    "l2_policy": l2_policy(N, naux, q)},  # the reference arm prints the same three keys
         "run": {"gw_iterations": counts["gw_iterations"], "davidson_iterations": counts["davidson_iterations"],
-                "results": rec["results"], "stage_seconds": rec["stage_seconds"], "ao_integrals": ao_note},
+                "results": rec["results"], "stage_seconds": rec["stage_seconds"], "ao_integrals": ao_note,
+                "bse_direct_terms": dict(rec["bse_dense"], note=(
+                    "Hd / Hd2 applied from their B x B blocks, materialised once per (Mmn, screening) when that pays "
+                    "back against the factorised products and the blocks fit in HBM (option bse_dense)"))},
         "tflops": {"value": rec["total_flops"] / (ms_per_step * 1e-3) / 1e12,
                    "algorithmic_tflop_per_step": rec["total_flops"] / 1e12,
                    "stages_tflop": {k: round(v / 1e12, 3) for k, v in flops.items()}},

@@ -318,6 +318,12 @@ int gwbse_bse_hd2_cross_dev(gwbse_ctx* ctx, gwbse_ctx* other, int homo_other, do
 /* accounting for bench.py: algorithmic flops (F_bse), operator products and trial columns applied
  * through gwbse_bse_matmul(_dev) since the last reset */
 int gwbse_bse_stats(gwbse_ctx* ctx, double* algo_flops, long long* products, long long* columns, int reset);
+/* The direct terms Hd / Hd2 of the operator (bse_operator.cc:61-116 rebuilds their rows for every product) are
+ * applied in factorised form until materialising the B x B block pays back, then from the resident block (option
+ * "bse_dense": 0 never, 1 when it pays back - default, 2 always; "bse_dense_payback": fraction of a build the
+ * factorised work under one (Mmn, screening, window) has to reach).  builds: blocks formed so far; columns: trial
+ * columns applied from a resident block; resident_bytes: bytes of the blocks valid right now on this rank.          */
+int gwbse_bse_dense_stats(gwbse_ctx* ctx, long long* builds, long long* columns, double* resident_bytes);
 /* BSE_OPERATOR::diagonal (bse_operator.cc:134-175) */
 int gwbse_bse_diagonal(gwbse_ctx* ctx, int cqp, int cx, int cd, int cd2, double* diag);
 

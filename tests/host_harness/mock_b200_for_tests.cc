@@ -1064,6 +1064,13 @@ int gwbse_bse_stats(gwbse_ctx* ctx, double* fl, long long* p, long long* c, int 
   if (reset) ctx->bse_products = ctx->bse_columns = 0;
   return 0;
 }
+int gwbse_bse_dense_stats(gwbse_ctx* ctx, long long* b, long long* c, double* r) {
+  if (!ctx) return 1;
+  if (b) *b = 0;
+  if (c) *c = 0;
+  if (r) *r = 0.0;
+  return 0;
+}
 int gwbse_bse_diagonal(gwbse_ctx* ctx, int cqp, int cx, int cd, int cd2, double* diag) {
   MOCK_BEGIN(ctx)
   REQUIRE(ctx->bse_ready, "BSE operator not configured (gwbse_bse_configure)");

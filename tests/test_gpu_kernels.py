@@ -3,6 +3,8 @@
 FP64 contractions are compared at 1e-11 relative Frobenius error (BASELINE.json asks 1e-10 for Mmn);
 the only difference to the oracle is summation order.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -401,11 +403,13 @@ def test_bse_operator_golden(ctx, golden):
 @pytest.mark.parametrize("dims", [(50, 30, 33, 9, 3, 27, 6), (90, 40, 47, 15, 0, 39, 21)])
 @pytest.mark.parametrize("chunk", [1 << 30, 1 << 16])
 def test_bse_operator_random(ctx, dims, chunk):
+    """The factorised form of every term (the materialised blocks are switched off here and have their own test)."""
     naux, mtotal, ntotal, homo, vmin, cmax, k = dims
     rng = np.random.default_rng(9)
     tc = random_tc(rng, naux, mtotal, ntotal)
     push(ctx, tc)
     ctx.set_option("bse_chunk_bytes", chunk)
+    ctx.set_option("bse_dense", 0)
     vt, ct = homo - vmin + 1, cmax - homo
     Hqp = rng.standard_normal((vt + ct, vt + ct))
     Hqp = Hqp + Hqp.T
@@ -420,6 +424,85 @@ def test_bse_operator_random(ctx, dims, chunk):
         assert rel_frob(ref, ctx.bse_matmul(co, X)) < TOL, name
         assert rel_frob(op.diagonal(), ctx.bse_diagonal(co)) < TOL, name
     ctx.set_option("bse_chunk_bytes", 8 << 30)
+    ctx.set_option("bse_dense", 1)
+
+
+@pytest.mark.parametrize("dims", [(50, 30, 33, 9, 3, 27, 6), (90, 40, 47, 15, 0, 39, 21), (800, 24, 40, 7, 1, 22, 5)])
+def test_bse_operator_materialised_blocks(ctx, dims):
+    """Hd / Hd2 from their resident B x B blocks (option bse_dense = 2: built at the first product) against the
+    reference formulation; the first block is parked in the second Mmn buffer, the second one gets its own; a
+    MultiplyRight (new Mmn content, buffers trade places) and a new screening each invalidate both."""
+    if os.environ.get("GWBSE_B200_TEST_MOCK_DIR"):
+        pytest.skip("a device-memory policy of the CUDA library; the CPU stand-in has none")
+    naux, mtotal, ntotal, homo, vmin, cmax, k = dims
+    rng = np.random.default_rng(19)
+    tc = random_tc(rng, naux, mtotal, ntotal)
+    push(ctx, tc)
+    Q, _ = np.linalg.qr(rng.standard_normal((naux, naux)))
+    ctx.mmn_mul_right(Q)  # the second Mmn buffer now exists
+    tc.multiply_right(Q)
+    ctx.set_option("bse_dense", 2)
+    vt, ct = homo - vmin + 1, cmax - homo
+    B = vt * ct
+    Hqp = rng.standard_normal((vt + ct, vt + ct))
+    Hqp = Hqp + Hqp.T
+    opt = bop.BSEOperatorOptions(homo=homo, rpamin=0, qpmin=0, vmin=vmin, cmax=cmax)
+    X = rng.standard_normal((B, k))
+
+    def check(eps, tensor):
+        ctx.bse_configure(homo, 0, vmin, cmax, eps, Hqp)
+        for name, co in OPS.items():
+            op = bop.BSEOperator(*co, eps, tensor, Hqp)
+            op.configure(opt)
+            assert rel_frob(op.matmul(X), ctx.bse_matmul(co, X)) < TOL, name
+            assert rel_frob(op.matmul(X[:, :1]), ctx.bse_matmul(co, X[:, :1])) < TOL, name
+
+    try:
+        b0, c0, _ = ctx.bse_dense_stats()
+        eps = rng.uniform(0.3, 1.0, naux)
+        check(eps, tc)
+        b1, c1, resident = ctx.bse_dense_stats()
+        assert b1 - b0 == 2  # one block per direct term, reused by singlet / triplet / bare Hd and by B / bare Hd2
+        assert c1 - c0 == 5 * (k + 1)
+        assert resident == 2 * 8.0 * (B + B % 2) * B
+        check(eps, tc)  # same key: no further build
+        assert ctx.bse_dense_stats()[0] == b1
+        eps2 = rng.uniform(0.3, 1.0, naux)
+        check(eps2, tc)  # new screening
+        assert ctx.bse_dense_stats()[0] == b1 + 2
+        ctx.mmn_mul_right(Q.T)  # new tensor, and the buffer the first block was parked in is the tensor now
+        tc.multiply_right(Q.T)
+        check(eps2, tc)
+        assert ctx.bse_dense_stats()[0] == b1 + 4
+    finally:
+        ctx.set_option("bse_dense", 1)
+
+
+def test_bse_materialised_blocks_pay_back_rule(ctx):
+    """Default policy: single-column products under ever-changing screening (the dynamical-screening loop of
+    bse.cc:608-716) never form a block; a many-column product does at once; the result is the same either way."""
+    if os.environ.get("GWBSE_B200_TEST_MOCK_DIR"):
+        pytest.skip("a device-memory policy of the CUDA library; the CPU stand-in has none")
+    rng = np.random.default_rng(29)
+    naux, mtotal, ntotal, homo, vmin, cmax = 60, 40, 47, 15, 0, 39
+    tc = random_tc(rng, naux, mtotal, ntotal)
+    push(ctx, tc)
+    vt, ct = homo - vmin + 1, cmax - homo
+    Hqp = np.eye(vt + ct)
+    X = rng.standard_normal((vt * ct, 64))
+    b0 = ctx.bse_dense_stats()[0]
+    for it in range(6):
+        ctx.bse_configure(homo, 0, vmin, cmax, rng.uniform(0.3, 1.0, naux), Hqp)
+        ctx.bse_matmul(OPS["hd"], X[:, :1])
+    assert ctx.bse_dense_stats()[0] == b0
+    eps = rng.uniform(0.3, 1.0, naux)
+    ctx.bse_configure(homo, 0, vmin, cmax, eps, Hqp)
+    ctx.set_option("bse_dense", 0)
+    fact = ctx.bse_matmul(OPS["hd"], X)
+    ctx.set_option("bse_dense", 1)
+    dense = ctx.bse_matmul(OPS["hd"], X)
+    assert ctx.bse_dense_stats()[0] == b0 + 1
+    assert rel_frob(fact, dense) < TOL
 
 
 def test_properties_medium_size(ctx):

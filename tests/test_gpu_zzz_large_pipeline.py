@@ -109,10 +109,12 @@ def _check_synthetic(job, ref):
 
 @pytest.mark.parametrize("name", ["small", "medium"])
 @pytest.mark.parametrize("tma", [1, 0], ids=["tma-gemm", "cpasync-gemm"])
-def test_synthetic_pipeline_with_the_benchmark_code_paths(name, tma):
+@pytest.mark.parametrize("dense", [0, 1], ids=["factorised-direct", "materialised-direct"])
+def test_synthetic_pipeline_with_the_benchmark_code_paths(name, tma, dense):
     """evGW(ppm) + full BSE against the oracle with: the treecode evaluator for every Sigma_c element (it normally
-    starts at 32768 terms), the BSE intermediate cut into several chunks, split-K plans (the planner picks them for
-    the epsilon SYRK and the long-K BSE leg at these shapes) - once with the TMA-staged GEMM, once with cp.async."""
+    starts at 32768 terms), the BSE intermediate cut into several chunks or the direct terms applied from their
+    materialised blocks (the default policy, as in the benchmark), split-K plans (the planner picks them for the
+    epsilon SYRK and the long-K BSE leg at these shapes) - once with the TMA-staged GEMM, once with cp.async."""
     path = os.path.join(GOLDEN, f"synthetic_{name}_evgw_ppm_bse.npz")
     if not os.path.exists(path):
         pytest.skip(f"{os.path.basename(path)} not generated (tests/golden/make_synthetic_pipeline.py {name})")
@@ -125,8 +127,11 @@ def test_synthetic_pipeline_with_the_benchmark_code_paths(name, tma):
         k.set_option("tma", tma)
         k.set_option("sigma_tree_min_terms", 0)
         k.set_option("bse_chunk_bytes", 8 << 20)
+        k.set_option("bse_dense", dense)
+        builds0 = k.bse_dense_stats()[0]
         k.gemm_profile(True)
         _check_synthetic(job, ref)
+        assert (k.bse_dense_stats()[0] - builds0 >= 2) == (dense == 1)  # A carries Hd, B carries Hd2
         shapes = k.gemm_shape_report()
         k.gemm_profile(False)
         import re
@@ -134,4 +139,5 @@ def test_synthetic_pipeline_with_the_benchmark_code_paths(name, tma):
         assert any(f" sk{n}" in shapes for n in range(2, 65)), "no split-K plan was exercised"
     finally:
         job.kernel_ctx().set_option("tma", 1)
+        job.kernel_ctx().set_option("bse_dense", 1)
         job.close()

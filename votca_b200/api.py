@@ -564,5 +564,15 @@ def _bse_stats(self, reset=False):
 
 
 Context.bse_stats = _bse_stats
+
+
+def _bse_dense_stats(self):
+    """(blocks built, trial columns applied from a resident block, bytes resident now)"""
+    b, c, r = ctypes.c_longlong(), ctypes.c_longlong(), ctypes.c_double()
+    self.call("gwbse_bse_dense_stats", ctypes.byref(b), ctypes.byref(c), ctypes.byref(r))
+    return int(b.value), int(c.value), float(r.value)
+
+
+Context.bse_dense_stats = _bse_dense_stats
 Context.profile_report = _profile_report
 Context.gemm_shape_report = _gemm_shape_report

@@ -120,6 +120,231 @@ void vc_expand(gwbse_ctx* ctx, double alpha, int k, const double* W, double* Y, 
   ctx->gemm(q);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Materialised direct-interaction blocks.  The factorised products above cost 2 Naux B (vt + ct) (Hd) and
+// 4 Naux vt^2 ct (Hd2) flops per trial vector; forming the block once costs 2 B^2 Naux, i.e. as much as
+// B / (vt + ct) resp. ct / 2 vectors - a Davidson solve applies the operator to ten times that many.  With 180 GB of
+// HBM the B x B blocks of a C60-sized problem (33 GB each) stay resident, and a product becomes one skinny GEMM that
+// streams the block once.  Rows of the result a rank owns (c-slices for Hd, v-slices for Hd2, as in the factorised
+// path) are the columns of the block it stores:
+//   Hd : H[(v2, c2), (v1, l)] = sum_chi M[v1][v2, chi] eps_inv[chi] M[c1(l)][c2, chi]
+//   Hd2: H[(v2, c2), (l, c1)] = sum_chi M[v1(l)][c2, chi] eps_inv[chi] M[c1][v2, chi]
+// built by one GEMM each over chi from compact (even-pitch, TMA-describable) copies of the two-index blocks, the
+// screening folded into one of the copies.  A block is valid for one (Mmn version, screening, level window); the
+// first one is parked in the second Mmn buffer (idle between MultiplyRight calls), the second one is allocated if
+// the device has the room, otherwise that term stays factorised.
+struct OwnedSlices {
+  int nvloc, v_rel0, lvfirst, ncloc, c_rel0, lcfirst;
+};
+OwnedSlices owned_slices(gwbse_ctx* ctx) {
+  auto& st = ctx->bse;
+  OwnedSlices o;
+  o.nvloc = ctx->owned_count(st.voff, st.vt, ctx->rank);
+  o.v_rel0 = ctx->first_owned(st.voff, ctx->rank) - st.voff;
+  o.lvfirst = o.nvloc ? ctx->local_index(st.voff + o.v_rel0) : 0;
+  o.ncloc = ctx->owned_count(st.coff, st.ct, ctx->rank);
+  o.c_rel0 = ctx->first_owned(st.coff, ctx->rank) - st.coff;
+  o.lcfirst = o.ncloc ? ctx->local_index(st.coff + o.c_rel0) : 0;
+  return o;
+}
+
+double factorised_flops_per_column(gwbse_ctx* ctx, int kind) {
+  auto& st = ctx->bse;
+  return kind == 0 ? 2.0 * ctx->naux * (double)st.vt * st.ct * (st.vt + st.ct)
+                   : 4.0 * (double)st.vt * st.vt * st.ct * ctx->naux;
+}
+
+bool dense_build(gwbse_ctx* ctx, int kind) {
+  auto& st = ctx->bse;
+  auto& blk = st.dense[kind];
+  const int vt = st.vt, ct = st.ct, B = st.size, naux = ctx->naux, npad = ctx->npad;
+  const OwnedSlices o = owned_slices(ctx);
+  const long long ld = round_up(B, 2);
+  const long long ncols = kind == 0 ? (long long)vt * o.ncloc : (long long)o.nvloc * ct;
+  blk.ld = ld;
+  blk.ncols = ncols;
+  blk.H = nullptr;
+  blk.in_x2 = false;
+  if (ncols == 0) {  // this rank owns no row of the result
+    blk.valid = true;
+    ctx->bse_dense_builds++;
+    ctx->bse_algo_flops += 2.0 * (double)B * B * naux;
+    return true;
+  }
+  if (ncols >= (1LL << 31) || (long long)vt * vt >= (1LL << 31) || (long long)ct * ct >= (1LL << 31)) return false;
+  // ---- operand copies: the replicated small block whole, the other one in chunks of local slices
+  const int nloc = kind == 0 ? o.ncloc : o.nvloc;               // chunked index l
+  const long long small_rows = kind == 0 ? (long long)vt * vt : (long long)ct * vt;
+  const long long small_plane = round_up((int)small_rows, 2);
+  const size_t pack_budget = (size_t)4 << 30;
+  int lchunk = (int)std::max<long long>(1, (long long)(pack_budget / sizeof(double)) / ((long long)ct * naux));
+  lchunk = std::min(lchunk, nloc);
+  const long long big_plane = round_up(lchunk * ct, 2);
+  const size_t need_small = (size_t)small_plane * naux, need_big = (size_t)big_plane * naux;
+  const size_t need_H = (size_t)ld * (size_t)ncols;
+  // ---- where the block lives
+  const auto& other = st.dense[1 - kind];
+  const bool x2_taken = other.valid && other.in_x2 && other.x2_epoch == ctx->x2_epoch;
+  const size_t x2_cap = ctx->X2 ? (size_t)ctx->ldx * (size_t)(naux + ctx->world) : 0;
+  const char* own_name = kind == 0 ? "bse_dense0" : "bse_dense1";
+  auto held = [&](const char* name) {
+    auto it = ctx->bufs.find(name);
+    return it == ctx->bufs.end() ? (size_t)0 : it->second.cap;
+  };
+  size_t extra = 0;  // doubles that would have to be newly allocated
+  if (held("bse_packA") < need_small) extra += need_small;
+  if (held("bse_packB") < need_big) extra += need_big;
+  const bool use_x2 = !x2_taken && x2_cap >= need_H;
+  if (!use_x2 && held(own_name) < need_H) extra += need_H;
+  {
+    size_t free_b = 0, total_b = 0;
+    GW_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    // buffers that are re-allocated give their old size back first
+    size_t back = 0;
+    if (held("bse_packA") < need_small) back += held("bse_packA");
+    if (held("bse_packB") < need_big) back += held("bse_packB");
+    if (!use_x2 && held(own_name) < need_H) back += held(own_name);
+    const size_t margin = std::max<size_t>((size_t)4 << 30, total_b / 32);
+    if (extra * sizeof(double) + margin > free_b + back * sizeof(double)) return false;
+  }
+  double* packA = ctx->buf("bse_packA", need_small);
+  double* packB = ctx->buf("bse_packB", need_big);
+  double* H = use_x2 ? ctx->X2 : ctx->buf(own_name, need_H);
+  if (use_x2) blk.x2_epoch = ++ctx->x2_epoch;
+  const BlockView vv = vv_view(ctx), cv = cv_view(ctx);
+  const double* X = ctx->X;
+  if (kind == 0) {
+    // packA[chi][(v1, v2)] = eps_inv[chi] M[v1][v2, chi]
+    launch_pack_block(vv.ptr, vv.pole, vv.row, vt, vt, st.eps_inv, packA, small_plane, naux, ctx->stream);
+  } else {
+    // packA[chi][(c1, v2)] = eps_inv[chi] M[c1][v2, chi]
+    launch_pack_block(cv.ptr, cv.pole, cv.row, ct, vt, st.eps_inv, packA, small_plane, naux, ctx->stream);
+  }
+  ctx->launches++;
+  for (int a = 0; a < nloc; a += lchunk) {
+    const int n1 = std::min(lchunk, nloc - a);
+    // packB[chi][(l, c2)] = M[slice(a + l)][coff + c2, chi]: c-slices for Hd, v-slices for Hd2
+    const long long lfirst = (kind == 0 ? o.lcfirst : o.lvfirst) + a;
+    launch_pack_block(X + lfirst * npad + st.coff, ctx->ldx, npad, n1, ct, nullptr, packB, big_plane, naux,
+                      ctx->stream);
+    ctx->launches++;
+    GemmParams p;
+    p.Ki = naux;
+    p.A.s_ri = 1;
+    p.B.s_ri = 1;
+    if (kind == 0) {
+      // rows (v1, v2), columns (l, c2) -> H[(v2, c2), v1 * ncloc + a + l]
+      p.M = vt * vt;
+      p.N = n1 * ct;
+      p.A.ptr = packA;
+      p.A.s_ki = small_plane;
+      p.B.ptr = packB;
+      p.B.s_ki = big_plane;
+      p.C = H + (long long)a * ld;
+      p.Lm = vt;
+      p.sC_mo = (long long)o.ncloc * ld;
+      p.sC_mi = ct;
+      p.Ln = ct;
+      p.sC_no = ld;
+      p.sC_ni = 1;
+    } else {
+      // rows (l, c2), columns (c1, v2) -> H[(v2, c2), (a + l) * ct + c1]
+      p.M = n1 * ct;
+      p.N = ct * vt;
+      p.A.ptr = packB;
+      p.A.s_ki = big_plane;
+      p.B.ptr = packA;
+      p.B.s_ki = small_plane;
+      p.C = H + (long long)a * ct * ld;
+      p.Lm = ct;
+      p.sC_mo = (long long)ct * ld;
+      p.sC_mi = 1;
+      p.Ln = vt;
+      p.sC_no = ld;
+      p.sC_ni = ct;
+    }
+    ctx->gemm(p);
+  }
+  blk.H = H;
+  blk.in_x2 = use_x2;
+  blk.valid = true;
+  ctx->bse_dense_builds++;
+  ctx->bse_algo_flops += 2.0 * (double)B * B * naux;
+  return true;
+}
+
+// true: the block of this kind is resident and current (built here if the policy says so)
+bool dense_ready(gwbse_ctx* ctx, int kind, int k) {
+  auto& st = ctx->bse;
+  auto& blk = st.dense[kind];
+  const bool same_key = blk.key_mmn == ctx->mmn_version && blk.key_eps == st.eps_version && blk.vt == st.vt &&
+                        blk.ct == st.ct && blk.voff == st.voff && blk.coff == st.coff;
+  if (!same_key) {
+    blk.valid = false;
+    blk.refused = false;
+    blk.spent_flops = 0.0;
+    blk.key_mmn = ctx->mmn_version;
+    blk.key_eps = st.eps_version;
+    blk.vt = st.vt;
+    blk.ct = st.ct;
+    blk.voff = st.voff;
+    blk.coff = st.coff;
+  }
+  if (blk.valid && blk.in_x2 && blk.x2_epoch != ctx->x2_epoch) blk.valid = false;
+  if (ctx->bse_dense_mode == 0) return false;
+  if (blk.valid) return true;
+  if (blk.refused) return false;
+  const double per_col = factorised_flops_per_column(ctx, kind);
+  if (ctx->bse_dense_mode == 1) {
+    const double build = 2.0 * (double)st.size * st.size * ctx->naux;
+    if (blk.spent_flops + per_col * k < ctx->bse_dense_payback * build) {
+      blk.spent_flops += per_col * k;
+      return false;
+    }
+  }
+  if (!dense_build(ctx, kind)) {
+    blk.refused = true;  // no room under this key: stay factorised without asking again
+    return false;
+  }
+  return true;
+}
+
+// Y[owned rows] += alpha H^T X
+void dense_apply(gwbse_ctx* ctx, int kind, double alpha, int k, const double* Xin, int ldin, double* Y, int ldy) {
+  auto& st = ctx->bse;
+  const auto& blk = st.dense[kind];
+  if (blk.ncols == 0) return;
+  const OwnedSlices o = owned_slices(ctx);
+  GemmParams p;
+  p.M = (int)blk.ncols;
+  p.N = k;
+  p.Ki = st.size;
+  p.A.ptr = blk.H;
+  p.A.s_ri = blk.ld;
+  p.A.s_ki = 1;
+  p.B.ptr = Xin;
+  p.B.s_ri = ldin;
+  p.B.s_ki = 1;
+  p.sC_ni = ldy;
+  p.alpha = alpha;
+  p.beta = 1.0;
+  if (kind == 0) {
+    // row v1 * ncloc + l -> Y[(v1, c_rel0 + l * world)]
+    p.C = Y + o.c_rel0;
+    p.Lm = o.ncloc;
+    p.sC_mo = st.ct;
+    p.sC_mi = ctx->world;
+  } else {
+    // row l * ct + c1 -> Y[(v_rel0 + l * world, c1)]
+    p.C = Y + (long long)o.v_rel0 * st.ct;
+    p.Lm = st.ct;
+    p.sC_mo = (long long)ctx->world * st.ct;
+    p.sC_mi = 1;
+  }
+  ctx->gemm(p);
+  ctx->bse_dense_columns += k;
+}
+
 // Y = H X.  With a sharded Mmn every rank computes the part its slices contribute (v-slices for Hx / Hd2,
 // c-slices for Hd, rank 0 the Hqp term) into disjoint or additive entries of Y, then Y is all-reduced.
 void bse_matmul_dev(gwbse_ctx* ctx, int cqp, int cx, int cd, int cd2, int k, const double* Xin, int ldin, double* Y,
@@ -133,10 +358,9 @@ void bse_matmul_dev(gwbse_ctx* ctx, int cqp, int cx, int cd, int cd2, int k, con
   const double* X = ctx->X;
   GW_REQUIRE(ldin >= B && ldy >= B, "Shape mismatch in BSE matmul");
   if (k <= 0) return;
-  ctx->bse_algo_flops += (double)k * ((cx != 0 ? 4.0 * B * naux : 0.0) +
-                                      (cd != 0 ? 2.0 * naux * (double)vt * ct * (vt + ct) : 0.0) +
-                                      (cd2 != 0 ? 4.0 * (double)vt * vt * ct * naux : 0.0) +
-                                      (cqp != 0 ? 2.0 * B * (vt + ct) : 0.0));
+  // work of the formulation that is executed (all ranks together); the direct terms are added where their path
+  // is chosen: factorised legs, or the skinny product with the resident block (plus the build, once)
+  ctx->bse_algo_flops += (double)k * ((cx != 0 ? 4.0 * B * naux : 0.0) + (cqp != 0 ? 2.0 * B * (vt + ct) : 0.0));
   ctx->bse_columns += k;
   ctx->bse_products++;
   ensure_gathered(ctx);
@@ -200,7 +424,12 @@ void bse_matmul_dev(gwbse_ctx* ctx, int cqp, int cx, int cd, int cd2, int k, con
     vc_expand(ctx, (double)cx, k, W, Y, ldy);
   }
 
-  if (cd != 0 || cd2 != 0) {
+  const bool direct_dense = (cd != 0 || cd2 != 0) && dense_ready(ctx, cd != 0 ? 0 : 1, k);
+  if (direct_dense) {
+    ctx->bse_algo_flops += 2.0 * (double)B * B * k;
+    dense_apply(ctx, cd != 0 ? 0 : 1, cd != 0 ? -(double)cd : -(double)cd2, k, Xin, ldin, Y, ldy);
+  } else if (cd != 0 || cd2 != 0) {
+    ctx->bse_algo_flops += (double)k * factorised_flops_per_column(ctx, cd != 0 ? 0 : 1);
     const int vtp = round_up(vt, 2);
     const long long ldU = (long long)vtp * naux;
     const int nout = cd != 0 ? ncloc : nvloc;  // chunked index: local c1 for Hd, local v1 for Hd2
@@ -442,6 +671,12 @@ int gwbse_bse_configure(gwbse_ctx* ctx, int homo, int rpamin, int vmin, int cmax
   GW_REQUIRE(st.coff + st.ct <= ctx->mtotal && st.coff + st.ct <= ctx->ntotal, "BSE range exceeds Mmn");
   const int hs = st.vt + st.ct;
   GW_REQUIRE(ldh >= hs, "Hqp leading dimension too small");
+  // a changed screening invalidates the materialised blocks (dense_ready compares eps_version)
+  if (st.eps_inv_host.size() != (size_t)ctx->naux ||
+      !std::equal(st.eps_inv_host.begin(), st.eps_inv_host.end(), eps_inv)) {
+    st.eps_inv_host.assign(eps_inv, eps_inv + ctx->naux);
+    st.eps_version++;
+  }
   st.eps_inv = ctx->buf("bse_eps_inv", ctx->naux);
   st.hqp = ctx->buf("bse_hqp", (size_t)hs * hs);
   GW_CUDA(cudaMemcpyAsync(st.eps_inv, eps_inv, sizeof(double) * ctx->naux, cudaMemcpyHostToDevice, ctx->stream));
@@ -529,6 +764,19 @@ int gwbse_bse_stats(gwbse_ctx* ctx, double* algo_flops, long long* products, lon
   if (reset) {
     ctx->bse_algo_flops = 0.0;
     ctx->bse_products = ctx->bse_columns = 0;
+  }
+  GW_API_END(ctx)
+}
+
+int gwbse_bse_dense_stats(gwbse_ctx* ctx, long long* builds, long long* columns, double* resident_bytes) {
+  GW_API_BEGIN(ctx)
+  if (builds) *builds = ctx->bse_dense_builds;
+  if (columns) *columns = ctx->bse_dense_columns;
+  if (resident_bytes) {
+    double b = 0.0;
+    for (const auto& blk : ctx->bse.dense)
+      if (blk.valid && blk.H && (!blk.in_x2 || blk.x2_epoch == ctx->x2_epoch)) b += 8.0 * (double)blk.ld * (double)blk.ncols;
+    *resident_bytes = b;
   }
   GW_API_END(ctx)
 }

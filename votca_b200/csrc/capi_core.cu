@@ -187,6 +187,14 @@ int gwbse_set_option(gwbse_ctx* ctx, const char* key, double value) {
   } else if (k == "bse_chunk_bytes") {
     GW_REQUIRE(value >= 1024, "bse_chunk_bytes too small");
     ctx->bse_chunk_bytes = (size_t)value;
+  } else if (k == "bse_dense") {
+    // 0: the direct terms of the BSE operator stay factorised; 1: their B x B blocks are materialised once that
+    // pays back (default); 2: always, memory permitting
+    GW_REQUIRE(value == 0.0 || value == 1.0 || value == 2.0, "bse_dense is 0, 1 or 2");
+    ctx->bse_dense_mode = (int)value;
+  } else if (k == "bse_dense_payback") {
+    GW_REQUIRE(value >= 0.0, "bse_dense_payback must not be negative");
+    ctx->bse_dense_payback = value;
   } else if (k == "sigma_tree_min_terms") {
     ctx->sigma_tree_min_terms = (long long)value;
   } else if (k == "sigma_tree_bytes") {

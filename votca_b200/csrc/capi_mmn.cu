@@ -144,6 +144,7 @@ void mul_right_dev(gwbse_ctx* ctx, const double* R_dev, int ldr) {
   ctx->gemm(p);
   std::swap(ctx->X, ctx->X2);
   ctx->mmn_version++;
+  ctx->x2_epoch++;
   // evaluators hold pointers into X
   ctx->sig_ppm.ready = false;
 }
@@ -196,6 +197,7 @@ HoleView hole_view(gwbse_ctx* ctx, int n_occ) {
 double* mmn_scratch_x2(gwbse_ctx* ctx) {
   require_mmn(ctx);
   ensure_x2(ctx);
+  ctx->x2_epoch++;  // whatever was parked in the buffer (a materialised BSE block) is gone
   return ctx->X2;
 }
 }  // namespace gwbse
@@ -214,7 +216,11 @@ int gwbse_mmn_alloc(gwbse_ctx* ctx, int naux, int mmin, int mmax, int nmin, int 
       if (*p) GW_CUDA(cudaFree(*p));
       *p = nullptr;
     }
+    // materialised BSE blocks of the previous shape: give the memory back before the new tensor is sized
+    for (const char* name : {"bse_dense0", "bse_dense1", "bse_packA", "bse_packB"}) ctx->release_buf(name);
   }
+  ctx->x2_epoch++;
+  for (auto& blk : ctx->bse.dense) blk.valid = false;
   ctx->alloc_world = ctx->world;
   ctx->naux = naux;
   ctx->mmin = mmin;
@@ -251,6 +257,9 @@ int gwbse_mmn_free(gwbse_ctx* ctx) {
     if (*p) GW_CUDA(cudaFree(*p));
     *p = nullptr;
   }
+  for (const char* name : {"bse_dense0", "bse_dense1", "bse_packA", "bse_packB"}) ctx->release_buf(name);
+  ctx->x2_epoch++;
+  for (auto& blk : ctx->bse.dense) blk.valid = false;
   ctx->sig_ppm.ready = ctx->sig_exact.ready = ctx->bse.ready = false;
   GW_API_END(ctx)
 }
@@ -344,6 +353,7 @@ int gwbse_mmn_fill_begin(gwbse_ctx* ctx, int aux_sharded) {
     ctx->fill_lo = ctx->aux_begin(ctx->rank);
     ctx->fill_hi = ctx->aux_begin(ctx->rank + 1);
     ensure_x2(ctx);
+    ctx->x2_epoch++;
     const size_t n = (size_t)(ctx->fill_hi - ctx->fill_lo) * ctx->ldx * ctx->world;
     GW_CUDA(cudaMemsetAsync(ctx->X2, 0, sizeof(double) * n, ctx->stream));
   }

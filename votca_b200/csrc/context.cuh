@@ -170,8 +170,26 @@ struct gwbse_ctx {
     long long gathered_version = -1;  // multi-GPU: version of X the replicated vv / cv blocks were built from
     int gathered_voff = -1, gathered_vt = -1, gathered_ct = -1;
     std::vector<double> hqp_host;
-    std::vector<double> eps_inv_host;
+    std::vector<double> eps_inv_host;  // last screening uploaded (eps_version counts its changes)
+    long long eps_version = 0;
+    // Materialised direct-interaction blocks (capi_bse.cu): kind 0 = Hd, 1 = Hd2.  Column j of H holds the
+    // coefficients of local output row j against every input row (v2, c2): H[(v2 * ct + c2) + j * ld].
+    struct DenseBlock {
+      double* H = nullptr;
+      long long ld = 0, ncols = 0;
+      bool valid = false, in_x2 = false, refused = false;
+      long long x2_epoch = -1;
+      // key the block (and the payback counter) belongs to
+      long long key_mmn = -1, key_eps = -1;
+      int vt = 0, ct = 0, voff = 0, coff = 0;
+      double spent_flops = 0.0;  // factorised work done under this key so far
+    } dense[2];
   } bse;
+  // bse_dense: 0 never materialise, 1 when it pays back (default), 2 always (if memory allows)
+  int bse_dense_mode = 1;
+  double bse_dense_payback = 0.25;  // build once the factorised work under one key reaches this fraction of a build
+  long long bse_dense_builds = 0, bse_dense_columns = 0;
+  long long x2_epoch = 0;  // bumped whenever the second Mmn buffer is written or handed out as scratch
   double bse_algo_flops = 0.0;  // SURVEY.md 8(d) F_bse summed over the operator products so far
   long long bse_columns = 0, bse_products = 0;
   size_t bse_chunk_bytes = (size_t)8 << 30;  // size of the Hd intermediate per chunk
@@ -186,6 +204,12 @@ struct gwbse_ctx {
       b.cap = n;
     }
     return b.p;
+  }
+  void release_buf(const std::string& name) {
+    auto it = bufs.find(name);
+    if (it == bufs.end()) return;
+    if (it->second.p) GW_CUDA(cudaFree(it->second.p));
+    bufs.erase(it);
   }
   // algo_flops < 0: 2*M*N*K per batch (half for lower_only)
   void gemm(const gwbse::GemmParams& p, int cfg = -1, int splitk = 0, double algo_flops = -1.0);
@@ -284,6 +308,8 @@ void launch_coldots(int m, int n, const double* X, long long ldx, const double* 
                     cudaStream_t s);
 void launch_scale_cols(int m, int n, double* A, long long lda, const double* s_dev, cudaStream_t s);
 void launch_copy_block(int m, int n, const double* A, long long lda, double* B, long long ldb, cudaStream_t s);
+void launch_pack_block(const double* src, long long s_pole, long long s_outer, int L1, int L2, const double* scale,
+                       double* out, long long plane, int npoles, cudaStream_t s);
 void launch_rotate_scatter(const double* T, int q, int nloc, int naux, double* X, long long ldx, int npad, int lfirst,
                            int row0, cudaStream_t s);
 void launch_invsqrt_scale(double* out, const double* w, int n, double etol, int* removed_dev, cudaStream_t s);

@@ -244,8 +244,8 @@ void gemm_launch(GemmParams p, cudaStream_t stream, double* ws, size_t ws_bytes,
   }
   if (p.splitk > 1) {
     dim3 rb(128);
-    dim3 rg(ceil_div(p.M, 128), p.N, p.Z1 * p.Z2);
-    GW_REQUIRE(p.N <= 65535 && p.Z1 * p.Z2 <= 65535, "split-K reduce grid too large");
+    dim3 rg(ceil_div(p.M, 128), std::min(p.N, 65535), p.Z1 * p.Z2);
+    GW_REQUIRE(p.Z1 * p.Z2 <= 65535, "split-K reduce grid too large");
     switch (pl.cfg) {
       case 0:
         gemm_splitk_reduce_kernel<128, 128><<<rg, rb, 0, stream>>>(p);

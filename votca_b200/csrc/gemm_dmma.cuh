@@ -415,18 +415,20 @@ __global__ void gemm_splitk_reduce_kernel(const GemmParams p) {
   const int z = blockIdx.z;
   const int z1 = z % p.Z1, z2 = z / p.Z1;
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
-  const int col = blockIdx.y;
-  if (row >= p.M || col >= p.N) return;
-  if (p.lower_only && (col / BN) * BN > (row / BM) * BM + BM - 1) return;
-  const double* wsp = p.ws + (long long)z * p.splitk * Mpad * Npad + (long long)col * Mpad + row;
-  double s = 0.0;
-  for (int k = 0; k < p.splitk; ++k) s += wsp[(long long)k * Mpad * Npad];
-  double* dst = p.C + z1 * p.sC_z1 + z2 * p.sC_z2 + (long long)(row / p.Lm) * p.sC_mo +
-                (long long)(row % p.Lm) * p.sC_mi + (long long)(col / p.Ln) * p.sC_no +
-                (long long)(col % p.Ln) * p.sC_ni;
-  double v = p.alpha * (p.nscale ? p.nscale[p.nscale_mod ? col % p.nscale_mod : col] : 1.0) * s;
-  if (p.beta != 0.0) v += p.beta * (*dst);
-  *dst = v;
+  if (row >= p.M) return;
+  // columns beyond the grid's y limit (65535) are taken in further rounds
+  for (int col = blockIdx.y; col < p.N; col += gridDim.y) {
+    if (p.lower_only && (col / BN) * BN > (row / BM) * BM + BM - 1) continue;
+    const double* wsp = p.ws + (long long)z * p.splitk * Mpad * Npad + (long long)col * Mpad + row;
+    double s = 0.0;
+    for (int k = 0; k < p.splitk; ++k) s += wsp[(long long)k * Mpad * Npad];
+    double* dst = p.C + z1 * p.sC_z1 + z2 * p.sC_z2 + (long long)(row / p.Lm) * p.sC_mo +
+                  (long long)(row % p.Lm) * p.sC_mi + (long long)(col / p.Ln) * p.sC_no +
+                  (long long)(col % p.Ln) * p.sC_ni;
+    double v = p.alpha * (p.nscale ? p.nscale[p.nscale_mod ? col % p.nscale_mod : col] : 1.0) * s;
+    if (p.beta != 0.0) v += p.beta * (*dst);
+    *dst = v;
+  }
 }
 
 // Host-side launcher (gemm_dmma.cu).  Chooses tile shape, split-K and vector

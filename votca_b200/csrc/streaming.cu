@@ -1,6 +1,7 @@
 // Streaming (HBM-bound) kernels of the GW-BSE path: coalesced, vectorised where
 // alignment allows, warp-shuffle reductions.  SURVEY.md section 8a rows a7 (weights),
 // a12/a14 (Sigma_c evaluation), a18 (BSE diagonal), a20 (Davidson corrections).
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 
@@ -153,6 +154,20 @@ __global__ void copy_block_kernel(int m, int n, const double* A, long long lda, 
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = blockIdx.y;
   if (i < m && j < n) B[i + j * ldb] = A[i + j * lda];
+}
+
+// Compact, optionally pole-scaled copy of a two-index block of the three-centre tensor (the operands of the
+// materialised BSE blocks): out[p * plane + a * L2 + b] = scale[p] * src[p * s_pole + a * s_outer + b].
+__global__ void pack_block_kernel(const double* __restrict__ src, long long s_pole, long long s_outer, int L1, int L2,
+                                  const double* __restrict__ scale, double* __restrict__ out, long long plane,
+                                  int npoles) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= L1 * L2) return;
+  const int a = idx / L2, b = idx - a * L2;
+  for (int p = blockIdx.y; p < npoles; p += gridDim.y) {
+    const double f = scale ? scale[p] : 1.0;
+    out[p * plane + idx] = f * src[p * s_pole + a * s_outer + b];
+  }
 }
 
 __global__ void invsqrt_scale_kernel(double* out, const double* w, int n, double etol, int* removed) {
@@ -457,6 +472,14 @@ void launch_rotate_scatter(const double* T, int q, int nloc, int naux, double* X
 void launch_copy_block(int m, int n, const double* A, long long lda, double* B, long long ldb, cudaStream_t s) {
   if (m <= 0 || n <= 0) return;
   copy_block_kernel<<<grid2(m, n), 256, 0, s>>>(m, n, A, lda, B, ldb);
+  GW_CUDA(cudaGetLastError());
+}
+void launch_pack_block(const double* src, long long s_pole, long long s_outer, int L1, int L2, const double* scale,
+                       double* out, long long plane, int npoles, cudaStream_t s) {
+  if (L1 <= 0 || L2 <= 0 || npoles <= 0) return;
+  GW_REQUIRE((long long)L1 * L2 < (1LL << 31), "block too large to pack");
+  dim3 grid((unsigned)(((long long)L1 * L2 + 255) / 256), (unsigned)std::min(npoles, 65535));
+  pack_block_kernel<<<grid, 256, 0, s>>>(src, s_pole, s_outer, L1, L2, scale, out, plane, npoles);
   GW_CUDA(cudaGetLastError());
 }
 void launch_invsqrt_scale(double* out, const double* w, int n, double etol, int* removed_dev, cudaStream_t s) {
