@@ -237,6 +237,12 @@ int gwbse_rpa_set_qsgw_rotation(gwbse_ctx* ctx, const double* U, int ldu, int qp
 /* RPA::Calculate_H2p_ApB (rpa.cc:281-326): (A+B) two-particle matrix, S x S, lower triangle */
 int gwbse_rpa_h2p_apb(gwbse_ctx* ctx, const double* energies, int homo, int rpamin, int rpamax,
                       double* apb_out_dev, int ld);
+/* One block of the unrestricted A+B matrix, RPA_UKS::Calculate_H2p_ApB (rpa_uks.cc:475-540):
+ *   block[(v1,c1), (v2,c2)] = alpha sum_chi M_ctx[v1][c1,chi] M_other[v2][c2,chi]
+ * rows: particle-hole pairs of `ctx` (homo), columns: those of `other` (homo_other), which holds the other spin
+ * channel's Mmn on the same GPU, idle during the call (it may be `ctx` itself).  diag(AmB) is added by the caller. */
+int gwbse_rpa_h2p_block(gwbse_ctx* ctx, gwbse_ctx* other, int homo, int homo_other, int rpamin, int rpamax,
+                        double alpha, double* block_dev, int ld);
 
 /* ---- Sigma (sigma_base.h:33-106) ---------------------------------------- */
 /* Sigma_base::CalcExchangeMatrix (sigma_base.cc:36-52): q x q, host out */
@@ -265,6 +271,19 @@ int gwbse_sigma_ppm_offdiag(gwbse_ctx* ctx, int q, const double* freqs, double* 
 int gwbse_sigma_exact_prepare(gwbse_ctx* ctx, const double* rpa_omegas, const double* XpY_dev, int ldxpy,
                               const double* energies, int homo, int rpamin, int rpamax, int qpmin, int qpmax,
                               double eta);
+/* The two halves of the call above on their own, for the unrestricted evaluator (Sigma_Exact_UKS::PrepareScreening,
+ * sigma_exact_uks.cc:37-61, with the screening modes of RPA_UKS::BuildCachedScreeningModes, rpa_uks.cc:91-161):
+ * project: Z[chi, s] (+)= sum_{v,c} M[v][c,chi] XpY[(v,c), s] for the channel held by ctx (XpY_dev points at the
+ *          channel's first row of the combined eigenvectors; accumulate != 0 adds to Z, which may live in the other
+ *          channel's context on the same GPU);
+ * prepare_modes: residues M_i Z of the qp window for nmodes screening modes (columns of Z) with frequencies omegas;
+ *          diag_pref / offdiag_pref multiply the pole sums of the diagonal / off-diagonal elements (closed shell:
+ *          2 and 1, sigma_exact.cc:57,106; per spin channel: 1 and 0.5, sigma_exact_uks.cc:82,140).               */
+int gwbse_sigma_exact_project(gwbse_ctx* ctx, const double* XpY_dev, int ldxpy, int ncols, int homo, int rpamin,
+                              int rpamax, int accumulate, double* Z_dev, int ldz);
+int gwbse_sigma_exact_prepare_modes(gwbse_ctx* ctx, const double* omegas, int nmodes, const double* Z_dev, int ldz,
+                                    const double* energies, int homo, int rpamin, int rpamax, int qpmin, int qpmax,
+                                    double eta, double diag_pref, double offdiag_pref);
 int gwbse_sigma_exact_eval(gwbse_ctx* ctx, int nreq, const int* levels, const double* freqs, double* sigma,
                            double* dsigma);
 int gwbse_sigma_exact_offdiag(gwbse_ctx* ctx, int q, const double* freqs, double* out, int ld);

@@ -5,6 +5,10 @@ Restates, on two oracle TCMatrix objects (alpha, beta):
                      :306-367 (epsilon(z))
   PPM on RPA_UKS     xtp/src/libxtp/gwbse/ppm.cc (same construction, spin-summed epsilon)
   Sigma_PPM_UKS      xtp/src/libxtp/self_energy_evaluators/sigma_ppm_uks.cc:30-142, sigma_base_uks.cc:25-69
+  H2p / screening    xtp/src/libxtp/gwbse/rpa_uks.cc:369-438 (Diagonalize_H2p), :440-556 (AmB, ApB), :91-161 (modes)
+  Sigma_Exact_UKS    xtp/src/libxtp/self_energy_evaluators/sigma_exact_uks.cc:37-141
+  Sigma_CDA_UKS      xtp/src/libxtp/self_energy_evaluators/sigma_cda_uks.cc:44-159 (the restricted formulas on the
+                     spin-summed dielectric matrix and the channel's own energies / Mmn)
   GW_UKS             xtp/src/libxtp/gwbse/gw_uks.cc:38-123 (configure), :188-295 (G0W0 / evGW loop), :314-383 (SolveQP),
                      :758-790 (Hqp)
   BSE_OPERATOR_UKS   xtp/src/libxtp/gwbse/bse_operator_uks.cc:26-264 (matmul, all blocks), :277-352 (diagonal)
@@ -110,6 +114,55 @@ class RPAUKS:
         res[np.diag_indices(len(res))] += 1.0
         return res
 
+    # rpa_uks.cc:440-474 (AmB), :475-556 (ApB: same prefactor 2 for the alpha-alpha, beta-beta and mixed blocks)
+    def _ph(self, s):
+        r = self.spin[s]
+        n_occ, n_unocc = r._sizes()
+        nt = r.Mmn.nsize()
+        # rows (v, c) of the channel's particle-hole space x aux
+        return np.concatenate([r.Mmn[v][nt - n_unocc:, :] for v in range(n_occ)], axis=0), n_occ, n_unocc
+
+    def h2p_amb(self):
+        out = []
+        for r in self.spin:
+            n_occ, n_unocc = r._sizes()
+            e = r.energies
+            out.append((e[n_occ:n_occ + n_unocc][None, :] - e[:n_occ][:, None]).reshape(-1))
+        return np.concatenate(out)
+
+    def h2p_apb(self):
+        Pa, _, _ = self._ph(0)
+        Pb, _, _ = self._ph(1)
+        P = np.concatenate([Pa, Pb], axis=0)
+        apb = 2.0 * (P @ P.T)
+        apb[np.diag_indices(len(apb))] += self.h2p_amb()
+        return apb
+
+    # rpa_uks.cc:369-438
+    def diagonalize_h2p(self):
+        amb = self.h2p_amb()
+        apb = self.h2p_apb()
+        erpa = -0.25 * (np.trace(apb) + amb.sum())
+        sq = np.sqrt(amb)
+        ev, evec = np.linalg.eigh(apb * sq[:, None] * sq[None, :])
+        if ev.min() <= 0.0:
+            raise RuntimeError("Detected non-positive eigenvalue.")
+        omega = np.sqrt(ev)
+        erpa += 0.5 * omega.sum()
+        XpY = (sq[:, None] * evec) / np.sqrt(omega)[None, :]
+        return omega, XpY, erpa
+
+    # rpa_uks.cc:91-161: the Coulomb-active modes sum_vc M[v][c,:] (X+Y)[vc, s] of both channels; dark (spin-like)
+    # combinations, norm below 1e-10 of the largest, are dropped
+    def screening_modes(self):
+        omega, XpY, _ = self.diagonalize_h2p()
+        Pa, _, _ = self._ph(0)
+        Pb, _, _ = self._ph(1)
+        modes = Pa.T @ XpY[:len(Pa)] + Pb.T @ XpY[len(Pa):]
+        norms = np.linalg.norm(modes, axis=0)
+        keep = norms > 1e-10 * max(1.0, norms.max())
+        return omega[keep], modes[:, keep]
+
 
 class SharedPPM:
     """ppm.cc:30-59 on the spin-summed dielectric matrix; shared by both spin channels (gw_uks.cc:107-122, 213-217)."""
@@ -142,20 +195,74 @@ class SigmaPPMUKS(osigma.SigmaPPM):
         self.Mmn.multiply_right(self.ppm.phi)
 
 
+class SigmaExactUKS(osigma.SigmaExact):
+    """sigma_exact_uks.cc: residues of the channel's Mmn on the shared screening modes; the pole sums carry no
+    closed-shell factor 2 (:82, :107, :140 against sigma_exact.cc:57, :76, :106)."""
+
+    def __init__(self, Mmn, rpa_spin, rpa_uks):
+        super().__init__(Mmn, rpa_spin)
+        self.rpa_uks = rpa_uks
+
+    def prepare_screening(self):  # :37-61
+        self.rpa_omegas, modes = self.rpa_uks.screening_modes()
+        off = self.opt.qpmin - self.opt.rpamin
+        self.residues = [self.Mmn[i + off] @ modes for i in range(self.qptotal)]
+
+    def calc_correlation_diag_element(self, level, frequency):
+        return 0.5 * super().calc_correlation_diag_element(level, frequency)
+
+    def calc_correlation_diag_element_derivative(self, level, frequency):
+        return 0.5 * super().calc_correlation_diag_element_derivative(level, frequency)
+
+    def calc_correlation_offdiag_element(self, l1, l2, f1, f2):
+        return 0.5 * super().calc_correlation_offdiag_element(l1, l2, f1, f2)
+
+
+class _SpinSummedRPA:
+    """What Sigma_CDA_UKS sees of RPA_UKS (sigma_cda_uks.cc:44-159): the dielectric matrix of both channels, the
+    energies and homo of its own."""
+
+    def __init__(self, rpa_uks, s):
+        self._uks, self._s = rpa_uks, s
+
+    def calculate_epsilon_i(self, frequency):
+        return self._uks.calculate_epsilon_i(frequency)
+
+    def calculate_epsilon_r(self, frequency):
+        return self._uks.calculate_epsilon_r(frequency)
+
+    def get_rpa_input_energies(self):
+        return self._uks.energies(self._s)
+
+    def __getattr__(self, name):  # ETA, homo, rpamin ... of the channel
+        return getattr(self._uks.spin[self._s], name)
+
+
+class SigmaCDAUKS(osigma.SigmaCDA):
+    def __init__(self, Mmn, rpa_uks, s):
+        super().__init__(Mmn, _SpinSummedRPA(rpa_uks, s))
+
+
 class _SpinGW(ogw.GW):
     """The per-spin half of GW_UKS: restricted root search (gw_uks.cc:314-747 mirrors gw.cc:323-757) on the spin's
     evaluator; the iteration loop is driven by GWUKS."""
 
-    def __init__(self, Mmn, vxc, dft_energies, rpa_spin, ppm):
+    def __init__(self, Mmn, vxc, dft_energies, rpa_spin, ppm, rpa_uks=None, spin=0):
         super().__init__(Mmn, vxc, dft_energies)
         self.rpa = rpa_spin
         self._ppm = ppm
+        self._rpa_uks, self._spin = rpa_uks, spin
 
     def configure(self, opt):
         self.opt = opt
         ogw.qps.normalize_grid_search_options(opt)
         self.qptotal = opt.qpmax - opt.qpmin + 1
-        self.sigma = SigmaPPMUKS(self.Mmn, self.rpa, self._ppm)
+        if opt.sigma_integration == "exact":
+            self.sigma = SigmaExactUKS(self.Mmn, self.rpa, self._rpa_uks)
+        elif opt.sigma_integration == "cda":
+            self.sigma = SigmaCDAUKS(self.Mmn, self._rpa_uks, self._spin)
+        else:
+            self.sigma = SigmaPPMUKS(self.Mmn, self.rpa, self._ppm)
         self.sigma.configure(osigma.SigmaOptions(
             homo=opt.homo, qpmin=opt.qpmin, qpmax=opt.qpmax, rpamin=opt.rpamin, rpamax=opt.rpamax, eta=opt.eta,
             quadrature_scheme=opt.quadrature_scheme, order=opt.order, alpha=opt.alpha))
@@ -170,13 +277,13 @@ class GWUKS:
         self.rpa = RPAUKS(Mmn_alpha, Mmn_beta)
         self.ppm = SharedPPM()
         self.dft = (np.asarray(dft_alpha, dtype=np.float64), np.asarray(dft_beta, dtype=np.float64))
-        self.spin = (_SpinGW(Mmn_alpha, vxc_alpha, dft_alpha, self.rpa.spin[0], self.ppm),
-                     _SpinGW(Mmn_beta, vxc_beta, dft_beta, self.rpa.spin[1], self.ppm))
+        self.spin = (_SpinGW(Mmn_alpha, vxc_alpha, dft_alpha, self.rpa.spin[0], self.ppm, self.rpa, 0),
+                     _SpinGW(Mmn_beta, vxc_beta, dft_beta, self.rpa.spin[1], self.ppm, self.rpa, 1))
 
     def configure(self, opt, homo_alpha, homo_beta):
         """opt: oracle GWOptions (homo is overwritten per spin)"""
-        if opt.sigma_integration != "ppm":
-            raise RuntimeError("oracle GW_UKS: only sigma_integration=ppm is restated")
+        if opt.sigma_integration not in ("ppm", "exact", "cda"):
+            raise RuntimeError("oracle GW_UKS: sigma_integration is ppm, exact or cda")
         import copy
         self.opt = opt
         self.rpa.configure(homo_alpha, homo_beta, opt.rpamin, opt.rpamax)
@@ -207,7 +314,8 @@ class GWUKS:
             if i_gw % o.reset_3c == 0 and i_gw != 0:
                 for g in self.spin:
                     g.Mmn.rebuild()
-            self.ppm.construct(self.rpa)
+            if o.sigma_integration == "ppm":  # gw_uks.cc:226-233: the other evaluators build their own screening
+                self.ppm.construct(self.rpa)
             for g in self.spin:
                 g.sigma.prepare_screening()
             if o.gw_mixing_order > 0 and i_gw > 0:

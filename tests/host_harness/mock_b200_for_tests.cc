@@ -40,7 +40,7 @@ struct gwbse_ctx {
   bool exact_ready = false;
   std::vector<double> residues, rpa_omegas, energies_exact;
   int ex_S = 0, ex_q = 0, ex_nocc = 0;
-  double ex_eta = 0.0;
+  double ex_eta = 0.0, ex_diag_pref = 2.0, ex_offdiag_pref = 1.0;
   // CDA: kappa matrices [order + 1][naux * naux] (last: kappa_0), quadrature, ranges
   bool cda_ready = false;
   std::vector<double> cda_kappa, cda_pts, cda_wts;
@@ -245,8 +245,8 @@ void exact_eval(gwbse_ctx* ctx, int level, double w, double* sigma, double* dsig
     for (int p = 0; p < S; ++p) {
       const double t = w - ctx->energies_exact[n] + (n < ctx->ex_nocc ? ctx->rpa_omegas[p] : -ctx->rpa_omegas[p]);
       const double r = ctx->residues[((size_t)level * ntot + n) * S + p], den = t * t + eta2;
-      s += 2.0 * r * r * t / den;
-      ds += 2.0 * r * r * (eta2 - t * t) / (den * den);
+      s += ctx->ex_diag_pref * r * r * t / den;
+      ds += ctx->ex_diag_pref * r * r * (eta2 - t * t) / (den * den);
     }
   *sigma = s;
   if (dsigma) *dsigma = ds;
@@ -769,6 +769,25 @@ int gwbse_sigma_update_energies(gwbse_ctx* ctx, int which, const double* e) {
   (which == 0 ? ctx->energies : ctx->energies_exact).assign(e, e + ctx->ntotal);
   MOCK_END(ctx)
 }
+int gwbse_rpa_h2p_block(gwbse_ctx* ctx, gwbse_ctx* other, int homo, int homo_other, int rpamin, int rpamax, double alpha,
+                        double* block, int ld) {
+  MOCK_BEGIN(ctx)
+  // RPA_UKS::Calculate_H2p_ApB, rpa_uks.cc:475-540 (one spin block, without the A-B diagonal)
+  require_mmn(ctx);
+  REQUIRE(other && other->naux == ctx->naux, "both channels live on one GPU with one aux basis");
+  const int n_occ = homo - rpamin + 1, n_unocc = rpamax - homo, no2 = homo_other - rpamin + 1, nu2 = rpamax - homo_other;
+  REQUIRE(n_occ > 0 && n_unocc > 0 && no2 > 0 && nu2 > 0, "empty particle-hole space");
+  REQUIRE(ld >= n_occ * n_unocc, "leading dimension too small");
+  for (int v2 = 0; v2 < no2; ++v2)
+    for (int c2 = 0; c2 < nu2; ++c2)
+      for (int v1 = 0; v1 < n_occ; ++v1)
+        for (int c1 = 0; c1 < n_unocc; ++c1) {
+          double s = 0.0;
+          for (int chi = 0; chi < ctx->naux; ++chi) s += ctx->hole(v1, n_occ + c1, chi) * other->hole(v2, no2 + c2, chi);
+          block[(v1 * n_unocc + c1) + (size_t)(v2 * nu2 + c2) * ld] = alpha * s;
+        }
+  MOCK_END(ctx)
+}
 int gwbse_sigma_ppm_eval(gwbse_ctx* ctx, int nreq, const int* levels, const double* freqs, double* sigma, double* dsigma) {
   MOCK_BEGIN(ctx)
   for (int i = 0; i < nreq; ++i) ppm_eval(ctx, levels[i], freqs[i], sigma + i, dsigma ? dsigma + i : nullptr);
@@ -835,6 +854,54 @@ int gwbse_sigma_exact_prepare(gwbse_ctx* ctx, const double* omegas, const double
   ctx->ex_q = q;
   ctx->ex_nocc = n_occ;
   ctx->ex_eta = eta;
+  ctx->ex_diag_pref = 2.0;
+  ctx->ex_offdiag_pref = 1.0;
+  ctx->exact_ready = true;
+  MOCK_END(ctx)
+}
+// halves of the call above for the unrestricted evaluator (sigma_exact_uks.cc:37-61, rpa_uks.cc:91-161)
+int gwbse_sigma_exact_project(gwbse_ctx* ctx, const double* XpY, int ldxpy, int ncols, int homo, int rpamin, int rpamax,
+                              int accumulate, double* Z, int ldz) {
+  MOCK_BEGIN(ctx)
+  require_mmn(ctx);
+  REQUIRE(rpamin == ctx->mmin && rpamin == ctx->nmin && rpamax == ctx->nmax, "RPA range must match Mmn");
+  const int n_occ = homo + 1 - rpamin, n_unocc = rpamax - homo, S = n_occ * n_unocc;
+  REQUIRE(ldxpy >= S && ldz >= ctx->naux && ncols >= 0, "invalid sizes");
+  for (int s2 = 0; s2 < ncols; ++s2)
+    for (int chi = 0; chi < ctx->naux; ++chi) {
+      double t = 0.0;
+      for (int v = 0; v < n_occ; ++v)
+        for (int c = 0; c < n_unocc; ++c)
+          t += ctx->hole(v, n_occ + c, chi) * XpY[(size_t)v * n_unocc + c + (size_t)s2 * ldxpy];
+      double& z = Z[chi + (size_t)s2 * ldz];
+      z = accumulate ? z + t : t;
+    }
+  MOCK_END(ctx)
+}
+int gwbse_sigma_exact_prepare_modes(gwbse_ctx* ctx, const double* omegas, int nmodes, const double* Z, int ldz,
+                                    const double* e, int homo, int rpamin, int rpamax, int qpmin, int qpmax, double eta,
+                                    double diag_pref, double offdiag_pref) {
+  MOCK_BEGIN(ctx)
+  require_mmn(ctx);
+  REQUIRE(rpamin == ctx->mmin && rpamin == ctx->nmin && rpamax == ctx->nmax, "RPA range must match Mmn");
+  const int q = qpmax - qpmin + 1, qpoff = qpmin - rpamin, ntot = ctx->ntotal;
+  REQUIRE(nmodes > 0 && ldz >= ctx->naux && q > 0 && qpoff >= 0 && qpoff + q <= ctx->mtotal, "invalid sizes");
+  ctx->residues.assign((size_t)q * ntot * nmodes, 0.0);
+  for (int i = 0; i < q; ++i)
+    for (int n = 0; n < ntot; ++n)
+      for (int s2 = 0; s2 < nmodes; ++s2) {
+        double r = 0.0;
+        for (int chi = 0; chi < ctx->naux; ++chi) r += ctx->M(qpoff + i, n, chi) * Z[chi + (size_t)s2 * ldz];
+        ctx->residues[((size_t)i * ntot + n) * nmodes + s2] = r;
+      }
+  ctx->rpa_omegas.assign(omegas, omegas + nmodes);
+  ctx->energies_exact.assign(e, e + ntot);
+  ctx->ex_S = nmodes;
+  ctx->ex_q = q;
+  ctx->ex_nocc = homo + 1 - rpamin;
+  ctx->ex_eta = eta;
+  ctx->ex_diag_pref = diag_pref;
+  ctx->ex_offdiag_pref = offdiag_pref;
   ctx->exact_ready = true;
   MOCK_END(ctx)
 }
@@ -857,8 +924,8 @@ int gwbse_sigma_exact_offdiag(gwbse_ctx* ctx, int q, const double* freqs, double
           for (int p = 0; p < S; ++p) {
             const double sh = n < ctx->ex_nocc ? ctx->rpa_omegas[p] : -ctx->rpa_omegas[p];
             const double t1 = freqs[i] - ctx->energies_exact[n] + sh, t2 = freqs[j] - ctx->energies_exact[n] + sh;
-            s += ctx->residues[((size_t)i * ntot + n) * S + p] * ctx->residues[((size_t)j * ntot + n) * S + p] *
-                 (t1 / (t1 * t1 + eta2) + t2 / (t2 * t2 + eta2));
+            s += ctx->ex_offdiag_pref * ctx->residues[((size_t)i * ntot + n) * S + p] *
+                 ctx->residues[((size_t)j * ntot + n) * S + p] * (t1 / (t1 * t1 + eta2) + t2 / (t2 * t2 + eta2));
           }
       out[i + (size_t)j * ld] = s;
     }

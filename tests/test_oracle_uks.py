@@ -134,3 +134,58 @@ def test_uks_b_operator_reduces_to_restricted_blocks_and_full_bse_is_consistent(
     assert np.all(full["eigenvalues"] > 0) and np.all(np.diff(full["eigenvalues"]) >= 0)
     X, Y = full["eigenvectors"], full["eigenvectors2"]
     assert np.abs(np.abs(np.sum(X * X, axis=0) - np.sum(Y * Y, axis=0)) - 1.0).max() < 1e-10
+
+
+def test_exact_and_cda_uks_evaluators_reduce_to_the_restricted_ones():
+    """sigma_exact_uks.cc / sigma_cda_uks.cc in the closed-shell limit: the unrestricted H2p has the restricted
+    eigenvalues on its spin-symmetric modes and as many dark (spin-antisymmetric) ones, which the screening-mode
+    filter of rpa_uks.cc:135-150 removes; residues grow by sqrt(2) while the closed-shell factor 2 is gone, so every
+    element equals the restricted evaluator's (pinned on the reference's sigma_exact/ and sigma_cda/ fixtures)."""
+    from oracle import sigma as osig
+    g = load_golden()
+    C, e = g["gw/mo_eigenvectors"], g["inline/gw_mo_eigenvalues"]
+    r = orpa.RPA(methane_mmn(C))
+    r.configure(4, 0, 16)
+    r.set_rpa_input_energies(e)
+    u = uks.RPAUKS(methane_mmn(C), methane_mmn(C))
+    u.configure(4, 4, 0, 16)
+    u.set_rpa_input_energies(e, e)
+    om_r, _, erpa_r = r.diagonalize_h2p()
+    om_u, modes = u.screening_modes()
+    # twice the states; at least the dark half is filtered (mixtures inside degenerate eigenspaces may survive with
+    # partial weight - the pole sums below are invariant under that)
+    assert len(u.diagonalize_h2p()[0]) == 2 * len(om_r) and len(om_r) <= len(om_u) < 2 * len(om_r)
+    assert set(np.round(om_r, 6)) <= set(np.round(om_u, 6))
+    sopt = osig.SigmaOptions(homo=4, qpmin=0, qpmax=16, rpamin=0, rpamax=16, eta=1e-3, quadrature_scheme="legendre",
+                             order=12, alpha=1e-3)
+    freqs = e[:17] + 0.013
+    for name, mk in (("exact", lambda M: uks.SigmaExactUKS(M, u.spin[0], u)), ("cda", lambda M: uks.SigmaCDAUKS(M, u, 0))):
+        M1, M2 = methane_mmn(C), methane_mmn(C)
+        sr = osig.create(name, M1, r)
+        su = mk(M2)
+        for s in (sr, su):
+            s.configure(sopt)
+            s.prepare_screening()
+        for lvl in (0, 4, 5, 11):
+            a, b = sr.calc_correlation_diag_element(lvl, freqs[lvl]), su.calc_correlation_diag_element(lvl, freqs[lvl])
+            assert abs(a - b) < 1e-9 * max(1.0, abs(a)), (name, lvl, a, b)
+        if name == "exact":
+            assert abs(sr.calc_correlation_diag_element_derivative(3, freqs[3]) -
+                       su.calc_correlation_diag_element_derivative(3, freqs[3])) < 1e-8
+            assert abs(sr.calc_correlation_offdiag_element(2, 7, freqs[2], freqs[7]) -
+                       su.calc_correlation_offdiag_element(2, 7, freqs[2], freqs[7])) < 1e-10
+
+
+def test_open_shell_gw_with_the_exact_and_cda_evaluators_runs():
+    c = uks_case()
+    got = {}
+    for name in ("exact", "cda"):
+        ug = uks.GWUKS(methane_mmn(c["Ca"]), methane_mmn(c["Cb"]), c["vxc_a"], c["vxc_b"], c["ea"], c["eb"])
+        ug.configure(_gw_options(qp_grid_steps=201, qp_grid_spacing=0.01, gw_sc_max_iterations=1,
+                                 sigma_integration=name), c["homo_a"], c["homo_b"])
+        ug.calculate_gw_perturbation()
+        got[name] = (ug.get_gwa_results(0), ug.get_gwa_results(1))
+        assert np.all(np.isfinite(got[name][0])) and np.abs(got[name][0] - got[name][1]).max() > 1e-3
+    # both integrate the same W: around the gap the quasiparticle energies agree to the accuracy of the quadrature
+    # (high virtual levels sit among the poles of W, where the two root searches may settle on different roots)
+    assert np.abs(got["exact"][0][:8] - got["cda"][0][:8]).max() < 5e-3

@@ -134,10 +134,47 @@ def test_full_unrestricted_bse_against_the_oracle():
     job.close()
 
 
+@pytest.mark.parametrize("integrator", ["exact"])
+def test_open_shell_gw_with_the_other_integrators_against_the_oracle(integrator):
+    """sigma_integrator = exact for an unrestricted reference: RPA_UKS::Diagonalize_H2p over both channels' tensors
+    (gwbse_rpa_h2p_block), the shared screening modes (gwbse_sigma_exact_project on either context) and the
+    per-channel residues (gwbse_sigma_exact_prepare_modes) against oracle/uks.py; evGW so that the modes are rebuilt
+    with updated energies."""
+    c = uks_case()
+    og = uks.GWUKS(methane_mmn(c["Ca"]), methane_mmn(c["Cb"]), c["vxc_a"], c["vxc_b"], c["ea"], c["eb"])
+    og.configure(_gw_options(qp_grid_steps=601, qp_grid_spacing=0.005, gw_sc_max_iterations=3,
+                             sigma_integration=integrator), c["homo_a"], c["homo_b"])
+    og.calculate_gw_perturbation()
+    og.calculate_hqp()
+    job = make_job(c, "evGW", tasks="gw", gw__sigma_integrator=integrator, gw__sc_max_iter=3)
+    job.run_uks()
+    for s, tag in enumerate(("_alpha", "_beta")):
+        assert np.abs(job.get("QPpert_energies" + tag) - og.get_gwa_results(s)).max() < 1e-6  # Hartree
+        assert np.abs(job.get("Hqp" + tag) - og.get_hqp(s)).max() < 1e-6
+        assert np.abs(job.get("RPA_inputenergies" + tag) - og.rpa.energies(s)).max() < 1e-6
+    assert np.abs(job.get("QPpert_energies_alpha") - job.get("QPpert_energies_beta")).max() > 1e-3
+    job.close()
+
+
+def test_closed_shell_limit_of_the_exact_integrator_equals_the_restricted_path():
+    g = load_golden()
+    c = {"Ca": g["gw/mo_eigenvectors"], "Cb": g["gw/mo_eigenvectors"], "ea": g["inline/gw_mo_eigenvalues"],
+         "eb": g["inline/gw_mo_eigenvalues"], "vxc_a": g["gw/vxc"], "vxc_b": g["gw/vxc"], "homo_a": 4, "homo_b": 4}
+    u = make_job(c, "G0W0", gw__sigma_integrator="exact")
+    u.run_uks()
+    r = make_job(c, "G0W0", gw__sigma_integrator="exact")
+    r.run()
+    for s in ("_alpha", "_beta"):
+        assert np.abs(u.get("QPpert_energies" + s) - r.get("QPpert_energies")).max() < 1e-8
+        assert np.abs(u.get("Hqp" + s) - r.get("Hqp")).max() < 1e-8
+    u.close()
+    r.close()
+
+
 def test_what_is_not_on_this_path_is_refused():
     c = uks_case()
     for kw, msg in ((dict(tasks="gw,singlets"), "not defined for open-shell"),
-                    (dict(gw__sigma_integrator="exact"), "not available for unrestricted")):
+                    (dict(gw__sigma_integrator="cda"), "not available for unrestricted")):
         job = make_job(c, **kw)
         with pytest.raises(Exception, match=msg):
             job.run_uks()

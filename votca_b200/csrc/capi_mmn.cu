@@ -666,6 +666,47 @@ int gwbse_rpa_h2p_apb(gwbse_ctx* ctx, const double* energies, int homo, int rpam
   GW_API_END(ctx)
 }
 
+// One block of the unrestricted A+B matrix (rpa_uks.cc:475-540: alpha-alpha, beta-beta and the mixed block, all
+// with the same prefactor): rows are the particle-hole pairs of `ctx`, columns those of `other` (same GPU; may be
+// the same context).  The caller adds diag(AmB) and owns the layout of the combined matrix.
+int gwbse_rpa_h2p_block(gwbse_ctx* ctx, gwbse_ctx* other, int homo, int homo_other, int rpamin, int rpamax,
+                        double alpha, double* block_dev, int ld) {
+  GW_API_BEGIN(ctx)
+  GW_PROF(ctx, "rpa_h2p_block");
+  require_mmn(ctx);
+  GW_REQUIRE(other && other->X, "the other spin channel has no Mmn");
+  GW_REQUIRE(ctx->world == 1 && other->world == 1, "H2p is single-GPU (exact sigma does not scale, SURVEY.md 8e)");
+  GW_REQUIRE(other->device == ctx->device && other->naux == ctx->naux, "both channels live on one GPU with one aux basis");
+  for (const gwbse_ctx* c : {ctx, other})
+    GW_REQUIRE(rpamin == c->mmin && rpamin == c->nmin && rpamax == c->nmax, "RPA range must match Mmn");
+  const int n_occ = homo + 1 - rpamin, n_unocc = rpamax - homo;
+  const int n_occ_o = homo_other + 1 - rpamin, n_unocc_o = rpamax - homo_other;
+  GW_REQUIRE(n_occ > 0 && n_unocc > 0 && n_occ_o > 0 && n_unocc_o > 0, "empty particle-hole space");
+  GW_REQUIRE(ld >= n_occ * n_unocc, "leading dimension too small");
+  GemmParams p;
+  p.M = n_occ * n_unocc;
+  p.N = n_occ_o * n_unocc_o;
+  p.Ki = ctx->naux;
+  const HoleView hv = hole_view(ctx, n_occ), ho = hole_view(other, n_occ_o);
+  p.A.ptr = hv.ptr;
+  p.A.Lr = n_unocc;
+  p.A.s_ri = 1;
+  p.A.s_ro = hv.s_v;
+  p.A.s_ki = hv.s_chi;
+  p.B.ptr = ho.ptr;
+  p.B.Lr = n_unocc_o;
+  p.B.s_ri = 1;
+  p.B.s_ro = ho.s_v;
+  p.B.s_ki = ho.s_chi;
+  p.C = block_dev;
+  p.sC_mi = 1;
+  p.sC_ni = ld;
+  p.alpha = alpha;
+  ctx->gemm(p);
+  GW_CUDA(cudaStreamSynchronize(ctx->stream));
+  GW_API_END(ctx)
+}
+
 // ------------------------------ Sigma_x -------------------------------------
 int gwbse_sigma_x(gwbse_ctx* ctx, int homo, int rpamin, int qpmin, int qpmax, double* out, int ld) {
   GW_API_BEGIN(ctx)

@@ -247,24 +247,20 @@ int gwbse_sigma_ppm_offdiag(gwbse_ctx* ctx, int q, const double* freqs, double* 
   GW_API_END(ctx)
 }
 
-int gwbse_sigma_exact_prepare(gwbse_ctx* ctx, const double* rpa_omegas, const double* XpY_dev, int ldxpy,
-                              const double* energies, int homo, int rpamin, int rpamax, int qpmin, int qpmax,
-                              double eta) {
-  GW_API_BEGIN(ctx)
-  GW_PROF(ctx, "sigma_exact_prepare");
+// Z[chi, s] (+)= sum_{v,c} M[v][c,chi] XpY[(v,c), s]: the projection of (X+Y) columns on the auxiliary basis
+// (sigma_exact.cc:119-145 first half; rpa_uks.cc:103-121 per spin channel, where both channels add into one Z)
+static void exact_project(gwbse_ctx* ctx, const double* XpY_dev, int ldxpy, int ncols, int homo, int rpamin, int rpamax,
+                          bool accumulate, double* Z, int ldz) {
   GW_REQUIRE(ctx->X != nullptr, "Mmn not allocated");
   GW_REQUIRE(ctx->world == 1, "exact sigma is single-GPU (SURVEY.md 8e)");
   GW_REQUIRE(rpamin == ctx->mmin && rpamin == ctx->nmin && rpamax == ctx->nmax, "RPA range must match Mmn");
   const int n_occ = homo + 1 - rpamin, n_unocc = rpamax - homo;
   const int S = n_occ * n_unocc;
-  const int q = qpmax - qpmin + 1, qpoff = qpmin - rpamin;
-  const int naux = ctx->naux, npad = ctx->npad;
-  GW_REQUIRE(ldxpy >= S && q > 0 && qpoff >= 0 && qpoff + q <= ctx->mtotal, "invalid sizes");
-  // Z[chi, s] = sum_{v,c} M[v][c,chi] XpY[(v,c), s]
-  double* Z = ctx->buf("exact_Z", (size_t)naux * S);
+  GW_REQUIRE(ldxpy >= S && ldz >= ctx->naux && ncols >= 0, "invalid sizes");
+  if (ncols == 0 || S == 0) return;
   GemmParams p;
-  p.M = naux;
-  p.N = S;
+  p.M = ctx->naux;
+  p.N = ncols;
   p.Ko = n_occ;
   p.Ki = n_unocc;
   const HoleView hv = hole_view(ctx, n_occ);  // QSGW: rotated inside the QP window (sigma_exact.cc:119-145)
@@ -278,38 +274,52 @@ int gwbse_sigma_exact_prepare(gwbse_ctx* ctx, const double* rpa_omegas, const do
   p.B.s_ko = n_unocc;
   p.C = Z;
   p.sC_mi = 1;
-  p.sC_ni = naux;
+  p.sC_ni = ldz;
+  p.beta = accumulate ? 1.0 : 0.0;
   ctx->gemm(p);
-  // R[(i,n), s] = sum_chi M_i[n,chi] Z[chi,s]
+}
+
+// R[(i,n), s] = sum_chi M_i[n,chi] Z[chi,s] for the qp window, and the evaluator state around it
+static void exact_install_modes(gwbse_ctx* ctx, const double* omegas, int nmodes, const double* Z, int ldz,
+                                const double* energies, int homo, int rpamin, int rpamax, int qpmin, int qpmax,
+                                double eta, double diag_pref, double offdiag_pref) {
+  GW_REQUIRE(ctx->X != nullptr, "Mmn not allocated");
+  GW_REQUIRE(ctx->world == 1, "exact sigma is single-GPU (SURVEY.md 8e)");
+  GW_REQUIRE(rpamin == ctx->mmin && rpamin == ctx->nmin && rpamax == ctx->nmax, "RPA range must match Mmn");
+  const int n_occ = homo + 1 - rpamin;
+  const int q = qpmax - qpmin + 1, qpoff = qpmin - rpamin;
+  const int naux = ctx->naux, npad = ctx->npad;
+  GW_REQUIRE(nmodes > 0 && ldz >= naux && q > 0 && qpoff >= 0 && qpoff + q <= ctx->mtotal, "invalid sizes");
   const long long ldr = (long long)q * npad;
   if (ctx->exact_res) GW_CUDA(cudaFree(ctx->exact_res));
   ctx->exact_res = nullptr;
-  GW_CUDA(cudaMalloc(&ctx->exact_res, sizeof(double) * (size_t)ldr * S));
+  GW_CUDA(cudaMalloc(&ctx->exact_res, sizeof(double) * (size_t)ldr * nmodes));
   GemmParams r;
   r.M = (int)ldr;
-  r.N = S;
+  r.N = nmodes;
   r.Ki = naux;
   r.A.ptr = ctx->X + (long long)qpoff * npad;
   r.A.s_ri = 1;
   r.A.s_ki = ctx->ldx;
   r.B.ptr = Z;
-  r.B.s_ri = naux;
+  r.B.s_ri = ldz;
   r.B.s_ki = 1;
   r.C = ctx->exact_res;
   r.sC_mi = 1;
   r.sC_ni = ldr;
   ctx->gemm(r);
   auto& st = ctx->sig_exact;
-  std::vector<double> fac(S, 1.0);
-  upload(ctx, &st.fac, fac.data(), S);
-  upload(ctx, &st.pole, rpa_omegas, S);
+  std::vector<double> fac(nmodes, 1.0);
+  upload(ctx, &st.fac, fac.data(), nmodes);
+  upload(ctx, &st.pole, omegas, nmodes);
   upload(ctx, &st.energies, energies, ctx->ntotal);
-  st.npoles = S;
+  st.npoles = nmodes;
   st.nocc_boundary = n_occ;
   st.qpoff = 0;
   st.q = q;
   st.eta = eta;
-  st.diag_pref = 2.0;
+  st.diag_pref = diag_pref;
+  st.offdiag_pref = offdiag_pref;
   st.mat = ctx->exact_res;
   st.ld = ldr;
   st.lstride = npad;
@@ -318,6 +328,38 @@ int gwbse_sigma_exact_prepare(gwbse_ctx* ctx, const double* rpa_omegas, const do
   st.content_version++;
   sigma_tree_invalidate(st.tree);
   GW_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+int gwbse_sigma_exact_prepare(gwbse_ctx* ctx, const double* rpa_omegas, const double* XpY_dev, int ldxpy,
+                              const double* energies, int homo, int rpamin, int rpamax, int qpmin, int qpmax,
+                              double eta) {
+  GW_API_BEGIN(ctx)
+  GW_PROF(ctx, "sigma_exact_prepare");
+  const int S = (homo + 1 - rpamin) * (rpamax - homo);
+  GW_REQUIRE(S > 0, "invalid sizes");
+  double* Z = ctx->buf("exact_Z", (size_t)ctx->naux * S);
+  exact_project(ctx, XpY_dev, ldxpy, S, homo, rpamin, rpamax, false, Z, ctx->naux);
+  // closed shell: 2 * sum (sigma_exact.cc:57, :76), off-diagonal 2 * 0.5 * (...) (:103-106)
+  exact_install_modes(ctx, rpa_omegas, S, Z, ctx->naux, energies, homo, rpamin, rpamax, qpmin, qpmax, eta, 2.0, 1.0);
+  GW_API_END(ctx)
+}
+
+int gwbse_sigma_exact_project(gwbse_ctx* ctx, const double* XpY_dev, int ldxpy, int ncols, int homo, int rpamin,
+                              int rpamax, int accumulate, double* Z_dev, int ldz) {
+  GW_API_BEGIN(ctx)
+  GW_PROF(ctx, "sigma_exact_project");
+  exact_project(ctx, XpY_dev, ldxpy, ncols, homo, rpamin, rpamax, accumulate != 0, Z_dev, ldz);
+  GW_CUDA(cudaStreamSynchronize(ctx->stream));
+  GW_API_END(ctx)
+}
+
+int gwbse_sigma_exact_prepare_modes(gwbse_ctx* ctx, const double* omegas, int nmodes, const double* Z_dev, int ldz,
+                                    const double* energies, int homo, int rpamin, int rpamax, int qpmin, int qpmax,
+                                    double eta, double diag_pref, double offdiag_pref) {
+  GW_API_BEGIN(ctx)
+  GW_PROF(ctx, "sigma_exact_prepare");
+  exact_install_modes(ctx, omegas, nmodes, Z_dev, ldz, energies, homo, rpamin, rpamax, qpmin, qpmax, eta, diag_pref,
+                      offdiag_pref);
   GW_API_END(ctx)
 }
 
@@ -332,7 +374,7 @@ int gwbse_sigma_exact_eval(gwbse_ctx* ctx, int nreq, const int* levels, const do
 int gwbse_sigma_exact_offdiag(gwbse_ctx* ctx, int q, const double* freqs, double* out, int ld) {
   GW_API_BEGIN(ctx)
   GW_PROF(ctx, "sigma_exact_offdiag");
-  sigma_offdiag(ctx, ctx->sig_exact, 1.0, q, freqs, out, ld);
+  sigma_offdiag(ctx, ctx->sig_exact, ctx->sig_exact.offdiag_pref, q, freqs, out, ld);
   GW_API_END(ctx)
 }
 

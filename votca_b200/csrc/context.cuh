@@ -123,6 +123,7 @@ struct gwbse_ctx {
     int q = 0;
     double eta = 0.0;
     double diag_pref = 1.0;  // multiplies fac[] for the diagonal element
+    double offdiag_pref = 1.0;  // exact evaluator: 1 closed shell (2 * 0.5), 0.5 per spin channel
     const double* mat = nullptr;  // matrix holding level blocks: element (level l, n, pole p) at mat[p*ld + l*lstride + n]
     long long ld = 0, lstride = 0;
     double* fac = nullptr;     // per pole prefactor (device)

@@ -19,7 +19,7 @@
 // The two contexts take turns: every call on one is completed (stream synchronised) before the other gets work.  That
 // costs nothing here (the channels' work is sequential in the reference too) and it is required: the TMA-staged GEMM
 // was found to write wrong tiles when grids of another stream share the SMs with it.
-// Scope: sigma_integrator = ppm (the default), BSE in the Tamm-Dancoff approximation and in full, one GPU.
+// Scope: sigma_integrator = ppm (the default) and exact, BSE in the Tamm-Dancoff approximation and in full, one GPU.
 #pragma once
 #include "bse.h"
 #include "gw.h"
@@ -50,6 +50,13 @@ class RPA_UKS {
   void setRPAInputEnergies(const VectorXd& e_alpha, const VectorXd& e_beta) {
     alpha_.setRPAInputEnergies(e_alpha);
     beta_.setRPAInputEnergies(e_beta);
+    InvalidateH2pCache();
+  }
+  // rpa_uks.cc:72-80
+  void InvalidateH2pCache() const {
+    screening_cached_ = false;
+    screening_omegas_ = VectorXd();
+    screening_modes_ = Device::Buffer();
   }
   const VectorXd& getRPAInputEnergiesAlpha() const { return alpha_.getRPAInputEnergies(); }
   const VectorXd& getRPAInputEnergiesBeta() const { return beta_.getRPAInputEnergies(); }
@@ -78,7 +85,141 @@ class RPA_UKS {
       for (Index i = e.size() - (rpamax_ - qpmax); i < e.size(); ++i) e(i) += virt;
       ch.setRPAInputEnergies(e);
     }
+    InvalidateH2pCache();
   }
+
+  struct rpa_eigensolution {
+    VectorXd omega;
+    double ERPA_correlation = 0.0;
+  };
+  // rpa_uks.cc:369-438 with Calculate_H2p_AmB / _ApB (:440-556).  The (S_alpha + S_beta)^2 matrix is assembled on
+  // the alpha context's device from four GEMMs over the two channels' tensors (gwbse_rpa_h2p_block; the reference
+  // computes the lower triangles and the mixed block and mirrors them) and stays there; XpY_dev receives (X+Y).
+  rpa_eigensolution Diagonalize_H2p(Device::Buffer* XpY_dev) const {
+    const Device& da = Mmn_.alpha.device();
+    const Device& db = Mmn_.beta.device();
+    if (da.world() > 1) throw std::runtime_error("Diagonalize_H2p is single-GPU (S x S matrix not sharded)");
+    const Index homo[2] = {alpha_.homo(), beta_.homo()};
+    Index size[2];
+    VectorXd AmB;
+    {
+      std::vector<double> amb;
+      for (int s = 0; s < 2; ++s) {
+        const VectorXd& e = s == 0 ? alpha_.getRPAInputEnergies() : beta_.getRPAInputEnergies();
+        const Index n_occ = homo[s] + 1 - rpamin_, n_unocc = rpamax_ - homo[s];
+        size[s] = n_occ * n_unocc;
+        for (Index v = 0; v < n_occ; ++v)
+          for (Index c = 0; c < n_unocc; ++c) amb.push_back(e(n_occ + c) - e(v));
+      }
+      AmB = VectorXd(static_cast<Index>(amb.size()));
+      for (Index i = 0; i < AmB.size(); ++i) AmB(i) = amb[static_cast<size_t>(i)];
+    }
+    const Index S = size[0] + size[1];
+    Device::Buffer C = da.alloc(static_cast<size_t>(S * S));
+    const double kUKSApBPrefactor = 2.0;  // rpa_uks.cc:34
+    db.sync();
+    for (int sr = 0; sr < 2; ++sr)
+      for (int sc = 0; sc < 2; ++sc) {
+        const Device& dr = sr == 0 ? da : db;
+        const Device& dc = sc == 0 ? da : db;
+        const Index r0 = sr == 0 ? 0 : size[0], c0 = sc == 0 ? 0 : size[0];
+        dr.check(gwbse_rpa_h2p_block(dr.ctx(), dc.ctx(), (int)homo[sr], (int)homo[sc], (int)rpamin_, (int)rpamax_,
+                                     kUKSApBPrefactor, C.get() + r0 + c0 * S, (int)S));
+        dr.sync();  // one context at a time (see the note at the top of this file)
+      }
+    Device::Buffer damb = da.upload(AmB);
+    da.check(gwbse_axpy_dev(da.ctx(), 1, (int)S, 1.0, damb.get(), 1, C.get(), (int)(S + 1)));  // + diag(AmB)
+    rpa_eigensolution sol;
+    {
+      Device::Buffer d = da.alloc(static_cast<size_t>(S));
+      da.check(gwbse_dev_memset_zero(da.ctx(), d.get(), static_cast<size_t>(S)));
+      da.check(gwbse_axpy_dev(da.ctx(), 1, (int)S, 1.0, C.get(), (int)(S + 1), d.get(), 1));
+      MatrixXd diag = da.download(d.get(), S, 1);
+      sol.ERPA_correlation = -0.25 * (diag.col(0).sum() + AmB.sum());
+    }
+    VectorXd sq(S);
+    for (Index i = 0; i < S; ++i) sq(i) = std::sqrt(AmB(i));
+    Device::Buffer dsq = da.upload(sq);
+    da.check(gwbse_diag_scale_dev(da.ctx(), 'L', (int)S, (int)S, C.get(), (int)S, dsq.get(), C.get(), (int)S));
+    da.check(gwbse_diag_scale_dev(da.ctx(), 'R', (int)S, (int)S, C.get(), (int)S, dsq.get(), C.get(), (int)S));
+    VectorXd ev(S);
+    da.check(gwbse_sym_eig_dev(da.ctx(), (int)S, C.get(), (int)S, ev.data()));
+    double minCoeff = ev(0);
+    for (Index i = 0; i < S; ++i) minCoeff = std::min(minCoeff, ev(i));
+    if (minCoeff <= 0.0) throw std::runtime_error("Detected non-positive eigenvalue.");
+    sol.omega = VectorXd(S);
+    VectorXd osi(S);
+    for (Index i = 0; i < S; ++i) {
+      sol.omega(i) = std::sqrt(ev(i));
+      osi(i) = 1.0 / std::sqrt(sol.omega(i));
+    }
+    sol.ERPA_correlation += 0.5 * sol.omega.sum();
+    Device::Buffer dos = da.upload(osi);
+    da.check(gwbse_diag_scale_dev(da.ctx(), 'L', (int)S, (int)S, C.get(), (int)S, dsq.get(), C.get(), (int)S));
+    da.check(gwbse_diag_scale_dev(da.ctx(), 'R', (int)S, (int)S, C.get(), (int)S, dos.get(), C.get(), (int)S));
+    da.sync();
+    if (XpY_dev) *XpY_dev = std::move(C);
+    return sol;
+  }
+
+  // rpa_uks.cc:82-161: the Coulomb-active screening modes sum_vc M[v][c,:] (X+Y)[vc, s] of both channels, cached
+  // until the RPA input energies change; dark combinations (norm below 1e-10 of the largest) are dropped.  The
+  // modes live on the alpha context's device (naux x nmodes, ld = naux); both channels' evaluators read them.
+  void GetCachedScreeningModes(const VectorXd*& omegas, const double*& modes_dev, Index& nmodes) const {
+    if (!screening_cached_) BuildCachedScreeningModes();
+    omegas = &screening_omegas_;
+    modes_dev = screening_modes_.get();
+    nmodes = screening_omegas_.size();
+  }
+  double ERPA_correlation() const { return erpa_; }
+
+ private:
+  void BuildCachedScreeningModes() const {
+    const Device& da = Mmn_.alpha.device();
+    const Device& db = Mmn_.beta.device();
+    const Index naux = Mmn_.alpha.auxsize();
+    Device::Buffer XpY;
+    const rpa_eigensolution sol = Diagonalize_H2p(&XpY);
+    erpa_ = sol.ERPA_correlation;
+    const Index S = sol.omega.size();
+    const Index size_alpha = (alpha_.homo() + 1 - rpamin_) * (rpamax_ - alpha_.homo());
+    Device::Buffer Z = da.alloc(static_cast<size_t>(naux * S));
+    da.check(gwbse_sigma_exact_project(da.ctx(), XpY.get(), (int)S, (int)S, (int)alpha_.homo(), (int)rpamin_,
+                                       (int)rpamax_, 0, Z.get(), (int)naux));
+    da.sync();
+    db.check(gwbse_sigma_exact_project(db.ctx(), XpY.get() + size_alpha, (int)S, (int)S, (int)beta_.homo(),
+                                       (int)rpamin_, (int)rpamax_, 1, Z.get(), (int)naux));
+    db.sync();
+    MatrixXd modes = da.download(Z.get(), naux, S);
+    std::vector<double> norm(static_cast<size_t>(S));
+    double max_norm = 0.0;
+    for (Index s = 0; s < S; ++s) {
+      double n2 = 0.0;
+      for (Index x = 0; x < naux; ++x) n2 += modes(x, s) * modes(x, s);
+      norm[static_cast<size_t>(s)] = std::sqrt(n2);
+      max_norm = std::max(max_norm, norm[static_cast<size_t>(s)]);
+    }
+    const double tol = 1e-10 * std::max(1.0, max_norm);
+    std::vector<Index> keep;
+    for (Index s = 0; s < S; ++s)
+      if (norm[static_cast<size_t>(s)] > tol) keep.push_back(s);
+    screening_omegas_ = VectorXd(static_cast<Index>(keep.size()));
+    if (static_cast<Index>(keep.size()) == S) {
+      for (Index s = 0; s < S; ++s) screening_omegas_(s) = sol.omega(s);
+      screening_modes_ = std::move(Z);
+    } else {
+      MatrixXd active(naux, static_cast<Index>(keep.size()));
+      for (size_t j = 0; j < keep.size(); ++j) {
+        screening_omegas_(static_cast<Index>(j)) = sol.omega(keep[j]);
+        for (Index x = 0; x < naux; ++x) active(x, static_cast<Index>(j)) = modes(x, keep[j]);
+      }
+      screening_modes_ = da.upload(active);
+    }
+    da.sync();
+    screening_cached_ = true;
+  }
+
+ public:
 
   // eps_uks on the alpha context's device; valid until the next call
   double* calculate_epsilon_i_dev(double frequency) const {
@@ -118,6 +259,10 @@ class RPA_UKS {
   RPA alpha_, beta_;
   Index rpamin_ = 0, rpamax_ = 0;
   mutable Device::Buffer eps_;
+  mutable bool screening_cached_ = false;
+  mutable VectorXd screening_omegas_;
+  mutable Device::Buffer screening_modes_;
+  mutable double erpa_ = 0.0;
 };
 
 // sigma_ppm_uks.h / .cc: the restricted evaluator of one channel with the plasmon-pole model handed in
@@ -135,6 +280,54 @@ class Sigma_PPM_UKS final : public Sigma_PPM {
   const PPM* shared_ = nullptr;
 };
 
+// sigma_exact_uks.h / .cc: residues of the channel's Mmn on the screening modes both channels share; the pole sums
+// carry no closed-shell factor (sigma_exact_uks.cc:82, :107, :140 against sigma_exact.cc:57, :76, :106)
+class Sigma_Exact_UKS final : public Sigma_base {
+ public:
+  Sigma_Exact_UKS(TCMatrix_gwbse& Mmn, const RPA& rpa_channel, const RPA_UKS& rpa_uks)
+      : Sigma_base(Mmn, rpa_channel), rpa_uks_(rpa_uks) {}
+  void PrepareScreening() override {  // sigma_exact_uks.cc:37-61
+    const VectorXd* omegas = nullptr;
+    const double* modes = nullptr;
+    Index nmodes = 0;
+    rpa_uks_.GetCachedScreeningModes(omegas, modes, nmodes);
+    if (nmodes == 0) throw std::runtime_error("Sigma_Exact_UKS: no Coulomb-active screening mode");
+    const Device& dev = Mmn_.device();
+    dev.check(gwbse_sigma_exact_prepare_modes(dev.ctx(), omegas->data(), (int)nmodes, modes, (int)Mmn_.auxsize(),
+                                              rpa_.getRPAInputEnergies().data(), (int)opt_.homo, (int)opt_.rpamin,
+                                              (int)opt_.rpamax, (int)opt_.qpmin, (int)opt_.qpmax, opt_.eta, 1.0, 0.5));
+    dev.sync();
+  }
+  void EvalBatch(const std::vector<int>& levels, const std::vector<double>& freqs, std::vector<double>& sigma,
+                 std::vector<double>* dsigma) const override {
+    const Device& dev = Mmn_.device();
+    sigma.resize(levels.size());
+    if (dsigma) dsigma->resize(levels.size());
+    dev.check(gwbse_sigma_update_energies(dev.ctx(), 1, rpa_.getRPAInputEnergies().data()));
+    dev.check(gwbse_sigma_exact_eval(dev.ctx(), (int)levels.size(), levels.data(), freqs.data(), sigma.data(),
+                                     dsigma ? dsigma->data() : nullptr));
+  }
+  void EvalGroups(const std::vector<int>& levels, const std::vector<int>& gptr, const std::vector<double>& freqs,
+                  std::vector<double>& sigma, std::vector<double>* dsigma) const override {
+    const Device& dev = Mmn_.device();
+    sigma.resize(freqs.size());
+    if (dsigma) dsigma->resize(freqs.size());
+    dev.check(gwbse_sigma_update_energies(dev.ctx(), 1, rpa_.getRPAInputEnergies().data()));
+    dev.check(gwbse_sigma_eval_groups(dev.ctx(), 1, (int)levels.size(), levels.data(), gptr.data(), freqs.data(),
+                                      sigma.data(), dsigma ? dsigma->data() : nullptr));
+  }
+  MatrixXd CalcCorrelationOffDiag(const VectorXd& frequencies) const override {
+    MatrixXd out(qptotal_, qptotal_);
+    const Device& dev = Mmn_.device();
+    dev.check(gwbse_sigma_update_energies(dev.ctx(), 1, rpa_.getRPAInputEnergies().data()));
+    dev.check(gwbse_sigma_exact_offdiag(dev.ctx(), (int)qptotal_, frequencies.data(), out.data(), (int)qptotal_));
+    return out;
+  }
+
+ private:
+  const RPA_UKS& rpa_uks_;
+};
+
 class GW_UKS {
  public:
   struct options : GW::options {
@@ -150,18 +343,22 @@ class GW_UKS {
   // gw_uks.cc:38-123
   void configure(const options& opt) {
     opt_ = opt;
-    if (opt_.sigma_integration != "ppm")
+    if (opt_.sigma_integration != "ppm" && opt_.sigma_integration != "exact")
       throw std::runtime_error("GW_UKS: sigma_integrator=" + opt_.sigma_integration +
-                               " is not available for unrestricted references on this path (ppm is)");
+                               " is not available for unrestricted references on this path (ppm and exact are)");
     if (opt_.do_qsgw) throw std::runtime_error("GW_UKS: QSGW is defined for restricted references only");
     rpa_.configure(opt_.homo_alpha, opt_.homo_beta, opt_.rpamin, opt_.rpamax);
     for (int s = 0; s < 2; ++s) {
       GW::options o = opt_;
       o.homo = s == 0 ? opt_.homo_alpha : opt_.homo_beta;
       TCMatrix_gwbse& M = s == 0 ? Mmn_.alpha : Mmn_.beta;
-      auto sigma = std::make_unique<Sigma_PPM_UKS>(M, gw_[s]->rpa_);
-      sigma->SetSharedPPM(ppm_);
-      gw_[s]->configure(o, std::move(sigma));
+      if (opt_.sigma_integration == "exact") {  // sigmafactory_uks.cc
+        gw_[s]->configure(o, std::make_unique<Sigma_Exact_UKS>(M, gw_[s]->rpa_, rpa_));
+      } else {
+        auto sigma = std::make_unique<Sigma_PPM_UKS>(M, gw_[s]->rpa_);
+        sigma->SetSharedPPM(ppm_);
+        gw_[s]->configure(o, std::move(sigma));
+      }
       log_(std::string(" UKS ") + (s == 0 ? "alpha" : "beta") + " effective ranges: HOMO=" + std::to_string(o.homo) +
            " LUMO=" + std::to_string(o.homo + 1) + " | RPA [" + std::to_string(o.rpamin) + ":" +
            std::to_string(o.rpamax) + "] | GW [" + std::to_string(o.qpmin) + ":" + std::to_string(o.qpmax) + "]");
@@ -197,8 +394,10 @@ class GW_UKS {
         log_(" Rebuilding alpha/beta 3c integrals");
       }
       // one plasmon-pole model from the spin-summed dielectric matrix, installed in both channels
-      ppm_.PPM_construct_parameters(rpa_, Mmn_.alpha);
-      Mmn_.alpha.device().sync();
+      if (opt_.sigma_integration == "ppm") {  // gw_uks.cc:228-235: the other evaluators build their own screening
+        ppm_.PPM_construct_parameters(rpa_, Mmn_.alpha);
+        Mmn_.alpha.device().sync();
+      }
       // one channel after the other, never both contexts' grids on the GPU at once (see the note on streams below)
       for (int s = 0; s < 2; ++s) {
         gw_[s]->sigma_->PrepareScreening();
