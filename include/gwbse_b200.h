@@ -306,6 +306,13 @@ int gwbse_sigma_cda_prepare(gwbse_ctx* ctx, int order, const double* points, con
  * levels are relative to qpmin and must be owned by this rank.                    */
 int gwbse_sigma_cda_eval(gwbse_ctx* ctx, int nreq, const int* levels, const double* freqs, const double* energies,
                          double* sigma);
+/* Sigma_CDA_UKS (self_energy_evaluators/sigma_cda_uks.cc:44-159): the restricted formulas with the dielectric matrix
+ * of RPA_UKS (rpa_uks.cc:203-367, both spin channels) and the channel's own energies / Mmn.  While a partner is
+ * registered, every eps(z) the two calls above assemble is the mean of this context's and the partner's matrices
+ * (their weights carry the closed-shell factor 2).  energies_other: the partner's RPA input energies (ntotal),
+ * to be refreshed whenever they change; other = NULL returns to the restricted evaluator.  The partner context lives
+ * on the same GPU and is idle during the calls.                                                                    */
+int gwbse_sigma_cda_set_partner(gwbse_ctx* ctx, gwbse_ctx* other, int homo_other, const double* energies_other);
 
 /* ---- BSE operator (bse_operator.h:32-87) --------------------------------- */
 /* BSE_OPERATOR::configure + ctor data (bse_operator.cc:29-38): eps_inv (naux), Hqp ((vt+ct)^2, ld) */

@@ -43,6 +43,9 @@ struct gwbse_ctx {
   double ex_eta = 0.0, ex_diag_pref = 2.0, ex_offdiag_pref = 1.0;
   // CDA: kappa matrices [order + 1][naux * naux] (last: kappa_0), quadrature, ranges
   bool cda_ready = false;
+  gwbse_ctx* cda_partner = nullptr;
+  int cda_partner_homo = 0;
+  std::vector<double> cda_partner_e;
   std::vector<double> cda_kappa, cda_pts, cda_wts;
   int cda_order = 0, cda_sym = 0, cda_homo = 0, cda_rpamin = 0, cda_rpamax = 0, cda_qpmin = 0, cda_q = 0;
   double cda_alpha = 0.0, cda_eta = 0.0;
@@ -934,6 +937,27 @@ int gwbse_sigma_exact_offdiag(gwbse_ctx* ctx, int q, const double* freqs, double
 
 // ---- Sigma_CDA (sigma_cda.cc:30-141, ImaginaryAxisIntegration.cc:90-176), evaluated the reference's way: one
 //      I kappa_j product per node and evaluation ------------------------------------------------------------------
+// eps of the channel, or the spin-summed one of RPA_UKS when a partner channel is registered (sigma_cda_uks.cc)
+static void cda_epsilon(gwbse_ctx* ctx, int kind, double fre, double fim, double eta, const double* e, int homo, int rpamin,
+                        int rpamax) {
+  if (gwbse_rpa_epsilon(ctx, kind, fre, fim, eta, e, homo, rpamin, rpamax, nullptr, 0)) throw std::runtime_error(ctx->err);
+  gwbse_ctx* o = ctx->cda_partner;
+  if (!o) return;
+  if (gwbse_rpa_epsilon(o, kind, fre, fim, eta, ctx->cda_partner_e.data(), ctx->cda_partner_homo, rpamin, rpamax, nullptr, 0))
+    throw std::runtime_error(o->err);
+  for (size_t i = 0; i < ctx->eps.size(); ++i) ctx->eps[i] = 0.5 * (ctx->eps[i] + o->eps[i]);
+}
+int gwbse_sigma_cda_set_partner(gwbse_ctx* ctx, gwbse_ctx* other, int homo_other, const double* energies_other) {
+  MOCK_BEGIN(ctx)
+  ctx->cda_partner = other;
+  ctx->cda_partner_homo = homo_other;
+  ctx->cda_partner_e.clear();
+  if (other) {
+    REQUIRE(other != ctx && energies_other, "the partner channel needs its own filled Mmn");
+    ctx->cda_partner_e.assign(energies_other, energies_other + other->ntotal);
+  }
+  MOCK_END(ctx)
+}
 int gwbse_sigma_cda_prepare(gwbse_ctx* ctx, int order, const double* points, const double* weights, int symmetry,
                             double alpha, const double* energies, int homo, int rpamin, int rpamax, int qpmin,
                             int qpmax, double eta) {
@@ -951,11 +975,10 @@ int gwbse_sigma_cda_prepare(gwbse_ctx* ctx, int order, const double* points, con
     for (int i = 0; i < n; ++i) I[i + (size_t)i * n] -= 1.0;
     std::copy(I.begin(), I.end(), dst);
   };
-  if (gwbse_rpa_epsilon(ctx, 2, 0.0, 0.0, eta, energies, homo, rpamin, rpamax, nullptr, 0)) throw std::runtime_error(ctx->err);
+  cda_epsilon(ctx, 2, 0.0, 0.0, eta, energies, homo, rpamin, rpamax);
   inverse_minus_one(kzero);
   for (int j = 0; j < order; ++j) {
-    if (gwbse_rpa_epsilon(ctx, 0, points[j], 0.0, eta, energies, homo, rpamin, rpamax, nullptr, 0))
-      throw std::runtime_error(ctx->err);
+    cda_epsilon(ctx, 0, points[j], 0.0, eta, energies, homo, rpamin, rpamax);
     double* k = ctx->cda_kappa.data() + nn * j;
     inverse_minus_one(k);
     const double sc = std::exp(-std::pow(alpha * points[j], 2));
@@ -1020,9 +1043,7 @@ int gwbse_sigma_cda_eval(gwbse_ctx* ctx, int nreq, const int* levels, const doub
       else if (ad < 1e-10 && fermi > energies[i]) factor = -0.5;
       else if (ad < 1e-10 && fermi < energies[i]) factor = 0.5;
       if (std::fabs(factor) > 1e-10) {
-        if (gwbse_rpa_epsilon(ctx, 2, ad, ctx->cda_eta, ctx->cda_eta, energies, ctx->cda_homo, ctx->cda_rpamin,
-                              ctx->cda_rpamax, nullptr, 0))
-          throw std::runtime_error(ctx->err);
+        cda_epsilon(ctx, 2, ad, ctx->cda_eta, ctx->cda_eta, energies, ctx->cda_homo, ctx->cda_rpamin, ctx->cda_rpamax);
         std::vector<double> A(ctx->eps), x(n), row(n);
         for (int a = 0; a < n; ++a) x[a] = row[a] = ctx->M(m, i, a);
         solve(n, 1, A.data(), n, x.data(), n);

@@ -134,19 +134,24 @@ def test_full_unrestricted_bse_against_the_oracle():
     job.close()
 
 
-@pytest.mark.parametrize("integrator", ["exact"])
+@pytest.mark.parametrize("integrator", ["exact", "cda"])
 def test_open_shell_gw_with_the_other_integrators_against_the_oracle(integrator):
     """sigma_integrator = exact for an unrestricted reference: RPA_UKS::Diagonalize_H2p over both channels' tensors
     (gwbse_rpa_h2p_block), the shared screening modes (gwbse_sigma_exact_project on either context) and the
-    per-channel residues (gwbse_sigma_exact_prepare_modes) against oracle/uks.py; evGW so that the modes are rebuilt
-    with updated energies."""
+    per-channel residues (gwbse_sigma_exact_prepare_modes); sigma_integrator = cda: the device-resident contour
+    deformation of a channel with the dielectric matrix of both (gwbse_sigma_cda_set_partner).  Against
+    oracle/uks.py; evGW so that the screening is rebuilt with updated energies of both channels."""
     c = uks_case()
+    # the contour-deformation oracle assembles eps(z) per pole and evaluation in NumPy: a coarser scan and two
+    # self-consistency steps keep it to seconds
+    steps, spacing, iters = (601, 0.005, 3) if integrator == "exact" else (151, 0.02, 2)
     og = uks.GWUKS(methane_mmn(c["Ca"]), methane_mmn(c["Cb"]), c["vxc_a"], c["vxc_b"], c["ea"], c["eb"])
-    og.configure(_gw_options(qp_grid_steps=601, qp_grid_spacing=0.005, gw_sc_max_iterations=3,
-                             sigma_integration=integrator), c["homo_a"], c["homo_b"])
+    og.configure(_gw_options(qp_grid_steps=steps, qp_grid_spacing=spacing, gw_sc_max_iterations=iters,
+                             sigma_integration=integrator, order=12, alpha=1e-3), c["homo_a"], c["homo_b"])
     og.calculate_gw_perturbation()
     og.calculate_hqp()
-    job = make_job(c, "evGW", tasks="gw", gw__sigma_integrator=integrator, gw__sc_max_iter=3)
+    job = make_job(c, "evGW", tasks="gw", gw__sigma_integrator=integrator, gw__sc_max_iter=iters,
+                   gw__quadrature_order=12, gw__alpha=1e-3, gw__qp_grid_steps=steps, gw__qp_grid_spacing=spacing)
     job.run_uks()
     for s, tag in enumerate(("_alpha", "_beta")):
         assert np.abs(job.get("QPpert_energies" + tag) - og.get_gwa_results(s)).max() < 1e-6  # Hartree
@@ -174,7 +179,7 @@ def test_closed_shell_limit_of_the_exact_integrator_equals_the_restricted_path()
 def test_what_is_not_on_this_path_is_refused():
     c = uks_case()
     for kw, msg in ((dict(tasks="gw,singlets"), "not defined for open-shell"),
-                    (dict(gw__sigma_integrator="cda"), "not available for unrestricted")):
+                    (dict(gw__mode="evGW", gw__do_qsgw=True), "restricted references only")):
         job = make_job(c, **kw)
         with pytest.raises(Exception, match=msg):
             job.run_uks()

@@ -122,6 +122,31 @@ void check(gwbse_ctx* ctx, int rc) {
   if (rc != 0) throw std::runtime_error(ctx->err);
 }
 
+__global__ void cda_mean_kernel(double* a, const double* b, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = 0.5 * (a[i] + b[i]);
+}
+
+// eps into ctx->eps: the channel's own matrix, or - with a partner channel registered - the spin-summed one of
+// RPA_UKS (rpa_uks.cc:203-367; the restricted weights carry the closed-shell factor 2, so the sum is the mean).
+// The two contexts take turns on the GPU: each stream is drained before the other one gets work.
+void cda_epsilon(gwbse_ctx* ctx, int kind, double fre, double fim, double eta, const double* energies, int homo,
+                 int rpamin, int rpamax) {
+  check(ctx, gwbse_rpa_epsilon(ctx, kind, fre, fim, eta, energies, homo, rpamin, rpamax, nullptr, 0));
+  gwbse_ctx* o = ctx->cda.partner;
+  if (!o) return;
+  GW_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (gwbse_rpa_epsilon(o, kind, fre, fim, eta, ctx->cda.partner_energies.data(), ctx->cda.partner_homo, rpamin, rpamax,
+                        nullptr, 0))
+    throw std::runtime_error(o->err);
+  GW_CUDA(cudaSetDevice(ctx->device));
+  GW_CUDA(cudaStreamSynchronize(o->stream));
+  const size_t nn = (size_t)ctx->naux * ctx->naux;
+  cda_mean_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, ctx->stream>>>(ctx->eps, o->eps, nn);
+  GW_CUDA(cudaGetLastError());
+  ctx->launches++;
+}
+
 // sigma_cda.cc:62-77
 double residue_prefactor(double e_f, double e_m, double frequency) {
   const double tolerance = 1e-10;
@@ -164,13 +189,13 @@ int gwbse_sigma_cda_prepare(gwbse_ctx* ctx, int order, const double* points, con
   double* kappa = ctx->buf("cda_kappa", nn * (size_t)(order + 1));
   double* kzero = kappa + nn * (size_t)order;
   // kappa_0 = eps(0)^-1 - 1
-  check(ctx, gwbse_rpa_epsilon(ctx, 2, 0.0, 0.0, eta, energies, homo, rpamin, rpamax, nullptr, 0));
+  cda_epsilon(ctx, 2, 0.0, 0.0, eta, energies, homo, rpamin, rpamax);
   GW_CUDA(cudaMemcpyAsync(kzero, ctx->eps, sizeof(double) * nn, cudaMemcpyDeviceToDevice, ctx->stream));
   check(ctx, gwbse_inverse_dev(ctx, n, kzero, n));
   cda_minus_identity_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(kzero, n);
   for (int j = 0; j < order; ++j) {
     double* k = kappa + nn * (size_t)j;
-    check(ctx, gwbse_rpa_epsilon(ctx, 0, points[j], 0.0, eta, energies, homo, rpamin, rpamax, nullptr, 0));
+    cda_epsilon(ctx, 0, points[j], 0.0, eta, energies, homo, rpamin, rpamax);
     GW_CUDA(cudaMemcpyAsync(k, ctx->eps, sizeof(double) * nn, cudaMemcpyDeviceToDevice, ctx->stream));
     check(ctx, gwbse_inverse_dev(ctx, n, k, n));
     cda_kappa_kernel<<<dim3((n + 255) / 256, n), 256, 0, ctx->stream>>>(k, kzero, n,
@@ -221,6 +246,25 @@ int gwbse_sigma_cda_prepare(gwbse_ctx* ctx, int order, const double* points, con
   GW_API_END(ctx)
 }
 
+int gwbse_sigma_cda_set_partner(gwbse_ctx* ctx, gwbse_ctx* other, int homo_other, const double* energies_other) {
+  GW_API_BEGIN(ctx)
+  auto& st = ctx->cda;
+  if (!other) {
+    st.partner = nullptr;
+    st.partner_energies.clear();
+  } else {
+    GW_REQUIRE(other != ctx && other->X != nullptr && energies_other, "the partner channel needs its own filled Mmn");
+    GW_REQUIRE(ctx->world == 1 && other->world == 1, "the unrestricted path is single-GPU");
+    GW_REQUIRE(other->device == ctx->device && other->naux == ctx->naux && other->ntotal == ctx->ntotal &&
+                   other->mmin == ctx->mmin && other->nmin == ctx->nmin,
+               "both channels live on one GPU with the same aux basis and level window");
+    st.partner = other;
+    st.partner_homo = homo_other;
+    st.partner_energies.assign(energies_other, energies_other + other->ntotal);
+  }
+  GW_API_END(ctx)
+}
+
 int gwbse_sigma_cda_eval(gwbse_ctx* ctx, int nreq, const int* levels, const double* freqs, const double* energies,
                          double* sigma) {
   GW_API_BEGIN(ctx)
@@ -259,8 +303,7 @@ int gwbse_sigma_cda_eval(gwbse_ctx* ctx, int nreq, const int* levels, const doub
         const double factor = residue_prefactor(fermi, energies[i], freqs[r]);
         if (std::abs(factor) <= 1e-10) continue;
         const double abs_delta = std::abs(energies[i] - freqs[r]);
-        check(ctx, gwbse_rpa_epsilon(ctx, 2, abs_delta, st.eta, st.eta, energies, st.homo, st.rpamin, st.rpamax,
-                                     nullptr, 0));
+        cda_epsilon(ctx, 2, abs_delta, st.eta, st.eta, energies, st.homo, st.rpamin, st.rpamax);
         const long long row = (long long)(slices[r] + st.lfirst) * ctx->npad + i;
         cda_gather_row_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->X, ctx->ldx, row, n, b, b + n);
         check(ctx, gwbse_lu_solve_dev(ctx, n, 1, ctx->eps, n, b, n));

@@ -158,6 +158,11 @@ struct gwbse_ctx {
     long long node_stride = 0;     // doubles between the Q tables of consecutive quadrature nodes
     long long mmn_version = -1;
     std::vector<double> pts, wts;
+    // unrestricted reference (sigma_cda_uks.cc): the dielectric matrix is the mean of this channel's and the
+    // partner channel's closed-shell-weighted matrices
+    gwbse_ctx* partner = nullptr;
+    int partner_homo = 0;
+    std::vector<double> partner_energies;
   } cda;
 
   // ---- BSE ----

@@ -277,6 +277,7 @@ class Sigma_CDA : public Sigma_base {
       throw std::runtime_error(
           "sigma_integrator=cda is single-GPU: every residue needs a collective eps(z) assembly, and the per-rank QP "
           "searches ask for them at different times");
+    BindDielectricSource();
     bool symmetry = false;
     mapped_gauss_legendre(opt_.quadrature_scheme, opt_.order, pts_, wts_, symmetry);
     dev.check(gwbse_sigma_cda_prepare(dev.ctx(), (int)pts_.size(), pts_.data(), wts_.data(), symmetry ? 1 : 0,
@@ -304,6 +305,7 @@ class Sigma_CDA : public Sigma_base {
       }
     }
     std::vector<double> out(lv.size());
+    BindDielectricSource();
     dev.check(gwbse_sigma_cda_eval(dev.ctx(), (int)lv.size(), lv.data(), fr.data(), rpa_.getRPAInputEnergies().data(),
                                    out.data()));
     for (size_t r = 0; r < n; ++r) {
@@ -313,6 +315,14 @@ class Sigma_CDA : public Sigma_base {
   }
   // sigma_cda.h:64-67
   MatrixXd CalcCorrelationOffDiag(const VectorXd&) const final { return MatrixXd::Zero(qptotal_, qptotal_); }
+
+ protected:
+  // which dielectric matrix the device assembles: the channel's own (restricted), or - overridden by the unrestricted
+  // evaluator - the one of both spin channels
+  virtual void BindDielectricSource() const {
+    const Device& dev = Mmn_.device();
+    dev.check(gwbse_sigma_cda_set_partner(dev.ctx(), nullptr, 0, nullptr));
+  }
 
  private:
   std::vector<double> pts_, wts_;

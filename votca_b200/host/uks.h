@@ -19,7 +19,7 @@
 // The two contexts take turns: every call on one is completed (stream synchronised) before the other gets work.  That
 // costs nothing here (the channels' work is sequential in the reference too) and it is required: the TMA-staged GEMM
 // was found to write wrong tiles when grids of another stream share the SMs with it.
-// Scope: sigma_integrator = ppm (the default) and exact, BSE in the Tamm-Dancoff approximation and in full, one GPU.
+// Scope: sigma_integrator = ppm (the default), exact and cda, BSE in the Tamm-Dancoff approximation and in full, one GPU.
 #pragma once
 #include "bse.h"
 #include "gw.h"
@@ -328,6 +328,26 @@ class Sigma_Exact_UKS final : public Sigma_base {
   const RPA_UKS& rpa_uks_;
 };
 
+// sigma_cda_uks.h / .cc: the restricted contour-deformation formulas with the dielectric matrix of both channels
+// (RPA_UKS::calculate_epsilon_*), the channel's own energies, homo and Mmn
+class Sigma_CDA_UKS final : public Sigma_CDA {
+ public:
+  Sigma_CDA_UKS(TCMatrix_gwbse& Mmn, const RPA& rpa_channel, const RPA& rpa_other_channel, const Device& other_device)
+      : Sigma_CDA(Mmn, rpa_channel), other_(rpa_other_channel), other_dev_(other_device) {}
+
+ protected:
+  void BindDielectricSource() const override {
+    const Device& dev = Mmn_.device();
+    other_dev_.sync();
+    dev.check(gwbse_sigma_cda_set_partner(dev.ctx(), other_dev_.ctx(), (int)other_.homo(),
+                                          other_.getRPAInputEnergies().data()));
+  }
+
+ private:
+  const RPA& other_;
+  const Device& other_dev_;
+};
+
 class GW_UKS {
  public:
   struct options : GW::options {
@@ -343,9 +363,8 @@ class GW_UKS {
   // gw_uks.cc:38-123
   void configure(const options& opt) {
     opt_ = opt;
-    if (opt_.sigma_integration != "ppm" && opt_.sigma_integration != "exact")
-      throw std::runtime_error("GW_UKS: sigma_integrator=" + opt_.sigma_integration +
-                               " is not available for unrestricted references on this path (ppm and exact are)");
+    if (opt_.sigma_integration != "ppm" && opt_.sigma_integration != "exact" && opt_.sigma_integration != "cda")
+      throw std::runtime_error("GW_UKS: unknown sigma_integrator '" + opt_.sigma_integration + "'");
     if (opt_.do_qsgw) throw std::runtime_error("GW_UKS: QSGW is defined for restricted references only");
     rpa_.configure(opt_.homo_alpha, opt_.homo_beta, opt_.rpamin, opt_.rpamax);
     for (int s = 0; s < 2; ++s) {
@@ -354,6 +373,9 @@ class GW_UKS {
       TCMatrix_gwbse& M = s == 0 ? Mmn_.alpha : Mmn_.beta;
       if (opt_.sigma_integration == "exact") {  // sigmafactory_uks.cc
         gw_[s]->configure(o, std::make_unique<Sigma_Exact_UKS>(M, gw_[s]->rpa_, rpa_));
+      } else if (opt_.sigma_integration == "cda") {
+        TCMatrix_gwbse& Mo = s == 0 ? Mmn_.beta : Mmn_.alpha;
+        gw_[s]->configure(o, std::make_unique<Sigma_CDA_UKS>(M, gw_[s]->rpa_, gw_[1 - s]->rpa_, Mo.device()));
       } else {
         auto sigma = std::make_unique<Sigma_PPM_UKS>(M, gw_[s]->rpa_);
         sigma->SetSharedPPM(ppm_);
