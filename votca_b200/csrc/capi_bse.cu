@@ -8,6 +8,7 @@
 //   Hqp : two small GEMMs with the cc and vv blocks of Hqp            (2 B (vt+ct) k)
 // all on sub-blocks of the device-resident Mmn consumed in place by the DMMA GEMM.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/gwbse_b200.h"
@@ -154,6 +155,15 @@ double factorised_flops_per_column(gwbse_ctx* ctx, int kind) {
                    : 4.0 * (double)st.vt * st.vt * st.ct * ctx->naux;
 }
 
+// measurement knob (scratch/ncu_bse_dense.py): tile shape of the build GEMM, -1 = the planner's choice
+int dense_build_cfg() {
+  static const int cfg = [] {
+    const char* e = std::getenv("GWBSE_DENSE_BUILD_CFG");
+    return e ? std::atoi(e) : -1;
+  }();
+  return cfg;
+}
+
 bool dense_build(gwbse_ctx* ctx, int kind) {
   auto& st = ctx->bse;
   auto& blk = st.dense[kind];
@@ -263,7 +273,7 @@ bool dense_build(gwbse_ctx* ctx, int kind) {
       p.sC_no = ld;
       p.sC_ni = ct;
     }
-    ctx->gemm(p);
+    ctx->gemm(p, dense_build_cfg());
   }
   blk.H = H;
   blk.in_x2 = use_x2;
