@@ -121,8 +121,8 @@ def run(world, naux, mtotal, ntotal, voff, vt, ct, k, lchunk_force, seed=0):
                 lfirst = (lcfirst if kind == 0 else lvfirst) + a
                 packB = pack(X, lfirst * npad + coff, ldx, npad, n1, ct, None, big_plane, naux)
                 if kind == 0:
-                    gemm(Op(packA, s_ri=1, s_ki=small_plane), Op(packB, s_ri=1, s_ki=big_plane), vt * vt, n1 * ct, naux,
-                         H, a * ld, Lm=vt, sC_mo=ncloc * ld, sC_mi=ct, Ln=ct, sC_no=ld, sC_ni=1)
+                    gemm(Op(packB, s_ri=1, s_ki=big_plane), Op(packA, s_ri=1, s_ki=small_plane), n1 * ct, vt * vt, naux,
+                         H, a * ld, Lm=ct, sC_mo=ld, sC_mi=1, Ln=vt, sC_no=ncloc * ld, sC_ni=ct)
                 else:
                     gemm(Op(packB, s_ri=1, s_ki=big_plane), Op(packA, s_ri=1, s_ki=small_plane), n1 * ct, ct * vt, naux,
                          H, a * ct * ld, Lm=ct, sC_mo=ct * ld, sC_mi=1, Ln=vt, sC_no=ld, sC_ni=ct)

@@ -242,21 +242,23 @@ bool dense_build(gwbse_ctx* ctx, int kind) {
     p.Ki = naux;
     p.A.s_ri = 1;
     p.B.s_ri = 1;
+    // either way the GEMM's row index carries c2, the contiguous index of the block: the 8 rows a warp stores per
+    // instruction are one 64-byte run
     if (kind == 0) {
-      // rows (v1, v2), columns (l, c2) -> H[(v2, c2), v1 * ncloc + a + l]
-      p.M = vt * vt;
-      p.N = n1 * ct;
-      p.A.ptr = packA;
-      p.A.s_ki = small_plane;
-      p.B.ptr = packB;
-      p.B.s_ki = big_plane;
+      // rows (l, c2), columns (v1, v2) -> H[(v2, c2), v1 * ncloc + a + l]
+      p.M = n1 * ct;
+      p.N = vt * vt;
+      p.A.ptr = packB;
+      p.A.s_ki = big_plane;
+      p.B.ptr = packA;
+      p.B.s_ki = small_plane;
       p.C = H + (long long)a * ld;
-      p.Lm = vt;
-      p.sC_mo = (long long)o.ncloc * ld;
-      p.sC_mi = ct;
-      p.Ln = ct;
-      p.sC_no = ld;
-      p.sC_ni = 1;
+      p.Lm = ct;
+      p.sC_mo = ld;
+      p.sC_mi = 1;
+      p.Ln = vt;
+      p.sC_no = (long long)o.ncloc * ld;
+      p.sC_ni = ct;
     } else {
       // rows (l, c2), columns (c1, v2) -> H[(v2, c2), (a + l) * ct + c1]
       p.M = n1 * ct;
@@ -273,7 +275,11 @@ bool dense_build(gwbse_ctx* ctx, int kind) {
       p.sC_no = ld;
       p.sC_ni = ct;
     }
-    ctx->gemm(p, dense_build_cfg());
+    // both operands M-major: the 128 x 128 tile of the TMA kernel runs 8-12 % above the planner's pick
+    // (profiles/r02_bse_block_build_tiles.txt); small problems keep the planner
+    int cfg = dense_build_cfg();
+    if (cfg < 0 && p.M >= 512 && p.N >= 512) cfg = 10;
+    ctx->gemm(p, cfg);
   }
   blk.H = H;
   blk.in_x2 = use_x2;
