@@ -203,6 +203,12 @@ int gwbse_mmn_fill_from_basis(gwbse_ctx* ctx, const gwbse_basis* aux, const gwbs
  * OpenMP_CUDA::MultiplyRight openmp_cuda.cc:131-150): M[m] <- M[m] * R      */
 int gwbse_mmn_mul_right(gwbse_ctx* ctx, const double* R, int ldr);
 int gwbse_mmn_mul_right_dev(gwbse_ctx* ctx, const double* R_dev, int ldr);
+/* The same product when the caller will next read only the rows n in [n_lo, n_hi) of every slice - the BSE operator
+ * after BSE::SetupDirectInteractionOperator (bse.cc:188-204) reads n in the (v, c) window only, a third of the rows
+ * of a full-range tensor.  Those rows are rotated now; the others keep the rotation pending and get it, transparently,
+ * when any entry point that may read them runs (every one except gwbse_bse_* on a covered window).  Results are those
+ * of gwbse_mmn_mul_right_dev.  R_dev is copied.                                                                     */
+int gwbse_mmn_mul_right_window_dev(gwbse_ctx* ctx, const double* R_dev, int ldr, int n_lo, int n_hi);
 /* TCMatrix_gwbse::Rotate (threecenter.cc:108-131, QSGW): for the m slices of the QP window,
  * M[m].middleRows(qpmin - nmin, q) <- U^T * M[m].middleRows(qpmin - nmin, q); U is q x q, q = qpmax - qpmin + 1 */
 int gwbse_mmn_rotate(gwbse_ctx* ctx, const double* U, int ldu, int qpmin, int qpmax);

@@ -589,6 +589,10 @@ int gwbse_mmn_mul_right(gwbse_ctx* ctx, const double* R, int ldr) {
   MOCK_END(ctx)
 }
 int gwbse_mmn_mul_right_dev(gwbse_ctx* ctx, const double* R, int ldr) { return gwbse_mmn_mul_right(ctx, R, ldr); }
+// the device library defers the rows outside the window; the result is the same product
+int gwbse_mmn_mul_right_window_dev(gwbse_ctx* ctx, const double* R, int ldr, int, int) {
+  return gwbse_mmn_mul_right(ctx, R, ldr);
+}
 int gwbse_mmn_rotate(gwbse_ctx* ctx, const double* U, int ldu, int qpmin, int qpmax) {
   MOCK_BEGIN(ctx)
   require_mmn(ctx);

@@ -478,6 +478,49 @@ def test_bse_operator_materialised_blocks(ctx, dims):
         ctx.set_option("bse_dense", 1)
 
 
+@pytest.mark.parametrize("window", [(6, 40), (3, 39), (0, 47)])
+def test_mul_right_on_a_row_window_then_the_rest(ctx, window):
+    """gwbse_mmn_mul_right_window_dev: the BSE operator configured inside the window sees the rotated tensor at once
+    (both the factorised and the materialised direct terms), every other reader gets the complete product - also
+    when a second rotation follows while the first is still pending outside its window."""
+    rng = np.random.default_rng(39)
+    naux, mtotal, ntotal, homo, vmin, cmax = 60, 40, 47, 15, 6, 38
+    tc = random_tc(rng, naux, mtotal, ntotal)
+    push(ctx, tc)
+    Q1, _ = np.linalg.qr(rng.standard_normal((naux, naux)))
+    Q2, _ = np.linalg.qr(rng.standard_normal((naux, naux)))
+    vt, ct = homo - vmin + 1, cmax - homo
+    Hqp = rng.standard_normal((vt + ct, vt + ct))
+    Hqp = Hqp + Hqp.T
+    eps = rng.uniform(0.3, 1.0, naux)
+    opt = bop.BSEOperatorOptions(homo=homo, rpamin=0, qpmin=0, vmin=vmin, cmax=cmax)
+    X = rng.standard_normal((vt * ct, 7))
+    try:
+        for Q in (Q1, Q2):
+            ctx.mmn_mul_right_window(Q, *window)
+            tc.multiply_right(Q)
+            ctx.bse_configure(homo, 0, vmin, cmax, eps, Hqp)
+            for dense in (0, 2):
+                ctx.set_option("bse_dense", dense)
+                for name, co in OPS.items():
+                    op = bop.BSEOperator(*co, eps, tc, Hqp)
+                    op.configure(opt)
+                    assert rel_frob(op.matmul(X), ctx.bse_matmul(co, X)) < TOL, (name, dense)
+                    assert rel_frob(op.diagonal(), ctx.bse_diagonal(co)) < TOL, (name, dense)
+        assert rel_frob(tc.M, ctx.mmn_get_all()) < 1e-12
+        # epsilon reads every unoccupied row: a pending rotation is completed first
+        ctx.mmn_mul_right_window(Q1.T, *window)
+        tc.multiply_right(Q1.T)
+        e = np.sort(rng.uniform(-1.0, 2.0, ntotal))
+        r = orpa.RPA(tc)
+        r.configure(homo, 0, ntotal - 1)
+        r.set_rpa_input_energies(e)
+        assert rel_frob(r.calculate_epsilon_i(0.5), ctx.rpa_epsilon(0, 0.5, 1e-4, e, homo, 0, ntotal - 1)) < TOL
+        assert rel_frob(tc.M, ctx.mmn_get_all()) < 1e-12
+    finally:
+        ctx.set_option("bse_dense", 1)
+
+
 def test_bse_materialised_blocks_pay_back_rule(ctx):
     """Default policy: single-column products under ever-changing screening (the dynamical-screening loop of
     bse.cc:608-716) never form a block; a many-column product does at once; the result is the same either way."""

@@ -169,6 +169,16 @@ class Context:
         R = fmat(R)
         self.call("gwbse_mmn_mul_right", ptr(R), R.shape[0])
 
+    def mmn_mul_right_window(self, R, n_lo, n_hi):
+        """M[m] <- M[m] R with only the rows n in [n_lo, n_hi) rotated at once (gwbse_mmn_mul_right_window_dev)."""
+        R = fmat(R)
+        d = self.upload(R)
+        try:
+            self.call("gwbse_mmn_mul_right_window_dev", d, R.shape[0], int(n_lo), int(n_hi))
+            self.sync()
+        finally:
+            self.free(d)
+
     # ---- AO Coulomb integrals on the device ----
     def basis_create(self, l, nprim, centers, exps, coefs):
         """Flat shell arrays (see gwbse_basis_create) -> opaque device basis handle."""

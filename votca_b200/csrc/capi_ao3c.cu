@@ -351,6 +351,7 @@ int gwbse_mmn_fill_from_basis(gwbse_ctx* ctx, const gwbse_basis* aux, const gwbs
   GW_API_BEGIN(ctx)
   GW_REQUIRE(aux && dft, "null argument");
   GW_REQUIRE(ctx->X != nullptr, "Mmn not allocated (gwbse_mmn_alloc)");
+  mmn_complete_rotation(ctx);
   GW_REQUIRE(aux->host.nfunc == ctx->naux, "aux basis does not match the Mmn tensor");
   GW_REQUIRE(dft->host.nfunc == ctx->nbasis, "orbital basis does not match the MO coefficients (gwbse_mmn_set_mos)");
   if (aux_block < 1) aux_block = 64;

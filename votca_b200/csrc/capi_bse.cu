@@ -57,6 +57,15 @@ BlockView cv_view(gwbse_ctx* ctx) {
   return {ctx->buf("bse_gcv", (size_t)ctx->naux * st.ct * vtp), vtp, (long long)st.ct * vtp};
 }
 
+// The operator reads rows n in [voff, coff + ct) of every slice only.  A rotation that is still pending outside a
+// window (gwbse_mmn_mul_right_window_dev) has to be completed only if that window does not cover them.
+void bse_rows_ready(gwbse_ctx* ctx) {
+  const auto& pr = ctx->pending_rot;
+  if (!pr.active) return;
+  const auto& st = ctx->bse;
+  if (!st.ready || st.voff < pr.n_lo || st.coff + st.ct > pr.n_hi) mmn_complete_rotation(ctx);
+}
+
 // The two halves of the exchange term, also the building blocks of the cross-spin coupling of the unrestricted
 // operator (BSE_OPERATOR_UKS::add_direct_cross_tda_block, bse_operator_uks.cc:174-211), where the projection of one
 // spin channel is expanded in the other:
@@ -374,6 +383,7 @@ void bse_matmul_dev(gwbse_ctx* ctx, int cqp, int cx, int cd, int cd2, int k, con
   const double* X = ctx->X;
   GW_REQUIRE(ldin >= B && ldy >= B, "Shape mismatch in BSE matmul");
   if (k <= 0) return;
+  bse_rows_ready(ctx);
   // work of the formulation that is executed (all ranks together); the direct terms are added where their path
   // is chosen: factorised legs, or the skinny product with the resident block (plus the build, once)
   ctx->bse_algo_flops += (double)k * ((cx != 0 ? 4.0 * B * naux : 0.0) + (cqp != 0 ? 2.0 * B * (vt + ct) : 0.0));
@@ -577,6 +587,7 @@ void hd2_cross(gwbse_ctx* ctx, const double* other_X, int homo_in, double alpha,
   auto& st = ctx->bse;
   GW_REQUIRE(st.ready, "BSE operator not configured (gwbse_bse_configure)");
   GW_REQUIRE(ctx->world == 1, "the unrestricted operator is single-GPU");
+  mmn_complete_rotation(ctx);
   const int naux = ctx->naux, npad = ctx->npad;
   const long long ldx = ctx->ldx;
   const int vt_o = st.vt, ct_o = st.ct, voff = st.voff, coff_o = st.coff;
@@ -736,6 +747,7 @@ int gwbse_bse_vc_project_dev(gwbse_ctx* ctx, int k, const double* X_dev, int ldx
   GW_PROF(ctx, "bse_vc_project");
   GW_REQUIRE(ctx->bse.ready, "BSE operator not configured (gwbse_bse_configure)");
   GW_REQUIRE(ldx >= ctx->bse.size, "Shape mismatch in BSE projection");
+  bse_rows_ready(ctx);
   if (k > 0) vc_project(ctx, k, X_dev, ldx, W_dev);
   GW_API_END(ctx)
 }
@@ -747,6 +759,7 @@ int gwbse_bse_vc_expand_dev(gwbse_ctx* ctx, double alpha, int screened, int k, c
   GW_REQUIRE(ctx->bse.ready, "BSE operator not configured (gwbse_bse_configure)");
   GW_REQUIRE(ldy >= ctx->bse.size, "Shape mismatch in BSE expansion");
   GW_REQUIRE(ctx->world == 1, "gwbse_bse_vc_expand_dev accumulates into Y in place: single-GPU (the UKS operator)");
+  bse_rows_ready(ctx);
   if (k > 0) {
     const double* W = W_dev;
     if (screened) {  // W <- diag(eps^-1) W
@@ -768,6 +781,8 @@ int gwbse_bse_hd2_cross_dev(gwbse_ctx* ctx, gwbse_ctx* other, int homo_other, do
   GW_REQUIRE(other->naux == ctx->naux && other->ldx == ctx->ldx && other->npad == ctx->npad &&
                  other->mmin == ctx->mmin && other->nmin == ctx->nmin && other->device == ctx->device,
              "the two Mmn tensors must have the same shape and live on the same GPU");
+  mmn_complete_rotation(other);
+  GW_CUDA(cudaStreamSynchronize(other->stream));
   hd2_cross(ctx, other->X, homo_other, alpha, k, X_dev, ldx, Y_dev, ldy);
   GW_API_END(ctx)
 }
@@ -803,6 +818,7 @@ int gwbse_bse_diagonal(gwbse_ctx* ctx, int cqp, int cx, int cd, int cd2, double*
   auto& st = ctx->bse;
   GW_REQUIRE(st.ready, "BSE operator not configured (gwbse_bse_configure)");
   GW_REQUIRE(!(cd != 0 && cd2 != 0), "Hamiltonian cannot contain Hd and Hd2 at the same time");
+  bse_rows_ready(ctx);
   ensure_gathered(ctx);
   const int vt = st.vt, ct = st.ct, naux = ctx->naux;
   double* d = ctx->buf("bse_diag", st.size);

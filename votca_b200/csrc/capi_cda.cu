@@ -167,6 +167,7 @@ int gwbse_sigma_cda_prepare(gwbse_ctx* ctx, int order, const double* points, con
   GW_API_BEGIN(ctx)
   GW_PROF(ctx, "sigma_cda_prepare");
   GW_REQUIRE(ctx->X != nullptr, "Mmn not allocated");
+  mmn_complete_rotation(ctx);
   GW_REQUIRE(order > 0 && points && weights && energies, "invalid quadrature");
   GW_REQUIRE(rpamin == ctx->mmin && rpamin == ctx->nmin && rpamax == ctx->nmax, "RPA range must match Mmn");
   auto& st = ctx->cda;
@@ -270,6 +271,7 @@ int gwbse_sigma_cda_eval(gwbse_ctx* ctx, int nreq, const int* levels, const doub
   GW_API_BEGIN(ctx)
   GW_PROF(ctx, "sigma_cda_eval");
   auto& st = ctx->cda;
+  mmn_complete_rotation(ctx);
   GW_REQUIRE(st.ready && st.mmn_version == ctx->mmn_version, "CDA screening not prepared (gwbse_sigma_cda_prepare)");
   if (nreq > 0) {
     const int n = ctx->naux, nt = ctx->ntotal, order = st.order;

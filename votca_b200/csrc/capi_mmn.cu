@@ -12,7 +12,11 @@ namespace {
 
 inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
 
-void require_mmn(const gwbse_ctx* ctx) { GW_REQUIRE(ctx->X != nullptr, "Mmn not allocated (gwbse_mmn_alloc)"); }
+// every entry point of this file may read any row of the tensor: a rotation pending outside its window is applied
+void require_mmn(gwbse_ctx* ctx) {
+  GW_REQUIRE(ctx->X != nullptr, "Mmn not allocated (gwbse_mmn_alloc)");
+  gwbse::mmn_complete_rotation(ctx);
+}
 
 // contraction for a block of aux functions whose AO integrals already sit on the device
 // second Mmn-sized buffer: out-of-place target of MultiplyRight and staging area of the aux-sharded fill
@@ -151,7 +155,50 @@ void mul_right_dev(gwbse_ctx* ctx, const double* R_dev, int ldr) {
 
 }  // namespace
 
+namespace {
+// X[ml][n, :] <- X[ml][n, :] R for n in [n0, n1) of every local slice: the product goes through the second Mmn
+// buffer (same addresses), then back in place.  ldx = mlmax * npad, so (chi, ml) is one row index of pitch npad.
+void rotate_rows(gwbse_ctx* ctx, const double* Rp, int ldp, int n0, int n1) {
+  const int nw = n1 - n0;
+  if (nw <= 0 || ctx->ldx == 0) return;
+  ensure_x2(ctx);
+  GemmParams p;
+  p.M = ctx->mlmax * nw;
+  p.N = ctx->naux;
+  p.Ki = ctx->naux;
+  p.A.ptr = ctx->X + n0;
+  p.A.Lr = nw;
+  p.A.s_ri = 1;
+  p.A.s_ro = ctx->npad;
+  p.A.s_ki = ctx->ldx;
+  p.B.ptr = Rp;
+  p.B.s_ri = ldp;
+  p.B.s_ki = 1;
+  p.C = ctx->X2 + n0;
+  p.Lm = nw;
+  p.sC_mi = 1;
+  p.sC_mo = ctx->npad;
+  p.sC_ni = ctx->ldx;
+  ctx->gemm(p);
+  GW_CUDA(cudaMemcpy2DAsync(ctx->X + n0, sizeof(double) * ctx->npad, ctx->X2 + n0, sizeof(double) * ctx->npad,
+                            sizeof(double) * nw, (size_t)ctx->mlmax * ctx->naux, cudaMemcpyDeviceToDevice,
+                            ctx->stream));
+  ctx->x2_epoch++;
+}
+}  // namespace
+
 namespace gwbse {
+void mmn_complete_rotation(gwbse_ctx* ctx) {
+  auto& pr = ctx->pending_rot;
+  if (!pr.active) return;
+  pr.active = false;  // first: the calls below go through entry-point helpers
+  if (ctx->X == nullptr) return;
+  rotate_rows(ctx, pr.R, pr.ld, 0, pr.n_lo);
+  rotate_rows(ctx, pr.R, pr.ld, pr.n_hi, ctx->ntotal);
+  ctx->mmn_version++;
+  ctx->sig_ppm.ready = false;
+}
+
 HoleView hole_view(gwbse_ctx* ctx, int n_occ) {
   auto& qs = ctx->qsgw;
   if (!qs.active) return {ctx->X + n_occ, ctx->ldx, ctx->npad};
@@ -220,6 +267,7 @@ int gwbse_mmn_alloc(gwbse_ctx* ctx, int naux, int mmin, int mmax, int nmin, int 
     for (const char* name : {"bse_dense0", "bse_dense1", "bse_packA", "bse_packB"}) ctx->release_buf(name);
   }
   ctx->x2_epoch++;
+  ctx->pending_rot.active = false;
   for (auto& blk : ctx->bse.dense) blk.valid = false;
   ctx->alloc_world = ctx->world;
   ctx->naux = naux;
@@ -259,6 +307,7 @@ int gwbse_mmn_free(gwbse_ctx* ctx) {
   }
   for (const char* name : {"bse_dense0", "bse_dense1", "bse_packA", "bse_packB"}) ctx->release_buf(name);
   ctx->x2_epoch++;
+  ctx->pending_rot.active = false;
   for (auto& blk : ctx->bse.dense) blk.valid = false;
   ctx->sig_ppm.ready = ctx->sig_exact.ready = ctx->bse.ready = false;
   GW_API_END(ctx)
@@ -390,6 +439,32 @@ int gwbse_mmn_mul_right_dev(gwbse_ctx* ctx, const double* R_dev, int ldr) {
   GW_API_END(ctx)
 }
 
+int gwbse_mmn_mul_right_window_dev(gwbse_ctx* ctx, const double* R_dev, int ldr, int n_lo, int n_hi) {
+  GW_API_BEGIN(ctx)
+  GW_PROF(ctx, "mmn_mul_right");
+  require_mmn(ctx);  // completes an earlier pending rotation: rotations compose in order
+  GW_REQUIRE(ldr >= ctx->naux, "Shape mismatch in MultiplyRight");
+  GW_REQUIRE(n_lo >= 0 && n_hi <= ctx->ntotal && n_lo < n_hi, "invalid row window");
+  if (n_lo == 0 && n_hi == ctx->ntotal) {
+    mul_right_dev(ctx, R_dev, ldr);
+  } else if (ctx->ldx != 0) {
+    auto& pr = ctx->pending_rot;
+    pr.ld = round_up(ctx->naux, 2);
+    pr.R = ctx->buf("pending_R", (size_t)pr.ld * ctx->naux);
+    GW_CUDA(cudaMemcpy2DAsync(pr.R, sizeof(double) * pr.ld, R_dev, sizeof(double) * ldr, sizeof(double) * ctx->naux,
+                              ctx->naux, cudaMemcpyDeviceToDevice, ctx->stream));
+    // an even first row keeps the window's operand 16-byte aligned (TMA-describable)
+    n_lo &= ~1;
+    rotate_rows(ctx, pr.R, pr.ld, n_lo, n_hi);
+    pr.n_lo = n_lo;
+    pr.n_hi = n_hi;
+    pr.active = true;
+    ctx->mmn_version++;
+    ctx->sig_ppm.ready = false;
+  }
+  GW_API_END(ctx)
+}
+
 int gwbse_mmn_mul_right(gwbse_ctx* ctx, const double* R, int ldr) {
   GW_API_BEGIN(ctx)
   GW_PROF(ctx, "mmn_mul_right_h2d");
@@ -505,6 +580,7 @@ int gwbse_mmn_snapshot(gwbse_ctx* ctx) {
 int gwbse_mmn_restore(gwbse_ctx* ctx) {
   GW_API_BEGIN(ctx)
   GW_PROF(ctx, "mmn_restore");
+  ctx->pending_rot.active = false;  // the whole tensor is replaced
   require_mmn(ctx);
   GW_REQUIRE(ctx->Xsnap != nullptr, "no Mmn snapshot to restore");
   const size_t bytes = sizeof(double) * (size_t)std::max<long long>(ctx->ldx, 1) * ctx->naux;
@@ -675,6 +751,7 @@ int gwbse_rpa_h2p_block(gwbse_ctx* ctx, gwbse_ctx* other, int homo, int homo_oth
   GW_PROF(ctx, "rpa_h2p_block");
   require_mmn(ctx);
   GW_REQUIRE(other && other->X, "the other spin channel has no Mmn");
+  mmn_complete_rotation(other);
   GW_REQUIRE(ctx->world == 1 && other->world == 1, "H2p is single-GPU (exact sigma does not scale, SURVEY.md 8e)");
   GW_REQUIRE(other->device == ctx->device && other->naux == ctx->naux, "both channels live on one GPU with one aux basis");
   for (const gwbse_ctx* c : {ctx, other})

@@ -173,6 +173,7 @@ int gwbse_sigma_ppm_set(gwbse_ctx* ctx, const double* ppm_weight, const double* 
                         int homo, int rpamin, int qpmin, double eta) {
   GW_API_BEGIN(ctx)
   GW_REQUIRE(ctx->X != nullptr, "Mmn not allocated");
+  mmn_complete_rotation(ctx);
   auto& st = ctx->sig_ppm;
   const int naux = ctx->naux;
   std::vector<double> fac(naux);
@@ -216,6 +217,7 @@ int gwbse_sigma_ppm_eval(gwbse_ctx* ctx, int nreq, const int* levels, const doub
                          double* dsigma) {
   GW_API_BEGIN(ctx)
   GW_PROF(ctx, "sigma_ppm_eval");
+  mmn_complete_rotation(ctx);
   ctx->sig_ppm.mat = ctx->X;
   sigma_eval(ctx, ctx->sig_ppm, nreq, levels, freqs, sigma, dsigma);
   GW_API_END(ctx)
@@ -226,7 +228,10 @@ int gwbse_sigma_eval_groups(gwbse_ctx* ctx, int which, int ngroups, const int* l
   GW_API_BEGIN(ctx)
   GW_PROF(ctx, "sigma_eval_groups");
   auto& st = which == 0 ? ctx->sig_ppm : ctx->sig_exact;
-  if (which == 0) st.mat = ctx->X;
+  if (which == 0) {
+    mmn_complete_rotation(ctx);
+    st.mat = ctx->X;
+  }
   sigma_eval_groups(ctx, st, ngroups, levels, group_ptr, freqs, sigma, dsigma);
   GW_API_END(ctx)
 }
@@ -234,6 +239,7 @@ int gwbse_sigma_eval_groups(gwbse_ctx* ctx, int which, int ngroups, const int* l
 int gwbse_sigma_ppm_offdiag(gwbse_ctx* ctx, int q, const double* freqs, double* out, int ld) {
   GW_API_BEGIN(ctx)
   GW_PROF(ctx, "sigma_ppm_offdiag");
+  mmn_complete_rotation(ctx);
   ctx->sig_ppm.mat = ctx->X;
   const int qsave = ctx->sig_ppm.q;
   ctx->sig_ppm.q = q;
@@ -252,6 +258,7 @@ int gwbse_sigma_ppm_offdiag(gwbse_ctx* ctx, int q, const double* freqs, double* 
 static void exact_project(gwbse_ctx* ctx, const double* XpY_dev, int ldxpy, int ncols, int homo, int rpamin, int rpamax,
                           bool accumulate, double* Z, int ldz) {
   GW_REQUIRE(ctx->X != nullptr, "Mmn not allocated");
+  mmn_complete_rotation(ctx);
   GW_REQUIRE(ctx->world == 1, "exact sigma is single-GPU (SURVEY.md 8e)");
   GW_REQUIRE(rpamin == ctx->mmin && rpamin == ctx->nmin && rpamax == ctx->nmax, "RPA range must match Mmn");
   const int n_occ = homo + 1 - rpamin, n_unocc = rpamax - homo;
@@ -284,6 +291,7 @@ static void exact_install_modes(gwbse_ctx* ctx, const double* omegas, int nmodes
                                 const double* energies, int homo, int rpamin, int rpamax, int qpmin, int qpmax,
                                 double eta, double diag_pref, double offdiag_pref) {
   GW_REQUIRE(ctx->X != nullptr, "Mmn not allocated");
+  mmn_complete_rotation(ctx);
   GW_REQUIRE(ctx->world == 1, "exact sigma is single-GPU (SURVEY.md 8e)");
   GW_REQUIRE(rpamin == ctx->mmin && rpamin == ctx->nmin && rpamax == ctx->nmax, "RPA range must match Mmn");
   const int n_occ = homo + 1 - rpamin;

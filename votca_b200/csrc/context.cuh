@@ -196,6 +196,14 @@ struct gwbse_ctx {
   double bse_dense_payback = 0.25;  // build once the factorised work under one key reaches this fraction of a build
   long long bse_dense_builds = 0, bse_dense_columns = 0;
   long long x2_epoch = 0;  // bumped whenever the second Mmn buffer is written or handed out as scratch
+  // MultiplyRight restricted to a window of n (gwbse_mmn_mul_right_window_dev): rows n in [n_lo, n_hi) of every slice
+  // carry the rotation R, the others get it when an entry point that may read them runs (mmn_complete_rotation)
+  struct PendingRotation {
+    bool active = false;
+    int n_lo = 0, n_hi = 0;
+    double* R = nullptr;  // naux x naux at pitch ld (named buffer "pending_R")
+    int ld = 0;
+  } pending_rot;
   double bse_algo_flops = 0.0;  // SURVEY.md 8(d) F_bse summed over the operator products so far
   long long bse_columns = 0, bse_products = 0;
   size_t bse_chunk_bytes = (size_t)8 << 30;  // size of the Hd intermediate per chunk
@@ -289,6 +297,9 @@ struct HoleView {
   long long s_chi, s_v;
 };
 HoleView hole_view(gwbse_ctx* ctx, int n_occ);
+// applies a rotation left pending by gwbse_mmn_mul_right_window_dev to the rows outside its window (capi_mmn.cu);
+// every entry point that may read such rows calls it first, the BSE operator's only if its window is not covered
+void mmn_complete_rotation(gwbse_ctx* ctx);
 // the second Mmn buffer (out-of-place target of MultiplyRight) as scratch of the same shape as X (capi_mmn.cu)
 double* mmn_scratch_x2(gwbse_ctx* ctx);
 // Fill3cMO contraction of a device-resident AO block whose columns are pitch doubles apart (capi_mmn.cu)

@@ -251,7 +251,8 @@ class BSE {
     dev.check(gwbse_d2d(dev.ctx(), U.get(), eps, static_cast<size_t>(n * n)));
     VectorXd ev(n);
     dev.check(gwbse_sym_eig_dev(dev.ctx(), (int)n, U.get(), (int)n, ev.data()));
-    Mmn_.MultiplyRightWithAuxMatrix_dev(U.get(), n);
+    // the operators built on this tensor read the rows of the (v, c) window only
+    Mmn_.MultiplyRightWithAuxMatrix_dev(U.get(), n, opt_.vmin, opt_.cmax + 1);
     epsilon_0_inv_ = VectorXd::Zero(n);
     for (Index i = 0; i < n; ++i)
       if (ev(i) > 1e-8) epsilon_0_inv_(i) = 1 / ev(i);

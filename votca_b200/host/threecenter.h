@@ -120,6 +120,11 @@ class TCMatrix_gwbse {
   void MultiplyRightWithAuxMatrix_dev(const double* R_dev, Index ld) {
     dev_.check(gwbse_mmn_mul_right_dev(dev_.ctx(), R_dev, (int)ld));
   }
+  // the same product for a caller that goes on to read rows [n_lo, n_hi) (absolute level indices) only: the device
+  // rotates those now and the rest when something else needs it (gwbse_mmn_mul_right_window_dev)
+  void MultiplyRightWithAuxMatrix_dev(const double* R_dev, Index ld, Index n_lo, Index n_hi) {
+    dev_.check(gwbse_mmn_mul_right_window_dev(dev_.ctx(), R_dev, (int)ld, (int)(n_lo - nmin_), (int)(n_hi - nmin_)));
+  }
 
  private:
   // libint2_calls.cc:595-651: aux functions are processed block by block (the reference goes shell by shell)
