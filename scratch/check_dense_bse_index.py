@@ -103,6 +103,8 @@ def run(world, naux, mtotal, ntotal, voff, vt, ct, k, lchunk_force, seed=0):
                 cv = (gcv, 0, vtp, ct * vtp)
             # ---------------- dense_build
             ld = round_up(B, 2)
+            if ld % 256 == 0:
+                ld += 2
             ncols = vt * ncloc if kind == 0 else nvloc * ct
             if ncols == 0:
                 continue
@@ -146,6 +148,7 @@ def run(world, naux, mtotal, ntotal, voff, vt, ct, k, lchunk_force, seed=0):
 if __name__ == "__main__":
     for world in (1, 2, 3):
         for (naux, mt, nt, voff, vt, ct, k, lch) in [(7, 12, 14, 0, 4, 5, 3, 100), (6, 13, 13, 1, 3, 7, 2, 2),
-                                                     (5, 9, 11, 2, 3, 4, 4, 1), (4, 20, 21, 3, 5, 6, 1, 3)]:
+                                                     (5, 9, 11, 2, 3, 4, 4, 1), (4, 20, 21, 3, 5, 6, 1, 3),
+                                                     (3, 33, 34, 1, 16, 16, 2, 5)]:
             run(world, naux, mt, nt, voff, vt, ct, k, lch, seed=world)
     print("dense BSE block index algebra: ok (worlds 1, 2, 3; Hd and Hd2; chunked builds)")

@@ -24,7 +24,7 @@ def _load():
 
 @pytest.mark.parametrize("world", [1, 2, 3])
 @pytest.mark.parametrize("case", [(7, 12, 14, 0, 4, 5, 3, 100), (6, 13, 13, 1, 3, 7, 2, 2), (5, 9, 11, 2, 3, 4, 4, 1),
-                                  (4, 20, 21, 3, 5, 6, 1, 3)])
+                                  (4, 20, 21, 3, 5, 6, 1, 3), (3, 33, 34, 1, 16, 16, 2, 5)])
 def test_block_build_and_product_index_algebra(world, case):
     naux, mtotal, ntotal, voff, vt, ct, k, lchunk = case
     assert _load().run(world, naux, mtotal, ntotal, voff, vt, ct, k, lchunk, seed=world)

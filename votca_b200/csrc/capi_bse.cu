@@ -178,7 +178,10 @@ bool dense_build(gwbse_ctx* ctx, int kind) {
   auto& blk = st.dense[kind];
   const int vt = st.vt, ct = st.ct, B = st.size, naux = ctx->naux, npad = ctx->npad;
   const OwnedSlices o = owned_slices(ctx);
-  const long long ld = round_up(B, 2);
+  // even (16-byte rows for TMA), and never a multiple of 2 KiB: columns 2^k bytes apart would land on the same
+  // L2 slices / HBM channels (a B = 8192 block ran its product 30x slower, profiles/r02_bse_block_build_tiles.txt)
+  long long ld = round_up(B, 2);
+  if (ld % 256 == 0) ld += 2;
   const long long ncols = kind == 0 ? (long long)vt * o.ncloc : (long long)o.nvloc * ct;
   blk.ld = ld;
   blk.ncols = ncols;
