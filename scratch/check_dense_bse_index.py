@@ -152,3 +152,57 @@ if __name__ == "__main__":
                                                      (3, 33, 34, 1, 16, 16, 2, 5)]:
             run(world, naux, mt, nt, voff, vt, ct, k, lch, seed=world)
     print("dense BSE block index algebra: ok (worlds 1, 2, 3; Hd and Hd2; chunked builds)")
+
+
+def run_window_rotation(world, naux, mtotal, ntotal, n_lo, n_hi, seed=0):
+    """capi_mmn.cu rotate_rows / gwbse_mmn_mul_right_window_dev / mmn_complete_rotation: rows n in [n_lo, n_hi) of every
+    local slice through the second buffer and back in place, then the rest; (chi, ml) is one row index of pitch npad."""
+    rng = np.random.default_rng(seed)
+    Mfull = rng.standard_normal((mtotal, ntotal, naux))
+    R = rng.standard_normal((naux, naux))
+    ref = Mfull @ R
+    npad = round_up(ntotal, 16)
+    mlmax = (mtotal + world - 1) // world
+    ldx = mlmax * npad
+    ldp = round_up(naux, 2)
+    Rp = np.zeros(ldp * naux)
+    for j in range(naux):
+        Rp[j * ldp:j * ldp + naux] = R[:, j]          # column-major R at pitch ldp: R[k, j] at j * ldp + k
+    for rank in range(world):
+        X = np.zeros(ldx * naux)
+        for m in range(rank, mtotal, world):
+            for x in range(naux):
+                X[x * ldx + (m // world) * npad:x * ldx + (m // world) * npad + ntotal] = Mfull[m, :, x]
+        X2 = np.full(ldx * (naux + world), np.nan)
+
+        def rotate_rows(n0, n1):
+            nw = n1 - n0
+            if nw <= 0:
+                return
+            # C[(ml, n), j] = sum_k X[k * ldx + ml * npad + n0 + n] * Rp[j * ldp + k]
+            gemm(Op(X, off=n0, s_ri=1, s_ro=npad, s_ki=ldx, Lr=nw), Op(Rp, s_ri=ldp, s_ki=1), mlmax * nw, naux, naux,
+                 X2, n0, Lm=nw, sC_mi=1, sC_mo=npad, sC_ni=ldx)
+            # cudaMemcpy2D: width nw, height mlmax * naux, pitch npad on both sides
+            for r in range(mlmax * naux):
+                X[n0 + r * npad:n0 + r * npad + nw] = X2[n0 + r * npad:n0 + r * npad + nw]
+
+        lo = n_lo & ~1
+        rotate_rows(lo, n_hi)
+        # window rows carry the rotation, the others are untouched
+        for m in range(rank, mtotal, world):
+            got = np.array([X[x * ldx + (m // world) * npad:x * ldx + (m // world) * npad + ntotal] for x in range(naux)]).T
+            assert np.abs(got[lo:n_hi] - ref[m, lo:n_hi]).max() < 1e-12
+            assert np.array_equal(got[:lo], Mfull[m, :lo]) and np.array_equal(got[n_hi:], Mfull[m, n_hi:])
+        rotate_rows(0, lo)
+        rotate_rows(n_hi, ntotal)
+        for m in range(rank, mtotal, world):
+            got = np.array([X[x * ldx + (m // world) * npad:x * ldx + (m // world) * npad + ntotal] for x in range(naux)]).T
+            assert np.abs(got - ref[m]).max() < 1e-12
+    return True
+
+
+if __name__ == "__main__":
+    for world in (1, 2, 3):
+        for (naux, mt, nt, lo, hi) in [(5, 7, 19, 4, 11), (6, 8, 17, 3, 17), (4, 5, 16, 0, 9)]:
+            run_window_rotation(world, naux, mt, nt, lo, hi, seed=world)
+    print("windowed MultiplyRight index algebra: ok")

@@ -28,3 +28,12 @@ def _load():
 def test_block_build_and_product_index_algebra(world, case):
     naux, mtotal, ntotal, voff, vt, ct, k, lchunk = case
     assert _load().run(world, naux, mtotal, ntotal, voff, vt, ct, k, lchunk, seed=world)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+@pytest.mark.parametrize("case", [(5, 7, 19, 4, 11), (6, 8, 17, 3, 17), (4, 5, 16, 0, 9)])
+def test_windowed_multiply_right_index_algebra(world, case):
+    """gwbse_mmn_mul_right_window_dev / mmn_complete_rotation (capi_mmn.cu rotate_rows): the window rows first, in
+    place through the second buffer, then the rest; device-side: test_mul_right_on_a_row_window_then_the_rest."""
+    naux, mtotal, ntotal, n_lo, n_hi = case
+    assert _load().run_window_rotation(world, naux, mtotal, ntotal, n_lo, n_hi, seed=world)
