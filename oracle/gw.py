@@ -154,6 +154,29 @@ class GW:
     def rpa_input_energies(self):
         return self.rpa.get_rpa_input_energies()
 
+    # gw.cc:1132-1182 (states: IndexParser.cc:36-70); array positions counted from qpmin
+    def plot_sigma(self, steps, spacing, states):
+        """(levels kept, table of shape steps x 2 * len(levels): omega, E_QP(omega) per level)"""
+        o = self.opt
+        ids = set()
+        for tok in states.replace(",", " ").split():
+            if ":" in tok:
+                a, b = tok.split(":")
+                ids.update(range(int(a), int(b) + 1))
+            else:
+                ids.add(int(tok))
+        levels = [l for l in sorted(ids) if o.qpmin <= l <= o.qpmax]
+        e = self.rpa.get_rpa_input_energies()
+        table = np.zeros((steps, 2 * len(levels)))
+        for i, lvl in enumerate(levels):
+            rel = lvl - o.qpmin
+            icpt = self.dft_energies[lvl] + self.Sigma_x[rel, rel] - self.vxc[rel, rel]
+            for g in range(steps):
+                w = e[o.qpmin - o.rpamin + rel] + (g - (steps - 1) / 2.0) * spacing
+                table[g, 2 * i] = w
+                table[g, 2 * i + 1] = self.sigma.calc_correlation_diag_element(rel, w) + icpt
+        return levels, table
+
     def calc_homo_lumo_shift(self, freqs):
         o = self.opt
         dftgap = self.dft_energies[o.homo + 1] - self.dft_energies[o.homo]

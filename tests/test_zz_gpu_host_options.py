@@ -138,3 +138,24 @@ def test_switching_the_integral_producer_on_one_job(golden, methane):
     job.run()
     assert np.abs(job.get("QPpert_energies") - first).max() < 1e-12
     job.close()
+
+
+def test_sigma_plot(golden, methane, tmp_path):
+    """gw.sigma_plot (GW::PlotSigma, gw.cc:1132-1182): E_QP(omega) of the chosen states on a frequency grid, one
+    grouped evaluation on the device, written in the reference's table format; states outside the qp window are
+    dropped, ranges and duplicates are handled as IndexParser does."""
+    out = tmp_path / "sigma.dat"
+    job = _job(golden, methane, gw__sigma_plot__states="3:5 2,5 40", gw__sigma_plot__steps=21,
+               gw__sigma_plot__spacing=0.02, gw__sigma_plot__filename=str(out))
+    job.run()
+    _, g = _oracle_gw(golden)
+    levels, table = g.plot_sigma(21, 0.02, "3:5 2,5 40")
+    assert levels == [2, 3, 4, 5]
+    lines = out.read_text().splitlines()
+    assert lines[0] == "#omega_2\tE_QP(omega)_2#\tomega_3\tE_QP(omega)_3#\tomega_4\tE_QP(omega)_4#\tomega_5\tE_QP(omega)_5"
+    got = np.array([[float(x) for x in ln.split("\t")] for ln in lines[1:] if ln.strip()])
+    assert got.shape == table.shape
+    assert all(tok[0] in "+-" and len(tok.split(".")[1]) == 6 for tok in lines[1].split("\t"))  # "%+1.6f"
+    assert np.abs(got - table).max() < 2e-6
+    assert np.abs(g.get_gwa_results() - job.get("QPpert_energies")).max() < 1e-6
+    job.close()

@@ -4,7 +4,10 @@
 // resumable objects (qp_rootsearch.h) advanced in lock step, so every round of all searches is ONE grouped kernel
 // pass over the Mmn slices instead of one Eigen loop per level and frequency.
 #pragma once
+#include <algorithm>
+#include <cstdio>
 #include <cstring>
+#include <fstream>
 #include <limits>
 #include <memory>
 
@@ -107,6 +110,91 @@ class GW {
   Index iterations() const { return gw_sc_iteration_ + 1; }
   std::size_t sigma_batches() const { return sigma_batches_; }
   std::size_t sigma_evaluations() const { return sigma_evaluations_; }
+
+  // gw.cc:1132-1182: E_QP(omega) = e_DFT + Sigma_x - Vxc + Sigma_c(omega) on a grid of `steps` points `spacing`
+  // apart around the RPA input energy of every chosen state, written as the reference writes it (one column pair
+  // per state, "%+1.6f", tab separated).  All (state, omega) pairs go to the device in one grouped call.
+  // `states`: IndexParser syntax ("0 3 5:9"); states outside the qp window are skipped.  Array positions are
+  // counted from qpmin (the reference indexes them with the absolute level, which is the same thing for qpmin = 0).
+  void PlotSigma(const std::string& filename, Index steps, double spacing, const std::string& states) const {
+    std::vector<Index> state_inds;
+    for (Index gw_level : ParseIndexList(states))
+      if (gw_level >= opt_.qpmin && gw_level <= opt_.qpmax) state_inds.push_back(gw_level);
+    std::string listed;
+    for (Index l : state_inds) listed += (listed.empty() ? "" : " ") + std::to_string(l);
+    log_(" PQP(omega) written to '" + filename + "' for states " + listed);
+    const Index num_states = static_cast<Index>(state_inds.size());
+    const VectorXd& rpa_e = rpa_.getRPAInputEnergies();
+    std::vector<int> levels, gptr{0};
+    std::vector<double> freqs, sig;
+    for (Index i = 0; i < num_states; ++i) {
+      const Index rel = state_inds[i] - opt_.qpmin;
+      levels.push_back(static_cast<int>(rel));
+      for (Index g = 0; g < steps; ++g)
+        freqs.push_back(rpa_e(opt_.qpmin - opt_.rpamin + rel) + ((double)g - ((double)(steps - 1) / 2.0)) * spacing);
+      gptr.push_back(static_cast<int>(freqs.size()));
+    }
+    if (!freqs.empty()) {
+      sigma_->CountDiagEval(freqs.size());
+      sigma_->EvalGroups(levels, gptr, freqs, sig, nullptr);
+    }
+    std::ofstream out(filename);
+    if (!out) throw std::runtime_error("GW::PlotSigma: cannot open " + filename);
+    for (Index i = 0; i < num_states; ++i)
+      out << "#" << (i == 0 ? "" : "\t") << "omega_" << state_inds[i] << "\tE_QP(omega)_" << state_inds[i];
+    out << std::endl;
+    char buf[64];
+    for (Index g = 0; g < steps; ++g) {
+      for (Index i = 0; i < num_states; ++i) {
+        const Index rel = state_inds[i] - opt_.qpmin;
+        const size_t k = static_cast<size_t>(i * steps + g);
+        const double intercept = dft_energies_(opt_.qpmin + rel) + Sigma_x_(rel, rel) - vxc_(rel, rel);
+        std::snprintf(buf, sizeof(buf), "%s%+1.6f\t%+1.6f", i == 0 ? "" : "\t", freqs[k], sig[k] + intercept);
+        out << buf;
+      }
+      out << "\n";
+    }
+    out << std::endl;
+  }
+  // IndexParser::CreateIndexVector (IndexParser.cc:36-70): tokens separated by blanks / commas, "a:b" ranges,
+  // sorted, duplicates removed
+  static std::vector<Index> ParseIndexList(const std::string& ids) {
+    std::vector<Index> result;
+    std::string tok;
+    auto flush = [&]() {
+      if (tok.empty()) return;
+      try {
+        const size_t c = tok.find(':');
+        size_t used = 0;
+        if (c != std::string::npos) {
+          const std::string a = tok.substr(0, c), b = tok.substr(c + 1);
+          const long start = std::stol(a, &used);
+          if (used != a.size()) throw std::invalid_argument(a);
+          const long stop = std::stol(b, &used);
+          if (used != b.size()) throw std::invalid_argument(b);
+          for (long i = start; i <= stop; ++i) result.push_back(static_cast<Index>(i));
+        } else {
+          const long v = std::stol(tok, &used);
+          if (used != tok.size()) throw std::invalid_argument(tok);
+          result.push_back(static_cast<Index>(v));
+        }
+      } catch (const std::exception&) {
+        throw std::runtime_error("Could not convert " + tok +
+                                 (tok.find(':') != std::string::npos ? " to range of integers." : " to integer."));
+      }
+      tok.clear();
+    };
+    for (char ch : ids) {
+      if (ch == ' ' || ch == ',' || ch == '\n' || ch == '\t')
+        flush();
+      else
+        tok.push_back(ch);
+    }
+    flush();
+    std::sort(result.begin(), result.end());
+    result.erase(std::unique(result.begin(), result.end()), result.end());
+    return result;
+  }
 
   // gw.cc:74-78: eigen-decomposition of Hqp (device symmetric eigensolver)
   std::pair<VectorXd, MatrixXd> DiagonalizeQPHamiltonian() const {

@@ -36,7 +36,8 @@ class Options {
         {"gw.qsgw_sc_limit", "1e-5"}, {"gw.qsgw_max_virt_correction", "0.5"}, {"bse.exctotal", "10"}, {"bse.useTDA", "false"},
         {"bse.dyn_screen_max_iter", "0"}, {"bse.dyn_screen_tol", "1e-5"}, {"bse.davidson.correction", "DPR"},
         {"bse.davidson.tolerance", "normal"}, {"bse.davidson.update", "safe"}, {"bse.davidson.maxiter", "50"},
-        {"bse.use_Hqp_offdiag", "false"}, {"bse.print_weight", "0.5"}};
+        {"bse.use_Hqp_offdiag", "false"}, {"bse.print_weight", "0.5"}, {"gw.sigma_plot.steps", "201"},
+        {"gw.sigma_plot.spacing", "1e-2"}, {"gw.sigma_plot.filename", "QPenergies_sigma.dat"}};
     for (auto& d : defaults) kv_[d[0]] = d[1];
   }
   void set(const std::string& key, const std::string& value) {
@@ -69,8 +70,6 @@ class Options {
     for (const char* n : known) ok = ok || k == n;
     if (!ok) throw std::runtime_error("unknown option '" + k + "' (not a key of gwbse.xml)");
     if (value.empty()) return;
-    if (k == "gw.sigma_plot.states")
-      throw std::runtime_error("gw.sigma_plot is not implemented on this path (GW::PlotSigma, gw.cc:778-796)");
     if (k.rfind("bse.fragments", 0) == 0)
       throw std::runtime_error("bse.fragments needs the atom tables of the host package (not on this path)");
   }
@@ -339,6 +338,16 @@ class GWBSE {
       gwopt_.quadrature_scheme = options.str("gw.quadrature_scheme");
       gwopt_.alpha = options.dbl("gw.alpha");
     }
+    if (options.exists("gw.sigma_plot.states")) {  // gwbse.cc:562-577
+      sigma_plot_states_ = options.str("gw.sigma_plot.states");
+      sigma_plot_steps_ = options.idx("gw.sigma_plot.steps");
+      sigma_plot_spacing_ = options.dbl("gw.sigma_plot.spacing");
+      sigma_plot_filename_ = options.str("gw.sigma_plot.filename");
+      log_(" Sigma plot states: " + sigma_plot_states_);
+      log_(" Sigma plot steps: " + std::to_string(sigma_plot_steps_));
+      log_(" Sigma plot spacing: " + std::to_string(sigma_plot_spacing_));
+      log_(" Sigma plot filename: " + sigma_plot_filename_);
+    }
     gwopt_.qp_solver = options.str("gw.qp_solver");
     if (gwopt_.qp_solver == "grid") {
       if (options.exists("gw.qp_full_window_half_width"))
@@ -475,6 +484,8 @@ class GWBSE {
       GW gw(log_, Mmn, *in_.vxc, *in_.mo_energies);
       gw.configure(gwopt_);
       gw.CalculateGWPerturbation();
+      if (!sigma_plot_states_.empty())  // gwbse.cc:1009-1012
+        gw.PlotSigma(sigma_plot_filename_, sigma_plot_steps_, sigma_plot_spacing_, sigma_plot_states_);
       res.QPpert_energies = gw.getGWAResults();
       res.RPA_inputenergies = gw.RPAInputEnergies();
       if (gwopt_.do_qsgw) {
@@ -705,6 +716,9 @@ class GWBSE {
   Logger& log_;
   Inputs in_;
   GW::options gwopt_;
+  std::string sigma_plot_states_, sigma_plot_filename_;
+  Index sigma_plot_steps_ = 201;
+  double sigma_plot_spacing_ = 1e-2;
   BSE::options bseopt_;
   MatrixXd qsgw_mos_;  // MO coefficients with the QP-window columns rotated to the QSGW wavefunctions
   bool do_gw_ = false, do_bse_singlets_ = false, do_bse_triplets_ = false, do_dynamical_screening_bse_ = false;
