@@ -23,7 +23,8 @@ from oracle import basis as obasis  # noqa: E402
 from oracle import mmio  # noqa: E402
 
 REF = "/root/reference/xtp/src/tests/DataFiles"
-DIRS = ["threecenter_gwbse", "rpa", "sigma_exact", "sigma_cda", "sigma_ppm", "gw", "bse", "bse_operator"]
+DIRS = ["threecenter_gwbse", "rpa", "sigma_exact", "sigma_cda", "sigma_ppm", "gw", "bse", "bse_operator",
+        "populationanalysis"]
 
 
 def main():

@@ -12,7 +12,7 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 IT = "/root/reference/xtp/src/tests/DataFiles/xtp_tools_integration_tests"
 
-# options of gwbse.xml this path does not consume (it rejects them when they are set): fragment analysis
+# options of gwbse.xml without a default value to compare (fragment lists, the aux basis name)
 NOT_CONSUMED = ("bse.fragments", "auxbasisset")
 
 
@@ -110,7 +110,8 @@ def test_unknown_and_unsupported_keys_are_rejected(lib):
     o = lib.opt_new()
     assert lib.opt_set(o, b"gw.moed", b"G0W0") == 1  # misspelled
     assert lib.opt_set(o, b"bse.davidson.tolerence", b"strict") == 1
-    assert lib.opt_set(o, b"bse.fragments.fragment.indices", b"1:3") == 1
+    assert lib.opt_set(o, b"bse.fragments.fragment.indices", b"1:3;4 5") == 0  # GWBSE::FragmentPopulations
+    assert lib.opt_set(o, b"bse.fragments.fragment.name", b"donor") == 1
     assert lib.opt_set(o, b"gw.sigma_plot.states", b"1 3 5") == 0  # GW::PlotSigma (tests/test_zz_gpu_host_options.py)
     assert lib.opt_set(o, b"gw.sigma_plot.steps", b"201") == 0
     assert lib.opt_set(o, b"gw.qsgw_max_iterations", b"7") == 0 and get(lib, o, "gw.qsgw_max_iterations") == "7"

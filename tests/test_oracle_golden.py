@@ -339,3 +339,24 @@ def test_oracle_boys_function_against_multiprecision():
             ref = mpmath.hyp1f1(n + 0.5, n + 1.5, -mpmath.mpf(float(x))) / (2 * n + 1)
             worst = max(worst, float(abs((mpmath.mpf(float(F[n, i])) - ref) / ref)))
     assert worst < 1e-14, worst
+
+
+# test_populationanalysis.cc:38-74 (atompop) and :95-180 (fragment_pop)
+def test_lowdin_charges_and_fragment_populations_known_answers(golden):
+    from oracle import population as opop
+    from tests.helpers import methane_integrals
+    m = methane_integrals()
+    S = m["S"]
+    basis_atom = np.concatenate([[sh.atom] * (2 * sh.l + 1) for sh in m["basis"].shells])
+    nuc = np.array([6.0, 1.0, 1.0, 1.0, 1.0])
+    MOs = golden["populationanalysis/MOs"]
+    charges = nuc - opop.lowdin_per_atom(opop.ground_state_density(MOs, 5), S, basis_atom, 5)
+    ref = np.array([0.68862, -0.172155, -0.172154, -0.172154, -0.172155])
+    assert np.abs(charges - ref).max() < 1e-5 * np.abs(ref).max() * 5
+    MOs2, spsi = golden["populationanalysis/MOs2"], golden["populationanalysis/spsi_ref"]
+    Gs, H, E = opop.fragment_populations(S, MOs2, 4, 0, 16, basis_atom, nuc, [[0, 1], [2, 3, 4]], spsi)
+    assert abs(Gs[0] - 0.5164649) < 1e-5 and abs(Gs[1] + 0.5164628) < 1e-5
+    assert np.abs(E[0] - [-0.384176, -0.812396, -0.414518]).max() < 1e-5
+    assert np.abs(H[0] - [0.657215, 0.622434, 0.654751]).max() < 1e-5
+    assert np.abs(E[1] - [-0.615827, -0.187602, -0.58548]).max() < 1e-5
+    assert np.abs(H[1] - [0.342785, 0.377565, 0.34525]).max() < 1e-5

@@ -159,3 +159,41 @@ def test_sigma_plot(golden, methane, tmp_path):
     assert np.abs(got - table).max() < 2e-6
     assert np.abs(g.get_gwa_results() - job.get("QPpert_energies")).max() < 1e-6
     job.close()
+
+
+@pytest.mark.parametrize("tda", [True, False])
+def test_fragment_populations(golden, methane, tda, tmp_path):
+    """bse.fragments: Lowdin populations of every exciton on groups of atoms (Lowdin::CalcChargeperFragment,
+    populationanalysis.cc:47-84, with the densities of orbitals.cc:516-650) against oracle/population.py, which
+    reproduces the known answers of the reference's test_populationanalysis.cc; TDA and full BSE (antiresonant part
+    subtracted), singlets and triplets; fragments given as two <fragment> elements of an options file."""
+    from oracle import population as opop
+    from tests.helpers import methane_integrals
+    m = methane_integrals()
+    basis_atom = np.concatenate([[sh.atom] * (2 * sh.l + 1) for sh in m["basis"].shells]).astype(float)
+    nuc = np.array([6.0, 1.0, 1.0, 1.0, 1.0])
+    mos = golden["gw/mo_eigenvectors"]
+    S_dft = np.linalg.inv(mos @ mos.T)  # the MOs of the fixture are orthonormal in the metric they were computed with
+    xml = tmp_path / "opts.xml"
+    xml.write_text("<options><gwbse><bse><fragments><fragment><indices>0</indices></fragment>"
+                   "<fragment><indices>1:3 4</indices></fragment></fragments></bse></gwbse></options>")
+    job = _job(golden, methane, tasks="gw,singlets,triplets", bse__exctotal=4, bse__useTDA=tda,
+               bse__davidson__tolerance="lapack")
+    job.load_options_xml(str(xml))
+    job.set_array("ao_overlap", S_dft)
+    job.set_array("basis_atom_index", basis_atom)
+    job.set_array("nuclear_charges", nuc)
+    job.run()
+    for kind in ("singlet", "triplet"):
+        X = job.get(f"BSE_{kind}_eigenvectors")
+        Y = None if tda else job.get(f"BSE_{kind}_eigenvectors2")
+        Gs, H, E = opop.fragment_populations(S_dft, mos, 4, 0, 16, basis_atom.astype(int), nuc, [[0], [1, 2, 3, 4]], X, Y)
+        assert np.abs(job.get("fragment_gs").ravel() - Gs).max() < 1e-9
+        assert np.abs(job.get(f"BSE_{kind}_fragment_hole") - H).max() < 1e-9
+        assert np.abs(job.get(f"BSE_{kind}_fragment_electron") - E).max() < 1e-9
+        # the exciton is neutral and normalised: hole and electron populations sum to +1 / -1 (TDA)
+        if tda:
+            assert np.abs(H.sum(axis=0) - 1.0).max() < 1e-8 and np.abs(E.sum(axis=0) + 1.0).max() < 1e-8
+    assert abs(Gs.sum()) < 1e-8  # neutral molecule
+    assert "Fragment    1 -- hole:" in job.log()
+    job.close()

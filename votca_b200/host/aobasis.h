@@ -7,6 +7,9 @@
 #include <algorithm>
 #include <vector>
 
+#include <array>
+#include <cmath>
+
 #include "threecenter.h"
 
 namespace votca {
@@ -22,6 +25,24 @@ struct AOBasisData {
     Index n = 0;
     for (int x : l) n += 2 * x + 1;
     return n;
+  }
+  // AOBasis::getFuncPerAtom as a map: the atom (shells sharing a centre, in order of appearance) of every function
+  std::vector<Index> AtomOfFunction() const {
+    std::vector<Index> out;
+    std::vector<std::array<double, 3>> atoms;
+    for (size_t sh = 0; sh < l.size(); ++sh) {
+      const std::array<double, 3> c = {centers[3 * sh], centers[3 * sh + 1], centers[3 * sh + 2]};
+      Index a = -1;
+      for (size_t k = 0; k < atoms.size(); ++k)
+        if (std::abs(atoms[k][0] - c[0]) + std::abs(atoms[k][1] - c[1]) + std::abs(atoms[k][2] - c[2]) < 1e-10)
+          a = static_cast<Index>(k);
+      if (a < 0) {
+        atoms.push_back(c);
+        a = static_cast<Index>(atoms.size()) - 1;
+      }
+      for (int m = 0; m < 2 * l[sh] + 1; ++m) out.push_back(a);
+    }
+    return out;
   }
   // raw contraction factors as they stand in a basis-set XML (basisset.cc:150-199) -> coefs
   void NormalizeFromRawContractions(const std::vector<double>& contractions) {
@@ -54,6 +75,13 @@ class DeviceAOBasis {
     std::vector<MatrixXd> out;
     for (int k = 0; k < 3; ++k) out.emplace_back(buf.data() + static_cast<size_t>(k) * n * n, n, n, n);
     return out;
+  }
+  // AOOverlap::Fill: <mu | nu>
+  MatrixXd Overlap() const {
+    const Index n = AOBasisSize();
+    MatrixXd S(n, n);
+    dev_.check(gwbse_ao_overlap(dev_.ctx(), h_, S.data(), (int)n));
+    return S;
   }
   Index AOBasisSize() const { return gwbse_basis_size(h_); }
 

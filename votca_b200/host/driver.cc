@@ -288,6 +288,29 @@ int gwbse_job_run(gwbse_job* job) {
     dip = {job->in["dipole_x"], job->in["dipole_y"], job->in["dipole_z"]};
     in.interlevel_dipoles = &dip;
   }
+  // bse.fragments: overlap / atom map from the arrays given, else from the dft basis
+  MatrixXd ao_overlap;
+  std::vector<Index> basis_atom;
+  VectorXd nuclear_charges;
+  if (job->in.count("nuclear_charges")) {
+    nuclear_charges = mat2vec(job->in["nuclear_charges"]);
+    in.nuclear_charges = &nuclear_charges;
+    if (job->in.count("ao_overlap")) {
+      in.ao_overlap = &job->in["ao_overlap"];
+    } else if (job->basis_data[0]) {
+      if (!job->dev_basis[0]) job->dev_basis[0] = std::make_unique<DeviceAOBasis>(*job->dev, *job->basis_data[0]);
+      ao_overlap = job->dev_basis[0]->Overlap();
+      in.ao_overlap = &ao_overlap;
+    }
+    if (job->in.count("basis_atom_index")) {
+      const VectorXd v = mat2vec(job->in["basis_atom_index"]);
+      for (Index i = 0; i < v.size(); ++i) basis_atom.push_back(static_cast<Index>(std::llround(v(i))));
+      in.basis_atom = &basis_atom;
+    } else if (job->basis_data[0]) {
+      basis_atom = job->basis_data[0]->AtomOfFunction();
+      in.basis_atom = &basis_atom;
+    }
+  }
   VectorXd rpa_in;
   if (job->in.count("Hqp") && job->in.count("RPA_inputenergies")) {
     in.Hqp = &job->in["Hqp"];
@@ -328,6 +351,11 @@ int gwbse_job_run(gwbse_job* job) {
   o["singlet_exchange_contrib"] = vec2mat(r.singlet_analysis.exchange_contrib);
   o["triplet_qp_contrib"] = vec2mat(r.triplet_analysis.qp_contrib);
   o["triplet_direct_contrib"] = vec2mat(r.triplet_analysis.direct_contrib);
+  o["fragment_gs"] = vec2mat(r.fragment_gs);
+  o["BSE_singlet_fragment_hole"] = r.singlet_fragment_hole;
+  o["BSE_singlet_fragment_electron"] = r.singlet_fragment_electron;
+  o["BSE_triplet_fragment_hole"] = r.triplet_fragment_hole;
+  o["BSE_triplet_fragment_electron"] = r.triplet_fragment_electron;
   auto& s = job->out_scalars;
   s["rpamin"] = r.rpamin;
   s["rpamax"] = r.rpamax;

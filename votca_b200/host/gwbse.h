@@ -70,8 +70,8 @@ class Options {
     for (const char* n : known) ok = ok || k == n;
     if (!ok) throw std::runtime_error("unknown option '" + k + "' (not a key of gwbse.xml)");
     if (value.empty()) return;
-    if (k.rfind("bse.fragments", 0) == 0)
-      throw std::runtime_error("bse.fragments needs the atom tables of the host package (not on this path)");
+    if (k.rfind("bse.fragments", 0) == 0 && k != "bse.fragments.fragment.indices")
+      throw std::runtime_error("unknown option '" + k + "' (bse.fragments holds fragment.indices elements)");
   }
   bool exists(const std::string& key) const {
     auto it = kv_.find(key);
@@ -128,7 +128,11 @@ class Options {
             }
             if (in_gwbse && !key.empty()) {
               check_key(key, t);
-              kv_[key] = t;
+              // one <fragment><indices> element per fragment (gwbse.cc:392-400): kept in order, ';' separated
+              if (key == "bse.fragments.fragment.indices" && kv_.count(key) && !kv_[key].empty())
+                kv_[key] += ";" + t;
+              else
+                kv_[key] = t;
             }
           }
           text.clear();
@@ -162,6 +166,11 @@ class GWBSE {
     // optional alternative: AO dipole matrices <mu|r_k|nu> (AODipole::Fill, e.g. DeviceAOBasis::Dipoles()); the
     // interlevel dipoles are then formed here as Orbitals::CalcFreeTransition_Dipoles does (orbitals.cc:742-760)
     const std::vector<MatrixXd>* ao_dipoles = nullptr;
+    // bse.fragments (Lowdin populations of the excitons on groups of atoms, populationanalysis.cc:47-84): the AO
+    // overlap of the dft basis, the atom every basis function sits on, the nuclear charges (QMAtom::getNuccharge)
+    const MatrixXd* ao_overlap = nullptr;
+    const std::vector<Index>* basis_atom = nullptr;
+    const VectorXd* nuclear_charges = nullptr;
     // BSE-only runs (do_gw == false): orbitals_.QPdiag / RPAInputEnergies from a previous run
     const MatrixXd* Hqp = nullptr;
     const VectorXd* rpa_input_energies = nullptr;
@@ -192,6 +201,9 @@ class GWBSE {
     std::vector<VectorXd> transition_dipoles;
     VectorXd oscillator_strengths;
     BSE::Interaction singlet_analysis, triplet_analysis;
+    // QMFragment<BSE_Population> per fragment (qmfragment.h, bse.cc:362-376): Gs, and H / E per state (nfrag x nstates)
+    VectorXd fragment_gs;
+    MatrixXd singlet_fragment_hole, singlet_fragment_electron, triplet_fragment_hole, triplet_fragment_electron;
     Index removed_functions = 0, gw_iterations = 0, qsgw_iterations = 0;
     bool is_qsgw = false;
     Index singlet_davidson_iterations = 0, triplet_davidson_iterations = 0;
@@ -347,6 +359,15 @@ class GWBSE {
       log_(" Sigma plot steps: " + std::to_string(sigma_plot_steps_));
       log_(" Sigma plot spacing: " + std::to_string(sigma_plot_spacing_));
       log_(" Sigma plot filename: " + sigma_plot_filename_);
+    }
+    fragments_.clear();
+    if (options.exists("bse.fragments.fragment.indices")) {  // gwbse.cc:392-400, :878-885
+      std::stringstream list(options.str("bse.fragments.fragment.indices"));
+      std::string item;
+      while (std::getline(list, item, ';')) {
+        fragments_.push_back(GW::ParseIndexList(item));
+        log_(" Fragment " + std::to_string(fragments_.size() - 1) + " size:" + std::to_string(fragments_.back().size()));
+      }
     }
     gwopt_.qp_solver = options.str("gw.qp_solver");
     if (gwopt_.qp_solver == "grid") {
@@ -539,6 +560,9 @@ class GWBSE {
         res.BSE_triplet = bse.Solve_triplets();
         res.triplet_davidson_iterations = bse.last_davidson_iterations();
         res.triplet_analysis = bse.Analyze_eh_interaction(false, res.BSE_triplet);
+        if (!fragments_.empty())
+          FragmentPopulations("triplet", res.BSE_triplet, res.fragment_gs, res.triplet_fragment_hole,
+                              res.triplet_fragment_electron);
       }
       if (do_bse_singlets_) {
         res.BSE_singlet = bse.Solve_singlets();
@@ -554,6 +578,9 @@ class GWBSE {
           res.oscillator_strengths = BSE::Oscillatorstrengths(res.transition_dipoles, res.BSE_singlet.eigenvalues);
         }
         res.singlet_analysis = bse.Analyze_eh_interaction(true, res.BSE_singlet);
+        if (!fragments_.empty())
+          FragmentPopulations("singlet", res.BSE_singlet, res.fragment_gs, res.singlet_fragment_hole,
+                              res.singlet_fragment_electron);
       }
       if (do_dynamical_screening_bse_) {
         if (do_bse_triplets_) res.BSE_triplet_dynamic = bse.Perturbative_DynamicalScreening(res.BSE_triplet, rpa_e);
@@ -566,6 +593,105 @@ class GWBSE {
     }
     log_(" GWBSE calculation finished ");
     return res;
+  }
+
+  // Lowdin::CalcChargeperFragment (populationanalysis.cc:47-84) for the excitons of one spin type, with
+  // Orbitals::DensityMatrixGroundState / DensityMatrixExcitedState (orbitals.cc:193-223, 516-650) folded in: with
+  // T = S^1/2 C, the electrons an AO density C_a K C_b^T puts on basis function mu are sum_kl T[mu,k] K[k,l] T[mu,l],
+  // and K = A A^T (CalcAuxMat_vv) or A^T A (CalcAuxMat_cc) makes that a row-wise sum of squares of T_v A or T_c A^T.
+  // S^1/2 C (eigensolver + two GEMMs) and the per-state products run on the device; the N x N densities are never
+  // formed.  Logs the reference's per-fragment line (BSE::printFragInfo, bse.cc:362-376).
+  void FragmentPopulations(const std::string& label, const EigenSystem& es, VectorXd& gs, MatrixXd& H, MatrixXd& E) {
+    if (!in_.ao_overlap || !in_.basis_atom || !in_.nuclear_charges)
+      throw std::runtime_error(
+          "bse.fragments needs the AO overlap of the dft basis (or the basis itself), the atom of every basis "
+          "function and the nuclear charges");
+    const MatrixXd& C = *in_.mos;
+    const MatrixXd& S = *in_.ao_overlap;
+    const Index N = C.rows(), homo = bseopt_.homo, vmin = bseopt_.vmin, cmax = bseopt_.cmax;
+    const Index vt = homo - vmin + 1, ct = cmax - homo, ncol = cmax + 1, nat = in_.nuclear_charges->size();
+    if (S.rows() != N || S.cols() != N || static_cast<Index>(in_.basis_atom->size()) != N)
+      throw std::runtime_error("bse.fragments: AO overlap / atom map do not match the dft basis");
+    for (Index a : *in_.basis_atom)
+      if (a < 0 || a >= nat) throw std::runtime_error("bse.fragments: atom index of a basis function out of range");
+    for (const auto& f : fragments_)
+      for (Index a : f)
+        if (a < 0 || a >= nat) throw std::runtime_error("bse.fragments: atom index " + std::to_string(a) + " out of range");
+    // T = S^1/2 C = U sqrt(w) U^T C for the levels 0 .. cmax
+    Device::Buffer U = dev_.upload(S), Cd = dev_.upload(C), T1 = dev_.alloc(static_cast<size_t>(N * ncol)),
+                   Td = dev_.alloc(static_cast<size_t>(N * ncol));
+    VectorXd w(N);
+    dev_.check(gwbse_sym_eig_dev(dev_.ctx(), (int)N, U.get(), (int)N, w.data()));
+    VectorXd sq(N);
+    for (Index i = 0; i < N; ++i) {
+      if (w(i) <= 0.0) throw std::runtime_error("bse.fragments: AO overlap is not positive definite");
+      sq(i) = std::sqrt(w(i));
+    }
+    Device::Buffer dsq = dev_.upload(sq);
+    dev_.gemm('T', 'N', N, ncol, N, 1.0, U.get(), N, Cd.get(), N, 0.0, T1.get(), N);
+    dev_.check(gwbse_diag_scale_dev(dev_.ctx(), 'L', (int)N, (int)ncol, T1.get(), (int)N, dsq.get(), T1.get(), (int)N));
+    dev_.gemm('N', 'N', N, ncol, N, 1.0, U.get(), N, T1.get(), N, 0.0, Td.get(), N);
+    auto per_atom = [&](const MatrixXd& G) {  // electrons per atom: rows of G squared, summed over the atom's functions
+      VectorXd out(nat, 0.0);
+      for (Index j = 0; j < G.cols(); ++j)
+        for (Index mu = 0; mu < N; ++mu) out((*in_.basis_atom)[static_cast<size_t>(mu)]) += G(mu, j) * G(mu, j);
+      return out;
+    };
+    auto per_fragment = [&](const VectorXd& atoms, Index f) {
+      double q = 0.0;
+      for (Index a : fragments_[static_cast<size_t>(f)]) q += atoms(a);
+      return q;
+    };
+    const Index nfrag = static_cast<Index>(fragments_.size());
+    {  // ground state, closed shell: 2 sum_occ T[mu,i]^2
+      const MatrixXd Tocc = dev_.download(Td.get(), N, homo + 1);
+      VectorXd atoms = per_atom(Tocc);
+      gs = VectorXd(nfrag);
+      VectorXd q(nat);
+      for (Index a = 0; a < nat; ++a) q(a) = (*in_.nuclear_charges)(a) - 2.0 * atoms(a);
+      for (Index f = 0; f < nfrag; ++f) gs(f) = per_fragment(q, f);
+    }
+    const Index nstates = es.eigenvalues.size();
+    H = MatrixXd(nfrag, nstates);
+    E = MatrixXd(nfrag, nstates);
+    const bool tda = es.eigenvectors2.size() == 0;
+    Device::Buffer Ad = dev_.alloc(static_cast<size_t>(vt * ct)), Gv = dev_.alloc(static_cast<size_t>(N * ct)),
+                   Gc = dev_.alloc(static_cast<size_t>(N * vt));
+    const double* Tv = Td.get() + vmin * N;
+    const double* Tc = Td.get() + (homo + 1) * N;
+    // coefficient vector as the ct x vt matrix A(c, v) (orbitals.cc:578-590):
+    // vv[mu] = sum_c (sum_v T_v[mu,v] A(c,v))^2, cc[mu] = sum_v (sum_c T_c[mu,c] A(c,v))^2
+    auto densities = [&](const MatrixXd& coeffs, Index state, VectorXd& vv, VectorXd& cc) {
+      dev_.check(gwbse_h2d(dev_.ctx(), Ad.get(), coeffs.data() + state * coeffs.rows(), static_cast<size_t>(vt * ct)));
+      dev_.gemm('N', 'T', N, ct, vt, 1.0, Tv, N, Ad.get(), ct, 0.0, Gv.get(), N);
+      dev_.gemm('N', 'N', N, vt, ct, 1.0, Tc, N, Ad.get(), ct, 0.0, Gc.get(), N);
+      vv = per_atom(dev_.download(Gv.get(), N, ct));
+      cc = per_atom(dev_.download(Gc.get(), N, vt));
+    };
+    for (Index s = 0; s < nstates; ++s) {
+      VectorXd xvv, xcc;
+      densities(es.eigenvectors, s, xvv, xcc);
+      VectorXd atom_h = xvv, atom_e(nat);
+      for (Index a = 0; a < nat; ++a) atom_e(a) = -xcc(a);
+      if (!tda) {  // antiresonant part (orbitals.cc:523-530): hole -= C_c Y_cc C_c^T, electron -= C_v Y_vv C_v^T
+        VectorXd yvv, ycc;
+        densities(es.eigenvectors2, s, yvv, ycc);
+        for (Index a = 0; a < nat; ++a) {
+          atom_h(a) -= ycc(a);
+          atom_e(a) += yvv(a);
+        }
+      }
+      for (Index f = 0; f < nfrag; ++f) {
+        H(f, s) = per_fragment(atom_h, f);
+        E(f, s) = per_fragment(atom_e, f);
+        const double dq = H(f, s) + E(f, s), qeff = dq + gs(f);
+        char buf[200];
+        std::snprintf(buf, sizeof(buf),
+                      "           %s %ld Fragment %4d -- hole: %5.1f%%  electron: %5.1f%%  dQ: %+5.2f  Qeff: %+5.2f",
+                      label.c_str(), (long)(s + 1), (int)f, 100.0 * H(f, s), -100.0 * E(f, s), dq, qeff);
+        log_(buf);
+      }
+    }
   }
 
   // Orbitals::CalcFreeTransition_Dipoles (orbitals.cc:742-760): interlevel[k] = empty^T * D_k * occ with
@@ -716,6 +842,7 @@ class GWBSE {
   Logger& log_;
   Inputs in_;
   GW::options gwopt_;
+  std::vector<std::vector<Index>> fragments_;  // atom indices per fragment (bse.fragments.fragment.indices)
   std::string sigma_plot_states_, sigma_plot_filename_;
   Index sigma_plot_steps_ = 201;
   double sigma_plot_spacing_ = 1e-2;
