@@ -17,6 +17,7 @@ dft_results.npz (the members of the parsed Orbitals object GWBSE reads):
                                                     two-centre Coulomb, overlap, dipoles) are produced on the device
     or ao3c (Naux x N x N) + aux_overlap + aux_coulomb [+ dipole_x/y/z interlevel dipoles]   host-computed integrals
     unrestricted references add mos_beta, mo_energies_beta, homo_beta, vxc_beta (tasks gw / exciton_uks).
+    bse.fragments needs the nuclear charges: taken from `elements`, or nuclear_charges + basis_atom_index + ao_overlap.
 """
 import argparse
 import re
@@ -69,6 +70,15 @@ def main(argv=None):
         job.set_basis("aux", *realsys.shell_arrays(str(d["auxbasis"]), el, d["positions_bohr"]))
     else:
         raise SystemExit("the DFT results hold neither AO integrals (ao3c) nor basis-set names (basis, auxbasis)")
+    # bse.fragments (Lowdin populations of the excitons on atom groups): nuclear charges from the elements, or the
+    # arrays nuclear_charges / basis_atom_index / ao_overlap of the DFT results when the integrals come as arrays
+    if "elements" in d.files and "nuclear_charges" not in d.files:
+        z = {"H": 1, "He": 2, "Li": 3, "Be": 4, "B": 5, "C": 6, "N": 7, "O": 8, "F": 9, "Ne": 10, "Na": 11, "Mg": 12,
+             "Al": 13, "Si": 14, "P": 15, "S": 16, "Cl": 17, "Ar": 18}
+        job.set_array("nuclear_charges", np.array([float(z[str(e)]) for e in d["elements"]]))
+    for name in ("nuclear_charges", "basis_atom_index", "ao_overlap"):
+        if name in d.files:
+            job.set_array(name, np.asarray(d[name], dtype=np.float64))
     archive, summary = job_name + ".orb", job_name + "_summary.xml"
     if unrestricted:
         job.run_uks()
