@@ -68,6 +68,35 @@ int gwbse_initialize_ranges(void* options, long homo, long nlevels, long* ranges
   }
 }
 
+// the same with the nuclear charges of the atoms given (ignore_corelevels, gwbse.cc:46-58, 128-152)
+int gwbse_initialize_ranges_z(void* options, long homo, long nlevels, const double* z, long nz, long* ranges, char* err,
+                              int cap) {
+  try {
+    alignas(Device) static unsigned char no_device[sizeof(Device)];
+    const Device& dev = *reinterpret_cast<const Device*>(no_device);
+    Logger log;
+    GWBSE g(dev, log);
+    MatrixXd mos(nlevels, nlevels);
+    VectorXd e(nlevels), zz(nz);
+    for (long i = 0; i < nz; ++i) zz(i) = z[i];
+    GWBSE::Inputs in;
+    in.homo = homo;
+    in.mos = &mos;
+    in.mo_energies = &e;
+    if (nz > 0) in.nuclear_charges = &zz;
+    g.Initialize(*static_cast<Options*>(options), in);
+    const GW::options& gw = g.gw_options();
+    const BSE::options& bse = g.bse_options();
+    const long r[6] = {gw.rpamin, gw.rpamax, gw.qpmin, gw.qpmax, bse.vmin, bse.cmax};
+    for (int i = 0; i < 6; ++i) ranges[i] = r[i];
+    return 0;
+  } catch (const std::exception& e) {
+    std::strncpy(err, e.what(), cap - 1);
+    err[cap - 1] = 0;
+    return 1;
+  }
+}
+
 // GWBSE::WriteToCpt on made-up results of the given sizes (values i + 0.5): checks names / types / shapes of the file
 int gwbse_write_results(const char* path, long nlevels, long homo, long q, long bse_size, long nstates, int tda) {
   try {

@@ -35,6 +35,7 @@ def lib():
     lib.bse_ranked_guess.restype = L
     lib.gwbse_write_results.argtypes = [s, L, L, L, L, L, ctypes.c_int]
     lib.gwbse_initialize_ranges.argtypes = [p, L, L, p, p, ctypes.c_char_p, ctypes.c_int]
+    lib.gwbse_initialize_ranges_z.argtypes = [p, L, L, p, L, p, ctypes.c_char_p, ctypes.c_int]
     return lib
 
 
@@ -238,3 +239,32 @@ def test_results_checkpoint_uses_the_names_and_types_of_the_reference(lib, tmp_p
         assert {k.split("/")[0] for k in rsets - set(ref_sets) if not k.startswith("transition_dipoles/")} <= \
             {"qmmolecule", "dft", "aux", "forces"}
         assert r.read("/QMdata/BSE_singlet/eigenvectors").shape[0] == r.read("/QMdata/BSE_singlet/eigenvectors2").shape[0]
+
+
+def test_ignore_corelevels(lib):
+    """gwbse.cc:46-58, 128-152: half the core electrons of corelevels.xml (C, N, O, F 2; Al, S 10; H 0) are cut from
+    the RPA / GW / BSE windows; thiophene C4H4S has 4 + 5 = 9 core levels."""
+    import numpy as np
+    z = np.array([16.0] + [6.0] * 4 + [1.0] * 4)
+    expect = {"none": (0, 0, 0), "BSE": (0, 0, 9), "GW": (0, 9, 9), "RPA": (9, 9, 9)}
+    for mode, (rpamin, qpmin, vmin) in expect.items():
+        o = lib.opt_new()
+        assert lib.opt_set(o, b"ignore_corelevels", mode.encode()) == 0
+        r = (ctypes.c_long * 6)()
+        err = ctypes.create_string_buffer(512)
+        rc = lib.gwbse_initialize_ranges_z(o, 21, 120, z.ctypes.data_as(ctypes.c_void_p), len(z), r, err, 512)
+        assert rc == 0, err.value
+        assert (r[0], r[2], r[4]) == (rpamin, qpmin, vmin), (mode, list(r))
+        assert (r[1], r[3], r[5]) == (119, 3 * 21 + 1, 3 * 21 + 1)
+        lib.opt_free(o)
+    o = lib.opt_new()
+    lib.opt_set(o, b"ignore_corelevels", b"GW")
+    r = (ctypes.c_long * 6)()
+    err = ctypes.create_string_buffer(512)
+    assert lib.gwbse_initialize_ranges_z(o, 21, 120, None, 0, r, err, 512) == 1 and b"nuclear charges" in err.value
+    zz = np.array([26.0])
+    assert lib.gwbse_initialize_ranges_z(o, 21, 120, zz.ctypes.data_as(ctypes.c_void_p), 1, r, err, 512) == 1
+    assert b"corelevels table" in err.value
+    lib.opt_set(o, b"ignore_corelevels", b"sometimes")
+    assert lib.gwbse_initialize_ranges_z(o, 21, 120, None, 0, r, err, 512) == 1
+    lib.opt_free(o)

@@ -197,3 +197,23 @@ def test_fragment_populations(golden, methane, tda, tmp_path):
     assert abs(Gs.sum()) < 1e-8  # neutral molecule
     assert "Fragment    1 -- hole:" in job.log()
     job.close()
+
+
+def test_ignore_corelevels_gw(golden, methane):
+    """ignore_corelevels = GW: the carbon 1s level leaves the QP and BSE windows (one core level for CH4) - the same
+    run as explicit ranges with qpmin = bsemin = 1."""
+    res = {}
+    for tag, kw in (("core", dict(ranges="full", ignore_corelevels="GW")),
+                    ("explicit", dict(ranges="explicit", rpamax=16, qpmin=1, qpmax=16, bsemin=1, bsemax=16))):
+        job = _job(golden, methane, tasks="gw,singlets", bse__exctotal=3, bse__useTDA=True)
+        job.set_options(**kw)
+        job.set_array("nuclear_charges", np.array([6.0, 1.0, 1.0, 1.0, 1.0]))
+        job.run()
+        res[tag] = (job.get("QPpert_energies").copy(), job.get("BSE_singlet_eigenvalues").copy(),
+                    job.scalar("qpmin"), job.scalar("bse_vmin"), job.scalar("rpamin"))
+        if tag == "core":
+            assert "Ignoring 1 core levels for GW and beyond." in job.log()
+        job.close()
+    assert res["core"][2:] == (1.0, 1.0, 0.0) == res["explicit"][2:]
+    assert np.abs(res["core"][0] - res["explicit"][0]).max() < 1e-12
+    assert np.abs(res["core"][1] - res["explicit"][1]).max() < 1e-10

@@ -252,8 +252,21 @@ class GWBSE {
     } else {
       throw std::runtime_error("unknown ranges option '" + ranges + "'");
     }
-    if (options.str("ignore_corelevels") != "none")
-      throw std::runtime_error("ignore_corelevels needs the ECP/element tables of the host package (not on this path)");
+    // gwbse.cc:128-152 with GWBSE::CountCoreLevels (:46-58): core electrons per element as share/xtp/ecps/corelevels.xml
+    // lists them, elements identified by their nuclear charge
+    const std::string ignore_corelevels = options.str("ignore_corelevels");
+    if (ignore_corelevels == "RPA" || ignore_corelevels == "GW" || ignore_corelevels == "BSE") {
+      if (!in.nuclear_charges)
+        throw std::runtime_error("ignore_corelevels needs the nuclear charges of the atoms (input 'nuclear_charges')");
+      const Index ignored_corelevels = CountCoreLevels(*in.nuclear_charges);
+      if (ignore_corelevels == "RPA") rpamin = ignored_corelevels;
+      if (ignore_corelevels == "GW" || ignore_corelevels == "RPA")
+        if (qpmin < ignored_corelevels) qpmin = ignored_corelevels;
+      if (bse_vmin < ignored_corelevels) bse_vmin = ignored_corelevels;
+      log_(" Ignoring " + std::to_string(ignored_corelevels) + " core levels for " + ignore_corelevels + " and beyond.");
+    } else if (ignore_corelevels != "none") {
+      throw std::runtime_error("ignore_corelevels is none, RPA, GW or BSE");
+    }
     if (rpamax >= num_of_levels) rpamax = num_of_levels - 1;
     if (qpmax >= num_of_levels) qpmax = num_of_levels - 1;
     if (bse_cmax >= num_of_levels) bse_cmax = num_of_levels - 1;
@@ -593,6 +606,25 @@ class GWBSE {
     }
     log_(" GWBSE calculation finished ");
     return res;
+  }
+
+  // GWBSE::CountCoreLevels (gwbse.cc:46-58): half the core electrons of share/xtp/ecps/corelevels.xml
+  static Index CountCoreLevels(const VectorXd& nuclear_charges) {
+    Index core_electrons = 0;
+    for (Index a = 0; a < nuclear_charges.size(); ++a) {
+      const long z = std::lround(nuclear_charges(a));
+      switch (z) {
+        case 1: break;                                  // H
+        case 6: case 7: case 8: case 9: core_electrons += 2; break;   // C N O F
+        case 13: case 16: core_electrons += 10; break;  // Al S
+        case 47: core_electrons += 28; break;           // Ag
+        case 80: core_electrons += 60; break;           // Hg
+        default:
+          throw std::runtime_error("ignore_corelevels: element with nuclear charge " + std::to_string(z) +
+                                   " is not in the corelevels table");
+      }
+    }
+    return core_electrons / 2;
   }
 
   // Lowdin::CalcChargeperFragment (populationanalysis.cc:47-84) for the excitons of one spin type, with
