@@ -125,19 +125,33 @@ class GW {
     log_(" PQP(omega) written to '" + filename + "' for states " + listed);
     const Index num_states = static_cast<Index>(state_inds.size());
     const VectorXd& rpa_e = rpa_.getRPAInputEnergies();
+    // every rank evaluates the levels whose Mmn slice it owns (all of them on one GPU), the tables are summed
     std::vector<int> levels, gptr{0};
-    std::vector<double> freqs, sig;
+    std::vector<double> freqs, mine_f, mine_s;
+    std::vector<size_t> first;  // position of a level's first grid point in the full table, for the owned levels
     for (Index i = 0; i < num_states; ++i) {
       const Index rel = state_inds[i] - opt_.qpmin;
-      levels.push_back(static_cast<int>(rel));
-      for (Index g = 0; g < steps; ++g)
-        freqs.push_back(rpa_e(opt_.qpmin - opt_.rpamin + rel) + ((double)g - ((double)(steps - 1) / 2.0)) * spacing);
-      gptr.push_back(static_cast<int>(freqs.size()));
+      const bool own = sigma_->OwnsLevel(rel);
+      if (own) {
+        levels.push_back(static_cast<int>(rel));
+        first.push_back(freqs.size());
+      }
+      for (Index g = 0; g < steps; ++g) {
+        const double w = rpa_e(opt_.qpmin - opt_.rpamin + rel) + ((double)g - ((double)(steps - 1) / 2.0)) * spacing;
+        freqs.push_back(w);
+        if (own) mine_f.push_back(w);
+      }
+      if (own) gptr.push_back(static_cast<int>(mine_f.size()));
     }
-    if (!freqs.empty()) {
-      sigma_->CountDiagEval(freqs.size());
-      sigma_->EvalGroups(levels, gptr, freqs, sig, nullptr);
+    std::vector<double> sig(freqs.size(), 0.0);
+    if (!mine_f.empty()) {
+      sigma_->CountDiagEval(mine_f.size());
+      sigma_->EvalGroups(levels, gptr, mine_f, mine_s, nullptr);
+      for (size_t l = 0; l < levels.size(); ++l)
+        for (Index g = 0; g < steps; ++g) sig[first[l] + static_cast<size_t>(g)] = mine_s[static_cast<size_t>(gptr[l]) + g];
     }
+    if (Mmn_.device().world() > 1 && !sig.empty()) Mmn_.device().allreduce(sig.data(), sig.size());
+    if (Mmn_.device().rank() != 0) return;  // one writer
     std::ofstream out(filename);
     if (!out) throw std::runtime_error("GW::PlotSigma: cannot open " + filename);
     for (Index i = 0; i < num_states; ++i)
