@@ -500,6 +500,57 @@ class BSEUKS:
             self.Hqp.append(Hs if opt.use_Hqp_offdiag else np.diag(np.diag(Hs)))
             self.M[s].multiply_right(U)
 
+    # bse_uks.cc:135-157.  The reference rotates a pristine copy of the tensors by the eigenvectors of epsilon(energy);
+    # here the tensors are rotated in place again: epsilon computed from rotated tensors has the rotated eigenvectors,
+    # so the product of the rotations is the same and the operator, which is all that is used, is identical.
+    def setup_direct_interaction_operator(self, rpa_e_alpha, rpa_e_beta, energy):
+        rpa = RPAUKS(*self.M)
+        rpa.configure(self.homo[0], self.homo[1], self.opt.rpamin, self.opt.rpamax)
+        rpa.set_rpa_input_energies(rpa_e_alpha, rpa_e_beta)
+        ev, U = np.linalg.eigh(rpa.calculate_epsilon_r(energy))
+        self.eps_inv = np.where(ev > 1e-8, 1.0 / np.where(ev > 1e-8, ev, 1.0), 0.0)
+        for s in range(2):
+            self.M[s].multiply_right(U)
+
+    def _operator(self, cqp, cx, cd, cd2):
+        op = BSEOperatorUKS(cqp, cx, cd, cd2, self.eps_inv, self.M[0], self.M[1], self.Hqp[0], self.Hqp[1])
+        op.configure(self.homo[0], self.homo[1], self.opt.rpamin, self.opt.vmin, self.opt.cmax)
+        return op
+
+    # bse_uks.cc:171-216
+    @staticmethod
+    def _expectation(es, op, tda, state=None):
+        X = es["eigenvectors"] if state is None else es["eigenvectors"][:, [state]]
+        HX = op.matmul(X)
+        direct = np.sum(X * HX, axis=0)
+        cross = None
+        if not tda:
+            Y = es["eigenvectors2"] if state is None else es["eigenvectors2"][:, [state]]
+            direct = direct + np.sum(Y * op.matmul(Y), axis=0)
+            cross = 2.0 * np.sum(Y * HX, axis=0)
+        return direct, cross
+
+    # bse_uks.cc:640-702
+    def perturbative_dynamical_screening(self, es, rpa_e_alpha, rpa_e_beta):
+        tda = self.opt.useTDA
+        self.setup_direct_interaction_operator(rpa_e_alpha, rpa_e_beta, 0.0)
+        static, _ = self._expectation(es, self._operator(0, 0, 1, 0), tda)
+        if not tda:
+            static = static + self._expectation(es, self._operator(0, 0, 0, 1), tda)[1]
+        E0 = np.asarray(es["eigenvalues"], dtype=np.float64)
+        dyn = E0.copy()
+        for i in range(len(E0)):
+            for _ in range(self.opt.max_dyn_iter):
+                old = dyn[i]
+                self.setup_direct_interaction_operator(rpa_e_alpha, rpa_e_beta, old)
+                d, _ = self._expectation(es, self._operator(0, 0, 1, 0), tda, state=i)
+                if not tda:
+                    d = d + self._expectation(es, self._operator(0, 0, 0, 1), tda, state=i)[1]
+                dyn[i] = E0[i] + static[i] - d[0]
+                if abs(dyn[i] - old) < self.opt.dyn_tolerance:
+                    break
+        return dyn
+
     def operator_tda(self):
         op = exciton_uks_tda(self.eps_inv, self.M[0], self.M[1], self.Hqp[0], self.Hqp[1])
         op.configure(self.homo[0], self.homo[1], self.opt.rpamin, self.opt.vmin, self.opt.cmax)

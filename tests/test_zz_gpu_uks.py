@@ -188,3 +188,32 @@ def test_what_is_not_on_this_path_is_refused():
     with pytest.raises(Exception, match="unrestricted reference"):
         job.run()  # the restricted driver refuses the unrestricted task
     job.close()
+
+
+@pytest.mark.parametrize("tda", [True, False])
+def test_unrestricted_dynamical_screening_against_the_oracle(tda):
+    """bse.dyn_screen_max_iter > 0 for an unrestricted reference (BSE_UKS::Perturbative_DynamicalScreening,
+    bse_uks.cc:640-702): the spin-summed eps(omega) re-diagonalised per excitation and iteration, expectation values
+    of the unrestricted Hd operator <0,0,1,0> and, without the TDA, the cross term of Hd2 <0,0,0,1>."""
+    c = uks_case()
+    og = uks.GWUKS(methane_mmn(c["Ca"]), methane_mmn(c["Cb"]), c["vxc_a"], c["vxc_b"], c["ea"], c["eb"])
+    og.configure(_gw_options(qp_grid_steps=601, qp_grid_spacing=0.005), c["homo_a"], c["homo_b"])
+    og.calculate_gw_perturbation()
+    og.calculate_hqp()
+    job = make_job(c, "G0W0", tasks="gw,exciton_uks", bse__useTDA=tda, bse__exctotal=3, bse__dyn_screen_max_iter=4,
+                   bse__dyn_screen_tol=1e-6)
+    job.run_uks()
+    es = {"eigenvalues": job.get("BSE_uks_eigenvalues").ravel(), "eigenvectors": job.get("BSE_uks_eigenvectors")}
+    if not tda:
+        es["eigenvectors2"] = job.get("BSE_uks_eigenvectors2")
+    ob = uks.BSEUKS(methane_mmn(c["Ca"]), methane_mmn(c["Cb"]))
+    o = obse.BSEOptions(cmax=16, rpamax=16, rpamin=0, vmin=0, nmax=3, useTDA=tda, homo=4, qpmin=0, qpmax=16,
+                        use_Hqp_offdiag=True, max_dyn_iter=4, dyn_tolerance=1e-6)
+    ob.configure(o, c["homo_a"], c["homo_b"], og.rpa.energies(0), og.rpa.energies(1), og.get_hqp(0), og.get_hqp(1))
+    ref = ob.perturbative_dynamical_screening(es, og.rpa.energies(0), og.rpa.energies(1))
+    got = job.get("BSE_uks_dynamic").ravel()
+    assert got.shape == ref.shape == (3,)
+    assert np.abs(got - ref).max() < 1e-6  # Hartree
+    shift = got - es["eigenvalues"]
+    assert np.all(np.abs(shift) > 1e-7) and np.all(np.abs(shift) < 0.05)  # a correction, and a small one
+    job.close()

@@ -557,6 +557,7 @@ int gwbse_job_run_uks(gwbse_job* job) {
   o["BSE_uks_eigenvalues"] = vec2mat(r.BSE_uks.eigenvalues);
   o["BSE_uks_eigenvectors"] = r.BSE_uks.eigenvectors;
   o["BSE_uks_eigenvectors2"] = r.BSE_uks.eigenvectors2;
+  o["BSE_uks_dynamic"] = vec2mat(r.BSE_uks_dynamic);
   auto& sc = job->out_scalars;
   sc.clear();
   sc["rpamin"] = r.rpamin;

@@ -188,6 +188,7 @@ class GWBSE {
     VectorXd RPA_inputenergies[2], QPpert_energies[2], QPdiag_eigenvalues[2];
     MatrixXd QPdiag_eigenvectors[2], Hqp[2], Sigma_x[2], Sigma_c[2];
     EigenSystem BSE_uks;
+    VectorXd BSE_uks_dynamic;
     Index alpha_size = 0, beta_size = 0, gw_iterations = 0, davidson_iterations = 0, removed_functions = 0;
     double time_fill = 0, time_gw = 0, time_bse = 0;
   };
@@ -481,6 +482,9 @@ class GWBSE {
       res.alpha_size = H.alpha_size();
       res.beta_size = H.beta_size();
       res.davidson_iterations = bse.last_davidson_iterations();
+      if (do_dynamical_screening_bse_)  // gwbse.cc:1207-1210
+        res.BSE_uks_dynamic =
+            bse.Perturbative_DynamicalScreening(res.BSE_uks, res.RPA_inputenergies[0], res.RPA_inputenergies[1]);
       res.time_bse = std::chrono::duration<double>(clock::now() - t0).count();
       log_(" BSE calculation took " + std::to_string(res.time_bse) + " seconds.");
     }

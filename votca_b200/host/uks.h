@@ -607,6 +607,7 @@ typedef BSE_OPERATOR_UKS<0, 0, 0, 1> Hd2UKSOperator;
 typedef BSE_OPERATOR_UKS<1, 0, 0, 0> HqpUKSOperator;
 typedef BSE_OPERATOR_UKS<0, 1, 0, 0> HxUKSOperator;
 typedef BSE_OPERATOR_UKS<0, 0, 1, 0> HdUKSOperator;
+typedef BSE_OPERATOR_UKS<0, 0, 0, 1> Hd2UKSOperator;
 
 class BSE_UKS {
  public:
@@ -628,12 +629,21 @@ class BSE_UKS {
                                          s == 0 ? RPAInputEnergiesAlpha : RPAInputEnergiesBeta);
       Hqp_[s] = opt_.use_Hqp_offdiag ? H : asDiagonal(H.diagonal());
     }
+    SetupDirectInteractionOperator(RPAInputEnergiesAlpha, RPAInputEnergiesBeta, 0.0);
+  }
+
+  // bse_uks.cc:135-157: spin-summed eps(energy), its eigen-decomposition, both tensors rotated into its eigenbasis.
+  // The reference rotates a pristine copy of the tensors each time; here the resident tensors are rotated again -
+  // eps computed from rotated tensors has the rotated eigenvectors, so the composed rotation and with it the
+  // operator are the same (as in the restricted BSE, bse.h).
+  void SetupDirectInteractionOperator(const VectorXd& RPAInputEnergiesAlpha, const VectorXd& RPAInputEnergiesBeta,
+                                      double energy) {
     RPA_UKS rpa(log_, Mmn_);
-    rpa.configure(homo_alpha, homo_beta, opt_.rpamin, opt_.rpamax);
+    rpa.configure(homo_[0], homo_[1], opt_.rpamin, opt_.rpamax);
     rpa.setRPAInputEnergies(RPAInputEnergiesAlpha, RPAInputEnergiesBeta);
     const Device& da = Mmn_.alpha.device();
     const Index n = Mmn_.alpha.auxsize();
-    double* eps = rpa.calculate_epsilon_r_dev(0.0);
+    double* eps = rpa.calculate_epsilon_r_dev(energy);
     Device::Buffer U = da.alloc(static_cast<size_t>(n * n));
     da.check(gwbse_d2d(da.ctx(), U.get(), eps, static_cast<size_t>(n * n)));
     VectorXd ev(n);
@@ -646,6 +656,74 @@ class BSE_UKS {
     epsilon_0_inv_ = VectorXd::Zero(n);
     for (Index i = 0; i < n; ++i)
       if (ev(i) > 1e-8) epsilon_0_inv_(i) = 1.0 / ev(i);
+  }
+
+  struct ExpectationValues {
+    VectorXd direct_term, cross_term;
+  };
+  // bse_uks.cc:171-216 (state < 0: every state)
+  template <typename OPERATOR>
+  ExpectationValues ExpectationValue_Operator(const EigenSystem& es, const OPERATOR& H, Index state = -1) const {
+    auto cols = [&](const MatrixXd& M) {
+      if (state < 0) return M;
+      MatrixXd c(M.rows(), 1);
+      for (Index i = 0; i < M.rows(); ++i) c(i, 0) = M(i, state);
+      return c;
+    };
+    auto exp_value = [](const MatrixXd& a, const MatrixXd& b) {
+      VectorXd r(a.cols(), 0.0);
+      for (Index j = 0; j < a.cols(); ++j)
+        for (Index i = 0; i < a.rows(); ++i) r(j) += a(i, j) * b(i, j);
+      return r;
+    };
+    ExpectationValues ev;
+    const MatrixXd X = cols(es.eigenvectors);
+    const MatrixXd HX = H.matmul(X);
+    ev.direct_term = exp_value(X, HX);
+    if (!opt_.useTDA) {
+      const MatrixXd Y = cols(es.eigenvectors2);
+      const VectorXd yy = exp_value(Y, H.matmul(Y)), yx = exp_value(Y, HX);
+      ev.cross_term = VectorXd(yx.size());
+      for (Index j = 0; j < yx.size(); ++j) {
+        ev.direct_term(j) += yy(j);
+        ev.cross_term(j) = 2.0 * yx(j);
+      }
+    }
+    return ev;
+  }
+
+  // bse_uks.cc:640-702: E_dyn = E + <Hd(0)> - <Hd(E_dyn)>, iterated per excitation (full BSE: plus the Hd2 cross terms)
+  VectorXd Perturbative_DynamicalScreening(const EigenSystem& es, const VectorXd& RPAInputEnergiesAlpha,
+                                           const VectorXd& RPAInputEnergiesBeta) {
+    auto contribution = [&](Index state) {
+      HdUKSOperator Hd(epsilon_0_inv_, Mmn_, Hqp_[0], Hqp_[1]);
+      Hd.configure({homo_[0], homo_[1], opt_.rpamin, opt_.qpmin, opt_.vmin, opt_.cmax});
+      VectorXd c = ExpectationValue_Operator(es, Hd, state).direct_term;
+      if (!opt_.useTDA) {
+        Hd2UKSOperator Hd2(epsilon_0_inv_, Mmn_, Hqp_[0], Hqp_[1]);
+        Hd2.configure({homo_[0], homo_[1], opt_.rpamin, opt_.qpmin, opt_.vmin, opt_.cmax});
+        const VectorXd x = ExpectationValue_Operator(es, Hd2, state).cross_term;
+        for (Index j = 0; j < c.size(); ++j) c(j) += x(j);
+      }
+      return c;
+    };
+    SetupDirectInteractionOperator(RPAInputEnergiesAlpha, RPAInputEnergiesBeta, 0.0);
+    const VectorXd Hd_static = contribution(-1);
+    VectorXd dyn = es.eigenvalues;
+    for (Index i = 0; i < dyn.size(); ++i) {
+      log_("Dynamical Screening UKS BSE, Excitation " + std::to_string(i) + " static " +
+           std::to_string(es.eigenvalues(i)));
+      for (Index iter = 0; iter < opt_.max_dyn_iter; ++iter) {
+        const double old_energy = dyn(i);
+        SetupDirectInteractionOperator(RPAInputEnergiesAlpha, RPAInputEnergiesBeta, old_energy);
+        const VectorXd Hd_dyn = contribution(i);
+        dyn(i) = es.eigenvalues(i) + Hd_static(i) - Hd_dyn(0);
+        log_("Dynamical Screening UKS BSE, excitation " + std::to_string(i) + " iteration " + std::to_string(iter) +
+             " dynamic " + std::to_string(dyn(i)));
+        if (std::abs(dyn(i) - old_energy) < opt_.dyn_tolerance) break;
+      }
+    }
+    return dyn;
   }
 
   ExcitonUKSOperator_TDA getExcitonOperator_TDA() const {
