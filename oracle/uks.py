@@ -551,6 +551,26 @@ class BSEUKS:
                     break
         return dyn
 
+    # Orbitals::CalcCoupledTransition_Dipoles(ExcitonUKS), orbitals.cc:798-877; Oscillatorstrengths :645-674
+    def transition_dipoles(self, es, dipole_ao, mos_alpha, mos_beta):
+        o = self.opt
+        out = []
+        inter = []
+        for C, homo in ((mos_alpha, self.homo[0]), (mos_beta, self.homo[1])):
+            occ, virt = C[:, o.vmin:homo + 1], C[:, homo + 1:o.cmax + 1]
+            inter.append([virt.T @ dipole_ao[k] @ occ for k in range(3)])       # ctotal x vtotal
+        na = inter[0][0].size
+        for s in range(es["eigenvectors"].shape[1]):
+            c = es["eigenvectors"][:, s].copy()
+            if not o.useTDA:
+                c = c + es["eigenvectors2"][:, s]
+            ma = c[:na].reshape(inter[0][0].shape, order="F")
+            mb = c[na:].reshape(inter[1][0].shape, order="F")
+            out.append(-np.array([np.sum(ma * inter[0][k]) + np.sum(mb * inter[1][k]) for k in range(3)]))
+        d = np.array(out)
+        f = np.sum(d * d, axis=1) * 2.0 / 3.0 * np.asarray(es["eigenvalues"])[:len(d)]
+        return d, f
+
     def operator_tda(self):
         op = exciton_uks_tda(self.eps_inv, self.M[0], self.M[1], self.Hqp[0], self.Hqp[1])
         op.configure(self.homo[0], self.homo[1], self.opt.rpamin, self.opt.vmin, self.opt.cmax)

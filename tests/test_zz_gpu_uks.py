@@ -217,3 +217,30 @@ def test_unrestricted_dynamical_screening_against_the_oracle(tda):
     shift = got - es["eigenvalues"]
     assert np.all(np.abs(shift) > 1e-7) and np.all(np.abs(shift) < 0.05)  # a correction, and a small one
     job.close()
+
+
+@pytest.mark.parametrize("tda", [True, False])
+def test_unrestricted_transition_dipoles_and_oscillator_strengths(tda):
+    """Orbitals::CalcCoupledTransition_Dipoles / Oscillatorstrengths for combined UKS excitons (orbitals.cc:798-877,
+    645-674): interlevel dipoles of both spin channels formed on the device from the AO dipole matrices, no sqrt(2);
+    oscillator strengths within 1e-5 of the oracle."""
+    from oracle import integrals
+    from tests.helpers import methane_integrals
+    c = uks_case()
+    dip = integrals.dipole(methane_integrals()["basis"])
+    job = make_job(c, "G0W0", tasks="gw,exciton_uks", bse__useTDA=tda, bse__exctotal=4)
+    for k, name in enumerate(("ao_dipole_x", "ao_dipole_y", "ao_dipole_z")):
+        job.set_array(name, dip[k])
+    job.run_uks()
+    es = {"eigenvalues": job.get("BSE_uks_eigenvalues").ravel(), "eigenvectors": job.get("BSE_uks_eigenvectors")}
+    if not tda:
+        es["eigenvectors2"] = job.get("BSE_uks_eigenvectors2")
+    ob = uks.BSEUKS(methane_mmn(c["Ca"]), methane_mmn(c["Cb"]))
+    ob.opt = obse.BSEOptions(cmax=16, rpamax=16, rpamin=0, vmin=0, nmax=4, useTDA=tda, homo=4, qpmin=0, qpmax=16)
+    ob.homo = (c["homo_a"], c["homo_b"])
+    d, f = ob.transition_dipoles(es, dip, c["Ca"], c["Cb"])
+    assert np.abs(job.get("uks_transition_dipoles").T - d).max() < 1e-8
+    assert np.abs(job.get("uks_oscillator_strengths").ravel() - f).max() < 1e-8
+    assert np.abs(f).max() > 1e-4  # (the toy doublet has excitations of negative energy: f carries their sign)
+    assert "TrDipole length gauge[e*bohr]" in job.log() and "XU1" in job.log()
+    job.close()

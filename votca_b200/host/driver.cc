@@ -280,7 +280,10 @@ int gwbse_job_run(gwbse_job* job) {
     in.integrals = &job->ints;
   }
   std::vector<MatrixXd> dip, ao_dip;
-  if (dft_basis && !job->in.count("dipole_x")) {  // AO dipoles from the device, interlevel dipoles formed by GWBSE
+  if (job->in.count("ao_dipole_x") && job->in.count("ao_dipole_y") && job->in.count("ao_dipole_z")) {
+    ao_dip = {job->in["ao_dipole_x"], job->in["ao_dipole_y"], job->in["ao_dipole_z"]};
+    in.ao_dipoles = &ao_dip;
+  } else if (dft_basis && !job->in.count("dipole_x")) {  // AO dipoles from the device, interlevel dipoles formed by GWBSE
     ao_dip = dft_basis->Dipoles();
     in.ao_dipoles = &ao_dip;
   }
@@ -539,6 +542,16 @@ int gwbse_job_run_uks(gwbse_job* job) {
     job->ints.V = &need("aux_coulomb");
     in.integrals = &job->ints;
   }
+  // AO dipole matrices <mu|r_k|nu>: from the dft basis on the device, or the arrays ao_dipole_x / _y / _z
+  std::vector<MatrixXd> ao_dip;
+  if (job->in.count("ao_dipole_x") && job->in.count("ao_dipole_y") && job->in.count("ao_dipole_z")) {
+    ao_dip = {job->in["ao_dipole_x"], job->in["ao_dipole_y"], job->in["ao_dipole_z"]};
+    in.ao_dipoles = &ao_dip;
+  } else if (job->basis_data[0]) {
+    if (!job->dev_basis[0]) job->dev_basis[0] = std::make_unique<DeviceAOBasis>(*job->dev, *job->basis_data[0]);
+    ao_dip = job->dev_basis[0]->Dipoles();
+    in.ao_dipoles = &ao_dip;
+  }
   GWBSE gwbse(*job->dev, job->log);
   gwbse.Initialize(job->options, in);
   GWBSE::ResultsUKS r = gwbse.EvaluateUKS();
@@ -558,6 +571,11 @@ int gwbse_job_run_uks(gwbse_job* job) {
   o["BSE_uks_eigenvectors"] = r.BSE_uks.eigenvectors;
   o["BSE_uks_eigenvectors2"] = r.BSE_uks.eigenvectors2;
   o["BSE_uks_dynamic"] = vec2mat(r.BSE_uks_dynamic);
+  o["uks_oscillator_strengths"] = vec2mat(r.oscillator_strengths);
+  MatrixXd utd(3, static_cast<Index>(r.transition_dipoles.size()));
+  for (size_t st = 0; st < r.transition_dipoles.size(); ++st)
+    for (Index i = 0; i < 3; ++i) utd(i, st) = r.transition_dipoles[st](i);
+  o["uks_transition_dipoles"] = utd;
   auto& sc = job->out_scalars;
   sc.clear();
   sc["rpamin"] = r.rpamin;

@@ -189,6 +189,8 @@ class GWBSE {
     MatrixXd QPdiag_eigenvectors[2], Hqp[2], Sigma_x[2], Sigma_c[2];
     EigenSystem BSE_uks;
     VectorXd BSE_uks_dynamic;
+    std::vector<VectorXd> transition_dipoles;  // Orbitals::CalcCoupledTransition_Dipoles(ExcitonUKS)
+    VectorXd oscillator_strengths;            // Orbitals::Oscillatorstrengths(ExcitonUKS)
     Index alpha_size = 0, beta_size = 0, gw_iterations = 0, davidson_iterations = 0, removed_functions = 0;
     double time_fill = 0, time_gw = 0, time_bse = 0;
   };
@@ -482,6 +484,44 @@ class GWBSE {
       res.alpha_size = H.alpha_size();
       res.beta_size = H.beta_size();
       res.davidson_iterations = bse.last_davidson_iterations();
+      if (in_.ao_dipoles) {
+        // Orbitals::CalcCoupledTransition_Dipoles(ExcitonUKS) (orbitals.cc:798-877): d = -(sum (X+Y)_alpha o D_alpha
+        // + sum (X+Y)_beta o D_beta), no sqrt(2): both spin sectors are explicit components of the eigenvector;
+        // f = 2/3 Omega |d|^2 (orbitals.cc:645-674)
+        const std::vector<MatrixXd> Da = CalcFreeTransition_Dipoles(*in_.ao_dipoles, *in_.mos, in_.homo),
+                                    Db = CalcFreeTransition_Dipoles(*in_.ao_dipoles, *in_.mos_beta, in_.homo_beta);
+        const Index nst = res.BSE_uks.eigenvalues.size(), na = res.alpha_size;
+        res.oscillator_strengths = VectorXd(nst);
+        log_(bseopt_.useTDA ? "  ====== combined UKS TDA exciton energies (eV) ====== "
+                            : "  ====== combined UKS full-BSE exciton energies (eV) ====== ");
+        for (Index s = 0; s < nst; ++s) {
+          VectorXd d(3, 0.0);
+          for (int k = 0; k < 3; ++k) {
+            double acc = 0.0;
+            for (int sp = 0; sp < 2; ++sp) {
+              const MatrixXd& D = (sp == 0 ? Da : Db)[static_cast<size_t>(k)];  // ct x vt, index c + ct * v
+              const Index off = sp == 0 ? 0 : na;
+              for (Index j = 0; j < D.cols(); ++j)
+                for (Index i = 0; i < D.rows(); ++i) {
+                  double c = res.BSE_uks.eigenvectors(off + j * D.rows() + i, s);
+                  if (!bseopt_.useTDA) c += res.BSE_uks.eigenvectors2(off + j * D.rows() + i, s);
+                  acc += c * D(i, j);
+                }
+            }
+            d(k) = -acc;
+          }
+          res.transition_dipoles.push_back(d);
+          const double d2 = d(0) * d(0) + d(1) * d(1) + d(2) * d(2);
+          res.oscillator_strengths(s) = d2 * 2.0 / 3.0 * res.BSE_uks.eigenvalues(s);
+          char buf[200];
+          std::snprintf(buf, sizeof(buf), "  XU%-4ld %+1.6f", (long)(s + 1), res.BSE_uks.eigenvalues(s) * 27.21138602);
+          log_(buf);
+          std::snprintf(buf, sizeof(buf),
+                        "           TrDipole length gauge[e*bohr]  dx = %+1.4f dy = %+1.4f dz = %+1.4f |d|^2 = %+1.4f f = %+1.4f",
+                        d(0), d(1), d(2), d2, res.oscillator_strengths(s));
+          log_(buf);
+        }
+      }
       if (do_dynamical_screening_bse_)  // gwbse.cc:1207-1210
         res.BSE_uks_dynamic =
             bse.Perturbative_DynamicalScreening(res.BSE_uks, res.RPA_inputenergies[0], res.RPA_inputenergies[1]);
@@ -733,8 +773,12 @@ class GWBSE {
   // Orbitals::CalcFreeTransition_Dipoles (orbitals.cc:742-760): interlevel[k] = empty^T * D_k * occ with
   // empty = MOs(:, bse_cmin..bse_cmax), occ = MOs(:, bse_vmin..homo); two small GEMMs per direction on the device
   std::vector<MatrixXd> CalcFreeTransition_Dipoles(const std::vector<MatrixXd>& ao_dipoles) const {
-    const MatrixXd& C = *in_.mos;
-    const Index N = C.rows(), vt = bseopt_.homo - bseopt_.vmin + 1, ct = bseopt_.cmax - bseopt_.homo;
+    return CalcFreeTransition_Dipoles(ao_dipoles, *in_.mos, bseopt_.homo);
+  }
+  // the same for one spin channel of an unrestricted reference (orbitals.cc:826-846): the channel's MOs and homo
+  std::vector<MatrixXd> CalcFreeTransition_Dipoles(const std::vector<MatrixXd>& ao_dipoles, const MatrixXd& C,
+                                                   Index homo) const {
+    const Index N = C.rows(), vt = homo - bseopt_.vmin + 1, ct = bseopt_.cmax - homo;
     if (ao_dipoles.size() != 3) throw std::runtime_error("three AO dipole matrices expected");
     Device::Buffer Cd = dev_.upload(C), T = dev_.alloc(static_cast<size_t>(N * vt)),
                    I = dev_.alloc(static_cast<size_t>(std::max<Index>(ct * vt, 1)));
@@ -743,7 +787,7 @@ class GWBSE {
       if (D.rows() != N || D.cols() != N) throw std::runtime_error("AO dipole matrix does not match the basis size");
       Device::Buffer Dd = dev_.upload(D);
       dev_.gemm('N', 'N', N, vt, N, 1.0, Dd.get(), N, Cd.get() + bseopt_.vmin * N, N, 0.0, T.get(), N);
-      dev_.gemm('T', 'N', ct, vt, N, 1.0, Cd.get() + (bseopt_.homo + 1) * N, N, T.get(), N, 0.0, I.get(), ct);
+      dev_.gemm('T', 'N', ct, vt, N, 1.0, Cd.get() + (homo + 1) * N, N, T.get(), N, 0.0, I.get(), ct);
       out.push_back(dev_.download(I.get(), ct, vt));
     }
     return out;
