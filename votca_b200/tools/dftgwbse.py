@@ -90,7 +90,8 @@ def main(argv=None):
     if unrestricted:
         np.savez(job_name + "_uks_results.npz", **{k: job.get(k) for k in (
             "QPpert_energies_alpha", "QPpert_energies_beta", "RPA_inputenergies_alpha", "RPA_inputenergies_beta",
-            "Hqp_alpha", "Hqp_beta", "BSE_uks_eigenvalues", "BSE_uks_eigenvectors")})
+            "Hqp_alpha", "Hqp_beta", "BSE_uks_eigenvalues", "BSE_uks_eigenvectors", "BSE_uks_eigenvectors2",
+            "BSE_uks_dynamic", "uks_transition_dipoles", "uks_oscillator_strengths")})
         print(f"Saving data to {job_name}_uks_results.npz")
     else:
         print(f"Saving data to {archive}")
