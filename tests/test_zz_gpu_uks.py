@@ -244,3 +244,40 @@ def test_unrestricted_transition_dipoles_and_oscillator_strengths(tda):
     assert np.abs(f).max() > 1e-4  # (the toy doublet has excitations of negative energy: f carries their sign)
     assert "TrDipole length gauge[e*bohr]" in job.log() and "XU1" in job.log()
     job.close()
+
+
+def test_unrestricted_summary_xml(tmp_path):
+    """<job>_summary.xml of an unrestricted run as GWBSE::addoutput writes it (gwbse.cc:591-633, 696-736): dft_alpha /
+    dft_beta level tables and the exciton_uks levels with omega, f and Trdipole, in eV."""
+    import xml.etree.ElementTree as ET
+    from oracle import integrals
+    from tests.helpers import methane_integrals
+    c = uks_case()
+    dip = integrals.dipole(methane_integrals()["basis"])
+    job = make_job(c, "G0W0", tasks="gw,exciton_uks", bse__exctotal=3)
+    for k, name in enumerate(("ao_dipole_x", "ao_dipole_y", "ao_dipole_z")):
+        job.set_array(name, dip[k])
+    out = tmp_path / "uks_summary.xml"
+    job.set_summary_output(str(out))
+    job.run_uks()
+    g = ET.parse(out).getroot().find("GWBSE")
+    assert g.get("units") == "eV"
+    h2e = 27.21138602
+    for tag, homo in (("alpha", c["homo_a"]), ("beta", c["homo_b"])):
+        t = g.find("dft_" + tag)
+        assert int(t.get("HOMO")) == homo and int(t.get("LUMO")) == homo + 1
+        lv = t.findall("level")
+        assert len(lv) == 17 and [int(x.get("number")) for x in lv] == list(range(17))
+        gw = np.array([float(x.find("gw_energy").text) for x in lv])
+        assert np.abs(gw - job.get("QPpert_energies_" + tag) * h2e).max() < 1e-6
+        qp = np.array([float(x.find("qp_energy").text) for x in lv])
+        assert np.abs(qp - job.get("QPdiag_eigenvalues_" + tag).ravel() * h2e).max() < 1e-6
+    ex = g.find("exciton_uks").findall("level")
+    assert [int(x.get("number")) for x in ex] == [1, 2, 3]
+    om = np.array([float(x.find("omega").text) for x in ex])
+    assert np.abs(om - job.get("BSE_uks_eigenvalues").ravel() * h2e).max() < 1e-6
+    f = np.array([float(x.find("f").text) for x in ex])
+    assert np.abs(f - job.get("uks_oscillator_strengths").ravel()).max() < 1e-6
+    td = ex[0].find("Trdipole")
+    assert td.get("unit") == "e*bohr" and td.get("gauge") == "length" and len(td.text.split()) == 3
+    job.close()

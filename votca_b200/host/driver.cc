@@ -555,6 +555,9 @@ int gwbse_job_run_uks(gwbse_job* job) {
   GWBSE gwbse(*job->dev, job->log);
   gwbse.Initialize(job->options, in);
   GWBSE::ResultsUKS r = gwbse.EvaluateUKS();
+  if (!job->summary_path.empty() && job->dev->rank() == 0)
+    gwbse.WriteSummaryXML(r, job->summary_path,
+                          job->scalars.count("dft_total_energy") ? job->scalars["dft_total_energy"] : 0.0);
   auto& o = job->out;
   o.clear();
   for (int s = 0; s < 2; ++s) {

@@ -850,6 +850,56 @@ class GWBSE {
     f << "\t</GWBSE>\n</output>\n";
   }
 
+  // the same file for an unrestricted reference (gwbse.cc:591-633 dft_alpha / dft_beta, :696-736 exciton_uks)
+  void WriteSummaryXML(const ResultsUKS& r, const std::string& filename, double dft_total_energy) const {
+    const double hrt2ev = 27.21138602;
+    auto ev = [&](double x) {
+      char b[48];
+      std::snprintf(b, sizeof(b), "%+1.6f ", x * hrt2ev);
+      return std::string(b);
+    };
+    std::ofstream f(filename);
+    if (!f) throw std::runtime_error("cannot write summary file " + filename);
+    f << "<output>\n";
+    if (do_gw_) {
+      f << "\t<GWBSE DFTEnergy=\"" << ev(dft_total_energy) << "\" units=\"eV\">\n";
+      for (int s = 0; s < 2; ++s) {
+        const Index homo = s == 0 ? in_.homo : in_.homo_beta;
+        const VectorXd& e = s == 0 ? *in_.mo_energies : *in_.mo_energies_beta;
+        const char* tag = s == 0 ? "dft_alpha" : "dft_beta";
+        f << "\t\t<" << tag << " HOMO=\"" << homo << "\" LUMO=\"" << homo + 1 << "\">\n";
+        for (Index state = 0; state < gwopt_.qpmax + 1 - gwopt_.qpmin; ++state) {
+          f << "\t\t\t<level number=\"" << state + gwopt_.qpmin << "\">\n";
+          f << "\t\t\t\t<dft_energy>" << ev(e(state + gwopt_.qpmin)) << "</dft_energy>\n";
+          f << "\t\t\t\t<gw_energy>" << ev(r.QPpert_energies[s](state)) << "</gw_energy>\n";
+          f << "\t\t\t\t<qp_energy>" << ev(r.QPdiag_eigenvalues[s](state)) << "</qp_energy>\n";
+          f << "\t\t\t</level>\n";
+        }
+        f << "\t\t</" << tag << ">\n";
+      }
+    } else {
+      f << "\t<GWBSE>\n";
+    }
+    if (do_bse_exciton_uks_) {
+      f << "\t\t<exciton_uks>\n";
+      for (Index state = 0; state < std::min<Index>(bseopt_.nmax, r.BSE_uks.eigenvalues.size()); ++state) {
+        f << "\t\t\t<level number=\"" << state + 1 << "\">\n";
+        f << "\t\t\t\t<omega>" << ev(r.BSE_uks.eigenvalues(state)) << "</omega>\n";
+        if (static_cast<size_t>(state) < r.transition_dipoles.size() && state < r.oscillator_strengths.size()) {
+          const VectorXd& d = r.transition_dipoles[static_cast<size_t>(state)];
+          char b[96];
+          std::snprintf(b, sizeof(b), "%+1.6f ", r.oscillator_strengths(state));
+          f << "\t\t\t\t<f>" << b << "</f>\n";
+          std::snprintf(b, sizeof(b), "%+1.4f %+1.4f %+1.4f", d(0), d(1), d(2));
+          f << "\t\t\t\t<Trdipole gauge=\"length\" unit=\"e*bohr\">" << b << "</Trdipole>\n";
+        }
+        f << "\t\t\t</level>\n";
+      }
+      f << "\t\t</exciton_uks>\n";
+    }
+    f << "\t</GWBSE>\n</output>\n";
+  }
+
   // The GW-BSE part of Orbitals::WriteToCpt (orbitals.cc:990-1063): same group (/QMdata), names and HDF5 types for
   // everything this stage reads or produces, and the scalar / empty members of an Orbitals object that has no
   // unrestricted, embedding or localised-orbital data (defaults of orbitals.h).  NOT written: the compound tables of

@@ -81,6 +81,7 @@ def main(argv=None):
             job.set_array(name, np.asarray(d[name], dtype=np.float64))
     archive, summary = job_name + ".orb", job_name + "_summary.xml"
     if unrestricted:
+        job.set_summary_output(summary)
         job.run_uks()
     else:
         job.set_orb_output(archive)
@@ -93,6 +94,7 @@ def main(argv=None):
             "Hqp_alpha", "Hqp_beta", "BSE_uks_eigenvalues", "BSE_uks_eigenvectors", "BSE_uks_eigenvectors2",
             "BSE_uks_dynamic", "uks_transition_dipoles", "uks_oscillator_strengths")})
         print(f"Saving data to {job_name}_uks_results.npz")
+        print(f"Writing output to {summary}")
     else:
         print(f"Saving data to {archive}")
         print(f"Writing output to {summary}")
