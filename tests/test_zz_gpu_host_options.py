@@ -195,7 +195,13 @@ def test_fragment_populations(golden, methane, tda, tmp_path):
         if tda:
             assert np.abs(H.sum(axis=0) - 1.0).max() < 1e-8 and np.abs(E.sum(axis=0) + 1.0).max() < 1e-8
     assert abs(Gs.sum()) < 1e-8  # neutral molecule
-    assert "Fragment    1 -- hole:" in job.log()
+    log = job.log()
+    assert "Fragment    1 -- hole:" in log
+    # the per-state report of BSE::Analyze_singlets / Analyze_triplets (bse.cc:394-490)
+    assert "  ====== singlet energies (eV) ====== " in log and "  ====== triplet energies (eV) ====== " in log
+    e1 = job.get("BSE_singlet_eigenvalues")[0] * 27.21138602
+    assert ("   S =    1 Omega = %+1.12f eV  lamdba = %+3.2f nm <FT> = " % (e1, 1240.0 / e1)) in log
+    assert "   T =    1 Omega = " in log and "<K_x>" in log and "HOMO-" in log and " -> LUMO+" in log
     job.close()
 
 

@@ -618,8 +618,9 @@ class GWBSE {
         res.triplet_davidson_iterations = bse.last_davidson_iterations();
         res.triplet_analysis = bse.Analyze_eh_interaction(false, res.BSE_triplet);
         if (!fragments_.empty())
-          FragmentPopulations("triplet", res.BSE_triplet, res.fragment_gs, res.triplet_fragment_hole,
-                              res.triplet_fragment_electron);
+          FragmentPopulations(res.BSE_triplet, res.fragment_gs, res.triplet_fragment_hole, res.triplet_fragment_electron);
+        ReportStates(false, res.BSE_triplet, res.triplet_analysis, res, res.triplet_fragment_hole,
+                     res.triplet_fragment_electron);
       }
       if (do_bse_singlets_) {
         res.BSE_singlet = bse.Solve_singlets();
@@ -636,8 +637,9 @@ class GWBSE {
         }
         res.singlet_analysis = bse.Analyze_eh_interaction(true, res.BSE_singlet);
         if (!fragments_.empty())
-          FragmentPopulations("singlet", res.BSE_singlet, res.fragment_gs, res.singlet_fragment_hole,
-                              res.singlet_fragment_electron);
+          FragmentPopulations(res.BSE_singlet, res.fragment_gs, res.singlet_fragment_hole, res.singlet_fragment_electron);
+        ReportStates(true, res.BSE_singlet, res.singlet_analysis, res, res.singlet_fragment_hole,
+                     res.singlet_fragment_electron);
       }
       if (do_dynamical_screening_bse_) {
         if (do_bse_triplets_) res.BSE_triplet_dynamic = bse.Perturbative_DynamicalScreening(res.BSE_triplet, rpa_e);
@@ -650,6 +652,55 @@ class GWBSE {
     }
     log_(" GWBSE calculation finished ");
     return res;
+  }
+
+  // The per-state report of BSE::Analyze_singlets / Analyze_triplets (bse.cc:394-490) with PrintWeights (:378-392) and
+  // printFragInfo (:362-376), line for line
+  void ReportStates(bool singlet, const EigenSystem& es, const BSE::Interaction& act, const Results& res,
+                    const MatrixXd& frag_h, const MatrixXd& frag_e) const {
+    const double hrt2ev = 27.21138602;
+    log_(singlet ? "  ====== singlet energies (eV) ====== " : "  ====== triplet energies (eV) ====== ");
+    const Index vt = bseopt_.homo - bseopt_.vmin + 1, ct = bseopt_.cmax - bseopt_.homo;
+    const bool tda = es.eigenvectors2.size() == 0;
+    char buf[256];
+    for (Index i = 0; i < std::min<Index>(bseopt_.nmax, es.eigenvalues.size()); ++i) {
+      const double e = hrt2ev * es.eigenvalues(i);
+      if (singlet)
+        std::snprintf(buf, sizeof(buf),
+                      "  %2s = %4ld Omega = %+1.12f eV  lamdba = %+3.2f nm <FT> = %+1.4f <K_x> = %+1.4f <K_d> = %+1.4f", "S",
+                      (long)(i + 1), e, 1240.0 / e, hrt2ev * act.qp_contrib(i), hrt2ev * act.exchange_contrib(i),
+                      hrt2ev * act.direct_contrib(i));
+      else
+        std::snprintf(buf, sizeof(buf), "  %2s = %4ld Omega = %+1.12f eV  lamdba = %+3.2f nm <FT> = %+1.4f <K_d> = %+1.4f",
+                      "T", (long)(i + 1), e, 1240.0 / e, hrt2ev * act.qp_contrib(i), hrt2ev * act.direct_contrib(i));
+      log_(buf);
+      if (singlet && static_cast<size_t>(i) < res.transition_dipoles.size() && i < res.oscillator_strengths.size()) {
+        const VectorXd& d = res.transition_dipoles[static_cast<size_t>(i)];
+        std::snprintf(buf, sizeof(buf),
+                      "           TrDipole length gauge[e*bohr]  dx = %+1.4f dy = %+1.4f dz = %+1.4f |d|^2 = %+1.4f f = %+1.4f",
+                      d(0), d(1), d(2), d(0) * d(0) + d(1) * d(1) + d(2) * d(2), res.oscillator_strengths(i));
+        log_(buf);
+      }
+      for (Index v = 0; v < vt; ++v)  // PrintWeights: index ct * v + c (vc2index)
+        for (Index c = 0; c < ct; ++c) {
+          const Index k = v * ct + c;
+          double w = es.eigenvectors(k, i) * es.eigenvectors(k, i);
+          if (!tda) w -= es.eigenvectors2(k, i) * es.eigenvectors2(k, i);
+          if (w > bseopt_.min_print_weight) {
+            std::snprintf(buf, sizeof(buf), "           HOMO-%-3ld -> LUMO+%-3ld  : %3.1f%%",
+                          (long)(bseopt_.homo - (bseopt_.vmin + v)), (long)c, 100.0 * w);
+            log_(buf);
+          }
+        }
+      for (Index f = 0; f < frag_h.rows() && i < frag_h.cols(); ++f) {
+        const double dq = frag_h(f, i) + frag_e(f, i), qeff = dq + res.fragment_gs(f);
+        std::snprintf(buf, sizeof(buf),
+                      "           Fragment %4d -- hole: %5.1f%%  electron: %5.1f%%  dQ: %+5.2f  Qeff: %+5.2f", (int)f,
+                      100.0 * frag_h(f, i), -100.0 * frag_e(f, i), dq, qeff);
+        log_(buf);
+      }
+      log_(singlet ? "" : "   ");
+    }
   }
 
   // GWBSE::CountCoreLevels (gwbse.cc:46-58): half the core electrons of share/xtp/ecps/corelevels.xml
@@ -676,8 +727,8 @@ class GWBSE {
   // T = S^1/2 C, the electrons an AO density C_a K C_b^T puts on basis function mu are sum_kl T[mu,k] K[k,l] T[mu,l],
   // and K = A A^T (CalcAuxMat_vv) or A^T A (CalcAuxMat_cc) makes that a row-wise sum of squares of T_v A or T_c A^T.
   // S^1/2 C (eigensolver + two GEMMs) and the per-state products run on the device; the N x N densities are never
-  // formed.  Logs the reference's per-fragment line (BSE::printFragInfo, bse.cc:362-376).
-  void FragmentPopulations(const std::string& label, const EigenSystem& es, VectorXd& gs, MatrixXd& H, MatrixXd& E) {
+  // formed.
+  void FragmentPopulations(const EigenSystem& es, VectorXd& gs, MatrixXd& H, MatrixXd& E) {
     if (!in_.ao_overlap || !in_.basis_atom || !in_.nuclear_charges)
       throw std::runtime_error(
           "bse.fragments needs the AO overlap of the dft basis (or the basis itself), the atom of every basis "
@@ -760,12 +811,6 @@ class GWBSE {
       for (Index f = 0; f < nfrag; ++f) {
         H(f, s) = per_fragment(atom_h, f);
         E(f, s) = per_fragment(atom_e, f);
-        const double dq = H(f, s) + E(f, s), qeff = dq + gs(f);
-        char buf[200];
-        std::snprintf(buf, sizeof(buf),
-                      "           %s %ld Fragment %4d -- hole: %5.1f%%  electron: %5.1f%%  dQ: %+5.2f  Qeff: %+5.2f",
-                      label.c_str(), (long)(s + 1), (int)f, 100.0 * H(f, s), -100.0 * E(f, s), dq, qeff);
-        log_(buf);
       }
     }
   }
