@@ -158,6 +158,12 @@ def test_sigma_plot(golden, methane, tmp_path):
     assert all(tok[0] in "+-" and len(tok.split(".")[1]) == 6 for tok in lines[1].split("\t"))  # "%+1.6f"
     assert np.abs(got - table).max() < 2e-6
     assert np.abs(g.get_gwa_results() - job.get("QPpert_energies")).max() < 1e-6
+    # GW::PrintGWA_Energies (gw.cc:80-111)
+    log = job.log()
+    assert "  ====== Perturbative quasiparticle energies (Hartree) ====== " in log and "   DeltaHLGap = " in log
+    qp = job.get("QPpert_energies")
+    assert ("  HOMO  =    4 DFT = %+1.4f VXC = " % golden["inline/gw_mo_eigenvalues"][4]) in log
+    assert ("GWA = %+1.4f" % qp[4]) in log and "  LUMO  =    5 DFT = " in log and "  Level =    0 DFT = " in log
     job.close()
 
 

@@ -214,6 +214,7 @@ class GW {
   std::pair<VectorXd, MatrixXd> DiagonalizeQPHamiltonian() const {
     MatrixXd H = getHQP();
     VectorXd w = Mmn_.device().sym_eig(H);
+    PrintQP_Energies(w);
     return {w, H};
   }
 
@@ -262,6 +263,38 @@ class GW {
     }
     VectorXd diag = sigma_->CalcCorrelationDiag(frequencies);
     for (Index i = 0; i < qptotal_; ++i) Sigma_c_(i, i) = diag(i);
+    PrintGWA_Energies();
+  }
+
+  // gw.cc:80-111
+  void PrintGWA_Energies() const {
+    const VectorXd gwa_energies = getGWAResults();
+    log_("  ====== Perturbative quasiparticle energies (Hartree) ====== ");
+    char buf[200];
+    if (opt_.homo >= opt_.qpmin && opt_.homo + 1 <= opt_.qpmax) {  // the gap needs both frontier levels in the window
+      std::snprintf(buf, sizeof(buf), "   DeltaHLGap = %+1.6f Hartree", CalcHomoLumoShift(gwa_energies));
+      log_(buf);
+    }
+    for (Index i = 0; i < qptotal_; ++i) {
+      const char* level = (i + opt_.qpmin) == opt_.homo ? "  HOMO " : (i + opt_.qpmin) == opt_.homo + 1 ? "  LUMO " : "  Level";
+      std::snprintf(buf, sizeof(buf), "%s = %4ld DFT = %+1.4f VXC = %+1.4f S-X = %+1.4f S-C = %+1.4f GWA = %+1.4f", level,
+                    (long)(i + opt_.qpmin), dft_energies_(i + opt_.qpmin), vxc_(i, i), Sigma_x_(i, i), Sigma_c_(i, i),
+                    gwa_energies(i));
+      log_(buf);
+    }
+  }
+  // gw.cc:183-208
+  void PrintQP_Energies(const VectorXd& qp_diag_energies) const {
+    const VectorXd gwa_energies = getGWAResults();
+    log_(" Full quasiparticle Hamiltonian  ");
+    log_("  ====== Diagonalized quasiparticle energies (Hartree) ====== ");
+    char buf[160];
+    for (Index i = 0; i < qptotal_; ++i) {
+      const char* level = (i + opt_.qpmin) == opt_.homo ? "  HOMO " : (i + opt_.qpmin) == opt_.homo + 1 ? "  LUMO " : "  Level";
+      std::snprintf(buf, sizeof(buf), "%s = %4ld PQP = %+1.6f DQP = %+1.6f ", level, (long)(i + opt_.qpmin),
+                    gwa_energies(i), qp_diag_energies(i));
+      log_(buf);
+    }
   }
 
   const MatrixXd& getQSGWRotation() const { return qsgw_rotation_; }
