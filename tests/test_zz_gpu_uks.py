@@ -242,7 +242,9 @@ def test_unrestricted_transition_dipoles_and_oscillator_strengths(tda):
     assert np.abs(job.get("uks_transition_dipoles").T - d).max() < 1e-8
     assert np.abs(job.get("uks_oscillator_strengths").ravel() - f).max() < 1e-8
     assert np.abs(f).max() > 1e-4  # (the toy doublet has excitations of negative energy: f carries their sign)
-    assert "TrDipole length gauge[e*bohr]" in job.log() and "XU1" in job.log()
+    log = job.log()
+    assert "TrDipole length gauge[e*bohr]" in log and "XU1" in log
+    assert "           alpha-sector: " in log and "beta-sector: " in log  # BSE_UKS::PrintWeightsUKS
     job.close()
 
 

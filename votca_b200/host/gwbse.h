@@ -520,6 +520,7 @@ class GWBSE {
                         "           TrDipole length gauge[e*bohr]  dx = %+1.4f dy = %+1.4f dz = %+1.4f |d|^2 = %+1.4f f = %+1.4f",
                         d(0), d(1), d(2), d2, res.oscillator_strengths(s));
           log_(buf);
+          PrintWeightsUKS(res, s);
         }
       }
       if (do_dynamical_screening_bse_)  // gwbse.cc:1207-1210
@@ -652,6 +653,52 @@ class GWBSE {
     }
     log_(" GWBSE calculation finished ");
     return res;
+  }
+
+  // BSE_UKS::PrintWeightsUKS (bse_uks.cc:520-595): weight of the two spin sectors, then the (at most eight) largest
+  // transitions above bse.print_weight, by magnitude
+  void PrintWeightsUKS(const ResultsUKS& res, Index state) const {
+    struct Contribution {
+      double weight;
+      bool is_alpha;
+      Index v, c;
+    };
+    const Index na = res.alpha_size, nb = res.beta_size;
+    const Index ct[2] = {bseopt_.cmax - in_.homo, bseopt_.cmax - in_.homo_beta};
+    const bool tda = res.BSE_uks.eigenvectors2.size() == 0;
+    auto weight = [&](Index k) {
+      double w = res.BSE_uks.eigenvectors(k, state) * res.BSE_uks.eigenvectors(k, state);
+      if (!tda) w -= res.BSE_uks.eigenvectors2(k, state) * res.BSE_uks.eigenvectors2(k, state);
+      return w;
+    };
+    double sector[2] = {0.0, 0.0};
+    std::vector<Contribution> contributions;
+    for (Index k = 0; k < na + nb; ++k) {
+      const bool a = k < na;
+      const Index i = a ? k : k - na;
+      const double w = weight(k);
+      sector[a ? 0 : 1] += w;
+      if (std::abs(w) > bseopt_.min_print_weight) contributions.push_back({w, a, i / ct[a ? 0 : 1], i % ct[a ? 0 : 1]});
+    }
+    char buf[160];
+    std::snprintf(buf, sizeof(buf), "           alpha-sector: %+6.2f%%   beta-sector: %+6.2f%%", 100.0 * sector[0],
+                  100.0 * sector[1]);
+    log_(buf);
+    std::stable_sort(contributions.begin(), contributions.end(),
+                     [](const Contribution& x, const Contribution& y) { return std::abs(x.weight) > std::abs(y.weight); });
+    const size_t nprint = std::min<size_t>(8, contributions.size());
+    for (size_t i = 0; i < nprint; ++i) {
+      const Contribution& c = contributions[i];
+      const Index homo = c.is_alpha ? in_.homo : in_.homo_beta;
+      std::snprintf(buf, sizeof(buf), "           [%s] HOMO-%-3ld -> LUMO+%-3ld  : %+6.2f%%", c.is_alpha ? "alpha" : "beta ",
+                    (long)(homo - (bseopt_.vmin + c.v)), (long)c.c, 100.0 * c.weight);
+      log_(buf);
+    }
+    if (contributions.size() > nprint) {
+      std::snprintf(buf, sizeof(buf), "           ... %ld more contributions above threshold",
+                    (long)(contributions.size() - nprint));
+      log_(buf);
+    }
   }
 
   // The per-state report of BSE::Analyze_singlets / Analyze_triplets (bse.cc:394-490) with PrintWeights (:378-392) and
