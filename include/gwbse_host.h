@@ -35,7 +35,12 @@ int gwbse_job_load_options_xml(gwbse_job* job, const char* path);
 int gwbse_job_set_scalar(gwbse_job* job, const char* name, double value);
 /* arrays (column-major, copied): "mos" (nbasis x nmo), "mo_energies" (nmo x 1), "vxc" (q x q),
  * "aux_overlap", "aux_coulomb" (naux x naux), "dipole_x|y|z" (ctotal x vtotal interlevel dipoles),
- * "Hqp", "RPA_inputenergies" (BSE-only runs).
+ * "Hqp", "RPA_inputenergies" (BSE-only runs); "ao_dipole_x|y|z" (N x N AO dipole matrices, AODipole::Fill: the
+ * interlevel dipoles are then formed on the device, for both spin channels of an unrestricted reference);
+ * "nuclear_charges" (natoms; ignore_corelevels and bse.fragments), "ao_overlap" (N x N) and "basis_atom_index" (N, the
+ * atom of every basis function) for bse.fragments - the last two come from the dft basis when gwbse_job_set_basis
+ * gave one.  Results of the optional analyses: "fragment_gs", "BSE_singlet|triplet_fragment_hole|electron"
+ * (nfragments x nstates); unrestricted runs: "BSE_uks_dynamic", "uks_transition_dipoles", "uks_oscillator_strengths".
  * "ao3c": naux matrices N x N, rows = N*N, cols = naux; NOT copied, must stay alive until run returns. */
 int gwbse_job_set_array(gwbse_job* job, const char* name, const double* data, long rows, long cols);
 /* AO integral producer callback instead of "ao3c": fill(user, aux_offset, aux_count, out[aux_count*N*N]) */
@@ -65,7 +70,8 @@ int gwbse_job_set_basis(gwbse_job* job, const char* which, int nshell, const int
 int gwbse_job_set_orb_output(gwbse_job* job, const char* path);
 /* GWBSE::addoutput (gwbse.cc:580-738) written as the dftgwbse tool does (tools/dftgwbse.cc:120-128,
  * <job>_summary.xml): DFT / GW / QP level energies, singlet and triplet excitation energies, oscillator strengths
- * and transition dipoles, eV.  The input scalar "dft_total_energy" (Hartree) fills the DFTEnergy attribute.      */
+ * and transition dipoles, eV; gwbse_job_run_uks writes the dft_alpha / dft_beta tables and the exciton_uks levels.
+ * The input scalar "dft_total_energy" (Hartree) fills the DFTEnergy attribute.                                   */
 int gwbse_job_set_summary_output(gwbse_job* job, const char* path);
 /* the kernel-library context of this job (gwbse_b200.h), e.g. for gwbse_gemm_stats / timers */
 void* gwbse_job_ctx(gwbse_job* job);
